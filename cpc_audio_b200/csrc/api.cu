@@ -1,0 +1,227 @@
+// api.cu - the extern "C" surface declared in include/cpc_b200.h, argument validation, GEMM dispatch.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace cpcb200 {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int make_geo(const cpcb200_dims* d, Geo* g) {
+  if (!d) return fail(CPCB200_ERR_NULL, "dims is NULL");
+  if (d->B <= 0 || d->L <= 0 || d->L % 160 != 0) return fail(CPCB200_ERR_BAD_DIMS, "B=%d L=%d (L must be a positive multiple of 160)", d->B, d->L);
+  if (d->H % 64 != 0 || d->H <= 0 || d->H > 512) return fail(CPCB200_ERR_BAD_DIMS, "H=%d must be a multiple of 64 in [64,512]", d->H);
+  if (d->Har % 64 != 0 || d->Har <= 0 || d->Har > 512) return fail(CPCB200_ERR_BAD_DIMS, "Har=%d must be a multiple of 64 in [64,512]", d->Har);
+  if (d->nLayers < 1 || d->nLayers > CPCB200_MAX_GRU_LAYERS) return fail(CPCB200_ERR_BAD_DIMS, "nLayers=%d", d->nLayers);
+  if (d->dtype != CPCB200_F32 && d->dtype != CPCB200_BF16) return fail(CPCB200_ERR_UNSUPPORTED, "dtype=%d", d->dtype);
+  g->B = d->B; g->L = d->L; g->H = d->H; g->Har = d->Har; g->K = d->K; g->N = d->N; g->nL = d->nLayers;
+  g->S = d->L / 160;
+  g->W = g->S - d->K;
+  g->bf16 = d->dtype == CPCB200_BF16;
+  int L = d->L;
+  for (int i = 0; i < 5; i++) { L = (L + 2 * kConvP[i] - kConvK[i]) / kConvS[i] + 1; g->Lout[i] = L; }
+  if (g->Lout[4] != g->S) return fail(CPCB200_ERR_BAD_DIMS, "internal: conv stack length %d != S %d", g->Lout[4], g->S);
+  return 0;
+}
+
+static int check_crit(const Geo& g) {
+  if (g.K < 1 || g.W < 1) return fail(CPCB200_ERR_BAD_DIMS, "K=%d leaves no anchor positions (S=%d)", g.K, g.S);
+  if (g.N < 1) return fail(CPCB200_ERR_BAD_DIMS, "N=%d", g.N);
+  return 0;
+}
+
+// implemented in the per-op translation units
+size_t encoder_save_elems(const Geo& g);
+size_t encoder_ws_bytes(const Geo& g, int backward);
+int encoder_fwd(const Geo&, const float*, const cpcb200_encoder_params*, float*, void*, void*, size_t, cudaStream_t);
+int encoder_bwd(const Geo&, const float*, const cpcb200_encoder_params*, const float*, const void*,
+                const cpcb200_encoder_params*, void*, size_t, cudaStream_t);
+size_t gru_save_bytes(const Geo& g);
+size_t gru_ws_bytes(const Geo& g, int backward);
+int gru_fwd(const Geo&, const float*, const float*, const cpcb200_gru_params*, float*, float*, void*, void*, size_t, cudaStream_t);
+int gru_bwd(const Geo&, const float*, const float*, const cpcb200_gru_params*, const float*, const float*, const void*, float*,
+            const cpcb200_gru_params*, void*, size_t, cudaStream_t);
+int sample_ext_idx(const Geo&, const int64_t*, const int64_t*, int32_t*, cudaStream_t);
+size_t criterion_save_bytes(const Geo& g);
+size_t criterion_ws_bytes(const Geo& g, int backward);
+int criterion_fwd(const Geo&, const float*, const float*, const float*, const int*, float*, float*, void*, void*, size_t, cudaStream_t);
+int criterion_bwd(const Geo&, const float*, const float*, const float*, const int*, const float*, const void*, float*, float*,
+                  float*, void*, size_t, cudaStream_t);
+
+int gemm_nt_simt(bool, bool, int, int, int, const RowView&, const void*, const float*, const OutView&, cudaStream_t);
+int gemm_tn_simt(bool, int, int, int, const RowView&, const RowView&, float*, int, int, int, int, cudaStream_t);
+int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C,
+               cudaStream_t st, bool* handled);
+int gemm_tn_tc(int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode, int Ci, int taps,
+               cudaStream_t st, bool* handled);
+
+// Dispatch: the bf16 path takes the tcgen05 kernels whenever the shape fits their tiling, else CUDA cores.
+int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias,
+            const OutView& C, cudaStream_t st) {
+  if (bf16_in) {
+    bool handled = false;
+    CPC_TRY(gemm_nt_tc(out_f32, nb, N, Kd, A, Bm, bias, C, st, &handled));
+    if (handled) return 0;
+  }
+  return gemm_nt_simt(bf16_in, out_f32, nb, N, Kd, A, Bm, bias, C, st);
+}
+int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode,
+            int Ci, int taps, cudaStream_t st) {
+  if (bf16_in) {
+    bool handled = false;
+    CPC_TRY(gemm_tn_tc(nb, N1, N2, A, B, Cacc, ldc, mode, Ci, taps, st, &handled));
+    if (handled) return 0;
+  }
+  return gemm_tn_simt(bf16_in, nb, N1, N2, A, B, Cacc, ldc, mode, Ci, taps, st);
+}
+
+// torch.optim.Adam (non-amsgrad) over a flat bucket: cpc/train.py:335-337
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            size_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace cpcb200
+
+using namespace cpcb200;
+
+#define GEO_OR_RETURN(d, g) \
+  Geo g;                    \
+  CPC_TRY(make_geo(d, &g))
+#define NOT_NULL(p) \
+  if (!(p)) return fail(CPCB200_ERR_NULL, #p " is NULL")
+
+extern "C" {
+
+int cpcb200_version(void) { return CPCB200_VERSION; }
+const char* cpcb200_last_error(void) { return g_err; }
+uint64_t cpcb200_launch_count(void) { return g_launches.load(); }
+
+size_t cpcb200_encoder_save_bytes(const cpcb200_dims* d) {
+  Geo g;
+  if (make_geo(d, &g)) return 0;
+  return encoder_save_elems(g) * (g.bf16 ? 2 : 4) + 256;
+}
+size_t cpcb200_encoder_ws_bytes(const cpcb200_dims* d, int backward) {
+  Geo g;
+  if (make_geo(d, &g)) return 0;
+  return encoder_ws_bytes(g, backward);
+}
+int cpcb200_encoder_fwd(const cpcb200_dims* d, const float* x, const cpcb200_encoder_params* p, float* z, void* save,
+                        void* ws, size_t ws_bytes, void* stream) {
+  GEO_OR_RETURN(d, g);
+  NOT_NULL(x); NOT_NULL(p); NOT_NULL(z); NOT_NULL(save); NOT_NULL(ws);
+  return encoder_fwd(g, x, p, z, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int cpcb200_encoder_bwd(const cpcb200_dims* d, const float* x, const cpcb200_encoder_params* p, const float* dz,
+                        const void* save, const cpcb200_encoder_params* grads, void* ws, size_t ws_bytes, void* stream) {
+  GEO_OR_RETURN(d, g);
+  NOT_NULL(x); NOT_NULL(p); NOT_NULL(dz); NOT_NULL(save); NOT_NULL(grads); NOT_NULL(ws);
+  return encoder_bwd(g, x, p, dz, save, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t cpcb200_gru_save_bytes(const cpcb200_dims* d) {
+  Geo g;
+  if (make_geo(d, &g)) return 0;
+  return gru_save_bytes(g);
+}
+size_t cpcb200_gru_ws_bytes(const cpcb200_dims* d, int backward) {
+  Geo g;
+  if (make_geo(d, &g)) return 0;
+  return gru_ws_bytes(g, backward);
+}
+int cpcb200_gru_fwd(const cpcb200_dims* d, const float* z, const float* h0, const cpcb200_gru_params* p, float* c, float* hT,
+                    void* save, void* ws, size_t ws_bytes, void* stream) {
+  GEO_OR_RETURN(d, g);
+  NOT_NULL(z); NOT_NULL(p); NOT_NULL(c); NOT_NULL(save); NOT_NULL(ws);
+  return gru_fwd(g, z, h0, p, c, hT, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int cpcb200_gru_bwd(const cpcb200_dims* d, const float* z, const float* h0, const cpcb200_gru_params* p, const float* c,
+                    const float* dc, const void* save, float* dz, const cpcb200_gru_params* grads, void* ws, size_t ws_bytes,
+                    void* stream) {
+  GEO_OR_RETURN(d, g);
+  NOT_NULL(z); NOT_NULL(p); NOT_NULL(c); NOT_NULL(dc); NOT_NULL(save); NOT_NULL(dz); NOT_NULL(grads); NOT_NULL(ws);
+  return gru_bwd(g, z, h0, p, c, dc, save, dz, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int cpcb200_sample_ext_idx(const cpcb200_dims* d, const int64_t* batch_idx, const int64_t* seq_idx, int32_t* ext, void* stream) {
+  GEO_OR_RETURN(d, g);
+  CPC_TRY(check_crit(g));
+  NOT_NULL(batch_idx); NOT_NULL(seq_idx); NOT_NULL(ext);
+  return sample_ext_idx(g, batch_idx, seq_idx, ext, static_cast<cudaStream_t>(stream));
+}
+
+size_t cpcb200_criterion_save_bytes(const cpcb200_dims* d) {
+  Geo g;
+  if (make_geo(d, &g) || check_crit(g)) return 0;
+  return criterion_save_bytes(g);
+}
+size_t cpcb200_criterion_ws_bytes(const cpcb200_dims* d, int backward) {
+  Geo g;
+  if (make_geo(d, &g) || check_crit(g)) return 0;
+  return criterion_ws_bytes(g, backward);
+}
+int cpcb200_criterion_fwd(const cpcb200_dims* d, const float* c, const float* z, const float* w_pred, const int32_t* ext,
+                          float* losses, float* acc, void* save, void* ws, size_t ws_bytes, void* stream) {
+  GEO_OR_RETURN(d, g);
+  CPC_TRY(check_crit(g));
+  NOT_NULL(c); NOT_NULL(z); NOT_NULL(w_pred); NOT_NULL(ext); NOT_NULL(losses); NOT_NULL(acc); NOT_NULL(save); NOT_NULL(ws);
+  return criterion_fwd(g, c, z, w_pred, ext, losses, acc, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int cpcb200_criterion_bwd(const cpcb200_dims* d, const float* c, const float* z, const float* w_pred, const int32_t* ext,
+                          const float* dlosses, const void* save, float* dc, float* dz, float* dw_pred, void* ws,
+                          size_t ws_bytes, void* stream) {
+  GEO_OR_RETURN(d, g);
+  CPC_TRY(check_crit(g));
+  NOT_NULL(c); NOT_NULL(z); NOT_NULL(w_pred); NOT_NULL(ext); NOT_NULL(dlosses); NOT_NULL(save); NOT_NULL(dc); NOT_NULL(dz);
+  NOT_NULL(dw_pred); NOT_NULL(ws);
+  return criterion_bwd(g, c, z, w_pred, ext, dlosses, save, dc, dz, dw_pred, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int32_t step, void* stream) {
+  NOT_NULL(param); NOT_NULL(grad); NOT_NULL(exp_avg); NOT_NULL(exp_avg_sq);
+  if (step < 1) return fail(CPCB200_ERR_BAD_DIMS, "adam: step=%d must be >= 1", step);
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                              eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+  CPC_LAUNCHED();
+  return 0;
+}
+
+int cpcb200_test_gemm_nt(int dtype, int M, int N, int Kd, const void* A, const void* B, const float* bias, float* C, void* stream) {
+  NOT_NULL(A); NOT_NULL(B); NOT_NULL(C);
+  RowView a{A, 0, (long long)Kd, M};
+  OutView c{C, 0, (long long)N, M, 0, M, 0};
+  return gemm_nt(dtype == CPCB200_BF16, true, 1, N, Kd, a, B, bias, c, static_cast<cudaStream_t>(stream));
+}
+int cpcb200_test_gemm_tn(int dtype, int M, int N1, int N2, const void* A, const void* B, float* C, void* stream) {
+  NOT_NULL(A); NOT_NULL(B); NOT_NULL(C);
+  RowView a{A, 0, (long long)N1, M};
+  RowView b{B, 0, (long long)N2, M};
+  return gemm_tn(dtype == CPCB200_BF16, 1, N1, N2, a, b, C, N2, STORE_PLAIN, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

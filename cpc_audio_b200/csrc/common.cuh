@@ -1,0 +1,180 @@
+// common.cuh - shared host/device helpers for libcpc_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/cpc_b200.h"
+
+namespace cpcb200 {
+
+// ---- error reporting (thread-local message, negative status) ---------------------------------------------
+extern thread_local char g_err[512];
+extern std::atomic<unsigned long long> g_launches;
+
+int fail(int code, const char* fmt, ...);
+
+#define CPC_CHECK_CUDA(expr)                                                                         \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::cpcb200::fail(CPCB200_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,          \
+                             cudaGetErrorString(_e));                                                \
+  } while (0)
+
+// call after every kernel launch: counts it and surfaces launch-configuration errors without syncing
+#define CPC_LAUNCHED()                                                                               \
+  do {                                                                                               \
+    ::cpcb200::g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+    cudaError_t _e = cudaPeekAtLastError();                                                          \
+    if (_e != cudaSuccess)                                                                           \
+      return ::cpcb200::fail(CPCB200_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,      \
+                             cudaGetErrorString(_e));                                                \
+  } while (0)
+
+#define CPC_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != 0) return _s;      \
+  } while (0)
+
+// ---- geometry of the encoder (cpc/model.py:83-92) --------------------------------------------------------
+constexpr int kConvK[5] = {10, 8, 4, 4, 4};
+constexpr int kConvS[5] = {5, 4, 2, 2, 2};
+constexpr int kConvP[5] = {3, 2, 1, 1, 1};
+constexpr int kPad = 2;  // zero rows stored before and after every window of a padded activation
+
+struct Geo {
+  int B, L, H, Har, K, N, nL, S, W;
+  int Lout[5];  // output length of conv i
+  bool bf16;
+};
+
+int make_geo(const cpcb200_dims* d, Geo* g);
+
+__host__ __device__ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// bump allocator over a caller-provided buffer
+struct Carver {
+  char* base;
+  size_t off = 0, cap;
+  Carver(void* p, size_t c) : base(static_cast<char*>(p)), cap(c) {}
+  template <class T>
+  T* take(size_t n) {
+    size_t bytes = align_up(n * sizeof(T));
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+  void* take_bytes(size_t n) { return take<char>(n); }
+  bool ok() const { return off <= cap; }
+};
+
+// ---- device helpers ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <class T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// load / store NV consecutive elements as fp32 (vectorised where the type allows)
+template <int NV> __device__ __forceinline__ void load_vec(const float* p, float (&v)[NV]) {
+  static_assert(NV % 4 == 0, "");
+#pragma unroll
+  for (int i = 0; i < NV / 4; i++) {
+    float4 t = reinterpret_cast<const float4*>(p)[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+template <int NV> __device__ __forceinline__ void load_vec(const bf16* p, float (&v)[NV]) {
+  static_assert(NV % 4 == 0, "");
+  if constexpr (NV % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < NV / 8; i++) {
+      uint4 t = reinterpret_cast<const uint4*>(p)[i];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int j = 0; j < 4; j++) { float2 f = __bfloat1622float2(h[j]); v[8 * i + 2 * j] = f.x; v[8 * i + 2 * j + 1] = f.y; }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV / 4; i++) {
+      uint2 t = reinterpret_cast<const uint2*>(p)[i];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int j = 0; j < 2; j++) { float2 f = __bfloat1622float2(h[j]); v[4 * i + 2 * j] = f.x; v[4 * i + 2 * j + 1] = f.y; }
+    }
+  }
+}
+template <int NV> __device__ __forceinline__ void store_vec(float* p, const float (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV / 4; i++) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <int NV> __device__ __forceinline__ void store_vec(bf16* p, const float (&v)[NV]) {
+  if constexpr (NV % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < NV / 8; i++) {
+      uint4 t;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+      for (int j = 0; j < 4; j++) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+      reinterpret_cast<uint4*>(p)[i] = t;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV / 4; i++) {
+      uint2 t;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+      for (int j = 0; j < 2; j++) h[j] = __floats2bfloat162_rn(v[4 * i + 2 * j], v[4 * i + 2 * j + 1]);
+      reinterpret_cast<uint2*>(p)[i] = t;
+    }
+  }
+}
+#endif  // __CUDACC__
+
+// ---- GEMM building blocks (gemm_simt.cu / gemm_tc.cu) -----------------------------------------------------
+// Row view: logical row m -> (b = m / rpb, t = m % rpb) -> element offset  b*bs + t*rs ; inner dim contiguous.
+// Rows may overlap (rs < row length): that is how a strided Conv1d over a channel-last activation becomes a
+// plain GEMM without im2col (DESIGN.md "conv as a strided-row view").
+struct RowView {
+  const void* p;
+  long long bs;  // elements between batches
+  long long rs;  // elements between consecutive rows
+  int rpb;       // rows per batch
+};
+struct OutView {
+  void* p;
+  long long bs, rs;
+  int rpb;
+  int t_lo, t_hi;  // only rows with t_lo <= t < t_hi are stored
+  int ldn;         // unused (inner dim contiguous)
+};
+enum StoreMode { STORE_PLAIN = 0, STORE_CONV_W = 1 };
+
+// C[m,n] = sum_k A[m,k] * B[n,k] (+ bias[n]).  A row view (M = nb*rpb rows, inner Kd); B dense (N, Kd) ld=Kd.
+// out_f32: C is fp32, else C has the activation dtype.
+int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias,
+            const OutView& C, cudaStream_t st);
+// Cacc[n1,n2] += sum_m A[m,n1] * B[m,n2]  (fp32 atomics).  mode STORE_CONV_W: n2 = tap*Ci + ci -> Cacc[(n1*Ci + ci)*taps + tap]
+int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc,
+            int mode, int Ci, int taps, cudaStream_t st);
+
+}  // namespace cpcb200

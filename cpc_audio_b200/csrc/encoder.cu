@@ -1,0 +1,534 @@
+// encoder.cu - CPCEncoder forward/backward (reference: cpc/model.py:83-105, ChannelNorm model.py:50-58).
+//
+// Data layout in HBM: every activation is CHANNEL-LAST, (B, kPad + L_i + kPad, H) with kPad zero rows around
+// each window.  A strided Conv1d(k, s, p) over such a tensor is a plain GEMM whose A operand is a view with
+// OVERLAPPING rows: output row t reads the k*H contiguous elements starting at padded row (kPad - p + s*t).
+// No im2col buffer exists anywhere; the transposed conv (dgrad) is s GEMMs over a 2-row overlapping view of
+// the output gradient, the weight gradient is a reduction over positions of the same views.
+//
+// conv0 (C_in = 1, k = 10) is not a GEMM: it is HBM-bound (AI ~ 5 FLOP/B) and runs as one fused CUDA-core
+// kernel conv + ChannelNorm + ReLU, one warp per output frame, channel-last vectorised stores.  Its backward
+// recomputes the conv instead of saving the 268 MB pre-norm tensor.
+#include "common.cuh"
+
+namespace cpcb200 {
+
+int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias,
+            const OutView& C, cudaStream_t st);
+
+namespace {
+
+constexpr float kEps = 1e-5f;  // cpc/model.py:29
+
+// Row ops: one warp per (b, t) row of H channels; lane owns float4 chunks at channel 4*(lane + 32*i), i < I.
+template <int I> struct RowRegs { float v[I][4]; };
+
+template <int I, class T>
+__device__ __forceinline__ void row_load(const T* row, int H, int lane, float (&v)[I][4]) {
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    int c = 4 * (lane + 32 * i);
+    if (c < H) load_vec<4>(row + c, v[i]);
+    else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+  }
+}
+template <int I, class T>
+__device__ __forceinline__ void row_store(T* row, int H, int lane, const float (&v)[I][4]) {
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    int c = 4 * (lane + 32 * i);
+    if (c < H) store_vec<4>(row + c, v[i]);
+  }
+}
+
+// ChannelNorm statistics of one row held across a warp (two-pass, unbiased variance: model.py:52-54)
+template <int I>
+__device__ __forceinline__ void row_stats(const float (&u)[I][4], int H, int lane, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < I; i++)
+    if (4 * (lane + 32 * i) < H) s += (u[i][0] + u[i][1]) + (u[i][2] + u[i][3]);
+  mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < I; i++)
+    if (4 * (lane + 32 * i) < H) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) { float dlt = u[i][j] - mean; q = fmaf(dlt, dlt, q); }
+    }
+  float var = warp_sum(q) / (float)(H - 1);
+  rstd = rsqrtf(var + kEps);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv0 + ChannelNorm + ReLU  (model.py:100).  x (B, L) fp32 -> y0 (B, Lp0, H) T.
+// ---------------------------------------------------------------------------------------------------------
+template <int I, class T>
+__global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const float* __restrict__ gam,
+                                                         const float* __restrict__ bet, T* __restrict__ y, int B, int L,
+                                                         int L0, int H) {
+  extern __shared__ __align__(16) float sm[];
+  float* ws = sm;            // [10][H]  tap-major so that a lane's float4 is conflict-free
+  float* bs = sm + 10 * H;   // bias, gamma, beta: [3][H]
+  for (int i = threadIdx.x; i < 10 * H; i += blockDim.x) { int tap = i / H, c = i - tap * H; ws[i] = w[c * 10 + tap]; }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { bs[i] = bias[i]; bs[H + i] = gam[i]; bs[2 * H + i] = bet[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const long long Lp0 = L0 + 2 * kPad;
+  const long long rows = (long long)B * L0;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const int b = (int)(r / L0), t = (int)(r - (long long)b * L0);
+    const float* xb = x + (long long)b * L;
+    float xs[10];
+    const int s0 = 5 * t - 3;
+#pragma unroll
+    for (int j = 0; j < 10; j++) { int s = s0 + j; xs[j] = (s >= 0 && s < L) ? __ldg(xb + s) : 0.f; }
+    float u[I][4];
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      int c = 4 * (lane + 32 * i);
+      if (c < H) {
+        float4 a = *reinterpret_cast<const float4*>(bs + c);
+        u[i][0] = a.x; u[i][1] = a.y; u[i][2] = a.z; u[i][3] = a.w;
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+          float4 wv = *reinterpret_cast<const float4*>(ws + j * H + c);
+          u[i][0] = fmaf(wv.x, xs[j], u[i][0]); u[i][1] = fmaf(wv.y, xs[j], u[i][1]);
+          u[i][2] = fmaf(wv.z, xs[j], u[i][2]); u[i][3] = fmaf(wv.w, xs[j], u[i][3]);
+        }
+      } else { u[i][0] = u[i][1] = u[i][2] = u[i][3] = 0.f; }
+    }
+    float mean, rstd;
+    row_stats<I>(u, H, lane, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      int c = 4 * (lane + 32 * i);
+      if (c < H) {
+        float4 g4 = *reinterpret_cast<const float4*>(bs + H + c);
+        float4 b4 = *reinterpret_cast<const float4*>(bs + 2 * H + c);
+        float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) u[i][j] = fmaxf(fmaf((u[i][j] - mean) * rstd, g[j], be[j]), 0.f);
+      }
+    }
+    row_store<I>(y + ((long long)b * Lp0 + kPad + t) * H, H, lane, u);
+  }
+}
+
+// conv0 backward: recompute u, ChannelNorm+ReLU backward, accumulate dW0 (H,1,10), db0, dgamma0, dbeta0.
+template <int I, class T>
+__global__ void __launch_bounds__(256) conv0_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const float* __restrict__ gam,
+                                                         const float* __restrict__ bet, const T* __restrict__ dy,
+                                                         float* __restrict__ dw, float* __restrict__ dbias,
+                                                         float* __restrict__ dgam, float* __restrict__ dbet, int B, int L,
+                                                         int L0, int H) {
+  extern __shared__ __align__(16) float sm[];
+  float* ws = sm;                 // [10][H]
+  float* bs = sm + 10 * H;        // [3][H]
+  float* accs = sm + 13 * H;      // [13][H] block accumulators: 10 taps, dbias, dgamma, dbeta
+  for (int i = threadIdx.x; i < 10 * H; i += blockDim.x) { int tap = i / H, c = i - tap * H; ws[i] = w[c * 10 + tap]; }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { bs[i] = bias[i]; bs[H + i] = gam[i]; bs[2 * H + i] = bet[i]; }
+  for (int i = threadIdx.x; i < 13 * H; i += blockDim.x) accs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const long long rows = (long long)B * L0;
+  float aw[I][10][4], ab[I][4], ag[I][4], abe[I][4];
+#pragma unroll
+  for (int i = 0; i < I; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      ab[i][j] = ag[i][j] = abe[i][j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 10; k++) aw[i][k][j] = 0.f;
+    }
+  for (long long r = warp; r < rows; r += nwarps) {
+    const int b = (int)(r / L0), t = (int)(r - (long long)b * L0);
+    const float* xb = x + (long long)b * L;
+    float xs[10];
+    const int s0 = 5 * t - 3;
+#pragma unroll
+    for (int j = 0; j < 10; j++) { int s = s0 + j; xs[j] = (s >= 0 && s < L) ? __ldg(xb + s) : 0.f; }
+    float u[I][4], d[I][4];
+    row_load<I>(dy + r * H, H, lane, d);
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      int c = 4 * (lane + 32 * i);
+      if (c < H) {
+        float4 a = *reinterpret_cast<const float4*>(bs + c);
+        u[i][0] = a.x; u[i][1] = a.y; u[i][2] = a.z; u[i][3] = a.w;
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+          float4 wv = *reinterpret_cast<const float4*>(ws + j * H + c);
+          u[i][0] = fmaf(wv.x, xs[j], u[i][0]); u[i][1] = fmaf(wv.y, xs[j], u[i][1]);
+          u[i][2] = fmaf(wv.z, xs[j], u[i][2]); u[i][3] = fmaf(wv.w, xs[j], u[i][3]);
+        }
+      } else { u[i][0] = u[i][1] = u[i][2] = u[i][3] = 0.f; }
+    }
+    float mean, rstd;
+    row_stats<I>(u, H, lane, mean, rstd);
+    // u <- xhat ; d <- dxhat ; accumulate dgamma, dbeta
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      int c = 4 * (lane + 32 * i);
+      if (c < H) {
+        float4 g4 = *reinterpret_cast<const float4*>(bs + H + c);
+        float4 b4 = *reinterpret_cast<const float4*>(bs + 2 * H + c);
+        float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float xh = (u[i][j] - mean) * rstd;
+          float v = fmaf(xh, g[j], be[j]);
+          float dv = v > 0.f ? d[i][j] : 0.f;
+          ag[i][j] = fmaf(dv, xh, ag[i][j]);
+          abe[i][j] += dv;
+          float dx = dv * g[j];
+          u[i][j] = xh; d[i][j] = dx;
+          s1 += dx; s2 = fmaf(dx, xh, s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)(H - 1);
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      int c = 4 * (lane + 32 * i);
+      if (c < H) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float du = rstd * (d[i][j] - s1 - u[i][j] * s2);
+          ab[i][j] += du;
+#pragma unroll
+          for (int k = 0; k < 10; k++) aw[i][k][j] = fmaf(du, xs[k], aw[i][k][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    int c = 4 * (lane + 32 * i);
+    if (c < H) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (int k = 0; k < 10; k++) atomicAdd(&accs[k * H + c + j], aw[i][k][j]);
+        atomicAdd(&accs[10 * H + c + j], ab[i][j]);
+        atomicAdd(&accs[11 * H + c + j], ag[i][j]);
+        atomicAdd(&accs[12 * H + c + j], abe[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 10 * H; i += blockDim.x) { int tap = i / H, c = i - tap * H; atomicAdd(dw + c * 10 + tap, accs[i]); }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(dbias + i, accs[10 * H + i]); atomicAdd(dgam + i, accs[11 * H + i]); atomicAdd(dbet + i, accs[12 * H + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ChannelNorm + ReLU over a padded activation (layers 1..4).  u (B,Lp,H) -> y (B,Lp,H) [+ z (B,Lc,H) fp32]
+// ---------------------------------------------------------------------------------------------------------
+template <int I, class T>
+__global__ void __launch_bounds__(256) cnorm_relu_fwd_kernel(const T* __restrict__ u, const float* __restrict__ gam,
+                                                              const float* __restrict__ bet, T* __restrict__ y,
+                                                              float* __restrict__ zout, int B, int Lc, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long rows = (long long)B * Lc;
+  if (warp >= rows) return;
+  const int b = (int)(warp / Lc), t = (int)(warp - (long long)b * Lc);
+  const long long prow = ((long long)b * (Lc + 2 * kPad) + kPad + t) * H;
+  float v[I][4];
+  row_load<I>(u + prow, H, lane, v);
+  float mean, rstd;
+  row_stats<I>(v, H, lane, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    int c = 4 * (lane + 32 * i);
+    if (c < H) {
+      float4 g4 = *reinterpret_cast<const float4*>(gam + c);
+      float4 b4 = *reinterpret_cast<const float4*>(bet + c);
+      float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[i][j] = fmaxf(fmaf((v[i][j] - mean) * rstd, g[j], be[j]), 0.f);
+    }
+  }
+  if (y) row_store<I>(y + prow, H, lane, v);
+  if (zout) row_store<I>(zout + warp * H, H, lane, v);
+}
+
+// backward of ChannelNorm+ReLU: dy (B,Lc,H) TD unpadded, u padded -> du padded (T); dgamma/dbeta/dbias +=
+template <int I, class TD, class T>
+__global__ void __launch_bounds__(256) cnorm_relu_bwd_kernel(const TD* __restrict__ dy, const T* __restrict__ u,
+                                                              const float* __restrict__ gam, const float* __restrict__ bet,
+                                                              T* __restrict__ du, float* __restrict__ dgam,
+                                                              float* __restrict__ dbet, float* __restrict__ dbias, int B,
+                                                              int Lc, int H) {
+  extern __shared__ __align__(16) float accs[];  // [3][H]
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) accs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long rows = (long long)B * Lc;
+  float ag[I][4], abe[I][4], ab[I][4];
+#pragma unroll
+  for (int i = 0; i < I; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) ag[i][j] = abe[i][j] = ab[i][j] = 0.f;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const int b = (int)(r / Lc), t = (int)(r - (long long)b * Lc);
+    const long long prow = ((long long)b * (Lc + 2 * kPad) + kPad + t) * H;
+    float v[I][4], d[I][4];
+    row_load<I>(u + prow, H, lane, v);
+    row_load<I>(dy + r * H, H, lane, d);
+    float mean, rstd;
+    row_stats<I>(v, H, lane, mean, rstd);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      int c = 4 * (lane + 32 * i);
+      if (c < H) {
+        float4 g4 = *reinterpret_cast<const float4*>(gam + c);
+        float4 b4 = *reinterpret_cast<const float4*>(bet + c);
+        float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float xh = (v[i][j] - mean) * rstd;
+          float a = fmaf(xh, g[j], be[j]);
+          float dv = a > 0.f ? d[i][j] : 0.f;
+          ag[i][j] = fmaf(dv, xh, ag[i][j]);
+          abe[i][j] += dv;
+          float dx = dv * g[j];
+          v[i][j] = xh; d[i][j] = dx;
+          s1 += dx; s2 = fmaf(dx, xh, s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)(H - 1);
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      int c = 4 * (lane + 32 * i);
+      if (c < H) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { float o = rstd * (d[i][j] - s1 - v[i][j] * s2); ab[i][j] += o; d[i][j] = o; }
+      }
+    }
+    row_store<I>(du + prow, H, lane, d);
+  }
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    int c = 4 * (lane + 32 * i);
+    if (c < H) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        atomicAdd(&accs[c + j], ag[i][j]); atomicAdd(&accs[H + c + j], abe[i][j]); atomicAdd(&accs[2 * H + c + j], ab[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(dgam + i, accs[i]); atomicAdd(dbet + i, accs[H + i]); atomicAdd(dbias + i, accs[2 * H + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small prep kernels
+// ---------------------------------------------------------------------------------------------------------
+// forward GEMM weights: Wp[co][tap*Ci + ci] = W[co][ci][tap]
+template <class T>
+__global__ void prep_w_fwd_kernel(const float* __restrict__ w, T* __restrict__ wp, int Co, int Ci, int taps) {
+  long long n = (long long)Co * Ci * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int ci = (int)(i % Ci); long long r = i / Ci; int tap = (int)(r % taps); int co = (int)(r / taps);
+    wp[i] = from_f<T>(w[((long long)co * Ci + ci) * taps + tap]);
+  }
+}
+// dgrad GEMM weights: Wd[r][ci][half*Co + co] = W[co][ci][r + s*(1-half)],  r in [0,s)
+template <class T>
+__global__ void prep_w_dgrad_kernel(const float* __restrict__ w, T* __restrict__ wd, int Co, int Ci, int s) {
+  const int taps = 2 * s;
+  long long n = (long long)s * Ci * 2 * Co;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(i % Co); long long r1 = i / Co; int half = (int)(r1 % 2); r1 /= 2; int ci = (int)(r1 % Ci); int r = (int)(r1 / Ci);
+    wd[i] = from_f<T>(w[((long long)co * Ci + ci) * taps + r + s * (1 - half)]);
+  }
+}
+// zero the kPad rows before and after every window
+template <class T>
+__global__ void zero_pads_kernel(T* __restrict__ buf, int B, int Lc, int H) {
+  const long long Lp = Lc + 2 * kPad;
+  const long long n = (long long)B * 2 * kPad * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % H); long long r = i / H; int pr = (int)(r % (2 * kPad)); int b = (int)(r / (2 * kPad));
+    long long row = pr < kPad ? pr : (Lc + pr);  // pr in [kPad, 2kPad) -> Lc + kPad + (pr - kPad)
+    buf[((long long)b * Lp + row) * H + c] = from_f<T>(0.f);
+  }
+}
+
+struct EncLayout {
+  size_t y[4], u[5];  // element offsets into save (u[0] unused)
+  size_t total;       // elements
+};
+EncLayout enc_layout(const Geo& g) {
+  EncLayout e{};
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t r = off; off += (n + 127) / 128 * 128; return r; };
+  for (int i = 0; i < 4; i++) e.y[i] = take((size_t)g.B * (g.Lout[i] + 2 * kPad) * g.H);
+  for (int i = 1; i < 5; i++) e.u[i] = take((size_t)g.B * (g.Lout[i] + 2 * kPad) * g.H);
+  e.total = off;
+  return e;
+}
+
+inline int ilog_I(int H) { return (H + 127) / 128; }
+
+template <class T>
+int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p, float* z, void* save, void* wsp,
+                  size_t ws_bytes, cudaStream_t st) {
+  const int H = g.H, B = g.B;
+  EncLayout e = enc_layout(g);
+  T* sv = static_cast<T*>(save);
+  Carver ws(wsp, ws_bytes);
+  T* wp[5] = {nullptr};
+  for (int i = 1; i < 5; i++) wp[i] = ws.take<T>((size_t)H * kConvK[i] * H);
+  if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "encoder_fwd: workspace %zu < %zu", ws_bytes, ws.off);
+
+  for (int i = 1; i < 5; i++) {
+    prep_w_fwd_kernel<T><<<148, 256, 0, st>>>(p->conv_w[i], wp[i], H, H, kConvK[i]);
+    CPC_LAUNCHED();
+  }
+  for (int i = 0; i < 4; i++) {
+    zero_pads_kernel<T><<<(B * 2 * kPad * H + 255) / 256, 256, 0, st>>>(sv + e.y[i], B, g.Lout[i], H);
+    CPC_LAUNCHED();
+  }
+  const int I = ilog_I(H);
+  {
+    const size_t smem = 13 * (size_t)H * sizeof(float);
+    const int blocks = 148 * 4;
+#define LAUNCH_C0(II)                                                                                             \
+  conv0_fwd_kernel<II, T><<<blocks, 256, smem, st>>>(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0],   \
+                                                     sv + e.y[0], B, g.L, g.Lout[0], H)
+    if (I == 1) LAUNCH_C0(1); else if (I == 2) LAUNCH_C0(2); else if (I == 3) LAUNCH_C0(3); else LAUNCH_C0(4);
+#undef LAUNCH_C0
+    CPC_LAUNCHED();
+  }
+  for (int i = 1; i < 5; i++) {
+    const int Lin = g.Lout[i - 1], Lo = g.Lout[i];
+    RowView A{sv + e.y[i - 1] + (size_t)(kPad - kConvP[i]) * H, (long long)(Lin + 2 * kPad) * H, (long long)kConvS[i] * H, Lo};
+    OutView C{sv + e.u[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo, 0, Lo, 0};
+    CPC_TRY(gemm_nt(g.bf16, false, B, H, kConvK[i] * H, A, wp[i], p->conv_b[i], C, st));
+    const long long rows = (long long)B * Lo;
+    const int blocks = (int)((rows * 32 + 255) / 256);
+    T* yo = i < 4 ? sv + e.y[i] : nullptr;
+    float* zo = i == 4 ? z : nullptr;
+#define LAUNCH_CN(II) cnorm_relu_fwd_kernel<II, T><<<blocks, 256, 0, st>>>(sv + e.u[i], p->norm_w[i], p->norm_b[i], yo, zo, B, Lo, H)
+    if (I == 1) LAUNCH_CN(1); else if (I == 2) LAUNCH_CN(2); else if (I == 3) LAUNCH_CN(3); else LAUNCH_CN(4);
+#undef LAUNCH_CN
+    CPC_LAUNCHED();
+  }
+  return 0;
+}
+
+template <class T>
+int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p, const float* dz, const void* save,
+                  const cpcb200_encoder_params* gr, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  const int H = g.H, B = g.B;
+  EncLayout e = enc_layout(g);
+  const T* sv = static_cast<const T*>(save);
+  Carver ws(wsp, ws_bytes);
+  T* wd[5] = {nullptr};
+  T* du[5] = {nullptr};
+  T* dy[4] = {nullptr};
+  for (int i = 1; i < 5; i++) wd[i] = ws.take<T>((size_t)kConvS[i] * H * 2 * H);
+  for (int i = 1; i < 5; i++) du[i] = ws.take<T>((size_t)B * (g.Lout[i] + 2 * kPad) * H);
+  for (int i = 0; i < 4; i++) dy[i] = ws.take<T>((size_t)B * g.Lout[i] * H);
+  if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "encoder_bwd: workspace %zu < %zu", ws_bytes, ws.off);
+  const int I = ilog_I(H);
+
+  for (int i = 1; i < 5; i++) {
+    prep_w_dgrad_kernel<T><<<148, 256, 0, st>>>(p->conv_w[i], wd[i], H, H, kConvS[i]);
+    CPC_LAUNCHED();
+    zero_pads_kernel<T><<<(B * 2 * kPad * H + 255) / 256, 256, 0, st>>>(du[i], B, g.Lout[i], H);
+    CPC_LAUNCHED();
+  }
+  for (int i = 4; i >= 1; i--) {
+    const int Lo = g.Lout[i], Lin = g.Lout[i - 1], s = kConvS[i], pp = kConvP[i];
+    // ChannelNorm+ReLU backward -> du_i, dgamma_i, dbeta_i, dbias_i
+    {
+      const long long rows = (long long)B * Lo;
+      int blocks = (int)((rows * 32 + 255) / 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      const size_t smem = 3 * (size_t)H * sizeof(float);
+#define LAUNCH_CB(II, TD, SRC)                                                                                       \
+  cnorm_relu_bwd_kernel<II, TD, T><<<blocks, 256, smem, st>>>(SRC, sv + e.u[i], p->norm_w[i], p->norm_b[i], du[i],  \
+                                                              gr->norm_w[i], gr->norm_b[i], gr->conv_b[i], B, Lo, H)
+      if (i == 4) { if (I == 1) LAUNCH_CB(1, float, dz); else if (I == 2) LAUNCH_CB(2, float, dz); else if (I == 3) LAUNCH_CB(3, float, dz); else LAUNCH_CB(4, float, dz); }
+      else { if (I == 1) LAUNCH_CB(1, T, dy[i]); else if (I == 2) LAUNCH_CB(2, T, dy[i]); else if (I == 3) LAUNCH_CB(3, T, dy[i]); else LAUNCH_CB(4, T, dy[i]); }
+#undef LAUNCH_CB
+      CPC_LAUNCHED();
+    }
+    // weight gradient: dW[co][ci][tap] += sum_{b,t} du[b,t,co] * y_{i-1}[b, s t - p + tap, ci]
+    {
+      RowView A{du[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo};
+      RowView Bv{sv + e.y[i - 1] + (size_t)(kPad - pp) * H, (long long)(Lin + 2 * kPad) * H, (long long)s * H, Lo};
+      CPC_TRY(gemm_tn(g.bf16, B, H, kConvK[i] * H, A, Bv, gr->conv_w[i], 0, STORE_CONV_W, H, kConvK[i], st));
+    }
+    // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r]
+    for (int r = 0; r < s; r++) {
+      RowView A{du[i] + (size_t)(kPad - 1) * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo + 1};
+      int t_lo = r < pp ? 1 : 0;
+      int q_max = (Lin - 1 - r + pp) / s;
+      OutView C{dy[i - 1] + (long long)(r - pp) * H, (long long)Lin * H, (long long)s * H, Lo + 1, t_lo, q_max + 1, 0};
+      CPC_TRY(gemm_nt(g.bf16, false, B, H, 2 * H, A, wd[i] + (size_t)r * H * 2 * H, nullptr, C, st));
+    }
+  }
+  {
+    const size_t smem = 26 * (size_t)H * sizeof(float);
+    const int blocks = 148 * 2;
+#define LAUNCH_C0B(II)                                                                                              \
+  conv0_bwd_kernel<II, T><<<blocks, 256, smem, st>>>(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0],    \
+                                                     dy[0], gr->conv_w[0], gr->conv_b[0], gr->norm_w[0],           \
+                                                     gr->norm_b[0], B, g.L, g.Lout[0], H)
+    if (I == 1) LAUNCH_C0B(1); else if (I == 2) LAUNCH_C0B(2); else if (I == 3) LAUNCH_C0B(3); else LAUNCH_C0B(4);
+#undef LAUNCH_C0B
+    CPC_LAUNCHED();
+  }
+  return 0;
+}
+
+}  // namespace
+
+size_t encoder_save_elems(const Geo& g) { return enc_layout(g).total; }
+
+size_t encoder_ws_bytes(const Geo& g, int backward) {
+  const size_t es = g.bf16 ? 2 : 4;
+  size_t tot = 0;
+  if (!backward) {
+    for (int i = 1; i < 5; i++) tot += align_up((size_t)g.H * kConvK[i] * g.H * es);
+  } else {
+    for (int i = 1; i < 5; i++) tot += align_up((size_t)kConvS[i] * g.H * 2 * g.H * es);
+    for (int i = 1; i < 5; i++) tot += align_up((size_t)g.B * (g.Lout[i] + 2 * kPad) * g.H * es);
+    for (int i = 0; i < 4; i++) tot += align_up((size_t)g.B * g.Lout[i] * g.H * es);
+  }
+  return tot + 256;
+}
+
+int encoder_fwd(const Geo& g, const float* x, const cpcb200_encoder_params* p, float* z, void* save, void* ws,
+                size_t ws_bytes, cudaStream_t st) {
+  if (g.bf16) return encoder_fwd_t<bf16>(g, x, p, z, save, ws, ws_bytes, st);
+  return encoder_fwd_t<float>(g, x, p, z, save, ws, ws_bytes, st);
+}
+int encoder_bwd(const Geo& g, const float* x, const cpcb200_encoder_params* p, const float* dz, const void* save,
+                const cpcb200_encoder_params* gr, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (g.bf16) return encoder_bwd_t<bf16>(g, x, p, dz, save, gr, ws, ws_bytes, st);
+  return encoder_bwd_t<float>(g, x, p, dz, save, gr, ws, ws_bytes, st);
+}
+
+}  // namespace cpcb200

@@ -1,0 +1,264 @@
+"""Drop-in mirrors of the reference module surfaces cpc/model.py:{ChannelNorm,CPCEncoder,CPCAR,CPCModel}.
+
+Same constructor arguments, attributes, state_dict keys and return shapes as the reference, so
+``cpc/train.py`` and ``cpc/feature_loader.py`` run unchanged once ``cpc.model`` is patched
+(``cpc_audio_b200.patch.install``).  All arithmetic runs in libcpc_b200.so (hand-written sm_100a CUDA) through
+the C ABI of ``include/cpc_b200.h``; there is no eager/CPU fallback - CPU tensors raise.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+_DTYPES = {"bf16": L.BF16, "bfloat16": L.BF16, "f32": L.F32, "fp32": L.F32, "float32": L.F32}
+
+
+def default_dtype() -> str:
+    return os.environ.get("CPC_B200_DTYPE", "bf16")
+
+
+def _dtype_code(name) -> int:
+    if name not in _DTYPES:
+        raise ValueError(f"compute dtype must be one of {sorted(_DTYPES)}, got {name!r}")
+    return _DTYPES[name]
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"cpc_audio_b200.{what}: input is on {t.device}; this implementation is CUDA (sm_100a) only "
+                           f"and has no CPU fallback")
+
+
+def _bytes(n, device):
+    return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
+
+
+class ChannelNorm(nn.Module):
+    """Parameter holder for cpc/model.py:25-58 (weight/bias of shape (1, C, 1)); the math is fused in the kernels."""
+
+    def __init__(self, numFeatures, epsilon=1e-05, affine=True):
+        super().__init__()
+        if not affine or epsilon != 1e-05:
+            raise NotImplementedError("cpc_audio_b200: ChannelNorm supports affine=True, epsilon=1e-5 only")
+        self.weight = nn.Parameter(torch.ones(1, numFeatures, 1))
+        self.bias = nn.Parameter(torch.zeros(1, numFeatures, 1))
+        self.epsilon = epsilon
+        self.affine = affine
+
+
+class _EncoderFn(torch.autograd.Function):
+    """x (B,1,L) -> z (B,S,H) channel-last.  cpc/model.py:99-105."""
+
+    @staticmethod
+    def forward(ctx, x, dtype_code, *params):
+        _require_cuda(x, "CPCEncoder")
+        lib = L.lib()
+        B, one, Lw = x.shape
+        H = params[0].shape[0]
+        dev = x.device
+        x = x.contiguous().float()
+        params = tuple(p.detach().contiguous() for p in params)
+        d = L.make_dims(B, Lw, H, H, 1, 1, 1, dtype_code)
+        S = Lw // 160
+        z = torch.empty(B, S, H, device=dev, dtype=torch.float32)
+        save = _bytes(lib.cpcb200_encoder_save_bytes(d), dev)
+        wsn = lib.cpcb200_encoder_ws_bytes(d, 0)
+        ws = _bytes(wsn, dev)
+        ep = _encoder_params(params)
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_encoder_fwd(d, L.ptr(x), ep, L.ptr(z), L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)),
+                    "encoder_fwd")
+        ctx.save_for_backward(x, save, *params)
+        ctx.dims = (B, Lw, H, dtype_code)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = L.lib()
+        x, save, *params = ctx.saved_tensors
+        B, Lw, H, dtype_code = ctx.dims
+        dev = x.device
+        d = L.make_dims(B, Lw, H, H, 1, 1, 1, dtype_code)
+        sizes = [p.numel() for p in params]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        grads = [g.view_as(p) for g, p in zip(flat.split(sizes), params)]
+        wsn = lib.cpcb200_encoder_ws_bytes(d, 1)
+        ws = _bytes(wsn, dev)
+        dz = dz.contiguous().float()
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_encoder_bwd(d, L.ptr(x), _encoder_params(params), L.ptr(dz), L.ptr(save),
+                                            _encoder_params(grads), L.ptr(ws), wsn, L.stream_ptr(dev)), "encoder_bwd")
+        return (None, None, *grads)
+
+
+def _encoder_params(ts):
+    ep = L.EncoderParams()
+    for i in range(5):
+        ep.conv_w[i] = ts[4 * i].data_ptr()
+        ep.conv_b[i] = ts[4 * i + 1].data_ptr()
+        ep.norm_w[i] = ts[4 * i + 2].data_ptr()
+        ep.norm_b[i] = ts[4 * i + 3].data_ptr()
+    return ep
+
+
+class CPCEncoder(nn.Module):
+    """cpc/model.py:61-105.  Returns (B, H, S) like the reference (a permuted view of the channel-last result)."""
+
+    def __init__(self, sizeHidden=512, normMode="layerNorm", compute_dtype=None):
+        super().__init__()
+        validModes = ["batchNorm", "instanceNorm", "ID", "layerNorm"]
+        if normMode not in validModes:
+            raise ValueError(f"Norm mode must be in {validModes}")
+        if normMode != "layerNorm":
+            raise NotImplementedError(f"cpc_audio_b200: normMode={normMode!r} is outside the accelerated hot path "
+                                      f"(only 'layerNorm' = ChannelNorm); no fallback is provided")
+        if sizeHidden % 64 != 0 or not 64 <= sizeHidden <= 512:
+            raise NotImplementedError("cpc_audio_b200: hiddenEncoder must be a multiple of 64 in [64, 512]")
+        self.dimEncoded = sizeHidden
+        # nn.Conv1d modules are parameter holders (same keys and default init as the reference); never called
+        self.conv0 = nn.Conv1d(1, sizeHidden, 10, stride=5, padding=3)
+        self.batchNorm0 = ChannelNorm(sizeHidden)
+        self.conv1 = nn.Conv1d(sizeHidden, sizeHidden, 8, stride=4, padding=2)
+        self.batchNorm1 = ChannelNorm(sizeHidden)
+        self.conv2 = nn.Conv1d(sizeHidden, sizeHidden, 4, stride=2, padding=1)
+        self.batchNorm2 = ChannelNorm(sizeHidden)
+        self.conv3 = nn.Conv1d(sizeHidden, sizeHidden, 4, stride=2, padding=1)
+        self.batchNorm3 = ChannelNorm(sizeHidden)
+        self.conv4 = nn.Conv1d(sizeHidden, sizeHidden, 4, stride=2, padding=1)
+        self.batchNorm4 = ChannelNorm(sizeHidden)
+        self.DOWNSAMPLING = 160
+        self.compute_dtype = compute_dtype or default_dtype()
+
+    def getDimOutput(self):
+        return self.conv4.out_channels
+
+    def _params(self):
+        out = []
+        for i in range(5):
+            conv, norm = getattr(self, f"conv{i}"), getattr(self, f"batchNorm{i}")
+            out += [conv.weight, conv.bias, norm.weight, norm.bias]
+        return out
+
+    def forward_channel_last(self, x):
+        if x.dim() != 3 or x.size(1) != 1 or x.size(2) % 160 != 0:
+            raise ValueError(f"CPCEncoder expects (B, 1, L) with L a multiple of 160, got {tuple(x.shape)}")
+        return _EncoderFn.apply(x, _dtype_code(self.compute_dtype), *self._params())
+
+    def forward(self, x):
+        return self.forward_channel_last(x).permute(0, 2, 1)
+
+
+class _GruFn(torch.autograd.Function):
+    """z (B,S,H), h0 (nL,B,Har)|None -> c (B,S,Har), hT (nL,B,Har).  torch.nn.GRU(batch_first=True) semantics."""
+
+    @staticmethod
+    def forward(ctx, z, h0, dtype_code, n_layers, *params):
+        _require_cuda(z, "CPCAR")
+        lib = L.lib()
+        B, S, H = z.shape
+        Har = params[1].shape[1]
+        dev = z.device
+        z = z.contiguous().float()
+        h0c = h0.contiguous().float() if h0 is not None else None
+        params = tuple(p.detach().contiguous() for p in params)
+        d = L.make_dims(B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
+        c = torch.empty(B, S, Har, device=dev, dtype=torch.float32)
+        hT = torch.empty(n_layers, B, Har, device=dev, dtype=torch.float32)
+        save = _bytes(lib.cpcb200_gru_save_bytes(d), dev)
+        wsn = lib.cpcb200_gru_ws_bytes(d, 0)
+        ws = _bytes(wsn, dev)
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_gru_fwd(d, L.ptr(z), L.ptr(h0c), _gru_params(params, n_layers), L.ptr(c), L.ptr(hT),
+                                        L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)), "gru_fwd")
+        ctx.save_for_backward(z, c, save, *params)
+        ctx.h0 = h0c
+        ctx.dims = (B, S, H, Har, n_layers, dtype_code)
+        ctx.mark_non_differentiable(hT)
+        return c, hT
+
+    @staticmethod
+    def backward(ctx, dc, _dhT):
+        lib = L.lib()
+        z, c, save, *params = ctx.saved_tensors
+        B, S, H, Har, n_layers, dtype_code = ctx.dims
+        dev = z.device
+        d = L.make_dims(B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
+        sizes = [p.numel() for p in params]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        grads = [g.view_as(p) for g, p in zip(flat.split(sizes), params)]
+        dz = torch.empty_like(z)
+        wsn = lib.cpcb200_gru_ws_bytes(d, 1)
+        ws = _bytes(wsn, dev)
+        dc = dc.contiguous().float()
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_gru_bwd(d, L.ptr(z), L.ptr(ctx.h0), _gru_params(params, n_layers), L.ptr(c), L.ptr(dc),
+                                        L.ptr(save), L.ptr(dz), _gru_params(grads, n_layers), L.ptr(ws), wsn,
+                                        L.stream_ptr(dev)), "gru_bwd")
+        return (dz, None, None, None, *grads)
+
+
+def _gru_params(ts, n_layers):
+    gp = L.GruParams()
+    for l in range(n_layers):
+        gp.w_ih[l] = ts[4 * l].data_ptr()
+        gp.w_hh[l] = ts[4 * l + 1].data_ptr()
+        gp.b_ih[l] = ts[4 * l + 2].data_ptr()
+        gp.b_hh[l] = ts[4 * l + 3].data_ptr()
+    return gp
+
+
+class CPCAR(nn.Module):
+    """cpc/model.py:155-204, GRU branch.  LSTM / RNN / reverse are outside the accelerated path and raise."""
+
+    def __init__(self, dimEncoded, dimOutput, keepHidden, nLevelsGRU, mode="GRU", reverse=False, compute_dtype=None):
+        super().__init__()
+        self.RESIDUAL_STD = 0.1
+        if mode != "GRU":
+            raise NotImplementedError(f"cpc_audio_b200: arMode={mode!r} is outside the accelerated hot path (GRU only); "
+                                      f"pass --arMode GRU")
+        if reverse:
+            raise NotImplementedError("cpc_audio_b200: cpc_mode='reverse' is outside the accelerated hot path")
+        if dimOutput % 64 != 0 or not 64 <= dimOutput <= 512 or not 1 <= nLevelsGRU <= L.MAX_GRU_LAYERS:
+            raise NotImplementedError("cpc_audio_b200: hiddenGar must be a multiple of 64 in [64, 512], nLevelsGRU in [1, 4]")
+        # parameter holder: same keys (gAR.baseNet.weight_ih_l0 ...) and default init as the reference
+        self.baseNet = nn.GRU(dimEncoded, dimOutput, num_layers=nLevelsGRU, batch_first=True)
+        self.hidden = None
+        self.keepHidden = keepHidden
+        self.reverse = reverse
+        self.compute_dtype = compute_dtype or default_dtype()
+
+    def getDimOutput(self):
+        return self.baseNet.hidden_size
+
+    def _params(self):
+        out = []
+        for l in range(self.baseNet.num_layers):
+            out += [getattr(self.baseNet, f"{n}_l{l}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        return out
+
+    def forward(self, x):
+        c, hT = _GruFn.apply(x, self.hidden, _dtype_code(self.compute_dtype), self.baseNet.num_layers, *self._params())
+        if self.keepHidden:
+            self.hidden = hT.detach()  # model.py:194-198
+        return c
+
+
+class CPCModel(nn.Module):
+    """cpc/model.py:276-289.  forward(batchData, label) -> (cFeature (B,S,Har), encodedData (B,S,H), label)."""
+
+    def __init__(self, encoder, AR):
+        super().__init__()
+        self.gEncoder = encoder
+        self.gAR = AR
+
+    def forward(self, batchData, label):
+        if isinstance(self.gEncoder, CPCEncoder):
+            encodedData = self.gEncoder.forward_channel_last(batchData)
+        else:
+            encodedData = self.gEncoder(batchData).permute(0, 2, 1)
+        cFeature = self.gAR(encodedData)
+        return cFeature, encodedData, label

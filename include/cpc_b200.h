@@ -1,0 +1,140 @@
+/*
+ * cpc_b200.h - C ABI of libcpc_b200.so: the B200 (sm_100a) implementation of the CPC training-step hot path.
+ *
+ * Drop-in boundary.  The reference (facebookresearch/CPC_audio @ b98a1bd) is pure Python on
+ * PyTorch: it has no FFI of its own, its "operator interface" for this path is the two torch.nn.Module
+ * surfaces cpc/model.py:276-289 (CPCModel) and cpc/criterion/criterion.py:139-257 (CPCUnsupersivedCriterion).
+ * Each entry point below replaces the torch-op sequence of the reference lines it cites; the Python mirror
+ * of the module surfaces (cpc_audio_b200/model.py, criterion.py) binds them through ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller unless stated otherwise;
+ *     the library never allocates, frees or retains device memory, and never synchronises the device.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, on the current device.
+ *   - tensors crossing the ABI are fp32 (activations, parameters, gradients) or int64/int32 (indices), dense,
+ *     row-major, CHANNEL-LAST: z/c are (B, S, H) exactly as CPCModel.forward returns them (model.py:287).
+ *   - `dims.dtype` selects the storage type of the library-internal activations (saved buffers, workspace):
+ *     CPCB200_F32 = everything fp32 on CUDA cores (tight parity); CPCB200_BF16 = bf16 storage, fp32
+ *     accumulation, tensor cores (tcgen05) for the dense contractions.
+ *   - `save`  = caller-allocated buffer written by *_fwd and read by the matching *_bwd (size: *_save_bytes);
+ *     `ws`    = caller-allocated scratch, contents undefined after return (size: *_ws_bytes); both 256-B aligned.
+ *   - return value: 0 on success, negative cpcb200_status on failure; message via cpcb200_last_error()
+ *     (thread-local).  Unsupported configurations fail with CPCB200_ERR_UNSUPPORTED - there is no fallback.
+ *   - re-entrant: no global mutable state besides per-device one-time kernel attributes and a launch counter.
+ */
+#ifndef CPC_B200_H_
+#define CPC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPCB200_VERSION 100
+
+typedef enum {
+  CPCB200_OK = 0,
+  CPCB200_ERR_BAD_DIMS = -1,
+  CPCB200_ERR_UNSUPPORTED = -2,
+  CPCB200_ERR_WORKSPACE = -3,
+  CPCB200_ERR_CUDA = -4,
+  CPCB200_ERR_NULL = -5
+} cpcb200_status;
+
+typedef enum { CPCB200_F32 = 0, CPCB200_BF16 = 1 } cpcb200_dtype;
+
+/* Shape of one local batch.  S = L/160 frames, W = S-K anchor positions (criterion.py:232). */
+typedef struct {
+  int32_t B;       /* windows in the local batch                                   */
+  int32_t L;       /* samples per window, multiple of 160 (cpc_default_config.py:41) */
+  int32_t H;       /* hiddenEncoder  (multiple of 64, <= 512)                      */
+  int32_t Har;     /* hiddenGar      (multiple of 64, <= 512)                      */
+  int32_t K;       /* nPredicts      (<= 16)                                       */
+  int32_t N;       /* negativeSamplingExt                                          */
+  int32_t nLayers; /* nLevelsGRU                                                   */
+  int32_t dtype;   /* cpcb200_dtype                                                */
+} cpcb200_dims;
+
+/* Parameters of CPCEncoder (cpc/model.py:83-93): conv{i}.weight (H,Cin,k), conv{i}.bias (H),
+ * batchNorm{i}.weight/.bias (1,H,1) viewed as (H).  The same struct carries the gradients in *_bwd. */
+typedef struct {
+  float* conv_w[5];
+  float* conv_b[5];
+  float* norm_w[5];
+  float* norm_b[5];
+} cpcb200_encoder_params;
+
+/* Parameters of torch.nn.GRU as held by CPCAR.baseNet (cpc/model.py:175-176), gate order (r,z,n). */
+#define CPCB200_MAX_GRU_LAYERS 4
+typedef struct {
+  float* w_ih[CPCB200_MAX_GRU_LAYERS]; /* (3Har, Hin)  */
+  float* w_hh[CPCB200_MAX_GRU_LAYERS]; /* (3Har, Har)  */
+  float* b_ih[CPCB200_MAX_GRU_LAYERS]; /* (3Har)       */
+  float* b_hh[CPCB200_MAX_GRU_LAYERS]; /* (3Har)       */
+} cpcb200_gru_params;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int cpcb200_version(void);
+const char* cpcb200_last_error(void);
+/* number of kernels this library has launched since load (all threads); bench.py reports the delta */
+uint64_t cpcb200_launch_count(void);
+
+/* ---- CPCEncoder.forward  (cpc/model.py:99-105: 5 x [Conv1d -> ChannelNorm(model.py:50-58) -> ReLU]) -------
+ * x (B,1,L) fp32  ->  z (B,S,H) fp32, channel-last (what model.py:287 obtains with .permute(0,2,1)). */
+size_t cpcb200_encoder_save_bytes(const cpcb200_dims* d);
+size_t cpcb200_encoder_ws_bytes(const cpcb200_dims* d, int backward);
+int cpcb200_encoder_fwd(const cpcb200_dims* d, const float* x, const cpcb200_encoder_params* p, float* z,
+                        void* save, void* ws, size_t ws_bytes, void* stream);
+/* dz (B,S,H) fp32 -> parameter gradients ACCUMULATED (+=) into `grads` (fp32, caller zero-fills). */
+int cpcb200_encoder_bwd(const cpcb200_dims* d, const float* x, const cpcb200_encoder_params* p,
+                        const float* dz, const void* save, const cpcb200_encoder_params* grads, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* ---- CPCAR.forward, GRU branch (cpc/model.py:185-204 -> torch.nn.GRU(batch_first=True)) -----------------
+ * z (B,S,H) -> c (B,S,Har).  h0 (nLayers,B,Har) or NULL (= zeros, model.py:189 hidden=None);
+ * hT (nLayers,B,Har) or NULL receives the final state (model.py:194-198 keepHidden). */
+size_t cpcb200_gru_save_bytes(const cpcb200_dims* d);
+size_t cpcb200_gru_ws_bytes(const cpcb200_dims* d, int backward);
+int cpcb200_gru_fwd(const cpcb200_dims* d, const float* z, const float* h0, const cpcb200_gru_params* p,
+                    float* c, float* hT, void* save, void* ws, size_t ws_bytes, void* stream);
+/* dc (B,S,Har) -> dz (B,S,H) (overwritten), parameter gradients accumulated into `grads`. */
+int cpcb200_gru_bwd(const cpcb200_dims* d, const float* z, const float* h0, const cpcb200_gru_params* p,
+                    const float* c, const float* dc, const void* save, float* dz,
+                    const cpcb200_gru_params* grads, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- negative sampling index arithmetic (criterion.py:191-199) -----------------------------------------
+ * batch_idx, seq_idx: the two raw torch.randint draws of criterion.py:181-189, int64, length B*N*W, flat
+ * layout (B,N,W).  ext[i] = ((seq_idx[i] + i%W) mod S) + batch_idx[i]*S  as int32.  Bit-exact. */
+int cpcb200_sample_ext_idx(const cpcb200_dims* d, const int64_t* batch_idx, const int64_t* seq_idx,
+                           int32_t* ext, void* stream);
+
+/* ---- PredictionNetwork linear heads + scoring + InfoNCE (criterion.py:106-117, 207-217, 245-257) -------
+ * c (B,S,Har), z (B,S,H) fp32; w_pred (K,H,Har) fp32 = predictors.{k}.weight stacked; ext (B,N,W) int32.
+ * losses (K), acc (K) fp32: per-step mean cross-entropy against class 0 and argmax accuracy. */
+size_t cpcb200_criterion_save_bytes(const cpcb200_dims* d);
+size_t cpcb200_criterion_ws_bytes(const cpcb200_dims* d, int backward);
+int cpcb200_criterion_fwd(const cpcb200_dims* d, const float* c, const float* z, const float* w_pred,
+                          const int32_t* ext, float* losses, float* acc, void* save, void* ws,
+                          size_t ws_bytes, void* stream);
+/* dlosses (K) fp32 = d(total)/d(losses[k]).  dc (B,S,Har), dz (B,S,H), dw_pred (K,H,Har) are OVERWRITTEN. */
+int cpcb200_criterion_bwd(const cpcb200_dims* d, const float* c, const float* z, const float* w_pred,
+                          const int32_t* ext, const float* dlosses, const void* save, float* dc, float* dz,
+                          float* dw_pred, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fused Adam over a flat fp32 bucket (cpc/train.py:335-337,90-91; torch.optim.Adam semantics) -------- */
+int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
+
+/* ---- test hooks: the GEMM building blocks, exposed so tests can pin them against torch.matmul ----------
+ * C[M,N] = A[M,Kd] * B[N,Kd]^T (+bias[N]) ; C2[N1,N2] += A[M,N1]^T * B[M,N2].  dtype as in cpcb200_dims. */
+int cpcb200_test_gemm_nt(int dtype, int M, int N, int Kd, const void* A, const void* B, const float* bias,
+                         float* C, void* stream);
+int cpcb200_test_gemm_tn(int dtype, int M, int N1, int N2, const void* A, const void* B, float* C,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPC_B200_H_ */

@@ -1,0 +1,104 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares,
+size queries / argument validation work without a GPU, and the Python mirrors keep the reference's surface."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from tests.conftest import REPO
+
+
+def header_symbols():
+    src = open(os.path.join(REPO, "include", "cpc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cpcb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from cpc_audio_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 19
+    raw = ctypes.CDLL(built_lib)
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in include/cpc_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in cpc_audio_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == syms
+    assert _lib.lib().cpcb200_version() == 100
+
+
+def test_size_queries_and_validation(built_lib):
+    from cpc_audio_b200 import _lib as L
+    lib = L.lib()
+    d = L.make_dims(64, 20480, 256, 256, 12, 128, 1, L.BF16)
+    assert lib.cpcb200_encoder_save_bytes(d) > 64 * 4096 * 256 * 2
+    assert lib.cpcb200_encoder_ws_bytes(d, 1) > lib.cpcb200_encoder_ws_bytes(d, 0) > 0
+    assert lib.cpcb200_gru_save_bytes(d) > 0 and lib.cpcb200_gru_ws_bytes(d, 0) > 0
+    assert lib.cpcb200_criterion_save_bytes(d) > 64 * 116 * 12 * 129 * 4
+    bad = L.make_dims(64, 20481, 256, 256, 12, 128, 1, L.BF16)
+    assert lib.cpcb200_encoder_save_bytes(bad) == 0
+    z = ctypes.c_void_p(16)
+    st = lib.cpcb200_sample_ext_idx(bad, z, z, z, None)
+    assert st == -1 and b"multiple of 160" in lib.cpcb200_last_error()
+    bad2 = L.make_dims(2, 20480, 100, 256, 12, 128, 1, L.F32)
+    assert lib.cpcb200_gru_ws_bytes(bad2, 0) == 0
+    st = lib.cpcb200_adam_step(None, z, z, z, 4, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None)
+    assert st == -5 and b"NULL" in lib.cpcb200_last_error()
+
+
+REF_MODEL_KEYS = [f"gEncoder.{n}{i}.{p}" for i in range(5) for n in ("conv", "batchNorm") for p in ("weight", "bias")] + \
+                 [f"gAR.baseNet.{n}_l0" for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+
+
+def test_module_surface_matches_reference():
+    import cpc_audio_b200 as M
+    enc = M.CPCEncoder(256, "layerNorm")
+    ar = M.CPCAR(256, 256, False, 1, mode="GRU", reverse=False)
+    model = M.CPCModel(enc, ar)
+    sd = model.state_dict()
+    assert sorted(sd) == sorted(REF_MODEL_KEYS)
+    assert sd["gEncoder.conv1.weight"].shape == (256, 256, 8) and sd["gEncoder.batchNorm3.bias"].shape == (1, 256, 1)
+    assert sd["gAR.baseNet.weight_hh_l0"].shape == (768, 256)
+    assert enc.DOWNSAMPLING == 160 and enc.dimEncoded == 256 and enc.getDimOutput() == 256 and ar.getDimOutput() == 256
+    assert ar.hidden is None and ar.keepHidden is False
+    crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode="linear", dropout=False, speakerEmbedding=0,
+                                      nSpeakers=0, sizeInputSeq=128)
+    assert sorted(crit.state_dict()) == sorted(f"wPrediction.predictors.{k}.weight" for k in range(12))
+    assert M.CPCUnsupervisedCriterion is M.CPCUnsupersivedCriterion
+    assert crit.warmUp() is False and crit.update() is None
+    n = sum(p.numel() for p in model.parameters()) + sum(p.numel() for p in crit.parameters())
+    assert n == 2498304
+
+
+def test_unsupported_modes_raise_instead_of_falling_back():
+    import cpc_audio_b200 as M
+    with pytest.raises(NotImplementedError):
+        M.CPCAR(256, 256, False, 1, mode="LSTM")
+    with pytest.raises(NotImplementedError):
+        M.CPCEncoder(256, "batchNorm")
+    with pytest.raises(ValueError):
+        M.CPCEncoder(256, "nope")
+    with pytest.raises(NotImplementedError):
+        M.CPCUnsupersivedCriterion(12, 256, 256, 128, rnnMode="transformer")
+    with pytest.raises(NotImplementedError):
+        M.CPCUnsupersivedCriterion(12, 256, 256, 128, rnnMode="linear", speakerEmbedding=8, nSpeakers=4)
+    model = M.CPCModel(M.CPCEncoder(64), M.CPCAR(64, 64, False, 1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(1, 1, 1600), torch.zeros(1, dtype=torch.long))
+
+
+def test_prediction_weights_share_one_buffer():
+    import cpc_audio_b200 as M
+    crit = M.CPCUnsupersivedCriterion(4, 64, 128, 8, rnnMode="linear", sizeInputSeq=16)
+    flat = crit.wPrediction.stacked()
+    assert flat.shape == (4, 128, 64)
+    crit.wPrediction.predictors[2].weight.data.fill_(3.0)
+    assert crit.wPrediction.stacked()[2].eq(3.0).all()          # in-place updates (optimizer) stay visible
+    sd = {k: torch.full_like(v, 7.0) for k, v in crit.state_dict().items()}
+    crit.load_state_dict(sd)
+    assert crit.wPrediction.stacked().eq(7.0).all()
+    crit2 = M.CPCUnsupersivedCriterion(4, 64, 128, 8, rnnMode="linear", sizeInputSeq=16)
+    crit2.double().float()                                      # _apply re-allocates every parameter
+    f2 = crit2.wPrediction.stacked()
+    assert all(p.weight.data_ptr() == f2[i].data_ptr() for i, p in enumerate(crit2.wPrediction.predictors))

@@ -1,0 +1,192 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): CUDA path through the C ABI vs the CPU oracle and the
+committed reference fixtures.  Tolerances (stated per dtype, see DESIGN.md "Parity"):
+
+  f32 path : z, c max-rel <= 1e-4 ; per-step loss |d| <= 1e-4 (+1e-5 rel) ; acc equal except near-tie rows ;
+             every parameter gradient rel-L2 <= 5e-4.
+  bf16 path: z, c rel-L2 <= 2e-2 ; loss |d| <= 3e-3 (reference init) / 2% (x30-scaled heads) ;
+             acc within 2% abs ; gradient cosine >= 0.99 per parameter tensor.
+  indices  : bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpc_oracle as O
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.detach().double().flatten().cpu(), b.detach().double().flatten().cpu()
+    return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("name", Hh.CASES)
+def test_ext_indices_bit_exact(name, built_lib):
+    import cpc_audio_b200 as M
+    g, d, mp, cp, x, label, bi, si = Hh.load_case(name)
+    crit = M.CPCUnsupersivedCriterion(d.K, d.Har, d.H, d.N, rnnMode="linear", sizeInputSeq=d.S).cuda()
+    dims = (d.B, d.S, d.H, d.Har, d.K, d.N, 0)
+    ext = crit.extIndices(bi.cuda(), si.cuda(), dims).cpu().numpy()
+    assert ext.dtype == np.int32 and np.array_equal(ext, g["ext_idx"])
+    assert np.array_equal(ext, O.ext_indices_np(bi.numpy(), si.numpy(), d.B, d.N, d.W, d.S))
+
+
+@pytest.mark.parametrize("name", Hh.CASES)
+def test_parity_f32(name, built_lib):
+    g, d, mp, cp, x, label, bi, si = Hh.load_case(name)
+    ref = Hh.oracle_run(d, mp, cp, x, bi, si)
+    model, crit = Hh.build_modules(d, mp, cp, "f32")
+    out = Hh.run_modules(model, crit, x, label, bi, si)
+    assert out["z"].shape == (d.B, d.S, d.H) and out["c"].shape == (d.B, d.S, d.Har)
+    assert out["losses"].shape == (1, d.K) and out["acc"].shape == (1, d.K)
+    assert Hh.max_rel(out["z"], ref["z"]) <= 1e-4
+    assert Hh.max_rel(out["c"], ref["c"]) <= 1e-4
+    # against the committed reference fixture
+    np.testing.assert_allclose(Hh.subsample(out["z"]), g["z_sub"], rtol=0, atol=1e-4 * np.abs(g["z_sub"]).max())
+    np.testing.assert_allclose(out["losses"].cpu().numpy(), g["losses"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(out["losses"].cpu().numpy(), ref["losses"].numpy(), rtol=1e-5, atol=1e-4)
+    tol = Hh.acc_tolerance(ref["logits"], d)
+    assert ((out["acc"].cpu() - ref["acc"]).abs() <= tol).all()
+    assert ((out["acc"].cpu() - torch.from_numpy(g["acc"])).abs() <= tol).all()
+    for k, gr in ref["grads"].items():
+        e = Hh.rel_err(out["grads"][k], gr)
+        assert e <= 5e-4, (k, e)
+        sub = g[f"gsub.{k}"]
+        assert np.abs(Hh.subsample(out["grads"][k], 512) - sub).max() <= 1e-3 * (np.abs(sub).max() + 1e-12), k
+
+
+@pytest.mark.parametrize("name", Hh.CASES)
+def test_parity_bf16(name, built_lib):
+    g, d, mp, cp, x, label, bi, si = Hh.load_case(name)
+    ref = Hh.oracle_run(d, mp, cp, x, bi, si)
+    model, crit = Hh.build_modules(d, mp, cp, "bf16")
+    out = Hh.run_modules(model, crit, x, label, bi, si)
+    assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2
+    assert Hh.rel_err(out["c"], ref["c"]) <= 2e-2
+    scaled = float(g["pred_scale"]) != 1.0
+    dl = (out["losses"].cpu() - ref["losses"]).abs()
+    if scaled:
+        assert (dl <= 0.02 * ref["losses"].abs() + 1e-2).all(), dl
+    else:
+        assert (dl <= 3e-3).all(), dl
+    assert ((out["acc"].cpu() - ref["acc"]).abs() <= 0.02 + Hh.acc_tolerance(ref["logits"], d)).all()
+    for k, gr in ref["grads"].items():
+        cs = _cos(out["grads"][k], gr)
+        assert cs >= 0.99, (k, cs)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_gemm_building_blocks(dtype, built_lib):
+    from cpc_audio_b200 import _lib as L
+    lib = L.lib()
+    code = L.F32 if dtype == "f32" else L.BF16
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for (M_, N_, K_) in [(200, 64, 64), (1024, 256, 2048), (7424, 3072, 256), (8192, 768, 256), (333, 128, 512)]:
+        A = torch.randn(M_, K_, device="cuda", generator=gen).to(tdt)
+        Bm = torch.randn(N_, K_, device="cuda", generator=gen).to(tdt)
+        bias = torch.randn(N_, device="cuda", generator=gen)
+        C = torch.empty(M_, N_, device="cuda")
+        L.check(lib.cpcb200_test_gemm_nt(code, M_, N_, K_, L.ptr(A), L.ptr(Bm), L.ptr(bias), L.ptr(C), L.stream_ptr(A.device)), "nt")
+        ref = A.double() @ Bm.double().t() + bias.double()
+        assert Hh.max_rel(C, ref) <= 2e-5, (M_, N_, K_, Hh.max_rel(C, ref))
+    for (M_, N1, N2) in [(500, 64, 64), (65536, 256, 2048), (8192, 768, 256), (7424, 3072, 256), (1000, 128, 192)]:
+        A = torch.randn(M_, N1, device="cuda", generator=gen).to(tdt)
+        Bm = torch.randn(M_, N2, device="cuda", generator=gen).to(tdt)
+        C = torch.zeros(N1, N2, device="cuda")
+        L.check(lib.cpcb200_test_gemm_tn(code, M_, N1, N2, L.ptr(A), L.ptr(Bm), L.ptr(C), L.stream_ptr(A.device)), "tn")
+        ref = A.double().t() @ Bm.double()
+        assert Hh.max_rel(C, ref) <= 5e-5, (M_, N1, N2, Hh.max_rel(C, ref))
+
+
+def test_gru_carried_hidden_state(built_lib):
+    """keepHidden (cpc/model.py:194-198): the second chunk starts from the first chunk's final state."""
+    import cpc_audio_b200 as M
+    d = O.Dims(B=3, L=160 * 12, H=64, Har=128, nLayers=2)
+    mp, _ = O.make_params(d, seed=11)
+    z = torch.randn(d.B, 2 * d.S, d.H, generator=torch.Generator().manual_seed(3))
+    ref, _ = O.gru_forward(z, mp, 2)
+    ar = M.CPCAR(d.H, d.Har, True, 2, compute_dtype="f32")
+    ar.load_state_dict({k.replace("gAR.", ""): v for k, v in mp.items() if k.startswith("gAR.")})
+    ar = ar.cuda()
+    zc = z.cuda().requires_grad_(True)
+    c1 = ar(zc[:, :d.S])
+    assert ar.hidden is not None and ar.hidden.shape == (2, d.B, d.Har) and not ar.hidden.requires_grad
+    c2 = ar(zc[:, d.S:])
+    assert Hh.max_rel(torch.cat([c1, c2], 1), ref) <= 1e-4
+    # gradient through the second chunk with a carried (detached) state
+    h0 = ar.hidden.cpu()
+    zr = z[:, d.S:].clone().requires_grad_(True)
+    mpr = {k: v.clone().requires_grad_(True) for k, v in mp.items()}
+    cr, _ = O.gru_forward(zr, mpr, 2, h0=O.gru_forward(z[:, :d.S], mp, 2)[1])
+    wgt = torch.randn(cr.shape, generator=torch.Generator().manual_seed(4))
+    (cr * wgt).sum().backward()
+    ar.zero_grad()
+    ar.hidden = h0.cuda()
+    c2b = ar(zc[:, d.S:])
+    (c2b * wgt.cuda()).sum().backward()
+    assert Hh.rel_err(zc.grad[:, d.S:], zr.grad) <= 5e-4
+    assert Hh.rel_err(ar.baseNet.weight_hh_l1.grad, mpr["gAR.baseNet.weight_hh_l1"].grad) <= 5e-4
+    assert Hh.rel_err(ar.baseNet.weight_hh_l0.grad, mpr["gAR.baseNet.weight_hh_l0"].grad) <= 5e-4
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_full_size_properties(dtype, built_lib):
+    """BASELINE config 2 shape (B=64, default dims): size-independent properties instead of an oracle run."""
+    d = O.Dims(B=64, L=20480, H=256, Har=256, K=12, N=128, nLayers=1)
+    mp, cp = O.make_params(d, seed=7, pred_scale=30.0)
+    x, label = O.make_batch(d, seed=77)
+    bi, si = O.make_raw_indices(d, seed=777)
+    model, crit = Hh.build_modules(d, mp, cp, dtype)
+    out = Hh.run_modules(model, crit, x, label, bi, si)
+    assert torch.isfinite(out["losses"]).all() and all(torch.isfinite(g).all() for g in out["grads"].values())
+    # (1) windows are independent through the model: permuting the batch permutes z and c
+    perm = torch.randperm(d.B, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        c2, z2, _ = model(x[perm].cuda(), label.cuda())
+    assert Hh.max_rel(z2, out["z"][perm.cuda()]) <= 1e-6 and Hh.max_rel(c2, out["c"][perm.cuda()]) <= 1e-6
+    # (2) sub-batch consistency against the CPU oracle on 4 of the 64 windows (encoder + GRU are per-window)
+    zo = O.encoder_forward(x[:4], mp).permute(0, 2, 1)
+    co, _ = O.gru_forward(zo, mp, 1)
+    tol = 1e-4 if dtype == "f32" else 3e-2
+    assert Hh.rel_err(out["z"][:4], zo) <= tol and Hh.rel_err(out["c"][:4], co) <= tol
+    # (3) zero heads: every logit is 0 -> loss = ln(N+1) exactly, accuracy 1 (class 0 wins ties, as torch.max)
+    for p in crit.parameters():
+        p.data.zero_()
+    o0 = Hh.run_modules(model, crit, x, label, bi, si)
+    assert (o0["losses"] - math.log(d.N + 1)).abs().max() <= 1e-5 and (o0["acc"] == 1).all()
+    # (4) scoring against the oracle criterion fed with the GPU's own c, z (full size, einsum form)
+    crit.load_state_dict(cp)
+    lo, ao, lg = O.criterion_forward(out["c"].cpu(), out["z"].cpu(), cp, bi, si, d.K, d.N, materialize=False)
+    dl = (out["losses"].cpu() - lo).abs()
+    assert (dl <= (1e-4 if dtype == "f32" else 0.02 * lo.abs())).all(), dl
+    assert ((out["acc"].cpu() - ao).abs() <= (0.0 if dtype == "f32" else 0.01) + Hh.acc_tolerance(lg, d)).all()
+
+
+def test_training_reduces_loss_and_is_reproducible(built_lib):
+    d = O.Dims(B=4, L=20480, H=256, Har=256, K=12, N=128, nLayers=1)
+    mp, cp = O.make_params(d, seed=21)
+    x, label = O.make_batch(d, seed=22)
+
+    def run():
+        torch.manual_seed(0)
+        model, crit = Hh.build_modules(d, mp, cp, "bf16")
+        opt = torch.optim.Adam(list(crit.parameters()) + list(model.parameters()), lr=2e-4)
+        hist = []
+        for _ in range(8):
+            c, z, _ = model(x.cuda(), label.cuda())
+            losses, acc = crit(c, z, label.cuda())
+            losses.sum().backward()
+            opt.step()
+            opt.zero_grad()
+            hist.append(losses.mean().item())
+        return hist
+
+    h1 = run()
+    assert h1[-1] < h1[0], h1
+    h2 = run()
+    assert np.allclose(h1, h2, rtol=1e-3), (h1, h2)
