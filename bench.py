@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py - CPC training-step throughput on B200 (audio-seconds/sec on 20480-sample windows).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # our arm (N=1)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W                  # our arm, one rank per GPU over NCCL
+    python bench.py --impl reference --steps 3 --warmup 1          # reference arm: CPU path on the host cores
+
+A step = CPCModel.forward + CPCUnsupersivedCriterion.forward + backward (+ gradient all-reduce when N > 1)
++ Adam step + zero_grad, exactly the body of cpc/train.py:83-91, on BASELINE.json config 2
+(CPC default: H=Har=256, 1-layer GRU, K=12, 128 negatives, 64 windows of 20480 samples per GPU, bf16 storage /
+fp32 accumulation).  Weak scaling: every rank processes its own 64 windows; the only collective is one NCCL
+all-reduce (sum, cpc/train.py:85 semantics) over a flat fp32 gradient bucket.
+
+One JSON line is printed by rank 0 (keys: see the driver contract in the task statement) with
+  value     : whole-job audio-s/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       : same through the public nn.Module API with HOST (pinned) inputs: H2D of the batch and D2H of the
+              losses inside the timed region
+  roofline  : dominant kernel of the step - algorithmic bytes (or FLOPs) / CUDA-event duration vs MEASURED_PEAKS
+  cpu_baseline : the reference algorithm (oracle port, same torch CPU ops as the reference) on the host cores
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+WINDOW = 20480
+SR = 16000.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="windows per GPU")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"])
+    ap.add_argument("--cpu-batch", type=int, default=8, help="windows per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on the host cores (oracle port; the reference itself is Python and is not
+# present on the GPU box).  Bounded sample: `cpu_batch` windows per step.
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_throughput(cpu_batch, steps, warmup):
+    import torch
+    from oracle import cpc_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    d = O.Dims(B=cpu_batch, L=WINDOW, H=256, Har=256, K=12, N=128, nLayers=1)
+    mp, cp = O.make_params(d, seed=0)
+    x, _ = O.make_batch(d, seed=1)
+    bi, si = O.make_raw_indices(d, seed=2)
+    params = [v.requires_grad_(True) for v in list(cp.values()) + list(mp.values())]
+    opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step_reference_style(x, mp, cp, bi, si, d)
+        opt.step()
+        opt.zero_grad()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(value=cpu_batch * WINDOW / SR / med, unit="audio-s/s", cores=threads, kind="port",
+                sample=f"{steps} steps of {cpu_batch} windows x {WINDOW} samples (fwd+bwd+Adam, fp32, torch CPU ops as the "
+                       f"reference uses them), median step {med * 1e3:.0f} ms", ms_per_step=med * 1e3)
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_throughput(a.cpu_batch, max(1, a.steps), max(1, a.warmup))
+    line = {"impl": "reference", "metric": "audio-seconds/sec", "value": r["value"], "unit": "audio-s/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CPC default (H=256, 1-layer GRU, K=12, 128 negatives), 20480-sample windows, "
+                                   f"{a.cpu_batch} windows per CPU step", "global_batch": a.cpu_batch, "seq_len": WINDOW},
+            "cpu_baseline": {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j.get("bf16_tflops_sustained", j["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def algorithmic_work(B, bf16):
+    """Per-launch algorithmic bytes / FLOPs of each kernel at default dims (DESIGN.md 'Rooflines')."""
+    es = 2 if bf16 else 4
+    H, S, W, K, N, L0 = 256, 128, 116, 12, 128, 4096
+    w = {}
+    # HBM-bound: bytes each launch must move once
+    w["conv0_fwd"] = ("hbm", B * (WINDOW * 4 + L0 * H * es))
+    w["conv0_bwd"] = ("hbm", B * (WINDOW * 4 + L0 * H * es))
+    w["gru_rec_fwd"] = ("hbm", B * S * (3 * H * es + H * 4 + 5 * H * es) + 3 * H * H * 4)
+    w["gru_rec_bwd"] = ("hbm", B * S * (2 * H * 4 + 4 * H * es + 6 * H * es) + 3 * H * H * 4)
+    w["score_fwd"] = ("hbm", B * W * (K * H * es + N * 4 + K * (N + 1) * 4) + B * S * H * es)
+    w["score_bwd"] = ("hbm", B * W * (2 * K * H * es + N * 4 + K * (N + 1) * 4) + B * S * H * (es + 4))
+    # tensor-bound: FLOPs per step summed over that kernel's launches (reported per launch by dividing)
+    conv = [(1024, 8), (512, 4), (256, 4), (128, 4)]
+    f_nt = sum(2.0 * B * lo * H * k * H for lo, k in conv)            # conv1-4 forward
+    f_nt += sum(2.0 * B * lo * H * k * H for lo, k in conv)           # dgrad
+    f_nt += 2.0 * B * S * 3 * H * H * 2                               # GRU input projection fwd + d(input)
+    f_nt += 2.0 * B * W * K * H * H * 2                               # heads fwd + dc
+    f_tn = sum(2.0 * B * lo * H * k * H for lo, k in conv) + 2.0 * B * S * 3 * H * H * 2 + 2.0 * B * W * K * H * H
+    w["gemm_nt_tc"] = ("tensor", f_nt)
+    w["gemm_tn_tc"] = ("tensor", f_tn)
+    w["gemm_nt_simt"] = ("tensor", f_nt)
+    w["gemm_tn_simt"] = ("tensor", f_tn)
+    return w
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import cpc_audio_b200 as M
+    from cpc_audio_b200 import _lib as L
+    from cpc_audio_b200.optim import FlatAdam, GradBucket
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.lib()
+    B = a.batch
+
+    torch.manual_seed(0)  # identical initial parameters on every rank (replicas)
+    model = M.CPCModel(M.CPCEncoder(256, "layerNorm", compute_dtype=a.dtype),
+                       M.CPCAR(256, 256, False, 1, mode="GRU", reverse=False, compute_dtype=a.dtype)).to(dev)
+    crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode="linear", dropout=False, speakerEmbedding=0,
+                                      nSpeakers=0, sizeInputSeq=WINDOW // 160, compute_dtype=a.dtype).to(dev)
+    params = list(crit.parameters()) + list(model.parameters())  # cpc/train.py:332 order
+    if a.optimizer == "fused":
+        opt = FlatAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+        bucket = opt.bucket
+    else:
+        opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+        bucket = GradBucket(params)
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    torch.cuda.manual_seed(4321 + rank)  # negative-sample draws differ per rank, like DataParallel replicas
+    x_dev = torch.randn(B, 1, WINDOW, device=dev, generator=gen) * 0.1
+    label = torch.zeros(B, dtype=torch.long, device=dev)
+    x_host = x_dev.cpu().pin_memory()
+    loss_host = torch.empty(1, 12).pin_memory()
+
+    def step(x):
+        c, z, _ = model(x, label)
+        losses, acc = crit(c, z, label)
+        losses.sum().backward()
+        if world > 1:
+            bucket.allreduce()
+        opt.step()
+        opt.zero_grad()
+        return losses
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, n):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync_all()
+        return ms.item()
+
+    W_ = max(3, a.warmup)
+    for _ in range(W_):
+        step(x_dev)
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    n0 = lib.cpcb200_launch_count()
+    ms = timed(lambda: step(x_dev), a.steps)
+    launches = lib.cpcb200_launch_count() - n0
+    clk = clocks.stop() if clocks else None
+
+    def e2e_step():
+        x = x_host.to(dev, non_blocking=True)
+        losses = step(x)
+        loss_host.copy_(losses.detach(), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()  # the loss is read on the host every step (train.py:98)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+
+    # per-kernel timing pass (CUDA events on the launching stream, same workload, after the timed region)
+    roof = None
+    if rank == 0:
+        lib.cpcb200_prof_enable(1)
+        for _ in range(min(a.steps, 10)):
+            step(x_dev)
+        buf = ctypes.create_string_buffer(1 << 16)
+        L.check(lib.cpcb200_prof_report(buf, len(buf)), "prof_report")
+        lib.cpcb200_prof_enable(0)
+        nst = min(a.steps, 10)
+        rows = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, tot = line.split()
+            rows[name] = (int(cnt), float(tot))
+        pk = peaks()
+        work = algorithmic_work(B, a.dtype == "bf16")
+        per_step = {k: v[1] / nst for k, v in rows.items()}
+        top = max(per_step, key=per_step.get)
+        kernels = {}
+        for k, (cnt, tot) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+            ent = {"launches_per_step": cnt / nst, "ms_per_step": round(tot / nst, 4)}
+            if k in work:
+                kind, amount = work[k]
+                if kind == "hbm":
+                    ach = amount / (tot / cnt * 1e-3) / 1e9
+                    ent.update(bound="hbm", achieved_gbs=round(ach, 1), frac=round(ach / pk["hbm"], 4))
+                else:
+                    ach = amount / (tot / nst * 1e-3) / 1e12
+                    ent.update(bound="tensor", achieved_tflops=round(ach, 1), frac=round(ach / pk["tf_sust"], 4))
+            kernels[k] = ent
+        t = kernels[top]
+        if t.get("bound") == "hbm":
+            roof = {"kernel": top, "bound": "hbm", "achieved": t["achieved_gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": t["frac"], "traffic": None, "peak_source": pk["src"] + " (MEASURED_PEAKS.json hbm_gbs)"}
+        elif t.get("bound") == "tensor":
+            roof = {"kernel": top, "bound": "tensor", "achieved": t["achieved_tflops"], "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                    "frac": t["frac"], "traffic": None, "peak_source": pk["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)"}
+        else:
+            roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+        roof["kernels"] = kernels
+        roof["kernel_ms_per_step_total"] = round(sum(per_step.values()), 4)
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            r = cpu_reference_throughput(a.cpu_batch, 3, 1)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        sec = B * world * WINDOW / SR
+        line = {"metric": "audio-seconds/sec", "value": sec / (ms / a.steps * 1e-3), "unit": "audio-s/s", "n_gpus": world,
+                "steps": a.steps, "warmup": W_, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+                "config": {"workload": "BASELINE config 2: CPC default (hiddenEncoder=256, 1-layer GRU, K=12, 128 negatives) "
+                                       f"batch={B}/GPU seq=20480, white-noise 16 kHz windows, random-init weights",
+                           "global_batch": B * world, "seq_len": WINDOW, "parallelism": f"dp{world}", "optimizer": a.optimizer,
+                           "l2": "no explicit flush: one step streams > 1 GB of activations (> 126 MB L2) between reuses"},
+                "e2e": {"value": sec / (ms_e2e / a.steps * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                        "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": ms_e2e / a.steps},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)

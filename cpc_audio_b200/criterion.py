@@ -68,6 +68,10 @@ class PredictionNetwork(nn.Module):
                  for i, w in enumerate(ws))
         if ok and getattr(self, "_flat", None) is not None and self._flat.data_ptr() == base:
             return self._flat
+        if ok and all(isinstance(w, nn.Parameter) and w.is_leaf for w in ws):
+            # already packed inside a larger buffer (e.g. FlatAdam's flat parameters): view it, do not copy
+            self._flat = ws[0].detach().as_strided((K, H, Har), (H * Har, Har, 1))
+            return self._flat
         flat = torch.stack([w.detach() for w in ws]).contiguous()
         if all(isinstance(w, nn.Parameter) and w.is_leaf for w in ws):
             for i, w in enumerate(ws):  # re-point the parameters at the packed buffer (like GRU.flatten_parameters)
@@ -96,6 +100,7 @@ class _CriterionFn(torch.autograd.Function):
             L.check(lib.cpcb200_criterion_fwd(d, L.ptr(c), L.ptr(z), L.ptr(w_flat), L.ptr(ext), L.ptr(losses), L.ptr(acc),
                                               L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)), "criterion_fwd")
         ctx.save_for_backward(c, z, ext, save, w_flat)
+        ctx.weights = weights
         ctx.dims = dims
         ctx.mark_non_differentiable(acc)
         return losses, acc
@@ -117,6 +122,12 @@ class _CriterionFn(torch.autograd.Function):
             L.check(lib.cpcb200_criterion_bwd(d, L.ptr(c), L.ptr(z), L.ptr(w_flat), L.ptr(ext), L.ptr(dlosses), L.ptr(save),
                                               L.ptr(dc), L.ptr(dz), L.ptr(dw), L.ptr(ws), wsn, L.stream_ptr(dev)),
                     "criterion_bwd")
+        from .optim import sinks_for
+        sinks = sinks_for(ctx.weights)
+        if sinks is not None and all(s.is_contiguous() and s.data_ptr() == sinks[0].data_ptr() + i * H * Har * 4
+                                     for i, s in enumerate(sinks)):
+            sinks[0].as_strided((K, H, Har), (H * Har, Har, 1)).add_(dw)  # one kernel into the bucket
+            return (dc, dz, None, None, None, *([None] * K))
         return (dc, dz, None, None, None, *dw.unbind(0))
 
 

@@ -1,5 +1,11 @@
 // api.cu - the extern "C" surface declared in include/cpc_b200.h, argument validation, GEMM dispatch.
 #include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -7,6 +13,39 @@ namespace cpcb200 {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+
+// ---- optional per-kernel timing (bench.py's roofline leg): one CUDA event after every launch, on the
+// launching stream; the time attributed to a kernel is the gap to the previous event of the same API call.
+namespace {
+struct ProfRec { const char* name; int prev, cur; };
+std::mutex g_prof_mu;
+std::atomic<int> g_prof_on{0};
+std::vector<cudaEvent_t> g_prof_ev;
+std::vector<ProfRec> g_prof_rec;
+int g_prof_used = 0, g_prof_last = -1;
+int prof_next_event(cudaStream_t st) {
+  if (g_prof_used == (int)g_prof_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    g_prof_ev.push_back(e);
+  }
+  int i = g_prof_used++;
+  cudaEventRecord(g_prof_ev[i], st);
+  return i;
+}
+}  // namespace
+void prof_mark(cudaStream_t st) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_last = prof_next_event(st);
+}
+void prof_note(const char* name, cudaStream_t st) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int e = prof_next_event(st);
+  if (e >= 0 && g_prof_last >= 0) g_prof_rec.push_back({name, g_prof_last, e});
+  g_prof_last = e;
+}
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -115,6 +154,37 @@ int cpcb200_version(void) { return CPCB200_VERSION; }
 const char* cpcb200_last_error(void) { return g_err; }
 uint64_t cpcb200_launch_count(void) { return g_launches.load(); }
 
+int cpcb200_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_rec.clear();
+  g_prof_used = 0;
+  g_prof_last = -1;
+  g_prof_on.store(on ? 1 : 0);
+  return 0;
+}
+int cpcb200_prof_report(char* buf, size_t cap) {
+  NOT_NULL(buf);
+  CPC_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, std::pair<int, double>> agg;
+  for (const ProfRec& r : g_prof_rec) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof_ev[r.prev], g_prof_ev[r.cur]) != cudaSuccess) continue;
+    auto& a = agg[r.name];
+    a.first += 1;
+    a.second += ms;
+  }
+  std::string out;
+  char line[160];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (out.size() + 1 > cap) return fail(CPCB200_ERR_WORKSPACE, "prof_report: buffer too small (%zu needed)", out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
+
 size_t cpcb200_encoder_save_bytes(const cpcb200_dims* d) {
   Geo g;
   if (make_geo(d, &g)) return 0;
@@ -129,12 +199,14 @@ int cpcb200_encoder_fwd(const cpcb200_dims* d, const float* x, const cpcb200_enc
                         void* ws, size_t ws_bytes, void* stream) {
   GEO_OR_RETURN(d, g);
   NOT_NULL(x); NOT_NULL(p); NOT_NULL(z); NOT_NULL(save); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
   return encoder_fwd(g, x, p, z, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int cpcb200_encoder_bwd(const cpcb200_dims* d, const float* x, const cpcb200_encoder_params* p, const float* dz,
                         const void* save, const cpcb200_encoder_params* grads, void* ws, size_t ws_bytes, void* stream) {
   GEO_OR_RETURN(d, g);
   NOT_NULL(x); NOT_NULL(p); NOT_NULL(dz); NOT_NULL(save); NOT_NULL(grads); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
   return encoder_bwd(g, x, p, dz, save, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -152,6 +224,7 @@ int cpcb200_gru_fwd(const cpcb200_dims* d, const float* z, const float* h0, cons
                     void* save, void* ws, size_t ws_bytes, void* stream) {
   GEO_OR_RETURN(d, g);
   NOT_NULL(z); NOT_NULL(p); NOT_NULL(c); NOT_NULL(save); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
   return gru_fwd(g, z, h0, p, c, hT, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int cpcb200_gru_bwd(const cpcb200_dims* d, const float* z, const float* h0, const cpcb200_gru_params* p, const float* c,
@@ -159,6 +232,7 @@ int cpcb200_gru_bwd(const cpcb200_dims* d, const float* z, const float* h0, cons
                     void* stream) {
   GEO_OR_RETURN(d, g);
   NOT_NULL(z); NOT_NULL(p); NOT_NULL(c); NOT_NULL(dc); NOT_NULL(save); NOT_NULL(dz); NOT_NULL(grads); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
   return gru_bwd(g, z, h0, p, c, dc, save, dz, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -184,6 +258,7 @@ int cpcb200_criterion_fwd(const cpcb200_dims* d, const float* c, const float* z,
   GEO_OR_RETURN(d, g);
   CPC_TRY(check_crit(g));
   NOT_NULL(c); NOT_NULL(z); NOT_NULL(w_pred); NOT_NULL(ext); NOT_NULL(losses); NOT_NULL(acc); NOT_NULL(save); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
   return criterion_fwd(g, c, z, w_pred, ext, losses, acc, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int cpcb200_criterion_bwd(const cpcb200_dims* d, const float* c, const float* z, const float* w_pred, const int32_t* ext,
@@ -193,6 +268,7 @@ int cpcb200_criterion_bwd(const cpcb200_dims* d, const float* c, const float* z,
   CPC_TRY(check_crit(g));
   NOT_NULL(c); NOT_NULL(z); NOT_NULL(w_pred); NOT_NULL(ext); NOT_NULL(dlosses); NOT_NULL(save); NOT_NULL(dc); NOT_NULL(dz);
   NOT_NULL(dw_pred); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
   return criterion_bwd(g, c, z, w_pred, ext, dlosses, save, dc, dz, dw_pred, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -205,9 +281,10 @@ int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   size_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                               eps, weight_decay, (float)bc1, (float)sqrt(bc2));
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N("adam", st);
   return 0;
 }
 

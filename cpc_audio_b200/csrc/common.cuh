@@ -25,10 +25,14 @@ int fail(int code, const char* fmt, ...);
                              cudaGetErrorString(_e));                                                \
   } while (0)
 
+void prof_mark(cudaStream_t st);
+void prof_note(const char* name, cudaStream_t st);
+
 // call after every kernel launch: counts it and surfaces launch-configuration errors without syncing
-#define CPC_LAUNCHED()                                                                               \
+#define CPC_LAUNCHED_N(name, st)                                                                             \
   do {                                                                                               \
     ::cpcb200::g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+    ::cpcb200::prof_note(name, st);                                                                  \
     cudaError_t _e = cudaPeekAtLastError();                                                          \
     if (_e != cudaSuccess)                                                                           \
       return ::cpcb200::fail(CPCB200_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,      \
@@ -159,6 +163,10 @@ struct RowView {
   long long bs;  // elements between batches
   long long rs;  // elements between consecutive rows
   int rpb;       // rows per batch
+  // conv-style rows: the inner dim is `taps` consecutive source rows of (inner/taps) channels and consecutive
+  // logical rows start `s` source rows apart (rs == s * inner/taps).  Plain matrices: taps = s = 1.
+  int taps = 1;
+  int s = 1;
 };
 struct OutView {
   void* p;

@@ -236,9 +236,9 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
   const size_t smem = ((size_t)H * KMAX + (size_t)K * (N + 1)) * sizeof(float);
   CPC_CHECK_CUDA(cudaFuncSetAttribute(score_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_fwd_kernel<T><<<P, threads, smem, st>>>(pred, zp, ext, logits, lossbuf, corrbuf, B, S, W, H, K, N);
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N("score_fwd", st);
   mean_over_positions_kernel<<<K, 256, 0, st>>>(lossbuf, corrbuf, losses, acc, P, K);
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N("mean_over_positions", st);
   return 0;
 }
 
@@ -274,7 +274,7 @@ int criterion_bwd_t(const Geo& g, const float* c, const float* z, const float* w
     const size_t smem = (size_t)(N + 1) * KMAX * sizeof(float) + (size_t)N * sizeof(int);
     CPC_CHECK_CUDA(cudaFuncSetAttribute(score_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     score_bwd_kernel<T><<<P, threads, smem, st>>>(pred, zp, ext, logits, dlosses, dpred, dz, B, S, W, H, K, N);
-    CPC_LAUNCHED();
+    CPC_LAUNCHED_N("score_bwd", st);
   }
   {  // dW[(k,h)][a] = sum_p dpred[p][(k,h)] * c[p][a]
     RowView A{dpred, (long long)W * K * H, (long long)K * H, W};
@@ -296,7 +296,7 @@ int sample_ext_idx(const Geo& g, const int64_t* bi, const int64_t* si, int32_t* 
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   ext_idx_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(bi), reinterpret_cast<const long long*>(si), ext, n, g.W, g.S);
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N("ext_idx", st);
   return 0;
 }
 

@@ -402,11 +402,11 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
 
   for (int i = 1; i < 5; i++) {
     prep_w_fwd_kernel<T><<<148, 256, 0, st>>>(p->conv_w[i], wp[i], H, H, kConvK[i]);
-    CPC_LAUNCHED();
+    CPC_LAUNCHED_N("prep_w_fwd", st);
   }
   for (int i = 0; i < 4; i++) {
     zero_pads_kernel<T><<<(B * 2 * kPad * H + 255) / 256, 256, 0, st>>>(sv + e.y[i], B, g.Lout[i], H);
-    CPC_LAUNCHED();
+    CPC_LAUNCHED_N("zero_pads", st);
   }
   const int I = ilog_I(H);
   {
@@ -417,11 +417,11 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
                                                      sv + e.y[0], B, g.L, g.Lout[0], H)
     if (I == 1) LAUNCH_C0(1); else if (I == 2) LAUNCH_C0(2); else if (I == 3) LAUNCH_C0(3); else LAUNCH_C0(4);
 #undef LAUNCH_C0
-    CPC_LAUNCHED();
+    CPC_LAUNCHED_N("conv0_fwd", st);
   }
   for (int i = 1; i < 5; i++) {
     const int Lin = g.Lout[i - 1], Lo = g.Lout[i];
-    RowView A{sv + e.y[i - 1] + (size_t)(kPad - kConvP[i]) * H, (long long)(Lin + 2 * kPad) * H, (long long)kConvS[i] * H, Lo};
+    RowView A{sv + e.y[i - 1] + (size_t)(kPad - kConvP[i]) * H, (long long)(Lin + 2 * kPad) * H, (long long)kConvS[i] * H, Lo, kConvK[i], kConvS[i]};
     OutView C{sv + e.u[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo, 0, Lo, 0};
     CPC_TRY(gemm_nt(g.bf16, false, B, H, kConvK[i] * H, A, wp[i], p->conv_b[i], C, st));
     const long long rows = (long long)B * Lo;
@@ -431,7 +431,7 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
 #define LAUNCH_CN(II) cnorm_relu_fwd_kernel<II, T><<<blocks, 256, 0, st>>>(sv + e.u[i], p->norm_w[i], p->norm_b[i], yo, zo, B, Lo, H)
     if (I == 1) LAUNCH_CN(1); else if (I == 2) LAUNCH_CN(2); else if (I == 3) LAUNCH_CN(3); else LAUNCH_CN(4);
 #undef LAUNCH_CN
-    CPC_LAUNCHED();
+    CPC_LAUNCHED_N("cnorm_relu_fwd", st);
   }
   return 0;
 }
@@ -454,9 +454,9 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
 
   for (int i = 1; i < 5; i++) {
     prep_w_dgrad_kernel<T><<<148, 256, 0, st>>>(p->conv_w[i], wd[i], H, H, kConvS[i]);
-    CPC_LAUNCHED();
+    CPC_LAUNCHED_N("prep_w_dgrad", st);
     zero_pads_kernel<T><<<(B * 2 * kPad * H + 255) / 256, 256, 0, st>>>(du[i], B, g.Lout[i], H);
-    CPC_LAUNCHED();
+    CPC_LAUNCHED_N("zero_pads", st);
   }
   for (int i = 4; i >= 1; i--) {
     const int Lo = g.Lout[i], Lin = g.Lout[i - 1], s = kConvS[i], pp = kConvP[i];
@@ -472,17 +472,17 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       if (i == 4) { if (I == 1) LAUNCH_CB(1, float, dz); else if (I == 2) LAUNCH_CB(2, float, dz); else if (I == 3) LAUNCH_CB(3, float, dz); else LAUNCH_CB(4, float, dz); }
       else { if (I == 1) LAUNCH_CB(1, T, dy[i]); else if (I == 2) LAUNCH_CB(2, T, dy[i]); else if (I == 3) LAUNCH_CB(3, T, dy[i]); else LAUNCH_CB(4, T, dy[i]); }
 #undef LAUNCH_CB
-      CPC_LAUNCHED();
+      CPC_LAUNCHED_N("cnorm_relu_bwd", st);
     }
     // weight gradient: dW[co][ci][tap] += sum_{b,t} du[b,t,co] * y_{i-1}[b, s t - p + tap, ci]
     {
       RowView A{du[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo};
-      RowView Bv{sv + e.y[i - 1] + (size_t)(kPad - pp) * H, (long long)(Lin + 2 * kPad) * H, (long long)s * H, Lo};
+      RowView Bv{sv + e.y[i - 1] + (size_t)(kPad - pp) * H, (long long)(Lin + 2 * kPad) * H, (long long)s * H, Lo, kConvK[i], s};
       CPC_TRY(gemm_tn(g.bf16, B, H, kConvK[i] * H, A, Bv, gr->conv_w[i], 0, STORE_CONV_W, H, kConvK[i], st));
     }
     // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r]
     for (int r = 0; r < s; r++) {
-      RowView A{du[i] + (size_t)(kPad - 1) * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo + 1};
+      RowView A{du[i] + (size_t)(kPad - 1) * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo + 1, 2, 1};
       int t_lo = r < pp ? 1 : 0;
       int q_max = (Lin - 1 - r + pp) / s;
       OutView C{dy[i - 1] + (long long)(r - pp) * H, (long long)Lin * H, (long long)s * H, Lo + 1, t_lo, q_max + 1, 0};
@@ -498,7 +498,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
                                                      gr->norm_b[0], B, g.L, g.Lout[0], H)
     if (I == 1) LAUNCH_C0B(1); else if (I == 2) LAUNCH_C0B(2); else if (I == 3) LAUNCH_C0B(3); else LAUNCH_C0B(4);
 #undef LAUNCH_C0B
-    CPC_LAUNCHED();
+    CPC_LAUNCHED_N("conv0_bwd", st);
   }
   return 0;
 }

@@ -148,7 +148,7 @@ int gemm_nt_simt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowVie
   } else {
     gemm_nt_kernel<bf16, bf16><<<grid, NT, 0, st>>>(M, N, Kd, A, static_cast<const bf16*>(Bm), bias, C);
   }
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N("gemm_nt_simt", st);
   return 0;
 }
 
@@ -168,7 +168,7 @@ int gemm_tn_simt(bool bf16_in, int nb, int N1, int N2, const RowView& A, const R
   dim3 grid((N2 + BN - 1) / BN, (N1 + BM - 1) / BM, splits);
   if (!bf16_in) gemm_tn_kernel<float><<<grid, NT, 0, st>>>(M, N1, N2, A, B, Cacc, ldc, mode, Ci, taps, rps);
   else gemm_tn_kernel<bf16><<<grid, NT, 0, st>>>(M, N1, N2, A, B, Cacc, ldc, mode, Ci, taps, rps);
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N("gemm_tn_simt", st);
   return 0;
 }
 

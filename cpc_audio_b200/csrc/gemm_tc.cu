@@ -1,6 +1,366 @@
-// gemm_tc.cu - tcgen05 / TMEM / TMA GEMM kernels for the bf16 path (placeholder until the kernels land).
+// gemm_tc.cu - tcgen05 / TMEM / TMA GEMM kernels (bf16 operands, fp32 accumulation) for the bf16 path.
+//
+//   gemm_nt_tc : C[m,n] = sum_k A[m,k] B[n,k] (+bias)    both operands K-major in shared memory (SWIZZLE_128B)
+//                conv1-4 forward / dgrad, GRU input projection, prediction heads and their data gradients.
+//   gemm_tn_tc : C[n1,n2] += sum_m A[m,n1] B[m,n2]       both operands MN-major (reduction dim = rows), split
+//                over row blocks across CTAs, fp32 red.global.add epilogue.  Every weight gradient.
+//
+// A conv-style row view (RowView.taps / .s) is loaded through a 4-D tensor map (c, phase, group, batch) with
+// dims (C, s, rows/s, nb): source row = s*group + phase, so tap j of output row t is the box at
+// (c0, j % s, t + j / s, b) - no im2col, no overlapping strides.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM lane group = warp % 4).  One output tile per CTA, 2 CTAs per SM co-resident so
+// that one CTA's epilogue overlaps the other's main loop.
 #include "common.cuh"
+#include "tc_ptx.cuh"
+
 namespace cpcb200 {
-int gemm_nt_tc(bool, int, int, int, const RowView&, const void*, const float*, const OutView&, cudaStream_t, bool* handled) { *handled = false; return 0; }
-int gemm_tn_tc(int, int, int, const RowView&, const RowView&, float*, int, int, int, int, cudaStream_t, bool* handled) { *handled = false; return 0; }
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UK = 16;
+constexpr int NT_THREADS = 192;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
 }
+
+// 4-D bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first; strides in ELEMENTS.
+int make_map4(CUtensorMap* m, const void* base, const unsigned long long dims[4], const unsigned long long strides_el[3],
+              const unsigned box[4]) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(CPCB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gs[3] = {strides_el[0] * 2, strides_el[1] * 2, strides_el[2] * 2};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(CPCB200_ERR_BAD_DIMS, "tensor map base not 16-B aligned");
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CPCB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu strides %llu %llu %llu box %u %u %u %u",
+                (int)r, dims[0], dims[1], dims[2], dims[3], strides_el[0], strides_el[1], strides_el[2], box[0], box[1], box[2], box[3]);
+  return 0;
+}
+
+// map of a RowView: dims (cin, s, groups, nb); box (64, 1, box_rows, 1)
+int make_rowview_map(CUtensorMap* m, const RowView& v, int inner, int nb, int box_rows, bool exact_rows) {
+  const int cin = inner / v.taps;
+  if (cin % 64 != 0) return fail(CPCB200_ERR_BAD_DIMS, "row view: %d channels per tap not a multiple of 64", cin);
+  if (v.taps > 1 && v.rs != (long long)v.s * cin) return fail(CPCB200_ERR_BAD_DIMS, "row view: rs != s*cin");
+  const long long group_stride = v.rs;                                   // elements between consecutive logical rows
+  const long long phase_stride = v.taps > 1 ? cin : v.rs;                // elements between consecutive source rows
+  const unsigned long long groups = exact_rows ? (unsigned long long)v.rpb : (unsigned long long)(v.rpb + (v.taps - 1) / v.s);
+  const long long bstride = nb > 1 ? v.bs : (long long)groups * group_stride;
+  unsigned long long dims[4] = {(unsigned long long)cin, (unsigned long long)v.s, groups, (unsigned long long)nb};
+  unsigned long long st[3] = {(unsigned long long)phase_stride, (unsigned long long)group_stride, (unsigned long long)bstride};
+  unsigned box[4] = {64, 1, (unsigned)box_rows, 1};
+  return make_map4(m, v.p, dims, st, box);
+}
+
+__device__ __forceinline__ void store_out(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void store_out(bf16* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; j++) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+    reinterpret_cast<uint4*>(p)[i] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NT kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, class TO>
+__global__ void __launch_bounds__(NT_THREADS) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB, int nkb,
+                                                                 int chunks_per_tap, int s, int tiles_per_batch, int N,
+                                                                 const float* __restrict__ bias, OutView C) {
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smA = sm;
+  unsigned char* smB = sm + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int b = blockIdx.y / tiles_per_batch;
+  const int t0 = (blockIdx.y - b * tiles_per_batch) * BM;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; i++) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_holder, BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int st = kb % STAGES, it = kb / STAGES;
+        if (it > 0) ptx::mbar_wait(&empty[st], (it - 1) & 1);
+        ptx::mbar_arrive_expect_tx(&full[st], A_BYTES + B_BYTES);
+        const int tap = kb / chunks_per_tap, c0 = (kb - tap * chunks_per_tap) * BK;
+        ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES, c0, tap % s, t0 + tap / s, b);
+        ptx::tma_load_4d(&tmB, &full[st], smB + st * B_BYTES, kb * BK, n0, 0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
+      for (int kb = 0; kb < nkb; kb++) {
+        const int st = kb % STAGES, it = kb / STAGES;
+        ptx::mbar_wait(&full[st], it & 1);
+        ptx::tc_fence_after();
+        const uint32_t a0 = ptx::smem_u32(smA + st * A_BYTES), b0 = ptx::smem_u32(smB + st * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UK; k++) {
+          const uint64_t ad = ptx::make_sdesc_sw128(a0 + k * UK * 2, 16, 1024);
+          const uint64_t bd = ptx::make_sdesc_sw128(b0 + k * UK * 2, 16, 1024);
+          ptx::umma_bf16(tmem_acc, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[st]);
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else {
+    // epilogue: thread <-> accumulator row (TMEM lane), 32 columns at a time
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int t = t0 + row;
+    const bool row_ok = t < C.rpb && t >= C.t_lo && t < C.t_hi;
+    TO* crow = static_cast<TO*>(C.p) + (long long)b * C.bs + (long long)t * C.rs + n0;
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      if (row_ok) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+        if (bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] += __ldg(bias + n0 + c0 + j);
+        }
+        store_out(crow + c0, v);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_acc, BN);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TN kernel (weight gradients): C[n1, n2] += sum over row blocks.  Operands MN-major.
+//   A tile  : [64 rows][128 n1]  = 2 swizzled [64][64] blocks   (UMMA M = 128)
+//   B tile  : [64 rows][BN n2]   = BN/64 swizzled [64][64] blocks (UMMA N = BN)
+// ---------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NT_THREADS) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB, int kb_total,
+                                                                 int kb_per_cta, int kb_per_batch, int b_chunks_per_tap,
+                                                                 int b_s, int N1, int N2, float* __restrict__ Cacc, int ldc,
+                                                                 int mode, int Ci, int taps) {
+  constexpr uint32_t BLK = 64 * 64 * 2;  // one swizzled [64 rows][64 ch] block
+  constexpr uint32_t A_BYTES = 2 * BLK, B_BYTES = (BN / 64) * BLK;
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smA = sm;
+  unsigned char* smB = sm + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n20 = blockIdx.x * BN, n10 = blockIdx.y * BM;
+  const int kb_beg = blockIdx.z * kb_per_cta;
+  const int kb_end = min(kb_total, kb_beg + kb_per_cta);
+  const int nkb = kb_end - kb_beg;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; i++) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_holder, BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // B operand columns n2 = tap*Ci' + c  ->  (tap, c0) per 64-wide block
+      for (int i = 0; i < nkb; i++) {
+        const int kb = kb_beg + i;
+        const int st = i % STAGES, it = i / STAGES;
+        if (it > 0) ptx::mbar_wait(&empty[st], (it - 1) & 1);
+        ptx::mbar_arrive_expect_tx(&full[st], A_BYTES + B_BYTES);
+        const int bb = kb / kb_per_batch, r0 = (kb - bb * kb_per_batch) * 64;
+#pragma unroll
+        for (int j = 0; j < 2; j++) ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES + j * BLK, n10 + j * 64, 0, r0, bb);
+#pragma unroll
+        for (int j = 0; j < BN / 64; j++) {
+          const int blk = (n20 >> 6) + j;
+          const int tap = blk / b_chunks_per_tap, c0 = (blk - tap * b_chunks_per_tap) * 64;
+          ptx::tma_load_4d(&tmB, &full[st], smB + st * B_BYTES + j * BLK, c0, tap % b_s, r0 + tap / b_s, bb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 1, 1);
+      for (int i = 0; i < nkb; i++) {
+        const int st = i % STAGES, it = i / STAGES;
+        ptx::mbar_wait(&full[st], it & 1);
+        ptx::tc_fence_after();
+        const uint32_t a0 = ptx::smem_u32(smA + st * A_BYTES), b0 = ptx::smem_u32(smB + st * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < 64 / UK; k++) {
+          // MN-major SW128: LBO = stride between 64-wide MN blocks, SBO = stride between 8-row K groups
+          const uint64_t ad = ptx::make_sdesc_sw128(a0 + k * UK * 128, BLK, 1024);
+          const uint64_t bd = ptx::make_sdesc_sw128(b0 + k * UK * 128, BLK, 1024);
+          ptx::umma_bf16(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[st]);
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else if (nkb > 0) {
+    const int lg = warp & 3;
+    const int n1 = n10 + lg * 32 + lane;
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      if (n1 < N1) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int n2 = n20 + c0 + j;
+          if (n2 < N2) {
+            long long o;
+            if (mode == STORE_CONV_W) { const int tap = n2 / Ci, ci = n2 - tap * Ci; o = ((long long)n1 * Ci + ci) * taps + tap; }
+            else o = (long long)n1 * ldc + n2;
+            atomicAdd(Cacc + o, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_acc, BN);
+}
+
+template <int BN, int STAGES> constexpr size_t nt_smem() { return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 1024; }
+template <int BN, int STAGES> constexpr size_t tn_smem() { return (size_t)STAGES * (2 * 8192 + (BN / 64) * 8192) + 256 + 1024; }
+
+}  // namespace
+
+int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C,
+               cudaStream_t st, bool* handled) {
+  *handled = false;
+  constexpr int BN = 128, STAGES = 3;
+  const int cin = Kd / A.taps;
+  if (N % BN != 0 || Kd % BK != 0 || cin % 64 != 0 || (A.taps > 1 && A.rs != (long long)A.s * cin)) return 0;
+  if ((A.rs % 8) != 0 || (A.bs % 8) != 0 || (reinterpret_cast<uintptr_t>(A.p) & 15) || (reinterpret_cast<uintptr_t>(Bm) & 15)) return 0;
+  if ((C.rs % 8) != 0 || (C.bs % 8) != 0) return 0;
+  CUtensorMap tmA, tmB;
+  CPC_TRY(make_rowview_map(&tmA, A, Kd, nb, BM, false));
+  {
+    unsigned long long dims[4] = {(unsigned long long)Kd, (unsigned long long)N, 1, 1};
+    unsigned long long stq[3] = {(unsigned long long)Kd, (unsigned long long)Kd * N, (unsigned long long)Kd * N};
+    unsigned box[4] = {64, (unsigned)BN, 1, 1};
+    CPC_TRY(make_map4(&tmB, Bm, dims, stq, box));
+  }
+  const int tpb = (A.rpb + BM - 1) / BM;
+  dim3 grid(N / BN, nb * tpb);
+  const size_t smem = nt_smem<BN, STAGES>();
+  if (out_f32) {
+    auto k = gemm_nt_tc_kernel<BN, STAGES, float>;
+    CPC_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, NT_THREADS, smem, st>>>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb, N, bias, C);
+  } else {
+    auto k = gemm_nt_tc_kernel<BN, STAGES, bf16>;
+    CPC_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, NT_THREADS, smem, st>>>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb, N, bias, C);
+  }
+  CPC_LAUNCHED_N("gemm_nt_tc", st);
+  *handled = true;
+  return 0;
+}
+
+int gemm_tn_tc(int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode, int Ci, int taps,
+               cudaStream_t st, bool* handled) {
+  *handled = false;
+  constexpr int BN = 128, STAGES = 3;
+  if (A.rpb != B.rpb || A.taps != 1) return 0;
+  const int bcin = N2 / B.taps;
+  if (N1 % BM != 0 || N2 % BN != 0 || bcin % 64 != 0 || (B.taps > 1 && B.rs != (long long)B.s * bcin)) return 0;
+  if ((A.rs % 8) != 0 || (A.bs % 8) != 0 || (B.rs % 8) != 0 || (B.bs % 8) != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(A.p) & 15) || (reinterpret_cast<uintptr_t>(B.p) & 15)) return 0;
+  CUtensorMap tmA, tmB;
+  CPC_TRY(make_rowview_map(&tmA, A, N1, nb, 64, true));   // exact row count: rows >= rpb are zero-filled by TMA
+  CPC_TRY(make_rowview_map(&tmB, B, N2, nb, 64, false));
+  const int kb_per_batch = (A.rpb + 63) / 64;
+  const int kb_total = kb_per_batch * nb;
+  const int tiles = (N1 / BM) * (N2 / BN);
+  int splits = (148 * 2 + tiles - 1) / tiles;
+  if (splits > kb_total) splits = kb_total;
+  if (splits < 1) splits = 1;
+  const int kb_per_cta = (kb_total + splits - 1) / splits;
+  splits = (kb_total + kb_per_cta - 1) / kb_per_cta;
+  dim3 grid(N2 / BN, N1 / BM, splits);
+  const size_t smem = tn_smem<BN, STAGES>();
+  auto k = gemm_tn_tc_kernel<BN, STAGES>;
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, NT_THREADS, smem, st>>>(tmA, tmB, kb_total, kb_per_cta, kb_per_batch, bcin / 64, B.s, N1, N2, Cacc, ldc, mode, Ci, taps);
+  CPC_LAUNCHED_N("gemm_tn_tc", st);
+  *handled = true;
+  return 0;
+}
+
+}  // namespace cpcb200

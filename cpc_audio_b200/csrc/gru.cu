@@ -256,7 +256,7 @@ template <class T> int launch_cast(const float* src, T* dst, long long n, cudaSt
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   cast_kernel<T><<<blocks, 256, 0, st>>>(src, dst, n);
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N("cast", st);
   return 0;
 }
 template int launch_cast<bf16>(const float*, bf16*, long long, cudaStream_t);
@@ -265,7 +265,7 @@ template int launch_cast<float>(const float*, float*, long long, cudaStream_t);
 template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st) {
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
   transpose_cast_kernel<T><<<grid, block, 0, st>>>(src, dst, R, C);
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N("transpose_cast", st);
   return 0;
 }
 template int launch_transpose_cast<bf16>(const float*, bf16*, int, int, cudaStream_t);
@@ -275,7 +275,7 @@ template <class T> int launch_colsum(const T* src, float* out, long long M, int 
   const int rpb = 256;
   dim3 grid((N + 127) / 128, (unsigned)((M + rpb - 1) / rpb));
   colsum_kernel<T><<<grid, 128, 0, st>>>(src, out, M, N, rpb);
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N("colsum", st);
   return 0;
 }
 template int launch_colsum<bf16>(const bf16*, float*, long long, int, cudaStream_t);
@@ -295,7 +295,7 @@ template <class WT> size_t rec_bwd_smem(int Har) {
 }
 
 template <class K>
-int launch_cluster(K kernel, int cs, int nclusters, int threads, size_t smem, cudaStream_t st, void** args) {
+int launch_cluster(const char* name, K kernel, int cs, int nclusters, int threads, size_t smem, cudaStream_t st, void** args) {
   CPC_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (cs > 8) CPC_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -308,7 +308,7 @@ int launch_cluster(K kernel, int cs, int nclusters, int threads, size_t smem, cu
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   CPC_CHECK_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kernel), args));
-  CPC_LAUNCHED();
+  CPC_LAUNCHED_N(name, st);
   return 0;
 }
 
@@ -382,7 +382,7 @@ int gru_fwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     const float* bhh = p->b_hh[l];
     int Bv = B, Sv = S, Hv = Har;
     void* args[] = {&gic, &whh, &bhh, &h0l, &cout, &cTo, &sR, &sU, &sN, &sHN, &hTl, &Bv, &Sv, &Hv};
-    CPC_TRY(launch_cluster(gru_rec_fwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, 3 * HC * 2, smem, st, args));
+    CPC_TRY(launch_cluster("gru_rec_fwd", gru_rec_fwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, 3 * HC * 2, smem, st, args));
   }
   return 0;
 }
@@ -423,7 +423,7 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     float* dh0 = nullptr;
     int Bv = B, Sv = S, Hv = Har;
     void* args[] = {&dcl, &cl, &h0l, &sR, &sU, &sN, &sHN, &whh, &dgi, &dgh, &dh0, &Bv, &Sv, &Hv};
-    CPC_TRY(launch_cluster(gru_rec_bwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, HC * 8, smem, st, args));
+    CPC_TRY(launch_cluster("gru_rec_bwd", gru_rec_bwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, HC * 8, smem, st, args));
 
     CPC_TRY(launch_colsum<T>(dgi, gr->b_ih[l], (long long)B * S, G, st));
     CPC_TRY(launch_colsum<T>(dgh, gr->b_hh[l], (long long)B * S, G, st));

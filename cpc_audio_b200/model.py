@@ -33,6 +33,18 @@ def _require_cuda(t, what):
                            f"and has no CPU fallback")
 
 
+def _grad_targets(params, dev):
+    """Where a backward pass accumulates parameter gradients: the views of a live GradBucket (then autograd gets
+    None for them) or one freshly zeroed flat buffer returned to autograd."""
+    from .optim import sinks_for
+    sinks = sinks_for(params)
+    if sinks is not None:
+        return sinks, True
+    sizes = [p.numel() for p in params]
+    flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+    return [g.view_as(p) for g, p in zip(flat.split(sizes), params)], False
+
+
 def _bytes(n, device):
     return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
 
@@ -83,16 +95,14 @@ class _EncoderFn(torch.autograd.Function):
         B, Lw, H, dtype_code = ctx.dims
         dev = x.device
         d = L.make_dims(B, Lw, H, H, 1, 1, 1, dtype_code)
-        sizes = [p.numel() for p in params]
-        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-        grads = [g.view_as(p) for g, p in zip(flat.split(sizes), params)]
+        grads, sunk = _grad_targets(params, dev)
         wsn = lib.cpcb200_encoder_ws_bytes(d, 1)
         ws = _bytes(wsn, dev)
         dz = dz.contiguous().float()
         with torch.cuda.device(dev):
             L.check(lib.cpcb200_encoder_bwd(d, L.ptr(x), _encoder_params(params), L.ptr(dz), L.ptr(save),
                                             _encoder_params(grads), L.ptr(ws), wsn, L.stream_ptr(dev)), "encoder_bwd")
-        return (None, None, *grads)
+        return (None, None, *([None] * len(grads) if sunk else grads))
 
 
 def _encoder_params(ts):
@@ -187,9 +197,7 @@ class _GruFn(torch.autograd.Function):
         B, S, H, Har, n_layers, dtype_code = ctx.dims
         dev = z.device
         d = L.make_dims(B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
-        sizes = [p.numel() for p in params]
-        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-        grads = [g.view_as(p) for g, p in zip(flat.split(sizes), params)]
+        grads, sunk = _grad_targets(params, dev)
         dz = torch.empty_like(z)
         wsn = lib.cpcb200_gru_ws_bytes(d, 1)
         ws = _bytes(wsn, dev)
@@ -198,7 +206,7 @@ class _GruFn(torch.autograd.Function):
             L.check(lib.cpcb200_gru_bwd(d, L.ptr(z), L.ptr(ctx.h0), _gru_params(params, n_layers), L.ptr(c), L.ptr(dc),
                                         L.ptr(save), L.ptr(dz), _gru_params(grads, n_layers), L.ptr(ws), wsn,
                                         L.stream_ptr(dev)), "gru_bwd")
-        return (dz, None, None, None, *grads)
+        return (dz, None, None, None, *([None] * len(grads) if sunk else grads))
 
 
 def _gru_params(ts, n_layers):

@@ -81,6 +81,11 @@ const char* cpcb200_last_error(void);
 /* number of kernels this library has launched since load (all threads); bench.py reports the delta */
 uint64_t cpcb200_launch_count(void);
 
+/* per-kernel timing for the roofline report: when enabled, a CUDA event is recorded on the launching stream
+ * after every kernel; report = text lines "<kernel> <launches> <total_ms>" (synchronises the device). */
+int cpcb200_prof_enable(int on);
+int cpcb200_prof_report(char* buf, size_t cap);
+
 /* ---- CPCEncoder.forward  (cpc/model.py:99-105: 5 x [Conv1d -> ChannelNorm(model.py:50-58) -> ReLU]) -------
  * x (B,1,L) fp32  ->  z (B,S,H) fp32, channel-last (what model.py:287 obtains with .permute(0,2,1)). */
 size_t cpcb200_encoder_save_bytes(const cpcb200_dims* d);
