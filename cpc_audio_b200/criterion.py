@@ -64,8 +64,10 @@ class PredictionNetwork(nn.Module):
         K, (H, Har) = len(ws), ws[0].shape
         step = H * Har * ws[0].element_size()
         base = ws[0].data_ptr()
+        sto = ws[0].untyped_storage()
         ok = all(w.is_contiguous() and w.data_ptr() == base + i * step and w.device == ws[0].device
-                 for i, w in enumerate(ws))
+                 and w.untyped_storage().data_ptr() == sto.data_ptr() for i, w in enumerate(ws))
+        ok = ok and (base - sto.data_ptr()) + K * step <= sto.nbytes()
         if ok and getattr(self, "_flat", None) is not None and self._flat.data_ptr() == base:
             return self._flat
         if ok and all(isinstance(w, nn.Parameter) and w.is_leaf for w in ws):

@@ -78,6 +78,8 @@ def test_parity_bf16(name, built_lib):
         cs = _cos(out["grads"][k], gr)
         # conv biases feed a ChannelNorm: their gradient is a heavily cancelling sum -> looser bound
         floor = 0.95 if (k.endswith(".bias") and "conv" in k) else 0.99
+        if d.H < 256:
+            floor = 0.95  # toy widths (64 / 128 channels): per-tensor sums are short and bf16 noise shows
         assert cs >= floor, (k, cs)
 
 
@@ -118,10 +120,12 @@ def test_gru_carried_hidden_state(built_lib):
     zc = z.cuda().requires_grad_(True)
     c1 = ar(zc[:, :d.S])
     assert ar.hidden is not None and ar.hidden.shape == (2, d.B, d.Har) and not ar.hidden.requires_grad
+    h_mid = ar.hidden.clone()
     c2 = ar(zc[:, d.S:])
     assert Hh.max_rel(torch.cat([c1, c2], 1), ref) <= 1e-4
     # gradient through the second chunk with a carried (detached) state
-    h0 = ar.hidden.cpu()
+    h0 = h_mid.cpu()
+    assert Hh.max_rel(h0, O.gru_forward(z[:, :d.S], mp, 2)[1]) <= 1e-4
     zr = z[:, d.S:].clone().requires_grad_(True)
     mpr = {k: v.clone().requires_grad_(True) for k, v in mp.items()}
     cr, _ = O.gru_forward(zr, mpr, 2, h0=O.gru_forward(z[:, :d.S], mp, 2)[1])
@@ -194,36 +198,46 @@ def test_training_reduces_loss_and_is_reproducible(built_lib):
     assert np.allclose(h1, h2, rtol=1e-3), (h1, h2)
 
 
-def test_fused_adam_and_bucket_match_torch_adam(built_lib):
-    """FlatAdam + GradBucket (one flat buffer, gradients written in place by the backward kernels) against
-    torch.optim.Adam on the same model: identical losses step by step, identical parameters after 5 steps."""
+def test_fused_adam_matches_torch_adam(built_lib):
+    """cpcb200_adam_step vs torch.optim.Adam on identical, deterministic gradients (cpc/train.py:335-337)."""
     from cpc_audio_b200.optim import FlatAdam
-    d = O.Dims(B=2, L=20480, H=256, Har=256, K=12, N=128, nLayers=1)
-    mp, cp = O.make_params(d, seed=31, pred_scale=5.0)
-    x, label = O.make_batch(d, seed=32)
-    bi, si = O.make_raw_indices(d, seed=33)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(256, 256, 8), (768,), (1, 256, 1), (12, 256, 256)]
+    p_t = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=gen)) for s in shapes]
+    p_f = [torch.nn.Parameter(p.detach().clone()) for p in p_t]
+    o_t = torch.optim.Adam(p_t, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+    o_f = FlatAdam(p_f, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+    for it in range(6):
+        for a, b in zip(p_t, p_f):
+            g = torch.randn(a.shape, device="cuda", generator=gen) * (10.0 ** (it - 4))
+            a.grad = g.clone()
+            b.grad.copy_(g)
+        o_t.step(); o_f.step()
+        o_t.zero_grad(); o_f.zero_grad()
+        assert all(b.grad.eq(0).all() for b in p_f)
+    o_f.bucket.detach()
+    for a, b in zip(p_t, p_f):
+        assert (a - b).abs().max().item() <= 2e-6 * max(1.0, a.abs().max().item())
 
-    def run(fused):
-        model, crit = Hh.build_modules(d, mp, cp, "f32")
-        crit.sampleIndices = lambda B, W, S, device: (bi.to(device), si.to(device))
-        params = list(crit.parameters()) + list(model.parameters())
-        opt = FlatAdam(params, lr=1e-3) if fused else torch.optim.Adam(params, lr=1e-3)
-        hist = []
-        for _ in range(5):
-            c, z, _ = model(x.cuda(), label.cuda())
-            losses, acc = crit(c, z, label.cuda())
-            losses.sum().backward()
-            opt.step()
-            opt.zero_grad()
-            hist.append(losses.detach().cpu())
-        if fused:
-            opt.bucket.detach()
-        sd = {**{f"m.{k}": v.detach().cpu().clone() for k, v in model.state_dict().items()},
-              **{f"c.{k}": v.detach().cpu().clone() for k, v in crit.state_dict().items()}}
-        return torch.cat(hist), sd
 
-    h_t, sd_t = run(False)
-    h_f, sd_f = run(True)
-    assert (h_t - h_f).abs().max() <= 2e-4, (h_t - h_f).abs().max()
-    for k in sd_t:
-        assert Hh.max_rel(sd_f[k], sd_t[k]) <= 2e-4, k
+def test_bucket_sinks_receive_the_same_gradients(built_lib):
+    """With a GradBucket attached the backward kernels accumulate straight into the flat buffer; the result must
+    equal the gradients autograd returns without a bucket (up to the atomics' summation order)."""
+    from cpc_audio_b200.optim import GradBucket
+    g, d, mp, cp, x, label, bi, si = Hh.load_case("cfg1_scaled")
+    model, crit = Hh.build_modules(d, mp, cp, "f32")
+    plain = Hh.run_modules(model, crit, x, label, bi, si)
+    plain = {k: v.clone() for k, v in plain["grads"].items()}
+    params = list(crit.parameters()) + list(model.parameters())
+    bucket = GradBucket(params)
+    crit.sampleIndices = lambda B, W, S, device: (bi.to(device), si.to(device))
+    for rep in range(2):  # twice: zero() must really clear the bucket
+        bucket.zero()
+        c, z, _ = model(x.cuda(), label.cuda())
+        losses, acc = crit(c, z, label.cuda())
+        losses.sum().backward()
+        named = {**{f"crit.{k}": v for k, v in crit.named_parameters()}, **{f"model.{k}": v for k, v in model.named_parameters()}}
+        for k, p in named.items():
+            assert p.grad.data_ptr() >= bucket.flat.data_ptr() and p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.flat.numel() * 4
+            assert Hh.rel_err(p.grad, plain[k]) <= 1e-5, (k, rep)
+    bucket.detach()
