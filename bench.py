@@ -214,11 +214,16 @@ def algorithmic_work(B, bf16):
     w = {}
     # HBM-bound: bytes each launch must move once
     w["conv0_fwd"] = ("hbm", B * (WINDOW * 4 + L0 * H * es))
-    w["conv0_bwd"] = ("hbm", B * (WINDOW * 4 + L0 * H * es))
+    w["conv0_bwd_du"] = ("hbm", B * (WINDOW * 4 + 2 * L0 * H * es))
+    w["conv0_wgrad"] = ("hbm", B * (WINDOW * 4 + L0 * H * es))
+    w["cnorm_relu_fwd"] = ("hbm", sum(B * lo * H * es * 2 for lo in (1024, 512, 256, 128)) + B * 128 * H * 4)
+    w["cnorm_relu_bwd"] = ("hbm", sum(B * lo * H * es * 3 for lo in (1024, 512, 256, 128)))
     w["gru_rec_fwd"] = ("hbm", B * S * (3 * H * es + H * 4 + 5 * H * es) + 3 * H * H * 4)
     w["gru_rec_bwd"] = ("hbm", B * S * (2 * H * 4 + 4 * H * es + 6 * H * es) + 3 * H * H * 4)
     w["score_fwd"] = ("hbm", B * W * (K * H * es + N * 4 + K * (N + 1) * 4) + B * S * H * es)
     w["score_bwd"] = ("hbm", B * W * (2 * K * H * es + N * 4 + K * (N + 1) * 4) + B * S * H * (es + 4))
+    w["score_fwd_mma"] = ("hbm", B * W * (K * H * es + N * 4 + 3 * K * 4) + B * S * H * es)
+    w["score_bwd_mma"] = ("hbm", B * W * (2 * K * H * es + N * 4 + K * 4) + B * S * H * (es + 4))
     # tensor-bound: FLOPs per step summed over that kernel's launches (reported per launch by dividing)
     conv = [(1024, 8), (512, 4), (256, 4), (128, 4)]
     f_nt = sum(2.0 * B * lo * H * k * H for lo, k in conv)            # conv1-4 forward
@@ -349,8 +354,8 @@ def run_ours(a):
             ent = {"launches_per_step": cnt / nst, "ms_per_step": round(tot / nst, 4)}
             if k in work:
                 kind, amount = work[k]
-                if kind == "hbm":
-                    ach = amount / (tot / cnt * 1e-3) / 1e9
+                if kind == "hbm":  # `amount` = bytes of all launches of this kernel in one step
+                    ach = amount / (tot / nst * 1e-3) / 1e9
                     ent.update(bound="hbm", achieved_gbs=round(ach, 1), frac=round(ach / pk["hbm"], 4))
                 else:
                     ach = amount / (tot / nst * 1e-3) / 1e12

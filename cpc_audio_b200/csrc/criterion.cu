@@ -15,6 +15,13 @@ int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowVie
 template <class T> int launch_cast(const float* src, T* dst, long long n, cudaStream_t st);
 template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st);
 
+bool score_mma_supported(int H, int K, int N);
+int score_transpose_ext(const int* ext, int* ext_t, int B, int N, int W, cudaStream_t st);
+int score_fwd_mma(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf, float* corrbuf, float* lsebuf, int B, int S,
+                  int W, int H, int K, int N, cudaStream_t st);
+int score_bwd_mma(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred,
+                  float* dz, int B, int S, int W, int H, int K, int N, cudaStream_t st);
+
 namespace {
 
 constexpr int KMAX = 16;
@@ -189,14 +196,21 @@ __global__ void score_bwd_kernel(const T* __restrict__ pred, const T* __restrict
   }
 }
 
-struct CritLayout { size_t pred, logits, total; };
+struct CritLayout { size_t pred, logits, lse, ext_t, total; bool mma; };
 CritLayout crit_layout(const Geo& g) {
   CritLayout l{};
   const size_t es = g.bf16 ? 2 : 4;
   const size_t P = (size_t)g.B * g.W;
+  l.mma = g.bf16 && score_mma_supported(g.H, g.K, g.N);
   l.pred = 0;
   l.logits = align_up(P * g.K * g.H * es);
-  l.total = l.logits + align_up(P * g.K * (g.N + 1) * 4);
+  if (!l.mma) {  // CUDA-core scoring keeps the logits for its backward
+    l.total = l.logits + align_up(P * g.K * (g.N + 1) * 4);
+  } else {       // tensor-core scoring recomputes them: only lse per (p, k) and the transposed indices are kept
+    l.lse = l.logits;
+    l.ext_t = l.lse + align_up(P * g.K * 4);
+    l.total = l.ext_t + align_up(P * g.N * 4);
+  }
   return l;
 }
 
@@ -230,6 +244,17 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
   OutView C{pred, (long long)W * K * H, (long long)K * H, W, 0, W, 0};
   CPC_TRY(gemm_nt(g.bf16, false, B, K * H, Har, A, wp, nullptr, C, st));
   // scoring + CE
+  if constexpr (!isf) {
+    if (lay.mma) {
+      float* lse = reinterpret_cast<float*>(sv + lay.lse);
+      int* ext_t = reinterpret_cast<int*>(sv + lay.ext_t);
+      CPC_TRY(score_transpose_ext(ext, ext_t, B, N, W, st));
+      CPC_TRY(score_fwd_mma(pred, zp, ext_t, lossbuf, corrbuf, lse, B, S, W, H, K, N, st));
+      mean_over_positions_kernel<<<K, 256, 0, st>>>(lossbuf, corrbuf, losses, acc, P, K);
+      CPC_LAUNCHED_N("mean_over_positions", st);
+      return 0;
+    }
+  }
   int threads = ((N + K + 31) / 32) * 32;
   if (threads < 64) threads = 64;
   if (threads > 1024) return fail(CPCB200_ERR_UNSUPPORTED, "criterion: N + K = %d > 1024", N + K);
@@ -269,7 +294,16 @@ int criterion_bwd_t(const Geo& g, const float* c, const float* z, const float* w
   CPC_CHECK_CUDA(cudaMemsetAsync(dz, 0, (size_t)B * S * H * sizeof(float), st));
   CPC_CHECK_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * S * Har * sizeof(float), st));
   CPC_CHECK_CUDA(cudaMemsetAsync(dw_pred, 0, (size_t)K * H * Har * sizeof(float), st));
-  {
+  bool done = false;
+  if constexpr (!isf) {
+    if (lay.mma) {
+      const float* lse = reinterpret_cast<const float*>(sv + lay.lse);
+      const int* ext_t = reinterpret_cast<const int*>(sv + lay.ext_t);
+      CPC_TRY(score_bwd_mma(pred, zp, ext_t, lse, dlosses, dpred, dz, B, S, W, H, K, N, st));
+      done = true;
+    }
+  }
+  if (!done) {
     int threads = H < 1024 ? H : 1024;
     const size_t smem = (size_t)(N + 1) * KMAX * sizeof(float) + (size_t)N * sizeof(int);
     CPC_CHECK_CUDA(cudaFuncSetAttribute(score_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

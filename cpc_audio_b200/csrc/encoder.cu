@@ -62,173 +62,235 @@ __device__ __forceinline__ void row_stats(const float (&u)[I][4], int H, int lan
 
 // ---------------------------------------------------------------------------------------------------------
 // conv0 + ChannelNorm + ReLU  (model.py:100).  x (B, L) fp32 -> y0 (B, Lp0, H) T.
+// One warp per chunk of kC0Chunk consecutive frames of one window: the lane's 4*I x 10 weights live in registers,
+// the 10-sample input window slides by 5 samples per frame (5 broadcast loads), stores are channel-last vectors.
 // ---------------------------------------------------------------------------------------------------------
-template <int I, class T>
-__global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                         const float* __restrict__ bias, const float* __restrict__ gam,
-                                                         const float* __restrict__ bet, T* __restrict__ y, int B, int L,
-                                                         int L0, int H) {
-  extern __shared__ __align__(16) float sm[];
-  float* ws = sm;            // [10][H]  tap-major so that a lane's float4 is conflict-free
-  float* bs = sm + 10 * H;   // bias, gamma, beta: [3][H]
-  for (int i = threadIdx.x; i < 10 * H; i += blockDim.x) { int tap = i / H, c = i - tap * H; ws[i] = w[c * 10 + tap]; }
-  for (int i = threadIdx.x; i < H; i += blockDim.x) { bs[i] = bias[i]; bs[H + i] = gam[i]; bs[2 * H + i] = bet[i]; }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const long long Lp0 = L0 + 2 * kPad;
-  const long long rows = (long long)B * L0;
-  for (long long r = warp; r < rows; r += nwarps) {
-    const int b = (int)(r / L0), t = (int)(r - (long long)b * L0);
-    const float* xb = x + (long long)b * L;
-    float xs[10];
-    const int s0 = 5 * t - 3;
+constexpr int kC0Chunk = 32;  // L0 = L/5 is a multiple of 32 because L is a multiple of 160
+
+template <int I>
+__device__ __forceinline__ void conv0_load_w(const float* __restrict__ w, int H, int lane, float (&wr)[I][4][10]) {
 #pragma unroll
-    for (int j = 0; j < 10; j++) { int s = s0 + j; xs[j] = (s >= 0 && s < L) ? __ldg(xb + s) : 0.f; }
-    float u[I][4];
+  for (int i = 0; i < I; i++) {
+    const int c = 4 * (lane + 32 * i);
 #pragma unroll
-    for (int i = 0; i < I; i++) {
-      int c = 4 * (lane + 32 * i);
-      if (c < H) {
-        float4 a = *reinterpret_cast<const float4*>(bs + c);
-        u[i][0] = a.x; u[i][1] = a.y; u[i][2] = a.z; u[i][3] = a.w;
+    for (int j = 0; j < 4; j++)
 #pragma unroll
-        for (int j = 0; j < 10; j++) {
-          float4 wv = *reinterpret_cast<const float4*>(ws + j * H + c);
-          u[i][0] = fmaf(wv.x, xs[j], u[i][0]); u[i][1] = fmaf(wv.y, xs[j], u[i][1]);
-          u[i][2] = fmaf(wv.z, xs[j], u[i][2]); u[i][3] = fmaf(wv.w, xs[j], u[i][3]);
-        }
-      } else { u[i][0] = u[i][1] = u[i][2] = u[i][3] = 0.f; }
-    }
-    float mean, rstd;
-    row_stats<I>(u, H, lane, mean, rstd);
-#pragma unroll
-    for (int i = 0; i < I; i++) {
-      int c = 4 * (lane + 32 * i);
-      if (c < H) {
-        float4 g4 = *reinterpret_cast<const float4*>(bs + H + c);
-        float4 b4 = *reinterpret_cast<const float4*>(bs + 2 * H + c);
-        float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) u[i][j] = fmaxf(fmaf((u[i][j] - mean) * rstd, g[j], be[j]), 0.f);
-      }
-    }
-    row_store<I>(y + ((long long)b * Lp0 + kPad + t) * H, H, lane, u);
+      for (int k = 0; k < 10; k++) wr[i][j][k] = (c < H) ? __ldg(w + (c + j) * 10 + k) : 0.f;
   }
 }
 
-// conv0 backward: recompute u, ChannelNorm+ReLU backward, accumulate dW0 (H,1,10), db0, dgamma0, dbeta0.
+template <int I>
+__device__ __forceinline__ void conv0_row(const float (&wr)[I][4][10], const float* __restrict__ bsm, const float (&xs)[10],
+                                          int H, int lane, float (&u)[I][4]) {
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    const int c = 4 * (lane + 32 * i);
+    if (c < H) {
+      float4 a = *reinterpret_cast<const float4*>(bsm + c);
+      u[i][0] = a.x; u[i][1] = a.y; u[i][2] = a.z; u[i][3] = a.w;
+#pragma unroll
+      for (int k = 0; k < 10; k++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) u[i][j] = fmaf(wr[i][j][k], xs[k], u[i][j]);
+      }
+    } else { u[i][0] = u[i][1] = u[i][2] = u[i][3] = 0.f; }
+  }
+}
+
+// sliding 10-sample window of frame t: samples 5t-3 .. 5t+6 (zero outside [0, L))
+__device__ __forceinline__ void conv0_window_init(const float* __restrict__ xb, int L, int t, float (&xs)[10]) {
+  const int s0 = 5 * t - 3;
+#pragma unroll
+  for (int j = 0; j < 10; j++) { const int s = s0 + j; xs[j] = (s >= 0 && s < L) ? __ldg(xb + s) : 0.f; }
+}
+__device__ __forceinline__ void conv0_window_next(const float* __restrict__ xb, int L, int t_next, float (&xs)[10]) {
+#pragma unroll
+  for (int j = 0; j < 5; j++) xs[j] = xs[j + 5];
+  const int s0 = 5 * t_next + 2;
+#pragma unroll
+  for (int j = 0; j < 5; j++) { const int s = s0 + j; xs[5 + j] = (s < L) ? __ldg(xb + s) : 0.f; }
+}
+
 template <int I, class T>
-__global__ void __launch_bounds__(256) conv0_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) conv0_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const float* __restrict__ gam,
-                                                         const float* __restrict__ bet, const T* __restrict__ dy,
-                                                         float* __restrict__ dw, float* __restrict__ dbias,
-                                                         float* __restrict__ dgam, float* __restrict__ dbet, int B, int L,
+                                                         const float* __restrict__ bet, T* __restrict__ y, int B, int L,
                                                          int L0, int H) {
-  extern __shared__ __align__(16) float sm[];
-  float* ws = sm;                 // [10][H]
-  float* bs = sm + 10 * H;        // [3][H]
-  float* accs = sm + 13 * H;      // [13][H] block accumulators: 10 taps, dbias, dgamma, dbeta
-  for (int i = threadIdx.x; i < 10 * H; i += blockDim.x) { int tap = i / H, c = i - tap * H; ws[i] = w[c * 10 + tap]; }
-  for (int i = threadIdx.x; i < H; i += blockDim.x) { bs[i] = bias[i]; bs[H + i] = gam[i]; bs[2 * H + i] = bet[i]; }
-  for (int i = threadIdx.x; i < 13 * H; i += blockDim.x) accs[i] = 0.f;
+  extern __shared__ __align__(16) float sm[];  // bias, gamma, beta: [3][H]
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { sm[i] = bias[i]; sm[H + i] = gam[i]; sm[2 * H + i] = bet[i]; }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const long long rows = (long long)B * L0;
-  float aw[I][10][4], ab[I][4], ag[I][4], abe[I][4];
+  float wr[I][4][10];
+  conv0_load_w<I>(w, H, lane, wr);
+  const int cpw = L0 / kC0Chunk;  // chunks per window
+  const long long Lp0 = L0 + 2 * kPad;
+  for (int ch = warp; ch < B * cpw; ch += nwarps) {
+    const int b = ch / cpw, t0 = (ch - b * cpw) * kC0Chunk;
+    const float* xb = x + (long long)b * L;
+    float xs[10];
+    conv0_window_init(xb, L, t0, xs);
+    T* yrow = y + ((long long)b * Lp0 + kPad + t0) * H;
+#pragma unroll 1
+    for (int tt = 0; tt < kC0Chunk; tt++) {
+      float u[I][4];
+      conv0_row<I>(wr, sm, xs, H, lane, u);
+      if (tt + 1 < kC0Chunk) conv0_window_next(xb, L, t0 + tt + 1, xs);
+      float mean, rstd;
+      row_stats<I>(u, H, lane, mean, rstd);
+#pragma unroll
+      for (int i = 0; i < I; i++) {
+        const int c = 4 * (lane + 32 * i);
+        if (c < H) {
+          float4 g4 = *reinterpret_cast<const float4*>(sm + H + c);
+          float4 b4 = *reinterpret_cast<const float4*>(sm + 2 * H + c);
+          float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) u[i][j] = fmaxf(fmaf((u[i][j] - mean) * rstd, g[j], be[j]), 0.f);
+        }
+      }
+      row_store<I>(yrow + (long long)tt * H, H, lane, u);
+    }
+  }
+}
+
+// conv0 backward, part 1: recompute u from x, ChannelNorm+ReLU backward in place (dy0 -> du0, same buffer),
+// accumulate dbias0, dgamma0, dbeta0.
+template <int I, class T>
+__global__ void __launch_bounds__(128) conv0_bwd_du_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, const float* __restrict__ gam,
+                                                            const float* __restrict__ bet, T* __restrict__ dy,
+                                                            float* __restrict__ dbias, float* __restrict__ dgam,
+                                                            float* __restrict__ dbet, int B, int L, int L0, int H) {
+  extern __shared__ __align__(16) float sm[];  // [3][H] params + [3][H] accumulators
+  float* accs = sm + 3 * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { sm[i] = bias[i]; sm[H + i] = gam[i]; sm[2 * H + i] = bet[i]; }
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) accs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float wr[I][4][10];
+  conv0_load_w<I>(w, H, lane, wr);
+  float ab[I][4], ag[I][4], abe[I][4];
 #pragma unroll
   for (int i = 0; i < I; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      ab[i][j] = ag[i][j] = abe[i][j] = 0.f;
-#pragma unroll
-      for (int k = 0; k < 10; k++) aw[i][k][j] = 0.f;
-    }
-  for (long long r = warp; r < rows; r += nwarps) {
-    const int b = (int)(r / L0), t = (int)(r - (long long)b * L0);
+    for (int j = 0; j < 4; j++) ab[i][j] = ag[i][j] = abe[i][j] = 0.f;
+  const int cpw = L0 / kC0Chunk;
+  for (int ch = warp; ch < B * cpw; ch += nwarps) {
+    const int b = ch / cpw, t0 = (ch - b * cpw) * kC0Chunk;
     const float* xb = x + (long long)b * L;
     float xs[10];
-    const int s0 = 5 * t - 3;
+    conv0_window_init(xb, L, t0, xs);
+    T* drow = dy + ((long long)b * L0 + t0) * H;
+#pragma unroll 1
+    for (int tt = 0; tt < kC0Chunk; tt++) {
+      float u[I][4], d[I][4];
+      row_load<I>(drow + (long long)tt * H, H, lane, d);
+      conv0_row<I>(wr, sm, xs, H, lane, u);
+      if (tt + 1 < kC0Chunk) conv0_window_next(xb, L, t0 + tt + 1, xs);
+      float mean, rstd;
+      row_stats<I>(u, H, lane, mean, rstd);
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 10; j++) { int s = s0 + j; xs[j] = (s >= 0 && s < L) ? __ldg(xb + s) : 0.f; }
-    float u[I][4], d[I][4];
-    row_load<I>(dy + r * H, H, lane, d);
+      for (int i = 0; i < I; i++) {
+        const int c = 4 * (lane + 32 * i);
+        if (c < H) {
+          float4 g4 = *reinterpret_cast<const float4*>(sm + H + c);
+          float4 b4 = *reinterpret_cast<const float4*>(sm + 2 * H + c);
+          float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-    for (int i = 0; i < I; i++) {
-      int c = 4 * (lane + 32 * i);
-      if (c < H) {
-        float4 a = *reinterpret_cast<const float4*>(bs + c);
-        u[i][0] = a.x; u[i][1] = a.y; u[i][2] = a.z; u[i][3] = a.w;
-#pragma unroll
-        for (int j = 0; j < 10; j++) {
-          float4 wv = *reinterpret_cast<const float4*>(ws + j * H + c);
-          u[i][0] = fmaf(wv.x, xs[j], u[i][0]); u[i][1] = fmaf(wv.y, xs[j], u[i][1]);
-          u[i][2] = fmaf(wv.z, xs[j], u[i][2]); u[i][3] = fmaf(wv.w, xs[j], u[i][3]);
-        }
-      } else { u[i][0] = u[i][1] = u[i][2] = u[i][3] = 0.f; }
-    }
-    float mean, rstd;
-    row_stats<I>(u, H, lane, mean, rstd);
-    // u <- xhat ; d <- dxhat ; accumulate dgamma, dbeta
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < I; i++) {
-      int c = 4 * (lane + 32 * i);
-      if (c < H) {
-        float4 g4 = *reinterpret_cast<const float4*>(bs + H + c);
-        float4 b4 = *reinterpret_cast<const float4*>(bs + 2 * H + c);
-        float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          float xh = (u[i][j] - mean) * rstd;
-          float v = fmaf(xh, g[j], be[j]);
-          float dv = v > 0.f ? d[i][j] : 0.f;
-          ag[i][j] = fmaf(dv, xh, ag[i][j]);
-          abe[i][j] += dv;
-          float dx = dv * g[j];
-          u[i][j] = xh; d[i][j] = dx;
-          s1 += dx; s2 = fmaf(dx, xh, s2);
+          for (int j = 0; j < 4; j++) {
+            const float xh = (u[i][j] - mean) * rstd;
+            const float v = fmaf(xh, g[j], be[j]);
+            const float dv = v > 0.f ? d[i][j] : 0.f;
+            ag[i][j] = fmaf(dv, xh, ag[i][j]);
+            abe[i][j] += dv;
+            const float dx = dv * g[j];
+            u[i][j] = xh; d[i][j] = dx;
+            s1 += dx; s2 = fmaf(dx, xh, s2);
+          }
         }
       }
-    }
-    s1 = warp_sum(s1) / (float)H;
-    s2 = warp_sum(s2) / (float)(H - 1);
+      s1 = warp_sum(s1) / (float)H;
+      s2 = warp_sum(s2) / (float)(H - 1);
 #pragma unroll
-    for (int i = 0; i < I; i++) {
-      int c = 4 * (lane + 32 * i);
-      if (c < H) {
+      for (int i = 0; i < I; i++) {
+        if (4 * (lane + 32 * i) < H) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          float du = rstd * (d[i][j] - s1 - u[i][j] * s2);
-          ab[i][j] += du;
-#pragma unroll
-          for (int k = 0; k < 10; k++) aw[i][k][j] = fmaf(du, xs[k], aw[i][k][j]);
+          for (int j = 0; j < 4; j++) { const float o = rstd * (d[i][j] - s1 - u[i][j] * s2); ab[i][j] += o; d[i][j] = o; }
         }
       }
+      row_store<I>(drow + (long long)tt * H, H, lane, d);
     }
   }
 #pragma unroll
   for (int i = 0; i < I; i++) {
-    int c = 4 * (lane + 32 * i);
+    const int c = 4 * (lane + 32 * i);
     if (c < H) {
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-#pragma unroll
-        for (int k = 0; k < 10; k++) atomicAdd(&accs[k * H + c + j], aw[i][k][j]);
-        atomicAdd(&accs[10 * H + c + j], ab[i][j]);
-        atomicAdd(&accs[11 * H + c + j], ag[i][j]);
-        atomicAdd(&accs[12 * H + c + j], abe[i][j]);
+        atomicAdd(&accs[c + j], ab[i][j]); atomicAdd(&accs[H + c + j], ag[i][j]); atomicAdd(&accs[2 * H + c + j], abe[i][j]);
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 10 * H; i += blockDim.x) { int tap = i / H, c = i - tap * H; atomicAdd(dw + c * 10 + tap, accs[i]); }
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    atomicAdd(dbias + i, accs[10 * H + i]); atomicAdd(dgam + i, accs[11 * H + i]); atomicAdd(dbet + i, accs[12 * H + i]);
+    atomicAdd(dbias + i, accs[i]); atomicAdd(dgam + i, accs[H + i]); atomicAdd(dbet + i, accs[2 * H + i]);
   }
+}
+
+// conv0 backward, part 2: dW0[c][tap] += sum_{b,t} du0[b,t,c] * x[b, 5t-3+tap]
+template <int I, class T>
+__global__ void __launch_bounds__(128) conv0_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ du,
+                                                           float* __restrict__ dw, int B, int L, int L0, int H) {
+  extern __shared__ __align__(16) float accs[];  // [10][H]
+  for (int i = threadIdx.x; i < 10 * H; i += blockDim.x) accs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float aw[I][4][10];
+#pragma unroll
+  for (int i = 0; i < I; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int k = 0; k < 10; k++) aw[i][j][k] = 0.f;
+  const int cpw = L0 / kC0Chunk;
+  for (int ch = warp; ch < B * cpw; ch += nwarps) {
+    const int b = ch / cpw, t0 = (ch - b * cpw) * kC0Chunk;
+    const float* xb = x + (long long)b * L;
+    float xs[10];
+    conv0_window_init(xb, L, t0, xs);
+    const T* drow = du + ((long long)b * L0 + t0) * H;
+#pragma unroll 2
+    for (int tt = 0; tt < kC0Chunk; tt++) {
+      float d[I][4];
+      row_load<I>(drow + (long long)tt * H, H, lane, d);
+#pragma unroll
+      for (int i = 0; i < I; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int k = 0; k < 10; k++) aw[i][j][k] = fmaf(d[i][j], xs[k], aw[i][j][k]);
+      if (tt + 1 < kC0Chunk) conv0_window_next(xb, L, t0 + tt + 1, xs);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    const int c = 4 * (lane + 32 * i);
+    if (c < H) {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < 10; k++) atomicAdd(&accs[k * H + c + j], aw[i][j][k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 10 * H; i += blockDim.x) { const int tap = i / H, c = i - tap * H; atomicAdd(dw + c * 10 + tap, accs[i]); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -410,10 +472,11 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   }
   const int I = ilog_I(H);
   {
-    const size_t smem = 13 * (size_t)H * sizeof(float);
-    const int blocks = 148 * 4;
+    const size_t smem = 3 * (size_t)H * sizeof(float);
+    int blocks = (B * (g.Lout[0] / kC0Chunk) + 3) / 4;
+    if (blocks > 148 * 8) blocks = 148 * 8;
 #define LAUNCH_C0(II)                                                                                             \
-  conv0_fwd_kernel<II, T><<<blocks, 256, smem, st>>>(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0],   \
+  conv0_fwd_kernel<II, T><<<blocks, 128, smem, st>>>(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0],   \
                                                      sv + e.y[0], B, g.L, g.Lout[0], H)
     if (I == 1) LAUNCH_C0(1); else if (I == 2) LAUNCH_C0(2); else if (I == 3) LAUNCH_C0(3); else LAUNCH_C0(4);
 #undef LAUNCH_C0
@@ -490,15 +553,20 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     }
   }
   {
-    const size_t smem = 26 * (size_t)H * sizeof(float);
-    const int blocks = 148 * 2;
+    int blocks = (B * (g.Lout[0] / kC0Chunk) + 3) / 4;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const size_t smem1 = 6 * (size_t)H * sizeof(float), smem2 = 10 * (size_t)H * sizeof(float);
 #define LAUNCH_C0B(II)                                                                                              \
-  conv0_bwd_kernel<II, T><<<blocks, 256, smem, st>>>(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0],    \
-                                                     dy[0], gr->conv_w[0], gr->conv_b[0], gr->norm_w[0],           \
-                                                     gr->norm_b[0], B, g.L, g.Lout[0], H)
+  conv0_bwd_du_kernel<II, T><<<blocks, 128, smem1, st>>>(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0], \
+                                                         dy[0], gr->conv_b[0], gr->norm_w[0], gr->norm_b[0], B, g.L, \
+                                                         g.Lout[0], H)
     if (I == 1) LAUNCH_C0B(1); else if (I == 2) LAUNCH_C0B(2); else if (I == 3) LAUNCH_C0B(3); else LAUNCH_C0B(4);
 #undef LAUNCH_C0B
-    CPC_LAUNCHED_N("conv0_bwd", st);
+    CPC_LAUNCHED_N("conv0_bwd_du", st);
+#define LAUNCH_C0W(II) conv0_wgrad_kernel<II, T><<<blocks, 128, smem2, st>>>(x, dy[0], gr->conv_w[0], B, g.L, g.Lout[0], H)
+    if (I == 1) LAUNCH_C0W(1); else if (I == 2) LAUNCH_C0W(2); else if (I == 3) LAUNCH_C0W(3); else LAUNCH_C0W(4);
+#undef LAUNCH_C0W
+    CPC_LAUNCHED_N("conv0_wgrad", st);
   }
   return 0;
 }

@@ -1,0 +1,452 @@
+// score_mma.cu - tensor-core scoring + InfoNCE for the bf16 path (reference: criterion.py:115-117, 207-217, 245-257).
+//
+// One WARP per anchor position p = (b, w), persistent over positions.  Per position the candidates are the N
+// negatives z[ext[b, :, w]] (gathered row by row with cp.async, 512 B per instruction, double-buffered in chunks
+// of 32 rows) followed by the K positives z[b, w+1 .. w+K] (contiguous rows).  All contractions run on
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32):
+//   forward : logits[j][k] = cand_j . pred_k / H        M = candidates, N = heads (padded to 16), K = H
+//             softmax / cross-entropy / argmax in the accumulator registers (reduction over candidates =
+//             in-thread + 3 shuffles), nothing but (loss, correct, lse) per (p, k) leaves the SM.
+//   backward: logits recomputed per chunk, G = (softmax - onehot) * dloss/(P*H) formed in registers;
+//             dz[cand_j] += G^T . pred   (A operand = the logits accumulator fragments themselves) staged in
+//                           shared memory and added to HBM by the TMA engine (cp.reduce.async.bulk .add.f32,
+//                           one 1 KB row per instruction) instead of per-lane atomics;
+//             dpred      += G . cand     accumulated over chunks in registers.
+// The kernel is bound by the L2 gather (N x 512 B per position) and the scatter-add, not by the tensor pipe.
+#include "common.cuh"
+
+namespace cpcb200 {
+
+namespace {
+
+constexpr int CH = 32;    // candidate rows per gather chunk (2 m-tiles)
+constexpr int NNEG = 4;   // negative chunks per position: the tensor-core path is specialised for N = 128
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// TMA-engine reduction: global[dst .. dst+bytes) += shared[src .. src+bytes)   (fp32 add)
+__device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// (P, N) <- (B, N, W): a position's N negative rows become contiguous
+__global__ void transpose_ext_kernel(const int* __restrict__ ext, int* __restrict__ ext_t, int B, int N, int W) {
+  const long long n = (long long)B * N * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % N);
+    const long long pw = i / N;
+    const int w = (int)(pw % W), b = (int)(pw / W);
+    ext_t[i] = ext[((long long)b * N + j) * W + w];
+  }
+}
+
+template <int H> struct Cfg {
+  static constexpr int RS = 2 * H + 16;        // bytes per staged row (16 B pad: conflict-free ldmatrix)
+  static constexpr int SEGS = H / 8;           // 16-B segments per row
+  static constexpr int KS = H / 16;            // k-steps over the feature dim
+  static constexpr int PSM = 16 * RS;          // pred tile [16 heads][H]
+  static constexpr int CBUF = CH * RS;         // one candidate chunk
+};
+
+// stage pred[p] (K x H bf16, contiguous) into psm[16][RS]; rows >= K stay zero
+template <int H>
+__device__ __forceinline__ void stage_pred(unsigned char* psm, const bf16* __restrict__ pp, int K, int lane) {
+  constexpr int SEGS = Cfg<H>::SEGS, RS = Cfg<H>::RS;
+  for (int i = lane; i < K * SEGS; i += 32) {
+    const int k = i / SEGS, sg = i - k * SEGS;
+    cp_async16(s_u32(psm + k * RS + sg * 16), pp + (size_t)k * H + sg * 8);
+  }
+}
+// gather `rows` candidate rows (row index held by lane r) into buf
+template <int H>
+__device__ __forceinline__ void gather_rows(unsigned char* buf, const bf16* __restrict__ z, int my_row, int rows, int lane) {
+  constexpr int SEGS = Cfg<H>::SEGS, RS = Cfg<H>::RS;
+#pragma unroll 4
+  for (int it = 0; it < (CH * SEGS) / 32; it++) {
+    const int flat = it * 32 + lane;
+    const int r = flat / SEGS, sg = flat - r * SEGS;
+    const int row = __shfl_sync(0xffffffffu, my_row, r);
+    if (r < rows) cp_async16(s_u32(buf + r * RS + sg * 16), z + (size_t)row * H + sg * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(192) score_fwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
+                                                             const int* __restrict__ ext_t, float* __restrict__ lossbuf,
+                                                             float* __restrict__ corrbuf, float* __restrict__ lsebuf, int B,
+                                                             int S, int W, int K, int N, int warps_per_cta) {
+  using C = Cfg<H>;
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  unsigned char* psm = sm + (size_t)warp * (C::PSM + 2 * C::CBUF);
+  unsigned char* cbuf = psm + C::PSM;
+  for (int i = lane; i < C::PSM / 16; i += 32) reinterpret_cast<uint4*>(psm)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  const int P = B * W;
+  constexpr int nneg = NNEG;
+  constexpr int nchunks = nneg + 1;
+  const float invH = 1.f / (float)H;
+
+  for (int p = blockIdx.x * warps_per_cta + warp; p < P; p += gridDim.x * warps_per_cta) {
+    const int b = p / W, w = p - b * W;
+    stage_pred<H>(psm, pred + (size_t)p * K * H, K, lane);
+    {
+      const int row = ext_t[(size_t)p * N + lane];
+      gather_rows<H>(cbuf, z, row, CH, lane);
+    }
+    cp_async_commit();
+    uint32_t bfr[C::KS][4];
+    float acc[9][2][4];
+#pragma unroll
+    for (int m = 0; m < 9; m++)
+#pragma unroll
+      for (int n = 0; n < 2; n++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc[m][n][e] = 0.f;
+
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      if (c < nchunks) {
+        unsigned char* cur = cbuf + (c & 1) * C::CBUF;
+        if (c + 1 < nchunks) {
+          unsigned char* nxt = cbuf + ((c + 1) & 1) * C::CBUF;
+          if (c + 1 < nneg) {
+            const int row = ext_t[(size_t)p * N + (c + 1) * CH + lane];
+            gather_rows<H>(nxt, z, row, CH, lane);
+          } else {
+            const int row = b * S + w + 1 + (lane < K ? lane : 0);
+            gather_rows<H>(nxt, z, row, K, lane);
+            for (int i = lane; i < (16 - K) * (C::RS / 16); i += 32)  // rows K..15 of the positive tile: zeros
+              reinterpret_cast<uint4*>(nxt + K * C::RS)[i] = make_uint4(0, 0, 0, 0);
+          }
+          cp_async_commit();
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncwarp();
+        if (c == 0) {
+#pragma unroll
+          for (int ks = 0; ks < C::KS; ks++) {
+            const int mi = lane >> 3;
+            ldsm_x4(bfr[ks], s_u32(psm + ((mi >> 1) * 8 + (lane & 7)) * C::RS + (ks * 16 + (mi & 1) * 8) * 2));
+          }
+        }
+        const int mts = (c < nneg) ? 2 : 1;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          if (mt < mts) {
+            const int m = (c < nneg) ? (c * 2 + mt) : 8;
+            if (m < 9) {
+#pragma unroll
+              for (int ks = 0; ks < C::KS; ks++) {
+                uint32_t a[4];
+                const int mi = lane >> 3;
+                ldsm_x4(a, s_u32(cur + (mt * 16 + (mi & 1) * 8 + (lane & 7)) * C::RS + (ks * 16 + (mi >> 1) * 8) * 2));
+                mma16816(acc[m][0], a, bfr[ks][0], bfr[ks][1]);
+                mma16816(acc[m][1], a, bfr[ks][2], bfr[ks][3]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // ---- softmax / CE / argmax per head column (this thread: heads 8*nt + 2*t + e) ----
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int k = nt * 8 + 2 * t + e;
+        const float pos = __shfl_sync(0xffffffffu, acc[8][nt][2 * nt + e], (2 * t + e) * 4 + t) * invH;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int m = 0; m < 8; m++)
+          if (m < 2 * nneg) mx = fmaxf(mx, fmaxf(acc[m][nt][e], acc[m][nt][2 + e]));
+        mx *= invH;
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        const float M = fmaxf(mx, pos);
+        float sum = 0.f;
+#pragma unroll
+        for (int m = 0; m < 8; m++)
+          if (m < 2 * nneg) sum += __expf(acc[m][nt][e] * invH - M) + __expf(acc[m][nt][2 + e] * invH - M);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        sum += __expf(pos - M);
+        if (g == 0 && k < K) {
+          const float lse = M + __logf(sum);
+          lossbuf[(size_t)p * K + k] = lse - pos;
+          corrbuf[(size_t)p * K + k] = (pos >= mx) ? 1.f : 0.f;
+          lsebuf[(size_t)p * K + k] = lse;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(96) score_bwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
+                                                            const int* __restrict__ ext_t, const float* __restrict__ lsebuf,
+                                                            const float* __restrict__ dloss, bf16* __restrict__ dpred,
+                                                            float* __restrict__ dz, int B, int S, int W, int K, int N,
+                                                            int warps_per_cta) {
+  using C = Cfg<H>;
+  constexpr int GRS = (CH + 8) * 2;     // bytes per row of Gs[16 heads][32 cand]
+  constexpr int STG = 16 * H * 4;       // staging tile [16 rows][H] fp32
+  constexpr int PER_WARP = C::PSM + 2 * C::CBUF + 16 * GRS + STG;
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  unsigned char* psm = sm + (size_t)warp * PER_WARP;
+  unsigned char* cbuf = psm + C::PSM;
+  unsigned char* gs = cbuf + 2 * C::CBUF;
+  unsigned char* stg = gs + 16 * GRS;
+  for (int i = lane; i < C::PSM / 16; i += 32) reinterpret_cast<uint4*>(psm)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  const int P = B * W;
+  constexpr int nneg = NNEG;
+  constexpr int nchunks = nneg + 1;
+  const float invH = 1.f / (float)H;
+  const float gscale = 1.f / ((float)P * (float)H);
+
+  for (int p = blockIdx.x * warps_per_cta + warp; p < P; p += gridDim.x * warps_per_cta) {
+    const int b = p / W, w = p - b * W;
+    stage_pred<H>(psm, pred + (size_t)p * K * H, K, lane);
+    int my_row = ext_t[(size_t)p * N + lane];
+    gather_rows<H>(cbuf, z, my_row, CH, lane);
+    cp_async_commit();
+    float lse[2][2], gk[2][2];
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int k = nt * 8 + 2 * t + e;
+        lse[nt][e] = k < K ? lsebuf[(size_t)p * K + k] : 0.f;
+        gk[nt][e] = k < K ? dloss[k] * gscale : 0.f;
+      }
+    float d1[2 * C::KS][4];  // dpred accumulators: 16 heads x H
+#pragma unroll
+    for (int n = 0; n < 2 * C::KS; n++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) d1[n][e] = 0.f;
+
+    for (int c = 0; c < nchunks; c++) {
+      unsigned char* cur = cbuf + (c & 1) * C::CBUF;
+      const int cur_row = my_row;
+      if (c + 1 < nchunks) {
+        unsigned char* nxt = cbuf + ((c + 1) & 1) * C::CBUF;
+        if (c + 1 < nneg) {
+          my_row = ext_t[(size_t)p * N + (c + 1) * CH + lane];
+          gather_rows<H>(nxt, z, my_row, CH, lane);
+        } else {
+          my_row = b * S + w + 1 + (lane < K ? lane : 0);
+          gather_rows<H>(nxt, z, my_row, K, lane);
+          for (int i = lane; i < (16 - K) * (C::RS / 16); i += 32)
+            reinterpret_cast<uint4*>(nxt + K * C::RS)[i] = make_uint4(0, 0, 0, 0);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      const bool is_pos = c >= nneg;
+      const int mts = is_pos ? 1 : 2;
+      // ---- logits of this chunk: L[mt][nt] ----
+      float L[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int n = 0; n < 2; n++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) L[mt][n][e] = 0.f;
+#pragma unroll 4
+      for (int ks = 0; ks < C::KS; ks++) {
+        uint32_t bq[4];
+        const int mi = lane >> 3;
+        ldsm_x4(bq, s_u32(psm + ((mi >> 1) * 8 + (lane & 7)) * C::RS + (ks * 16 + (mi & 1) * 8) * 2));
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          if (mt < mts) {
+            uint32_t a[4];
+            ldsm_x4(a, s_u32(cur + (mt * 16 + (mi & 1) * 8 + (lane & 7)) * C::RS + (ks * 16 + (mi >> 1) * 8) * 2));
+            mma16816(L[mt][0], a, bq[0], bq[1]);
+            mma16816(L[mt][1], a, bq[2], bq[3]);
+          }
+        }
+      }
+      // ---- G = (softmax - onehot) * dloss / (P*H); A fragments for dz and Gs[k][j] for dpred ----
+      uint32_t ga[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        float G[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int ce = e & 1;
+            const int k = nt * 8 + 2 * t + ce;
+            const int j = g + (e >> 1) * 8;  // row inside the m-tile
+            float v = 0.f;
+            if (mt < mts && k < K) {
+              const float pr = __expf(L[mt][nt][e] * invH - lse[nt][ce]);
+              if (!is_pos) v = pr * gk[nt][ce];
+              else v = (j == k) ? (pr - 1.f) * gk[nt][ce] : 0.f;
+            }
+            G[nt][e] = v;
+            *reinterpret_cast<bf16*>(gs + k * GRS + (mt * 16 + j) * 2) = __float2bfloat16_rn(v);
+          }
+        ga[mt][0] = pack_bf16(G[0][0], G[0][1]);
+        ga[mt][1] = pack_bf16(G[0][2], G[0][3]);
+        ga[mt][2] = pack_bf16(G[1][0], G[1][1]);
+        ga[mt][3] = pack_bf16(G[1][2], G[1][3]);
+      }
+      __syncwarp();
+      // ---- dz rows of this chunk: D2[16 j][H] = G^T . pred, staged then added to HBM by the TMA engine ----
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        if (mt < mts) {
+          if (lane < 16) bulk_wait_read0();  // the staging tile is free again
+          __syncwarp();
+#pragma unroll 4
+          for (int np = 0; np < C::KS; np++) {
+            uint32_t bq[4];
+            const int mi = lane >> 3;
+            ldsm_x4_t(bq, s_u32(psm + ((mi & 1) * 8 + (lane & 7)) * C::RS + (np * 16 + (mi >> 1) * 8) * 2));
+            float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(o0, ga[mt], bq[0], bq[1]);
+            mma16816(o1, ga[mt], bq[2], bq[3]);
+            float* r0 = reinterpret_cast<float*>(stg) + (size_t)g * H + np * 16 + 2 * t;
+            float* r1 = r0 + 8 * H;
+            *reinterpret_cast<float2*>(r0) = make_float2(o0[0], o0[1]);
+            *reinterpret_cast<float2*>(r1) = make_float2(o0[2], o0[3]);
+            *reinterpret_cast<float2*>(r0 + 8) = make_float2(o1[0], o1[1]);
+            *reinterpret_cast<float2*>(r1 + 8) = make_float2(o1[2], o1[3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          const int drow = __shfl_sync(0xffffffffu, cur_row, (mt * 16 + lane) & 31);
+          if (lane < 16 && (!is_pos || lane < K)) {
+            bulk_reduce_add_f32(dz + (size_t)drow * H, s_u32(stg + (size_t)lane * H * 4), H * 4);
+            bulk_commit();
+          }
+        }
+      }
+      // ---- dpred += G . cand ----
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) {
+        if (ks < mts) {
+          uint32_t a[4];
+          const int mi = lane >> 3;
+          ldsm_x4(a, s_u32(gs + ((mi & 1) * 8 + (lane & 7)) * GRS + (ks * 16 + (mi >> 1) * 8) * 2));
+#pragma unroll
+          for (int np = 0; np < C::KS; np++) {
+            uint32_t bq[4];
+            ldsm_x4_t(bq, s_u32(cur + (ks * 16 + (mi & 1) * 8 + (lane & 7)) * C::RS + (np * 16 + (mi >> 1) * 8) * 2));
+            mma16816(d1[2 * np], a, bq[0], bq[1]);
+            mma16816(d1[2 * np + 1], a, bq[2], bq[3]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- dpred[p][k][d] (bf16) ----
+    bf16* dp = dpred + (size_t)p * K * H;
+#pragma unroll
+    for (int n = 0; n < 2 * C::KS; n++) {
+      const int d = n * 8 + 2 * t;
+      if (g < K) *reinterpret_cast<uint32_t*>(dp + (size_t)g * H + d) = pack_bf16(d1[n][0], d1[n][1]);
+      if (g + 8 < K) *reinterpret_cast<uint32_t*>(dp + (size_t)(g + 8) * H + d) = pack_bf16(d1[n][2], d1[n][3]);
+    }
+  }
+  if (lane < 16) bulk_wait0();
+}
+
+template <int H> constexpr size_t fwd_warp_smem() { return Cfg<H>::PSM + 2 * Cfg<H>::CBUF; }
+template <int H> constexpr size_t bwd_warp_smem() { return Cfg<H>::PSM + 2 * Cfg<H>::CBUF + 16 * (CH + 8) * 2 + 16 * H * 4; }
+
+template <int H>
+int launch_fwd(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf, float* corrbuf, float* lsebuf, int B, int S,
+               int W, int K, int N, cudaStream_t st) {
+  int wpc = (int)((200 * 1024) / fwd_warp_smem<H>());
+  if (wpc > 6) wpc = 6;
+  const size_t smem = wpc * fwd_warp_smem<H>();
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(score_fwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  score_fwd_mma_kernel<H><<<148, wpc * 32, smem, st>>>(pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, wpc);
+  CPC_LAUNCHED_N("score_fwd_mma", st);
+  return 0;
+}
+template <int H>
+int launch_bwd(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred, float* dz,
+               int B, int S, int W, int K, int N, cudaStream_t st) {
+  int wpc = (int)((200 * 1024) / bwd_warp_smem<H>());
+  if (wpc > 3) wpc = 3;
+  const size_t smem = wpc * bwd_warp_smem<H>();
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(score_bwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  score_bwd_mma_kernel<H><<<148, wpc * 32, smem, st>>>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, wpc);
+  CPC_LAUNCHED_N("score_bwd_mma", st);
+  return 0;
+}
+
+}  // namespace
+
+bool score_mma_supported(int H, int K, int N) { return (H == 64 || H == 128 || H == 256) && K >= 1 && K <= 16 && N == NNEG * CH; }
+
+int score_transpose_ext(const int* ext, int* ext_t, int B, int N, int W, cudaStream_t st) {
+  const long long n = (long long)B * N * W;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  transpose_ext_kernel<<<blocks, 256, 0, st>>>(ext, ext_t, B, N, W);
+  CPC_LAUNCHED_N("transpose_ext", st);
+  return 0;
+}
+
+int score_fwd_mma(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf, float* corrbuf, float* lsebuf, int B, int S,
+                  int W, int H, int K, int N, cudaStream_t st) {
+  if (H == 256) return launch_fwd<256>(pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, st);
+  if (H == 128) return launch_fwd<128>(pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, st);
+  return launch_fwd<64>(pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, st);
+}
+int score_bwd_mma(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred,
+                  float* dz, int B, int S, int W, int H, int K, int N, cudaStream_t st) {
+  if (H == 256) return launch_bwd<256>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
+  if (H == 128) return launch_bwd<128>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
+  return launch_bwd<64>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
+}
+
+}  // namespace cpcb200
