@@ -18,6 +18,12 @@ int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A,
 int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode,
             int Ci, int taps, cudaStream_t st);
 
+bool gru_mma_supported(int Har);
+int gru_rec_fwd_mma(const bf16* gi, const float* w_hh, const float* b_hh, const float* h0, float* c, bf16* cT, bf16* sR, bf16* sU,
+                    bf16* sN, bf16* sHN, float* hT, int B, int S, int Har, cudaStream_t st);
+int gru_rec_bwd_mma(const float* dc, const float* c, const float* h0, const bf16* sR, const bf16* sU, const bf16* sN,
+                    const bf16* sHN, const float* w_hh, bf16* dgi, bf16* dgh, float* dh0, int B, int S, int Har, cudaStream_t st);
+
 namespace {
 
 constexpr int HC = 64;  // hidden units owned by one CTA of the cluster
@@ -381,8 +387,17 @@ int gru_fwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     const float* whh = p->w_hh[l];
     const float* bhh = p->b_hh[l];
     int Bv = B, Sv = S, Hv = Har;
-    void* args[] = {&gic, &whh, &bhh, &h0l, &cout, &cTo, &sR, &sU, &sN, &sHN, &hTl, &Bv, &Sv, &Hv};
-    CPC_TRY(launch_cluster("gru_rec_fwd", gru_rec_fwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, 3 * HC * 2, smem, st, args));
+    bool done = false;
+    if constexpr (!isf) {
+      if (gru_mma_supported(Har)) {  // tensor-core recurrence, W_hh slice resident in registers
+        CPC_TRY(gru_rec_fwd_mma(gic, whh, bhh, h0l, cout, cTo, sR, sU, sN, sHN, hTl, B, S, Har, st));
+        done = true;
+      }
+    }
+    if (!done) {
+      void* args[] = {&gic, &whh, &bhh, &h0l, &cout, &cTo, &sR, &sU, &sN, &sHN, &hTl, &Bv, &Sv, &Hv};
+      CPC_TRY(launch_cluster("gru_rec_fwd", gru_rec_fwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, 3 * HC * 2, smem, st, args));
+    }
   }
   return 0;
 }
@@ -422,8 +437,17 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     const float* whh = p->w_hh[l];
     float* dh0 = nullptr;
     int Bv = B, Sv = S, Hv = Har;
-    void* args[] = {&dcl, &cl, &h0l, &sR, &sU, &sN, &sHN, &whh, &dgi, &dgh, &dh0, &Bv, &Sv, &Hv};
-    CPC_TRY(launch_cluster("gru_rec_bwd", gru_rec_bwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, HC * 8, smem, st, args));
+    bool done = false;
+    if constexpr (!isf) {
+      if (gru_mma_supported(Har)) {
+        CPC_TRY(gru_rec_bwd_mma(dcl, cl, h0l, sR, sU, sN, sHN, whh, dgi, dgh, dh0, B, S, Har, st));
+        done = true;
+      }
+    }
+    if (!done) {
+      void* args[] = {&dcl, &cl, &h0l, &sR, &sU, &sN, &sHN, &whh, &dgi, &dgh, &dh0, &Bv, &Sv, &Hv};
+      CPC_TRY(launch_cluster("gru_rec_bwd", gru_rec_bwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, HC * 8, smem, st, args));
+    }
 
     CPC_TRY(launch_colsum<T>(dgi, gr->b_ih[l], (long long)B * S, G, st));
     CPC_TRY(launch_colsum<T>(dgh, gr->b_hh[l], (long long)B * S, G, st));
