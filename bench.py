@@ -220,6 +220,8 @@ def algorithmic_work(B, bf16):
     w["cnorm_relu_bwd"] = ("hbm", sum(B * lo * H * es * 3 for lo in (1024, 512, 256, 128)))
     w["gru_rec_fwd"] = ("hbm", B * S * (3 * H * es + H * 4 + 5 * H * es) + 3 * H * H * 4)
     w["gru_rec_bwd"] = ("hbm", B * S * (2 * H * 4 + 4 * H * es + 6 * H * es) + 3 * H * H * 4)
+    w["gru_rec_fwd_mma"] = w["gru_rec_fwd"]
+    w["gru_rec_bwd_mma"] = w["gru_rec_bwd"]
     w["score_fwd"] = ("hbm", B * W * (K * H * es + N * 4 + K * (N + 1) * 4) + B * S * H * es)
     w["score_bwd"] = ("hbm", B * W * (2 * K * H * es + N * 4 + K * (N + 1) * 4) + B * S * H * (es + 4))
     w["score_fwd_mma"] = ("hbm", B * W * (K * H * es + N * 4 + 3 * K * 4) + B * S * H * es)
@@ -233,6 +235,8 @@ def algorithmic_work(B, bf16):
     f_tn = sum(2.0 * B * lo * H * k * H for lo, k in conv) + 2.0 * B * S * 3 * H * H * 2 + 2.0 * B * W * K * H * H
     w["gemm_nt_tc"] = ("tensor", f_nt)
     w["gemm_tn_tc"] = ("tensor", f_tn)
+    w["gemm_nt_tc2"] = ("tensor", f_nt)
+    w["gemm_tn_tc2"] = ("tensor", f_tn)
     w["gemm_nt_simt"] = ("tensor", f_nt)
     w["gemm_tn_simt"] = ("tensor", f_tn)
     return w

@@ -12,6 +12,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (TMEM lane group = warp % 4).  One output tile per CTA, 2 CTAs per SM co-resident so
 // that one CTA's epilogue overlaps the other's main loop.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -295,6 +297,284 @@ __global__ void __launch_bounds__(NT_THREADS) gemm_tn_tc_kernel(const __grid_con
   if (warp == 1) ptx::tmem_dealloc(tmem_acc, BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// NT kernel, second generation: persistent, 128 x 256 tiles, the weight tile (B operand, identical for every
+// M tile) is loaded ONCE per cluster and multicast by TMA to the CM CTAs of the cluster (each CTA fetches
+// 256/CM rows), accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  L2->SM operand traffic per 128x256x64 block drops from 48 KB to 16 + 32/CM KB.
+// ---------------------------------------------------------------------------------------------------------
+template <int CM, class TO>
+__global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                     const __grid_constant__ CUtensorMap tmB, int nkb,
+                                                                     int chunks_per_tap, int s, int tiles_per_batch,
+                                                                     int m_tiles, int n_tiles, int nb,
+                                                                     const float* __restrict__ bias, OutView C) {
+  constexpr int BN2 = 256, STAGES = 4;
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN2 * BK * 2, B_SLICE = B_BYTES / CM;
+  constexpr uint16_t MASK = (uint16_t)((1u << CM) - 1);
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smA = sm;
+  unsigned char* smB = sm + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();
+  const int cluster_id = blockIdx.x / CM, num_clusters = gridDim.x / CM;
+  const int m_groups = (m_tiles + CM - 1) / CM;
+  const int total_groups = m_groups * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; i++) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], CM); }
+    for (int i = 0; i < 2; i++) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_holder, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int gid = cluster_id; gid < total_groups; gid += num_clusters) {
+        const int gm = gid / n_tiles, gn = gid - gm * n_tiles;
+        const int mt = gm * CM + rank;
+        const int b = mt < m_tiles ? mt / tiles_per_batch : nb;  // b == nb: out of bounds -> zero fill
+        const int t0 = (mt % tiles_per_batch) * BM;
+        const int n0 = gn * BN2;
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int st = it % STAGES, u = it / STAGES;
+          if (u > 0) ptx::mbar_wait(&empty[st], (u - 1) & 1);
+          ptx::mbar_arrive_expect_tx(&full[st], A_BYTES + B_BYTES);
+          const int tap = kb / chunks_per_tap, c0 = (kb - tap * chunks_per_tap) * BK;
+          ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES, c0, tap % s, t0 + tap / s, b);
+          if (CM == 1) ptx::tma_load_4d(&tmB, &full[st], smB + st * B_BYTES, kb * BK, n0, 0, 0);
+          else ptx::tma_load_4d_mc(&tmB, &full[st], smB + st * B_BYTES + rank * B_SLICE, kb * BK, n0 + rank * (BN2 / CM), 0, 0, MASK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN2, 0, 0);
+      int it = 0, ti = 0;
+      for (int gid = cluster_id; gid < total_groups; gid += num_clusters, ti++) {
+        const int acc = ti & 1, ua = ti >> 1;
+        if (ua > 0) ptx::mbar_wait(&tempty[acc], (ua - 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN2;
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int st = it % STAGES, u = it / STAGES;
+          ptx::mbar_wait(&full[st], u & 1);
+          ptx::tc_fence_after();
+          const uint32_t a0 = ptx::smem_u32(smA + st * A_BYTES), b0 = ptx::smem_u32(smB + st * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; k++) {
+            const uint64_t ad = ptx::make_sdesc_sw128(a0 + k * UK * 2, 16, 1024);
+            const uint64_t bd = ptx::make_sdesc_sw128(b0 + k * UK * 2, 16, 1024);
+            ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (CM == 1) ptx::umma_commit(&empty[st]);
+          else ptx::umma_commit_mc(&empty[st], MASK);
+        }
+        ptx::umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    int ti = 0;
+    for (int gid = cluster_id; gid < total_groups; gid += num_clusters, ti++) {
+      const int gm = gid / n_tiles, gn = gid - gm * n_tiles;
+      const int mt = gm * CM + rank;
+      const int b = mt / tiles_per_batch;
+      const int t = (mt % tiles_per_batch) * BM + row;
+      const int n0 = gn * BN2;
+      const bool row_ok = mt < m_tiles && t < C.rpb && t >= C.t_lo && t < C.t_hi;
+      TO* crow = static_cast<TO*>(C.p) + (long long)b * C.bs + (long long)t * C.rs + n0;
+      const int acc = ti & 1, ua = ti >> 1;
+      ptx::mbar_wait(&tfull[acc], ua & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN2; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN2 + c0), r);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] += __ldg(bias + n0 + c0 + j);
+          }
+          store_out(crow + c0, v);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+constexpr size_t nt2_smem() { return (size_t)4 * (BM * BK * 2 + 256 * BK * 2) + 256 + 1024; }
+
+template <int CM, class TO>
+int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt, int s, int tpb, int m_tiles, int n_tiles, int nb,
+               const float* bias, const OutView& C, cudaStream_t st) {
+  auto k = gemm_nt_tc2_kernel<CM, TO>;
+  const size_t smem = nt2_smem();
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int total_groups = ((m_tiles + CM - 1) / CM) * n_tiles;
+  int clusters = 148 / CM;
+  if (clusters > total_groups) clusters = total_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CM);
+  cfg.blockDim = dim3(NT_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CM; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, tmA, tmB, nkb, cpt, s, tpb, m_tiles, n_tiles, nb, bias, C));
+  CPC_LAUNCHED_N("gemm_nt_tc2", st);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TN kernel, second generation: 128 x 256 output tiles; the two CTAs of a cluster take the two n1 tiles of the
+// same (n2 tile, row range) and share the B operand: each fetches half of its four [64 rows][64 ch] blocks and
+// multicasts them.  4-stage ring, 256 TMEM columns, fp32 red.global.add epilogue.
+// ---------------------------------------------------------------------------------------------------------
+template <int CM>
+__global__ void __launch_bounds__(NT_THREADS, 1) gemm_tn_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                     const __grid_constant__ CUtensorMap tmB, int kb_total,
+                                                                     int kb_per_cta, int kb_per_batch, int b_chunks_per_tap,
+                                                                     int b_s, int N1, int N2, float* __restrict__ Cacc, int ldc,
+                                                                     int mode, int Ci, int taps) {
+  constexpr int BN2 = 256, STAGES = 4;
+  constexpr uint32_t BLK = 64 * 64 * 2;
+  constexpr uint32_t A_BYTES = 2 * BLK, B_BYTES = 4 * BLK;
+  constexpr uint16_t MASK = (uint16_t)((1u << CM) - 1);
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smA = sm;
+  unsigned char* smB = sm + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();     // == blockIdx.y % CM
+  const int n20 = blockIdx.x * BN2, n10 = blockIdx.y * BM;
+  const int kb_beg = blockIdx.z * kb_per_cta;
+  const int kb_end = min(kb_total, kb_beg + kb_per_cta);
+  const int nkb = kb_end - kb_beg;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; i++) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], CM); }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_holder, BN2);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (CM > 1) ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; i++) {
+        const int kb = kb_beg + i;
+        const int st = i % STAGES, u = i / STAGES;
+        if (u > 0) ptx::mbar_wait(&empty[st], (u - 1) & 1);
+        ptx::mbar_arrive_expect_tx(&full[st], A_BYTES + B_BYTES);
+        const int bb = kb / kb_per_batch, r0 = (kb - bb * kb_per_batch) * 64;
+#pragma unroll
+        for (int j = 0; j < 2; j++) ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES + j * BLK, n10 + j * 64, 0, r0, bb);
+#pragma unroll
+        for (int jj = 0; jj < 4 / CM; jj++) {
+          const int j = rank * (4 / CM) + jj;
+          const int blk = (n20 >> 6) + j;
+          const int tap = blk / b_chunks_per_tap, c0 = (blk - tap * b_chunks_per_tap) * 64;
+          if (CM == 1) ptx::tma_load_4d(&tmB, &full[st], smB + st * B_BYTES + j * BLK, c0, tap % b_s, r0 + tap / b_s, bb);
+          else ptx::tma_load_4d_mc(&tmB, &full[st], smB + st * B_BYTES + j * BLK, c0, tap % b_s, r0 + tap / b_s, bb, MASK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN2, 1, 1);
+      for (int i = 0; i < nkb; i++) {
+        const int st = i % STAGES, u = i / STAGES;
+        ptx::mbar_wait(&full[st], u & 1);
+        ptx::tc_fence_after();
+        const uint32_t a0 = ptx::smem_u32(smA + st * A_BYTES), b0 = ptx::smem_u32(smB + st * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < 64 / UK; k++) {
+          const uint64_t ad = ptx::make_sdesc_sw128(a0 + k * UK * 128, BLK, 1024);
+          const uint64_t bd = ptx::make_sdesc_sw128(b0 + k * UK * 128, BLK, 1024);
+          ptx::umma_bf16(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        if (CM == 1) ptx::umma_commit(&empty[st]);
+        else ptx::umma_commit_mc(&empty[st], MASK);
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else if (nkb > 0) {
+    const int lg = warp & 3;
+    const int n1 = n10 + lg * 32 + lane;
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN2; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      if (n1 < N1) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int n2 = n20 + c0 + j;
+          if (n2 < N2) {
+            long long o;
+            if (mode == STORE_CONV_W) { const int tap = n2 / Ci, ci = n2 - tap * Ci; o = ((long long)n1 * Ci + ci) * taps + tap; }
+            else o = (long long)n1 * ldc + n2;
+            atomicAdd(Cacc + o, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (CM > 1) ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc(tmem_acc, BN2);
+}
+
 template <int BN, int STAGES> constexpr size_t nt_smem() { return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 1024; }
 template <int BN, int STAGES> constexpr size_t tn_smem() { return (size_t)STAGES * (2 * 8192 + (BN / 64) * 8192) + 256 + 1024; }
 
@@ -310,6 +590,24 @@ int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void
   if ((C.rs % 8) != 0 || (C.bs % 8) != 0) return 0;
   CUtensorMap tmA, tmB;
   CPC_TRY(make_rowview_map(&tmA, A, Kd, nb, BM, false));
+  static const int gen = []() { const char* e = getenv("CPC_B200_GEMM_GEN"); return e ? atoi(e) : 2; }();
+  static const int cm_env = []() { const char* e = getenv("CPC_B200_GEMM_CM"); return e ? atoi(e) : 2; }();
+  if (gen == 2 && N % 256 == 0) {
+    const int cm = (cm_env == 1 || cm_env == 2 || cm_env == 4) ? cm_env : 2;
+    unsigned long long dims[4] = {(unsigned long long)Kd, (unsigned long long)N, 1, 1};
+    unsigned long long stq[3] = {(unsigned long long)Kd, (unsigned long long)Kd * N, (unsigned long long)Kd * N};
+    unsigned box[4] = {64, (unsigned)(256 / cm), 1, 1};
+    CPC_TRY(make_map4(&tmB, Bm, dims, stq, box));
+    const int tpb2 = (A.rpb + BM - 1) / BM;
+    const int m_tiles = nb * tpb2, n_tiles = N / 256;
+#define NT2(CMV)                                                                                                         \
+  (out_f32 ? launch_nt2<CMV, float>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb2, m_tiles, n_tiles, nb, bias, C, st)            \
+           : launch_nt2<CMV, bf16>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb2, m_tiles, n_tiles, nb, bias, C, st))
+    if (cm == 4) CPC_TRY(NT2(4)); else if (cm == 2) CPC_TRY(NT2(2)); else CPC_TRY(NT2(1));
+#undef NT2
+    *handled = true;
+    return 0;
+  }
   {
     unsigned long long dims[4] = {(unsigned long long)Kd, (unsigned long long)N, 1, 1};
     unsigned long long stq[3] = {(unsigned long long)Kd, (unsigned long long)Kd * N, (unsigned long long)Kd * N};
@@ -347,6 +645,31 @@ int gemm_tn_tc(int nb, int N1, int N2, const RowView& A, const RowView& B, float
   CPC_TRY(make_rowview_map(&tmB, B, N2, nb, 64, false));
   const int kb_per_batch = (A.rpb + 63) / 64;
   const int kb_total = kb_per_batch * nb;
+  static const int gen = []() { const char* e = getenv("CPC_B200_GEMM_GEN"); return e ? atoi(e) : 2; }();
+  if (gen == 2 && N1 % 256 == 0 && N2 % 256 == 0) {
+    const int tiles2 = (N1 / BM) * (N2 / 256);
+    int sp = 148 / tiles2;  // one CTA per SM, a single wave
+    if (sp > kb_total) sp = kb_total;
+    if (sp < 1) sp = 1;
+    const int kpc = (kb_total + sp - 1) / sp;
+    sp = (kb_total + kpc - 1) / kpc;
+    auto k2 = gemm_tn_tc2_kernel<2>;
+    const size_t smem2 = (size_t)4 * (2 * 8192 + 4 * 8192) + 256 + 1024;
+    CPC_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(N2 / 256, N1 / BM, sp);
+    cfg.blockDim = dim3(NT_THREADS);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k2, tmA, tmB, kb_total, kpc, kb_per_batch, bcin / 64, B.s, N1, N2, Cacc, ldc, mode, Ci, taps));
+    CPC_LAUNCHED_N("gemm_tn_tc2", st);
+    *handled = true;
+    return 0;
+  }
   const int tiles = (N1 / BM) * (N2 / BN);
   int splits = (148 * 2 + tiles - 1) / tiles;
   if (splits > kb_total) splits = kb_total;

@@ -38,6 +38,33 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
+// ---- hidden-state exchange without a cluster barrier: every 32-bit store into a peer's shared memory also
+// completes 4 bytes on that peer's mbarrier (st.async), the consumer waits for the byte count of one step.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
+                 : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap();  // a broken exchange faults instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void fence_mbar_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------
 // forward.  block = 128 threads (4 warps), cluster = HAR/64 CTAs, grid = cluster * ceil(B/8).
 // ---------------------------------------------------------------------------------------------------------
@@ -56,6 +83,13 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
   const int g = lane >> 2, t4 = lane & 3;
 
   __shared__ __align__(128) bf16 hs[2][HAR][BT];  // h_{t-1} as the B operand: [k][sequence]
+  __shared__ __align__(8) uint64_t hbar[2];        // hbar[b] completes when buffer b holds a full new state
+  constexpr uint32_t kStepBytes = HAR * BT * 2;
+  if (threadIdx.x == 0) {
+    mbar_init(&hbar[0], 1);
+    mbar_init(&hbar[1], 1);
+    fence_mbar_init_cluster();
+  }
 
   // resident A fragments: gate gt, rows 16*warp + {g, g+8} of this CTA's slice
   uint32_t wf[3][KS][4];
@@ -88,19 +122,38 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
     const int k = i / BT, bq = b0 + (i - k * BT);
     hs[0][k][i - k * BT] = __float2bfloat16_rn((h0 != nullptr && bq < B) ? h0[(size_t)bq * HAR + k] : 0.f);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // arm both buffers: hs[1] is produced by step 0, hs[0] by step 1
+    mbar_expect_tx(&hbar[1], kStepBytes);
+    mbar_expect_tx(&hbar[0], kStepBytes);
+  }
   cluster.sync();
+  const uint32_t hs_local = s_u32(&hs[0][0][0]), bar_local = s_u32(&hbar[0]);
 
-  for (int t = 0; t < S; t++) {
-    const int cur = t & 1, nxt = cur ^ 1;
-    // prefetch the input projections of this step (consumed after the matrix product)
-    float gq[3][4];
+  bf16 gq_raw[3][4];
+  auto load_gi = [&](int tt) {
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       const int col = HC * rank + 16 * warp + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
-      if (bq < B) {
-        const bf16* gp = gi + ((size_t)bq * S + t) * 3 * HAR + col;
-        gq[0][e] = __bfloat162float(gp[0]); gq[1][e] = __bfloat162float(gp[HAR]); gq[2][e] = __bfloat162float(gp[2 * HAR]);
-      } else { gq[0][e] = gq[1][e] = gq[2][e] = 0.f; }
+      if (bq < B && tt < S) {
+        const bf16* gp = gi + ((size_t)bq * S + tt) * 3 * HAR + col;
+        gq_raw[0][e] = gp[0]; gq_raw[1][e] = gp[HAR]; gq_raw[2][e] = gp[2 * HAR];
+      } else { gq_raw[0][e] = gq_raw[1][e] = gq_raw[2][e] = __float2bfloat16_rn(0.f); }
+    }
+  };
+  load_gi(0);
+
+  for (int t = 0; t < S; t++) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    float gq[3][4];
+#pragma unroll
+    for (int gt = 0; gt < 3; gt++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) gq[gt][e] = __bfloat162float(gq_raw[gt][e]);
+    load_gi(t + 1);  // in flight during this step's product and exchange
+    if (t > 0) {
+      mbar_wait(&hbar[cur], ((t - 1 - (cur ^ 1)) >> 1) & 1);
+      if (threadIdx.x == 0 && t + 2 < S + 1) mbar_expect_tx(&hbar[cur], kStepBytes);  // re-arm for step t+2
     }
     float acc[3][4];
 #pragma unroll
@@ -137,18 +190,23 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
         if (hT != nullptr && t == S - 1) hT[(size_t)bq * HAR + col] = hn[e];
       }
     }
-    // publish the 64 new units to every CTA of the cluster: rows (unit), 2 sequences per 32-bit store
-    {
+    // publish the 64 new units to every CTA of the cluster: rows (unit), 2 sequences per 32-bit st.async
+    if (t + 1 < S) {
       const uint32_t v0 = pack_bf16(hn[0], hn[1]), v1 = pack_bf16(hn[2], hn[3]);
       const int row0 = HC * rank + 16 * warp + g;
-      for (int pr = 0; pr < CS; pr++) {
-        bf16* base = cluster.map_shared_rank(&hs[nxt][0][0], pr);
-        *reinterpret_cast<uint32_t*>(base + (size_t)row0 * BT + 2 * t4) = v0;
-        *reinterpret_cast<uint32_t*>(base + (size_t)(row0 + 8) * BT + 2 * t4) = v1;
+      const uint32_t off0 = (uint32_t)(((size_t)nxt * HAR + row0) * BT + 2 * t4) * 2;
+      const uint32_t off1 = off0 + 8 * BT * 2;
+#pragma unroll
+      for (int pr = 0; pr < 8; pr++) {
+        if (pr < CS) {
+          const uint32_t ph = mapa_u32(hs_local, pr), pb = mapa_u32(bar_local + nxt * 8, pr);
+          st_async_u32(ph + off0, v0, pb);
+          st_async_u32(ph + off1, v1, pb);
+        }
       }
     }
-    cluster.sync();
   }
+  cluster.sync();  // nobody leaves while a peer may still be writing into it
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -169,6 +227,13 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
   const int g = lane >> 2, t4 = lane & 3;
 
   __shared__ __align__(128) bf16 ds[2][G][BT];  // dgh_t as the B operand: [gate index][sequence]
+  __shared__ __align__(8) uint64_t dbar[2];
+  constexpr uint32_t kStepBytes = G * BT * 2;
+  if (threadIdx.x == 0) {
+    mbar_init(&dbar[0], 1);
+    mbar_init(&dbar[1], 1);
+    fence_mbar_init_cluster();
+  }
 
   uint32_t wf[KS][4];
   {
@@ -183,23 +248,67 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     }
   }
   float carry[4] = {0.f, 0.f, 0.f, 0.f};
+  float direct[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&dbar[0], kStepBytes);
+    mbar_expect_tx(&dbar[1], kStepBytes);
+  }
   cluster.sync();
+  const uint32_t ds_local = s_u32(&ds[0][0][0]), bar_local = s_u32(&dbar[0]);
 
-  for (int t = S - 1; t >= 0; t--) {
-    const int buf = t & 1;
-    float direct[4], dr[4], du[4], dnr[4];
+  // dh_{t-1} contribution of step `tt` (its dgh sits in ds[tt & 1]):  carry = direct + dgh . W_hh[:, slice]
+  auto consume = [&](int it) {  // it = iteration index of the step whose exchange we wait for
+    const int tt = S - 1 - it, buf = tt & 1;
+    mbar_wait(&dbar[buf], (it >> 1) & 1);
+    if (threadIdx.x == 0 && it + 2 < S) mbar_expect_tx(&dbar[buf], kStepBytes);
+    float acc[3][4];
+#pragma unroll
+    for (int a3 = 0; a3 < 3; a3++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[a3][e] = 0.f;
+#pragma unroll
+    for (int q = 0; q < KS / 2; q++) {
+      uint32_t bq4[4];
+      ldsm_x4_t(bq4, s_u32(&ds[buf][32 * q + lane][0]));
+      mma16816(acc[q % 3], wf[2 * q], bq4[0], bq4[1]);
+      mma16816(acc[q % 3], wf[2 * q + 1], bq4[2], bq4[3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) carry[e] = direct[e] + (acc[0][e] + acc[1][e]) + acc[2][e];
+  };
+
+  for (int it = 0; it < S; it++) {
+    const int t = S - 1 - it, buf = t & 1;
+    // (A) this step's operands: independent of the running gradient, in flight during the previous product
+    float dcv[4], hp[4];
+    uint32_t gRU[4], gNH[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int col = HC * rank + 16 * warp + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
+      dcv[e] = 0.f; hp[e] = 0.f; gRU[e] = 0u; gNH[e] = 0u;
+      if (bq < B) {
+        const size_t o = ((size_t)bq * S + t) * HAR + col;
+        dcv[e] = dc[o];
+        gRU[e] = (uint32_t)__bfloat16_as_ushort(sR[o]) | ((uint32_t)__bfloat16_as_ushort(sU[o]) << 16);
+        gNH[e] = (uint32_t)__bfloat16_as_ushort(sN[o]) | ((uint32_t)__bfloat16_as_ushort(sHN[o]) << 16);
+        hp[e] = t > 0 ? c[o - HAR] : (h0 != nullptr ? h0[(size_t)bq * HAR + col] : 0.f);
+      }
+    }
+    // (B) finish the previous step: wait for its exchange, dh += dgh . W_hh
+    if (it > 0) consume(it - 1);
+    // (C) gate gradients of step t, publish dgh_t
+    float dr[4], du[4], dnr[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       const int col = HC * rank + 16 * warp + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
       dr[e] = du[e] = dnr[e] = direct[e] = 0.f;
       if (bq < B) {
-        const size_t o = ((size_t)bq * S + t) * HAR + col;
-        const float dh = carry[e] + dc[o];
-        const float rg = __bfloat162float(sR[o]), ug = __bfloat162float(sU[o]), ng = __bfloat162float(sN[o]);
-        const float hnv = __bfloat162float(sHN[o]);
-        const float hp = t > 0 ? c[o - HAR] : (h0 != nullptr ? h0[(size_t)bq * HAR + col] : 0.f);
+        const float dh = carry[e] + dcv[e];
+        const float rg = __uint_as_float(gRU[e] << 16), ug = __uint_as_float(gRU[e] & 0xffff0000u);
+        const float ng = __uint_as_float(gNH[e] << 16), hnv = __uint_as_float(gNH[e] & 0xffff0000u);
         const float dn = dh * (1.f - ug) * (1.f - ng * ng);
-        du[e] = dh * (hp - ng) * ug * (1.f - ug);
+        du[e] = dh * (hp[e] - ng) * ug * (1.f - ug);
         dr[e] = dn * hnv * rg * (1.f - rg);
         dnr[e] = dn * rg;
         direct[e] = dh * ug;
@@ -210,33 +319,22 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     }
     {
       const int row0 = HC * rank + 16 * warp + g;
-      for (int pr = 0; pr < CS; pr++) {
-        bf16* base = cluster.map_shared_rank(&ds[buf][0][0], pr);
 #pragma unroll
-        for (int hf = 0; hf < 2; hf++) {
-          const int r = row0 + 8 * hf;
-          *reinterpret_cast<uint32_t*>(base + (size_t)r * BT + 2 * t4) = pack_bf16(dr[2 * hf], dr[2 * hf + 1]);
-          *reinterpret_cast<uint32_t*>(base + (size_t)(HAR + r) * BT + 2 * t4) = pack_bf16(du[2 * hf], du[2 * hf + 1]);
-          *reinterpret_cast<uint32_t*>(base + (size_t)(2 * HAR + r) * BT + 2 * t4) = pack_bf16(dnr[2 * hf], dnr[2 * hf + 1]);
+      for (int pr = 0; pr < 8; pr++) {
+        if (pr < CS) {
+          const uint32_t pd = mapa_u32(ds_local, pr), pb = mapa_u32(bar_local + buf * 8, pr);
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const uint32_t base = pd + (uint32_t)(((size_t)buf * G + row0 + 8 * hf) * BT + 2 * t4) * 2;
+            st_async_u32(base, pack_bf16(dr[2 * hf], dr[2 * hf + 1]), pb);
+            st_async_u32(base + HAR * BT * 2, pack_bf16(du[2 * hf], du[2 * hf + 1]), pb);
+            st_async_u32(base + 2 * HAR * BT * 2, pack_bf16(dnr[2 * hf], dnr[2 * hf + 1]), pb);
+          }
         }
       }
     }
-    cluster.sync();
-    float acc[3][4];
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int e = 0; e < 4; e++) acc[a][e] = 0.f;
-#pragma unroll
-    for (int q = 0; q < KS / 2; q++) {
-      uint32_t bq4[4];
-      ldsm_x4_t(bq4, s_u32(&ds[buf][32 * q + lane][0]));
-      mma16816(acc[q % 3], wf[2 * q], bq4[0], bq4[1]);
-      mma16816(acc[q % 3], wf[2 * q + 1], bq4[2], bq4[3]);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; e++) carry[e] = direct[e] + (acc[0][e] + acc[1][e]) + acc[2][e];
   }
+  consume(S - 1);
   if (dh0 != nullptr) {
 #pragma unroll
     for (int e = 0; e < 4; e++) {
@@ -244,6 +342,7 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
       if (bq < B) dh0[(size_t)bq * HAR + col] = carry[e];
     }
   }
+  cluster.sync();
 }
 
 template <class K>
