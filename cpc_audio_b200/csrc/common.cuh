@@ -173,8 +173,21 @@ struct OutView {
   long long bs, rs;
   int rpb;
   int t_lo, t_hi;  // only rows with t_lo <= t < t_hi are stored
-  int ldn;         // unused (inner dim contiguous)
+  // merged transposed-conv output (dgrad): the N columns are `s` residues of res_w channels each; column block
+  // r = n / res_w of logical row t is input row s*t + r - res_p, which exists unless (t == 0 && r < res_p) or
+  // (t == rpb-1 && r >= res_p).  res_w == 0: plain output.
+  int res_w = 0;
+  int res_p = 0;
 };
+__host__ __device__ inline bool out_row_ok(const OutView& C, int t, int n0) {
+  if (t >= C.rpb || t < C.t_lo || t >= C.t_hi) return false;
+  if (C.res_w > 0) {
+    const int r = n0 / C.res_w;
+    if (t == 0 && r < C.res_p) return false;
+    if (t == C.rpb - 1 && r >= C.res_p) return false;
+  }
+  return true;
+}
 enum StoreMode { STORE_PLAIN = 0, STORE_CONV_W = 1 };
 
 // C[m,n] = sum_k A[m,k] * B[n,k] (+ bias[n]).  A row view (M = nb*rpb rows, inner Kd); B dense (N, Kd) ld=Kd.

@@ -41,6 +41,12 @@ __device__ __forceinline__ void row_store(T* row, int H, int lane, const float (
   }
 }
 
+// zero one padded row (all H channels) with a warp
+template <class T>
+__device__ __forceinline__ void zero_row(T* row, int H, int lane) {
+  for (int c = 4 * lane; c < H; c += 128) { float z4[4] = {0.f, 0.f, 0.f, 0.f}; store_vec<4>(row + c, z4); }
+}
+
 // ChannelNorm statistics of one row held across a warp (two-pass, unbiased variance: model.py:52-54)
 template <int I>
 __device__ __forceinline__ void row_stats(const float (&u)[I][4], int H, int lane, float& mean, float& rstd) {
@@ -132,6 +138,8 @@ __global__ void __launch_bounds__(128) conv0_fwd_kernel(const float* __restrict_
     float xs[10];
     conv0_window_init(xb, L, t0, xs);
     T* yrow = y + ((long long)b * Lp0 + kPad + t0) * H;
+    if (t0 == 0) { for (int r = 0; r < kPad; r++) zero_row(y + ((long long)b * Lp0 + r) * H, H, lane); }
+    if (t0 + kC0Chunk == L0) { for (int r = 0; r < kPad; r++) zero_row(y + ((long long)b * Lp0 + kPad + L0 + r) * H, H, lane); }
 #pragma unroll 1
     for (int tt = 0; tt < kC0Chunk; tt++) {
       float u[I][4];
@@ -321,7 +329,12 @@ __global__ void __launch_bounds__(256) cnorm_relu_fwd_kernel(const T* __restrict
       for (int j = 0; j < 4; j++) v[i][j] = fmaxf(fmaf((v[i][j] - mean) * rstd, g[j], be[j]), 0.f);
     }
   }
-  if (y) row_store<I>(y + prow, H, lane, v);
+  if (y) {
+    row_store<I>(y + prow, H, lane, v);
+    const long long w0 = (long long)b * (Lc + 2 * kPad) * H;
+    if (t == 0) { for (int r = 0; r < kPad; r++) zero_row(y + w0 + (long long)r * H, H, lane); }
+    if (t == Lc - 1) { for (int r = 0; r < kPad; r++) zero_row(y + w0 + (long long)(kPad + Lc + r) * H, H, lane); }
+  }
   if (zout) row_store<I>(zout + warp * H, H, lane, v);
 }
 
@@ -384,6 +397,9 @@ __global__ void __launch_bounds__(256) cnorm_relu_bwd_kernel(const TD* __restric
       }
     }
     row_store<I>(du + prow, H, lane, d);
+    const long long w0 = (long long)b * (Lc + 2 * kPad) * H;
+    if (t == 0) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)r2 * H, H, lane); }
+    if (t == Lc - 1) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)(kPad + Lc + r2) * H, H, lane); }
   }
 #pragma unroll
   for (int i = 0; i < I; i++) {
@@ -466,10 +482,7 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     prep_w_fwd_kernel<T><<<148, 256, 0, st>>>(p->conv_w[i], wp[i], H, H, kConvK[i]);
     CPC_LAUNCHED_N("prep_w_fwd", st);
   }
-  for (int i = 0; i < 4; i++) {
-    zero_pads_kernel<T><<<(B * 2 * kPad * H + 255) / 256, 256, 0, st>>>(sv + e.y[i], B, g.Lout[i], H);
-    CPC_LAUNCHED_N("zero_pads", st);
-  }
+  // the zero rows around every window of y0..y3 are written by the kernels that produce the interior
   const int I = ilog_I(H);
   {
     const size_t smem = 3 * (size_t)H * sizeof(float);
@@ -518,8 +531,6 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   for (int i = 1; i < 5; i++) {
     prep_w_dgrad_kernel<T><<<148, 256, 0, st>>>(p->conv_w[i], wd[i], H, H, kConvS[i]);
     CPC_LAUNCHED_N("prep_w_dgrad", st);
-    zero_pads_kernel<T><<<(B * 2 * kPad * H + 255) / 256, 256, 0, st>>>(du[i], B, g.Lout[i], H);
-    CPC_LAUNCHED_N("zero_pads", st);
   }
   for (int i = 4; i >= 1; i--) {
     const int Lo = g.Lout[i], Lin = g.Lout[i - 1], s = kConvS[i], pp = kConvP[i];
@@ -543,13 +554,12 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       RowView Bv{sv + e.y[i - 1] + (size_t)(kPad - pp) * H, (long long)(Lin + 2 * kPad) * H, (long long)s * H, Lo, kConvK[i], s};
       CPC_TRY(gemm_tn(g.bf16, B, H, kConvK[i] * H, A, Bv, gr->conv_w[i], 0, STORE_CONV_W, H, kConvK[i], st));
     }
-    // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r]
-    for (int r = 0; r < s; r++) {
+    // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r].  All s residues in ONE GEMM with
+    // N = s*H: row q of the product is the s consecutive input rows s q - p .. s q - p + s - 1.
+    {
       RowView A{du[i] + (size_t)(kPad - 1) * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo + 1, 2, 1};
-      int t_lo = r < pp ? 1 : 0;
-      int q_max = (Lin - 1 - r + pp) / s;
-      OutView C{dy[i - 1] + (long long)(r - pp) * H, (long long)Lin * H, (long long)s * H, Lo + 1, t_lo, q_max + 1, 0};
-      CPC_TRY(gemm_nt(g.bf16, false, B, H, 2 * H, A, wd[i] + (size_t)r * H * 2 * H, nullptr, C, st));
+      OutView C{dy[i - 1] - (long long)pp * H, (long long)Lin * H, (long long)s * H, Lo + 1, 0, Lo + 1, H, pp};
+      CPC_TRY(gemm_nt(g.bf16, false, B, s * H, 2 * H, A, wd[i], nullptr, C, st));
     }
   }
   {

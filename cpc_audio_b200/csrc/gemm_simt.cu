@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(NT) gemm_nt_kernel(int M, int N, int Kd, RowVi
     int m = m0 + ty * 4 + i;
     if (m >= M) continue;
     int b = m / C.rpb, t = m - b * C.rpb;
-    if (t < C.t_lo || t >= C.t_hi) continue;
+    if (!out_row_ok(C, t, n)) continue;
     float o[4] = {acc[i][0] + bb[0], acc[i][1] + bb[1], acc[i][2] + bb[2], acc[i][3] + bb[3]};
     store_vec<4>(Cp + (long long)b * C.bs + (long long)t * C.rs + n, o);
   }

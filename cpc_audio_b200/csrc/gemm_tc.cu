@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(NT_THREADS) gemm_nt_tc_kernel(const __grid_con
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
     const int t = t0 + row;
-    const bool row_ok = t < C.rpb && t >= C.t_lo && t < C.t_hi;
+    const bool row_ok = out_row_ok(C, t, n0);
     TO* crow = static_cast<TO*>(C.p) + (long long)b * C.bs + (long long)t * C.rs + n0;
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
       const int b = mt / tiles_per_batch;
       const int t = (mt % tiles_per_batch) * BM + row;
       const int n0 = gn * BN2;
-      const bool row_ok = mt < m_tiles && t < C.rpb && t >= C.t_lo && t < C.t_hi;
+      const bool row_ok = mt < m_tiles && out_row_ok(C, t, n0);
       TO* crow = static_cast<TO*>(C.p) + (long long)b * C.bs + (long long)t * C.rs + n0;
       const int acc = ti & 1, ua = ti >> 1;
       ptx::mbar_wait(&tfull[acc], ua & 1);
@@ -592,7 +592,8 @@ int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void
   CPC_TRY(make_rowview_map(&tmA, A, Kd, nb, BM, false));
   static const int gen = []() { const char* e = getenv("CPC_B200_GEMM_GEN"); return e ? atoi(e) : 2; }();
   static const int cm_env = []() { const char* e = getenv("CPC_B200_GEMM_CM"); return e ? atoi(e) : 2; }();
-  if (gen == 2 && N % 256 == 0) {
+  if (C.res_w > 0 && C.res_w % BN != 0) return 0;  // an output tile must not straddle two dgrad residues
+  if (gen == 2 && N % 256 == 0 && (C.res_w == 0 || C.res_w % 256 == 0)) {
     const int cm = (cm_env == 1 || cm_env == 2 || cm_env == 4) ? cm_env : 2;
     unsigned long long dims[4] = {(unsigned long long)Kd, (unsigned long long)N, 1, 1};
     unsigned long long stq[3] = {(unsigned long long)Kd, (unsigned long long)Kd * N, (unsigned long long)Kd * N};
