@@ -439,6 +439,14 @@ __global__ void prep_w_dgrad_kernel(const float* __restrict__ w, T* __restrict__
     wd[i] = from_f<T>(w[((long long)co * Ci + ci) * taps + r + s * (1 - half)]);
   }
 }
+// dW[co][ci][tap] += scratch[co][tap*Ci + ci]   (scratch is the GEMM-friendly layout of the weight gradient)
+__global__ void permute_add_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Co, int Ci, int taps) {
+  const long long n = (long long)Co * Ci * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps); long long r = i / taps; const int ci = (int)(r % Ci); const int co = (int)(r / Ci);
+    dw[i] += scratch[((long long)co * taps + tap) * Ci + ci];
+  }
+}
 // zero the kPad rows before and after every window
 template <class T>
 __global__ void zero_pads_kernel(T* __restrict__ buf, int B, int Lc, int H) {
@@ -525,7 +533,11 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   for (int i = 1; i < 5; i++) wd[i] = ws.take<T>((size_t)kConvS[i] * H * 2 * H);
   for (int i = 1; i < 5; i++) du[i] = ws.take<T>((size_t)B * (g.Lout[i] + 2 * kPad) * H);
   for (int i = 0; i < 4; i++) dy[i] = ws.take<T>((size_t)B * g.Lout[i] * H);
+  float* dwp[5] = {nullptr};
+  size_t dwp_total = 0;
+  for (int i = 1; i < 5; i++) { dwp[i] = ws.take<float>((size_t)H * kConvK[i] * H); dwp_total = (size_t)((char*)dwp[i] - (char*)dwp[1]) + (size_t)H * kConvK[i] * H * 4; }
   if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "encoder_bwd: workspace %zu < %zu", ws_bytes, ws.off);
+  CPC_CHECK_CUDA(cudaMemsetAsync(dwp[1], 0, dwp_total, st));
   const int I = ilog_I(H);
 
   for (int i = 1; i < 5; i++) {
@@ -552,7 +564,9 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     {
       RowView A{du[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo};
       RowView Bv{sv + e.y[i - 1] + (size_t)(kPad - pp) * H, (long long)(Lin + 2 * kPad) * H, (long long)s * H, Lo, kConvK[i], s};
-      CPC_TRY(gemm_tn(g.bf16, B, H, kConvK[i] * H, A, Bv, gr->conv_w[i], 0, STORE_CONV_W, H, kConvK[i], st));
+      CPC_TRY(gemm_tn(g.bf16, B, H, kConvK[i] * H, A, Bv, dwp[i], kConvK[i] * H, STORE_PLAIN, 0, 0, st));
+      permute_add_wgrad_kernel<<<148 * 2, 256, 0, st>>>(dwp[i], gr->conv_w[i], H, H, kConvK[i]);
+      CPC_LAUNCHED_N("permute_add_wgrad", st);
     }
     // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r].  All s residues in ONE GEMM with
     // N = s*H: row q of the product is the s consecutive input rows s q - p .. s q - p + s - 1.
@@ -594,6 +608,7 @@ size_t encoder_ws_bytes(const Geo& g, int backward) {
     for (int i = 1; i < 5; i++) tot += align_up((size_t)kConvS[i] * g.H * 2 * g.H * es);
     for (int i = 1; i < 5; i++) tot += align_up((size_t)g.B * (g.Lout[i] + 2 * kPad) * g.H * es);
     for (int i = 0; i < 4; i++) tot += align_up((size_t)g.B * g.Lout[i] * g.H * es);
+    for (int i = 1; i < 5; i++) tot += align_up((size_t)g.H * kConvK[i] * g.H * 4);
   }
   return tot + 256;
 }

@@ -65,24 +65,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_mbar_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+__device__ __forceinline__ void pair_sync(int ub) { asm volatile("bar.sync %0, 64;" ::"r"(ub + 1) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------
-// forward.  block = 128 threads (4 warps), cluster = HAR/64 CTAs, grid = cluster * ceil(B/8).
+// forward.  block = 256 threads = 8 warps: warp w owns units 16*(w&3).. of the CTA's 64-unit slice and the k
+// range [ (w>>2)*HAR/2, +HAR/2 ) of the product; warps 0-3 ("gate warps") add the partner's partial sums
+// (through shared memory, 64-thread named barrier per pair), do the gate math and publish.
+// cluster = HAR/64 CTAs, grid = cluster * ceil(B/8).
 // ---------------------------------------------------------------------------------------------------------
 template <int HAR>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                        const float* __restrict__ h0, float* __restrict__ c, bf16* __restrict__ cT, bf16* __restrict__ sR,
                        bf16* __restrict__ sU, bf16* __restrict__ sN, bf16* __restrict__ sHN, float* __restrict__ hT, int B,
                        int S) {
-  constexpr int KS = HAR / 16;
+  constexpr int KS = HAR / 16, KSH = KS / 2;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int CS = (int)cluster.num_blocks();
   const int b0 = (blockIdx.x / CS) * BT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ub = warp & 3, kh = warp >> 2;
   const int g = lane >> 2, t4 = lane & 3;
 
   __shared__ __align__(128) bf16 hs[2][HAR][BT];  // h_{t-1} as the B operand: [k][sequence]
+  __shared__ float part[4][12][32];                // partial sums of the upper k half, per unit block
   __shared__ __align__(8) uint64_t hbar[2];        // hbar[b] completes when buffer b holds a full new state
   constexpr uint32_t kStepBytes = HAR * BT * 2;
   if (threadIdx.x == 0) {
@@ -91,31 +98,31 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
     fence_mbar_init_cluster();
   }
 
-  // resident A fragments: gate gt, rows 16*warp + {g, g+8} of this CTA's slice
-  uint32_t wf[3][KS][4];
+  // resident A fragments: gate gt, rows 16*ub + {g, g+8} of this CTA's slice, k-steps of this warp's half
+  uint32_t wf[3][KSH][4];
 #pragma unroll
   for (int gt = 0; gt < 3; gt++) {
-    const float* r0 = w_hh + (size_t)(gt * HAR + HC * rank + 16 * warp + g) * HAR;
+    const float* r0 = w_hh + (size_t)(gt * HAR + HC * rank + 16 * ub + g) * HAR;
     const float* r1 = r0 + 8 * HAR;
 #pragma unroll
-    for (int ks = 0; ks < KS; ks++) {
-      const int k = ks * 16 + 2 * t4;
+    for (int ks = 0; ks < KSH; ks++) {
+      const int k = (kh * KSH + ks) * 16 + 2 * t4;
       wf[gt][ks][0] = pack_bf16(__ldg(r0 + k), __ldg(r0 + k + 1));
       wf[gt][ks][1] = pack_bf16(__ldg(r1 + k), __ldg(r1 + k + 1));
       wf[gt][ks][2] = pack_bf16(__ldg(r0 + k + 8), __ldg(r0 + k + 9));
       wf[gt][ks][3] = pack_bf16(__ldg(r1 + k + 8), __ldg(r1 + k + 9));
     }
   }
-  // element e of a thread: unit jj = g + 8*(e>>1), sequence bb = 2*t4 + (e&1)
+  // element e of a gate thread: unit jj = g + 8*(e>>1), sequence bb = 2*t4 + (e&1)
   float bh[3][2];
 #pragma unroll
   for (int gt = 0; gt < 3; gt++)
 #pragma unroll
-    for (int hf = 0; hf < 2; hf++) bh[gt][hf] = __ldg(b_hh + gt * HAR + HC * rank + 16 * warp + g + 8 * hf);
+    for (int hf = 0; hf < 2; hf++) bh[gt][hf] = __ldg(b_hh + gt * HAR + HC * rank + 16 * ub + g + 8 * hf);
   float hprev[4];
 #pragma unroll
   for (int e = 0; e < 4; e++) {
-    const int col = HC * rank + 16 * warp + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
+    const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
     hprev[e] = (h0 != nullptr && bq < B) ? h0[(size_t)bq * HAR + col] : 0.f;
   }
   for (int i = threadIdx.x; i < HAR * BT; i += blockDim.x) {
@@ -134,8 +141,8 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
   auto load_gi = [&](int tt) {
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const int col = HC * rank + 16 * warp + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
-      if (bq < B && tt < S) {
+      const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
+      if (kh == 0 && bq < B && tt < S) {
         const bf16* gp = gi + ((size_t)bq * S + tt) * 3 * HAR + col;
         gq_raw[0][e] = gp[0]; gq_raw[1][e] = gp[HAR]; gq_raw[2][e] = gp[2 * HAR];
       } else { gq_raw[0][e] = gq_raw[1][e] = gq_raw[2][e] = __float2bfloat16_rn(0.f); }
@@ -153,55 +160,72 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
     load_gi(t + 1);  // in flight during this step's product and exchange
     if (t > 0) {
       mbar_wait(&hbar[cur], ((t - 1 - (cur ^ 1)) >> 1) & 1);
-      if (threadIdx.x == 0 && t + 2 < S + 1) mbar_expect_tx(&hbar[cur], kStepBytes);  // re-arm for step t+2
+      if (threadIdx.x == 0 && t + 1 < S) mbar_expect_tx(&hbar[cur], kStepBytes);  // re-arm for step t+2
     }
-    float acc[3][4];
+    float acc[3][2][4];
 #pragma unroll
     for (int gt = 0; gt < 3; gt++)
 #pragma unroll
-      for (int e = 0; e < 4; e++) acc[gt][e] = 0.f;
+      for (int ch = 0; ch < 2; ch++)
 #pragma unroll
-    for (int q = 0; q < KS / 2; q++) {
+        for (int e = 0; e < 4; e++) acc[gt][ch][e] = 0.f;
+#pragma unroll
+    for (int q = 0; q < KSH / 2; q++) {
       uint32_t bq4[4];
-      ldsm_x4_t(bq4, s_u32(&hs[cur][32 * q + lane][0]));
+      ldsm_x4_t(bq4, s_u32(&hs[cur][kh * (HAR / 2) + 32 * q + lane][0]));
 #pragma unroll
       for (int gt = 0; gt < 3; gt++) {
-        mma16816(acc[gt], wf[gt][2 * q], bq4[0], bq4[1]);
-        mma16816(acc[gt], wf[gt][2 * q + 1], bq4[2], bq4[3]);
+        mma16816(acc[gt][0], wf[gt][2 * q], bq4[0], bq4[1]);
+        mma16816(acc[gt][1], wf[gt][2 * q + 1], bq4[2], bq4[3]);
       }
     }
-    float hn[4];
+    float a[3][4];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int hf = e >> 1;
-      const float ghn = acc[2][e] + bh[2][hf];
-      const float rg = sigmoidf_(gq[0][e] + acc[0][e] + bh[0][hf]);
-      const float ug = sigmoidf_(gq[1][e] + acc[1][e] + bh[1][hf]);
-      const float ng = tanhf(gq[2][e] + rg * ghn);
-      hn[e] = (1.f - ug) * ng + ug * hprev[e];
-      hprev[e] = hn[e];
-      const int col = HC * rank + 16 * warp + g + 8 * hf, bq = b0 + 2 * t4 + (e & 1);
-      if (bq < B) {
-        const size_t o = ((size_t)bq * S + t) * HAR + col;
-        c[o] = hn[e];
-        cT[o] = __float2bfloat16_rn(hn[e]);
-        sR[o] = __float2bfloat16_rn(rg); sU[o] = __float2bfloat16_rn(ug); sN[o] = __float2bfloat16_rn(ng);
-        sHN[o] = __float2bfloat16_rn(ghn);
-        if (hT != nullptr && t == S - 1) hT[(size_t)bq * HAR + col] = hn[e];
-      }
+    for (int gt = 0; gt < 3; gt++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) a[gt][e] = acc[gt][0][e] + acc[gt][1][e];
+    if (kh == 1) {
+#pragma unroll
+      for (int gt = 0; gt < 3; gt++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) part[ub][gt * 4 + e][lane] = a[gt][e];
     }
-    // publish the 64 new units to every CTA of the cluster: rows (unit), 2 sequences per 32-bit st.async
-    if (t + 1 < S) {
-      const uint32_t v0 = pack_bf16(hn[0], hn[1]), v1 = pack_bf16(hn[2], hn[3]);
-      const int row0 = HC * rank + 16 * warp + g;
-      const uint32_t off0 = (uint32_t)(((size_t)nxt * HAR + row0) * BT + 2 * t4) * 2;
-      const uint32_t off1 = off0 + 8 * BT * 2;
+    pair_sync(ub);
+    if (kh == 0) {
+      float hn[4];
 #pragma unroll
-      for (int pr = 0; pr < 8; pr++) {
-        if (pr < CS) {
-          const uint32_t ph = mapa_u32(hs_local, pr), pb = mapa_u32(bar_local + nxt * 8, pr);
-          st_async_u32(ph + off0, v0, pb);
-          st_async_u32(ph + off1, v1, pb);
+      for (int e = 0; e < 4; e++) {
+        const int hf = e >> 1;
+        const float ar = a[0][e] + part[ub][e][lane], au = a[1][e] + part[ub][4 + e][lane], an = a[2][e] + part[ub][8 + e][lane];
+        const float ghn = an + bh[2][hf];
+        const float rg = sigmoidf_(gq[0][e] + ar + bh[0][hf]);
+        const float ug = sigmoidf_(gq[1][e] + au + bh[1][hf]);
+        const float ng = tanhf(gq[2][e] + rg * ghn);
+        hn[e] = (1.f - ug) * ng + ug * hprev[e];
+        hprev[e] = hn[e];
+        const int col = HC * rank + 16 * ub + g + 8 * hf, bq = b0 + 2 * t4 + (e & 1);
+        if (bq < B) {
+          const size_t o = ((size_t)bq * S + t) * HAR + col;
+          c[o] = hn[e];
+          cT[o] = __float2bfloat16_rn(hn[e]);
+          sR[o] = __float2bfloat16_rn(rg); sU[o] = __float2bfloat16_rn(ug); sN[o] = __float2bfloat16_rn(ng);
+          sHN[o] = __float2bfloat16_rn(ghn);
+          if (hT != nullptr && t == S - 1) hT[(size_t)bq * HAR + col] = hn[e];
+        }
+      }
+      // publish the 64 new units to every CTA of the cluster: rows (unit), 2 sequences per 32-bit st.async
+      if (t + 1 < S) {
+        const uint32_t v0 = pack_bf16(hn[0], hn[1]), v1 = pack_bf16(hn[2], hn[3]);
+        const int row0 = HC * rank + 16 * ub + g;
+        const uint32_t off0 = (uint32_t)(((size_t)nxt * HAR + row0) * BT + 2 * t4) * 2;
+        const uint32_t off1 = off0 + 8 * BT * 2;
+#pragma unroll
+        for (int pr = 0; pr < 8; pr++) {
+          if (pr < CS) {
+            const uint32_t ph = mapa_u32(hs_local, pr), pb = mapa_u32(bar_local + nxt * 8, pr);
+            st_async_u32(ph + off0, v0, pb);
+            st_async_u32(ph + off1, v1, pb);
+          }
         }
       }
     }
@@ -210,23 +234,26 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// BPTT.  Same launch shape.  Resident: A[i][gate index] = W_hh[gate index][64*rank + 16*warp + i].
+// BPTT.  Same launch shape.  Resident: A[i][gate index] = W_hh[gate index][64*rank + 16*(w&3) + i], gate-index
+// range of warp w: [ (w>>2)*3HAR/2, +3HAR/2 ).
 // ---------------------------------------------------------------------------------------------------------
 template <int HAR>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c, const float* __restrict__ h0,
                        const bf16* __restrict__ sR, const bf16* __restrict__ sU, const bf16* __restrict__ sN,
                        const bf16* __restrict__ sHN, const float* __restrict__ w_hh, bf16* __restrict__ dgi,
                        bf16* __restrict__ dgh, float* __restrict__ dh0, int B, int S) {
-  constexpr int G = 3 * HAR, KS = G / 16;
+  constexpr int G = 3 * HAR, KS = G / 16, KSH = KS / 2;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int CS = (int)cluster.num_blocks();
   const int b0 = (blockIdx.x / CS) * BT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ub = warp & 3, kh = warp >> 2;
   const int g = lane >> 2, t4 = lane & 3;
 
   __shared__ __align__(128) bf16 ds[2][G][BT];  // dgh_t as the B operand: [gate index][sequence]
+  __shared__ float part[4][4][32];
   __shared__ __align__(8) uint64_t dbar[2];
   constexpr uint32_t kStepBytes = G * BT * 2;
   if (threadIdx.x == 0) {
@@ -235,12 +262,12 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     fence_mbar_init_cluster();
   }
 
-  uint32_t wf[KS][4];
+  uint32_t wf[KSH][4];
   {
-    const int c0 = HC * rank + 16 * warp + g;
+    const int c0 = HC * rank + 16 * ub + g;
 #pragma unroll
-    for (int ks = 0; ks < KS; ks++) {
-      const int k = ks * 16 + 2 * t4;
+    for (int ks = 0; ks < KSH; ks++) {
+      const int k = (kh * KSH + ks) * 16 + 2 * t4;
       wf[ks][0] = pack_bf16(__ldg(w_hh + (size_t)k * HAR + c0), __ldg(w_hh + (size_t)(k + 1) * HAR + c0));
       wf[ks][1] = pack_bf16(__ldg(w_hh + (size_t)k * HAR + c0 + 8), __ldg(w_hh + (size_t)(k + 1) * HAR + c0 + 8));
       wf[ks][2] = pack_bf16(__ldg(w_hh + (size_t)(k + 8) * HAR + c0), __ldg(w_hh + (size_t)(k + 9) * HAR + c0));
@@ -257,8 +284,8 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
   cluster.sync();
   const uint32_t ds_local = s_u32(&ds[0][0][0]), bar_local = s_u32(&dbar[0]);
 
-  // dh_{t-1} contribution of step `tt` (its dgh sits in ds[tt & 1]):  carry = direct + dgh . W_hh[:, slice]
-  auto consume = [&](int it) {  // it = iteration index of the step whose exchange we wait for
+  // finish step `it`: wait for its exchange, carry = direct + dgh . W_hh[:, slice]
+  auto consume = [&](int it) {
     const int tt = S - 1 - it, buf = tt & 1;
     mbar_wait(&dbar[buf], (it >> 1) & 1);
     if (threadIdx.x == 0 && it + 2 < S) mbar_expect_tx(&dbar[buf], kStepBytes);
@@ -268,14 +295,24 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
 #pragma unroll
       for (int e = 0; e < 4; e++) acc[a3][e] = 0.f;
 #pragma unroll
-    for (int q = 0; q < KS / 2; q++) {
+    for (int q = 0; q < KSH / 2; q++) {
       uint32_t bq4[4];
-      ldsm_x4_t(bq4, s_u32(&ds[buf][32 * q + lane][0]));
+      ldsm_x4_t(bq4, s_u32(&ds[buf][kh * (G / 2) + 32 * q + lane][0]));
       mma16816(acc[q % 3], wf[2 * q], bq4[0], bq4[1]);
-      mma16816(acc[q % 3], wf[2 * q + 1], bq4[2], bq4[3]);
+      mma16816(acc[(q + 1) % 3], wf[2 * q + 1], bq4[2], bq4[3]);
     }
+    float a[4];
 #pragma unroll
-    for (int e = 0; e < 4; e++) carry[e] = direct[e] + (acc[0][e] + acc[1][e]) + acc[2][e];
+    for (int e = 0; e < 4; e++) a[e] = (acc[0][e] + acc[1][e]) + acc[2][e];
+    if (kh == 1) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) part[ub][e][lane] = a[e];
+    }
+    pair_sync(ub);
+    if (kh == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) carry[e] = direct[e] + a[e] + part[ub][e][lane];
+    }
   };
 
   for (int it = 0; it < S; it++) {
@@ -285,9 +322,9 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     uint32_t gRU[4], gNH[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const int col = HC * rank + 16 * warp + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
+      const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
       dcv[e] = 0.f; hp[e] = 0.f; gRU[e] = 0u; gNH[e] = 0u;
-      if (bq < B) {
+      if (kh == 0 && bq < B) {
         const size_t o = ((size_t)bq * S + t) * HAR + col;
         dcv[e] = dc[o];
         gRU[e] = (uint32_t)__bfloat16_as_ushort(sR[o]) | ((uint32_t)__bfloat16_as_ushort(sU[o]) << 16);
@@ -295,30 +332,30 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
         hp[e] = t > 0 ? c[o - HAR] : (h0 != nullptr ? h0[(size_t)bq * HAR + col] : 0.f);
       }
     }
-    // (B) finish the previous step: wait for its exchange, dh += dgh . W_hh
+    // (B) finish the previous step
     if (it > 0) consume(it - 1);
     // (C) gate gradients of step t, publish dgh_t
-    float dr[4], du[4], dnr[4];
+    if (kh == 0) {
+      float dr[4], du[4], dnr[4];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int col = HC * rank + 16 * warp + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
-      dr[e] = du[e] = dnr[e] = direct[e] = 0.f;
-      if (bq < B) {
-        const float dh = carry[e] + dcv[e];
-        const float rg = __uint_as_float(gRU[e] << 16), ug = __uint_as_float(gRU[e] & 0xffff0000u);
-        const float ng = __uint_as_float(gNH[e] << 16), hnv = __uint_as_float(gNH[e] & 0xffff0000u);
-        const float dn = dh * (1.f - ug) * (1.f - ng * ng);
-        du[e] = dh * (hp[e] - ng) * ug * (1.f - ug);
-        dr[e] = dn * hnv * rg * (1.f - rg);
-        dnr[e] = dn * rg;
-        direct[e] = dh * ug;
-        const size_t og = ((size_t)bq * S + t) * G + col;
-        dgi[og] = __float2bfloat16_rn(dr[e]); dgi[og + HAR] = __float2bfloat16_rn(du[e]); dgi[og + 2 * HAR] = __float2bfloat16_rn(dn);
-        dgh[og] = __float2bfloat16_rn(dr[e]); dgh[og + HAR] = __float2bfloat16_rn(du[e]); dgh[og + 2 * HAR] = __float2bfloat16_rn(dnr[e]);
+      for (int e = 0; e < 4; e++) {
+        const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
+        dr[e] = du[e] = dnr[e] = direct[e] = 0.f;
+        if (bq < B) {
+          const float dh = carry[e] + dcv[e];
+          const float rg = __uint_as_float(gRU[e] << 16), ug = __uint_as_float(gRU[e] & 0xffff0000u);
+          const float ng = __uint_as_float(gNH[e] << 16), hnv = __uint_as_float(gNH[e] & 0xffff0000u);
+          const float dn = dh * (1.f - ug) * (1.f - ng * ng);
+          du[e] = dh * (hp[e] - ng) * ug * (1.f - ug);
+          dr[e] = dn * hnv * rg * (1.f - rg);
+          dnr[e] = dn * rg;
+          direct[e] = dh * ug;
+          const size_t og = ((size_t)bq * S + t) * G + col;
+          dgi[og] = __float2bfloat16_rn(dr[e]); dgi[og + HAR] = __float2bfloat16_rn(du[e]); dgi[og + 2 * HAR] = __float2bfloat16_rn(dn);
+          dgh[og] = __float2bfloat16_rn(dr[e]); dgh[og + HAR] = __float2bfloat16_rn(du[e]); dgh[og + 2 * HAR] = __float2bfloat16_rn(dnr[e]);
+        }
       }
-    }
-    {
-      const int row0 = HC * rank + 16 * warp + g;
+      const int row0 = HC * rank + 16 * ub + g;
 #pragma unroll
       for (int pr = 0; pr < 8; pr++) {
         if (pr < CS) {
@@ -335,10 +372,10 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     }
   }
   consume(S - 1);
-  if (dh0 != nullptr) {
+  if (kh == 0 && dh0 != nullptr) {
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const int col = HC * rank + 16 * warp + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
+      const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
       if (bq < B) dh0[(size_t)bq * HAR + col] = carry[e];
     }
   }
@@ -349,7 +386,7 @@ template <class K>
 int launch_cluster(const char* name, K kernel, int cs, int nclusters, cudaStream_t st, void** args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs * nclusters);
-  cfg.blockDim = dim3(128);
+  cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
