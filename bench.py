@@ -216,6 +216,9 @@ def algorithmic_work(B, bf16):
     w["conv0_fwd"] = ("hbm", B * (WINDOW * 4 + L0 * H * es))
     w["conv0_bwd_du"] = ("hbm", B * (WINDOW * 4 + 2 * L0 * H * es))
     w["conv0_wgrad"] = ("hbm", B * (WINDOW * 4 + L0 * H * es))
+    w["conv0_fwd_mma"] = w["conv0_fwd"]
+    w["conv0_bwd_du_mma"] = w["conv0_bwd_du"]
+    w["conv0_wgrad_mma"] = w["conv0_wgrad"]
     w["cnorm_relu_fwd"] = ("hbm", sum(B * lo * H * es * 2 for lo in (1024, 512, 256, 128)) + B * 128 * H * 4)
     w["cnorm_relu_bwd"] = ("hbm", sum(B * lo * H * es * 3 for lo in (1024, 512, 256, 128)))
     w["gru_rec_fwd"] = ("hbm", B * S * (3 * H * es + H * 4 + 5 * H * es) + 3 * H * H * 4)

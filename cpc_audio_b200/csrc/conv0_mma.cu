@@ -1,0 +1,422 @@
+// conv0_mma.cu - conv0 + ChannelNorm + ReLU (cpc/model.py:100) for the bf16 path, forward and backward, with the
+// 10-tap convolution on mma.sync instead of 80 FFMA per lane per frame.
+//
+// A tile = 16 consecutive frames of one window x all H channels, owned by one warp:
+//   u[16 x H] = X[16 x 16] . W0^T[16 x H]     taps 0..9 = the 10 samples of the frame, tap 10 = 1.0 (carries the
+//                                             bias), taps 11..15 = 0.  X is split x = hi + lo (two bf16 MMAs) so
+//                                             the waveform keeps ~16 mantissa bits; W0 is bf16 like every weight
+//                                             of the tensor-core path.
+// Accumulator layout (m16n8k16): thread (g, t) holds rows g, g+8 and channels 8j+2t, 8j+2t+1 of every n-tile j,
+// so the ChannelNorm statistics of a frame are an in-thread sum over 2H/8 values plus two shuffles.
+// Tiles are staged through shared memory so that HBM sees 512-byte rows.
+#include "common.cuh"
+
+namespace cpcb200 {
+
+namespace {
+
+constexpr float kEps = 1e-5f;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// B fragments of W0^T for all n-tiles: b0 = taps (2t, 2t+1), b1 = taps (2t+8, 2t+9) with tap 10 = bias
+template <int H>
+__device__ __forceinline__ void load_wfrags(const float* __restrict__ w, const float* __restrict__ bias, int g, int t,
+                                            uint32_t (&wb)[H / 8][2]) {
+#pragma unroll
+  for (int j = 0; j < H / 8; j++) {
+    const int c = 8 * j + g;
+    wb[j][0] = pack_bf16(__ldg(w + c * 10 + 2 * t), __ldg(w + c * 10 + 2 * t + 1));
+    float lo = 0.f, hi = 0.f;
+    if (t == 0) { lo = __ldg(w + c * 10 + 8); hi = __ldg(w + c * 10 + 9); }
+    else if (t == 1) { lo = __ldg(bias + c); }
+    wb[j][1] = pack_bf16(lo, hi);
+  }
+}
+
+// A fragments (hi and lo parts) of the 16 frames starting at f0 of window xb
+__device__ __forceinline__ void load_xfrags(const float* __restrict__ xb, int L, int f0, int g, int t, uint32_t (&ah)[4],
+                                            uint32_t (&al)[4]) {
+  float v[2][4];  // [row half][tap 2t, 2t+1, 2t+8, 2t+9]
+#pragma unroll
+  for (int hf = 0; hf < 2; hf++) {
+    const int s0 = 5 * (f0 + g + 8 * hf) - 3;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int s = s0 + 2 * t + q;
+      v[hf][q] = (s >= 0 && s < L) ? __ldg(xb + s) : 0.f;
+    }
+    v[hf][2] = v[hf][3] = 0.f;
+    if (t == 0) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) { const int s = s0 + 8 + q; v[hf][2 + q] = (s >= 0 && s < L) ? __ldg(xb + s) : 0.f; }
+    } else if (t == 1) {
+      v[hf][2] = 1.f;  // bias tap
+    }
+  }
+  float h[2][4];
+#pragma unroll
+  for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) h[hf][q] = bf16_round(v[hf][q]);
+  ah[0] = pack_bf16(h[0][0], h[0][1]); ah[1] = pack_bf16(h[1][0], h[1][1]);
+  ah[2] = pack_bf16(h[0][2], h[0][3]); ah[3] = pack_bf16(h[1][2], h[1][3]);
+  al[0] = pack_bf16(v[0][0] - h[0][0], v[0][1] - h[0][1]); al[1] = pack_bf16(v[1][0] - h[1][0], v[1][1] - h[1][1]);
+  al[2] = pack_bf16(v[0][2] - h[0][2], v[0][3] - h[0][3]); al[3] = pack_bf16(v[1][2] - h[1][2], v[1][3] - h[1][3]);
+}
+
+// row statistics (model.py:52-54) of the two rows a thread holds: mean, rstd with unbiased variance
+template <int NT>
+__device__ __forceinline__ void tile_stats(const float (&acc)[NT][4], int H, float (&mean)[2], float (&rstd)[2]) {
+  float s[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NT; j++) { s[0] += acc[j][0] + acc[j][1]; s[1] += acc[j][2] + acc[j][3]; }
+#pragma unroll
+  for (int hf = 0; hf < 2; hf++) {
+    s[hf] += __shfl_xor_sync(0xffffffffu, s[hf], 1);
+    s[hf] += __shfl_xor_sync(0xffffffffu, s[hf], 2);
+    mean[hf] = s[hf] / (float)H;
+  }
+  float q[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NT; j++) {
+    float d0 = acc[j][0] - mean[0], d1 = acc[j][1] - mean[0], d2 = acc[j][2] - mean[1], d3 = acc[j][3] - mean[1];
+    q[0] = fmaf(d0, d0, q[0]); q[0] = fmaf(d1, d1, q[0]); q[1] = fmaf(d2, d2, q[1]); q[1] = fmaf(d3, d3, q[1]);
+  }
+#pragma unroll
+  for (int hf = 0; hf < 2; hf++) {
+    q[hf] += __shfl_xor_sync(0xffffffffu, q[hf], 1);
+    q[hf] += __shfl_xor_sync(0xffffffffu, q[hf], 2);
+    rstd[hf] = rsqrtf(q[hf] / (float)(H - 1) + kEps);
+  }
+}
+
+// copy a staged [16][H] bf16 tile (row stride RS bytes) to 16 consecutive global rows of H channels
+template <int H>
+__device__ __forceinline__ void tile_to_global(const unsigned char* st, bf16* __restrict__ dst, int lane) {
+  constexpr int SEGS = H / 8, RS = 2 * H + 16;
+#pragma unroll
+  for (int it = 0; it < (16 * SEGS) / 32; it++) {
+    const int flat = it * 32 + lane, r = flat / SEGS, sg = flat - r * SEGS;
+    const uint4 v = *reinterpret_cast<const uint4*>(st + r * RS + sg * 16);
+    *reinterpret_cast<uint4*>(dst + (size_t)r * H + sg * 8) = v;
+  }
+}
+template <int H>
+__device__ __forceinline__ void tile_from_global(unsigned char* st, const bf16* __restrict__ src, int lane) {
+  constexpr int SEGS = H / 8, RS = 2 * H + 16;
+#pragma unroll
+  for (int it = 0; it < (16 * SEGS) / 32; it++) {
+    const int flat = it * 32 + lane, r = flat / SEGS, sg = flat - r * SEGS;
+    *reinterpret_cast<uint4*>(st + r * RS + sg * 16) = *reinterpret_cast<const uint4*>(src + (size_t)r * H + sg * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward: x (B, L) fp32 -> y0 (B, kPad + L0 + kPad, H) bf16 (pads zeroed here)
+// ---------------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(128) conv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ gam,
+                                                             const float* __restrict__ bet, bf16* __restrict__ y, int B, int L,
+                                                             int L0) {
+  constexpr int NT = H / 8, RS = 2 * H + 16;
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* gb = reinterpret_cast<float*>(sm);                       // gamma[H], beta[H]
+  unsigned char* stage = sm + 2 * H * 4 + (threadIdx.x >> 5) * (16 * RS);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { gb[i] = gam[i]; gb[H + i] = bet[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t wb[NT][2];
+  load_wfrags<H>(w, bias, g, t, wb);
+  const int tpw = L0 / 16;  // tiles per window
+  const long long Lp0 = L0 + 2 * kPad;
+  for (int tile = warp; tile < B * tpw; tile += nwarps) {
+    const int b = tile / tpw, f0 = (tile - b * tpw) * 16;
+    uint32_t ah[4], al[4];
+    load_xfrags(x + (long long)b * L, L, f0, g, t, ah, al);
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      mma16816(acc[j], ah, wb[j][0], wb[j][1]);
+      mma16816(acc[j], al, wb[j][0], wb[j][1]);
+    }
+    float mean[2], rstd[2];
+    tile_stats<NT>(acc, H, mean, rstd);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const int c = 8 * j + 2 * t;
+      const float2 g2 = *reinterpret_cast<const float2*>(gb + c), b2 = *reinterpret_cast<const float2*>(gb + H + c);
+      const float y0 = fmaxf(fmaf((acc[j][0] - mean[0]) * rstd[0], g2.x, b2.x), 0.f);
+      const float y1 = fmaxf(fmaf((acc[j][1] - mean[0]) * rstd[0], g2.y, b2.y), 0.f);
+      const float y2 = fmaxf(fmaf((acc[j][2] - mean[1]) * rstd[1], g2.x, b2.x), 0.f);
+      const float y3 = fmaxf(fmaf((acc[j][3] - mean[1]) * rstd[1], g2.y, b2.y), 0.f);
+      *reinterpret_cast<uint32_t*>(stage + g * RS + c * 2) = pack_bf16(y0, y1);
+      *reinterpret_cast<uint32_t*>(stage + (g + 8) * RS + c * 2) = pack_bf16(y2, y3);
+    }
+    __syncwarp();
+    bf16* dst = y + ((long long)b * Lp0 + kPad + f0) * H;
+    tile_to_global<H>(stage, dst, lane);
+    if (f0 == 0 || f0 + 16 == L0) {  // zero rows around the window
+      bf16* pad = y + ((long long)b * Lp0 + (f0 == 0 ? 0 : kPad + L0)) * H;
+      for (int i = lane; i < kPad * H / 8; i += 32) reinterpret_cast<uint4*>(pad)[i] = make_uint4(0, 0, 0, 0);
+      if (f0 == 0 && f0 + 16 == L0) {
+        bf16* pad2 = y + ((long long)b * Lp0 + kPad + L0) * H;
+        for (int i = lane; i < kPad * H / 8; i += 32) reinterpret_cast<uint4*>(pad2)[i] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward part 1: recompute u, ChannelNorm+ReLU backward in place (dy0 -> du0), dbias0/dgamma0/dbeta0.
+// The three per-channel sums over frames are column sums of bf16 tiles: computed with MMAs against a ones
+// matrix (A = tile^T via ldmatrix.trans) and accumulated in shared memory.
+// ---------------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(128) conv0_bwd_du_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, const float* __restrict__ gam,
+                                                                const float* __restrict__ bet, bf16* __restrict__ dy,
+                                                                float* __restrict__ dbias, float* __restrict__ dgam,
+                                                                float* __restrict__ dbet, int B, int L, int L0) {
+  constexpr int NT = H / 8, RS = 2 * H + 16, TILE = 16 * RS;
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* gb = reinterpret_cast<float*>(sm);           // gamma[H], beta[H]
+  float* accs = gb + 2 * H;                           // [3][H]: dbias, dgamma, dbeta
+  unsigned char* wbase = sm + 5 * H * 4 + (threadIdx.x >> 5) * (3 * TILE);
+  unsigned char* t_du = wbase;                        // dy on input, du on output
+  unsigned char* t_dv = wbase + TILE;                 // dv = dy masked by the ReLU
+  unsigned char* t_dvx = wbase + 2 * TILE;            // dv * xhat
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { gb[i] = gam[i]; gb[H + i] = bet[i]; }
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) accs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t wb[NT][2];
+  load_wfrags<H>(w, bias, g, t, wb);
+  const int tpw = L0 / 16;
+  const uint32_t ones = 0x3f803f80u;  // bf16 (1, 1)
+  for (int tile = warp; tile < B * tpw; tile += nwarps) {
+    const int b = tile / tpw, f0 = (tile - b * tpw) * 16;
+    bf16* drow = dy + ((long long)b * L0 + f0) * H;
+    tile_from_global<H>(t_du, drow, lane);
+    uint32_t ah[4], al[4];
+    load_xfrags(x + (long long)b * L, L, f0, g, t, ah, al);
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      mma16816(acc[j], ah, wb[j][0], wb[j][1]);
+      mma16816(acc[j], al, wb[j][0], wb[j][1]);
+    }
+    float mean[2], rstd[2];
+    tile_stats<NT>(acc, H, mean, rstd);
+    __syncwarp();
+    // pass 1: xhat (kept in acc), dv, dv*xhat tiles, row sums s1 = sum dx, s2 = sum dx*xhat
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const int c = 8 * j + 2 * t;
+      const float2 g2 = *reinterpret_cast<const float2*>(gb + c), b2 = *reinterpret_cast<const float2*>(gb + H + c);
+      const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(t_du + g * RS + c * 2);
+      const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(t_du + (g + 8) * RS + c * 2);
+      const float dyv[4] = {__low2float(d01), __high2float(d01), __low2float(d23), __high2float(d23)};
+      const float gg[4] = {g2.x, g2.y, g2.x, g2.y}, bb[4] = {b2.x, b2.y, b2.x, b2.y};
+      float dv[4], dvx[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int hf = e >> 1;
+        const float xh = (acc[j][e] - mean[hf]) * rstd[hf];
+        dv[e] = fmaf(xh, gg[e], bb[e]) > 0.f ? dyv[e] : 0.f;
+        dvx[e] = dv[e] * xh;
+        const float dx = dv[e] * gg[e];
+        s1[hf] += dx;
+        s2[hf] = fmaf(dx, xh, s2[hf]);
+        acc[j][e] = xh;
+      }
+      *reinterpret_cast<uint32_t*>(t_dv + g * RS + c * 2) = pack_bf16(dv[0], dv[1]);
+      *reinterpret_cast<uint32_t*>(t_dv + (g + 8) * RS + c * 2) = pack_bf16(dv[2], dv[3]);
+      *reinterpret_cast<uint32_t*>(t_dvx + g * RS + c * 2) = pack_bf16(dvx[0], dvx[1]);
+      *reinterpret_cast<uint32_t*>(t_dvx + (g + 8) * RS + c * 2) = pack_bf16(dvx[2], dvx[3]);
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {
+      s1[hf] += __shfl_xor_sync(0xffffffffu, s1[hf], 1); s1[hf] += __shfl_xor_sync(0xffffffffu, s1[hf], 2);
+      s2[hf] += __shfl_xor_sync(0xffffffffu, s2[hf], 1); s2[hf] += __shfl_xor_sync(0xffffffffu, s2[hf], 2);
+      s1[hf] /= (float)H;
+      s2[hf] /= (float)(H - 1);
+    }
+    // pass 2: du = rstd * (dx - s1 - xhat * s2), written over the dy tile
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const int c = 8 * j + 2 * t;
+      const float2 g2 = *reinterpret_cast<const float2*>(gb + c);
+      const __nv_bfloat162 v01 = *reinterpret_cast<const __nv_bfloat162*>(t_dv + g * RS + c * 2);
+      const __nv_bfloat162 v23 = *reinterpret_cast<const __nv_bfloat162*>(t_dv + (g + 8) * RS + c * 2);
+      const float o0 = rstd[0] * (__low2float(v01) * g2.x - s1[0] - acc[j][0] * s2[0]);
+      const float o1 = rstd[0] * (__high2float(v01) * g2.y - s1[0] - acc[j][1] * s2[0]);
+      const float o2 = rstd[1] * (__low2float(v23) * g2.x - s1[1] - acc[j][2] * s2[1]);
+      const float o3 = rstd[1] * (__high2float(v23) * g2.y - s1[1] - acc[j][3] * s2[1]);
+      *reinterpret_cast<uint32_t*>(t_du + g * RS + c * 2) = pack_bf16(o0, o1);
+      *reinterpret_cast<uint32_t*>(t_du + (g + 8) * RS + c * 2) = pack_bf16(o2, o3);
+    }
+    __syncwarp();
+    tile_to_global<H>(t_du, drow, lane);
+    // column sums over the 16 frames of du, dv*xhat, dv:  [16 ch x 8] = tile^T[16 ch x 16 frames] . ones
+#pragma unroll
+    for (int m = 0; m < H / 16; m++) {
+      const int mi = lane >> 3;
+      const uint32_t off = ((mi >> 1) * 8 + (lane & 7)) * RS + (m * 16 + (mi & 1) * 8) * 2;
+      uint32_t a[4];
+      float cs[4];
+      ldsm_x4_t(a, s_u32(t_du + off));
+      cs[0] = cs[1] = cs[2] = cs[3] = 0.f; mma16816(cs, a, ones, ones);
+      if (t == 0) { atomicAdd(&accs[m * 16 + g], cs[0]); atomicAdd(&accs[m * 16 + g + 8], cs[2]); }
+      ldsm_x4_t(a, s_u32(t_dvx + off));
+      cs[0] = cs[1] = cs[2] = cs[3] = 0.f; mma16816(cs, a, ones, ones);
+      if (t == 0) { atomicAdd(&accs[H + m * 16 + g], cs[0]); atomicAdd(&accs[H + m * 16 + g + 8], cs[2]); }
+      ldsm_x4_t(a, s_u32(t_dv + off));
+      cs[0] = cs[1] = cs[2] = cs[3] = 0.f; mma16816(cs, a, ones, ones);
+      if (t == 0) { atomicAdd(&accs[2 * H + m * 16 + g], cs[0]); atomicAdd(&accs[2 * H + m * 16 + g + 8], cs[2]); }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(dbias + i, accs[i]); atomicAdd(dgam + i, accs[H + i]); atomicAdd(dbet + i, accs[2 * H + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward part 2: dW0[c][tap] += sum_frames du0[frame][c] * x[5 frame - 3 + tap]
+//   D[16 ch x 8 taps] (x2 n-tiles: taps 0-7, 8-15) += du^T[16 ch x 16 frames] . X[16 frames x taps]
+// accumulated in registers over all the tiles of a warp (x in bf16: weight-gradient precision).
+// ---------------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(128) conv0_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ du,
+                                                               float* __restrict__ dw, int B, int L, int L0) {
+  constexpr int MT = H / 16, RS = 2 * H + 16, TILE = 16 * RS;
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* accs = reinterpret_cast<float*>(sm);  // [H][10]
+  unsigned char* stage = sm + H * 10 * 4 + (threadIdx.x >> 5) * TILE;
+  for (int i = threadIdx.x; i < H * 10; i += blockDim.x) accs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float acc[MT][2][4];
+#pragma unroll
+  for (int m = 0; m < MT; m++)
+#pragma unroll
+    for (int n = 0; n < 2; n++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[m][n][e] = 0.f;
+  const int tpw = L0 / 16;
+  for (int tile = warp; tile < B * tpw; tile += nwarps) {
+    const int b = tile / tpw, f0 = (tile - b * tpw) * 16;
+    tile_from_global<H>(stage, du + ((long long)b * L0 + f0) * H, lane);
+    // B fragments: X[k = frame][n = tap]: b0 = frames (2t, 2t+1), b1 = frames (2t+8, 2t+9); n = g (taps 0-7) / g+8
+    const float* xb = x + (long long)b * L;
+    uint32_t bx[2][2];
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      const int tap = g + 8 * n;
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int fr = f0 + 2 * t + (q & 1) + 8 * (q >> 1);
+        const int s = 5 * fr - 3 + tap;
+        v[q] = (tap < 10 && s >= 0 && s < L) ? __ldg(xb + s) : 0.f;
+      }
+      bx[n][0] = pack_bf16(v[0], v[1]);
+      bx[n][1] = pack_bf16(v[2], v[3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+      const int mi = lane >> 3;
+      uint32_t a[4];
+      ldsm_x4_t(a, s_u32(stage + ((mi >> 1) * 8 + (lane & 7)) * RS + (m * 16 + (mi & 1) * 8) * 2));
+      mma16816(acc[m][0], a, bx[0][0], bx[0][1]);
+      mma16816(acc[m][1], a, bx[1][0], bx[1][1]);
+    }
+    __syncwarp();
+  }
+  // D fragment: rows = channels 16m + g (+8), cols = taps 8n + 2t (+1)
+#pragma unroll
+  for (int m = 0; m < MT; m++)
+#pragma unroll
+    for (int n = 0; n < 2; n++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int c = 16 * m + g + 8 * (e >> 1), tap = 8 * n + 2 * t + (e & 1);
+        if (tap < 10) atomicAdd(&accs[c * 10 + tap], acc[m][n][e]);
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * 10; i += blockDim.x) atomicAdd(dw + i, accs[i]);
+}
+
+template <int H>
+int launch_all_fwd(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* y, int B, int L,
+                   int L0, cudaStream_t st) {
+  const size_t smem = 2 * H * 4 + 4 * 16 * (2 * H + 16);
+  int blocks = (B * (L0 / 16) + 3) / 4;
+  if (blocks > 148 * 3) blocks = 148 * 3;
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_fwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv0_fwd_mma_kernel<H><<<blocks, 128, smem, st>>>(x, w, bias, gam, bet, y, B, L, L0);
+  CPC_LAUNCHED_N("conv0_fwd_mma", st);
+  return 0;
+}
+template <int H>
+int launch_all_bwd(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* dy, float* dw,
+                   float* dbias, float* dgam, float* dbet, int B, int L, int L0, cudaStream_t st) {
+  const size_t smem1 = 5 * H * 4 + 4 * 3 * 16 * (2 * H + 16);
+  const size_t smem2 = H * 10 * 4 + 4 * 16 * (2 * H + 16);
+  int blocks = (B * (L0 / 16) + 3) / 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd_du_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  conv0_bwd_du_mma_kernel<H><<<blocks, 128, smem1, st>>>(x, w, bias, gam, bet, dy, dbias, dgam, dbet, B, L, L0);
+  CPC_LAUNCHED_N("conv0_bwd_du_mma", st);
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_wgrad_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  conv0_wgrad_mma_kernel<H><<<blocks, 128, smem2, st>>>(x, dy, dw, B, L, L0);
+  CPC_LAUNCHED_N("conv0_wgrad_mma", st);
+  return 0;
+}
+
+}  // namespace
+
+bool conv0_mma_supported(int H) { return H == 64 || H == 128 || H == 256; }
+
+int conv0_fwd_mma(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* y, int B, int L, int L0,
+                  int H, cudaStream_t st) {
+  if (H == 256) return launch_all_fwd<256>(x, w, bias, gam, bet, y, B, L, L0, st);
+  if (H == 128) return launch_all_fwd<128>(x, w, bias, gam, bet, y, B, L, L0, st);
+  return launch_all_fwd<64>(x, w, bias, gam, bet, y, B, L, L0, st);
+}
+int conv0_bwd_mma(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* dy, float* dw,
+                  float* dbias, float* dgam, float* dbet, int B, int L, int L0, int H, cudaStream_t st) {
+  if (H == 256) return launch_all_bwd<256>(x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0, st);
+  if (H == 128) return launch_all_bwd<128>(x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0, st);
+  return launch_all_bwd<64>(x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0, st);
+}
+
+}  // namespace cpcb200

@@ -16,6 +16,12 @@ namespace cpcb200 {
 int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias,
             const OutView& C, cudaStream_t st);
 
+bool conv0_mma_supported(int H);
+int conv0_fwd_mma(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* y, int B, int L, int L0,
+                  int H, cudaStream_t st);
+int conv0_bwd_mma(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* dy, float* dw,
+                  float* dbias, float* dgam, float* dbet, int B, int L, int L0, int H, cudaStream_t st);
+
 namespace {
 
 constexpr float kEps = 1e-5f;  // cpc/model.py:29
@@ -492,7 +498,14 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   }
   // the zero rows around every window of y0..y3 are written by the kernels that produce the interior
   const int I = ilog_I(H);
-  {
+  bool c0_done = false;
+  if constexpr (sizeof(T) == 2) {
+    if (conv0_mma_supported(H)) {
+      CPC_TRY(conv0_fwd_mma(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0], sv + e.y[0], B, g.L, g.Lout[0], H, st));
+      c0_done = true;
+    }
+  }
+  if (!c0_done) {
     const size_t smem = 3 * (size_t)H * sizeof(float);
     int blocks = (B * (g.Lout[0] / kC0Chunk) + 3) / 4;
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -576,7 +589,15 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       CPC_TRY(gemm_nt(g.bf16, false, B, s * H, 2 * H, A, wd[i], nullptr, C, st));
     }
   }
-  {
+  bool c0_done = false;
+  if constexpr (sizeof(T) == 2) {
+    if (conv0_mma_supported(H)) {
+      CPC_TRY(conv0_bwd_mma(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0], dy[0], gr->conv_w[0], gr->conv_b[0],
+                            gr->norm_w[0], gr->norm_b[0], B, g.L, g.Lout[0], H, st));
+      c0_done = true;
+    }
+  }
+  if (!c0_done) {
     int blocks = (B * (g.Lout[0] / kC0Chunk) + 3) / 4;
     if (blocks > 148 * 4) blocks = 148 * 4;
     const size_t smem1 = 6 * (size_t)H * sizeof(float), smem2 = 10 * (size_t)H * sizeof(float);

@@ -48,6 +48,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) 
 __device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, uint32_t remote_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
 }
+// one bulk copy local shared -> a peer's shared memory, completing `bytes` on the peer's mbarrier
+__device__ __forceinline__ void bulk_s2s(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
 }
@@ -90,6 +96,7 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
 
   __shared__ __align__(128) bf16 hs[2][HAR][BT];  // h_{t-1} as the B operand: [k][sequence]
   __shared__ float part[4][12][32];                // partial sums of the upper k half, per unit block
+  __shared__ __align__(128) bf16 hstage[2][4][16][BT];  // new units of one warp, staged for the bulk copies
   __shared__ __align__(8) uint64_t hbar[2];        // hbar[b] completes when buffer b holds a full new state
   constexpr uint32_t kStepBytes = HAR * BT * 2;
   if (threadIdx.x == 0) {
@@ -214,18 +221,15 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
         }
       }
       // publish the 64 new units to every CTA of the cluster: rows (unit), 2 sequences per 32-bit st.async
+      // ONE 256-byte bulk copy per destination CTA (the mbarrier handles 16 transactions per step, not 1024)
       if (t + 1 < S) {
-        const uint32_t v0 = pack_bf16(hn[0], hn[1]), v1 = pack_bf16(hn[2], hn[3]);
-        const int row0 = HC * rank + 16 * ub + g;
-        const uint32_t off0 = (uint32_t)(((size_t)nxt * HAR + row0) * BT + 2 * t4) * 2;
-        const uint32_t off1 = off0 + 8 * BT * 2;
-#pragma unroll
-        for (int pr = 0; pr < 8; pr++) {
-          if (pr < CS) {
-            const uint32_t ph = mapa_u32(hs_local, pr), pb = mapa_u32(bar_local + nxt * 8, pr);
-            st_async_u32(ph + off0, v0, pb);
-            st_async_u32(ph + off1, v1, pb);
-          }
+        *reinterpret_cast<uint32_t*>(&hstage[cur][ub][g][2 * t4]) = pack_bf16(hn[0], hn[1]);
+        *reinterpret_cast<uint32_t*>(&hstage[cur][ub][g + 8][2 * t4]) = pack_bf16(hn[2], hn[3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane < CS) {
+          const uint32_t dst = mapa_u32(hs_local + (uint32_t)(((size_t)nxt * HAR + HC * rank + 16 * ub) * BT) * 2, lane);
+          bulk_s2s(dst, s_u32(&hstage[cur][ub][0][0]), 16 * BT * 2, mapa_u32(bar_local + nxt * 8, lane));
         }
       }
     }
@@ -254,6 +258,7 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
 
   __shared__ __align__(128) bf16 ds[2][G][BT];  // dgh_t as the B operand: [gate index][sequence]
   __shared__ float part[4][4][32];
+  __shared__ __align__(128) bf16 dstage[2][4][3][16][BT];
   __shared__ __align__(8) uint64_t dbar[2];
   constexpr uint32_t kStepBytes = G * BT * 2;
   if (threadIdx.x == 0) {
@@ -355,19 +360,18 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
           dgh[og] = __float2bfloat16_rn(dr[e]); dgh[og + HAR] = __float2bfloat16_rn(du[e]); dgh[og + 2 * HAR] = __float2bfloat16_rn(dnr[e]);
         }
       }
-      const int row0 = HC * rank + 16 * ub + g;
 #pragma unroll
-      for (int pr = 0; pr < 8; pr++) {
-        if (pr < CS) {
-          const uint32_t pd = mapa_u32(ds_local, pr), pb = mapa_u32(bar_local + buf * 8, pr);
-#pragma unroll
-          for (int hf = 0; hf < 2; hf++) {
-            const uint32_t base = pd + (uint32_t)(((size_t)buf * G + row0 + 8 * hf) * BT + 2 * t4) * 2;
-            st_async_u32(base, pack_bf16(dr[2 * hf], dr[2 * hf + 1]), pb);
-            st_async_u32(base + HAR * BT * 2, pack_bf16(du[2 * hf], du[2 * hf + 1]), pb);
-            st_async_u32(base + 2 * HAR * BT * 2, pack_bf16(dnr[2 * hf], dnr[2 * hf + 1]), pb);
-          }
-        }
+      for (int hf = 0; hf < 2; hf++) {
+        *reinterpret_cast<uint32_t*>(&dstage[buf][ub][0][g + 8 * hf][2 * t4]) = pack_bf16(dr[2 * hf], dr[2 * hf + 1]);
+        *reinterpret_cast<uint32_t*>(&dstage[buf][ub][1][g + 8 * hf][2 * t4]) = pack_bf16(du[2 * hf], du[2 * hf + 1]);
+        *reinterpret_cast<uint32_t*>(&dstage[buf][ub][2][g + 8 * hf][2 * t4]) = pack_bf16(dnr[2 * hf], dnr[2 * hf + 1]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane < 3 * CS) {  // lane -> (destination CTA, gate block): one 256-byte bulk copy each
+        const int pr = lane / 3, gt = lane - 3 * pr;
+        const uint32_t dst = mapa_u32(ds_local + (uint32_t)(((size_t)buf * G + gt * HAR + HC * rank + 16 * ub) * BT) * 2, pr);
+        bulk_s2s(dst, s_u32(&dstage[buf][ub][gt][0][0]), 16 * BT * 2, mapa_u32(bar_local + buf * 8, pr));
       }
     }
   }

@@ -19,8 +19,10 @@ namespace cpcb200 {
 
 namespace {
 
-constexpr int CH = 32;    // candidate rows per gather chunk (2 m-tiles)
-constexpr int NNEG = 4;   // negative chunks per position: the tensor-core path is specialised for N = 128
+constexpr int CH = 16;    // candidate rows per gather chunk (CH/16 m-tiles); small chunks -> more warps per SM
+constexpr int MPC = CH / 16;
+constexpr int NNEG = 8;   // negative chunks per position: the tensor-core path is specialised for N = NNEG*CH = 128
+constexpr int NMT = NNEG * MPC;  // m-tiles of negatives; m-tile NMT holds the positives
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -99,7 +101,7 @@ __device__ __forceinline__ void gather_rows(unsigned char* buf, const bf16* __re
 // forward
 // ---------------------------------------------------------------------------------------------------------
 template <int H>
-__global__ void __launch_bounds__(192) score_fwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
+__global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
                                                              const int* __restrict__ ext_t, float* __restrict__ lossbuf,
                                                              float* __restrict__ corrbuf, float* __restrict__ lsebuf, int B,
                                                              int S, int W, int K, int N, int warps_per_cta) {
@@ -120,27 +122,27 @@ __global__ void __launch_bounds__(192) score_fwd_mma_kernel(const bf16* __restri
     const int b = p / W, w = p - b * W;
     stage_pred<H>(psm, pred + (size_t)p * K * H, K, lane);
     {
-      const int row = ext_t[(size_t)p * N + lane];
+      const int row = lane < CH ? ext_t[(size_t)p * N + lane] : 0;
       gather_rows<H>(cbuf, z, row, CH, lane);
     }
     cp_async_commit();
     uint32_t bfr[C::KS][4];
-    float acc[9][2][4];
+    float acc[NMT + 1][2][4];
 #pragma unroll
-    for (int m = 0; m < 9; m++)
+    for (int m = 0; m < NMT + 1; m++)
 #pragma unroll
       for (int n = 0; n < 2; n++)
 #pragma unroll
         for (int e = 0; e < 4; e++) acc[m][n][e] = 0.f;
 
 #pragma unroll
-    for (int c = 0; c < 5; c++) {
+    for (int c = 0; c < NNEG + 1; c++) {
       if (c < nchunks) {
         unsigned char* cur = cbuf + (c & 1) * C::CBUF;
         if (c + 1 < nchunks) {
           unsigned char* nxt = cbuf + ((c + 1) & 1) * C::CBUF;
           if (c + 1 < nneg) {
-            const int row = ext_t[(size_t)p * N + (c + 1) * CH + lane];
+            const int row = lane < CH ? ext_t[(size_t)p * N + (c + 1) * CH + lane] : 0;
             gather_rows<H>(nxt, z, row, CH, lane);
           } else {
             const int row = b * S + w + 1 + (lane < K ? lane : 0);
@@ -161,12 +163,12 @@ __global__ void __launch_bounds__(192) score_fwd_mma_kernel(const bf16* __restri
             ldsm_x4(bfr[ks], s_u32(psm + ((mi >> 1) * 8 + (lane & 7)) * C::RS + (ks * 16 + (mi & 1) * 8) * 2));
           }
         }
-        const int mts = (c < nneg) ? 2 : 1;
+        const int mts = (c < nneg) ? MPC : 1;
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
+        for (int mt = 0; mt < MPC; mt++) {
           if (mt < mts) {
-            const int m = (c < nneg) ? (c * 2 + mt) : 8;
-            if (m < 9) {
+            const int m = (c < nneg) ? (c * MPC + mt) : NMT;
+            if (m < NMT + 1) {
 #pragma unroll
               for (int ks = 0; ks < C::KS; ks++) {
                 uint32_t a[4];
@@ -187,11 +189,10 @@ __global__ void __launch_bounds__(192) score_fwd_mma_kernel(const bf16* __restri
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int k = nt * 8 + 2 * t + e;
-        const float pos = __shfl_sync(0xffffffffu, acc[8][nt][2 * nt + e], (2 * t + e) * 4 + t) * invH;
+        const float pos = __shfl_sync(0xffffffffu, acc[NMT][nt][2 * nt + e], (2 * t + e) * 4 + t) * invH;
         float mx = -INFINITY;
 #pragma unroll
-        for (int m = 0; m < 8; m++)
-          if (m < 2 * nneg) mx = fmaxf(mx, fmaxf(acc[m][nt][e], acc[m][nt][2 + e]));
+        for (int m = 0; m < NMT; m++) mx = fmaxf(mx, fmaxf(acc[m][nt][e], acc[m][nt][2 + e]));
         mx *= invH;
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
@@ -199,8 +200,7 @@ __global__ void __launch_bounds__(192) score_fwd_mma_kernel(const bf16* __restri
         const float M = fmaxf(mx, pos);
         float sum = 0.f;
 #pragma unroll
-        for (int m = 0; m < 8; m++)
-          if (m < 2 * nneg) sum += __expf(acc[m][nt][e] * invH - M) + __expf(acc[m][nt][2 + e] * invH - M);
+        for (int m = 0; m < NMT; m++) sum += __expf(acc[m][nt][e] * invH - M) + __expf(acc[m][nt][2 + e] * invH - M);
         sum += __shfl_xor_sync(0xffffffffu, sum, 4);
         sum += __shfl_xor_sync(0xffffffffu, sum, 8);
         sum += __shfl_xor_sync(0xffffffffu, sum, 16);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(192) score_fwd_mma_kernel(const bf16* __restri
 // backward
 // ---------------------------------------------------------------------------------------------------------
 template <int H>
-__global__ void __launch_bounds__(96) score_bwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
+__global__ void __launch_bounds__(160) score_bwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
                                                             const int* __restrict__ ext_t, const float* __restrict__ lsebuf,
                                                             const float* __restrict__ dloss, bf16* __restrict__ dpred,
                                                             float* __restrict__ dz, int B, int S, int W, int K, int N,
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(96) score_bwd_mma_kernel(const bf16* __restric
   for (int p = blockIdx.x * warps_per_cta + warp; p < P; p += gridDim.x * warps_per_cta) {
     const int b = p / W, w = p - b * W;
     stage_pred<H>(psm, pred + (size_t)p * K * H, K, lane);
-    int my_row = ext_t[(size_t)p * N + lane];
+    int my_row = lane < CH ? ext_t[(size_t)p * N + lane] : 0;
     gather_rows<H>(cbuf, z, my_row, CH, lane);
     cp_async_commit();
     float lse[2][2], gk[2][2];
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(96) score_bwd_mma_kernel(const bf16* __restric
       if (c + 1 < nchunks) {
         unsigned char* nxt = cbuf + ((c + 1) & 1) * C::CBUF;
         if (c + 1 < nneg) {
-          my_row = ext_t[(size_t)p * N + (c + 1) * CH + lane];
+          my_row = lane < CH ? ext_t[(size_t)p * N + (c + 1) * CH + lane] : 0;
           gather_rows<H>(nxt, z, my_row, CH, lane);
         } else {
           my_row = b * S + w + 1 + (lane < K ? lane : 0);
@@ -286,11 +286,11 @@ __global__ void __launch_bounds__(96) score_bwd_mma_kernel(const bf16* __restric
       }
       __syncwarp();
       const bool is_pos = c >= nneg;
-      const int mts = is_pos ? 1 : 2;
+      const int mts = is_pos ? 1 : MPC;
       // ---- logits of this chunk: L[mt][nt] ----
-      float L[2][2][4];
+      float L[MPC][2][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++)
+      for (int mt = 0; mt < MPC; mt++)
 #pragma unroll
         for (int n = 0; n < 2; n++)
 #pragma unroll
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(96) score_bwd_mma_kernel(const bf16* __restric
         const int mi = lane >> 3;
         ldsm_x4(bq, s_u32(psm + ((mi >> 1) * 8 + (lane & 7)) * C::RS + (ks * 16 + (mi & 1) * 8) * 2));
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
+        for (int mt = 0; mt < MPC; mt++) {
           if (mt < mts) {
             uint32_t a[4];
             ldsm_x4(a, s_u32(cur + (mt * 16 + (mi & 1) * 8 + (lane & 7)) * C::RS + (ks * 16 + (mi >> 1) * 8) * 2));
@@ -311,9 +311,9 @@ __global__ void __launch_bounds__(96) score_bwd_mma_kernel(const bf16* __restric
         }
       }
       // ---- G = (softmax - onehot) * dloss / (P*H); A fragments for dz and Gs[k][j] for dpred ----
-      uint32_t ga[2][4];
+      uint32_t ga[MPC][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
+      for (int mt = 0; mt < MPC; mt++) {
         float G[2][4];
 #pragma unroll
         for (int nt = 0; nt < 2; nt++)
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(96) score_bwd_mma_kernel(const bf16* __restric
       __syncwarp();
       // ---- dz rows of this chunk: D2[16 j][H] = G^T . pred, staged then added to HBM by the TMA engine ----
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
+      for (int mt = 0; mt < MPC; mt++) {
         if (mt < mts) {
           if (lane < 16) bulk_wait_read0();  // the staging tile is free again
           __syncwarp();
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(96) score_bwd_mma_kernel(const bf16* __restric
       }
       // ---- dpred += G . cand ----
 #pragma unroll
-      for (int ks = 0; ks < 2; ks++) {
+      for (int ks = 0; ks < MPC; ks++) {
         if (ks < mts) {
           uint32_t a[4];
           const int mi = lane >> 3;
@@ -403,8 +403,8 @@ template <int H> constexpr size_t bwd_warp_smem() { return Cfg<H>::PSM + 2 * Cfg
 template <int H>
 int launch_fwd(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf, float* corrbuf, float* lsebuf, int B, int S,
                int W, int K, int N, cudaStream_t st) {
-  int wpc = (int)((200 * 1024) / fwd_warp_smem<H>());
-  if (wpc > 6) wpc = 6;
+  int wpc = (int)((216 * 1024) / fwd_warp_smem<H>());
+  if (wpc > 8) wpc = 8;
   const size_t smem = wpc * fwd_warp_smem<H>();
   CPC_CHECK_CUDA(cudaFuncSetAttribute(score_fwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_fwd_mma_kernel<H><<<148, wpc * 32, smem, st>>>(pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, wpc);
@@ -414,8 +414,8 @@ int launch_fwd(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf
 template <int H>
 int launch_bwd(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred, float* dz,
                int B, int S, int W, int K, int N, cudaStream_t st) {
-  int wpc = (int)((200 * 1024) / bwd_warp_smem<H>());
-  if (wpc > 3) wpc = 3;
+  int wpc = (int)((216 * 1024) / bwd_warp_smem<H>());
+  if (wpc > 5) wpc = 5;
   const size_t smem = wpc * bwd_warp_smem<H>();
   CPC_CHECK_CUDA(cudaFuncSetAttribute(score_bwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_bwd_mma_kernel<H><<<148, wpc * 32, smem, st>>>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, wpc);
