@@ -22,15 +22,19 @@ int score_fwd_mma(const bf16* pred, const bf16* z, const int* ext_t, float* loss
 int score_bwd_mma(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred,
                   float* dz, int B, int S, int W, int H, int K, int N, cudaStream_t st);
 
+int launch_cast3_bf16(const float* s0, bf16* d0, long long n0, const float* s1, bf16* d1, long long n1, const float* s2, bf16* d2,
+                      long long n2, cudaStream_t st);
+
 namespace {
 
 constexpr int KMAX = 16;
 
 __global__ void ext_idx_kernel(const long long* __restrict__ bi, const long long* __restrict__ si, int* __restrict__ ext,
                                long long n, int W, int S) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long w = i % W;
-    long long s = (si[i] + w) % S;  // torch.remainder of non-negative operands
+  const unsigned nn = (unsigned)n;  // n < 2^31 (checked on the host): 32-bit index arithmetic
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) {
+    const unsigned w = i % (unsigned)W;
+    long long s = (si[i] + (long long)w) % S;  // torch.remainder of non-negative operands
     if (s < 0) s += S;
     ext[i] = (int)(s + bi[i] * S);
   }
@@ -196,7 +200,7 @@ __global__ void score_bwd_kernel(const T* __restrict__ pred, const T* __restrict
   }
 }
 
-struct CritLayout { size_t pred, logits, lse, ext_t, total; bool mma; };
+struct CritLayout { size_t pred, logits, lse, ext_t, cT, zT, total; bool mma; };
 CritLayout crit_layout(const Geo& g) {
   CritLayout l{};
   const size_t es = g.bf16 ? 2 : 4;
@@ -210,6 +214,11 @@ CritLayout crit_layout(const Geo& g) {
     l.lse = l.logits;
     l.ext_t = l.lse + align_up(P * g.K * 4);
     l.total = l.ext_t + align_up(P * g.N * 4);
+  }
+  if (g.bf16) {  // bf16 copies of c and z made once in forward, reused by backward
+    l.cT = l.total;
+    l.zT = l.cT + align_up((size_t)g.B * g.S * g.Har * 2);
+    l.total = l.zT + align_up((size_t)g.B * g.S * g.H * 2);
   }
   return l;
 }
@@ -225,8 +234,8 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
   T* pred = reinterpret_cast<T*>(sv + lay.pred);
   float* logits = reinterpret_cast<float*>(sv + lay.logits);
   Carver ws(wsp, ws_bytes);
-  T* cT = ws.take<T>(isf ? 1 : (size_t)B * S * Har);
-  T* zT = ws.take<T>(isf ? 1 : (size_t)B * S * H);
+  T* cT = isf ? nullptr : reinterpret_cast<T*>(sv + lay.cT);
+  T* zT = isf ? nullptr : reinterpret_cast<T*>(sv + lay.zT);
   T* wT = ws.take<T>(isf ? 1 : (size_t)K * H * Har);
   float* lossbuf = ws.take<float>((size_t)P * K);
   float* corrbuf = ws.take<float>((size_t)P * K);
@@ -234,9 +243,8 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
   const T *cp, *zp, *wp;
   if (isf) { cp = reinterpret_cast<const T*>(c); zp = reinterpret_cast<const T*>(z); wp = reinterpret_cast<const T*>(w_pred); }
   else {
-    CPC_TRY(launch_cast<T>(c, cT, (long long)B * S * Har, st));
-    CPC_TRY(launch_cast<T>(z, zT, (long long)B * S * H, st));
-    CPC_TRY(launch_cast<T>(w_pred, wT, (long long)K * H * Har, st));
+    CPC_TRY(launch_cast3_bf16(c, reinterpret_cast<bf16*>(cT), (long long)B * S * Har, z, reinterpret_cast<bf16*>(zT),
+                              (long long)B * S * H, w_pred, reinterpret_cast<bf16*>(wT), (long long)K * H * Har, st));
     cp = cT; zp = zT; wp = wT;
   }
   // heads: pred[(b,w), (k,h)] = sum_a c[b,w,a] * Wk[h,a]
@@ -278,16 +286,14 @@ int criterion_bwd_t(const Geo& g, const float* c, const float* z, const float* w
   const T* pred = reinterpret_cast<const T*>(sv + lay.pred);
   const float* logits = reinterpret_cast<const float*>(sv + lay.logits);
   Carver ws(wsp, ws_bytes);
-  T* cT = ws.take<T>(isf ? 1 : (size_t)B * S * Har);
-  T* zT = ws.take<T>(isf ? 1 : (size_t)B * S * H);
+  const T* cT = isf ? nullptr : reinterpret_cast<const T*>(sv + lay.cT);
+  const T* zT = isf ? nullptr : reinterpret_cast<const T*>(sv + lay.zT);
   T* wTt = ws.take<T>((size_t)K * H * Har);  // transposed heads: [Har][K*H]
   T* dpred = ws.take<T>((size_t)P * K * H);
   if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "criterion_bwd: workspace %zu < %zu", ws_bytes, ws.off);
   const T *cp, *zp;
   if (isf) { cp = reinterpret_cast<const T*>(c); zp = reinterpret_cast<const T*>(z); }
   else {
-    CPC_TRY(launch_cast<T>(c, cT, (long long)B * S * Har, st));
-    CPC_TRY(launch_cast<T>(z, zT, (long long)B * S * H, st));
     cp = cT; zp = zT;
   }
   CPC_TRY(launch_transpose_cast<T>(w_pred, wTt, K * H, Har, st));
@@ -340,8 +346,6 @@ size_t criterion_ws_bytes(const Geo& g, int backward) {
   const size_t es = g.bf16 ? 2 : 4;
   const size_t P = (size_t)g.B * g.W;
   size_t tot = 0;
-  tot += align_up(g.bf16 ? (size_t)g.B * g.S * g.Har * es : 4);
-  tot += align_up(g.bf16 ? (size_t)g.B * g.S * g.H * es : 4);
   if (!backward) {
     tot += align_up(g.bf16 ? (size_t)g.K * g.H * g.Har * es : 4);
     tot += 2 * align_up(P * g.K * 4);

@@ -22,7 +22,8 @@ bool gru_mma_supported(int Har);
 int gru_rec_fwd_mma(const bf16* gi, const float* w_hh, const float* b_hh, const float* h0, float* c, bf16* cT, bf16* sR, bf16* sU,
                     bf16* sN, bf16* sHN, float* hT, int B, int S, int Har, cudaStream_t st);
 int gru_rec_bwd_mma(const float* dc, const float* c, const float* h0, const bf16* sR, const bf16* sU, const bf16* sN,
-                    const bf16* sHN, const float* w_hh, bf16* dgi, bf16* dgh, float* dh0, int B, int S, int Har, cudaStream_t st);
+                    const bf16* sHN, const float* w_hh, bf16* dgi, bf16* dgh, float* dh0, float* db_ih, float* db_hh, int B, int S,
+                    int Har, cudaStream_t st);
 
 namespace {
 
@@ -229,6 +230,20 @@ __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f<T>(src[i]);
 }
+__global__ void cast3_bf16_kernel(const float* __restrict__ s0, bf16* __restrict__ d0, long long n0, const float* __restrict__ s1,
+                                  bf16* __restrict__ d1, long long n1, const float* __restrict__ s2, bf16* __restrict__ d2,
+                                  long long n2) {
+  const long long n = n0 + n1 + n2;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+    const float* s; bf16* d; long long j;
+    if (i < n0) { s = s0; d = d0; j = i; } else if (i < n0 + n1) { s = s1; d = d1; j = i - n0; } else { s = s2; d = d2; j = i - n0 - n1; }
+    const float4 v = *reinterpret_cast<const float4*>(s + j);  // every tensor length is a multiple of 4
+    uint2 o;
+    *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(d + j) = o;
+  }
+}
 // dst[c][r] = src[r][c]
 template <class T>
 __global__ void transpose_cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int R, int C) {
@@ -258,6 +273,16 @@ __global__ void colsum_kernel(const T* __restrict__ src, float* __restrict__ out
 
 }  // namespace
 
+int launch_cast3_bf16(const float* s0, bf16* d0, long long n0, const float* s1, bf16* d1, long long n1, const float* s2, bf16* d2,
+                      long long n2, cudaStream_t st) {
+  if ((n0 | n1 | n2) & 3) return fail(CPCB200_ERR_BAD_DIMS, "cast3: lengths must be multiples of 4");
+  const long long n = n0 + n1 + n2;
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cast3_bf16_kernel<<<blocks, 256, 0, st>>>(s0, d0, n0, s1, d1, n1, s2, d2, n2);
+  CPC_LAUNCHED_N("cast3", st);
+  return 0;
+}
 template <class T> int launch_cast(const float* src, T* dst, long long n, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -288,6 +313,8 @@ template int launch_colsum<bf16>(const bf16*, float*, long long, int, cudaStream
 template int launch_colsum<float>(const float*, float*, long long, int, cudaStream_t);
 
 namespace {
+
+template <class T> constexpr bool isf_dummy() { return sizeof(T) == 4; }
 
 constexpr int kBT = 2;
 
@@ -322,6 +349,7 @@ struct GruLayout {
   size_t gates[CPCB200_MAX_GRU_LAYERS][4];  // byte offsets: R,U,N,HN (T)
   size_t cT[CPCB200_MAX_GRU_LAYERS];        // T copy of the layer output (bf16 path only)
   size_t cf[CPCB200_MAX_GRU_LAYERS];        // fp32 output of non-last layers
+  size_t inT;                               // bf16 copy of z (layer-0 input), bf16 path only
   size_t total;
 };
 GruLayout gru_layout(const Geo& g) {
@@ -335,6 +363,7 @@ GruLayout gru_layout(const Geo& g) {
     l.cT[i] = g.bf16 ? take(n * es) : 0;
     l.cf[i] = (i < g.nL - 1) ? take(n * 4) : 0;
   }
+  l.inT = g.bf16 ? take((size_t)g.B * g.S * g.H * 2) : 0;
   l.total = off;
   return l;
 }
@@ -351,7 +380,7 @@ int gru_fwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
   char* sv = static_cast<char*>(save);
   Carver ws(wsp, ws_bytes);
   const int Hmax = g.H > Har ? g.H : Har;
-  T* inT = ws.take<T>((size_t)B * S * g.H);
+  T* inT = isf_dummy<T>() ? ws.take<T>(1) : reinterpret_cast<T*>(sv + lay.inT);
   T* wih = ws.take<T>((size_t)3 * Har * Hmax);
   T* gi = ws.take<T>((size_t)B * S * 3 * Har);
   if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "gru_fwd: workspace %zu < %zu", ws_bytes, ws.off);
@@ -365,9 +394,14 @@ int gru_fwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
       in = reinterpret_cast<const T*>(l == 0 ? z : reinterpret_cast<const float*>(sv + lay.cf[l - 1]));
       w = reinterpret_cast<const T*>(p->w_ih[l]);
     } else {
-      if (l == 0) { CPC_TRY(launch_cast<T>(z, inT, (long long)B * S * Hin, st)); in = inT; }
-      else in = reinterpret_cast<const T*>(sv + lay.cT[l - 1]);
-      CPC_TRY(launch_cast<T>(p->w_ih[l], wih, (long long)3 * Har * Hin, st));
+      if (l == 0) {
+        CPC_TRY(launch_cast3_bf16(z, reinterpret_cast<bf16*>(inT), (long long)B * S * Hin, p->w_ih[l], reinterpret_cast<bf16*>(wih),
+                                  (long long)3 * Har * Hin, nullptr, nullptr, 0, st));
+        in = inT;
+      } else {
+        in = reinterpret_cast<const T*>(sv + lay.cT[l - 1]);
+        CPC_TRY(launch_cast<T>(p->w_ih[l], wih, (long long)3 * Har * Hin, st));
+      }
       w = wih;
     }
     RowView A{in, 0, (long long)Hin, B * S};
@@ -414,7 +448,7 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
   const char* sv = static_cast<const char*>(save);
   Carver ws(wsp, ws_bytes);
   const int Hmax = g.H > Har ? g.H : Har;
-  T* inT = ws.take<T>((size_t)B * S * g.H);
+  const T* inT = isf_dummy<T>() ? nullptr : reinterpret_cast<const T*>(sv + lay.inT);
   T* wihT = ws.take<T>((size_t)G * Hmax);
   T* dgi = ws.take<T>((size_t)B * S * G);
   T* dgh = ws.take<T>((size_t)B * S * G);
@@ -440,7 +474,7 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     bool done = false;
     if constexpr (!isf) {
       if (gru_mma_supported(Har)) {
-        CPC_TRY(gru_rec_bwd_mma(dcl, cl, h0l, sR, sU, sN, sHN, whh, dgi, dgh, dh0, B, S, Har, st));
+        CPC_TRY(gru_rec_bwd_mma(dcl, cl, h0l, sR, sU, sN, sHN, whh, dgi, dgh, dh0, gr->b_ih[l], gr->b_hh[l], B, S, Har, st));
         done = true;
       }
     }
@@ -449,8 +483,10 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
       CPC_TRY(launch_cluster("gru_rec_bwd", gru_rec_bwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, HC * 8, smem, st, args));
     }
 
-    CPC_TRY(launch_colsum<T>(dgi, gr->b_ih[l], (long long)B * S, G, st));
-    CPC_TRY(launch_colsum<T>(dgh, gr->b_hh[l], (long long)B * S, G, st));
+    if (!done) {  // the tensor-core recurrence accumulates the bias gradients itself
+      CPC_TRY(launch_colsum<T>(dgi, gr->b_ih[l], (long long)B * S, G, st));
+      CPC_TRY(launch_colsum<T>(dgh, gr->b_hh[l], (long long)B * S, G, st));
+    }
 
     // operands of the hoisted weight-gradient GEMMs
     const T* in;
@@ -459,7 +495,7 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
       in = reinterpret_cast<const T*>(l == 0 ? z : reinterpret_cast<const float*>(sv + lay.cf[l - 1]));
       hseq = reinterpret_cast<const T*>(cl);
     } else {
-      if (l == 0) { CPC_TRY(launch_cast<T>(z, inT, (long long)B * S * Hin, st)); in = inT; }
+      if (l == 0) in = inT;
       else in = reinterpret_cast<const T*>(sv + lay.cT[l - 1]);
       hseq = reinterpret_cast<const T*>(sv + lay.cT[l]);
     }

@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(256, 1)
 gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c, const float* __restrict__ h0,
                        const bf16* __restrict__ sR, const bf16* __restrict__ sU, const bf16* __restrict__ sN,
                        const bf16* __restrict__ sHN, const float* __restrict__ w_hh, bf16* __restrict__ dgi,
-                       bf16* __restrict__ dgh, float* __restrict__ dh0, int B, int S) {
+                       bf16* __restrict__ dgh, float* __restrict__ dh0, float* __restrict__ db_ih, float* __restrict__ db_hh,
+                       int B, int S) {
   constexpr int G = 3 * HAR, KS = G / 16, KSH = KS / 2;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -281,6 +282,7 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
   }
   float carry[4] = {0.f, 0.f, 0.f, 0.f};
   float direct[4] = {0.f, 0.f, 0.f, 0.f};
+  float sb[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // sums over (t, sequence) of dr, du, dn, dn*r per unit half
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(&dbar[0], kStepBytes);
@@ -355,6 +357,7 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
           dr[e] = dn * hnv * rg * (1.f - rg);
           dnr[e] = dn * rg;
           direct[e] = dh * ug;
+          sb[0][e >> 1] += dr[e]; sb[1][e >> 1] += du[e]; sb[2][e >> 1] += dn; sb[3][e >> 1] += dnr[e];
           const size_t og = ((size_t)bq * S + t) * G + col;
           dgi[og] = __float2bfloat16_rn(dr[e]); dgi[og + HAR] = __float2bfloat16_rn(du[e]); dgi[og + 2 * HAR] = __float2bfloat16_rn(dn);
           dgh[og] = __float2bfloat16_rn(dr[e]); dgh[og + HAR] = __float2bfloat16_rn(du[e]); dgh[og + 2 * HAR] = __float2bfloat16_rn(dnr[e]);
@@ -376,6 +379,25 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     }
   }
   consume(S - 1);
+  if (kh == 0 && db_ih != nullptr) {  // bias gradients: db_ih = sum(dr, du, dn), db_hh = sum(dr, du, dn*r)
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        float v = sb[q][hf];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        sb[q][hf] = v;
+      }
+    if (t4 == 0) {
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        const int col = HC * rank + 16 * ub + g + 8 * hf;
+        atomicAdd(db_ih + col, sb[0][hf]); atomicAdd(db_ih + HAR + col, sb[1][hf]); atomicAdd(db_ih + 2 * HAR + col, sb[2][hf]);
+        atomicAdd(db_hh + col, sb[0][hf]); atomicAdd(db_hh + HAR + col, sb[1][hf]); atomicAdd(db_hh + 2 * HAR + col, sb[3][hf]);
+      }
+    }
+  }
   if (kh == 0 && dh0 != nullptr) {
 #pragma unroll
     for (int e = 0; e < 4; e++) {
@@ -415,8 +437,9 @@ int gru_rec_fwd_mma(const bf16* gi, const float* w_hh, const float* b_hh, const 
   return launch_cluster("gru_rec_fwd_mma", gru_rec_fwd_mma_kernel<64>, 1, ncl, st, args);
 }
 int gru_rec_bwd_mma(const float* dc, const float* c, const float* h0, const bf16* sR, const bf16* sU, const bf16* sN,
-                    const bf16* sHN, const float* w_hh, bf16* dgi, bf16* dgh, float* dh0, int B, int S, int Har, cudaStream_t st) {
-  void* args[] = {&dc, &c, &h0, &sR, &sU, &sN, &sHN, &w_hh, &dgi, &dgh, &dh0, &B, &S};
+                    const bf16* sHN, const float* w_hh, bf16* dgi, bf16* dgh, float* dh0, float* db_ih, float* db_hh, int B, int S,
+                    int Har, cudaStream_t st) {
+  void* args[] = {&dc, &c, &h0, &sR, &sU, &sN, &sHN, &w_hh, &dgi, &dgh, &dh0, &db_ih, &db_hh, &B, &S};
   const int ncl = (B + BT - 1) / BT;
   if (Har == 256) return launch_cluster("gru_rec_bwd_mma", gru_rec_bwd_mma_kernel<256>, 4, ncl, st, args);
   if (Har == 128) return launch_cluster("gru_rec_bwd_mma", gru_rec_bwd_mma_kernel<128>, 2, ncl, st, args);
