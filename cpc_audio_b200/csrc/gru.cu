@@ -423,7 +423,7 @@ int gru_fwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     int Bv = B, Sv = S, Hv = Har;
     bool done = false;
     if constexpr (!isf) {
-      if (gru_mma_supported(Har)) {  // tensor-core recurrence, W_hh slice resident in registers
+      if (gru_mma_supported(Har) && ((size_t)B * S * Har * 2) % 256 == 0) {  // (gate arrays contiguous)  // tensor-core recurrence, W_hh slice resident in registers
         CPC_TRY(gru_rec_fwd_mma(gic, whh, bhh, h0l, cout, cTo, sR, sU, sN, sHN, hTl, B, S, Har, st));
         done = true;
       }
@@ -473,7 +473,7 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     int Bv = B, Sv = S, Hv = Har;
     bool done = false;
     if constexpr (!isf) {
-      if (gru_mma_supported(Har)) {
+      if (gru_mma_supported(Har) && ((size_t)B * S * Har * 2) % 256 == 0) {  // (gate arrays contiguous)
         CPC_TRY(gru_rec_bwd_mma(dcl, cl, h0l, sR, sU, sN, sHN, whh, dgi, dgh, dh0, gr->b_ih[l], gr->b_hh[l], B, S, Har, st));
         done = true;
       }

@@ -72,19 +72,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_mbar_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void pair_sync(int ub) { asm volatile("bar.sync %0, 64;" ::"r"(ub + 1) : "memory"); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
 
 // ---------------------------------------------------------------------------------------------------------
 // forward.  block = 256 threads = 8 warps: warp w owns units 16*(w&3).. of the CTA's 64-unit slice and the k
-// range [ (w>>2)*HAR/2, +HAR/2 ) of the product; warps 0-3 ("gate warps") add the partner's partial sums
-// (through shared memory, 64-thread named barrier per pair), do the gate math and publish.
+// range [ (w>>2)*HAR/2, +HAR/2 ) of the product.  The two warps of a pair swap half of their partial sums
+// through shared memory (64-thread named barrier), so each finishes 8 units x 8 sequences: gate math
+// (tanh.approx), one 8-byte store of the four saved gates per element, one 128-byte bulk copy per peer CTA.
 // cluster = HAR/64 CTAs, grid = cluster * ceil(B/8).
 // ---------------------------------------------------------------------------------------------------------
 template <int HAR>
 __global__ void __launch_bounds__(256, 1)
 gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
-                       const float* __restrict__ h0, float* __restrict__ c, bf16* __restrict__ cT, bf16* __restrict__ sR,
-                       bf16* __restrict__ sU, bf16* __restrict__ sN, bf16* __restrict__ sHN, float* __restrict__ hT, int B,
-                       int S) {
+                       const float* __restrict__ h0, float* __restrict__ c, bf16* __restrict__ cT, uint2* __restrict__ gates4,
+                       float* __restrict__ hT, int B, int S) {
   constexpr int KS = HAR / 16, KSH = KS / 2;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -95,8 +101,8 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
   const int g = lane >> 2, t4 = lane & 3;
 
   __shared__ __align__(128) bf16 hs[2][HAR][BT];  // h_{t-1} as the B operand: [k][sequence]
-  __shared__ float part[4][12][32];                // partial sums of the upper k half, per unit block
-  __shared__ __align__(128) bf16 hstage[2][4][16][BT];  // new units of one warp, staged for the bulk copies
+  __shared__ float part[4][2][6][32];              // partial sums handed to the partner warp, per unit block
+  __shared__ __align__(128) bf16 hstage[2][8][8][BT];  // the 8 new units of one warp, staged for the bulk copies
   __shared__ __align__(8) uint64_t hbar[2];        // hbar[b] completes when buffer b holds a full new state
   constexpr uint32_t kStepBytes = HAR * BT * 2;
   if (threadIdx.x == 0) {
@@ -120,17 +126,16 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
       wf[gt][ks][3] = pack_bf16(__ldg(r1 + k + 8), __ldg(r1 + k + 9));
     }
   }
-  // element e of a gate thread: unit jj = g + 8*(e>>1), sequence bb = 2*t4 + (e&1)
-  float bh[3][2];
+  // this thread finishes unit `col` (row g + 8*kh of the 16-block) for sequences b0 + 2*t4 + {0, 1}
+  const int col = HC * rank + 16 * ub + 8 * kh + g;
+  float bh[3];
 #pragma unroll
-  for (int gt = 0; gt < 3; gt++)
+  for (int gt = 0; gt < 3; gt++) bh[gt] = __ldg(b_hh + gt * HAR + col);
+  float hprev[2];
 #pragma unroll
-    for (int hf = 0; hf < 2; hf++) bh[gt][hf] = __ldg(b_hh + gt * HAR + HC * rank + 16 * ub + g + 8 * hf);
-  float hprev[4];
-#pragma unroll
-  for (int e = 0; e < 4; e++) {
-    const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
-    hprev[e] = (h0 != nullptr && bq < B) ? h0[(size_t)bq * HAR + col] : 0.f;
+  for (int q = 0; q < 2; q++) {
+    const int bq = b0 + 2 * t4 + q;
+    hprev[q] = (h0 != nullptr && bq < B) ? h0[(size_t)bq * HAR + col] : 0.f;
   }
   for (int i = threadIdx.x; i < HAR * BT; i += blockDim.x) {
     const int k = i / BT, bq = b0 + (i - k * BT);
@@ -144,26 +149,26 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
   cluster.sync();
   const uint32_t hs_local = s_u32(&hs[0][0][0]), bar_local = s_u32(&hbar[0]);
 
-  bf16 gq_raw[3][4];
+  bf16 gq_raw[3][2];
   auto load_gi = [&](int tt) {
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
-      if (kh == 0 && bq < B && tt < S) {
+    for (int q = 0; q < 2; q++) {
+      const int bq = b0 + 2 * t4 + q;
+      if (bq < B && tt < S) {
         const bf16* gp = gi + ((size_t)bq * S + tt) * 3 * HAR + col;
-        gq_raw[0][e] = gp[0]; gq_raw[1][e] = gp[HAR]; gq_raw[2][e] = gp[2 * HAR];
-      } else { gq_raw[0][e] = gq_raw[1][e] = gq_raw[2][e] = __float2bfloat16_rn(0.f); }
+        gq_raw[0][q] = gp[0]; gq_raw[1][q] = gp[HAR]; gq_raw[2][q] = gp[2 * HAR];
+      } else { gq_raw[0][q] = gq_raw[1][q] = gq_raw[2][q] = __float2bfloat16_rn(0.f); }
     }
   };
   load_gi(0);
 
   for (int t = 0; t < S; t++) {
     const int cur = t & 1, nxt = cur ^ 1;
-    float gq[3][4];
+    float gq[3][2];
 #pragma unroll
     for (int gt = 0; gt < 3; gt++)
 #pragma unroll
-      for (int e = 0; e < 4; e++) gq[gt][e] = __bfloat162float(gq_raw[gt][e]);
+      for (int q = 0; q < 2; q++) gq[gt][q] = __bfloat162float(gq_raw[gt][q]);
     load_gi(t + 1);  // in flight during this step's product and exchange
     if (t > 0) {
       mbar_wait(&hbar[cur], ((t - 1 - (cur ^ 1)) >> 1) & 1);
@@ -186,51 +191,48 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
         mma16816(acc[gt][1], wf[gt][2 * q + 1], bq4[2], bq4[3]);
       }
     }
-    float a[3][4];
+    // accumulator e: row g (e = 0,1) / g+8 (e = 2,3), sequence 2*t4 + (e&1).  Keep rows g + 8*kh, hand the other
+    // two of every gate to the partner warp.
+    float mine[3][2];
 #pragma unroll
     for (int gt = 0; gt < 3; gt++)
 #pragma unroll
-      for (int e = 0; e < 4; e++) a[gt][e] = acc[gt][0][e] + acc[gt][1][e];
-    if (kh == 1) {
-#pragma unroll
-      for (int gt = 0; gt < 3; gt++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) part[ub][gt * 4 + e][lane] = a[gt][e];
-    }
-    pair_sync(ub);
-    if (kh == 0) {
-      float hn[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int hf = e >> 1;
-        const float ar = a[0][e] + part[ub][e][lane], au = a[1][e] + part[ub][4 + e][lane], an = a[2][e] + part[ub][8 + e][lane];
-        const float ghn = an + bh[2][hf];
-        const float rg = sigmoidf_(gq[0][e] + ar + bh[0][hf]);
-        const float ug = sigmoidf_(gq[1][e] + au + bh[1][hf]);
-        const float ng = tanhf(gq[2][e] + rg * ghn);
-        hn[e] = (1.f - ug) * ng + ug * hprev[e];
-        hprev[e] = hn[e];
-        const int col = HC * rank + 16 * ub + g + 8 * hf, bq = b0 + 2 * t4 + (e & 1);
-        if (bq < B) {
-          const size_t o = ((size_t)bq * S + t) * HAR + col;
-          c[o] = hn[e];
-          cT[o] = __float2bfloat16_rn(hn[e]);
-          sR[o] = __float2bfloat16_rn(rg); sU[o] = __float2bfloat16_rn(ug); sN[o] = __float2bfloat16_rn(ng);
-          sHN[o] = __float2bfloat16_rn(ghn);
-          if (hT != nullptr && t == S - 1) hT[(size_t)bq * HAR + col] = hn[e];
-        }
+      for (int q = 0; q < 2; q++) {
+        const float lo = acc[gt][0][q] + acc[gt][1][q], hi = acc[gt][0][2 + q] + acc[gt][1][2 + q];
+        const float keep = kh ? hi : lo, give = kh ? lo : hi;
+        mine[gt][q] = keep;
+        part[ub][kh][gt * 2 + q][lane] = give;
       }
-      // publish the 64 new units to every CTA of the cluster: rows (unit), 2 sequences per 32-bit st.async
-      // ONE 256-byte bulk copy per destination CTA (the mbarrier handles 16 transactions per step, not 1024)
-      if (t + 1 < S) {
-        *reinterpret_cast<uint32_t*>(&hstage[cur][ub][g][2 * t4]) = pack_bf16(hn[0], hn[1]);
-        *reinterpret_cast<uint32_t*>(&hstage[cur][ub][g + 8][2 * t4]) = pack_bf16(hn[2], hn[3]);
-        fence_async_smem();
-        __syncwarp();
-        if (lane < CS) {
-          const uint32_t dst = mapa_u32(hs_local + (uint32_t)(((size_t)nxt * HAR + HC * rank + 16 * ub) * BT) * 2, lane);
-          bulk_s2s(dst, s_u32(&hstage[cur][ub][0][0]), 16 * BT * 2, mapa_u32(bar_local + nxt * 8, lane));
-        }
+    pair_sync(ub);
+    float hn[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const float ar = mine[0][q] + part[ub][1 - kh][q][lane];
+      const float au = mine[1][q] + part[ub][1 - kh][2 + q][lane];
+      const float an = mine[2][q] + part[ub][1 - kh][4 + q][lane];
+      const float ghn = an + bh[2];
+      const float rg = sigmoid_fast(gq[0][q] + ar + bh[0]);
+      const float ug = sigmoid_fast(gq[1][q] + au + bh[1]);
+      const float ng = tanh_fast(gq[2][q] + rg * ghn);
+      hn[q] = fmaf(ug, hprev[q] - ng, ng);  // (1-u) n + u h
+      hprev[q] = hn[q];
+      const int bq = b0 + 2 * t4 + q;
+      if (bq < B) {
+        const size_t o = ((size_t)bq * S + t) * HAR + col;
+        c[o] = hn[q];
+        cT[o] = __float2bfloat16_rn(hn[q]);
+        gates4[o] = make_uint2(pack_bf16(rg, ug), pack_bf16(ng, ghn));
+        if (hT != nullptr && t == S - 1) hT[(size_t)bq * HAR + col] = hn[q];
+      }
+    }
+    // publish this warp's 8 units: ONE 128-byte bulk copy per destination CTA
+    if (t + 1 < S) {
+      *reinterpret_cast<uint32_t*>(&hstage[cur][warp][g][2 * t4]) = pack_bf16(hn[0], hn[1]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane < CS) {
+        const uint32_t dst = mapa_u32(hs_local + (uint32_t)(((size_t)nxt * HAR + HC * rank + 16 * ub + 8 * kh) * BT) * 2, lane);
+        bulk_s2s(dst, s_u32(&hstage[cur][warp][0][0]), 8 * BT * 2, mapa_u32(bar_local + nxt * 8, lane));
       }
     }
   }
@@ -239,13 +241,12 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
 
 // ---------------------------------------------------------------------------------------------------------
 // BPTT.  Same launch shape.  Resident: A[i][gate index] = W_hh[gate index][64*rank + 16*(w&3) + i], gate-index
-// range of warp w: [ (w>>2)*3HAR/2, +3HAR/2 ).
+// range of warp w: [ (w>>2)*3HAR/2, +3HAR/2 ).  Each warp finishes 8 units x 8 sequences per step.
 // ---------------------------------------------------------------------------------------------------------
 template <int HAR>
 __global__ void __launch_bounds__(256, 1)
 gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c, const float* __restrict__ h0,
-                       const bf16* __restrict__ sR, const bf16* __restrict__ sU, const bf16* __restrict__ sN,
-                       const bf16* __restrict__ sHN, const float* __restrict__ w_hh, bf16* __restrict__ dgi,
+                       const uint2* __restrict__ gates4, const float* __restrict__ w_hh, bf16* __restrict__ dgi,
                        bf16* __restrict__ dgh, float* __restrict__ dh0, float* __restrict__ db_ih, float* __restrict__ db_hh,
                        int B, int S) {
   constexpr int G = 3 * HAR, KS = G / 16, KSH = KS / 2;
@@ -258,8 +259,8 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
   const int g = lane >> 2, t4 = lane & 3;
 
   __shared__ __align__(128) bf16 ds[2][G][BT];  // dgh_t as the B operand: [gate index][sequence]
-  __shared__ float part[4][4][32];
-  __shared__ __align__(128) bf16 dstage[2][4][3][16][BT];
+  __shared__ float part[4][2][2][32];
+  __shared__ __align__(128) bf16 dstage[2][8][3][8][BT];
   __shared__ __align__(8) uint64_t dbar[2];
   constexpr uint32_t kStepBytes = G * BT * 2;
   if (threadIdx.x == 0) {
@@ -280,9 +281,10 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
       wf[ks][3] = pack_bf16(__ldg(w_hh + (size_t)(k + 8) * HAR + c0 + 8), __ldg(w_hh + (size_t)(k + 9) * HAR + c0 + 8));
     }
   }
-  float carry[4] = {0.f, 0.f, 0.f, 0.f};
-  float direct[4] = {0.f, 0.f, 0.f, 0.f};
-  float sb[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // sums over (t, sequence) of dr, du, dn, dn*r per unit half
+  const int col = HC * rank + 16 * ub + 8 * kh + g;  // the unit this thread finishes, sequences b0 + 2*t4 + {0,1}
+  float carry[2] = {0.f, 0.f};
+  float direct[2] = {0.f, 0.f};
+  float sb[4] = {0.f, 0.f, 0.f, 0.f};  // sums over (t, sequence) of dr, du, dn, dn*r for this unit
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(&dbar[0], kStepBytes);
@@ -308,101 +310,87 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
       mma16816(acc[q % 3], wf[2 * q], bq4[0], bq4[1]);
       mma16816(acc[(q + 1) % 3], wf[2 * q + 1], bq4[2], bq4[3]);
     }
-    float a[4];
+    float keep[2];
 #pragma unroll
-    for (int e = 0; e < 4; e++) a[e] = (acc[0][e] + acc[1][e]) + acc[2][e];
-    if (kh == 1) {
-#pragma unroll
-      for (int e = 0; e < 4; e++) part[ub][e][lane] = a[e];
+    for (int q = 0; q < 2; q++) {
+      const float lo = (acc[0][q] + acc[1][q]) + acc[2][q], hi = (acc[0][2 + q] + acc[1][2 + q]) + acc[2][2 + q];
+      keep[q] = kh ? hi : lo;
+      part[ub][kh][q][lane] = kh ? lo : hi;
     }
     pair_sync(ub);
-    if (kh == 0) {
 #pragma unroll
-      for (int e = 0; e < 4; e++) carry[e] = direct[e] + a[e] + part[ub][e][lane];
-    }
+    for (int q = 0; q < 2; q++) carry[q] = direct[q] + keep[q] + part[ub][1 - kh][q][lane];
   };
 
   for (int it = 0; it < S; it++) {
     const int t = S - 1 - it, buf = t & 1;
-    // (A) this step's operands: independent of the running gradient, in flight during the previous product
-    float dcv[4], hp[4];
-    uint32_t gRU[4], gNH[4];
+    // (A) this step's operands: raw loads only, consumed after the previous step's product
+    float dcv[2], hp[2];
+    uint2 g4[2];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
-      dcv[e] = 0.f; hp[e] = 0.f; gRU[e] = 0u; gNH[e] = 0u;
-      if (kh == 0 && bq < B) {
+    for (int q = 0; q < 2; q++) {
+      const int bq = b0 + 2 * t4 + q;
+      dcv[q] = 0.f; hp[q] = 0.f; g4[q] = make_uint2(0u, 0u);
+      if (bq < B) {
         const size_t o = ((size_t)bq * S + t) * HAR + col;
-        dcv[e] = dc[o];
-        gRU[e] = (uint32_t)__bfloat16_as_ushort(sR[o]) | ((uint32_t)__bfloat16_as_ushort(sU[o]) << 16);
-        gNH[e] = (uint32_t)__bfloat16_as_ushort(sN[o]) | ((uint32_t)__bfloat16_as_ushort(sHN[o]) << 16);
-        hp[e] = t > 0 ? c[o - HAR] : (h0 != nullptr ? h0[(size_t)bq * HAR + col] : 0.f);
+        dcv[q] = dc[o];
+        g4[q] = gates4[o];
+        hp[q] = t > 0 ? c[o - HAR] : (h0 != nullptr ? h0[(size_t)bq * HAR + col] : 0.f);
       }
     }
     // (B) finish the previous step
     if (it > 0) consume(it - 1);
     // (C) gate gradients of step t, publish dgh_t
-    if (kh == 0) {
-      float dr[4], du[4], dnr[4];
+    float dr[2], du[2], dnr[2];
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
-        dr[e] = du[e] = dnr[e] = direct[e] = 0.f;
-        if (bq < B) {
-          const float dh = carry[e] + dcv[e];
-          const float rg = __uint_as_float(gRU[e] << 16), ug = __uint_as_float(gRU[e] & 0xffff0000u);
-          const float ng = __uint_as_float(gNH[e] << 16), hnv = __uint_as_float(gNH[e] & 0xffff0000u);
-          const float dn = dh * (1.f - ug) * (1.f - ng * ng);
-          du[e] = dh * (hp[e] - ng) * ug * (1.f - ug);
-          dr[e] = dn * hnv * rg * (1.f - rg);
-          dnr[e] = dn * rg;
-          direct[e] = dh * ug;
-          sb[0][e >> 1] += dr[e]; sb[1][e >> 1] += du[e]; sb[2][e >> 1] += dn; sb[3][e >> 1] += dnr[e];
-          const size_t og = ((size_t)bq * S + t) * G + col;
-          dgi[og] = __float2bfloat16_rn(dr[e]); dgi[og + HAR] = __float2bfloat16_rn(du[e]); dgi[og + 2 * HAR] = __float2bfloat16_rn(dn);
-          dgh[og] = __float2bfloat16_rn(dr[e]); dgh[og + HAR] = __float2bfloat16_rn(du[e]); dgh[og + 2 * HAR] = __float2bfloat16_rn(dnr[e]);
-        }
+    for (int q = 0; q < 2; q++) {
+      const int bq = b0 + 2 * t4 + q;
+      dr[q] = du[q] = dnr[q] = direct[q] = 0.f;
+      if (bq < B) {
+        const float dh = carry[q] + dcv[q];
+        const float rg = __uint_as_float(g4[q].x << 16), ug = __uint_as_float(g4[q].x & 0xffff0000u);
+        const float ng = __uint_as_float(g4[q].y << 16), hnv = __uint_as_float(g4[q].y & 0xffff0000u);
+        const float dn = dh * (1.f - ug) * (1.f - ng * ng);
+        du[q] = dh * (hp[q] - ng) * ug * (1.f - ug);
+        dr[q] = dn * hnv * rg * (1.f - rg);
+        dnr[q] = dn * rg;
+        direct[q] = dh * ug;
+        sb[0] += dr[q]; sb[1] += du[q]; sb[2] += dn; sb[3] += dnr[q];
+        const size_t og = ((size_t)bq * S + t) * G + col;
+        dgi[og] = __float2bfloat16_rn(dr[q]); dgi[og + HAR] = __float2bfloat16_rn(du[q]); dgi[og + 2 * HAR] = __float2bfloat16_rn(dn);
+        dgh[og] = __float2bfloat16_rn(dr[q]); dgh[og + HAR] = __float2bfloat16_rn(du[q]); dgh[og + 2 * HAR] = __float2bfloat16_rn(dnr[q]);
       }
-#pragma unroll
-      for (int hf = 0; hf < 2; hf++) {
-        *reinterpret_cast<uint32_t*>(&dstage[buf][ub][0][g + 8 * hf][2 * t4]) = pack_bf16(dr[2 * hf], dr[2 * hf + 1]);
-        *reinterpret_cast<uint32_t*>(&dstage[buf][ub][1][g + 8 * hf][2 * t4]) = pack_bf16(du[2 * hf], du[2 * hf + 1]);
-        *reinterpret_cast<uint32_t*>(&dstage[buf][ub][2][g + 8 * hf][2 * t4]) = pack_bf16(dnr[2 * hf], dnr[2 * hf + 1]);
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane < 3 * CS) {  // lane -> (destination CTA, gate block): one 256-byte bulk copy each
-        const int pr = lane / 3, gt = lane - 3 * pr;
-        const uint32_t dst = mapa_u32(ds_local + (uint32_t)(((size_t)buf * G + gt * HAR + HC * rank + 16 * ub) * BT) * 2, pr);
-        bulk_s2s(dst, s_u32(&dstage[buf][ub][gt][0][0]), 16 * BT * 2, mapa_u32(bar_local + buf * 8, pr));
-      }
+    }
+    *reinterpret_cast<uint32_t*>(&dstage[buf][warp][0][g][2 * t4]) = pack_bf16(dr[0], dr[1]);
+    *reinterpret_cast<uint32_t*>(&dstage[buf][warp][1][g][2 * t4]) = pack_bf16(du[0], du[1]);
+    *reinterpret_cast<uint32_t*>(&dstage[buf][warp][2][g][2 * t4]) = pack_bf16(dnr[0], dnr[1]);
+    fence_async_smem();
+    __syncwarp();
+    if (lane < 3 * CS) {  // lane -> (destination CTA, gate block): one 128-byte bulk copy each
+      const int pr = lane / 3, gt = lane - 3 * pr;
+      const uint32_t dst = mapa_u32(ds_local + (uint32_t)(((size_t)buf * G + gt * HAR + HC * rank + 16 * ub + 8 * kh) * BT) * 2, pr);
+      bulk_s2s(dst, s_u32(&dstage[buf][warp][gt][0][0]), 8 * BT * 2, mapa_u32(bar_local + buf * 8, pr));
     }
   }
   consume(S - 1);
-  if (kh == 0 && db_ih != nullptr) {  // bias gradients: db_ih = sum(dr, du, dn), db_hh = sum(dr, du, dn*r)
+  if (db_ih != nullptr) {  // bias gradients: db_ih = sum(dr, du, dn), db_hh = sum(dr, du, dn*r)
 #pragma unroll
-    for (int q = 0; q < 4; q++)
-#pragma unroll
-      for (int hf = 0; hf < 2; hf++) {
-        float v = sb[q][hf];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        sb[q][hf] = v;
-      }
+    for (int q = 0; q < 4; q++) {
+      float v = sb[q];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      sb[q] = v;
+    }
     if (t4 == 0) {
-#pragma unroll
-      for (int hf = 0; hf < 2; hf++) {
-        const int col = HC * rank + 16 * ub + g + 8 * hf;
-        atomicAdd(db_ih + col, sb[0][hf]); atomicAdd(db_ih + HAR + col, sb[1][hf]); atomicAdd(db_ih + 2 * HAR + col, sb[2][hf]);
-        atomicAdd(db_hh + col, sb[0][hf]); atomicAdd(db_hh + HAR + col, sb[1][hf]); atomicAdd(db_hh + 2 * HAR + col, sb[3][hf]);
-      }
+      atomicAdd(db_ih + col, sb[0]); atomicAdd(db_ih + HAR + col, sb[1]); atomicAdd(db_ih + 2 * HAR + col, sb[2]);
+      atomicAdd(db_hh + col, sb[0]); atomicAdd(db_hh + HAR + col, sb[1]); atomicAdd(db_hh + 2 * HAR + col, sb[3]);
     }
   }
-  if (kh == 0 && dh0 != nullptr) {
+  if (dh0 != nullptr) {
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int col = HC * rank + 16 * ub + g + 8 * (e >> 1), bq = b0 + 2 * t4 + (e & 1);
-      if (bq < B) dh0[(size_t)bq * HAR + col] = carry[e];
+    for (int q = 0; q < 2; q++) {
+      const int bq = b0 + 2 * t4 + q;
+      if (bq < B) dh0[(size_t)bq * HAR + col] = carry[q];
     }
   }
   cluster.sync();
@@ -430,7 +418,14 @@ bool gru_mma_supported(int Har) { return Har == 64 || Har == 128 || Har == 256; 
 
 int gru_rec_fwd_mma(const bf16* gi, const float* w_hh, const float* b_hh, const float* h0, float* c, bf16* cT, bf16* sR, bf16* sU,
                     bf16* sN, bf16* sHN, float* hT, int B, int S, int Har, cudaStream_t st) {
-  void* args[] = {&gi, &w_hh, &b_hh, &h0, &c, &cT, &sR, &sU, &sN, &sHN, &hT, &B, &S};
+  // the four gate arrays are contiguous in the save buffer: the tensor-core kernels use them as ONE array of
+  // {r, u, n, W_hn h + b_hn} bf16 quadruples (8-byte loads / stores)
+  if (reinterpret_cast<char*>(sU) - reinterpret_cast<char*>(sR) != (ptrdiff_t)((size_t)B * S * Har * 2) ||
+      reinterpret_cast<char*>(sHN) - reinterpret_cast<char*>(sR) != (ptrdiff_t)((size_t)3 * B * S * Har * 2))
+    return fail(CPCB200_ERR_BAD_DIMS, "gru mma: gate arrays are not contiguous");
+  uint2* gates4 = reinterpret_cast<uint2*>(sR);
+  (void)sN;
+  void* args[] = {&gi, &w_hh, &b_hh, &h0, &c, &cT, &gates4, &hT, &B, &S};
   const int ncl = (B + BT - 1) / BT;
   if (Har == 256) return launch_cluster("gru_rec_fwd_mma", gru_rec_fwd_mma_kernel<256>, 4, ncl, st, args);
   if (Har == 128) return launch_cluster("gru_rec_fwd_mma", gru_rec_fwd_mma_kernel<128>, 2, ncl, st, args);
@@ -439,7 +434,9 @@ int gru_rec_fwd_mma(const bf16* gi, const float* w_hh, const float* b_hh, const 
 int gru_rec_bwd_mma(const float* dc, const float* c, const float* h0, const bf16* sR, const bf16* sU, const bf16* sN,
                     const bf16* sHN, const float* w_hh, bf16* dgi, bf16* dgh, float* dh0, float* db_ih, float* db_hh, int B, int S,
                     int Har, cudaStream_t st) {
-  void* args[] = {&dc, &c, &h0, &sR, &sU, &sN, &sHN, &w_hh, &dgi, &dgh, &dh0, &db_ih, &db_hh, &B, &S};
+  const uint2* gates4 = reinterpret_cast<const uint2*>(sR);
+  (void)sU; (void)sN; (void)sHN;
+  void* args[] = {&dc, &c, &h0, &gates4, &w_hh, &dgi, &dgh, &dh0, &db_ih, &db_hh, &B, &S};
   const int ncl = (B + BT - 1) / BT;
   if (Har == 256) return launch_cluster("gru_rec_bwd_mma", gru_rec_bwd_mma_kernel<256>, 4, ncl, st, args);
   if (Har == 128) return launch_cluster("gru_rec_bwd_mma", gru_rec_bwd_mma_kernel<128>, 2, ncl, st, args);
