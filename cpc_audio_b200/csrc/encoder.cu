@@ -426,42 +426,40 @@ __global__ void __launch_bounds__(256) cnorm_relu_bwd_kernel(const TD* __restric
 // ---------------------------------------------------------------------------------------------------------
 // small prep kernels
 // ---------------------------------------------------------------------------------------------------------
-// forward GEMM weights: Wp[co][tap*Ci + ci] = W[co][ci][tap]
+// ---- all four H->H layers in one launch each (blockIdx.y = layer - 1) ----------------------------------
+struct Conv4Ptrs { const float* w[4]; void* out[4]; float* acc[4]; int taps[4]; int s[4]; };
+
+// forward GEMM weights: block (co, layer), thread ci reads its `taps` contiguous floats (coalesced 32-B pieces) and
+// writes Wp[co][tap*Ci + ci] coalesced over ci
 template <class T>
-__global__ void prep_w_fwd_kernel(const float* __restrict__ w, T* __restrict__ wp, int Co, int Ci, int taps) {
-  long long n = (long long)Co * Ci * taps;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int ci = (int)(i % Ci); long long r = i / Ci; int tap = (int)(r % taps); int co = (int)(r / taps);
-    wp[i] = from_f<T>(w[((long long)co * Ci + ci) * taps + tap]);
+__global__ void prep_w_fwd_all_kernel(Conv4Ptrs P, int Ci) {
+  const int l = blockIdx.y, co = blockIdx.x, taps = P.taps[l];
+  const float* w = P.w[l] + (size_t)co * Ci * taps;
+  T* wp = static_cast<T*>(P.out[l]) + (size_t)co * Ci * taps;
+  for (int ci = threadIdx.x; ci < Ci; ci += blockDim.x) {
+    for (int tap = 0; tap < taps; tap++) wp[(size_t)tap * Ci + ci] = from_f<T>(w[(size_t)ci * taps + tap]);
   }
 }
-// dgrad GEMM weights: Wd[r][ci][half*Co + co] = W[co][ci][r + s*(1-half)],  r in [0,s)
+// dgrad GEMM weights: block (ci, layer), thread co: Wd[r][ci][half*Co + co] = W[co][ci][r + s*(1-half)]
 template <class T>
-__global__ void prep_w_dgrad_kernel(const float* __restrict__ w, T* __restrict__ wd, int Co, int Ci, int s) {
-  const int taps = 2 * s;
-  long long n = (long long)s * Ci * 2 * Co;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int co = (int)(i % Co); long long r1 = i / Co; int half = (int)(r1 % 2); r1 /= 2; int ci = (int)(r1 % Ci); int r = (int)(r1 / Ci);
-    wd[i] = from_f<T>(w[((long long)co * Ci + ci) * taps + r + s * (1 - half)]);
+__global__ void prep_w_dgrad_all_kernel(Conv4Ptrs P, int Co, int Ci) {
+  const int l = blockIdx.y, ci = blockIdx.x, taps = P.taps[l], s = P.s[l];
+  T* wd = static_cast<T*>(P.out[l]);
+  for (int co = threadIdx.x; co < Co; co += blockDim.x) {
+    const float* w = P.w[l] + ((size_t)co * Ci + ci) * taps;
+    for (int tap = 0; tap < taps; tap++) {
+      const int r = tap % s, half = 1 - tap / s;
+      wd[((size_t)r * Ci + ci) * 2 * Co + (size_t)half * Co + co] = from_f<T>(w[tap]);
+    }
   }
 }
-// dW[co][ci][tap] += scratch[co][tap*Ci + ci]   (scratch is the GEMM-friendly layout of the weight gradient)
-__global__ void permute_add_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Co, int Ci, int taps) {
-  const long long n = (long long)Co * Ci * taps;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % taps); long long r = i / taps; const int ci = (int)(r % Ci); const int co = (int)(r / Ci);
-    dw[i] += scratch[((long long)co * taps + tap) * Ci + ci];
-  }
-}
-// zero the kPad rows before and after every window
-template <class T>
-__global__ void zero_pads_kernel(T* __restrict__ buf, int B, int Lc, int H) {
-  const long long Lp = Lc + 2 * kPad;
-  const long long n = (long long)B * 2 * kPad * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % H); long long r = i / H; int pr = (int)(r % (2 * kPad)); int b = (int)(r / (2 * kPad));
-    long long row = pr < kPad ? pr : (Lc + pr);  // pr in [kPad, 2kPad) -> Lc + kPad + (pr - kPad)
-    buf[((long long)b * Lp + row) * H + c] = from_f<T>(0.f);
+// dW[co][ci][tap] += scratch[co][tap*Ci + ci]: block (co, layer), thread ci
+__global__ void permute_add_wgrad_all_kernel(Conv4Ptrs P, int Ci) {
+  const int l = blockIdx.y, co = blockIdx.x, taps = P.taps[l];
+  const float* sc = P.w[l] + (size_t)co * Ci * taps;
+  float* dw = P.acc[l] + (size_t)co * Ci * taps;
+  for (int ci = threadIdx.x; ci < Ci; ci += blockDim.x) {
+    for (int tap = 0; tap < taps; tap++) dw[(size_t)ci * taps + tap] += sc[(size_t)tap * Ci + ci];
   }
 }
 
@@ -492,9 +490,11 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   for (int i = 1; i < 5; i++) wp[i] = ws.take<T>((size_t)H * kConvK[i] * H);
   if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "encoder_fwd: workspace %zu < %zu", ws_bytes, ws.off);
 
-  for (int i = 1; i < 5; i++) {
-    prep_w_fwd_kernel<T><<<148, 256, 0, st>>>(p->conv_w[i], wp[i], H, H, kConvK[i]);
-    CPC_LAUNCHED_N("prep_w_fwd", st);
+  {
+    Conv4Ptrs P{};
+    for (int i = 1; i < 5; i++) { P.w[i - 1] = p->conv_w[i]; P.out[i - 1] = wp[i]; P.taps[i - 1] = kConvK[i]; P.s[i - 1] = kConvS[i]; }
+    prep_w_fwd_all_kernel<T><<<dim3(H, 4), 256, 0, st>>>(P, H);
+    CPC_LAUNCHED_N("prep_w_fwd_all", st);
   }
   // the zero rows around every window of y0..y3 are written by the kernels that produce the interior
   const int I = ilog_I(H);
@@ -553,9 +553,11 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   CPC_CHECK_CUDA(cudaMemsetAsync(dwp[1], 0, dwp_total, st));
   const int I = ilog_I(H);
 
-  for (int i = 1; i < 5; i++) {
-    prep_w_dgrad_kernel<T><<<148, 256, 0, st>>>(p->conv_w[i], wd[i], H, H, kConvS[i]);
-    CPC_LAUNCHED_N("prep_w_dgrad", st);
+  {
+    Conv4Ptrs P{};
+    for (int i = 1; i < 5; i++) { P.w[i - 1] = p->conv_w[i]; P.out[i - 1] = wd[i]; P.taps[i - 1] = kConvK[i]; P.s[i - 1] = kConvS[i]; }
+    prep_w_dgrad_all_kernel<T><<<dim3(H, 4), 256, 0, st>>>(P, H, H);
+    CPC_LAUNCHED_N("prep_w_dgrad_all", st);
   }
   for (int i = 4; i >= 1; i--) {
     const int Lo = g.Lout[i], Lin = g.Lout[i - 1], s = kConvS[i], pp = kConvP[i];
@@ -578,8 +580,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       RowView A{du[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo};
       RowView Bv{sv + e.y[i - 1] + (size_t)(kPad - pp) * H, (long long)(Lin + 2 * kPad) * H, (long long)s * H, Lo, kConvK[i], s};
       CPC_TRY(gemm_tn(g.bf16, B, H, kConvK[i] * H, A, Bv, dwp[i], kConvK[i] * H, STORE_PLAIN, 0, 0, st));
-      permute_add_wgrad_kernel<<<148 * 2, 256, 0, st>>>(dwp[i], gr->conv_w[i], H, H, kConvK[i]);
-      CPC_LAUNCHED_N("permute_add_wgrad", st);
+
     }
     // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r].  All s residues in ONE GEMM with
     // N = s*H: row q of the product is the s consecutive input rows s q - p .. s q - p + s - 1.
@@ -588,6 +589,12 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       OutView C{dy[i - 1] - (long long)pp * H, (long long)Lin * H, (long long)s * H, Lo + 1, 0, Lo + 1, H, pp};
       CPC_TRY(gemm_nt(g.bf16, false, B, s * H, 2 * H, A, wd[i], nullptr, C, st));
     }
+  }
+  {  // scratch (Co, k*Ci) layout -> parameter layout (Co, Ci, k), all four layers
+    Conv4Ptrs P{};
+    for (int i = 1; i < 5; i++) { P.w[i - 1] = dwp[i]; P.acc[i - 1] = gr->conv_w[i]; P.taps[i - 1] = kConvK[i]; P.s[i - 1] = kConvS[i]; }
+    permute_add_wgrad_all_kernel<<<dim3(H, 4), 256, 0, st>>>(P, H);
+    CPC_LAUNCHED_N("permute_add_wgrad_all", st);
   }
   bool c0_done = false;
   if constexpr (sizeof(T) == 2) {
