@@ -48,6 +48,23 @@ __device__ __forceinline__ void load_wfrags(const float* __restrict__ w, const f
   }
 }
 
+// the same fragments parked in shared memory ([n-tile][lane] -> one 8-byte load per n-tile, conflict-free): keeps
+// 2*H/8 registers free so that three CTAs fit an SM
+template <int H>
+__device__ __forceinline__ void stage_wfrags(const float* __restrict__ w, const float* __restrict__ bias, uint2* wsm) {
+  for (int i = threadIdx.x; i < (H / 8) * 32; i += blockDim.x) {
+    const int j = i >> 5, lane = i & 31, g = lane >> 2, t = lane & 3;
+    const int c = 8 * j + g;
+    uint2 v;
+    v.x = pack_bf16(__ldg(w + c * 10 + 2 * t), __ldg(w + c * 10 + 2 * t + 1));
+    float lo = 0.f, hi = 0.f;
+    if (t == 0) { lo = __ldg(w + c * 10 + 8); hi = __ldg(w + c * 10 + 9); }
+    else if (t == 1) { lo = __ldg(bias + c); }
+    v.y = pack_bf16(lo, hi);
+    wsm[i] = v;
+  }
+}
+
 // A fragments (hi and lo parts) of the 16 frames starting at f0 of window xb
 __device__ __forceinline__ void load_xfrags(const float* __restrict__ xb, int L, int f0, int g, int t, uint32_t (&ah)[4],
                                             uint32_t (&al)[4]) {
@@ -130,21 +147,21 @@ __device__ __forceinline__ void tile_from_global(unsigned char* st, const bf16* 
 // forward: x (B, L) fp32 -> y0 (B, kPad + L0 + kPad, H) bf16 (pads zeroed here)
 // ---------------------------------------------------------------------------------------------------------
 template <int H>
-__global__ void __launch_bounds__(128) conv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(128, 3) conv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, const float* __restrict__ gam,
                                                              const float* __restrict__ bet, bf16* __restrict__ y, int B, int L,
                                                              int L0) {
   constexpr int NT = H / 8, RS = 2 * H + 16;
   extern __shared__ __align__(16) unsigned char sm[];
   float* gb = reinterpret_cast<float*>(sm);                       // gamma[H], beta[H]
-  unsigned char* stage = sm + 2 * H * 4 + (threadIdx.x >> 5) * (16 * RS);
+  uint2* wsm = reinterpret_cast<uint2*>(sm + 2 * H * 4);          // weight fragments [NT][32]
+  unsigned char* stage = sm + 2 * H * 4 + NT * 32 * 8 + (threadIdx.x >> 5) * (16 * RS);
   for (int i = threadIdx.x; i < H; i += blockDim.x) { gb[i] = gam[i]; gb[H + i] = bet[i]; }
+  stage_wfrags<H>(w, bias, wsm);
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  uint32_t wb[NT][2];
-  load_wfrags<H>(w, bias, g, t, wb);
   const int tpw = L0 / 16;  // tiles per window
   const long long Lp0 = L0 + 2 * kPad;
   for (int tile = warp; tile < B * tpw; tile += nwarps) {
@@ -154,9 +171,10 @@ __global__ void __launch_bounds__(128) conv0_fwd_mma_kernel(const float* __restr
     float acc[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; j++) {
+      const uint2 wv = wsm[j * 32 + lane];
       acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      mma16816(acc[j], ah, wb[j][0], wb[j][1]);
-      mma16816(acc[j], al, wb[j][0], wb[j][1]);
+      mma16816(acc[j], ah, wv.x, wv.y);
+      mma16816(acc[j], al, wv.x, wv.y);
     }
     float mean[2], rstd[2];
     tile_stats<NT>(acc, H, mean, rstd);
@@ -192,7 +210,7 @@ __global__ void __launch_bounds__(128) conv0_fwd_mma_kernel(const float* __restr
 // matrix (A = tile^T via ldmatrix.trans) and accumulated in shared memory.
 // ---------------------------------------------------------------------------------------------------------
 template <int H>
-__global__ void __launch_bounds__(128) conv0_bwd_du_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(128, 3) conv0_bwd_du_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, const float* __restrict__ gam,
                                                                 const float* __restrict__ bet, bf16* __restrict__ dy,
                                                                 float* __restrict__ dbias, float* __restrict__ dgam,
@@ -201,32 +219,32 @@ __global__ void __launch_bounds__(128) conv0_bwd_du_mma_kernel(const float* __re
   extern __shared__ __align__(16) unsigned char sm[];
   float* gb = reinterpret_cast<float*>(sm);           // gamma[H], beta[H]
   float* accs = gb + 2 * H;                           // [3][H]: dbias, dgamma, dbeta
-  unsigned char* wbase = sm + 5 * H * 4 + (threadIdx.x >> 5) * (3 * TILE);
-  unsigned char* t_du = wbase;                        // dy on input, du on output
-  unsigned char* t_dv = wbase + TILE;                 // dv = dy masked by the ReLU
-  unsigned char* t_dvx = wbase + 2 * TILE;            // dv * xhat
+  uint2* wsm = reinterpret_cast<uint2*>(sm + 5 * H * 4);  // weight fragments [NT][32]
+  unsigned char* wbase = sm + 5 * H * 4 + NT * 32 * 8 + (threadIdx.x >> 5) * (2 * TILE);
+  unsigned char* t_a = wbase;                         // dy on input -> dv * xhat (in place)
+  unsigned char* t_b = wbase + TILE;                  // dv = dy masked by the ReLU -> du (in place)
   for (int i = threadIdx.x; i < H; i += blockDim.x) { gb[i] = gam[i]; gb[H + i] = bet[i]; }
   for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) accs[i] = 0.f;
+  stage_wfrags<H>(w, bias, wsm);
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  uint32_t wb[NT][2];
-  load_wfrags<H>(w, bias, g, t, wb);
   const int tpw = L0 / 16;
   const uint32_t ones = 0x3f803f80u;  // bf16 (1, 1)
   for (int tile = warp; tile < B * tpw; tile += nwarps) {
     const int b = tile / tpw, f0 = (tile - b * tpw) * 16;
     bf16* drow = dy + ((long long)b * L0 + f0) * H;
-    tile_from_global<H>(t_du, drow, lane);
+    tile_from_global<H>(t_a, drow, lane);
     uint32_t ah[4], al[4];
     load_xfrags(x + (long long)b * L, L, f0, g, t, ah, al);
     float acc[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; j++) {
+      const uint2 wv = wsm[j * 32 + lane];
       acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      mma16816(acc[j], ah, wb[j][0], wb[j][1]);
-      mma16816(acc[j], al, wb[j][0], wb[j][1]);
+      mma16816(acc[j], ah, wv.x, wv.y);
+      mma16816(acc[j], al, wv.x, wv.y);
     }
     float mean[2], rstd[2];
     tile_stats<NT>(acc, H, mean, rstd);
@@ -237,8 +255,8 @@ __global__ void __launch_bounds__(128) conv0_bwd_du_mma_kernel(const float* __re
     for (int j = 0; j < NT; j++) {
       const int c = 8 * j + 2 * t;
       const float2 g2 = *reinterpret_cast<const float2*>(gb + c), b2 = *reinterpret_cast<const float2*>(gb + H + c);
-      const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(t_du + g * RS + c * 2);
-      const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(t_du + (g + 8) * RS + c * 2);
+      const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(t_a + g * RS + c * 2);
+      const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(t_a + (g + 8) * RS + c * 2);
       const float dyv[4] = {__low2float(d01), __high2float(d01), __low2float(d23), __high2float(d23)};
       const float gg[4] = {g2.x, g2.y, g2.x, g2.y}, bb[4] = {b2.x, b2.y, b2.x, b2.y};
       float dv[4], dvx[4];
@@ -253,10 +271,10 @@ __global__ void __launch_bounds__(128) conv0_bwd_du_mma_kernel(const float* __re
         s2[hf] = fmaf(dx, xh, s2[hf]);
         acc[j][e] = xh;
       }
-      *reinterpret_cast<uint32_t*>(t_dv + g * RS + c * 2) = pack_bf16(dv[0], dv[1]);
-      *reinterpret_cast<uint32_t*>(t_dv + (g + 8) * RS + c * 2) = pack_bf16(dv[2], dv[3]);
-      *reinterpret_cast<uint32_t*>(t_dvx + g * RS + c * 2) = pack_bf16(dvx[0], dvx[1]);
-      *reinterpret_cast<uint32_t*>(t_dvx + (g + 8) * RS + c * 2) = pack_bf16(dvx[2], dvx[3]);
+      *reinterpret_cast<uint32_t*>(t_b + g * RS + c * 2) = pack_bf16(dv[0], dv[1]);
+      *reinterpret_cast<uint32_t*>(t_b + (g + 8) * RS + c * 2) = pack_bf16(dv[2], dv[3]);
+      *reinterpret_cast<uint32_t*>(t_a + g * RS + c * 2) = pack_bf16(dvx[0], dvx[1]);   // over the dy this thread just read
+      *reinterpret_cast<uint32_t*>(t_a + (g + 8) * RS + c * 2) = pack_bf16(dvx[2], dvx[3]);
     }
 #pragma unroll
     for (int hf = 0; hf < 2; hf++) {
@@ -265,38 +283,46 @@ __global__ void __launch_bounds__(128) conv0_bwd_du_mma_kernel(const float* __re
       s1[hf] /= (float)H;
       s2[hf] /= (float)(H - 1);
     }
-    // pass 2: du = rstd * (dx - s1 - xhat * s2), written over the dy tile
-#pragma unroll
-    for (int j = 0; j < NT; j++) {
-      const int c = 8 * j + 2 * t;
-      const float2 g2 = *reinterpret_cast<const float2*>(gb + c);
-      const __nv_bfloat162 v01 = *reinterpret_cast<const __nv_bfloat162*>(t_dv + g * RS + c * 2);
-      const __nv_bfloat162 v23 = *reinterpret_cast<const __nv_bfloat162*>(t_dv + (g + 8) * RS + c * 2);
-      const float o0 = rstd[0] * (__low2float(v01) * g2.x - s1[0] - acc[j][0] * s2[0]);
-      const float o1 = rstd[0] * (__high2float(v01) * g2.y - s1[0] - acc[j][1] * s2[0]);
-      const float o2 = rstd[1] * (__low2float(v23) * g2.x - s1[1] - acc[j][2] * s2[1]);
-      const float o3 = rstd[1] * (__high2float(v23) * g2.y - s1[1] - acc[j][3] * s2[1]);
-      *reinterpret_cast<uint32_t*>(t_du + g * RS + c * 2) = pack_bf16(o0, o1);
-      *reinterpret_cast<uint32_t*>(t_du + (g + 8) * RS + c * 2) = pack_bf16(o2, o3);
-    }
     __syncwarp();
-    tile_to_global<H>(t_du, drow, lane);
-    // column sums over the 16 frames of du, dv*xhat, dv:  [16 ch x 8] = tile^T[16 ch x 16 frames] . ones
+    // column sums over the 16 frames of dv*xhat and dv:  [16 ch x 8] = tile^T[16 ch x 16 frames] . ones
 #pragma unroll
     for (int m = 0; m < H / 16; m++) {
       const int mi = lane >> 3;
       const uint32_t off = ((mi >> 1) * 8 + (lane & 7)) * RS + (m * 16 + (mi & 1) * 8) * 2;
       uint32_t a[4];
       float cs[4];
-      ldsm_x4_t(a, s_u32(t_du + off));
-      cs[0] = cs[1] = cs[2] = cs[3] = 0.f; mma16816(cs, a, ones, ones);
-      if (t == 0) { atomicAdd(&accs[m * 16 + g], cs[0]); atomicAdd(&accs[m * 16 + g + 8], cs[2]); }
-      ldsm_x4_t(a, s_u32(t_dvx + off));
+      ldsm_x4_t(a, s_u32(t_a + off));
       cs[0] = cs[1] = cs[2] = cs[3] = 0.f; mma16816(cs, a, ones, ones);
       if (t == 0) { atomicAdd(&accs[H + m * 16 + g], cs[0]); atomicAdd(&accs[H + m * 16 + g + 8], cs[2]); }
-      ldsm_x4_t(a, s_u32(t_dv + off));
+      ldsm_x4_t(a, s_u32(t_b + off));
       cs[0] = cs[1] = cs[2] = cs[3] = 0.f; mma16816(cs, a, ones, ones);
       if (t == 0) { atomicAdd(&accs[2 * H + m * 16 + g], cs[0]); atomicAdd(&accs[2 * H + m * 16 + g + 8], cs[2]); }
+    }
+    __syncwarp();
+    // pass 2: du = rstd * (dx - s1 - xhat * s2), written in place over dv
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const int c = 8 * j + 2 * t;
+      const float2 g2 = *reinterpret_cast<const float2*>(gb + c);
+      const __nv_bfloat162 v01 = *reinterpret_cast<const __nv_bfloat162*>(t_b + g * RS + c * 2);
+      const __nv_bfloat162 v23 = *reinterpret_cast<const __nv_bfloat162*>(t_b + (g + 8) * RS + c * 2);
+      const float o0 = rstd[0] * (__low2float(v01) * g2.x - s1[0] - acc[j][0] * s2[0]);
+      const float o1 = rstd[0] * (__high2float(v01) * g2.y - s1[0] - acc[j][1] * s2[0]);
+      const float o2 = rstd[1] * (__low2float(v23) * g2.x - s1[1] - acc[j][2] * s2[1]);
+      const float o3 = rstd[1] * (__high2float(v23) * g2.y - s1[1] - acc[j][3] * s2[1]);
+      *reinterpret_cast<uint32_t*>(t_b + g * RS + c * 2) = pack_bf16(o0, o1);
+      *reinterpret_cast<uint32_t*>(t_b + (g + 8) * RS + c * 2) = pack_bf16(o2, o3);
+    }
+    __syncwarp();
+    tile_to_global<H>(t_b, drow, lane);
+#pragma unroll
+    for (int m = 0; m < H / 16; m++) {  // column sums of du
+      const int mi = lane >> 3;
+      uint32_t a[4];
+      float cs[4] = {0.f, 0.f, 0.f, 0.f};
+      ldsm_x4_t(a, s_u32(t_b + ((mi >> 1) * 8 + (lane & 7)) * RS + (m * 16 + (mi & 1) * 8) * 2));
+      mma16816(cs, a, ones, ones);
+      if (t == 0) { atomicAdd(&accs[m * 16 + g], cs[0]); atomicAdd(&accs[m * 16 + g + 8], cs[2]); }
     }
     __syncwarp();
   }
@@ -378,7 +404,7 @@ __global__ void __launch_bounds__(128) conv0_wgrad_mma_kernel(const float* __res
 template <int H>
 int launch_all_fwd(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* y, int B, int L,
                    int L0, cudaStream_t st) {
-  const size_t smem = 2 * H * 4 + 4 * 16 * (2 * H + 16);
+  const size_t smem = 2 * H * 4 + (H / 8) * 32 * 8 + 4 * 16 * (2 * H + 16);
   int blocks = (B * (L0 / 16) + 3) / 4;
   if (blocks > 148 * 3) blocks = 148 * 3;
   CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_fwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -389,10 +415,10 @@ int launch_all_fwd(const float* x, const float* w, const float* bias, const floa
 template <int H>
 int launch_all_bwd(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* dy, float* dw,
                    float* dbias, float* dgam, float* dbet, int B, int L, int L0, cudaStream_t st) {
-  const size_t smem1 = 5 * H * 4 + 4 * 3 * 16 * (2 * H + 16);
+  const size_t smem1 = 5 * H * 4 + (H / 8) * 32 * 8 + 4 * 2 * 16 * (2 * H + 16);
   const size_t smem2 = H * 10 * 4 + 4 * 16 * (2 * H + 16);
   int blocks = (B * (L0 / 16) + 3) / 4;
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks > 148 * 3) blocks = 148 * 3;
   CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd_du_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   conv0_bwd_du_mma_kernel<H><<<blocks, 128, smem1, st>>>(x, w, bias, gam, bet, dy, dbias, dgam, dbet, B, L, L0);
   CPC_LAUNCHED_N("conv0_bwd_du_mma", st);

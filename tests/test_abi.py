@@ -102,3 +102,34 @@ def test_prediction_weights_share_one_buffer():
     crit2.double().float()                                      # _apply re-allocates every parameter
     f2 = crit2.wPrediction.stacked()
     assert all(p.weight.data_ptr() == f2[i].data_ptr() for i, p in enumerate(crit2.wPrediction.predictors))
+
+
+def test_patch_install_swaps_reference_symbols(tmp_path, monkeypatch):
+    """cpc_audio_b200.patch.install replaces the hot-path classes inside an importable `cpc` package (here a stub
+    with the reference's module layout), which is all cpc/train.py needs to build the B200 modules."""
+    import sys
+    import types
+    pkg = types.ModuleType("cpc"); pkg.__path__ = []
+    model = types.ModuleType("cpc.model")
+    crit_pkg = types.ModuleType("cpc.criterion"); crit_pkg.__path__ = []
+    crit = types.ModuleType("cpc.criterion.criterion")
+    for name in ("ChannelNorm", "CPCEncoder", "CPCAR", "CPCModel"):
+        setattr(model, name, object)
+    for m in (crit_pkg, crit):
+        m.CPCUnsupersivedCriterion = object
+        m.PredictionNetwork = object
+    for name, mod in (("cpc", pkg), ("cpc.model", model), ("cpc.criterion", crit_pkg), ("cpc.criterion.criterion", crit)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    import cpc_audio_b200 as M
+    from cpc_audio_b200 import patch
+    patch.install(pkg)
+    assert model.CPCEncoder is M.CPCEncoder and model.CPCAR is M.CPCAR and model.CPCModel is M.CPCModel
+    assert crit.CPCUnsupersivedCriterion is M.CPCUnsupersivedCriterion
+    assert crit_pkg.CPCUnsupersivedCriterion is M.CPCUnsupersivedCriterion
+    # the constructor calls made by cpc/feature_loader.py:133-152 and cpc/train.py:31-40 work on the mirrors
+    enc = model.CPCEncoder(256, "layerNorm")
+    ar = model.CPCAR(256, 256, False, 1, mode="GRU", reverse=False)
+    m = model.CPCModel(enc, ar)
+    c = crit.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode="linear", dropout=False, nSpeakers=3,
+                                      speakerEmbedding=0, sizeInputSeq=128)
+    assert m.gEncoder.DOWNSAMPLING == 160 and c.nPredicts == 12

@@ -241,3 +241,29 @@ def test_bucket_sinks_receive_the_same_gradients(built_lib):
             assert p.grad.data_ptr() >= bucket.flat.data_ptr() and p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.flat.numel() * 4
             assert Hh.rel_err(p.grad, plain[k]) <= 1e-5, (k, rep)
     bucket.detach()
+
+
+@pytest.mark.parametrize("B,L", [(1, 20480), (5, 20480), (3, 10240), (9, 5120)])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_ragged_shapes_against_oracle(B, L, dtype, built_lib):
+    """Batch sizes that are not multiples of any tile (GRU tiles of 8 sequences, 128-row GEMM tiles, 16-frame conv0
+    tiles, warps per position) and shorter windows (S = 64, 32), default widths so that the tensor-core kernels run."""
+    d = O.Dims(B=B, L=L, H=256, Har=256, K=12, N=128, nLayers=1)
+    mp, cp = O.make_params(d, seed=40 + B, pred_scale=30.0)
+    x, label = O.make_batch(d, seed=50 + B)
+    bi, si = O.make_raw_indices(d, seed=60 + B)
+    ref = Hh.oracle_run(d, mp, cp, x, bi, si)
+    model, crit = Hh.build_modules(d, mp, cp, dtype)
+    out = Hh.run_modules(model, crit, x, label, bi, si)
+    if dtype == "f32":
+        assert Hh.max_rel(out["z"], ref["z"]) <= 1e-4 and Hh.max_rel(out["c"], ref["c"]) <= 1e-4
+        np.testing.assert_allclose(out["losses"].cpu().numpy(), ref["losses"].numpy(), rtol=1e-5, atol=1e-4)
+        for k, gr in ref["grads"].items():
+            assert Hh.rel_err(out["grads"][k], gr) <= 5e-4, k
+    else:
+        assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2 and Hh.rel_err(out["c"], ref["c"]) <= 2e-2
+        assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.02 * ref["losses"].abs() + 1e-2).all()
+        for k, gr in ref["grads"].items():
+            floor = 0.95 if (k.endswith(".bias") and "conv" in k) else 0.985
+            assert _cos(out["grads"][k], gr) >= floor, (k, _cos(out["grads"][k], gr))
+    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else 0.03) + Hh.acc_tolerance(ref["logits"], d)).all()
