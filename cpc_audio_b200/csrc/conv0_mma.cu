@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128, 3) conv0_fwd_mma_kernel(const float* __re
 // matrix (A = tile^T via ldmatrix.trans) and accumulated in shared memory.
 // ---------------------------------------------------------------------------------------------------------
 template <int H>
-__global__ void __launch_bounds__(128, 3) conv0_bwd_du_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(128, 2) conv0_bwd_du_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, const float* __restrict__ gam,
                                                                 const float* __restrict__ bet, bf16* __restrict__ dy,
                                                                 float* __restrict__ dbias, float* __restrict__ dgam,

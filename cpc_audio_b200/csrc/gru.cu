@@ -318,13 +318,13 @@ template <class T> constexpr bool isf_dummy() { return sizeof(T) == 4; }
 
 constexpr int kBT = 2;
 
-template <class WT> size_t rec_fwd_smem(int Har) {
+template <class WT> size_t rec_fwd_smem(int Har, int bt = kBT) {
   const int wstride = Har + WVec<WT>::V * 2;
-  return align_up((size_t)3 * HC * wstride * sizeof(WT), 16) + (size_t)(2 * kBT * Har + 3 * HC * kBT + 3 * HC) * sizeof(float);
+  return align_up((size_t)3 * HC * wstride * sizeof(WT), 16) + (size_t)(2 * bt * Har + 3 * HC * bt + 3 * HC) * sizeof(float);
 }
-template <class WT> size_t rec_bwd_smem(int Har) {
+template <class WT> size_t rec_bwd_smem(int Har, int bt = kBT) {
   const int wstride = 3 * Har + WVec<WT>::V * 8;
-  return align_up((size_t)HC * wstride * sizeof(WT), 16) + (size_t)(2 * kBT * 3 * Har + HC * kBT) * sizeof(float);
+  return align_up((size_t)HC * wstride * sizeof(WT), 16) + (size_t)(2 * bt * 3 * Har + HC * bt) * sizeof(float);
 }
 
 template <class K>
@@ -374,7 +374,9 @@ int gru_fwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
   typedef T WT;
   const int B = g.B, S = g.S, Har = g.Har;
   if (Har % HC != 0 || Har / HC > 8) return fail(CPCB200_ERR_UNSUPPORTED, "gru: Har=%d needs a cluster of %d CTAs (max 8)", Har, Har / HC);
-  const size_t smem = rec_fwd_smem<WT>(Har);
+  int bt = kBT;  // sequences per cluster; falls back to 1 when the resident slice leaves no room for 2
+  size_t smem = rec_fwd_smem<WT>(Har, bt);
+  if (smem > 227 * 1024) { bt = 1; smem = rec_fwd_smem<WT>(Har, bt); }
   if (smem > 227 * 1024) return fail(CPCB200_ERR_UNSUPPORTED, "gru fwd: W_hh slice needs %zu B of shared memory (Har=%d, dtype %s)", smem, Har, g.bf16 ? "bf16" : "f32");
   GruLayout lay = gru_layout(g);
   char* sv = static_cast<char*>(save);
@@ -430,7 +432,8 @@ int gru_fwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     }
     if (!done) {
       void* args[] = {&gic, &whh, &bhh, &h0l, &cout, &cTo, &sR, &sU, &sN, &sHN, &hTl, &Bv, &Sv, &Hv};
-      CPC_TRY(launch_cluster("gru_rec_fwd", gru_rec_fwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, 3 * HC * 2, smem, st, args));
+      if (bt == kBT) CPC_TRY(launch_cluster("gru_rec_fwd", gru_rec_fwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, 3 * HC * 2, smem, st, args));
+      else CPC_TRY(launch_cluster("gru_rec_fwd", gru_rec_fwd_kernel<WT, T, 1>, Har / HC, B, 3 * HC * 2, smem, st, args));
     }
   }
   return 0;
@@ -442,7 +445,9 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
   typedef T WT;
   const int B = g.B, S = g.S, Har = g.Har, G = 3 * Har;
   if (Har % HC != 0 || Har / HC > 8) return fail(CPCB200_ERR_UNSUPPORTED, "gru: Har=%d", Har);
-  const size_t smem = rec_bwd_smem<WT>(Har);
+  int bt = kBT;
+  size_t smem = rec_bwd_smem<WT>(Har, bt);
+  if (smem > 227 * 1024) { bt = 1; smem = rec_bwd_smem<WT>(Har, bt); }
   if (smem > 227 * 1024) return fail(CPCB200_ERR_UNSUPPORTED, "gru bwd: W_hh slice needs %zu B of shared memory", smem);
   GruLayout lay = gru_layout(g);
   const char* sv = static_cast<const char*>(save);
@@ -480,7 +485,8 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     }
     if (!done) {
       void* args[] = {&dcl, &cl, &h0l, &sR, &sU, &sN, &sHN, &whh, &dgi, &dgh, &dh0, &Bv, &Sv, &Hv};
-      CPC_TRY(launch_cluster("gru_rec_bwd", gru_rec_bwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, HC * 8, smem, st, args));
+      if (bt == kBT) CPC_TRY(launch_cluster("gru_rec_bwd", gru_rec_bwd_kernel<WT, T, kBT>, Har / HC, (B + kBT - 1) / kBT, HC * 8, smem, st, args));
+      else CPC_TRY(launch_cluster("gru_rec_bwd", gru_rec_bwd_kernel<WT, T, 1>, Har / HC, B, HC * 8, smem, st, args));
     }
 
     if (!done) {  // the tensor-core recurrence accumulates the bias gradients itself
