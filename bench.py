@@ -342,8 +342,10 @@ def run_ours(a):
     log(f"e2e: {ms_e2e / a.steps:.3f} ms/step; per-kernel pass")
     if rank == 0:
         lib.cpcb200_prof_enable(1)
-        for _ in range(min(a.steps, 10)):
-            step(x_dev)
+    for _ in range(min(a.steps, 10)):  # every rank runs these steps (they contain the all-reduce)
+        step(x_dev)
+    torch.cuda.synchronize(dev)
+    if rank == 0:
         buf = ctypes.create_string_buffer(1 << 16)
         L.check(lib.cpcb200_prof_report(buf, len(buf)), "prof_report")
         lib.cpcb200_prof_enable(0)
