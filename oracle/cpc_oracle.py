@@ -89,6 +89,64 @@ def make_params(d: Dims, seed: int = 0, pred_scale: float = 1.0):
     return model, crit
 
 
+T_HEADS, T_DFF = 8, 2048  # cpc/transformers.py:98-99 defaults (nheads=8, dff=2048)
+
+
+def make_params_transformer(d: Dims, seed: int = 0, out_scale: float = 1.0):
+    """Deterministic parameters of the K one-layer transformer prediction heads (rnnMode='transformer',
+    criterion.py:82-88 -> transformers.py:129-139), keyed like the reference state_dict.  Requires Har == H."""
+    assert d.H == d.Har
+    g = torch.Generator().manual_seed(seed + 7919)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g, dtype=torch.float32) * std
+
+    D, dk, W = d.H, d.H // T_HEADS, d.W
+    crit = {}
+    for k in range(d.K):
+        pre = f"wPrediction.predictors.{k}.0."
+        for nm in ("Wo", "Wk", "Wq", "Wv"):
+            crit[pre + f"multihead.{nm}.weight"] = rn(D, D, std=1.0 / math.sqrt(D))
+        crit[pre + "multihead.Att.Krelpos"] = rn(dk, W, std=1.0 / math.sqrt(dk))
+        crit[pre + "ln_multihead.weight"] = 1.0 + rn(D, std=0.1)
+        crit[pre + "ln_multihead.bias"] = rn(D, std=0.1)
+        crit[pre + "ffnetwork.lin1.weight"] = rn(T_DFF, D, std=1.0 / math.sqrt(D))
+        crit[pre + "ffnetwork.lin1.bias"] = rn(T_DFF, std=0.1)
+        crit[pre + "ffnetwork.lin2.weight"] = rn(D, T_DFF, std=1.0 / math.sqrt(T_DFF))
+        crit[pre + "ffnetwork.lin2.bias"] = rn(D, std=0.1)
+        crit[pre + "ln_ffnetwork.weight"] = (1.0 + rn(D, std=0.1)) * out_scale
+        crit[pre + "ln_ffnetwork.bias"] = rn(D, std=0.1) * out_scale
+    return crit
+
+
+def transformer_head_forward(x, p, pre):
+    """One TransformerLayer in eval mode (dropout = identity): transformers.py:38-49 (attention with the relative-
+    position skew), 76-83 (multi-head), 86-95 (FFN), 109-111 (post-LN residuals).  x (B, W, D) -> (B, W, D)."""
+    B, W, D = x.shape
+    nh, dk = T_HEADS, D // T_HEADS
+
+    def heads(t):  # transformers.py:67-69
+        return t.view(B, W, nh, dk).transpose(1, 2).contiguous().view(B * nh, W, dk)
+
+    q = heads(x @ p[pre + "multihead.Wq.weight"].t())
+    k = heads(x @ p[pre + "multihead.Wk.weight"].t())
+    v = heads(x @ p[pre + "multihead.Wv.weight"].t())
+    qk = torch.bmm(q, k.transpose(-2, -1))
+    qp = q.matmul(p[pre + "multihead.Att.Krelpos"])                         # (B*nh, W, W)
+    i = torch.arange(W).view(W, 1)
+    c = torch.arange(W).view(1, W)
+    idx = (W - 1 - i + c).clamp(0, W - 1)                                   # skew: key c <= query i reads column W-1-(i-c)
+    qk = qk + torch.gather(qp, 2, idx.unsqueeze(0).expand(B * nh, W, W))
+    mask = torch.zeros(W, W).masked_fill(c > i, float("-inf"))            # transformers.py:29-32 (causal)
+    a = torch.softmax(qk / math.sqrt(dk) + mask, dim=2)
+    y = torch.bmm(a, v).view(B, nh, W, dk).transpose(1, 2).contiguous().view(B, W, D)
+    y = y @ p[pre + "multihead.Wo.weight"].t()
+    y1 = F.layer_norm(x + y, (D,), p[pre + "ln_multihead.weight"], p[pre + "ln_multihead.bias"], 1e-5)
+    f = torch.relu(y1 @ p[pre + "ffnetwork.lin1.weight"].t() + p[pre + "ffnetwork.lin1.bias"])
+    f = f @ p[pre + "ffnetwork.lin2.weight"].t() + p[pre + "ffnetwork.lin2.bias"]
+    return F.layer_norm(y1 + f, (D,), p[pre + "ln_ffnetwork.weight"], p[pre + "ln_ffnetwork.bias"], 1e-5)
+
+
 def make_batch(d: Dims, seed: int = 1234):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(d.B, 1, d.L, generator=g, dtype=torch.float32) * 0.1
@@ -179,7 +237,7 @@ def ext_indices_np(batch_idx, seq_idx, B, N, W, S):
     return (seq + batch_idx * S).reshape(B, N, W)
 
 
-def criterion_forward(c, z, crit_p, batch_idx, seq_idx, K, N, materialize=True):
+def criterion_forward(c, z, crit_p, batch_idx, seq_idx, K, N, materialize=True, heads="linear"):
     """criterion.py:225-257 with the linear heads of criterion.py:89-95,106-117.
 
     c (B,S,Har), z (B,S,H) fp32.  Returns (losses (1,K), acc (1,K), logits list of (B*W, N+1)).
@@ -195,7 +253,10 @@ def criterion_forward(c, z, crit_p, batch_idx, seq_idx, K, N, materialize=True):
     losses, accs, all_logits = [], [], []
     for k in range(1, K + 1):
         pos = z[:, k:k + W].reshape(B, 1, W, H)                        # criterion.py:207-215
-        pred = cw @ crit_p[f"wPrediction.predictors.{k - 1}.weight"].t()   # criterion.py:108
+        if heads == "linear":
+            pred = cw @ crit_p[f"wPrediction.predictors.{k - 1}.weight"].t()   # criterion.py:108
+        else:                                                                   # criterion.py:82-88 (eval mode)
+            pred = transformer_head_forward(cw, crit_p, f"wPrediction.predictors.{k - 1}.0.")
         if materialize:
             full = torch.cat((pos, neg), dim=1)                        # criterion.py:216
             out = (pred.view(B, 1, W, H) * full).mean(dim=3)           # criterion.py:115-116

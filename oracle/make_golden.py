@@ -30,21 +30,26 @@ def import_reference():
             sys.modules[name] = types.ModuleType(name)
     sys.path.insert(0, REF)
     import cpc.model as ref_model
+    import cpc.transformers as ref_tr
+    sys.modules["transformers"] = ref_tr  # criterion.py:83 does a bare `from transformers import ...`
     import cpc.criterion as ref_crit
     return ref_model, ref_crit
 
 
-def run_reference(d: O.Dims, pred_scale: float, seed: int):
+def run_reference(d: O.Dims, pred_scale: float, seed: int, heads="linear"):
     ref_model, ref_crit = import_reference()
     torch.manual_seed(0)
     enc = ref_model.CPCEncoder(d.H, "layerNorm")
     ar = ref_model.CPCAR(d.H, d.Har, False, d.nLayers, mode="GRU", reverse=False)
     model = ref_model.CPCModel(enc, ar)
-    crit = ref_crit.CPCUnsupersivedCriterion(d.K, d.Har, d.H, d.N, mode=None, rnnMode="linear", dropout=False,
+    crit = ref_crit.CPCUnsupersivedCriterion(d.K, d.Har, d.H, d.N, mode=None, rnnMode=heads, dropout=False,
                                              speakerEmbedding=0, nSpeakers=0, sizeInputSeq=d.S)
     mp, cp = O.make_params(d, seed=seed, pred_scale=pred_scale)
+    if heads == "transformer":
+        cp = O.make_params_transformer(d, seed=seed, out_scale=pred_scale)
     missing = model.load_state_dict(mp, strict=True)
-    crit.load_state_dict(cp, strict=True)
+    crit.load_state_dict(cp, strict=False)  # the transformer heads also hold the constant buffers Att.z / Att.mask
+    assert all(k.endswith(("Att.z", "Att.mask")) for k in set(crit.state_dict()) - set(cp)), set(crit.state_dict()) - set(cp)
     x, label = O.make_batch(d, seed=1234 + seed)
     bi, si = O.make_raw_indices(d, seed=4321 + seed)
 
@@ -63,6 +68,8 @@ def run_reference(d: O.Dims, pred_scale: float, seed: int):
     try:
         model.train()
         crit.train()
+        if heads == "transformer":
+            crit.eval()  # dropout 0.1 inside the heads (transformers.py:18,92): parity is defined in eval mode
         c, z, _ = model(x, label)
         losses, acc = crit(c, z, label)
     finally:
@@ -75,12 +82,12 @@ def run_reference(d: O.Dims, pred_scale: float, seed: int):
                 acc=acc.detach(), grads=grads, mp=mp, cp=cp)
 
 
-def check_oracle(d, r):
+def check_oracle(d, r, heads="linear"):
     """The restatement must reproduce the reference (this is what pins the oracle)."""
     mp = {k: v.clone().requires_grad_(True) for k, v in r["mp"].items()}
     cp = {k: v.clone().requires_grad_(True) for k, v in r["cp"].items()}
     c, z = O.model_forward(r["x"], mp, d.nLayers)
-    losses, acc, _ = O.criterion_forward(c, z, cp, r["bi"], r["si"], d.K, d.N)
+    losses, acc, _ = O.criterion_forward(c, z, cp, r["bi"], r["si"], d.K, d.N, heads=heads)
     losses.sum().backward()
     errs = dict(z=(z - r["z"]).abs().max().item(), c=(c - r["c"]).abs().max().item(),
                 loss=(losses - r["losses"]).abs().max().item(), acc=(acc - r["acc"]).abs().max().item())
@@ -101,8 +108,8 @@ def subsample(t, n=4096):
     return f[::step][:n].numpy().copy()
 
 
-def save(name, d, r, pred_scale, seed):
-    out = dict(dims=np.array([d.B, d.L, d.H, d.Har, d.K, d.N, d.nLayers], dtype=np.int64),
+def save(name, d, r, pred_scale, seed, heads="linear"):
+    out = dict(heads=np.array(heads), dims=np.array([d.B, d.L, d.H, d.Har, d.K, d.N, d.nLayers], dtype=np.int64),
                pred_scale=np.float32(pred_scale), seed=np.int64(seed),
                losses=r["losses"].numpy(), acc=r["acc"].numpy(),
                z_sub=subsample(r["z"]), c_sub=subsample(r["c"]),
@@ -123,13 +130,21 @@ CASES = {
     "small2l": (O.Dims(B=2, L=3200, H=128, Har=64, K=5, N=16, nLayers=2), 30.0, 2),
     "cfg1": (O.Dims(B=2, L=20480, H=256, Har=256, K=12, N=128, nLayers=1), 1.0, 3),      # BASELINE config 1
     "cfg1_scaled": (O.Dims(B=2, L=20480, H=256, Har=256, K=12, N=128, nLayers=1), 30.0, 4),
+    # rnnMode='transformer' prediction heads (BASELINE config 4 dims at B=2; small variant with 64-wide model)
+    "cfg4": (O.Dims(B=2, L=20480, H=256, Har=256, K=12, N=128, nLayers=1), 30.0, 5, "transformer"),
+    "cfg4_small": (O.Dims(B=3, L=3200, H=64, Har=64, K=3, N=8, nLayers=1), 30.0, 6, "transformer"),
 }
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    for name, (d, ps, seed) in CASES.items():
-        print(f"[{name}] {d} pred_scale={ps}")
-        r = run_reference(d, ps, seed)
+    only = sys.argv[1:]
+    for name, case in CASES.items():
+        if only and name not in only:
+            continue
+        d, ps, seed = case[:3]
+        heads = case[3] if len(case) > 3 else "linear"
+        print(f"[{name}] {d} pred_scale={ps} heads={heads}")
+        r = run_reference(d, ps, seed, heads)
         print("  losses", np.round(r["losses"].numpy().ravel(), 4), "\n  acc", np.round(r["acc"].numpy().ravel(), 4))
-        check_oracle(d, r)
-        save(name, d, r, ps, seed)
+        check_oracle(d, r, heads)
+        save(name, d, r, ps, seed, heads)

@@ -8,6 +8,11 @@ from oracle import cpc_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["small", "small2l", "cfg1", "cfg1_scaled"]
+T_CASES = ["cfg4_small", "cfg4"]  # rnnMode='transformer' prediction heads
+
+
+def case_heads(g):
+    return str(g["heads"]) if "heads" in g.files else "linear"
 
 
 def load_case(name):
@@ -16,6 +21,8 @@ def load_case(name):
     d = O.Dims(B=B, L=L, H=H, Har=Har, K=K, N=N, nLayers=nL)
     seed = int(g["seed"])
     mp, cp = O.make_params(d, seed=seed, pred_scale=float(g["pred_scale"]))
+    if case_heads(g) == "transformer":
+        cp = O.make_params_transformer(d, seed=seed, out_scale=float(g["pred_scale"]))
     x, label = O.make_batch(d, seed=1234 + seed)
     bi, si = O.make_raw_indices(d, seed=4321 + seed)
     return g, d, mp, cp, x, label, bi, si
@@ -27,27 +34,28 @@ def subsample(t, n=4096):
     return f[::step][:n].cpu().numpy().copy()
 
 
-def oracle_run(d, mp, cp, x, bi, si, materialize=True):
+def oracle_run(d, mp, cp, x, bi, si, materialize=True, heads="linear"):
     """fwd + bwd of the CPU oracle; returns dict(c, z, losses, acc, grads{model.*, crit.*})."""
     mp = {k: v.clone().requires_grad_(True) for k, v in mp.items()}
     cp = {k: v.clone().requires_grad_(True) for k, v in cp.items()}
     c, z = O.model_forward(x, mp, d.nLayers)
-    losses, acc, logits = O.criterion_forward(c, z, cp, bi, si, d.K, d.N, materialize=materialize)
+    losses, acc, logits = O.criterion_forward(c, z, cp, bi, si, d.K, d.N, materialize=materialize, heads=heads)
     losses.sum().backward()
     grads = {f"model.{k}": v.grad for k, v in mp.items()}
     grads.update({f"crit.{k}": v.grad for k, v in cp.items()})
     return dict(c=c.detach(), z=z.detach(), losses=losses.detach(), acc=acc.detach(), grads=grads, logits=logits)
 
 
-def build_modules(d, mp, cp, dtype, device="cuda"):
+def build_modules(d, mp, cp, dtype, device="cuda", heads="linear"):
     import cpc_audio_b200 as M
     enc = M.CPCEncoder(d.H, "layerNorm", compute_dtype=dtype)
     ar = M.CPCAR(d.H, d.Har, False, d.nLayers, mode="GRU", reverse=False, compute_dtype=dtype)
     model = M.CPCModel(enc, ar)
-    crit = M.CPCUnsupersivedCriterion(d.K, d.Har, d.H, d.N, mode=None, rnnMode="linear", dropout=False,
+    crit = M.CPCUnsupersivedCriterion(d.K, d.Har, d.H, d.N, mode=None, rnnMode=heads, dropout=False,
                                       speakerEmbedding=0, nSpeakers=0, sizeInputSeq=d.S, compute_dtype=dtype)
     model.load_state_dict(mp, strict=True)
-    crit.load_state_dict(cp, strict=True)
+    missing = crit.load_state_dict(cp, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith(("Att.z", "Att.mask")) for k in missing.missing_keys), missing
     return model.to(device), crit.to(device)
 
 

@@ -11,13 +11,13 @@ from oracle import cpc_oracle as O
 from tests import helpers as Hh
 
 
-@pytest.mark.parametrize("name", Hh.CASES)
+@pytest.mark.parametrize("name", Hh.CASES + Hh.T_CASES)
 def test_oracle_matches_reference_fixture(name):
     g, d, mp, cp, x, label, bi, si = Hh.load_case(name)
     assert int(bi.sum()) == int(g["bi_sum"]) and int(si.sum()) == int(g["si_sum"]), "seeded draws changed"
     ext = O.ext_indices_np(bi.numpy(), si.numpy(), d.B, d.N, d.W, d.S)
     assert np.array_equal(ext.astype(np.int32), g["ext_idx"]), "negative-sample indices must be bit-exact"
-    r = Hh.oracle_run(d, mp, cp, x, bi, si)
+    r = Hh.oracle_run(d, mp, cp, x, bi, si, heads=Hh.case_heads(g))
     np.testing.assert_allclose(r["losses"].numpy(), g["losses"], rtol=0, atol=2e-5)
     np.testing.assert_array_equal(r["acc"].numpy(), g["acc"])
     np.testing.assert_allclose(Hh.subsample(r["z"]), g["z_sub"], rtol=0, atol=2e-5)
