@@ -29,6 +29,13 @@ class GruParams(C.Structure):
                 ("b_ih", C.c_void_p * MAX_GRU_LAYERS), ("b_hh", C.c_void_p * MAX_GRU_LAYERS)]
 
 
+class THeadParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("wq", "wk", "wv", "wo", "krelpos", "ln1_w", "ln1_b", "w1", "b1", "w2", "b2",
+                                          "ln2_w", "ln2_b")] + [("dff", C.c_int32), ("nheads", C.c_int32)]
+
+
+THEAD_FIELDS = ("wq", "wk", "wv", "wo", "krelpos", "ln1_w", "ln1_b", "w1", "b1", "w2", "b2", "ln2_w", "ln2_b")
+
 _P, _SZ, _I = C.c_void_p, C.c_size_t, C.c_int
 _DP = C.POINTER(Dims)
 
@@ -52,6 +59,10 @@ SIGNATURES = {
     "cpcb200_criterion_ws_bytes": (_SZ, [_DP, _I]),
     "cpcb200_criterion_fwd": (_I, [_DP, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "cpcb200_criterion_bwd": (_I, [_DP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "cpcb200_criterion_t_save_bytes": (_SZ, [_DP, _I, _I]),
+    "cpcb200_criterion_t_ws_bytes": (_SZ, [_DP, _I, _I, _I]),
+    "cpcb200_criterion_t_fwd": (_I, [_DP, _P, _P, C.POINTER(THeadParams), _P, _P, _P, _P, _P, _SZ, _P]),
+    "cpcb200_criterion_t_bwd": (_I, [_DP, _P, _P, C.POINTER(THeadParams), _P, _P, _P, _P, _P, C.POINTER(THeadParams), _P, _SZ, _P]),
     "cpcb200_adam_step": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
     "cpcb200_test_gemm_nt": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "cpcb200_test_gemm_tn": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

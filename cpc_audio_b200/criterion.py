@@ -34,20 +34,83 @@ class _PredictorWeight(nn.Module):
         self.out_features = weight.shape[0]
 
 
+T_HEADS, T_DFF = 8, 2048  # cpc/transformers.py:98-99 defaults used by criterion.py:84-88
+
+
+class _Attention(nn.Module):
+    """Parameter / buffer holder of transformers.py:10-32 (relpos=True): Krelpos (dk, S), buffers z and mask."""
+
+    def __init__(self, sizeSeq, dk):
+        super().__init__()
+        import math
+        self.sizeSeq = sizeSeq
+        self.Krelpos = nn.Parameter(torch.empty(dk, sizeSeq).uniform_(-1.0 / math.sqrt(dk), 1.0 / math.sqrt(dk)))
+        self.register_buffer("z", torch.zeros(1, sizeSeq, 1))
+        mask = 1 - torch.tril(torch.ones(sizeSeq, sizeSeq), diagonal=0)
+        mask[mask == 1] = -float("inf")
+        self.register_buffer("mask", mask.unsqueeze(0))
+
+
+class _MultiHead(nn.Module):
+    def __init__(self, sizeSeq, dmodel, nheads):
+        super().__init__()
+        self.Wo = nn.Linear(dmodel, dmodel, bias=False)
+        self.Wk = nn.Linear(dmodel, dmodel, bias=False)
+        self.Wq = nn.Linear(dmodel, dmodel, bias=False)
+        self.Wv = nn.Linear(dmodel, dmodel, bias=False)
+        self.nheads, self.dk = nheads, dmodel // nheads
+        self.Att = _Attention(sizeSeq, self.dk)
+
+
+class _FFN(nn.Module):
+    def __init__(self, dmodel, dff):
+        super().__init__()
+        self.lin1 = nn.Linear(dmodel, dff, bias=True)
+        self.lin2 = nn.Linear(dff, dmodel, bias=True)
+
+
+class _TransformerLayer(nn.Module):
+    """Parameter holder with the module tree (hence state_dict keys) of transformers.py:98-106."""
+
+    def __init__(self, sizeSeq, dmodel, dff=T_DFF, nheads=T_HEADS):
+        super().__init__()
+        self.multihead = _MultiHead(sizeSeq, dmodel, nheads)
+        self.ln_multihead = nn.LayerNorm(dmodel)
+        self.ffnetwork = _FFN(dmodel, dff)
+        self.ln_ffnetwork = nn.LayerNorm(dmodel)
+
+    def thead_tensors(self):
+        m = self.multihead
+        return [m.Wq.weight, m.Wk.weight, m.Wv.weight, m.Wo.weight, m.Att.Krelpos, self.ln_multihead.weight,
+                self.ln_multihead.bias, self.ffnetwork.lin1.weight, self.ffnetwork.lin1.bias, self.ffnetwork.lin2.weight,
+                self.ffnetwork.lin2.bias, self.ln_ffnetwork.weight, self.ln_ffnetwork.bias]
+
+
 class PredictionNetwork(nn.Module):
-    """cpc/criterion/criterion.py:44-95, linear heads.  Parameters are K views into one (K, H, Har) buffer so
-    that the K projections run as a single GEMM; ``stacked()`` re-packs them if .to()/.cuda() split them."""
+    """cpc/criterion/criterion.py:44-95: K prediction heads, ``rnnMode`` 'linear' (nn.Linear, criterion.py:89-95) or
+    'transformer' (one-layer transformers, criterion.py:82-88).  The linear weights are K views into one (K, H, Har)
+    buffer so that the K projections run as a single GEMM; ``stacked()`` re-packs them if .to()/.cuda() split them."""
 
     def __init__(self, nPredicts, dimOutputAR, dimOutputEncoder, rnnMode=None, dropout=False, sizeInputSeq=116):
         super().__init__()
-        if rnnMode in ("RNN", "LSTM", "ffd", "conv4", "conv8", "conv12", "transformer"):
+        if rnnMode in ("RNN", "LSTM", "ffd", "conv4", "conv8", "conv12"):
             raise NotImplementedError(f"cpc_audio_b200: rnnMode={rnnMode!r} prediction heads are outside the accelerated "
-                                      f"hot path of this build (linear heads only: pass --rnnMode linear)")
+                                      f"hot path of this build (use --rnnMode linear or --rnnMode transformer)")
         if dropout:
             raise NotImplementedError("cpc_audio_b200: criterion dropout is outside the accelerated hot path")
         self.RESIDUAL_STD = 0.01
         self.dimOutputAR = dimOutputAR
         self.dropout = None
+        self.transformer = rnnMode == "transformer"
+        if self.transformer:
+            if dimOutputAR != dimOutputEncoder or dimOutputEncoder % T_HEADS != 0:
+                raise NotImplementedError("cpc_audio_b200: transformer heads need hiddenGar == hiddenEncoder (criterion.py:85)")
+            if sizeInputSeq > 128:
+                raise NotImplementedError("cpc_audio_b200: transformer heads support at most 128 anchor positions")
+            self.sizeInputSeq = sizeInputSeq
+            self.predictors = nn.ModuleList([nn.Sequential(_TransformerLayer(sizeInputSeq, dimOutputEncoder))
+                                             for _ in range(nPredicts)])
+            return
         flat = torch.empty(nPredicts, dimOutputEncoder, dimOutputAR)
         for i in range(nPredicts):
             # nn.Linear default init first (consumes the generator like the reference constructor does) ...
@@ -133,6 +196,56 @@ class _CriterionFn(torch.autograd.Function):
         return (dc, dz, None, None, None, *dw.unbind(0))
 
 
+class _CriterionTFn(torch.autograd.Function):
+    """Transformer heads + scoring + InfoNCE.  params = 13 tensors per head, head-major (see _TransformerLayer)."""
+
+    @staticmethod
+    def forward(ctx, c, z, ext, dims, *params):
+        lib = L.lib()
+        B, S, H, Har, K, N, dtype_code = dims
+        dev = c.device
+        c = c.contiguous().float()
+        z = z.contiguous().float()
+        nf = len(L.THEAD_FIELDS)
+        stacked = [torch.stack([params[k * nf + j].detach() for k in range(K)]).contiguous() for j in range(nf)]
+        tp = L.THeadParams(*[t.data_ptr() for t in stacked], T_DFF, T_HEADS)
+        d = L.make_dims(B, S * 160, H, Har, K, N, 1, dtype_code)
+        losses = torch.empty(K, device=dev, dtype=torch.float32)
+        acc = torch.empty(K, device=dev, dtype=torch.float32)
+        save = _bytes(lib.cpcb200_criterion_t_save_bytes(d, T_DFF, T_HEADS), dev)
+        wsn = lib.cpcb200_criterion_t_ws_bytes(d, T_DFF, T_HEADS, 0)
+        ws = _bytes(wsn, dev)
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_criterion_t_fwd(d, L.ptr(c), L.ptr(z), tp, L.ptr(ext), L.ptr(losses), L.ptr(acc), L.ptr(save),
+                                                L.ptr(ws), wsn, L.stream_ptr(dev)), "criterion_t_fwd")
+        ctx.save_for_backward(c, z, ext, save, *stacked)
+        ctx.dims = dims
+        ctx.mark_non_differentiable(acc)
+        return losses, acc
+
+    @staticmethod
+    def backward(ctx, dlosses, _dacc):
+        lib = L.lib()
+        c, z, ext, save, *stacked = ctx.saved_tensors
+        B, S, H, Har, K, N, dtype_code = ctx.dims
+        dev = c.device
+        d = L.make_dims(B, S * 160, H, Har, K, N, 1, dtype_code)
+        tp = L.THeadParams(*[t.data_ptr() for t in stacked], T_DFF, T_HEADS)
+        grads = [torch.zeros_like(t) for t in stacked]
+        tg = L.THeadParams(*[t.data_ptr() for t in grads], T_DFF, T_HEADS)
+        dc = torch.empty_like(c)
+        dz = torch.empty_like(z)
+        wsn = lib.cpcb200_criterion_t_ws_bytes(d, T_DFF, T_HEADS, 1)
+        ws = _bytes(wsn, dev)
+        dlosses = dlosses.contiguous().float()
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_criterion_t_bwd(d, L.ptr(c), L.ptr(z), tp, L.ptr(ext), L.ptr(dlosses), L.ptr(save), L.ptr(dc),
+                                                L.ptr(dz), tg, L.ptr(ws), wsn, L.stream_ptr(dev)), "criterion_t_bwd")
+        nf = len(L.THEAD_FIELDS)
+        flat = [grads[j][k] for k in range(K) for j in range(nf)]
+        return (dc, dz, None, None, *flat)
+
+
 class CPCUnsupersivedCriterion(BaseCriterion):
     """cpc/criterion/criterion.py:139-257 (class name spelled as in the reference)."""
 
@@ -184,6 +297,16 @@ class CPCUnsupersivedCriterion(BaseCriterion):
         dims = (batchSize, seqSize, H, dimAR, self.nPredicts, self.negativeSamplingExt, _dtype_code(self.compute_dtype))
         batchIdx, seqIdx = self.sampleIndices(batchSize, windowSize, seqSize, encodedData.device)
         ext = self.extIndices(batchIdx, seqIdx, dims)
+        if self.wPrediction.transformer:
+            if self.training:
+                raise NotImplementedError("cpc_audio_b200: the transformer prediction heads apply dropout 0.1 in train() mode "
+                                          "(transformers.py:18,92); this build implements their eval() semantics - call "
+                                          "criterion.eval() (gradients are still computed)")
+            if windowSize != self.wPrediction.sizeInputSeq:
+                raise ValueError(f"transformer heads were built for {self.wPrediction.sizeInputSeq} positions, got {windowSize}")
+            params = [t for p in self.wPrediction.predictors for t in p[0].thead_tensors()]
+            losses, acc = _CriterionTFn.apply(cFeature, encodedData, ext, dims, *params)
+            return losses.view(1, -1), acc.view(1, -1)
         w_flat = self.wPrediction.stacked()
         weights = [p.weight for p in self.wPrediction.predictors]
         losses, acc = _CriterionFn.apply(cFeature, encodedData, ext, dims, w_flat, *weights)

@@ -92,9 +92,10 @@ int gru_bwd(const Geo&, const float*, const float*, const cpcb200_gru_params*, c
 int sample_ext_idx(const Geo&, const int64_t*, const int64_t*, int32_t*, cudaStream_t);
 size_t criterion_save_bytes(const Geo& g);
 size_t criterion_ws_bytes(const Geo& g, int backward);
-int criterion_fwd(const Geo&, const float*, const float*, const float*, const int*, float*, float*, void*, void*, size_t, cudaStream_t);
-int criterion_bwd(const Geo&, const float*, const float*, const float*, const int*, const float*, const void*, float*, float*,
-                  float*, void*, size_t, cudaStream_t);
+int criterion_fwd(const Geo&, const float*, const float*, const float*, const cpcb200_thead_params*, const int*, float*, float*,
+                  void*, void*, size_t, cudaStream_t);
+int criterion_bwd(const Geo&, const float*, const float*, const float*, const cpcb200_thead_params*, const int*, const float*,
+                  const void*, float*, float*, float*, const cpcb200_thead_params*, void*, size_t, cudaStream_t);
 
 int gemm_nt_simt(bool, bool, int, int, int, const RowView&, const void*, const float*, const OutView&, cudaStream_t);
 int gemm_tn_simt(bool, int, int, int, const RowView&, const RowView&, float*, int, int, int, int, cudaStream_t);
@@ -259,7 +260,7 @@ int cpcb200_criterion_fwd(const cpcb200_dims* d, const float* c, const float* z,
   CPC_TRY(check_crit(g));
   NOT_NULL(c); NOT_NULL(z); NOT_NULL(w_pred); NOT_NULL(ext); NOT_NULL(losses); NOT_NULL(acc); NOT_NULL(save); NOT_NULL(ws);
   prof_mark(static_cast<cudaStream_t>(stream));
-  return criterion_fwd(g, c, z, w_pred, ext, losses, acc, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  return criterion_fwd(g, c, z, w_pred, nullptr, ext, losses, acc, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int cpcb200_criterion_bwd(const cpcb200_dims* d, const float* c, const float* z, const float* w_pred, const int32_t* ext,
                           const float* dlosses, const void* save, float* dc, float* dz, float* dw_pred, void* ws,
@@ -269,7 +270,49 @@ int cpcb200_criterion_bwd(const cpcb200_dims* d, const float* c, const float* z,
   NOT_NULL(c); NOT_NULL(z); NOT_NULL(w_pred); NOT_NULL(ext); NOT_NULL(dlosses); NOT_NULL(save); NOT_NULL(dc); NOT_NULL(dz);
   NOT_NULL(dw_pred); NOT_NULL(ws);
   prof_mark(static_cast<cudaStream_t>(stream));
-  return criterion_bwd(g, c, z, w_pred, ext, dlosses, save, dc, dz, dw_pred, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  return criterion_bwd(g, c, z, w_pred, nullptr, ext, dlosses, save, dc, dz, dw_pred, nullptr, ws, ws_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+static int thead_geo(const cpcb200_dims* d, int dff, int nheads, Geo* g) {
+  CPC_TRY(make_geo(d, g));
+  CPC_TRY(check_crit(*g));
+  if (dff <= 0 || dff % 64 != 0 || nheads <= 0 || g->H % nheads != 0)
+    return fail(CPCB200_ERR_BAD_DIMS, "transformer heads: dff=%d (multiple of 64), nheads=%d (divides H=%d)", dff, nheads, g->H);
+  if (g->H != g->Har) return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads need hiddenGar == hiddenEncoder");
+  if (g->W > 128) return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads: W=%d > 128", g->W);
+  g->dff = dff;
+  g->nheads = nheads;
+  return 0;
+}
+size_t cpcb200_criterion_t_save_bytes(const cpcb200_dims* d, int dff, int nheads) {
+  Geo g;
+  if (thead_geo(d, dff, nheads, &g)) return 0;
+  return criterion_save_bytes(g);
+}
+size_t cpcb200_criterion_t_ws_bytes(const cpcb200_dims* d, int dff, int nheads, int backward) {
+  Geo g;
+  if (thead_geo(d, dff, nheads, &g)) return 0;
+  return criterion_ws_bytes(g, backward);
+}
+int cpcb200_criterion_t_fwd(const cpcb200_dims* d, const float* c, const float* z, const cpcb200_thead_params* p,
+                            const int32_t* ext, float* losses, float* acc, void* save, void* ws, size_t ws_bytes, void* stream) {
+  NOT_NULL(p);
+  Geo g;
+  CPC_TRY(thead_geo(d, p->dff, p->nheads, &g));
+  NOT_NULL(c); NOT_NULL(z); NOT_NULL(ext); NOT_NULL(losses); NOT_NULL(acc); NOT_NULL(save); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
+  return criterion_fwd(g, c, z, nullptr, p, ext, losses, acc, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int cpcb200_criterion_t_bwd(const cpcb200_dims* d, const float* c, const float* z, const cpcb200_thead_params* p,
+                            const int32_t* ext, const float* dlosses, const void* save, float* dc, float* dz,
+                            const cpcb200_thead_params* grads, void* ws, size_t ws_bytes, void* stream) {
+  NOT_NULL(p); NOT_NULL(grads);
+  Geo g;
+  CPC_TRY(thead_geo(d, p->dff, p->nheads, &g));
+  NOT_NULL(c); NOT_NULL(z); NOT_NULL(ext); NOT_NULL(dlosses); NOT_NULL(save); NOT_NULL(dc); NOT_NULL(dz); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
+  return criterion_bwd(g, c, z, nullptr, p, ext, dlosses, save, dc, dz, nullptr, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,

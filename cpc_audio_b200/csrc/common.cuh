@@ -53,6 +53,7 @@ constexpr int kPad = 2;  // zero rows stored before and after every window of a 
 
 struct Geo {
   int B, L, H, Har, K, N, nL, S, W;
+  int dff = 0, nheads = 0;  // > 0: transformer prediction heads (rnnMode='transformer')
   int Lout[5];  // output length of conv i
   bool bf16;
 };
@@ -178,6 +179,7 @@ struct OutView {
   // (t == rpb-1 && r >= res_p).  res_w == 0: plain output.
   int res_w = 0;
   int res_p = 0;
+  int relu = 0;  // apply max(., 0) after the bias (FFN of the transformer prediction heads)
 };
 __host__ __device__ inline bool out_row_ok(const OutView& C, int t, int n0) {
   if (t >= C.rpb || t < C.t_lo || t >= C.t_hi) return false;

@@ -25,6 +25,12 @@ int score_bwd_mma(const bf16* pred, const bf16* z, const int* ext_t, const float
 int launch_cast3_bf16(const float* s0, bf16* d0, long long n0, const float* s1, bf16* d1, long long n1, const float* s2, bf16* d2,
                       long long n2, cudaStream_t st);
 
+size_t thead_save_bytes(const Geo& g);
+size_t thead_ws_bytes(const Geo& g, int backward);
+template <class T> int thead_fwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, T* pred, void* save, Carver& ws, cudaStream_t st);
+template <class T> int thead_bwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, const T* dpred, const void* save, float* dc,
+                                 const cpcb200_thead_params* gr, Carver& ws, cudaStream_t st);
+
 namespace {
 
 constexpr int KMAX = 16;
@@ -200,7 +206,7 @@ __global__ void score_bwd_kernel(const T* __restrict__ pred, const T* __restrict
   }
 }
 
-struct CritLayout { size_t pred, logits, lse, ext_t, cT, zT, total; bool mma; };
+struct CritLayout { size_t pred, logits, lse, ext_t, cT, zT, thead, total; bool mma; };
 CritLayout crit_layout(const Geo& g) {
   CritLayout l{};
   const size_t es = g.bf16 ? 2 : 4;
@@ -220,12 +226,16 @@ CritLayout crit_layout(const Geo& g) {
     l.zT = l.cT + align_up((size_t)g.B * g.S * g.Har * 2);
     l.total = l.zT + align_up((size_t)g.B * g.S * g.H * 2);
   }
+  if (g.dff > 0) {  // transformer prediction heads keep their activations here
+    l.thead = l.total;
+    l.total = l.thead + align_up(thead_save_bytes(g));
+  }
   return l;
 }
 
 template <class T>
-int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w_pred, const int* ext, float* losses,
-                    float* acc, void* save, void* wsp, size_t ws_bytes, cudaStream_t st) {
+int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w_pred, const cpcb200_thead_params* tp,
+                    const int* ext, float* losses, float* acc, void* save, void* wsp, size_t ws_bytes, cudaStream_t st) {
   const int B = g.B, S = g.S, W = g.W, H = g.H, Har = g.Har, K = g.K, N = g.N;
   const int P = B * W;
   constexpr bool isf = sizeof(T) == 4;
@@ -236,7 +246,7 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
   Carver ws(wsp, ws_bytes);
   T* cT = isf ? nullptr : reinterpret_cast<T*>(sv + lay.cT);
   T* zT = isf ? nullptr : reinterpret_cast<T*>(sv + lay.zT);
-  T* wT = ws.take<T>(isf ? 1 : (size_t)K * H * Har);
+  T* wT = ws.take<T>((isf || tp) ? 1 : (size_t)K * H * Har);
   float* lossbuf = ws.take<float>((size_t)P * K);
   float* corrbuf = ws.take<float>((size_t)P * K);
   if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "criterion_fwd: workspace %zu < %zu", ws_bytes, ws.off);
@@ -244,13 +254,17 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
   if (isf) { cp = reinterpret_cast<const T*>(c); zp = reinterpret_cast<const T*>(z); wp = reinterpret_cast<const T*>(w_pred); }
   else {
     CPC_TRY(launch_cast3_bf16(c, reinterpret_cast<bf16*>(cT), (long long)B * S * Har, z, reinterpret_cast<bf16*>(zT),
-                              (long long)B * S * H, w_pred, reinterpret_cast<bf16*>(wT), (long long)K * H * Har, st));
+                              (long long)B * S * H, tp ? nullptr : w_pred, reinterpret_cast<bf16*>(wT),
+                              tp ? 0 : (long long)K * H * Har, st));
     cp = cT; zp = zT; wp = wT;
   }
-  // heads: pred[(b,w), (k,h)] = sum_a c[b,w,a] * Wk[h,a]
-  RowView A{cp, (long long)S * Har, (long long)Har, W};
-  OutView C{pred, (long long)W * K * H, (long long)K * H, W, 0, W, 0};
-  CPC_TRY(gemm_nt(g.bf16, false, B, K * H, Har, A, wp, nullptr, C, st));
+  if (tp) {  // transformer heads (rnnMode='transformer')
+    CPC_TRY(thead_fwd<T>(g, cp, tp, pred, sv + lay.thead, ws, st));
+  } else {   // linear heads: pred[(b,w), (k,h)] = sum_a c[b,w,a] * Wk[h,a]
+    RowView A{cp, (long long)S * Har, (long long)Har, W};
+    OutView C{pred, (long long)W * K * H, (long long)K * H, W, 0, W, 0};
+    CPC_TRY(gemm_nt(g.bf16, false, B, K * H, Har, A, wp, nullptr, C, st));
+  }
   // scoring + CE
   if constexpr (!isf) {
     if (lay.mma) {
@@ -276,8 +290,9 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
 }
 
 template <class T>
-int criterion_bwd_t(const Geo& g, const float* c, const float* z, const float* w_pred, const int* ext, const float* dlosses,
-                    const void* save, float* dc, float* dz, float* dw_pred, void* wsp, size_t ws_bytes, cudaStream_t st) {
+int criterion_bwd_t(const Geo& g, const float* c, const float* z, const float* w_pred, const cpcb200_thead_params* tp,
+                    const int* ext, const float* dlosses, const void* save, float* dc, float* dz, float* dw_pred,
+                    const cpcb200_thead_params* tg, void* wsp, size_t ws_bytes, cudaStream_t st) {
   const int B = g.B, S = g.S, W = g.W, H = g.H, Har = g.Har, K = g.K, N = g.N;
   const int P = B * W;
   constexpr bool isf = sizeof(T) == 4;
@@ -288,7 +303,7 @@ int criterion_bwd_t(const Geo& g, const float* c, const float* z, const float* w
   Carver ws(wsp, ws_bytes);
   const T* cT = isf ? nullptr : reinterpret_cast<const T*>(sv + lay.cT);
   const T* zT = isf ? nullptr : reinterpret_cast<const T*>(sv + lay.zT);
-  T* wTt = ws.take<T>((size_t)K * H * Har);  // transposed heads: [Har][K*H]
+  T* wTt = ws.take<T>(tp ? 1 : (size_t)K * H * Har);  // transposed heads: [Har][K*H]
   T* dpred = ws.take<T>((size_t)P * K * H);
   if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "criterion_bwd: workspace %zu < %zu", ws_bytes, ws.off);
   const T *cp, *zp;
@@ -296,10 +311,10 @@ int criterion_bwd_t(const Geo& g, const float* c, const float* z, const float* w
   else {
     cp = cT; zp = zT;
   }
-  CPC_TRY(launch_transpose_cast<T>(w_pred, wTt, K * H, Har, st));
+  if (!tp) CPC_TRY(launch_transpose_cast<T>(w_pred, wTt, K * H, Har, st));
   CPC_CHECK_CUDA(cudaMemsetAsync(dz, 0, (size_t)B * S * H * sizeof(float), st));
   CPC_CHECK_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * S * Har * sizeof(float), st));
-  CPC_CHECK_CUDA(cudaMemsetAsync(dw_pred, 0, (size_t)K * H * Har * sizeof(float), st));
+  if (!tp) CPC_CHECK_CUDA(cudaMemsetAsync(dw_pred, 0, (size_t)K * H * Har * sizeof(float), st));
   bool done = false;
   if constexpr (!isf) {
     if (lay.mma) {
@@ -316,6 +331,7 @@ int criterion_bwd_t(const Geo& g, const float* c, const float* z, const float* w
     score_bwd_kernel<T><<<P, threads, smem, st>>>(pred, zp, ext, logits, dlosses, dpred, dz, B, S, W, H, K, N);
     CPC_LAUNCHED_N("score_bwd", st);
   }
+  if (tp) return thead_bwd<T>(g, cp, tp, dpred, sv + lay.thead, dc, tg, ws, st);
   {  // dW[(k,h)][a] = sum_p dpred[p][(k,h)] * c[p][a]
     RowView A{dpred, (long long)W * K * H, (long long)K * H, W};
     RowView Bv{cp, (long long)S * Har, (long long)Har, W};
@@ -353,20 +369,22 @@ size_t criterion_ws_bytes(const Geo& g, int backward) {
     tot += align_up((size_t)g.K * g.H * g.Har * es);
     tot += align_up(P * g.K * g.H * es);
   }
+  if (g.dff > 0) tot += thead_ws_bytes(g, backward);
   return tot + 256;
 }
 
-int criterion_fwd(const Geo& g, const float* c, const float* z, const float* w_pred, const int* ext, float* losses,
-                  float* acc, void* save, void* ws, size_t ws_bytes, cudaStream_t st) {
+int criterion_fwd(const Geo& g, const float* c, const float* z, const float* w_pred, const cpcb200_thead_params* tp,
+                  const int* ext, float* losses, float* acc, void* save, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (g.K > KMAX) return fail(CPCB200_ERR_UNSUPPORTED, "criterion: K=%d > %d", g.K, KMAX);
-  if (g.bf16) return criterion_fwd_t<bf16>(g, c, z, w_pred, ext, losses, acc, save, ws, ws_bytes, st);
-  return criterion_fwd_t<float>(g, c, z, w_pred, ext, losses, acc, save, ws, ws_bytes, st);
+  if (g.bf16) return criterion_fwd_t<bf16>(g, c, z, w_pred, tp, ext, losses, acc, save, ws, ws_bytes, st);
+  return criterion_fwd_t<float>(g, c, z, w_pred, tp, ext, losses, acc, save, ws, ws_bytes, st);
 }
-int criterion_bwd(const Geo& g, const float* c, const float* z, const float* w_pred, const int* ext, const float* dlosses,
-                  const void* save, float* dc, float* dz, float* dw_pred, void* ws, size_t ws_bytes, cudaStream_t st) {
+int criterion_bwd(const Geo& g, const float* c, const float* z, const float* w_pred, const cpcb200_thead_params* tp,
+                  const int* ext, const float* dlosses, const void* save, float* dc, float* dz, float* dw_pred,
+                  const cpcb200_thead_params* tg, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (g.K > KMAX) return fail(CPCB200_ERR_UNSUPPORTED, "criterion: K=%d > %d", g.K, KMAX);
-  if (g.bf16) return criterion_bwd_t<bf16>(g, c, z, w_pred, ext, dlosses, save, dc, dz, dw_pred, ws, ws_bytes, st);
-  return criterion_bwd_t<float>(g, c, z, w_pred, ext, dlosses, save, dc, dz, dw_pred, ws, ws_bytes, st);
+  if (g.bf16) return criterion_bwd_t<bf16>(g, c, z, w_pred, tp, ext, dlosses, save, dc, dz, dw_pred, tg, ws, ws_bytes, st);
+  return criterion_bwd_t<float>(g, c, z, w_pred, tp, ext, dlosses, save, dc, dz, dw_pred, tg, ws, ws_bytes, st);
 }
 
 }  // namespace cpcb200

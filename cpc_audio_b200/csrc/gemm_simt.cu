@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(NT) gemm_nt_kernel(int M, int N, int Kd, RowVi
     int b = m / C.rpb, t = m - b * C.rpb;
     if (!out_row_ok(C, t, n)) continue;
     float o[4] = {acc[i][0] + bb[0], acc[i][1] + bb[1], acc[i][2] + bb[2], acc[i][3] + bb[3]};
+    if (C.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
     store_vec<4>(Cp + (long long)b * C.bs + (long long)t * C.rs + n, o);
   }
 }

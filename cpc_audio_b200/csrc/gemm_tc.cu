@@ -177,6 +177,10 @@ __global__ void __launch_bounds__(NT_THREADS) gemm_nt_tc_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] += __ldg(bias + n0 + c0 + j);
         }
+        if (C.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
+        }
         store_out(crow + c0, v);
       }
     }
@@ -418,6 +422,10 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
           if (bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] += __ldg(bias + n0 + c0 + j);
+          }
+          if (C.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
           }
           store_out(crow + c0, v);
         }

@@ -1,0 +1,591 @@
+// thead.cu - the K one-layer transformer prediction heads of rnnMode='transformer'
+// (reference: cpc/criterion/criterion.py:82-88 -> cpc/transformers.py:10-139, nLayers = 1, abspos = False).
+//
+// Per head k (input x = c[:, :W], D = dmodel = H = Har, nh heads of dk = D/nh, F = dff):
+//   q,k,v = x Wq^T, x Wk^T, x Wv^T                                   transformers.py:60-65,76-80   (GEMMs)
+//   scores[i][c] = (q_i.k_c + q_i.Krelpos[:, W-1-(i-c)]) / sqrt(dk), c <= i   38-48 (relative-position "skew")
+//   a = softmax(scores) ; att = a v                                  48-49 (dropout: eval mode only)   attn kernels
+//   y1 = LN(x + att Wo^T)                                            81-83, 109                       GEMM + add_ln
+//   out = LN(y1 + relu(y1 W1^T + b1) W2^T + b2)                      86-95, 110-111                   GEMMs + add_ln
+// Everything dense goes through gemm_nt / gemm_tn (tcgen05 on the bf16 path); attention, LayerNorm and the ReLU
+// mask are CUDA-core kernels (fp32 math, T storage).  Backward recomputes the attention probabilities.
+#include "common.cuh"
+
+namespace cpcb200 {
+
+int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias,
+            const OutView& C, cudaStream_t st);
+int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode,
+            int Ci, int taps, cudaStream_t st);
+template <class T> int launch_cast(const float* src, T* dst, long long n, cudaStream_t st);
+template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st);
+template <class T> int launch_colsum(const T* src, float* out, long long M, int N, cudaStream_t st);
+
+namespace {
+
+constexpr float kLnEps = 1e-5f;
+
+// ---------------------------------------------------------------------------------------------------------
+// attention forward: one CTA per (head, window), thread i = query row i.
+// qkv: (P, 3D) rows = (b, w); att: (P, D).
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int DK>
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ krel,
+                                                        T* __restrict__ att, int W, int D) {
+  extern __shared__ __align__(16) float sm[];
+  float* Ks = sm;                      // [W][DK+1]
+  float* Vs = Ks + W * (DK + 1);       // [W][DK+1]
+  float* Rs = Vs + W * (DK + 1);       // [DK][W]  Krelpos
+  float* Ps = Rs + DK * W;             // [W][W+1]
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const T* base = qkv + (size_t)b * W * 3 * D + h * DK;
+  for (int i = tid; i < W * DK; i += blockDim.x) {
+    const int r = i / DK, d = i - r * DK;
+    Ks[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + D + d]);
+    Vs[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + 2 * D + d]);
+  }
+  for (int i = tid; i < DK * W; i += blockDim.x) Rs[i] = krel[i];
+  __syncthreads();
+  const int i = tid;
+  if (i >= W) return;
+  float q[DK];
+#pragma unroll
+  for (int d = 0; d < DK; d++) q[d] = to_f(base[(size_t)i * 3 * D + d]);
+  const float scale = rsqrtf((float)DK);
+  float* prow = Ps + (size_t)i * (W + 1);
+  float mx = -INFINITY;
+  for (int c = 0; c <= i; c++) {
+    const int m = W - 1 - i + c;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DK; d++) s = fmaf(q[d], Ks[c * (DK + 1) + d] + Rs[d * W + m], s);
+    s *= scale;
+    prow[c] = s;
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.f;
+  for (int c = 0; c <= i; c++) { const float e = __expf(prow[c] - mx); prow[c] = e; sum += e; }
+  const float inv = 1.f / sum;
+  float o[DK];
+#pragma unroll
+  for (int d = 0; d < DK; d++) o[d] = 0.f;
+  for (int c = 0; c <= i; c++) {
+    const float p = prow[c] * inv;
+#pragma unroll
+    for (int d = 0; d < DK; d++) o[d] = fmaf(p, Vs[c * (DK + 1) + d], o[d]);
+  }
+  T* orow = att + ((size_t)b * W + i) * D + h * DK;
+#pragma unroll
+  for (int d = 0; d < DK; d++) orow[d] = from_f<T>(o[d]);
+}
+
+// attention backward: recompute P, then dq (thread = query), dk/dv (thread = key), dKrelpos (thread = column m)
+template <class T, int DK>
+__global__ void __launch_bounds__(128) attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ datt,
+                                                        const float* __restrict__ krel, T* __restrict__ dqkv,
+                                                        float* __restrict__ dkrel, int W, int D) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                      // [W][DK+1]
+  float* Ks = Qs + W * (DK + 1);
+  float* Vs = Ks + W * (DK + 1);
+  float* Gs = Vs + W * (DK + 1);       // dO
+  float* Rs = Gs + W * (DK + 1);       // [DK][W]
+  float* Ps = Rs + DK * W;             // [W][W+1] probabilities
+  float* Ss = Ps + W * (W + 1);        // [W][W+1] d(scaled score)
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const T* base = qkv + (size_t)b * W * 3 * D + h * DK;
+  const T* gbase = datt + (size_t)b * W * D + h * DK;
+  for (int i = tid; i < W * DK; i += blockDim.x) {
+    const int r = i / DK, d = i - r * DK;
+    Qs[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + d]);
+    Ks[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + D + d]);
+    Vs[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + 2 * D + d]);
+    Gs[r * (DK + 1) + d] = to_f(gbase[(size_t)r * D + d]);
+  }
+  for (int i = tid; i < DK * W; i += blockDim.x) Rs[i] = krel[i];
+  for (int i = tid; i < W * (W + 1); i += blockDim.x) { Ps[i] = 0.f; Ss[i] = 0.f; }
+  __syncthreads();
+  const float scale = rsqrtf((float)DK);
+  T* dbase = dqkv + (size_t)b * W * 3 * D + h * DK;
+  if (tid < W) {
+    const int i = tid;
+    float* prow = Ps + (size_t)i * (W + 1);
+    float* srow = Ss + (size_t)i * (W + 1);
+    float mx = -INFINITY;
+    for (int c = 0; c <= i; c++) {
+      const int m = W - 1 - i + c;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < DK; d++) s = fmaf(Qs[i * (DK + 1) + d], Ks[c * (DK + 1) + d] + Rs[d * W + m], s);
+      s *= scale;
+      prow[c] = s;
+      mx = fmaxf(mx, s);
+    }
+    float sum = 0.f;
+    for (int c = 0; c <= i; c++) { const float e = __expf(prow[c] - mx); prow[c] = e; sum += e; }
+    const float inv = 1.f / sum;
+    float dsum = 0.f;
+    for (int c = 0; c <= i; c++) {
+      const float p = prow[c] * inv;
+      prow[c] = p;
+      float dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < DK; d++) dp = fmaf(Gs[i * (DK + 1) + d], Vs[c * (DK + 1) + d], dp);
+      srow[c] = dp;
+      dsum = fmaf(dp, p, dsum);
+    }
+    float dq[DK];
+#pragma unroll
+    for (int d = 0; d < DK; d++) dq[d] = 0.f;
+    for (int c = 0; c <= i; c++) {
+      const int m = W - 1 - i + c;
+      const float ds = prow[c] * (srow[c] - dsum) * scale;
+      srow[c] = ds;
+#pragma unroll
+      for (int d = 0; d < DK; d++) dq[d] = fmaf(ds, Ks[c * (DK + 1) + d] + Rs[d * W + m], dq[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < DK; d++) dbase[(size_t)i * 3 * D + d] = from_f<T>(dq[d]);
+  }
+  __syncthreads();
+  if (tid < W) {
+    const int c = tid;  // key index
+    float dk[DK], dv[DK];
+#pragma unroll
+    for (int d = 0; d < DK; d++) { dk[d] = 0.f; dv[d] = 0.f; }
+    for (int i = c; i < W; i++) {
+      const float ds = Ss[(size_t)i * (W + 1) + c], p = Ps[(size_t)i * (W + 1) + c];
+#pragma unroll
+      for (int d = 0; d < DK; d++) {
+        dk[d] = fmaf(ds, Qs[i * (DK + 1) + d], dk[d]);
+        dv[d] = fmaf(p, Gs[i * (DK + 1) + d], dv[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < DK; d++) {
+      dbase[(size_t)c * 3 * D + D + d] = from_f<T>(dk[d]);
+      dbase[(size_t)c * 3 * D + 2 * D + d] = from_f<T>(dv[d]);
+    }
+    // dKrelpos[d][m] += sum_{i >= W-1-m} dS[i][i-(W-1-m)] * q_i[d]
+    const int m = tid;
+    float dr[DK];
+#pragma unroll
+    for (int d = 0; d < DK; d++) dr[d] = 0.f;
+    for (int i = W - 1 - m; i < W; i++) {
+      const float ds = Ss[(size_t)i * (W + 1) + (i - (W - 1 - m))];
+#pragma unroll
+      for (int d = 0; d < DK; d++) dr[d] = fmaf(ds, Qs[i * (DK + 1) + d], dr[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < DK; d++) atomicAdd(dkrel + d * W + m, dr[d]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// row kernels over D channels: one warp per row, lane owns float4 chunks at channel 4*(lane + 32*i)
+// ---------------------------------------------------------------------------------------------------------
+template <int I, class T>
+__device__ __forceinline__ void rload(const T* row, int D, int lane, float (&v)[I][4]) {
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    const int c = 4 * (lane + 32 * i);
+    if (c < D) load_vec<4>(row + c, v[i]);
+    else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+  }
+}
+template <int I, class T>
+__device__ __forceinline__ void rstore(T* row, int D, int lane, const float (&v)[I][4]) {
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    const int c = 4 * (lane + 32 * i);
+    if (c < D) store_vec<4>(row + c, v[i]);
+  }
+}
+// biased-variance LayerNorm statistics (torch.nn.LayerNorm, eps 1e-5)
+template <int I>
+__device__ __forceinline__ void ln_stats(const float (&u)[I][4], int D, int lane, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < I; i++)
+    if (4 * (lane + 32 * i) < D) s += (u[i][0] + u[i][1]) + (u[i][2] + u[i][3]);
+  mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < I; i++)
+    if (4 * (lane + 32 * i) < D) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const float dl = u[i][j] - mean; q = fmaf(dl, dl, q); }
+    }
+  rstd = rsqrtf(warp_sum(q) / (float)D + kLnEps);
+}
+
+// s = a + b ; y = LN(s).  a: rows (p / rpb, p % rpb) with strides (a_bs, a_rs); b, s dense (P, D); y rows stride y_rs.
+template <int I, class TA, class T>
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const TA* __restrict__ a, long long a_bs, long long a_rs, int rpb,
+                                                          const T* __restrict__ b, const float* __restrict__ gam,
+                                                          const float* __restrict__ bet, T* __restrict__ s_out,
+                                                          T* __restrict__ y, long long y_rs, int P, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (p >= P) return;
+  const int bi = (int)(p / rpb), ti = (int)(p - (long long)bi * rpb);
+  float va[I][4], vb[I][4];
+  rload<I>(a + (long long)bi * a_bs + (long long)ti * a_rs, D, lane, va);
+  rload<I>(b + p * D, D, lane, vb);
+#pragma unroll
+  for (int i = 0; i < I; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) va[i][j] += vb[i][j];
+  rstore<I>(s_out + p * D, D, lane, va);
+  // statistics on the value that was stored (bf16-rounded on the bf16 path) so that backward sees the same xhat
+  rload<I>(s_out + p * D, D, lane, va);
+  float mean, rstd;
+  ln_stats<I>(va, D, lane, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    const int c = 4 * (lane + 32 * i);
+    if (c < D) {
+      const float4 g4 = *reinterpret_cast<const float4*>(gam + c), b4 = *reinterpret_cast<const float4*>(bet + c);
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) va[i][j] = fmaf((va[i][j] - mean) * rstd, g[j], be[j]);
+    }
+  }
+  rstore<I>(y + p * y_rs, D, lane, va);
+}
+
+// LayerNorm backward: dy = dya (+ dyb); ds = rstd (dxh - mean(dxh) - xh mean(dxh xh)); dgamma += dy xh; dbeta += dy
+template <int I, class T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dya, long long dya_rs, const T* __restrict__ dyb,
+                                                      const T* __restrict__ s, const float* __restrict__ gam,
+                                                      T* __restrict__ ds, float* __restrict__ dgam, float* __restrict__ dbet,
+                                                      int P, int D) {
+  extern __shared__ __align__(16) float accs[];  // [2][D]
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) accs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  float ag[I][4], ab[I][4];
+#pragma unroll
+  for (int i = 0; i < I; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) ag[i][j] = ab[i][j] = 0.f;
+  for (long long p = w0; p < P; p += nw) {
+    float v[I][4], d[I][4];
+    rload<I>(s + p * D, D, lane, v);
+    rload<I>(dya + p * dya_rs, D, lane, d);
+    if (dyb != nullptr) {
+      float e[I][4];
+      rload<I>(dyb + p * D, D, lane, e);
+#pragma unroll
+      for (int i = 0; i < I; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) d[i][j] += e[i][j];
+    }
+    float mean, rstd;
+    ln_stats<I>(v, D, lane, mean, rstd);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      const int c = 4 * (lane + 32 * i);
+      if (c < D) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gam + c);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float xh = (v[i][j] - mean) * rstd;
+          ag[i][j] = fmaf(d[i][j], xh, ag[i][j]);
+          ab[i][j] += d[i][j];
+          const float dx = d[i][j] * g[j];
+          v[i][j] = xh; d[i][j] = dx;
+          s1 += dx; s2 = fmaf(dx, xh, s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int i = 0; i < I; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) d[i][j] = rstd * (d[i][j] - s1 - v[i][j] * s2);
+    rstore<I>(ds + p * D, D, lane, d);
+  }
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    const int c = 4 * (lane + 32 * i);
+    if (c < D) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) { atomicAdd(&accs[c + j], ag[i][j]); atomicAdd(&accs[D + c + j], ab[i][j]); }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) { atomicAdd(dgam + i, accs[i]); atomicAdd(dbet + i, accs[D + i]); }
+}
+
+template <class T>
+__global__ void relu_mask_kernel(T* __restrict__ dh, const T* __restrict__ h, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!(to_f(h[i]) > 0.f)) dh[i] = from_f<T>(0.f);
+}
+// acc (fp32, P x D) += a + b
+template <class T>
+__global__ void acc_add_kernel(float* __restrict__ acc, const T* __restrict__ a, const T* __restrict__ b, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc[i] += to_f(a[i]) + to_f(b[i]);
+}
+// dc[b, w < W, :] = acc[(b, w), :]
+__global__ void scatter_rows_kernel(const float* __restrict__ acc, float* __restrict__ dc, int B, int S, int W, int D) {
+  const long long n = (long long)B * W * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D); const long long pw = i / D; const int w = (int)(pw % W), b = (int)(pw / W);
+    dc[((long long)b * S + w) * D + d] = acc[i];
+  }
+}
+// dst[d][j*D + r] = w_j[r][d]  for j in {q, k, v}: the (D, 3D) transposed concatenation used by d(x) = dqkv . [Wq;Wk;Wv]
+template <class T>
+__global__ void concat_transpose3_kernel(const float* __restrict__ wq, const float* __restrict__ wk, const float* __restrict__ wv,
+                                         T* __restrict__ dst, int D) {
+  const long long n = (long long)3 * D * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % (3 * D)), d = (int)(i / (3 * D));
+    const int j = col / D, r = col - j * D;
+    const float* w = j == 0 ? wq : (j == 1 ? wk : wv);
+    dst[i] = from_f<T>(w[(size_t)r * D + d]);
+  }
+}
+
+inline int grid_for(long long n) { long long b = (n + 255) / 256; return (int)(b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b)); }
+
+template <class T> size_t attn_fwd_smem(int W, int DK) { return (size_t)(2 * W * (DK + 1) + DK * W + W * (W + 1)) * 4; }
+template <class T> size_t attn_bwd_smem(int W, int DK) { return (size_t)(4 * W * (DK + 1) + DK * W + 2 * W * (W + 1)) * 4; }
+
+template <class T>
+int launch_attn_fwd(const T* qkv, const float* krel, T* att, int B, int W, int D, int nh, cudaStream_t st) {
+  const int DK = D / nh;
+  const size_t smem = attn_fwd_smem<T>(W, DK);
+  dim3 grid(nh, B);
+#define AF(DKV)                                                                                                   \
+  {                                                                                                               \
+    CPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<T, DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    attn_fwd_kernel<T, DKV><<<grid, 128, smem, st>>>(qkv, krel, att, W, D);                                        \
+  }
+  if (DK == 32) AF(32) else if (DK == 8) AF(8) else if (DK == 16) AF(16) else if (DK == 64) AF(64)
+  else return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads: dk=%d", DK);
+#undef AF
+  CPC_LAUNCHED_N("attn_fwd", st);
+  return 0;
+}
+template <class T>
+int launch_attn_bwd(const T* qkv, const T* datt, const float* krel, T* dqkv, float* dkrel, int B, int W, int D, int nh, cudaStream_t st) {
+  const int DK = D / nh;
+  const size_t smem = attn_bwd_smem<T>(W, DK);
+  dim3 grid(nh, B);
+#define AB(DKV)                                                                                                   \
+  {                                                                                                               \
+    CPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<T, DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    attn_bwd_kernel<T, DKV><<<grid, 128, smem, st>>>(qkv, datt, krel, dqkv, dkrel, W, D);                          \
+  }
+  if (DK == 32) AB(32) else if (DK == 8) AB(8) else if (DK == 16) AB(16) else if (DK == 64) AB(64)
+  else return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads: dk=%d", DK);
+#undef AB
+  CPC_LAUNCHED_N("attn_bwd", st);
+  return 0;
+}
+
+template <class TA, class T>
+int launch_add_ln(const TA* a, long long a_bs, long long a_rs, int rpb, const T* b, const float* gam, const float* bet, T* s_out,
+                  T* y, long long y_rs, int P, int D, cudaStream_t st) {
+  const int I = (D + 127) / 128;
+  const int blocks = (int)(((long long)P * 32 + 255) / 256);
+#define AL(II) add_ln_fwd_kernel<II, TA, T><<<blocks, 256, 0, st>>>(a, a_bs, a_rs, rpb, b, gam, bet, s_out, y, y_rs, P, D)
+  if (I == 1) AL(1); else if (I == 2) AL(2); else if (I == 3) AL(3); else AL(4);
+#undef AL
+  CPC_LAUNCHED_N("add_ln_fwd", st);
+  return 0;
+}
+template <class T>
+int launch_ln_bwd(const T* dya, long long dya_rs, const T* dyb, const T* s, const float* gam, T* ds, float* dgam, float* dbet, int P,
+                  int D, cudaStream_t st) {
+  const int I = (D + 127) / 128;
+  int blocks = (int)(((long long)P * 32 + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  const size_t smem = 2 * (size_t)D * 4;
+#define LB(II) ln_bwd_kernel<II, T><<<blocks, 256, smem, st>>>(dya, dya_rs, dyb, s, gam, ds, dgam, dbet, P, D)
+  if (I == 1) LB(1); else if (I == 2) LB(2); else if (I == 3) LB(3); else LB(4);
+#undef LB
+  CPC_LAUNCHED_N("ln_bwd", st);
+  return 0;
+}
+
+struct THeadLayout { size_t qkv, att, s1, y1, h, s2, per_k; };  // element offsets (units of T) inside one head's block
+THeadLayout thead_layout(const Geo& g) {
+  THeadLayout l{};
+  const size_t P = (size_t)g.B * g.W, D = g.H, F = g.dff;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t r = off; off += (n + 127) / 128 * 128; return r; };
+  l.qkv = take(P * 3 * D); l.att = take(P * D); l.s1 = take(P * D); l.y1 = take(P * D); l.h = take(P * F); l.s2 = take(P * D);
+  l.per_k = off;
+  return l;
+}
+
+}  // namespace
+
+size_t thead_save_bytes(const Geo& g) { return thead_layout(g).per_k * g.K * (g.bf16 ? 2 : 4) + 256; }
+
+size_t thead_ws_bytes(const Geo& g, int backward) {
+  const size_t es = g.bf16 ? 2 : 4, P = (size_t)g.B * g.W, D = g.H, F = g.dff;
+  size_t t = 0;
+  if (!backward) {
+    t += 4 * align_up(D * D * es) + 2 * align_up(F * D * es);   // Wq, Wk, Wv, Wo, W1, W2 in T
+    t += 2 * align_up(P * D * es);                              // o, f
+  } else {
+    t += align_up(3 * D * D * es) + align_up(D * D * es) + 2 * align_up(F * D * es);   // transposed weights
+    t += 5 * align_up(P * D * es) + align_up(P * F * es) + align_up(P * 3 * D * es);   // ds2, dy1, ds1, datt, dx, dh, dqkv
+    t += align_up(P * D * 4);                                                          // dc accumulator
+  }
+  return t + 1024;
+}
+
+template <class T>
+int thead_fwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, T* pred, void* save, Carver& ws, cudaStream_t st) {
+  const int B = g.B, S = g.S, W = g.W, D = g.H, K = g.K, F = g.dff, nh = g.nheads;
+  const int P = B * W;
+  if (g.Har != g.H) return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads need hiddenGar == hiddenEncoder (criterion.py:85)");
+  if (W > 128 || D % nh != 0) return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads: W=%d (max 128), D=%d, heads=%d", W, D, nh);
+  constexpr bool isf = sizeof(T) == 4;
+  const THeadLayout lay = thead_layout(g);
+  T* sv = static_cast<T*>(save);
+  T* wq = ws.take<T>((size_t)D * D); T* wk = ws.take<T>((size_t)D * D); T* wv = ws.take<T>((size_t)D * D);
+  T* wo = ws.take<T>((size_t)D * D); T* w1 = ws.take<T>((size_t)F * D); T* w2 = ws.take<T>((size_t)F * D);
+  T* o = ws.take<T>((size_t)P * D); T* f = ws.take<T>((size_t)P * D);
+  if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "thead_fwd: workspace too small (%zu needed)", ws.off);
+  const RowView X{cp, (long long)S * D, (long long)D, W};
+  for (int k = 0; k < K; k++) {
+    T* blk = sv + (size_t)k * lay.per_k;
+    T *qkv = blk + lay.qkv, *att = blk + lay.att, *s1 = blk + lay.s1, *y1 = blk + lay.y1, *h = blk + lay.h, *s2 = blk + lay.s2;
+    const T *Wq, *Wk, *Wv, *Wo, *W1, *W2;
+    if (isf) {
+      Wq = reinterpret_cast<const T*>(tp->wq + (size_t)k * D * D); Wk = reinterpret_cast<const T*>(tp->wk + (size_t)k * D * D);
+      Wv = reinterpret_cast<const T*>(tp->wv + (size_t)k * D * D); Wo = reinterpret_cast<const T*>(tp->wo + (size_t)k * D * D);
+      W1 = reinterpret_cast<const T*>(tp->w1 + (size_t)k * F * D); W2 = reinterpret_cast<const T*>(tp->w2 + (size_t)k * D * F);
+    } else {
+      CPC_TRY(launch_cast<T>(tp->wq + (size_t)k * D * D, wq, (long long)D * D, st));
+      CPC_TRY(launch_cast<T>(tp->wk + (size_t)k * D * D, wk, (long long)D * D, st));
+      CPC_TRY(launch_cast<T>(tp->wv + (size_t)k * D * D, wv, (long long)D * D, st));
+      CPC_TRY(launch_cast<T>(tp->wo + (size_t)k * D * D, wo, (long long)D * D, st));
+      CPC_TRY(launch_cast<T>(tp->w1 + (size_t)k * F * D, w1, (long long)F * D, st));
+      CPC_TRY(launch_cast<T>(tp->w2 + (size_t)k * D * F, w2, (long long)D * F, st));
+      Wq = wq; Wk = wk; Wv = wv; Wo = wo; W1 = w1; W2 = w2;
+    }
+    const T* Wqkv[3] = {Wq, Wk, Wv};
+    for (int j = 0; j < 3; j++) {  // q | k | v column blocks of qkv
+      OutView C{qkv + (size_t)j * D, (long long)W * 3 * D, (long long)3 * D, W, 0, W, 0};
+      CPC_TRY(gemm_nt(g.bf16, false, B, D, D, X, Wqkv[j], nullptr, C, st));
+    }
+    CPC_TRY(launch_attn_fwd<T>(qkv, tp->krelpos + (size_t)k * (D / nh) * W, att, B, W, D, nh, st));
+    {
+      RowView A{att, 0, (long long)D, P};
+      OutView C{o, 0, (long long)D, P, 0, P, 0};
+      CPC_TRY(gemm_nt(g.bf16, false, 1, D, D, A, Wo, nullptr, C, st));
+    }
+    CPC_TRY((launch_add_ln<T, T>(cp, (long long)S * D, (long long)D, W, o, tp->ln1_w + (size_t)k * D, tp->ln1_b + (size_t)k * D, s1, y1,
+                                 (long long)D, P, D, st)));
+    {
+      RowView A{y1, 0, (long long)D, P};
+      OutView C{h, 0, (long long)F, P, 0, P, 0};
+      C.relu = 1;
+      CPC_TRY(gemm_nt(g.bf16, false, 1, F, D, A, W1, tp->b1 + (size_t)k * F, C, st));
+    }
+    {
+      RowView A{h, 0, (long long)F, P};
+      OutView C{f, 0, (long long)D, P, 0, P, 0};
+      CPC_TRY(gemm_nt(g.bf16, false, 1, D, F, A, W2, tp->b2 + (size_t)k * D, C, st));
+    }
+    CPC_TRY((launch_add_ln<T, T>(y1, (long long)P * D, (long long)D, P, f, tp->ln2_w + (size_t)k * D, tp->ln2_b + (size_t)k * D, s2,
+                                 pred + (size_t)k * D, (long long)K * D, P, D, st)));
+  }
+  return 0;
+}
+
+template <class T>
+int thead_bwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, const T* dpred, const void* save, float* dc,
+              const cpcb200_thead_params* gr, Carver& ws, cudaStream_t st) {
+  const int B = g.B, S = g.S, W = g.W, D = g.H, K = g.K, F = g.dff, nh = g.nheads;
+  const int P = B * W, DK = D / nh;
+  const THeadLayout lay = thead_layout(g);
+  const T* sv = static_cast<const T*>(save);
+  T* wqkvT = ws.take<T>((size_t)3 * D * D); T* woT = ws.take<T>((size_t)D * D);
+  T* w1T = ws.take<T>((size_t)F * D); T* w2T = ws.take<T>((size_t)F * D);
+  T* ds2 = ws.take<T>((size_t)P * D); T* dy1 = ws.take<T>((size_t)P * D); T* ds1 = ws.take<T>((size_t)P * D);
+  T* datt = ws.take<T>((size_t)P * D); T* dx = ws.take<T>((size_t)P * D);
+  T* dh = ws.take<T>((size_t)P * F); T* dqkv = ws.take<T>((size_t)P * 3 * D);
+  float* dcw = ws.take<float>((size_t)P * D);
+  if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "thead_bwd: workspace too small (%zu needed)", ws.off);
+  CPC_CHECK_CUDA(cudaMemsetAsync(dcw, 0, (size_t)P * D * 4, st));
+  const RowView X{cp, (long long)S * D, (long long)D, W};
+  for (int k = 0; k < K; k++) {
+    const T* blk = sv + (size_t)k * lay.per_k;
+    const T *qkv = blk + lay.qkv, *att = blk + lay.att, *s1 = blk + lay.s1, *y1 = blk + lay.y1, *h = blk + lay.h, *s2 = blk + lay.s2;
+    const size_t oDD = (size_t)k * D * D, oFD = (size_t)k * F * D;
+    concat_transpose3_kernel<T><<<grid_for((long long)3 * D * D), 256, 0, st>>>(tp->wq + oDD, tp->wk + oDD, tp->wv + oDD, wqkvT, D);
+    CPC_LAUNCHED_N("concat_transpose3", st);
+    CPC_TRY(launch_transpose_cast<T>(tp->wo + oDD, woT, D, D, st));       // woT[a][o] = Wo[o][a]
+    CPC_TRY(launch_transpose_cast<T>(tp->w1 + oFD, w1T, F, D, st));       // [D][F]
+    CPC_TRY(launch_transpose_cast<T>(tp->w2 + oFD, w2T, D, F, st));       // [F][D]
+    // LN2 backward
+    CPC_TRY(launch_ln_bwd<T>(dpred + (size_t)k * D, (long long)K * D, nullptr, s2, tp->ln2_w + (size_t)k * D, ds2,
+                             gr->ln2_w + (size_t)k * D, gr->ln2_b + (size_t)k * D, P, D, st));
+    // FFN backward
+    CPC_TRY(launch_colsum<T>(ds2, gr->b2 + (size_t)k * D, P, D, st));
+    {
+      RowView A{ds2, 0, (long long)D, P}, Bv{h, 0, (long long)F, P};
+      CPC_TRY(gemm_tn(g.bf16, 1, D, F, A, Bv, gr->w2 + oFD, F, STORE_PLAIN, 0, 0, st));       // dW2[d][f]
+      OutView C{dh, 0, (long long)F, P, 0, P, 0};
+      CPC_TRY(gemm_nt(g.bf16, false, 1, F, D, A, w2T, nullptr, C, st));                       // dh = ds2 . W2
+    }
+    relu_mask_kernel<T><<<grid_for((long long)P * F), 256, 0, st>>>(dh, h, (long long)P * F);
+    CPC_LAUNCHED_N("relu_mask", st);
+    CPC_TRY(launch_colsum<T>(dh, gr->b1 + (size_t)k * F, P, F, st));
+    {
+      RowView A{dh, 0, (long long)F, P}, Bv{y1, 0, (long long)D, P};
+      CPC_TRY(gemm_tn(g.bf16, 1, F, D, A, Bv, gr->w1 + oFD, D, STORE_PLAIN, 0, 0, st));       // dW1[f][d]
+      OutView C{dy1, 0, (long long)D, P, 0, P, 0};
+      CPC_TRY(gemm_nt(g.bf16, false, 1, D, F, A, w1T, nullptr, C, st));                       // dy1 (FFN branch)
+    }
+    // LN1 backward on dy1 + ds2 (residual)
+    CPC_TRY(launch_ln_bwd<T>(dy1, (long long)D, ds2, s1, tp->ln1_w + (size_t)k * D, ds1, gr->ln1_w + (size_t)k * D,
+                             gr->ln1_b + (size_t)k * D, P, D, st));
+    {  // Wo
+      RowView A{ds1, 0, (long long)D, P}, Bv{att, 0, (long long)D, P};
+      CPC_TRY(gemm_tn(g.bf16, 1, D, D, A, Bv, gr->wo + oDD, D, STORE_PLAIN, 0, 0, st));
+      OutView C{datt, 0, (long long)D, P, 0, P, 0};
+      CPC_TRY(gemm_nt(g.bf16, false, 1, D, D, A, woT, nullptr, C, st));
+    }
+    CPC_TRY(launch_attn_bwd<T>(qkv, datt, tp->krelpos + (size_t)k * DK * W, dqkv, gr->krelpos + (size_t)k * DK * W, B, W, D, nh, st));
+    {  // Wq, Wk, Wv and d(x)
+      float* dw3[3] = {gr->wq + oDD, gr->wk + oDD, gr->wv + oDD};
+      for (int j = 0; j < 3; j++) {
+        RowView A{dqkv + (size_t)j * D, (long long)W * 3 * D, (long long)3 * D, W};
+        CPC_TRY(gemm_tn(g.bf16, B, D, D, A, X, dw3[j], D, STORE_PLAIN, 0, 0, st));
+      }
+      RowView A{dqkv, 0, (long long)3 * D, P};
+      OutView C{dx, 0, (long long)D, P, 0, P, 0};
+      CPC_TRY(gemm_nt(g.bf16, false, 1, D, 3 * D, A, wqkvT, nullptr, C, st));
+    }
+    acc_add_kernel<T><<<grid_for((long long)P * D), 256, 0, st>>>(dcw, dx, ds1, (long long)P * D);
+    CPC_LAUNCHED_N("acc_add", st);
+  }
+  scatter_rows_kernel<<<grid_for((long long)P * D), 256, 0, st>>>(dcw, dc, B, S, W, D);
+  CPC_LAUNCHED_N("scatter_rows", st);
+  return 0;
+}
+
+template int thead_fwd<float>(const Geo&, const float*, const cpcb200_thead_params*, float*, void*, Carver&, cudaStream_t);
+template int thead_fwd<bf16>(const Geo&, const bf16*, const cpcb200_thead_params*, bf16*, void*, Carver&, cudaStream_t);
+template int thead_bwd<float>(const Geo&, const float*, const cpcb200_thead_params*, const float*, const void*, float*,
+                              const cpcb200_thead_params*, Carver&, cudaStream_t);
+template int thead_bwd<bf16>(const Geo&, const bf16*, const cpcb200_thead_params*, const bf16*, const void*, float*,
+                             const cpcb200_thead_params*, Carver&, cudaStream_t);
+
+}  // namespace cpcb200

@@ -128,6 +128,26 @@ int cpcb200_criterion_bwd(const cpcb200_dims* d, const float* c, const float* z,
                           const int32_t* ext, const float* dlosses, const void* save, float* dc, float* dz,
                           float* dw_pred, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- rnnMode='transformer' prediction heads (criterion.py:82-88 -> cpc/transformers.py:98-139): K one-layer
+ * post-LN transformers with relative-position attention, eval-mode semantics (dropout = identity).  Every array is
+ * the per-head parameter stacked over K: wq/wk/wv/wo (K,H,H) = multihead.W{q,k,v,o}.weight, krelpos (K, H/nheads, W)
+ * = multihead.Att.Krelpos, ln1_* (K,H) = ln_multihead, w1 (K,dff,H) b1 (K,dff) = ffnetwork.lin1, w2 (K,H,dff) b2 (K,H)
+ * = ffnetwork.lin2, ln2_* (K,H) = ln_ffnetwork.  Requires Har == H and W <= 128.  The same struct carries the
+ * gradients in _bwd (ACCUMULATED, caller zero-fills). */
+typedef struct {
+  float *wq, *wk, *wv, *wo, *krelpos, *ln1_w, *ln1_b, *w1, *b1, *w2, *b2, *ln2_w, *ln2_b;
+  int32_t dff;     /* 2048 in the reference (transformers.py:98) */
+  int32_t nheads;  /* 8 */
+} cpcb200_thead_params;
+size_t cpcb200_criterion_t_save_bytes(const cpcb200_dims* d, int dff, int nheads);
+size_t cpcb200_criterion_t_ws_bytes(const cpcb200_dims* d, int dff, int nheads, int backward);
+int cpcb200_criterion_t_fwd(const cpcb200_dims* d, const float* c, const float* z, const cpcb200_thead_params* p,
+                            const int32_t* ext, float* losses, float* acc, void* save, void* ws, size_t ws_bytes,
+                            void* stream);
+int cpcb200_criterion_t_bwd(const cpcb200_dims* d, const float* c, const float* z, const cpcb200_thead_params* p,
+                            const int32_t* ext, const float* dlosses, const void* save, float* dc, float* dz,
+                            const cpcb200_thead_params* grads, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- fused Adam over a flat fp32 bucket (cpc/train.py:335-337,90-91; torch.optim.Adam semantics) -------- */
 int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);

@@ -63,6 +63,8 @@ def run_modules(model, crit, x, label, bi, si):
     """fwd + bwd through the B200 modules with the negative draws forced to (bi, si)."""
     dev = next(model.parameters()).device
     crit.sampleIndices = lambda B, W, S, device: (bi.to(device), si.to(device))
+    if getattr(crit.wPrediction, "transformer", False):
+        crit.eval()  # the heads' dropout makes train() mode non-deterministic; parity is defined in eval mode
     model.zero_grad(set_to_none=True)
     crit.zero_grad(set_to_none=True)
     c, z, _ = model(x.to(dev), label.to(dev))

@@ -80,7 +80,9 @@ def test_unsupported_modes_raise_instead_of_falling_back():
     with pytest.raises(ValueError):
         M.CPCEncoder(256, "nope")
     with pytest.raises(NotImplementedError):
-        M.CPCUnsupersivedCriterion(12, 256, 256, 128, rnnMode="transformer")
+        M.CPCUnsupersivedCriterion(12, 256, 256, 128, rnnMode="conv4")
+    with pytest.raises(NotImplementedError):
+        M.CPCUnsupersivedCriterion(12, 128, 256, 128, rnnMode="transformer")  # needs hiddenGar == hiddenEncoder
     with pytest.raises(NotImplementedError):
         M.CPCUnsupersivedCriterion(12, 256, 256, 128, rnnMode="linear", speakerEmbedding=8, nSpeakers=4)
     model = M.CPCModel(M.CPCEncoder(64), M.CPCAR(64, 64, False, 1))
@@ -133,3 +135,17 @@ def test_patch_install_swaps_reference_symbols(tmp_path, monkeypatch):
     c = crit.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode="linear", dropout=False, nSpeakers=3,
                                       speakerEmbedding=0, sizeInputSeq=128)
     assert m.gEncoder.DOWNSAMPLING == 160 and c.nPredicts == 12
+
+
+def test_transformer_heads_surface():
+    """rnnMode='transformer' (the reference default, cpc_default_config.py:80): same state_dict keys / parameter count."""
+    import cpc_audio_b200 as M
+    crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode="transformer", dropout=False, speakerEmbedding=0,
+                                      nSpeakers=0, sizeInputSeq=128)
+    sd = crit.state_dict()
+    pre = "wPrediction.predictors.3.0."
+    for k, shape in {"multihead.Wq.weight": (256, 256), "multihead.Att.Krelpos": (32, 116), "multihead.Att.mask": (1, 116, 116),
+                     "multihead.Att.z": (1, 116, 1), "ln_multihead.weight": (256,), "ffnetwork.lin1.weight": (2048, 256),
+                     "ffnetwork.lin2.bias": (256,), "ln_ffnetwork.bias": (256,)}.items():
+        assert tuple(sd[pre + k].shape) == shape, k
+    assert len(sd) == 12 * 15 and sum(p.numel() for p in crit.parameters()) == 15813120  # SURVEY.md 8(a) row T

@@ -285,3 +285,25 @@ def test_config5_dims_bf16(built_lib):
     for k, gr in ref["grads"].items():
         floor = 0.95 if (k.endswith(".bias") and "conv" in k) else 0.98
         assert _cos(out["grads"][k], gr) >= floor, (k, _cos(out["grads"][k], gr))
+
+
+@pytest.mark.parametrize("name", Hh.T_CASES)
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_transformer_heads_parity(name, dtype, built_lib):
+    """rnnMode='transformer' (BASELINE config 4) against the reference fixture and the oracle, eval mode."""
+    g, d, mp, cp, x, label, bi, si = Hh.load_case(name)
+    ref = Hh.oracle_run(d, mp, cp, x, bi, si, heads="transformer")
+    model, crit = Hh.build_modules(d, mp, cp, dtype, heads="transformer")
+    out = Hh.run_modules(model, crit, x, label, bi, si)
+    if dtype == "f32":
+        np.testing.assert_allclose(out["losses"].cpu().numpy(), g["losses"], rtol=1e-5, atol=2e-4)
+        np.testing.assert_allclose(out["losses"].cpu().numpy(), ref["losses"].numpy(), rtol=1e-5, atol=2e-4)
+        for k, gr in ref["grads"].items():
+            e = Hh.rel_err(out["grads"][k], gr)
+            assert e <= 2e-3, (k, e)
+    else:
+        assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.02 * ref["losses"].abs() + 1e-2).all()
+        for k, gr in ref["grads"].items():
+            floor = 0.95 if (d.H < 256 or (k.endswith(".bias") and "conv" in k)) else 0.98
+            assert _cos(out["grads"][k], gr) >= floor, (k, _cos(out["grads"][k], gr))
+    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else 0.03) + Hh.acc_tolerance(ref["logits"], d)).all()
