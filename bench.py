@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="windows per GPU")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"])
+    ap.add_argument("--heads", default="linear", choices=["linear", "transformer"],
+                    help="prediction heads: 'linear' = BASELINE config 2/3 (default), 'transformer' = config 4 (eval-mode heads)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="windows per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -265,8 +267,10 @@ def run_ours(a):
     torch.manual_seed(0)  # identical initial parameters on every rank (replicas)
     model = M.CPCModel(M.CPCEncoder(256, "layerNorm", compute_dtype=a.dtype),
                        M.CPCAR(256, 256, False, 1, mode="GRU", reverse=False, compute_dtype=a.dtype)).to(dev)
-    crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode="linear", dropout=False, speakerEmbedding=0,
+    crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode=a.heads, dropout=False, speakerEmbedding=0,
                                       nSpeakers=0, sizeInputSeq=WINDOW // 160, compute_dtype=a.dtype).to(dev)
+    if a.heads == "transformer":
+        crit.eval()  # the heads implement the reference's eval() semantics (no dropout); gradients still flow
     params = list(crit.parameters()) + list(model.parameters())  # cpc/train.py:332 order
     if a.optimizer == "fused":
         opt = FlatAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
@@ -393,8 +397,10 @@ def run_ours(a):
         line = {"metric": "audio-seconds/sec", "value": sec / (ms / a.steps * 1e-3), "unit": "audio-s/s", "n_gpus": world,
                 "steps": a.steps, "warmup": W_, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-                "config": {"workload": "BASELINE config 2: CPC default (hiddenEncoder=256, 1-layer GRU, K=12, 128 negatives) "
-                                       f"batch={B}/GPU seq=20480, white-noise 16 kHz windows, random-init weights",
+                "config": {"workload": ("BASELINE config 2: CPC default (hiddenEncoder=256, 1-layer GRU, K=12, 128 negatives) "
+                                        if a.heads == "linear" else
+                                        "BASELINE config 4: --rnnMode transformer prediction heads (eval-mode), GRU context net, K=12, 128 negatives ")
+                                       + f"batch={B}/GPU seq=20480, white-noise 16 kHz windows, random-init weights",
                            "global_batch": B * world, "seq_len": WINDOW, "parallelism": f"dp{world}", "optimizer": a.optimizer,
                            "l2": "no explicit flush: one step streams > 1 GB of activations (> 126 MB L2) between reuses"},
                 "e2e": {"value": sec / (ms_e2e / a.steps * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4,
