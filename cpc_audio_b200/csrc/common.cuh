@@ -192,10 +192,26 @@ __host__ __device__ inline bool out_row_ok(const OutView& C, int t, int n0) {
 }
 enum StoreMode { STORE_PLAIN = 0, STORE_CONV_W = 1 };
 
+// ChannelNorm + ReLU fused into the GEMM epilogue (N == 256: one output tile holds every channel of a frame, so the
+// statistics of model.py:52-54 are a per-thread reduction over the accumulator row).  The pre-norm row u goes to the
+// OutView (saved for backward), the normalised row to y (activation dtype, same row geometry as the OutView, its
+// kPad zero rows around each window written here) or, for the last layer, to z (fp32, (nb, rpb, 256) dense).
+struct CNormEpi {
+  const float* gam;
+  const float* bet;
+  void* y;
+  float* z;
+  int pad_rows;
+};
+
 // C[m,n] = sum_k A[m,k] * B[n,k] (+ bias[n]).  A row view (M = nb*rpb rows, inner Kd); B dense (N, Kd) ld=Kd.
 // out_f32: C is fp32, else C has the activation dtype.
 int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias,
             const OutView& C, cudaStream_t st);
+// bf16 tensor-core path only: u = A.B^T + bias -> C (bf16), ChannelNorm+ReLU(u) -> E.y / E.z.  *handled = false
+// when the shape does not fit (N != 256, ...): the caller then runs gemm_nt + the stand-alone norm kernel.
+int gemm_nt_cnorm_tc(int nb, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C, const CNormEpi& E,
+                     cudaStream_t st, bool* handled);
 // Cacc[n1,n2] += sum_m A[m,n1] * B[m,n2]  (fp32 atomics).  mode STORE_CONV_W: n2 = tap*Ci + ci -> Cacc[(n1*Ci + ci)*taps + tap]
 int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc,
             int mode, int Ci, int taps, cudaStream_t st);

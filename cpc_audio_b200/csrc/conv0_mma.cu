@@ -9,6 +9,7 @@
 // Accumulator layout (m16n8k16): thread (g, t) holds rows g, g+8 and channels 8j+2t, 8j+2t+1 of every n-tile j,
 // so the ChannelNorm statistics of a frame are an in-thread sum over 2H/8 values plus two shuffles.
 // Tiles are staged through shared memory so that HBM sees 512-byte rows.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cpcb200 {
@@ -401,6 +402,283 @@ __global__ void __launch_bounds__(128) conv0_wgrad_mma_kernel(const float* __res
   for (int i = threadIdx.x; i < H * 10; i += blockDim.x) atomicAdd(dw + i, accs[i]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// backward, second generation (L0 % 64 == 0).  A CTA owns a tile of 64 frames x H channels; warp w owns the channel
+// slice [64w, 64w+64) of all 64 frames (4 m-tiles x 8 n-tiles of m16n8k16).  Compared with the warp-per-16-frames
+// kernel above: (i) the three per-channel sums (dgamma, dbeta, and dW0/dbias) accumulate in REGISTERS over all the
+// tiles of the CTA - no ones-matrix MMAs, no shared-memory atomics; (ii) the dy tile and the waveform samples of
+// the next tile are prefetched with cp.async while the current one is processed; (iii) the weight gradient
+// dW0[c][tap] += sum_f du[f][c] x[5f-3+tap] is taken from the du tile while it is still in shared memory
+// (A = du^T by ldmatrix.trans, B = waveform samples; tap 10 = 1.0 yields dbias0), so du is not read again.
+// Row statistics cross the NW warps through two small shared arrays (sum / sum of squares, then s1 / s2).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int kFT = 64;    // frames per tile
+constexpr int kXS = 336;   // floats reserved for the 5*64+5 samples of a tile
+
+template <int H>
+constexpr size_t bwd2_smem() {
+  return (size_t)2 * H * 4 + (size_t)(H / 8) * 32 * 8 + (size_t)2 * (H / 64) * kFT * 8 + 2 * kXS * 4 + (size_t)2 * kFT * (2 * H + 16);
+}
+
+template <int H>
+__global__ void __launch_bounds__(H / 2, (H <= 256 ? 2 : 1))
+conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      const float* __restrict__ gam, const float* __restrict__ bet, bf16* __restrict__ dy,
+                      float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ dgam, float* __restrict__ dbet,
+                      int B, int L, int L0) {
+  constexpr int NW = H / 64, NTHR = NW * 32, RS = 2 * H + 16, TILE = kFT * RS, SEGS = H / 8;
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* gb = reinterpret_cast<float*>(sm);                                    // gamma[H], beta[H]
+  uint2* wsm = reinterpret_cast<uint2*>(sm + 2 * H * 4);                       // weight fragments [H/8][32]
+  float2* part0 = reinterpret_cast<float2*>(sm + 2 * H * 4 + SEGS * 32 * 8);   // [NW][64] (sum u, sum u^2)
+  float2* part1 = part0 + NW * kFT;                                            // [NW][64] (s1, s2)
+  float* xs = reinterpret_cast<float*>(part1 + NW * kFT);                      // [2][kXS]
+  unsigned char* tiles = reinterpret_cast<unsigned char*>(xs + 2 * kXS);       // [2][TILE]
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < H; i += NTHR) { gb[i] = gam[i]; gb[H + i] = bet[i]; }
+  stage_wfrags<H>(w, bias, wsm);
+
+  const int tpw = L0 / kFT, ntiles = B * tpw;
+  auto issue = [&](int tile, int buf) {
+    const int b = tile / tpw, f0 = (tile - b * tpw) * kFT;
+    const bf16* src = dy + ((long long)b * L0 + f0) * H;
+    const uint32_t dst = s_u32(tiles + buf * TILE);
+    for (int i = tid; i < kFT * SEGS; i += NTHR) {
+      const int r = i / SEGS, sg = i - r * SEGS;
+      cp_async16(dst + r * RS + sg * 16, src + (size_t)r * H + sg * 8);
+    }
+    const float* xb = x + (long long)b * L;
+    const int s0 = 5 * f0 - 3;
+    for (int i = tid; i < 5 * kFT + 5; i += NTHR) {
+      const int sidx = s0 + i;
+      if (sidx >= 0 && sidx < L) cp_async4(s_u32(xs + buf * kXS + i), xb + sidx);
+      else xs[buf * kXS + i] = 0.f;
+    }
+    cp_async_commit();
+  };
+
+  float cdg[8][2], cdb[8][2], wacc[4][2][4];
+#pragma unroll
+  for (int j = 0; j < 8; j++) cdg[j][0] = cdg[j][1] = cdb[j][0] = cdb[j][1] = 0.f;
+#pragma unroll
+  for (int m = 0; m < 4; m++)
+#pragma unroll
+    for (int n = 0; n < 2; n++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) wacc[m][n][e] = 0.f;
+
+  int tile = blockIdx.x, it = 0;
+  if (tile < ntiles) issue(tile, 0);
+  for (; tile < ntiles; tile += gridDim.x, it++) {
+    const int buf = it & 1;
+    cp_async_wait_all();
+    __syncthreads();  // (A) this tile is visible; every warp is done with the other buffer
+    if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, buf ^ 1);
+    unsigned char* tl = tiles + buf * TILE;
+    const float* xt = xs + buf * kXS;
+    const int b = tile / tpw, f0 = (tile - b * tpw) * kFT;
+
+    // ---- u = X . W0^T for the warp's 64 channels -------------------------------------------------------
+    float acc[4][8][4];
+    {
+      uint32_t ah[4][4], al[4][4];
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        float v[2][4], h[2][4];
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+          const int base = 5 * (16 * m + g + 8 * hf);
+          v[hf][0] = xt[base + 2 * t]; v[hf][1] = xt[base + 2 * t + 1];
+          v[hf][2] = t == 0 ? xt[base + 8] : (t == 1 ? 1.f : 0.f);
+          v[hf][3] = t == 0 ? xt[base + 9] : 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; q++) h[hf][q] = bf16_round(v[hf][q]);
+        }
+        ah[m][0] = pack_bf16(h[0][0], h[0][1]); ah[m][1] = pack_bf16(h[1][0], h[1][1]);
+        ah[m][2] = pack_bf16(h[0][2], h[0][3]); ah[m][3] = pack_bf16(h[1][2], h[1][3]);
+        al[m][0] = pack_bf16(v[0][0] - h[0][0], v[0][1] - h[0][1]); al[m][1] = pack_bf16(v[1][0] - h[1][0], v[1][1] - h[1][1]);
+        al[m][2] = pack_bf16(v[0][2] - h[0][2], v[0][3] - h[0][3]); al[m][3] = pack_bf16(v[1][2] - h[1][2], v[1][3] - h[1][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint2 wv = wsm[(8 * wp + j) * 32 + lane];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          acc[m][j][0] = acc[m][j][1] = acc[m][j][2] = acc[m][j][3] = 0.f;
+          mma16816(acc[m][j], ah[m], wv.x, wv.y);
+          mma16816(acc[m][j], al[m], wv.x, wv.y);
+        }
+      }
+    }
+    // ---- row statistics over all H channels (model.py:52-54) ----------------------------------------------
+    float rstd[4][2], nmr[4][2];
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float a0 = acc[m][j][2 * hf], a1 = acc[m][j][2 * hf + 1];
+          s += a0 + a1; q = fmaf(a0, a0, q); q = fmaf(a1, a1, q);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
+        q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2);
+        if (t == 0) part0[wp * kFT + 16 * m + g + 8 * hf] = make_float2(s, q);
+      }
+    __syncthreads();  // (B)
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++) { const float2 p2 = part0[ww * kFT + 16 * m + g + 8 * hf]; s += p2.x; q += p2.y; }
+        const float mean = s / (float)H;
+        const float var = fmaxf((q - s * mean) / (float)(H - 1), 0.f);
+        rstd[m][hf] = rsqrtf(var + kEps);
+        nmr[m][hf] = -mean * rstd[m][hf];
+      }
+    // ---- pass 1: xhat (kept in acc), dgamma / dbeta partial sums, row sums s1 = sum dx, s2 = sum dx*xhat ----
+    float s1[4][2], s2[4][2];
+#pragma unroll
+    for (int m = 0; m < 4; m++) s1[m][0] = s1[m][1] = s2[m][0] = s2[m][1] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int c = 64 * wp + 8 * j + 2 * t;
+      const float2 g2 = *reinterpret_cast<const float2*>(gb + c), b2 = *reinterpret_cast<const float2*>(gb + H + c);
+#pragma unroll
+      for (int m = 0; m < 4; m++)
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+          const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(tl + (16 * m + g + 8 * hf) * RS + c * 2);
+          const float dyv[2] = {__low2float(d2), __high2float(d2)}, gg[2] = {g2.x, g2.y}, bb[2] = {b2.x, b2.y};
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const float xh = fmaf(acc[m][j][2 * hf + q], rstd[m][hf], nmr[m][hf]);
+            const float dv = fmaf(xh, gg[q], bb[q]) > 0.f ? dyv[q] : 0.f;
+            cdg[j][q] = fmaf(dv, xh, cdg[j][q]);
+            cdb[j][q] += dv;
+            const float dx = dv * gg[q];
+            s1[m][hf] += dx;
+            s2[m][hf] = fmaf(dx, xh, s2[m][hf]);
+            acc[m][j][2 * hf + q] = xh;
+          }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        float a = s1[m][hf], c2 = s2[m][hf];
+        a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, 1); c2 += __shfl_xor_sync(0xffffffffu, c2, 2);
+        if (t == 0) part1[wp * kFT + 16 * m + g + 8 * hf] = make_float2(a, c2);
+      }
+    __syncthreads();  // (C)
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        float a = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++) { const float2 p2 = part1[ww * kFT + 16 * m + g + 8 * hf]; a += p2.x; c2 += p2.y; }
+        s1[m][hf] = rstd[m][hf] * a / (float)H;          // rstd * mean(dx)
+        s2[m][hf] = rstd[m][hf] * c2 / (float)(H - 1);   // rstd * sum(dx xhat) / (H-1)
+      }
+    // ---- pass 2: du = rstd * (dx - s1 - xhat * s2), in place over dy (this warp's columns only) -----------
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int c = 64 * wp + 8 * j + 2 * t;
+      const float2 g2 = *reinterpret_cast<const float2*>(gb + c), b2 = *reinterpret_cast<const float2*>(gb + H + c);
+      __nv_bfloat162 d2[4][2];
+#pragma unroll
+      for (int m = 0; m < 4; m++)
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) d2[m][hf] = *reinterpret_cast<const __nv_bfloat162*>(tl + (16 * m + g + 8 * hf) * RS + c * 2);
+#pragma unroll
+      for (int m = 0; m < 4; m++)
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+          const float dyv[2] = {__low2float(d2[m][hf]), __high2float(d2[m][hf])}, gg[2] = {g2.x, g2.y}, bb[2] = {b2.x, b2.y};
+          float o[2];
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const float xh = acc[m][j][2 * hf + q];
+            const float dv = fmaf(xh, gg[q], bb[q]) > 0.f ? dyv[q] : 0.f;
+            o[q] = fmaf(-xh, s2[m][hf], fmaf(dv * gg[q], rstd[m][hf], -s1[m][hf]));
+          }
+          *reinterpret_cast<uint32_t*>(tl + (16 * m + g + 8 * hf) * RS + c * 2) = pack_bf16(o[0], o[1]);
+        }
+    }
+    __syncwarp();
+    // ---- dW0 / dbias0 from the du tile: D[16 ch x taps] += du^T[16 ch x 16 frames] . X[16 frames x taps] ----
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      uint32_t bx[2][2];
+#pragma unroll
+      for (int n = 0; n < 2; n++) {
+        const int tap = g + 8 * n;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int fr = 16 * ks + 2 * t + (q & 1) + 8 * (q >> 1);
+          v[q] = tap < 10 ? xt[5 * fr + tap] : (tap == 10 ? 1.f : 0.f);
+        }
+        bx[n][0] = pack_bf16(v[0], v[1]);
+        bx[n][1] = pack_bf16(v[2], v[3]);
+      }
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        const int mi = lane >> 3;
+        uint32_t a[4];
+        ldsm_x4_t(a, s_u32(tl + (16 * ks + (mi >> 1) * 8 + (lane & 7)) * RS + (64 * wp + 16 * m + (mi & 1) * 8) * 2));
+        mma16816(wacc[m][0], a, bx[0][0], bx[0][1]);
+        mma16816(wacc[m][1], a, bx[1][0], bx[1][1]);
+      }
+    }
+    __syncthreads();  // (D) the du tile is complete
+    {
+      bf16* dst = dy + ((long long)b * L0 + f0) * H;
+      for (int i = tid; i < kFT * SEGS; i += NTHR) {
+        const int r = i / SEGS, sg = i - r * SEGS;
+        *reinterpret_cast<uint4*>(dst + (size_t)r * H + sg * 8) = *reinterpret_cast<const uint4*>(tl + r * RS + sg * 16);
+      }
+    }
+  }
+  cp_async_wait_all();
+  // ---- flush the register accumulators -------------------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      float a = cdg[j][q], c2 = cdb[j][q];
+      a += __shfl_xor_sync(0xffffffffu, a, 4); a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, 4); c2 += __shfl_xor_sync(0xffffffffu, c2, 8); c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
+      if (g == 0) { const int c = 64 * wp + 8 * j + 2 * t + q; atomicAdd(dgam + c, a); atomicAdd(dbet + c, c2); }
+    }
+#pragma unroll
+  for (int m = 0; m < 4; m++)
+#pragma unroll
+    for (int n = 0; n < 2; n++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int c = 64 * wp + 16 * m + g + 8 * (e >> 1), tap = 8 * n + 2 * t + (e & 1);
+        if (tap < 10) atomicAdd(dw + c * 10 + tap, wacc[m][n][e]);
+        else if (tap == 10) atomicAdd(dbias + c, wacc[m][n][e]);
+      }
+}
+
 template <int H>
 int launch_all_fwd(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* y, int B, int L,
                    int L0, cudaStream_t st) {
@@ -417,6 +695,16 @@ int launch_all_bwd(const float* x, const float* w, const float* bias, const floa
                    float* dbias, float* dgam, float* dbet, int B, int L, int L0, cudaStream_t st) {
   const size_t smem1 = 5 * H * 4 + (H / 8) * 32 * 8 + 4 * 2 * 16 * (2 * H + 16);
   const size_t smem2 = H * 10 * 4 + 4 * 16 * (2 * H + 16);
+  static const bool gen1 = []() { const char* e = getenv("CPC_B200_CONV0_BWD_GEN"); return e && atoi(e) == 1; }();
+  if (L0 % kFT == 0 && !gen1) {
+    const size_t smem = bwd2_smem<H>();
+    int blocks2 = B * (L0 / kFT);
+    if (blocks2 > 148 * 2) blocks2 = 148 * 2;
+    CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd2_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv0_bwd2_mma_kernel<H><<<blocks2, H / 2, smem, st>>>(x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0);
+    CPC_LAUNCHED_N("conv0_bwd2_mma", st);
+    return 0;
+  }
   int blocks = (B * (L0 / 16) + 3) / 4;
   if (blocks > 148 * 3) blocks = 148 * 3;
   CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd_du_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));

@@ -345,81 +345,99 @@ __global__ void __launch_bounds__(256) cnorm_relu_fwd_kernel(const T* __restrict
 }
 
 // backward of ChannelNorm+ReLU: dy (B,Lc,H) TD unpadded, u padded -> du padded (T); dgamma/dbeta/dbias +=
+// Persistent grid, each warp takes kCbR consecutive rows per trip with all 2*kCbR row loads in flight before the
+// first use; the per-channel sums stay in registers for the whole kernel and leave through one shared-memory
+// reduction over the 8 warps + one global atomic per channel per CTA.
+
 template <int I, class TD, class T>
-__global__ void __launch_bounds__(256) cnorm_relu_bwd_kernel(const TD* __restrict__ dy, const T* __restrict__ u,
-                                                              const float* __restrict__ gam, const float* __restrict__ bet,
-                                                              T* __restrict__ du, float* __restrict__ dgam,
-                                                              float* __restrict__ dbet, float* __restrict__ dbias, int B,
-                                                              int Lc, int H) {
-  extern __shared__ __align__(16) float accs[];  // [3][H]
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) accs[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256, (I <= 2 ? 2 : 1)) cnorm_relu_bwd_kernel(const TD* __restrict__ dy, const T* __restrict__ u,
+                                                                 const float* __restrict__ gam, const float* __restrict__ bet,
+                                                                 T* __restrict__ du, float* __restrict__ dgam,
+                                                                 float* __restrict__ dbet, float* __restrict__ dbias, int B,
+                                                                 int Lc, int H) {
+  constexpr int kCbR = I <= 2 ? 4 : 2;
+  extern __shared__ __align__(16) float red[];  // [8 warps][3][H]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long rows = (long long)B * Lc;
-  float ag[I][4], abe[I][4], ab[I][4];
-#pragma unroll
-  for (int i = 0; i < I; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) ag[i][j] = abe[i][j] = ab[i][j] = 0.f;
-  for (long long r = warp0; r < rows; r += nwarps) {
-    const int b = (int)(r / Lc), t = (int)(r - (long long)b * Lc);
-    const long long prow = ((long long)b * (Lc + 2 * kPad) + kPad + t) * H;
-    float v[I][4], d[I][4];
-    row_load<I>(u + prow, H, lane, v);
-    row_load<I>(dy + r * H, H, lane, d);
-    float mean, rstd;
-    row_stats<I>(v, H, lane, mean, rstd);
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < I; i++) {
-      int c = 4 * (lane + 32 * i);
-      if (c < H) {
-        float4 g4 = *reinterpret_cast<const float4*>(gam + c);
-        float4 b4 = *reinterpret_cast<const float4*>(bet + c);
-        float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          float xh = (v[i][j] - mean) * rstd;
-          float a = fmaf(xh, g[j], be[j]);
-          float dv = a > 0.f ? d[i][j] : 0.f;
-          ag[i][j] = fmaf(dv, xh, ag[i][j]);
-          abe[i][j] += dv;
-          float dx = dv * g[j];
-          v[i][j] = xh; d[i][j] = dx;
-          s1 += dx; s2 = fmaf(dx, xh, s2);
-        }
-      }
-    }
-    s1 = warp_sum(s1) / (float)H;
-    s2 = warp_sum(s2) / (float)(H - 1);
-#pragma unroll
-    for (int i = 0; i < I; i++) {
-      int c = 4 * (lane + 32 * i);
-      if (c < H) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) { float o = rstd * (d[i][j] - s1 - v[i][j] * s2); ab[i][j] += o; d[i][j] = o; }
-      }
-    }
-    row_store<I>(du + prow, H, lane, d);
-    const long long w0 = (long long)b * (Lc + 2 * kPad) * H;
-    if (t == 0) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)r2 * H, H, lane); }
-    if (t == Lc - 1) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)(kPad + Lc + r2) * H, H, lane); }
-  }
+  float ag[I][4], abe[I][4], ab[I][4], g[I][4], be[I][4];
 #pragma unroll
   for (int i = 0; i < I; i++) {
-    int c = 4 * (lane + 32 * i);
-    if (c < H) {
+    const int c = 4 * (lane + 32 * i);
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
+    if (c < H) { g4 = *reinterpret_cast<const float4*>(gam + c); b4 = *reinterpret_cast<const float4*>(bet + c); }
+    g[i][0] = g4.x; g[i][1] = g4.y; g[i][2] = g4.z; g[i][3] = g4.w;
+    be[i][0] = b4.x; be[i][1] = b4.y; be[i][2] = b4.z; be[i][3] = b4.w;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        atomicAdd(&accs[c + j], ag[i][j]); atomicAdd(&accs[H + c + j], abe[i][j]); atomicAdd(&accs[2 * H + c + j], ab[i][j]);
+    for (int j = 0; j < 4; j++) ag[i][j] = abe[i][j] = ab[i][j] = 0.f;
+  }
+  for (long long r0 = warp0 * kCbR; r0 < rows; r0 += nwarps * kCbR) {
+    float v[kCbR][I][4], d[kCbR][I][4];
+    long long prow[kCbR];
+#pragma unroll
+    for (int rr = 0; rr < kCbR; rr++) {
+      const long long r = r0 + rr < rows ? r0 + rr : rows - 1;
+      const int b = (int)(r / Lc), t = (int)(r - (long long)b * Lc);
+      prow[rr] = ((long long)b * (Lc + 2 * kPad) + kPad + t) * H;
+      row_load<I>(u + prow[rr], H, lane, v[rr]);
+      row_load<I>(dy + r * H, H, lane, d[rr]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < kCbR; rr++) {
+      if (r0 + rr >= rows) break;
+      float mean, rstd;
+      row_stats<I>(v[rr], H, lane, mean, rstd);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < I; i++) {
+        if (4 * (lane + 32 * i) < H) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float xh = (v[rr][i][j] - mean) * rstd;
+            const float dv = fmaf(xh, g[i][j], be[i][j]) > 0.f ? d[rr][i][j] : 0.f;
+            ag[i][j] = fmaf(dv, xh, ag[i][j]);
+            abe[i][j] += dv;
+            const float dx = dv * g[i][j];
+            v[rr][i][j] = xh; d[rr][i][j] = dx;
+            s1 += dx; s2 = fmaf(dx, xh, s2);
+          }
+        }
       }
+      s1 = warp_sum(s1) / (float)H;
+      s2 = warp_sum(s2) / (float)(H - 1);
+#pragma unroll
+      for (int i = 0; i < I; i++) {
+        if (4 * (lane + 32 * i) < H) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) { const float o = rstd * (d[rr][i][j] - s1 - v[rr][i][j] * s2); ab[i][j] += o; d[rr][i][j] = o; }
+        }
+      }
+      row_store<I>(du + prow[rr], H, lane, d[rr]);
+      const long long r = r0 + rr;
+      const int b = (int)(r / Lc), t = (int)(r - (long long)b * Lc);
+      const long long w0 = (long long)b * (Lc + 2 * kPad) * H;
+      if (t == 0) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)r2 * H, H, lane); }
+      if (t == Lc - 1) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)(kPad + Lc + r2) * H, H, lane); }
+    }
+  }
+  float* mine = red + (size_t)wib * 3 * H;
+#pragma unroll
+  for (int i = 0; i < I; i++) {
+    const int c = 4 * (lane + 32 * i);
+    if (c < H) {
+      *reinterpret_cast<float4*>(mine + c) = make_float4(ag[i][0], ag[i][1], ag[i][2], ag[i][3]);
+      *reinterpret_cast<float4*>(mine + H + c) = make_float4(abe[i][0], abe[i][1], abe[i][2], abe[i][3]);
+      *reinterpret_cast<float4*>(mine + 2 * H + c) = make_float4(ab[i][0], ab[i][1], ab[i][2], ab[i][3]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    atomicAdd(dgam + i, accs[i]); atomicAdd(dbet + i, accs[H + i]); atomicAdd(dbias + i, accs[2 * H + i]);
+  const int nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) {
+    float a = 0.f;
+    for (int ww = 0; ww < nw; ww++) a += red[(size_t)ww * 3 * H + i];
+    const int k = i / H, c = i - k * H;
+    atomicAdd((k == 0 ? dgam : k == 1 ? dbet : dbias) + c, a);
   }
 }
 
@@ -520,11 +538,17 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     const int Lin = g.Lout[i - 1], Lo = g.Lout[i];
     RowView A{sv + e.y[i - 1] + (size_t)(kPad - kConvP[i]) * H, (long long)(Lin + 2 * kPad) * H, (long long)kConvS[i] * H, Lo, kConvK[i], kConvS[i]};
     OutView C{sv + e.u[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo, 0, Lo, 0};
+    T* yo = i < 4 ? sv + e.y[i] : nullptr;
+    float* zo = i == 4 ? z : nullptr;
+    if (g.bf16 && H == 256) {  // ChannelNorm + ReLU inside the GEMM epilogue
+      bool fused = false;
+      CNormEpi E{p->norm_w[i], p->norm_b[i], yo != nullptr ? static_cast<void*>(yo + (size_t)kPad * H) : nullptr, zo, kPad};
+      CPC_TRY(gemm_nt_cnorm_tc(B, kConvK[i] * H, A, wp[i], p->conv_b[i], C, E, st, &fused));
+      if (fused) continue;
+    }
     CPC_TRY(gemm_nt(g.bf16, false, B, H, kConvK[i] * H, A, wp[i], p->conv_b[i], C, st));
     const long long rows = (long long)B * Lo;
     const int blocks = (int)((rows * 32 + 255) / 256);
-    T* yo = i < 4 ? sv + e.y[i] : nullptr;
-    float* zo = i == 4 ? z : nullptr;
 #define LAUNCH_CN(II) cnorm_relu_fwd_kernel<II, T><<<blocks, 256, 0, st>>>(sv + e.u[i], p->norm_w[i], p->norm_b[i], yo, zo, B, Lo, H)
     if (I == 1) LAUNCH_CN(1); else if (I == 2) LAUNCH_CN(2); else if (I == 3) LAUNCH_CN(3); else LAUNCH_CN(4);
 #undef LAUNCH_CN
@@ -564,9 +588,11 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     // ChannelNorm+ReLU backward -> du_i, dgamma_i, dbeta_i, dbias_i
     {
       const long long rows = (long long)B * Lo;
-      int blocks = (int)((rows * 32 + 255) / 256);
-      if (blocks > 148 * 8) blocks = 148 * 8;
-      const size_t smem = 3 * (size_t)H * sizeof(float);
+      const int kCbR = I <= 2 ? 4 : 2;
+      int blocks = (int)((rows * 32 / kCbR + 255) / 256);
+      if (blocks > 148 * 2) blocks = 148 * 2;
+      if (blocks < 1) blocks = 1;
+      const size_t smem = 8 * 3 * (size_t)H * sizeof(float);
 #define LAUNCH_CB(II, TD, SRC)                                                                                       \
   cnorm_relu_bwd_kernel<II, TD, T><<<blocks, 256, smem, st>>>(SRC, sv + e.u[i], p->norm_w[i], p->norm_b[i], du[i],  \
                                                               gr->norm_w[i], gr->norm_b[i], gr->conv_b[i], B, Lo, H)

@@ -307,12 +307,12 @@ __global__ void __launch_bounds__(NT_THREADS) gemm_tn_tc_kernel(const __grid_con
 // 256/CM rows), accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  L2->SM operand traffic per 128x256x64 block drops from 48 KB to 16 + 32/CM KB.
 // ---------------------------------------------------------------------------------------------------------
-template <int CM, class TO>
+template <int CM, class TO, bool CN>
 __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB, int nkb,
                                                                      int chunks_per_tap, int s, int tiles_per_batch,
                                                                      int m_tiles, int n_tiles, int nb,
-                                                                     const float* __restrict__ bias, OutView C) {
+                                                                     const float* __restrict__ bias, OutView C, CNormEpi E) {
   constexpr int BN2 = 256, STAGES = 4;
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN2 * BK * 2, B_SLICE = B_BYTES / CM;
   constexpr uint16_t MASK = (uint16_t)((1u << CM) - 1);
@@ -325,10 +325,16 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* cn_par = reinterpret_cast<float*>(sm + STAGES * (A_BYTES + B_BYTES) + 256);  // [3][256]: bias, gamma, beta (CN)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)ptx::cluster_ctarank();
   const int cluster_id = blockIdx.x / CM, num_clusters = gridDim.x / CM;
+  if (CN) {
+    for (int i = threadIdx.x; i < BN2; i += NT_THREADS) {
+      cn_par[i] = bias != nullptr ? bias[i] : 0.f; cn_par[BN2 + i] = E.gam[i]; cn_par[2 * BN2 + i] = E.bet[i];
+    }
+  }
   const int m_groups = (m_tiles + CM - 1) / CM;
   const int total_groups = m_groups * n_tiles;
 
@@ -410,6 +416,65 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
       const int acc = ti & 1, ua = ti >> 1;
       ptx::mbar_wait(&tfull[acc], ua & 1);
       ptx::tc_fence_after();
+      if constexpr (CN) {
+        // u = bf16(acc + bias) exactly as the unfused path stores it; statistics and the ReLU mask are taken from the
+        // rounded values so that backward (which re-derives them from the saved u) sees the same numbers.
+        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN2);
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN2; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(trow + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) sum += __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]) + cn_par[c0 + j]));
+        }
+        const float mean = sum * (1.f / BN2);
+        float sq = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN2; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(trow + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float d = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]) + cn_par[c0 + j])) - mean;
+            sq = fmaf(d, d, sq);
+          }
+        }
+        const float rstd = rsqrtf(sq * (1.f / (BN2 - 1)) + 1e-5f);
+        const long long roff = (long long)b * C.bs + (long long)t * C.rs;
+        bf16* yrow = E.y != nullptr ? static_cast<bf16*>(E.y) + roff : nullptr;
+        float* zrow = E.z != nullptr ? E.z + ((long long)b * C.rpb + t) * BN2 : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN2; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(trow + c0, r);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]) + cn_par[c0 + j]));
+            store_out(crow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = fmaxf(fmaf((v[j] - mean) * rstd, cn_par[BN2 + c0 + j], cn_par[2 * BN2 + c0 + j]), 0.f);
+            if (yrow != nullptr) store_out(yrow + c0, v);
+            if (zrow != nullptr) store_out(zrow + c0, v);
+          }
+        }
+        if (row_ok && yrow != nullptr) {  // zero rows around the window (the conv padding of the next layer)
+          for (int pr = 1; pr <= E.pad_rows; pr++) {
+            if (t == 0) {
+              uint4* z4 = reinterpret_cast<uint4*>(yrow - (long long)pr * C.rs);
+              for (int i = 0; i < BN2 / 8; i++) z4[i] = make_uint4(0, 0, 0, 0);
+            }
+            if (t == C.rpb - 1) {
+              uint4* z4 = reinterpret_cast<uint4*>(yrow + (long long)pr * C.rs);
+              for (int i = 0; i < BN2 / 8; i++) z4[i] = make_uint4(0, 0, 0, 0);
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN2; c0 += 32) {
         uint32_t r[32];
@@ -430,6 +495,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
           store_out(crow + c0, v);
         }
       }
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -441,12 +507,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-constexpr size_t nt2_smem() { return (size_t)4 * (BM * BK * 2 + 256 * BK * 2) + 256 + 1024; }
+constexpr size_t nt2_smem() { return (size_t)4 * (BM * BK * 2 + 256 * BK * 2) + 256 + 3 * 256 * 4 + 1024; }
 
-template <int CM, class TO>
+template <int CM, class TO, bool CN = false>
 int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt, int s, int tpb, int m_tiles, int n_tiles, int nb,
-               const float* bias, const OutView& C, cudaStream_t st) {
-  auto k = gemm_nt_tc2_kernel<CM, TO>;
+               const float* bias, const OutView& C, cudaStream_t st, const CNormEpi& E = CNormEpi{}) {
+  auto k = gemm_nt_tc2_kernel<CM, TO, CN>;
   const size_t smem = nt2_smem();
   CPC_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int total_groups = ((m_tiles + CM - 1) / CM) * n_tiles;
@@ -461,8 +527,8 @@ int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt,
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CM; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, tmA, tmB, nkb, cpt, s, tpb, m_tiles, n_tiles, nb, bias, C));
-  CPC_LAUNCHED_N("gemm_nt_tc2", st);
+  CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, tmA, tmB, nkb, cpt, s, tpb, m_tiles, n_tiles, nb, bias, C, E));
+  CPC_LAUNCHED_N(CN ? "gemm_nt_cnorm_tc2" : "gemm_nt_tc2", st);
   return 0;
 }
 
@@ -644,6 +710,33 @@ int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void
     k<<<grid, NT_THREADS, smem, st>>>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb, N, bias, C);
   }
   CPC_LAUNCHED_N("gemm_nt_tc", st);
+  *handled = true;
+  return 0;
+}
+
+int gemm_nt_cnorm_tc(int nb, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C, const CNormEpi& E,
+                     cudaStream_t st, bool* handled) {
+  *handled = false;
+  constexpr int N = 256;
+  static const bool off = []() { const char* e = getenv("CPC_B200_CNORM_FUSE"); return e && atoi(e) == 0; }();
+  static const int cm_env = []() { const char* e = getenv("CPC_B200_GEMM_CM"); return e ? atoi(e) : 2; }();
+  const int cin = Kd / A.taps;
+  if (off || Kd % BK != 0 || cin % 64 != 0 || (A.taps > 1 && A.rs != (long long)A.s * cin)) return 0;
+  if ((A.rs % 8) != 0 || (A.bs % 8) != 0 || (reinterpret_cast<uintptr_t>(A.p) & 15) || (reinterpret_cast<uintptr_t>(Bm) & 15)) return 0;
+  if ((C.rs % 8) != 0 || (C.bs % 8) != 0 || C.res_w != 0 || C.relu != 0 || C.t_lo != 0 || C.t_hi != C.rpb) return 0;
+  if (reinterpret_cast<uintptr_t>(C.p) & 15) return 0;
+  if (E.y != nullptr && (reinterpret_cast<uintptr_t>(E.y) & 15)) return 0;
+  CUtensorMap tmA, tmB;
+  CPC_TRY(make_rowview_map(&tmA, A, Kd, nb, BM, false));
+  const int cm = cm_env == 1 ? 1 : 2;
+  unsigned long long dims[4] = {(unsigned long long)Kd, (unsigned long long)N, 1, 1};
+  unsigned long long stq[3] = {(unsigned long long)Kd, (unsigned long long)Kd * N, (unsigned long long)Kd * N};
+  unsigned box[4] = {64, (unsigned)(256 / cm), 1, 1};
+  CPC_TRY(make_map4(&tmB, Bm, dims, stq, box));
+  const int tpb2 = (A.rpb + BM - 1) / BM;
+  const int m_tiles = nb * tpb2;
+  if (cm == 2) CPC_TRY((launch_nt2<2, bf16, true>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb2, m_tiles, 1, nb, bias, C, st, E)));
+  else CPC_TRY((launch_nt2<1, bf16, true>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb2, m_tiles, 1, nb, bias, C, st, E)));
   *handled = true;
   return 0;
 }
