@@ -66,6 +66,8 @@ SIGNATURES = {
     "cpcb200_adam_step": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
     "cpcb200_test_gemm_nt": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "cpcb200_test_gemm_tn": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "cpcb200_test_gemm_nt_act": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "cpcb200_debug_gemm_timeline": (_I, [_P]),
 }
 
 _lib = None

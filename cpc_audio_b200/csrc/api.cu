@@ -99,6 +99,7 @@ int criterion_bwd(const Geo&, const float*, const float*, const float*, const cp
 
 int gemm_nt_simt(bool, bool, int, int, int, const RowView&, const void*, const float*, const OutView&, cudaStream_t);
 int gemm_tn_simt(bool, int, int, int, const RowView&, const RowView&, float*, int, int, int, int, cudaStream_t);
+int debug_gemm_timeline(unsigned long long* host_out);
 int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C,
                cudaStream_t st, bool* handled);
 int gemm_tn_tc(int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode, int Ci, int taps,
@@ -336,6 +337,16 @@ int cpcb200_test_gemm_nt(int dtype, int M, int N, int Kd, const void* A, const v
   RowView a{A, 0, (long long)Kd, M};
   OutView c{C, 0, (long long)N, M, 0, M, 0};
   return gemm_nt(dtype == CPCB200_BF16, true, 1, N, Kd, a, B, bias, c, static_cast<cudaStream_t>(stream));
+}
+int cpcb200_test_gemm_nt_act(int dtype, int M, int N, int Kd, const void* A, const void* B, const float* bias, void* C, void* stream) {
+  NOT_NULL(A); NOT_NULL(B); NOT_NULL(C);
+  RowView a{A, 0, (long long)Kd, M};
+  OutView c{C, 0, (long long)N, M, 0, M, 0};
+  return gemm_nt(dtype == CPCB200_BF16, false, 1, N, Kd, a, B, bias, c, static_cast<cudaStream_t>(stream));
+}
+int cpcb200_debug_gemm_timeline(unsigned long long* host_out) {
+  NOT_NULL(host_out);
+  return debug_gemm_timeline(host_out);
 }
 int cpcb200_test_gemm_tn(int dtype, int M, int N1, int N2, const void* A, const void* B, float* C, void* stream) {
   NOT_NULL(A); NOT_NULL(B); NOT_NULL(C);

@@ -345,9 +345,106 @@ __global__ void __launch_bounds__(256) cnorm_relu_fwd_kernel(const T* __restrict
 }
 
 // backward of ChannelNorm+ReLU: dy (B,Lc,H) TD unpadded, u padded -> du padded (T); dgamma/dbeta/dbias +=
-// Persistent grid, each warp takes kCbR consecutive rows per trip with all 2*kCbR row loads in flight before the
-// first use; the per-channel sums stay in registers for the whole kernel and leave through one shared-memory
-// reduction over the 8 warps + one global atomic per channel per CTA.
+// Persistent grid; a warp takes R consecutive rows per trip: all 2R row loads are in flight before the first use and
+// the four warp reductions of the R rows (sum, centred squares, s1, s2) run as R interleaved shuffle chains.  The
+// per-channel sums stay in registers for the whole kernel and leave through one shared-memory reduction over the
+// 8 warps + one global atomic per channel per CTA.
+template <int R>
+__device__ __forceinline__ void warp_sum_n(float (&x)[R]) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; r++) x[r] += __shfl_xor_sync(0xffffffffu, x[r], off);
+}
+
+template <int I, int R, class TD, class T>
+__device__ __forceinline__ void cnorm_bwd_rows(const TD* __restrict__ dy, const T* __restrict__ u, T* __restrict__ du,
+                                               long long r0l, int Lc, int H, int lane, const float (&g)[I][4],
+                                               const float (&be)[I][4], float (&ag)[I][4], float (&abe)[I][4],
+                                               float (&ab)[I][4], float inv_h, float inv_h1) {
+  float v[R][I][4], d[R][I][4];
+  long long prow[R];
+  int tt[R], bb[R];
+  const long long Lp = (long long)Lc + 2 * kPad;
+  {
+    const unsigned r0 = (unsigned)r0l;  // rows < 2^31 (checked by the host)
+    int b = (int)(r0 / (unsigned)Lc), t = (int)(r0 - (unsigned)b * (unsigned)Lc);
+#pragma unroll
+    for (int rr = 0; rr < R; rr++) {
+      bb[rr] = b; tt[rr] = t;
+      prow[rr] = ((long long)b * Lp + kPad + t) * H;
+      row_load<I>(u + prow[rr], H, lane, v[rr]);
+      row_load<I>(dy + (r0l + rr) * H, H, lane, d[rr]);
+      if (++t >= Lc) { t = 0; b++; }
+    }
+  }
+  float mean[R], rstd[R], nmr[R];
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < I; i++) s += (v[rr][i][0] + v[rr][i][1]) + (v[rr][i][2] + v[rr][i][3]);  // lanes past H hold zeros
+    mean[rr] = s;
+  }
+  warp_sum_n<R>(mean);
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    mean[rr] *= inv_h;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < I; i++)
+      if (4 * (lane + 32 * i) < H) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const float dl = v[rr][i][j] - mean[rr]; q = fmaf(dl, dl, q); }
+      }
+    rstd[rr] = q;
+  }
+  warp_sum_n<R>(rstd);
+  float s1[R], s2[R];
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    rstd[rr] = rsqrtf(rstd[rr] * inv_h1 + kEps);
+    nmr[rr] = -mean[rr] * rstd[rr];
+    s1[rr] = s2[rr] = 0.f;
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      if (4 * (lane + 32 * i) < H) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float xh = fmaf(v[rr][i][j], rstd[rr], nmr[rr]);
+          const float dv = fmaf(xh, g[i][j], be[i][j]) > 0.f ? d[rr][i][j] : 0.f;
+          ag[i][j] = fmaf(dv, xh, ag[i][j]);
+          abe[i][j] += dv;
+          const float dx = dv * g[i][j];
+          v[rr][i][j] = xh; d[rr][i][j] = dx;
+          s1[rr] += dx; s2[rr] = fmaf(dx, xh, s2[rr]);
+        }
+      }
+    }
+  }
+  warp_sum_n<R>(s1);
+  warp_sum_n<R>(s2);
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    const float c1 = -rstd[rr] * s1[rr] * inv_h, c2 = -rstd[rr] * s2[rr] * inv_h1;
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+      if (4 * (lane + 32 * i) < H) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float o = fmaf(v[rr][i][j], c2, fmaf(d[rr][i][j], rstd[rr], c1));
+          ab[i][j] += o; d[rr][i][j] = o;
+        }
+      }
+    }
+    row_store<I>(du + prow[rr], H, lane, d[rr]);
+    if (tt[rr] == 0 || tt[rr] == Lc - 1) {
+      const long long w0 = (long long)bb[rr] * Lp * H;
+      if (tt[rr] == 0) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)r2 * H, H, lane); }
+      if (tt[rr] == Lc - 1) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)(kPad + Lc + r2) * H, H, lane); }
+    }
+  }
+}
 
 template <int I, class TD, class T>
 __global__ void __launch_bounds__(256, (I <= 2 ? 2 : 1)) cnorm_relu_bwd_kernel(const TD* __restrict__ dy, const T* __restrict__ u,
@@ -372,55 +469,12 @@ __global__ void __launch_bounds__(256, (I <= 2 ? 2 : 1)) cnorm_relu_bwd_kernel(c
 #pragma unroll
     for (int j = 0; j < 4; j++) ag[i][j] = abe[i][j] = ab[i][j] = 0.f;
   }
-  for (long long r0 = warp0 * kCbR; r0 < rows; r0 += nwarps * kCbR) {
-    float v[kCbR][I][4], d[kCbR][I][4];
-    long long prow[kCbR];
-#pragma unroll
-    for (int rr = 0; rr < kCbR; rr++) {
-      const long long r = r0 + rr < rows ? r0 + rr : rows - 1;
-      const int b = (int)(r / Lc), t = (int)(r - (long long)b * Lc);
-      prow[rr] = ((long long)b * (Lc + 2 * kPad) + kPad + t) * H;
-      row_load<I>(u + prow[rr], H, lane, v[rr]);
-      row_load<I>(dy + r * H, H, lane, d[rr]);
-    }
-#pragma unroll
-    for (int rr = 0; rr < kCbR; rr++) {
-      if (r0 + rr >= rows) break;
-      float mean, rstd;
-      row_stats<I>(v[rr], H, lane, mean, rstd);
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < I; i++) {
-        if (4 * (lane + 32 * i) < H) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const float xh = (v[rr][i][j] - mean) * rstd;
-            const float dv = fmaf(xh, g[i][j], be[i][j]) > 0.f ? d[rr][i][j] : 0.f;
-            ag[i][j] = fmaf(dv, xh, ag[i][j]);
-            abe[i][j] += dv;
-            const float dx = dv * g[i][j];
-            v[rr][i][j] = xh; d[rr][i][j] = dx;
-            s1 += dx; s2 = fmaf(dx, xh, s2);
-          }
-        }
-      }
-      s1 = warp_sum(s1) / (float)H;
-      s2 = warp_sum(s2) / (float)(H - 1);
-#pragma unroll
-      for (int i = 0; i < I; i++) {
-        if (4 * (lane + 32 * i) < H) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) { const float o = rstd * (d[rr][i][j] - s1 - v[rr][i][j] * s2); ab[i][j] += o; d[rr][i][j] = o; }
-        }
-      }
-      row_store<I>(du + prow[rr], H, lane, d[rr]);
-      const long long r = r0 + rr;
-      const int b = (int)(r / Lc), t = (int)(r - (long long)b * Lc);
-      const long long w0 = (long long)b * (Lc + 2 * kPad) * H;
-      if (t == 0) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)r2 * H, H, lane); }
-      if (t == Lc - 1) { for (int r2 = 0; r2 < kPad; r2++) zero_row(du + w0 + (long long)(kPad + Lc + r2) * H, H, lane); }
-    }
-  }
+  const float inv_h = 1.f / (float)H, inv_h1 = 1.f / (float)(H - 1);
+  const long long full = rows / kCbR;  // trips of kCbR rows; the < kCbR leftover rows go one at a time
+  for (long long trip = warp0; trip < full; trip += nwarps)
+    cnorm_bwd_rows<I, kCbR, TD, T>(dy, u, du, trip * kCbR, Lc, H, lane, g, be, ag, abe, ab, inv_h, inv_h1);
+  for (long long r = full * kCbR + warp0; r < rows; r += nwarps)
+    cnorm_bwd_rows<I, 1, TD, T>(dy, u, du, r, Lc, H, lane, g, be, ag, abe, ab, inv_h, inv_h1);
   float* mine = red + (size_t)wib * 3 * H;
 #pragma unroll
   for (int i = 0; i < I; i++) {

@@ -24,6 +24,10 @@ namespace {
 constexpr int BM = 128, BK = 64, UK = 16;
 constexpr int NT_THREADS = 192;
 
+// per-CTA cycle stamps of the last gemm_nt_tc2 launch (debug hook cpcb200_debug_gemm_timeline): 8 slots per CTA
+__device__ unsigned long long g_nt2_tl[148 * 8];
+#define TL_STAMP(slot) do { if (blockIdx.x < 148) g_nt2_tl[blockIdx.x * 8 + (slot)] = (unsigned long long)(clock64() - tl_t0); } while (0)
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -301,6 +305,61 @@ __global__ void __launch_bounds__(NT_THREADS) gemm_tn_tc_kernel(const __grid_con
   if (warp == 1) ptx::tmem_dealloc(tmem_acc, BN);
 }
 
+// ---- epilogue staging (gen 2): a warp parks 32 rows x 64 bytes in shared memory (row stride 80 B: conflict-free
+// 16-byte stores) and copies them out with 8 rows x 64 B per instruction instead of 32 rows x 16 B -------------
+constexpr int NT2_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant: column halves)
+constexpr int STG_RS = 80, STG_WARP = 32 * STG_RS;
+
+__device__ __forceinline__ void stage_put(unsigned char* my_row, const float (&v)[32], int sub, bf16*) {  // 32 bf16 = 64 B
+  (void)sub;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; j++) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+    reinterpret_cast<uint4*>(my_row)[i] = t;
+  }
+}
+__device__ __forceinline__ void stage_put(unsigned char* my_row, const float (&v)[32], int sub, float*) {  // 16 fp32 = 64 B
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    reinterpret_cast<float4*>(my_row)[i] = make_float4(v[16 * sub + 4 * i], v[16 * sub + 4 * i + 1], v[16 * sub + 4 * i + 2], v[16 * sub + 4 * i + 3]);
+}
+// rows whose bit is set in `ok` go to gbase + row * row_bytes (64 contiguous bytes each)
+__device__ __forceinline__ void stage_flush(const unsigned char* stg, unsigned char* gbase, long long row_bytes, uint32_t ok, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int row = 8 * i + (lane >> 2), piece = lane & 3;
+    if ((ok >> row) & 1u)
+      *reinterpret_cast<uint4*>(gbase + (long long)row * row_bytes + piece * 16) = *reinterpret_cast<const uint4*>(stg + row * STG_RS + piece * 16);
+  }
+}
+// same, as 16-byte fp32 reductions (split-K accumulation of the TN kernel)
+__device__ __forceinline__ void stage_flush_red(const unsigned char* stg, float* gbase, long long row_el, uint32_t ok, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int row = 8 * i + (lane >> 2), piece = lane & 3;
+    if ((ok >> row) & 1u) {
+      const float4 v = *reinterpret_cast<const float4*>(stg + row * STG_RS + piece * 16);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + (long long)row * row_el + piece * 4), "f"(v.x), "f"(v.y),
+                   "f"(v.z), "f"(v.w) : "memory");
+    }
+  }
+}
+// one 32-column chunk of this thread's row -> global through the warp's staging buffer
+template <class TO>
+__device__ __forceinline__ void emit_chunk(unsigned char* stg, int lane, const float (&v)[32], TO* gchunk, long long rs_el, uint32_t ok) {
+  constexpr int SUBS = sizeof(TO) == 2 ? 1 : 2;
+#pragma unroll
+  for (int sub = 0; sub < SUBS; sub++) {
+    stage_put(stg + lane * STG_RS, v, sub, static_cast<TO*>(nullptr));
+    __syncwarp();
+    stage_flush(stg, reinterpret_cast<unsigned char*>(gchunk + sub * 16), rs_el * (long long)sizeof(TO), ok, lane);
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // NT kernel, second generation: persistent, 128 x 256 tiles, the weight tile (B operand, identical for every
 // M tile) is loaded ONCE per cluster and multicast by TMA to the CM CTAs of the cluster (each CTA fetches
@@ -308,7 +367,7 @@ __global__ void __launch_bounds__(NT_THREADS) gemm_tn_tc_kernel(const __grid_con
 // main loop of tile i+1.  L2->SM operand traffic per 128x256x64 block drops from 48 KB to 16 + 32/CM KB.
 // ---------------------------------------------------------------------------------------------------------
 template <int CM, class TO, bool CN>
-__global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB, int nkb,
                                                                      int chunks_per_tap, int s, int tiles_per_batch,
                                                                      int m_tiles, int n_tiles, int nb,
@@ -326,12 +385,15 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
   float* cn_par = reinterpret_cast<float*>(sm + STAGES * (A_BYTES + B_BYTES) + 256);  // [3][256]: bias, gamma, beta (CN)
+  float2* cn_xch = reinterpret_cast<float2*>(cn_par + 3 * BN2);                       // [tile parity][2 halves][128 rows] (mean, M2)
+  unsigned char* stg_all = reinterpret_cast<unsigned char*>(cn_xch + 4 * BM);         // [8 warps][STG_WARP]
 
+  const long long tl_t0 = clock64();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)ptx::cluster_ctarank();
   const int cluster_id = blockIdx.x / CM, num_clusters = gridDim.x / CM;
   if (CN) {
-    for (int i = threadIdx.x; i < BN2; i += NT_THREADS) {
+    for (int i = threadIdx.x; i < BN2; i += NT2_THREADS) {
       cn_par[i] = bias != nullptr ? bias[i] : 0.f; cn_par[BN2 + i] = E.gam[i]; cn_par[2 * BN2 + i] = E.bet[i];
     }
   }
@@ -342,7 +404,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int i = 0; i < STAGES; i++) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], CM); }
-    for (int i = 0; i < 2; i++) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; i++) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 8); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -354,6 +416,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) TL_STAMP(0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -372,6 +435,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
           ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES, c0, tap % s, t0 + tap / s, b);
           if (CM == 1) ptx::tma_load_4d(&tmB, &full[st], smB + st * B_BYTES, kb * BK, n0, 0, 0);
           else ptx::tma_load_4d_mc(&tmB, &full[st], smB + st * B_BYTES + rank * B_SLICE, kb * BK, n0 + rank * (BN2 / CM), 0, 0, MASK);
+          if (it == 0) TL_STAMP(1);
         }
       }
     }
@@ -387,6 +451,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
         for (int kb = 0; kb < nkb; kb++, it++) {
           const int st = it % STAGES, u = it / STAGES;
           ptx::mbar_wait(&full[st], u & 1);
+          if (it == 0) TL_STAMP(2);
           ptx::tc_fence_after();
           const uint32_t a0 = ptx::smem_u32(smA + st * A_BYTES), b0 = ptx::smem_u32(smB + st * B_BYTES);
 #pragma unroll
@@ -399,11 +464,14 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
           else ptx::umma_commit_mc(&empty[st], MASK);
         }
         ptx::umma_commit(&tfull[acc]);
+        TL_STAMP(3);
       }
     }
   } else {
-    const int lg = warp & 3;
+    // epilogue: warp -> TMEM lane quadrant lg = warp % 4 (hardware rule), column half hf = (warp - 2) / 4
+    const int lg = warp & 3, hf = (warp - 2) >> 2;
     const int row = lg * 32 + lane;
+    unsigned char* stg = stg_all + (warp - 2) * STG_WARP;
     int ti = 0;
     for (int gid = cluster_id; gid < total_groups; gid += num_clusters, ti++) {
       const int gm = gid / n_tiles, gn = gid - gm * n_tiles;
@@ -412,57 +480,60 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
       const int t = (mt % tiles_per_batch) * BM + row;
       const int n0 = gn * BN2;
       const bool row_ok = mt < m_tiles && out_row_ok(C, t, n0);
-      TO* crow = static_cast<TO*>(C.p) + (long long)b * C.bs + (long long)t * C.rs + n0;
+      const uint32_t ok = __ballot_sync(0xffffffffu, row_ok);
+      // global address of (first row of this warp, first column of this warp's half)
+      TO* cwarp = static_cast<TO*>(C.p) + (long long)b * C.bs + (long long)(t - lane) * C.rs + n0 + hf * (BN2 / 2);
       const int acc = ti & 1, ua = ti >> 1;
       ptx::mbar_wait(&tfull[acc], ua & 1);
       ptx::tc_fence_after();
+      if (warp == 2 && lane == 0) { if (ti == 0) TL_STAMP(4); TL_STAMP(7); }
+      const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN2 + hf * (BN2 / 2));
       if constexpr (CN) {
         // u = bf16(acc + bias) exactly as the unfused path stores it; statistics and the ReLU mask are taken from the
-        // rounded values so that backward (which re-derives them from the saved u) sees the same numbers.
-        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN2);
-        float sum = 0.f;
+        // rounded values so that backward (which re-derives them from the saved u) sees the same numbers.  Each warp
+        // owns 128 of the 256 channels: shifted one-pass moments per half, merged across the two warps of the quadrant.
+        const float* pb = cn_par + hf * (BN2 / 2);
+        float sd = 0.f, sd2 = 0.f, v0 = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN2; c0 += 32) {
+        for (int c0 = 0; c0 < BN2 / 2; c0 += 32) {
           uint32_t r[32];
           ptx::tmem_ld32(trow + c0, r);
           ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j++) sum += __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]) + cn_par[c0 + j]));
-        }
-        const float mean = sum * (1.f / BN2);
-        float sq = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN2; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld32(trow + c0, r);
-          ptx::tmem_ld_wait();
+          if (c0 == 0) v0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[0]) + pb[0]));
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            const float d = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]) + cn_par[c0 + j])) - mean;
-            sq = fmaf(d, d, sq);
+            const float d = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]) + pb[c0 + j])) - v0;
+            sd += d; sd2 = fmaf(d, d, sd2);
           }
         }
-        const float rstd = rsqrtf(sq * (1.f / (BN2 - 1)) + 1e-5f);
-        const long long roff = (long long)b * C.bs + (long long)t * C.rs;
-        bf16* yrow = E.y != nullptr ? static_cast<bf16*>(E.y) + roff : nullptr;
-        float* zrow = E.z != nullptr ? E.z + ((long long)b * C.rpb + t) * BN2 : nullptr;
+        constexpr float inv_half = 1.f / (BN2 / 2);
+        const float m_mine = v0 + sd * inv_half, q_mine = fmaxf(sd2 - sd * sd * inv_half, 0.f);
+        float2* xch = cn_xch + (ti & 1) * 2 * BM;
+        xch[hf * BM + row] = make_float2(m_mine, q_mine);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");
+        const float2 oth = xch[(hf ^ 1) * BM + row];
+        const float mean = 0.5f * (m_mine + oth.x);
+        const float dm = m_mine - oth.x;
+        const float m2 = q_mine + oth.y + dm * dm * (float)(BN2 / 4);
+        const float rstd = rsqrtf(m2 * (1.f / (BN2 - 1)) + 1e-5f);
+        bf16* ywarp = E.y != nullptr ? static_cast<bf16*>(E.y) + (long long)b * C.bs + (long long)(t - lane) * C.rs + hf * (BN2 / 2) : nullptr;
+        float* zwarp = E.z != nullptr ? E.z + ((long long)b * C.rpb + (t - lane)) * BN2 + hf * (BN2 / 2) : nullptr;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN2; c0 += 32) {
+        for (int c0 = 0; c0 < BN2 / 2; c0 += 32) {
           uint32_t r[32];
           ptx::tmem_ld32(trow + c0, r);
           ptx::tmem_ld_wait();
-          if (row_ok) {
-            float v[32];
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]) + cn_par[c0 + j]));
-            store_out(crow + c0, v);
+          for (int j = 0; j < 32; j++) v[j] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]) + pb[c0 + j]));
+          emit_chunk<bf16>(stg, lane, v, static_cast<bf16*>(static_cast<void*>(cwarp)) + c0, C.rs, ok);
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = fmaxf(fmaf((v[j] - mean) * rstd, cn_par[BN2 + c0 + j], cn_par[2 * BN2 + c0 + j]), 0.f);
-            if (yrow != nullptr) store_out(yrow + c0, v);
-            if (zrow != nullptr) store_out(zrow + c0, v);
-          }
+          for (int j = 0; j < 32; j++) v[j] = fmaxf(fmaf((v[j] - mean) * rstd, pb[BN2 + c0 + j], pb[2 * BN2 + c0 + j]), 0.f);
+          if (ywarp != nullptr) emit_chunk<bf16>(stg, lane, v, ywarp + c0, C.rs, ok);
+          if (zwarp != nullptr) emit_chunk<float>(stg, lane, v, zwarp + c0, (long long)BN2, ok);
         }
-        if (row_ok && yrow != nullptr) {  // zero rows around the window (the conv padding of the next layer)
+        if (row_ok && E.y != nullptr && hf == 0) {  // zero rows around the window (the conv padding of the next layer)
+          bf16* yrow = static_cast<bf16*>(E.y) + (long long)b * C.bs + (long long)t * C.rs;
           for (int pr = 1; pr <= E.pad_rows; pr++) {
             if (t == 0) {
               uint4* z4 = reinterpret_cast<uint4*>(yrow - (long long)pr * C.rs);
@@ -475,39 +546,41 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc2_kernel(const __grid
           }
         }
       } else {
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN2; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN2 + c0), r);
-        ptx::tmem_ld_wait();
-        if (row_ok) {
+        uint32_t r[2][32];
+        ptx::tmem_ld32(trow, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < 4) ptx::tmem_ld32(trow + 32 * (c + 1), r[(c + 1) & 1]);
+          const int cc = hf * (BN2 / 2) + 32 * c;
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[c & 1][j]);
           if (bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] += __ldg(bias + n0 + c0 + j);
+            for (int j = 0; j < 32; j++) v[j] += __ldg(bias + n0 + cc + j);
           }
           if (C.relu) {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
           }
-          store_out(crow + c0, v);
+          emit_chunk<TO>(stg, lane, v, cwarp + 32 * c, C.rs, ok);
         }
-      }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      if (warp == 2 && lane == 0) TL_STAMP(5);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync_all();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 0) TL_STAMP(6);
 }
 
-constexpr size_t nt2_smem() { return (size_t)4 * (BM * BK * 2 + 256 * BK * 2) + 256 + 3 * 256 * 4 + 1024; }
+constexpr size_t nt2_smem() { return (size_t)4 * (BM * BK * 2 + 256 * BK * 2) + 256 + 3 * 256 * 4 + 4 * BM * 8 + 8 * STG_WARP + 1024; }
 
 template <int CM, class TO, bool CN = false>
 int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt, int s, int tpb, int m_tiles, int n_tiles, int nb,
@@ -520,7 +593,7 @@ int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt,
   if (clusters > total_groups) clusters = total_groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CM);
-  cfg.blockDim = dim3(NT_THREADS);
+  cfg.blockDim = dim3(NT2_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -538,7 +611,7 @@ int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt,
 // multicasts them.  4-stage ring, 256 TMEM columns, fp32 red.global.add epilogue.
 // ---------------------------------------------------------------------------------------------------------
 template <int CM>
-__global__ void __launch_bounds__(NT_THREADS, 1) gemm_tn_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(NT2_THREADS, 1) gemm_tn_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB, int kb_total,
                                                                      int kb_per_cta, int kb_per_batch, int b_chunks_per_tap,
                                                                      int b_s, int N1, int N2, float* __restrict__ Cacc, int ldc,
@@ -555,6 +628,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_tn_tc2_kernel(const __grid
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+  unsigned char* stg_all = sm + STAGES * (A_BYTES + B_BYTES) + 256;  // [8 warps][STG_WARP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)ptx::cluster_ctarank();     // == blockIdx.y % CM
@@ -620,32 +694,43 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_tn_tc2_kernel(const __grid
       ptx::umma_commit(acc_full);
     }
   } else if (nkb > 0) {
-    const int lg = warp & 3;
+    // epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves; rows go out as 64-byte runs through the staging buffer
+    const int lg = warp & 3, hf = (warp - 2) >> 2;
     const int n1 = n10 + lg * 32 + lane;
+    unsigned char* stg = stg_all + (warp - 2) * STG_WARP;
+    const uint32_t ok = __ballot_sync(0xffffffffu, n1 < N1);
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN2; c0 += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld32(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
+    const uint32_t trow = tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hf * (BN2 / 2));
+    const bool vec = mode == STORE_PLAIN && (ldc & 3) == 0 && n20 + BN2 <= N2;
+    uint32_t r[2][32];
+    ptx::tmem_ld32(trow, r[0]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
       ptx::tmem_ld_wait();
-      if (n1 < N1) {
-        if (mode == STORE_PLAIN && (ldc & 3) == 0) {  // 16-byte vector reductions: 4x fewer L2 atomic operations
-          float* dst = Cacc + (long long)n1 * ldc + n20 + c0;
+      if (c + 1 < 4) ptx::tmem_ld32(trow + 32 * (c + 1), r[(c + 1) & 1]);
+      const int c0 = hf * (BN2 / 2) + 32 * c;
+      if (vec) {  // 16-byte vector reductions, 8 rows x 64 B per instruction
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
-                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
-        } else {
+        for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[c & 1][j]);
+        float* gwarp = Cacc + (long long)(n1 - lane) * ldc + n20 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const int n2 = n20 + c0 + j;
-            if (n2 < N2) {
-              long long o;
-              if (mode == STORE_CONV_W) { const int tap = n2 / Ci, ci = n2 - tap * Ci; o = ((long long)n1 * Ci + ci) * taps + tap; }
-              else o = (long long)n1 * ldc + n2;
-              atomicAdd(Cacc + o, __uint_as_float(r[j]));
-            }
+        for (int sub = 0; sub < 2; sub++) {
+          stage_put(stg + lane * STG_RS, v, sub, static_cast<float*>(nullptr));
+          __syncwarp();
+          stage_flush_red(stg, gwarp + 16 * sub, (long long)ldc, ok, lane);
+          __syncwarp();
+        }
+      } else if (n1 < N1) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int n2 = n20 + c0 + j;
+          if (n2 < N2) {
+            long long o;
+            if (mode == STORE_CONV_W) { const int tap = n2 / Ci, ci = n2 - tap * Ci; o = ((long long)n1 * Ci + ci) * taps + tap; }
+            else o = (long long)n1 * ldc + n2;
+            atomicAdd(Cacc + o, __uint_as_float(r[c & 1][j]));
           }
         }
       }
@@ -714,6 +799,11 @@ int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void
   return 0;
 }
 
+int debug_gemm_timeline(unsigned long long* host_out) {
+  CPC_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_nt2_tl, sizeof(unsigned long long) * 148 * 8));
+  return 0;
+}
+
 int gemm_nt_cnorm_tc(int nb, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C, const CNormEpi& E,
                      cudaStream_t st, bool* handled) {
   *handled = false;
@@ -764,11 +854,11 @@ int gemm_tn_tc(int nb, int N1, int N2, const RowView& A, const RowView& B, float
     const int kpc = (kb_total + sp - 1) / sp;
     sp = (kb_total + kpc - 1) / kpc;
     auto k2 = gemm_tn_tc2_kernel<2>;
-    const size_t smem2 = (size_t)4 * (2 * 8192 + 4 * 8192) + 256 + 1024;
+    const size_t smem2 = (size_t)4 * (2 * 8192 + 4 * 8192) + 256 + 8 * STG_WARP + 1024;
     CPC_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(N2 / 256, N1 / BM, sp);
-    cfg.blockDim = dim3(NT_THREADS);
+    cfg.blockDim = dim3(NT2_THREADS);
     cfg.dynamicSmemBytes = smem2;
     cfg.stream = st;
     cudaLaunchAttribute at[1];

@@ -158,6 +158,13 @@ int cpcb200_test_gemm_nt(int dtype, int M, int N, int Kd, const void* A, const v
                          float* C, void* stream);
 int cpcb200_test_gemm_tn(int dtype, int M, int N1, int N2, const void* A, const void* B, float* C,
                          void* stream);
+/* same product with C in the activation dtype (bf16 when dtype == CPCB200_BF16), as the conv layers store it */
+int cpcb200_test_gemm_nt_act(int dtype, int M, int N, int Kd, const void* A, const void* B, const float* bias,
+                             void* C, void* stream);
+/* debug: per-CTA cycle stamps (148 x 8 uint64, relative to each CTA's start) of the last persistent NT GEMM launch:
+ * [0] prologue done, [1] first TMA issued, [2] first operands landed, [3] last MMA committed, [4] first accumulator
+ * ready, [5] last epilogue done, [6] teardown done, [7] last accumulator ready.  Synchronises the device. */
+int cpcb200_debug_gemm_timeline(unsigned long long* host_out);
 
 #ifdef __cplusplus
 }
