@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cpcb200 {
@@ -123,6 +124,19 @@ int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowVie
     if (handled) return 0;
   }
   return gemm_tn_simt(bf16_in, nb, N1, N2, A, B, Cacc, ldc, mode, Ci, taps, st);
+}
+
+int gemm_tn_group_tc(int n, const TnDesc* d, cudaStream_t st, bool* handled);
+int gemm_tn_group(bool bf16_in, int n, const TnDesc* d, cudaStream_t st) {
+  static const bool off = []() { const char* e = getenv("CPC_B200_TN_GROUP"); return e && atoi(e) == 0; }();
+  if (bf16_in && n > 1 && !off) {
+    bool handled = false;
+    CPC_TRY(gemm_tn_group_tc(n, d, st, &handled));
+    if (handled) return 0;
+  }
+  for (int i = 0; i < n; i++)
+    CPC_TRY(gemm_tn(bf16_in, d[i].nb, d[i].N1, d[i].N2, d[i].A, d[i].B, d[i].Cacc, d[i].ldc, d[i].mode, d[i].Ci, d[i].taps, st));
+  return 0;
 }
 
 // torch.optim.Adam (non-amsgrad) over a flat bucket: cpc/train.py:335-337

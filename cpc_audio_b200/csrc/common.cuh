@@ -216,4 +216,8 @@ int gemm_nt_cnorm_tc(int nb, int Kd, const RowView& A, const void* Bm, const flo
 int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc,
             int mode, int Ci, int taps, cudaStream_t st);
 
+// several independent TN products in one launch (bf16 tensor-core path; falls back to one gemm_tn per problem)
+struct TnDesc { int nb, N1, N2; RowView A, B; float* Cacc; int ldc, mode, Ci, taps; };
+int gemm_tn_group(bool bf16_in, int n, const TnDesc* d, cudaStream_t st);
+
 }  // namespace cpcb200

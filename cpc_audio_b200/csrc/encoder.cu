@@ -637,6 +637,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     prep_w_dgrad_all_kernel<T><<<dim3(H, 4), 256, 0, st>>>(P, H, H);
     CPC_LAUNCHED_N("prep_w_dgrad_all", st);
   }
+  TnDesc wg[4];
   for (int i = 4; i >= 1; i--) {
     const int Lo = g.Lout[i], Lin = g.Lout[i - 1], s = kConvS[i], pp = kConvP[i];
     // ChannelNorm+ReLU backward -> du_i, dgamma_i, dbeta_i, dbias_i
@@ -655,12 +656,12 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
 #undef LAUNCH_CB
       CPC_LAUNCHED_N("cnorm_relu_bwd", st);
     }
-    // weight gradient: dW[co][ci][tap] += sum_{b,t} du[b,t,co] * y_{i-1}[b, s t - p + tap, ci]
+    // weight gradient: dW[co][ci][tap] += sum_{b,t} du[b,t,co] * y_{i-1}[b, s t - p + tap, ci].  The four products are
+    // independent of the rest of the chain: they are collected here and run as ONE grouped launch after the loop.
     {
       RowView A{du[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo};
       RowView Bv{sv + e.y[i - 1] + (size_t)(kPad - pp) * H, (long long)(Lin + 2 * kPad) * H, (long long)s * H, Lo, kConvK[i], s};
-      CPC_TRY(gemm_tn(g.bf16, B, H, kConvK[i] * H, A, Bv, dwp[i], kConvK[i] * H, STORE_PLAIN, 0, 0, st));
-
+      wg[4 - i] = TnDesc{B, H, kConvK[i] * H, A, Bv, dwp[i], kConvK[i] * H, STORE_PLAIN, 0, 0};
     }
     // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r].  All s residues in ONE GEMM with
     // N = s*H: row q of the product is the s consecutive input rows s q - p .. s q - p + s - 1.
@@ -670,6 +671,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       CPC_TRY(gemm_nt(g.bf16, false, B, s * H, 2 * H, A, wd[i], nullptr, C, st));
     }
   }
+  CPC_TRY(gemm_tn_group(g.bf16, 4, wg, st));  // wg[0] = layer 4 ... wg[3] = layer 1
   {  // scratch (Co, k*Ci) layout -> parameter layout (Co, Ci, k), all four layers
     Conv4Ptrs P{};
     for (int i = 1; i < 5; i++) { P.w[i - 1] = dwp[i]; P.acc[i - 1] = gr->conv_w[i]; P.taps[i - 1] = kConvK[i]; P.s[i - 1] = kConvS[i]; }

@@ -14,6 +14,7 @@
 // that one CTA's epilogue overlaps the other's main loop.
 #include <stdlib.h>
 
+#include <cstring>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -610,12 +611,33 @@ int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt,
 // same (n2 tile, row range) and share the B operand: each fetches half of its four [64 rows][64 ch] blocks and
 // multicasts them.  4-stage ring, 256 TMEM columns, fp32 red.global.add epilogue.
 // ---------------------------------------------------------------------------------------------------------
+// Up to four independent problems share one launch ("grouped" split-K): the CTA range of the grid is cut into one
+// slice per problem (TnProblem::cta_begin), so that the small weight-gradient GEMMs of a backward pass fill the SMs the
+// big one leaves idle and pay one launch / prologue / tail instead of four.
+struct TnProblem {
+  int cta_begin, n2_tiles, kb_total, kb_per_cta, kb_per_batch, b_chunks_per_tap, b_s, N1, N2, ldc, mode, Ci, taps;
+  float* Cacc;
+};
+struct TnGroup {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB[4];
+  TnProblem pr[4];
+  int n;
+};
+
 template <int CM>
-__global__ void __launch_bounds__(NT2_THREADS, 1) gemm_tn_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                     const __grid_constant__ CUtensorMap tmB, int kb_total,
-                                                                     int kb_per_cta, int kb_per_batch, int b_chunks_per_tap,
-                                                                     int b_s, int N1, int N2, float* __restrict__ Cacc, int ldc,
-                                                                     int mode, int Ci, int taps) {
+__global__ void __launch_bounds__(NT2_THREADS, 1) gemm_tn_tc2_kernel(const __grid_constant__ TnGroup G) {
+  int pid = 0;
+#pragma unroll
+  for (int i = 1; i < 4; i++)
+    if (i < G.n && (int)blockIdx.x >= G.pr[i].cta_begin) pid = i;
+  const TnProblem& pr = G.pr[pid];
+  const CUtensorMap* tmA = &G.tmA[pid];
+  const CUtensorMap* tmB = &G.tmB[pid];
+  const int kb_total = pr.kb_total, kb_per_cta = pr.kb_per_cta, kb_per_batch = pr.kb_per_batch;
+  const int b_chunks_per_tap = pr.b_chunks_per_tap, b_s = pr.b_s, N1 = pr.N1, N2 = pr.N2, ldc = pr.ldc;
+  const int mode = pr.mode, Ci = pr.Ci, taps = pr.taps;
+  float* __restrict__ Cacc = pr.Cacc;
   constexpr int BN2 = 256, STAGES = 4;
   constexpr uint32_t BLK = 64 * 64 * 2;
   constexpr uint32_t A_BYTES = 2 * BLK, B_BYTES = 4 * BLK;
@@ -631,15 +653,18 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_tn_tc2_kernel(const __gri
   unsigned char* stg_all = sm + STAGES * (A_BYTES + B_BYTES) + 256;  // [8 warps][STG_WARP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)ptx::cluster_ctarank();     // == blockIdx.y % CM
-  const int n20 = blockIdx.x * BN2, n10 = blockIdx.y * BM;
-  const int kb_beg = blockIdx.z * kb_per_cta;
+  const int rank = (int)ptx::cluster_ctarank();     // == n1 tile % CM (consecutive CTAs = consecutive n1 tiles)
+  const int local = (int)blockIdx.x - pr.cta_begin, n1_tiles = N1 / BM;
+  const int n1t = local % n1_tiles, rest = local / n1_tiles;
+  const int n2t = rest % pr.n2_tiles, split = rest / pr.n2_tiles;
+  const int n20 = n2t * BN2, n10 = n1t * BM;
+  const int kb_beg = split * kb_per_cta;
   const int kb_end = min(kb_total, kb_beg + kb_per_cta);
   const int nkb = kb_end - kb_beg;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmA);
-    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(tmA);
+    ptx::prefetch_tmap(tmB);
     for (int i = 0; i < STAGES; i++) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], CM); }
     ptx::mbar_init(acc_full, 1);
     ptx::fence_barrier_init();
@@ -663,14 +688,14 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_tn_tc2_kernel(const __gri
         ptx::mbar_arrive_expect_tx(&full[st], A_BYTES + B_BYTES);
         const int bb = kb / kb_per_batch, r0 = (kb - bb * kb_per_batch) * 64;
 #pragma unroll
-        for (int j = 0; j < 2; j++) ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES + j * BLK, n10 + j * 64, 0, r0, bb);
+        for (int j = 0; j < 2; j++) ptx::tma_load_4d(tmA, &full[st], smA + st * A_BYTES + j * BLK, n10 + j * 64, 0, r0, bb);
 #pragma unroll
         for (int jj = 0; jj < 4 / CM; jj++) {
           const int j = rank * (4 / CM) + jj;
           const int blk = (n20 >> 6) + j;
           const int tap = blk / b_chunks_per_tap, c0 = (blk - tap * b_chunks_per_tap) * 64;
-          if (CM == 1) ptx::tma_load_4d(&tmB, &full[st], smB + st * B_BYTES + j * BLK, c0, tap % b_s, r0 + tap / b_s, bb);
-          else ptx::tma_load_4d_mc(&tmB, &full[st], smB + st * B_BYTES + j * BLK, c0, tap % b_s, r0 + tap / b_s, bb, MASK);
+          if (CM == 1) ptx::tma_load_4d(tmB, &full[st], smB + st * B_BYTES + j * BLK, c0, tap % b_s, r0 + tap / b_s, bb);
+          else ptx::tma_load_4d_mc(tmB, &full[st], smB + st * B_BYTES + j * BLK, c0, tap % b_s, r0 + tap / b_s, bb, MASK);
         }
       }
     }
@@ -831,9 +856,89 @@ int gemm_nt_cnorm_tc(int nb, int Kd, const RowView& A, const void* Bm, const flo
   return 0;
 }
 
+// problems that fit the gen-2 TN kernel (any other shape goes through gemm_tn one by one)
+static bool tn2_fits(const TnDesc& d) {
+  const RowView &A = d.A, &B = d.B;
+  if (A.rpb != B.rpb || A.taps != 1) return false;
+  const int bcin = d.N2 / B.taps;
+  if (d.N1 % 256 != 0 || d.N2 % 256 != 0 || bcin % 64 != 0 || (B.taps > 1 && B.rs != (long long)B.s * bcin)) return false;
+  if ((A.rs % 8) != 0 || (A.bs % 8) != 0 || (B.rs % 8) != 0 || (B.bs % 8) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(A.p) & 15) || (reinterpret_cast<uintptr_t>(B.p) & 15)) return false;
+  return true;
+}
+
+int gemm_tn_group_tc(int n, const TnDesc* d, cudaStream_t st, bool* handled) {
+  *handled = false;
+  static const int gen = []() { const char* e = getenv("CPC_B200_GEMM_GEN"); return e ? atoi(e) : 2; }();
+  if (gen != 2 || n < 1 || n > 4) return 0;
+  for (int i = 0; i < n; i++)
+    if (!tn2_fits(d[i])) return 0;
+  TnGroup G;
+  memset(&G, 0, sizeof(G));
+  G.n = n;
+  long long work = 0;
+  int tiles[4], kbt[4];
+  for (int i = 0; i < n; i++) {
+    CPC_TRY(make_rowview_map(&G.tmA[i], d[i].A, d[i].N1, d[i].nb, 64, true));   // exact row count: rows >= rpb are zero-filled by TMA
+    CPC_TRY(make_rowview_map(&G.tmB[i], d[i].B, d[i].N2, d[i].nb, 64, false));
+    tiles[i] = (d[i].N1 / BM) * (d[i].N2 / 256);
+    kbt[i] = ((d[i].A.rpb + 63) / 64) * d[i].nb;
+    work += (long long)tiles[i] * kbt[i];
+  }
+  // smallest per-CTA k-block count L for which all problems fit one wave of 148 CTAs
+  int L = (int)((work + 147) / 148);
+  if (L < 1) L = 1;
+  for (;; L++) {
+    int ctas = 0;
+    for (int i = 0; i < n; i++) ctas += tiles[i] * ((kbt[i] + L - 1) / L);
+    if (ctas <= 148) break;
+    bool all_one = true;
+    for (int i = 0; i < n; i++) all_one = all_one && (kbt[i] <= L);
+    if (all_one) break;  // more than 148 tiles in total: several waves, no split-K
+  }
+  int cta = 0;
+  for (int i = 0; i < n; i++) {
+    TnProblem& p = G.pr[i];
+    int sp = (kbt[i] + L - 1) / L;
+    const int kpc = (kbt[i] + sp - 1) / sp;
+    sp = (kbt[i] + kpc - 1) / kpc;
+    p.cta_begin = cta;
+    p.n2_tiles = d[i].N2 / 256;
+    p.kb_total = kbt[i];
+    p.kb_per_cta = kpc;
+    p.kb_per_batch = (d[i].A.rpb + 63) / 64;
+    p.b_chunks_per_tap = (d[i].N2 / d[i].B.taps) / 64;
+    p.b_s = d[i].B.s;
+    p.N1 = d[i].N1; p.N2 = d[i].N2; p.ldc = d[i].ldc; p.mode = d[i].mode; p.Ci = d[i].Ci; p.taps = d[i].taps;
+    p.Cacc = d[i].Cacc;
+    cta += tiles[i] * sp;
+  }
+  auto k2 = gemm_tn_tc2_kernel<2>;
+  const size_t smem2 = (size_t)4 * (2 * 8192 + 4 * 8192) + 256 + 8 * STG_WARP + 1024;
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cta);
+  cfg.blockDim = dim3(NT2_THREADS);
+  cfg.dynamicSmemBytes = smem2;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k2, G));
+  CPC_LAUNCHED_N("gemm_tn_tc2", st);
+  *handled = true;
+  return 0;
+}
+
 int gemm_tn_tc(int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode, int Ci, int taps,
                cudaStream_t st, bool* handled) {
   *handled = false;
+  {
+    TnDesc one{nb, N1, N2, A, B, Cacc, ldc, mode, Ci, taps};
+    CPC_TRY(gemm_tn_group_tc(1, &one, st, handled));
+    if (*handled) return 0;
+  }
   constexpr int BN = 128, STAGES = 3;
   if (A.rpb != B.rpb || A.taps != 1) return 0;
   const int bcin = N2 / B.taps;
@@ -845,31 +950,6 @@ int gemm_tn_tc(int nb, int N1, int N2, const RowView& A, const RowView& B, float
   CPC_TRY(make_rowview_map(&tmB, B, N2, nb, 64, false));
   const int kb_per_batch = (A.rpb + 63) / 64;
   const int kb_total = kb_per_batch * nb;
-  static const int gen = []() { const char* e = getenv("CPC_B200_GEMM_GEN"); return e ? atoi(e) : 2; }();
-  if (gen == 2 && N1 % 256 == 0 && N2 % 256 == 0) {
-    const int tiles2 = (N1 / BM) * (N2 / 256);
-    int sp = 148 / tiles2;  // one CTA per SM, a single wave
-    if (sp > kb_total) sp = kb_total;
-    if (sp < 1) sp = 1;
-    const int kpc = (kb_total + sp - 1) / sp;
-    sp = (kb_total + kpc - 1) / kpc;
-    auto k2 = gemm_tn_tc2_kernel<2>;
-    const size_t smem2 = (size_t)4 * (2 * 8192 + 4 * 8192) + 256 + 8 * STG_WARP + 1024;
-    CPC_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(N2 / 256, N1 / BM, sp);
-    cfg.blockDim = dim3(NT2_THREADS);
-    cfg.dynamicSmemBytes = smem2;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k2, tmA, tmB, kb_total, kpc, kb_per_batch, bcin / 64, B.s, N1, N2, Cacc, ldc, mode, Ci, taps));
-    CPC_LAUNCHED_N("gemm_tn_tc2", st);
-    *handled = true;
-    return 0;
-  }
   const int tiles = (N1 / BM) * (N2 / BN);
   int splits = (148 * 2 + tiles - 1) / tiles;
   if (splits > kb_total) splits = kb_total;

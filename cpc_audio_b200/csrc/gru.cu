@@ -505,15 +505,15 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
       else in = reinterpret_cast<const T*>(sv + lay.cT[l - 1]);
       hseq = reinterpret_cast<const T*>(sv + lay.cT[l]);
     }
-    {  // dW_ih += dgi^T . in
-      RowView A{dgi, 0, (long long)G, B * S};
-      RowView Bv2{in, 0, (long long)Hin, B * S};
-      CPC_TRY(gemm_tn(g.bf16, 1, G, Hin, A, Bv2, gr->w_ih[l], Hin, STORE_PLAIN, 0, 0, st));
-    }
-    if (S > 1) {  // dW_hh += sum_{t>=1} dgh_t^T . h_{t-1}
-      RowView A{dgh + G, (long long)S * G, (long long)G, S - 1};
-      RowView Bv2{hseq, (long long)S * Har, (long long)Har, S - 1};
-      CPC_TRY(gemm_tn(g.bf16, B, G, Har, A, Bv2, gr->w_hh[l], Har, STORE_PLAIN, 0, 0, st));
+    {  // dW_ih += dgi^T . in  and  dW_hh += sum_{t>=1} dgh_t^T . h_{t-1}: one grouped launch
+      TnDesc wg[2];
+      int nw = 0;
+      wg[nw++] = TnDesc{1, G, Hin, RowView{dgi, 0, (long long)G, B * S}, RowView{in, 0, (long long)Hin, B * S}, gr->w_ih[l], Hin,
+                        STORE_PLAIN, 0, 0};
+      if (S > 1)
+        wg[nw++] = TnDesc{B, G, Har, RowView{dgh + G, (long long)S * G, (long long)G, S - 1},
+                          RowView{hseq, (long long)S * Har, (long long)Har, S - 1}, gr->w_hh[l], Har, STORE_PLAIN, 0, 0};
+      CPC_TRY(gemm_tn_group(g.bf16, nw, wg, st));
     }
     if (h0l) {  // t = 0 term with the carried hidden state
       const T* h0p;
