@@ -72,6 +72,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_mbar_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void pair_sync(int ub) { asm volatile("bar.sync %0, 64;" ::"r"(ub + 1) : "memory"); }
+// publish barrier (id 5, all 256 threads): producers arrive without blocking, the issuing warp waits
+__device__ __forceinline__ void publish_arrive() { asm volatile("bar.arrive 5, 256;" ::: "memory"); }
+__device__ __forceinline__ void publish_sync() { asm volatile("bar.sync 5, 256;" ::: "memory"); }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -102,7 +105,7 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
 
   __shared__ __align__(128) bf16 hs[2][HAR][BT];  // h_{t-1} as the B operand: [k][sequence]
   __shared__ float part[4][2][6][32];              // partial sums handed to the partner warp, per unit block
-  __shared__ __align__(128) bf16 hstage[2][8][8][BT];  // the 8 new units of one warp, staged for the bulk copies
+  __shared__ __align__(128) bf16 hstage[2][HC][BT];    // the CTA's 64 new units, staged for ONE bulk copy per destination CTA
   __shared__ __align__(8) uint64_t hbar[2];        // hbar[b] completes when buffer b holds a full new state
   constexpr uint32_t kStepBytes = HAR * BT * 2;
   if (threadIdx.x == 0) {
@@ -148,19 +151,37 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
   }
   cluster.sync();
   const uint32_t hs_local = s_u32(&hs[0][0][0]), bar_local = s_u32(&hbar[0]);
+  // lane l < CS of warp 0 delivers to CTA l: its rows of that CTA's hs[0] and that CTA's hbar[0]
+  const uint32_t pub_dst = mapa_u32(hs_local + (uint32_t)(HC * rank * BT * 2), lane < CS ? lane : 0);
+  const uint32_t pub_bar = mapa_u32(bar_local, lane < CS ? lane : 0);
 
+  // per-thread streams (sequence q of this thread): pointers advance by one time step per iteration instead of being
+  // rebuilt from (b, t) with 64-bit multiplies on the critical path; out-of-range sequences alias sequence b0 for loads
+  // and are masked for stores
+  bool okq[2];
+  const bf16* gip[2];
+  float* cptr[2];
+  bf16* ctptr[2];
+  uint2* g4ptr[2];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int bq = b0 + 2 * t4 + q;
+    okq[q] = bq < B;
+    const size_t row0 = (size_t)(okq[q] ? bq : b0) * S;
+    gip[q] = gi + row0 * 3 * HAR + col;
+    cptr[q] = c + row0 * HAR + col;
+    ctptr[q] = cT + row0 * HAR + col;
+    g4ptr[q] = gates4 + row0 * HAR + col;
+  }
   bf16 gq_raw[3][2];
-  auto load_gi = [&](int tt) {
+  auto load_gi = [&]() {
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-      const int bq = b0 + 2 * t4 + q;
-      if (bq < B && tt < S) {
-        const bf16* gp = gi + ((size_t)bq * S + tt) * 3 * HAR + col;
-        gq_raw[0][q] = gp[0]; gq_raw[1][q] = gp[HAR]; gq_raw[2][q] = gp[2 * HAR];
-      } else { gq_raw[0][q] = gq_raw[1][q] = gq_raw[2][q] = __float2bfloat16_rn(0.f); }
+      gq_raw[0][q] = gip[q][0]; gq_raw[1][q] = gip[q][HAR]; gq_raw[2][q] = gip[q][2 * HAR];
+      gip[q] += 3 * HAR;
     }
   };
-  load_gi(0);
+  load_gi();
 
   for (int t = 0; t < S; t++) {
     const int cur = t & 1, nxt = cur ^ 1;
@@ -169,7 +190,7 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
     for (int gt = 0; gt < 3; gt++)
 #pragma unroll
       for (int q = 0; q < 2; q++) gq[gt][q] = __bfloat162float(gq_raw[gt][q]);
-    load_gi(t + 1);  // in flight during this step's product and exchange
+    if (t + 1 < S) load_gi();  // in flight during this step's product and exchange
     if (t > 0) {
       mbar_wait(&hbar[cur], ((t - 1 - (cur ^ 1)) >> 1) & 1);
       if (threadIdx.x == 0 && t + 1 < S) mbar_expect_tx(&hbar[cur], kStepBytes);  // re-arm for step t+2
@@ -205,6 +226,7 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
       }
     pair_sync(ub);
     float hn[2];
+    uint2 sv4[2];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       const float ar = mine[0][q] + part[ub][1 - kh][q][lane];
@@ -216,25 +238,35 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
       const float ng = tanh_fast(gq[2][q] + rg * ghn);
       hn[q] = fmaf(ug, hprev[q] - ng, ng);  // (1-u) n + u h
       hprev[q] = hn[q];
-      const int bq = b0 + 2 * t4 + q;
-      if (bq < B) {
-        const size_t o = ((size_t)bq * S + t) * HAR + col;
-        c[o] = hn[q];
-        cT[o] = __float2bfloat16_rn(hn[q]);
-        gates4[o] = make_uint2(pack_bf16(rg, ug), pack_bf16(ng, ghn));
-        if (hT != nullptr && t == S - 1) hT[(size_t)bq * HAR + col] = hn[q];
-      }
+      sv4[q] = make_uint2(pack_bf16(rg, ug), pack_bf16(ng, ghn));
     }
-    // publish this warp's 8 units: ONE 128-byte bulk copy per destination CTA
+    // publish the CTA's 64 units FIRST (the peers wait for them): every warp parks its 8 units in the staging tile and
+    // arrives on a named barrier; warp 0 waits for all of them and issues ONE 1 KB bulk copy per destination CTA
     if (t + 1 < S) {
-      *reinterpret_cast<uint32_t*>(&hstage[cur][warp][g][2 * t4]) = pack_bf16(hn[0], hn[1]);
+      *reinterpret_cast<uint32_t*>(&hstage[cur][16 * ub + 8 * kh + g][2 * t4]) = pack_bf16(hn[0], hn[1]);
       fence_async_smem();
-      __syncwarp();
-      if (lane < CS) {
-        const uint32_t dst = mapa_u32(hs_local + (uint32_t)(((size_t)nxt * HAR + HC * rank + 16 * ub + 8 * kh) * BT) * 2, lane);
-        bulk_s2s(dst, s_u32(&hstage[cur][warp][0][0]), 8 * BT * 2, mapa_u32(bar_local + nxt * 8, lane));
+      if (warp == 0) {
+        publish_sync();
+        if (lane < CS) bulk_s2s(pub_dst + nxt * (HAR * BT * 2), s_u32(&hstage[cur][0][0]), HC * BT * 2, pub_bar + nxt * 8);
+      } else {
+        publish_arrive();
       }
     }
+    // then the outputs and the gates saved for backward (nobody waits for these)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      if (okq[q]) {
+        *cptr[q] = hn[q];
+        *ctptr[q] = __float2bfloat16_rn(hn[q]);
+        *g4ptr[q] = sv4[q];
+      }
+      cptr[q] += HAR; ctptr[q] += HAR; g4ptr[q] += HAR;
+    }
+  }
+  if (hT != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+      if (okq[q]) hT[(size_t)(b0 + 2 * t4 + q) * HAR + col] = hprev[q];
   }
   cluster.sync();  // nobody leaves while a peer may still be writing into it
 }
@@ -258,9 +290,11 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
   const int ub = warp & 3, kh = warp >> 2;
   const int g = lane >> 2, t4 = lane & 3;
 
-  __shared__ __align__(128) bf16 ds[2][G][BT];  // dgh_t as the B operand: [gate index][sequence]
+  // dgh_t as the B operand, [row][sequence]; row(gate index k) = (u / 64) * 192 + gate * 64 + u % 64 with gate = k / HAR,
+  // u = k % HAR: the 3 x 64 rows a source CTA produces are contiguous, so that it delivers them with ONE bulk copy
+  __shared__ __align__(128) bf16 ds[2][G][BT];
   __shared__ float part[4][2][2][32];
-  __shared__ __align__(128) bf16 dstage[2][8][3][8][BT];
+  __shared__ __align__(128) bf16 dstage[2][3][HC][BT];
   __shared__ __align__(8) uint64_t dbar[2];
   constexpr uint32_t kStepBytes = G * BT * 2;
   if (threadIdx.x == 0) {
@@ -292,6 +326,8 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
   }
   cluster.sync();
   const uint32_t ds_local = s_u32(&ds[0][0][0]), bar_local = s_u32(&dbar[0]);
+  const uint32_t pub_dst = mapa_u32(ds_local + (uint32_t)(3 * HC * rank * BT * 2), lane < CS ? lane : 0);
+  const uint32_t pub_bar = mapa_u32(bar_local, lane < CS ? lane : 0);
 
   // finish step `it`: wait for its exchange, carry = direct + dgh . W_hh[:, slice]
   auto consume = [&](int it) {
@@ -306,7 +342,8 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
 #pragma unroll
     for (int q = 0; q < KSH / 2; q++) {
       uint32_t bq4[4];
-      ldsm_x4_t(bq4, s_u32(&ds[buf][kh * (G / 2) + 32 * q + lane][0]));
+      const int kidx = kh * (G / 2) + 32 * q, gate = kidx / HAR, u = kidx - gate * HAR;
+      ldsm_x4_t(bq4, s_u32(&ds[buf][(u / HC) * 3 * HC + gate * HC + (u % HC) + lane][0]));
       mma16816(acc[q % 3], wf[2 * q], bq4[0], bq4[1]);
       mma16816(acc[(q + 1) % 3], wf[2 * q + 1], bq4[2], bq4[3]);
     }
@@ -322,6 +359,25 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     for (int q = 0; q < 2; q++) carry[q] = direct[q] + keep[q] + part[ub][1 - kh][q][lane];
   };
 
+  // per-thread streams, walking backwards in time (see the forward kernel)
+  bool okq[2];
+  const float* dcp[2];
+  const float* hpp[2];   // h_{t-1}
+  const uint2* g4p[2];
+  bf16* dgip[2];
+  bf16* dghp[2];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int bq = b0 + 2 * t4 + q;
+    okq[q] = bq < B;
+    const size_t last = (size_t)(okq[q] ? bq : b0) * S + (S - 1);
+    dcp[q] = dc + last * HAR + col;
+    hpp[q] = c + last * HAR + col - HAR;
+    g4p[q] = gates4 + last * HAR + col;
+    dgip[q] = dgi + last * G + col;
+    dghp[q] = dgh + last * G + col;
+  }
+
   for (int it = 0; it < S; it++) {
     const int t = S - 1 - it, buf = t & 1;
     // (A) this step's operands: raw loads only, consumed after the previous step's product
@@ -329,24 +385,20 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     uint2 g4[2];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-      const int bq = b0 + 2 * t4 + q;
-      dcv[q] = 0.f; hp[q] = 0.f; g4[q] = make_uint2(0u, 0u);
-      if (bq < B) {
-        const size_t o = ((size_t)bq * S + t) * HAR + col;
-        dcv[q] = dc[o];
-        g4[q] = gates4[o];
-        hp[q] = t > 0 ? c[o - HAR] : (h0 != nullptr ? h0[(size_t)bq * HAR + col] : 0.f);
-      }
+      dcv[q] = *dcp[q];
+      g4[q] = *g4p[q];
+      if (t > 0) hp[q] = *hpp[q];
+      else hp[q] = (h0 != nullptr && okq[q]) ? h0[(size_t)(b0 + 2 * t4 + q) * HAR + col] : 0.f;
+      dcp[q] -= HAR; g4p[q] -= HAR; hpp[q] -= HAR;
     }
     // (B) finish the previous step
     if (it > 0) consume(it - 1);
     // (C) gate gradients of step t, publish dgh_t
-    float dr[2], du[2], dnr[2];
+    float dr[2], du[2], dnr[2], dnv[2];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-      const int bq = b0 + 2 * t4 + q;
-      dr[q] = du[q] = dnr[q] = direct[q] = 0.f;
-      if (bq < B) {
+      dr[q] = du[q] = dnr[q] = dnv[q] = direct[q] = 0.f;
+      if (okq[q]) {
         const float dh = carry[q] + dcv[q];
         const float rg = __uint_as_float(g4[q].x << 16), ug = __uint_as_float(g4[q].x & 0xffff0000u);
         const float ng = __uint_as_float(g4[q].y << 16), hnv = __uint_as_float(g4[q].y & 0xffff0000u);
@@ -354,22 +406,32 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
         du[q] = dh * (hp[q] - ng) * ug * (1.f - ug);
         dr[q] = dn * hnv * rg * (1.f - rg);
         dnr[q] = dn * rg;
+        dnv[q] = dn;
         direct[q] = dh * ug;
         sb[0] += dr[q]; sb[1] += du[q]; sb[2] += dn; sb[3] += dnr[q];
-        const size_t og = ((size_t)bq * S + t) * G + col;
-        dgi[og] = __float2bfloat16_rn(dr[q]); dgi[og + HAR] = __float2bfloat16_rn(du[q]); dgi[og + 2 * HAR] = __float2bfloat16_rn(dn);
-        dgh[og] = __float2bfloat16_rn(dr[q]); dgh[og + HAR] = __float2bfloat16_rn(du[q]); dgh[og + 2 * HAR] = __float2bfloat16_rn(dnr[q]);
       }
     }
-    *reinterpret_cast<uint32_t*>(&dstage[buf][warp][0][g][2 * t4]) = pack_bf16(dr[0], dr[1]);
-    *reinterpret_cast<uint32_t*>(&dstage[buf][warp][1][g][2 * t4]) = pack_bf16(du[0], du[1]);
-    *reinterpret_cast<uint32_t*>(&dstage[buf][warp][2][g][2 * t4]) = pack_bf16(dnr[0], dnr[1]);
+    // publish dgh_t first (the peers wait for it), then write the hoisted-GEMM operands
+    const int urow = 16 * ub + 8 * kh + g;
+    *reinterpret_cast<uint32_t*>(&dstage[buf][0][urow][2 * t4]) = pack_bf16(dr[0], dr[1]);
+    *reinterpret_cast<uint32_t*>(&dstage[buf][1][urow][2 * t4]) = pack_bf16(du[0], du[1]);
+    *reinterpret_cast<uint32_t*>(&dstage[buf][2][urow][2 * t4]) = pack_bf16(dnr[0], dnr[1]);
     fence_async_smem();
-    __syncwarp();
-    if (lane < 3 * CS) {  // lane -> (destination CTA, gate block): one 128-byte bulk copy each
-      const int pr = lane / 3, gt = lane - 3 * pr;
-      const uint32_t dst = mapa_u32(ds_local + (uint32_t)(((size_t)buf * G + gt * HAR + HC * rank + 16 * ub + 8 * kh) * BT) * 2, pr);
-      bulk_s2s(dst, s_u32(&dstage[buf][warp][gt][0][0]), 8 * BT * 2, mapa_u32(bar_local + buf * 8, pr));
+    if (warp == 0) {  // ONE 3 KB bulk copy per destination CTA once all 8 warps have parked their rows
+      publish_sync();
+      if (lane < CS) bulk_s2s(pub_dst + buf * (G * BT * 2), s_u32(&dstage[buf][0][0][0]), 3 * HC * BT * 2, pub_bar + buf * 8);
+    } else {
+      publish_arrive();
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      if (okq[q]) {
+        bf16* pi = dgip[q];
+        bf16* ph = dghp[q];
+        pi[0] = __float2bfloat16_rn(dr[q]); pi[HAR] = __float2bfloat16_rn(du[q]); pi[2 * HAR] = __float2bfloat16_rn(dnv[q]);
+        ph[0] = __float2bfloat16_rn(dr[q]); ph[HAR] = __float2bfloat16_rn(du[q]); ph[2 * HAR] = __float2bfloat16_rn(dnr[q]);
+      }
+      dgip[q] -= G; dghp[q] -= G;
     }
   }
   consume(S - 1);

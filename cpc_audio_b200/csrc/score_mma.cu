@@ -13,6 +13,8 @@
 //                           one 1 KB row per instruction) instead of per-lane atomics;
 //             dpred      += G . cand     accumulated over chunks in registers.
 // The kernel is bound by the L2 gather (N x 512 B per position) and the scatter-add, not by the tensor pipe.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cpcb200 {
@@ -55,6 +57,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // (P, N) <- (B, N, W): a position's N negative rows become contiguous
 __global__ void transpose_ext_kernel(const int* __restrict__ ext, int* __restrict__ ext_t, int B, int N, int W) {
@@ -219,15 +227,21 @@ __global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restri
 // ---------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------
-template <int H>
-__global__ void __launch_bounds__(160) score_bwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
+// RED selects how the dz rows leave the SM:  0 = staged in shared memory, one TMA bulk reduction (1 KB) per row;
+// 1 = red.global.add.v2.f32 straight from the accumulator fragments; 2 = red.global.add.v4.f32 after a lane-pair swap.
+// Both reach the same L2 reduction ceiling (tools/redbench: 5.4 TB/s); without the 16 KB staging tile a warp needs
+// 26 KB of shared memory instead of 42 KB, so 8 warps fit on an SM instead of 5.
+template <int H, int RED>
+__global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
                                                             const int* __restrict__ ext_t, const float* __restrict__ lsebuf,
                                                             const float* __restrict__ dloss, bf16* __restrict__ dpred,
                                                             float* __restrict__ dz, int B, int S, int W, int K, int N,
                                                             int warps_per_cta) {
   using C = Cfg<H>;
   constexpr int GRS = (CH + 8) * 2;     // bytes per row of Gs[16 heads][32 cand]
-  constexpr int STG = 16 * H * 4;       // staging tile [16 rows][H] fp32
+  constexpr int SRS = H * 4 + 32;                 // staging row stride: 32 B pad -> the 8-byte fragment stores of the 8 row
+                                                  // groups fall into distinct banks (an unpadded 1 KB stride is an 8-way conflict)
+  constexpr int STG = RED == 0 ? 16 * SRS : 0;    // staging tile [16 rows][H] fp32
   constexpr int PER_WARP = C::PSM + 2 * C::CBUF + 16 * GRS + STG;
   extern __shared__ __align__(128) unsigned char sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,10 +258,34 @@ __global__ void __launch_bounds__(160) score_bwd_mma_kernel(const bf16* __restri
   const float invH = 1.f / (float)H;
   const float gscale = 1.f / ((float)P * (float)H);
 
-  for (int p = blockIdx.x * warps_per_cta + warp; p < P; p += gridDim.x * warps_per_cta) {
+  // negative-sample rows of a position: lane l holds ext_t[p][32 j + l], j = 0..3 (N = 128); those of the NEXT position are
+  // fetched while the current one is processed, so no index load sits in front of a gather
+  const int pstride = gridDim.x * warps_per_cta;
+  int nidx[NNEG * CH / 32];
+  {
+    const int p0 = blockIdx.x * warps_per_cta + warp;
+#pragma unroll
+    for (int j = 0; j < NNEG * CH / 32; j++) nidx[j] = p0 < P ? ext_t[(size_t)p0 * N + 32 * j + lane] : 0;
+  }
+  auto chunk_rows = [&](const int (&idx)[NNEG * CH / 32], int c) {  // lanes 0..CH-1 get the rows of negative chunk c
+    const int q = (c * CH) >> 5;
+    int v = idx[0];
+#pragma unroll
+    for (int j = 1; j < NNEG * CH / 32; j++) v = (q == j) ? idx[j] : v;
+    return __shfl_sync(0xffffffffu, v, ((c * CH) & 31) + (lane & (CH - 1)));
+  };
+
+  for (int p = blockIdx.x * warps_per_cta + warp; p < P; p += pstride) {
     const int b = p / W, w = p - b * W;
     stage_pred<H>(psm, pred + (size_t)p * K * H, K, lane);
-    int my_row = lane < CH ? ext_t[(size_t)p * N + lane] : 0;
+    int cidx[NNEG * CH / 32];
+#pragma unroll
+    for (int j = 0; j < NNEG * CH / 32; j++) cidx[j] = nidx[j];
+    if (p + pstride < P) {
+#pragma unroll
+      for (int j = 0; j < NNEG * CH / 32; j++) nidx[j] = ext_t[(size_t)(p + pstride) * N + 32 * j + lane];
+    }
+    int my_row = chunk_rows(cidx, 0);
     gather_rows<H>(cbuf, z, my_row, CH, lane);
     cp_async_commit();
     float lse[2][2], gk[2][2];
@@ -271,7 +309,7 @@ __global__ void __launch_bounds__(160) score_bwd_mma_kernel(const bf16* __restri
       if (c + 1 < nchunks) {
         unsigned char* nxt = cbuf + ((c + 1) & 1) * C::CBUF;
         if (c + 1 < nneg) {
-          my_row = lane < CH ? ext_t[(size_t)p * N + (c + 1) * CH + lane] : 0;
+          my_row = chunk_rows(cidx, c + 1);
           gather_rows<H>(nxt, z, my_row, CH, lane);
         } else {
           my_row = b * S + w + 1 + (lane < K ? lane : 0);
@@ -287,29 +325,39 @@ __global__ void __launch_bounds__(160) score_bwd_mma_kernel(const bf16* __restri
       __syncwarp();
       const bool is_pos = c >= nneg;
       const int mts = is_pos ? 1 : MPC;
-      // ---- logits of this chunk: L[mt][nt] ----
-      float L[MPC][2][4];
+      // ---- logits of this chunk: L[mt][nt]; even / odd k-steps accumulate separately (two independent HMMA chains) ----
+      float L[MPC][2][4], L2[MPC][2][4];
 #pragma unroll
       for (int mt = 0; mt < MPC; mt++)
 #pragma unroll
         for (int n = 0; n < 2; n++)
 #pragma unroll
-          for (int e = 0; e < 4; e++) L[mt][n][e] = 0.f;
+          for (int e = 0; e < 4; e++) L[mt][n][e] = L2[mt][n][e] = 0.f;
 #pragma unroll 4
-      for (int ks = 0; ks < C::KS; ks++) {
-        uint32_t bq[4];
+      for (int ks = 0; ks < C::KS; ks += 2) {
+        uint32_t bq[4], bq2[4];
         const int mi = lane >> 3;
         ldsm_x4(bq, s_u32(psm + ((mi >> 1) * 8 + (lane & 7)) * C::RS + (ks * 16 + (mi & 1) * 8) * 2));
+        ldsm_x4(bq2, s_u32(psm + ((mi >> 1) * 8 + (lane & 7)) * C::RS + ((ks + 1) * 16 + (mi & 1) * 8) * 2));
 #pragma unroll
         for (int mt = 0; mt < MPC; mt++) {
           if (mt < mts) {
-            uint32_t a[4];
+            uint32_t a[4], a2[4];
             ldsm_x4(a, s_u32(cur + (mt * 16 + (mi & 1) * 8 + (lane & 7)) * C::RS + (ks * 16 + (mi >> 1) * 8) * 2));
+            ldsm_x4(a2, s_u32(cur + (mt * 16 + (mi & 1) * 8 + (lane & 7)) * C::RS + ((ks + 1) * 16 + (mi >> 1) * 8) * 2));
             mma16816(L[mt][0], a, bq[0], bq[1]);
             mma16816(L[mt][1], a, bq[2], bq[3]);
+            mma16816(L2[mt][0], a2, bq2[0], bq2[1]);
+            mma16816(L2[mt][1], a2, bq2[2], bq2[3]);
           }
         }
       }
+#pragma unroll
+      for (int mt = 0; mt < MPC; mt++)
+#pragma unroll
+        for (int n = 0; n < 2; n++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) L[mt][n][e] += L2[mt][n][e];
       // ---- G = (softmax - onehot) * dloss / (P*H); A fragments for dz and Gs[k][j] for dpred ----
       uint32_t ga[MPC][4];
 #pragma unroll
@@ -337,33 +385,69 @@ __global__ void __launch_bounds__(160) score_bwd_mma_kernel(const bf16* __restri
         ga[mt][3] = pack_bf16(G[1][2], G[1][3]);
       }
       __syncwarp();
-      // ---- dz rows of this chunk: D2[16 j][H] = G^T . pred, staged then added to HBM by the TMA engine ----
+      // ---- dz rows of this chunk: D2[16 j][H] = G^T . pred, added to dz (L2-resident) by reductions ----
 #pragma unroll
       for (int mt = 0; mt < MPC; mt++) {
         if (mt < mts) {
-          if (lane < 16) bulk_wait_read0();  // the staging tile is free again
-          __syncwarp();
-#pragma unroll 4
-          for (int np = 0; np < C::KS; np++) {
-            uint32_t bq[4];
+          if constexpr (RED == 0) {
+            if (lane < 16) bulk_wait_read0();  // the staging tile is free again
+            __syncwarp();
+            // the B fragments of step np + 1 are fetched before the products of step np (no LDSM latency in front of an HMMA)
             const int mi = lane >> 3;
-            ldsm_x4_t(bq, s_u32(psm + ((mi & 1) * 8 + (lane & 7)) * C::RS + (np * 16 + (mi >> 1) * 8) * 2));
-            float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-            mma16816(o0, ga[mt], bq[0], bq[1]);
-            mma16816(o1, ga[mt], bq[2], bq[3]);
-            float* r0 = reinterpret_cast<float*>(stg) + (size_t)g * H + np * 16 + 2 * t;
-            float* r1 = r0 + 8 * H;
-            *reinterpret_cast<float2*>(r0) = make_float2(o0[0], o0[1]);
-            *reinterpret_cast<float2*>(r1) = make_float2(o0[2], o0[3]);
-            *reinterpret_cast<float2*>(r0 + 8) = make_float2(o1[0], o1[1]);
-            *reinterpret_cast<float2*>(r1 + 8) = make_float2(o1[2], o1[3]);
-          }
-          fence_async_smem();
-          __syncwarp();
-          const int drow = __shfl_sync(0xffffffffu, cur_row, (mt * 16 + lane) & 31);
-          if (lane < 16 && (!is_pos || lane < K)) {
-            bulk_reduce_add_f32(dz + (size_t)drow * H, s_u32(stg + (size_t)lane * H * 4), H * 4);
-            bulk_commit();
+            const uint32_t pbase = s_u32(psm + ((mi & 1) * 8 + (lane & 7)) * C::RS + ((mi >> 1) * 8) * 2);
+            uint32_t bqq[2][4];
+            ldsm_x4_t(bqq[0], pbase);
+#pragma unroll
+            for (int np = 0; np < C::KS; np++) {
+              if (np + 1 < C::KS) ldsm_x4_t(bqq[(np + 1) & 1], pbase + (np + 1) * 32);
+              const uint32_t (&bq)[4] = bqq[np & 1];
+              float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+              mma16816(o0, ga[mt], bq[0], bq[1]);
+              mma16816(o1, ga[mt], bq[2], bq[3]);
+              float* r0 = reinterpret_cast<float*>(stg + (size_t)g * SRS) + np * 16 + 2 * t;
+              float* r1 = reinterpret_cast<float*>(stg + (size_t)(g + 8) * SRS) + np * 16 + 2 * t;
+              *reinterpret_cast<float2*>(r0) = make_float2(o0[0], o0[1]);
+              *reinterpret_cast<float2*>(r1) = make_float2(o0[2], o0[3]);
+              *reinterpret_cast<float2*>(r0 + 8) = make_float2(o1[0], o1[1]);
+              *reinterpret_cast<float2*>(r1 + 8) = make_float2(o1[2], o1[3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            const int drow = __shfl_sync(0xffffffffu, cur_row, (mt * 16 + lane) & 31);
+            if (lane < 16 && (!is_pos || lane < K)) {
+              bulk_reduce_add_f32(dz + (size_t)drow * H, s_u32(stg + (size_t)lane * SRS), H * 4);
+              bulk_commit();
+            }
+          } else {
+            // accumulator rows g and g + 8 of the m-tile are candidates mt*16 + g and mt*16 + g + 8
+            const int row_lo = __shfl_sync(0xffffffffu, cur_row, mt * 16 + g);
+            const int row_hi = __shfl_sync(0xffffffffu, cur_row, mt * 16 + g + 8);
+            const bool ok_lo = !is_pos || g < K, ok_hi = !is_pos || g + 8 < K;
+            float* d_lo = dz + (size_t)row_lo * H;
+            float* d_hi = dz + (size_t)row_hi * H;
+#pragma unroll 4
+            for (int np = 0; np < C::KS; np++) {
+              uint32_t bq[4];
+              const int mi = lane >> 3;
+              ldsm_x4_t(bq, s_u32(psm + ((mi & 1) * 8 + (lane & 7)) * C::RS + (np * 16 + (mi >> 1) * 8) * 2));
+              float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+              mma16816(o0, ga[mt], bq[0], bq[1]);
+              mma16816(o1, ga[mt], bq[2], bq[3]);
+              if constexpr (RED == 1) {
+                const int cc = np * 16 + 2 * t;
+                if (ok_lo) { red_add_v2(d_lo + cc, o0[0], o0[1]); red_add_v2(d_lo + cc + 8, o1[0], o1[1]); }
+                if (ok_hi) { red_add_v2(d_hi + cc, o0[2], o0[3]); red_add_v2(d_hi + cc + 8, o1[2], o1[3]); }
+              } else {
+                // even lanes of a pair take row g, odd lanes row g + 8: four consecutive columns each
+                const bool odd = t & 1;
+                const float s0 = odd ? o0[0] : o0[2], s1 = odd ? o0[1] : o0[3], s2 = odd ? o1[0] : o1[2], s3 = odd ? o1[1] : o1[3];
+                const float q0 = __shfl_xor_sync(0xffffffffu, s0, 1), q1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                const float q2 = __shfl_xor_sync(0xffffffffu, s2, 1), q3 = __shfl_xor_sync(0xffffffffu, s3, 1);
+                const int cc = np * 16 + 2 * (t & 2);
+                if (!odd) { if (ok_lo) { red_add_v4(d_lo + cc, o0[0], o0[1], q0, q1); red_add_v4(d_lo + cc + 8, o1[0], o1[1], q2, q3); } }
+                else { if (ok_hi) { red_add_v4(d_hi + cc, q0, q1, o0[2], o0[3]); red_add_v4(d_hi + cc + 8, q2, q3, o1[2], o1[3]); } }
+              }
+            }
           }
         }
       }
@@ -394,11 +478,13 @@ __global__ void __launch_bounds__(160) score_bwd_mma_kernel(const bf16* __restri
       if (g + 8 < K) *reinterpret_cast<uint32_t*>(dp + (size_t)(g + 8) * H + d) = pack_bf16(d1[n][2], d1[n][3]);
     }
   }
-  if (lane < 16) bulk_wait0();
+  if (RED == 0 && lane < 16) bulk_wait0();
 }
 
 template <int H> constexpr size_t fwd_warp_smem() { return Cfg<H>::PSM + 2 * Cfg<H>::CBUF; }
-template <int H> constexpr size_t bwd_warp_smem() { return Cfg<H>::PSM + 2 * Cfg<H>::CBUF + 16 * (CH + 8) * 2 + 16 * H * 4; }
+template <int H, int RED> constexpr size_t bwd_warp_smem() {
+  return Cfg<H>::PSM + 2 * Cfg<H>::CBUF + 16 * (CH + 8) * 2 + (RED == 0 ? 16 * (H * 4 + 32) : 0);
+}
 
 template <int H>
 int launch_fwd(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf, float* corrbuf, float* lsebuf, int B, int S,
@@ -411,16 +497,25 @@ int launch_fwd(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf
   CPC_LAUNCHED_N("score_fwd_mma", st);
   return 0;
 }
+template <int H, int RED>
+int launch_bwd_red(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred, float* dz,
+                   int B, int S, int W, int K, int N, cudaStream_t st) {
+  int wpc = (int)((216 * 1024) / bwd_warp_smem<H, RED>());
+  const int cap = RED == 0 ? 5 : 8;
+  if (wpc > cap) wpc = cap;
+  const size_t smem = wpc * bwd_warp_smem<H, RED>();
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(score_bwd_mma_kernel<H, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  score_bwd_mma_kernel<H, RED><<<148, wpc * 32, smem, st>>>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, wpc);
+  CPC_LAUNCHED_N("score_bwd_mma", st);
+  return 0;
+}
 template <int H>
 int launch_bwd(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred, float* dz,
                int B, int S, int W, int K, int N, cudaStream_t st) {
-  int wpc = (int)((216 * 1024) / bwd_warp_smem<H>());
-  if (wpc > 5) wpc = 5;
-  const size_t smem = wpc * bwd_warp_smem<H>();
-  CPC_CHECK_CUDA(cudaFuncSetAttribute(score_bwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  score_bwd_mma_kernel<H><<<148, wpc * 32, smem, st>>>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, wpc);
-  CPC_LAUNCHED_N("score_bwd_mma", st);
-  return 0;
+  static const int red = []() { const char* e = getenv("CPC_B200_SCORE_RED"); return e ? atoi(e) : 0; }();
+  if (red == 0) return launch_bwd_red<H, 0>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
+  if (red == 1) return launch_bwd_red<H, 1>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
+  return launch_bwd_red<H, 2>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
 }
 
 }  // namespace
