@@ -48,6 +48,11 @@ void prof_note(const char* name, cudaStream_t st) {
   g_prof_last = e;
 }
 
+bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("CPC_B200_PDL"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -142,6 +147,8 @@ int gemm_tn_group(bool bf16_in, int n, const TnDesc* d, cudaStream_t st) {
 // torch.optim.Adam (non-amsgrad) over a flat bucket: cpc/train.py:335-337
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             size_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  pdl_wait();
+  pdl_trigger();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float gi = g[i];
     const float pi = p[i];
@@ -340,8 +347,8 @@ int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   size_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                                              eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+  CPC_CHECK_CUDA(launch_k(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                          beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2)));
   CPC_LAUNCHED_N("adam", st);
   return 0;
 }

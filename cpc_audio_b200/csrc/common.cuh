@@ -78,6 +78,46 @@ struct Carver {
   bool ok() const { return off <= cap; }
 };
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// Every kernel of the library calls pdl_wait() before its first access to global memory - it returns once the previous
+// kernel in the stream has completed and flushed - and pdl_trigger() right after it: the NEXT kernel may then be scheduled
+// while this one runs, so its launch latency and prologue (barrier init, TMEM allocation, descriptor prefetch) overlap
+// this kernel instead of following it.  Wait-then-trigger keeps at most two kernels in flight, so code in front of the
+// wait may only race with the immediately preceding kernel.  Kernels launched through launch_k() carry the
+// stream-serialization attribute that arms this; with CPC_B200_PDL=0 (or a plain <<<>>> launch) both instructions are
+// no-ops and the stream order is the classic one.
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// launch `kern` on `st`; cluster_x > 1 adds a cluster dimension
+template <class... KA, class... A>
+inline cudaError_t launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+  }
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    n++;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+#endif
+
 // ---- device helpers ---------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 typedef __nv_bfloat16 bf16;

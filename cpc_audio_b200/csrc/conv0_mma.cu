@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(128, 3) conv0_fwd_mma_kernel(const float* __re
                                                              const float* __restrict__ bias, const float* __restrict__ gam,
                                                              const float* __restrict__ bet, bf16* __restrict__ y, int B, int L,
                                                              int L0) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int NT = H / 8, RS = 2 * H + 16;
   extern __shared__ __align__(16) unsigned char sm[];
   float* gb = reinterpret_cast<float*>(sm);                       // gamma[H], beta[H]
@@ -216,6 +218,8 @@ __global__ void __launch_bounds__(128, 2) conv0_bwd_du_mma_kernel(const float* _
                                                                 const float* __restrict__ bet, bf16* __restrict__ dy,
                                                                 float* __restrict__ dbias, float* __restrict__ dgam,
                                                                 float* __restrict__ dbet, int B, int L, int L0) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int NT = H / 8, RS = 2 * H + 16, TILE = 16 * RS;
   extern __shared__ __align__(16) unsigned char sm[];
   float* gb = reinterpret_cast<float*>(sm);           // gamma[H], beta[H]
@@ -341,6 +345,8 @@ __global__ void __launch_bounds__(128, 2) conv0_bwd_du_mma_kernel(const float* _
 template <int H>
 __global__ void __launch_bounds__(128) conv0_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ du,
                                                                float* __restrict__ dw, int B, int L, int L0) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int MT = H / 16, RS = 2 * H + 16, TILE = 16 * RS;
   extern __shared__ __align__(16) unsigned char sm[];
   float* accs = reinterpret_cast<float*>(sm);  // [H][10]
@@ -436,6 +442,8 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
                       const float* __restrict__ gam, const float* __restrict__ bet, bf16* __restrict__ dy,
                       float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ dgam, float* __restrict__ dbet,
                       int B, int L, int L0) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int NW = H / 64, NTHR = NW * 32, RS = 2 * H + 16, TILE = kFT * RS, SEGS = H / 8;
   extern __shared__ __align__(16) unsigned char sm[];
   float* gb = reinterpret_cast<float*>(sm);                                    // gamma[H], beta[H]
@@ -686,7 +694,7 @@ int launch_all_fwd(const float* x, const float* w, const float* bias, const floa
   int blocks = (B * (L0 / 16) + 3) / 4;
   if (blocks > 148 * 3) blocks = 148 * 3;
   CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_fwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv0_fwd_mma_kernel<H><<<blocks, 128, smem, st>>>(x, w, bias, gam, bet, y, B, L, L0);
+  CPC_CHECK_CUDA(launch_k(conv0_fwd_mma_kernel<H>, dim3(blocks), dim3(128), smem, st, 1, x, w, bias, gam, bet, y, B, L, L0));
   CPC_LAUNCHED_N("conv0_fwd_mma", st);
   return 0;
 }
@@ -701,17 +709,17 @@ int launch_all_bwd(const float* x, const float* w, const float* bias, const floa
     int blocks2 = B * (L0 / kFT);
     if (blocks2 > 148 * 2) blocks2 = 148 * 2;
     CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd2_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv0_bwd2_mma_kernel<H><<<blocks2, H / 2, smem, st>>>(x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0);
+    CPC_CHECK_CUDA(launch_k(conv0_bwd2_mma_kernel<H>, dim3(blocks2), dim3(H / 2), smem, st, 1, x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0));
     CPC_LAUNCHED_N("conv0_bwd2_mma", st);
     return 0;
   }
   int blocks = (B * (L0 / 16) + 3) / 4;
   if (blocks > 148 * 3) blocks = 148 * 3;
   CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd_du_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-  conv0_bwd_du_mma_kernel<H><<<blocks, 128, smem1, st>>>(x, w, bias, gam, bet, dy, dbias, dgam, dbet, B, L, L0);
+  CPC_CHECK_CUDA(launch_k(conv0_bwd_du_mma_kernel<H>, dim3(blocks), dim3(128), smem1, st, 1, x, w, bias, gam, bet, dy, dbias, dgam, dbet, B, L, L0));
   CPC_LAUNCHED_N("conv0_bwd_du_mma", st);
   CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_wgrad_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  conv0_wgrad_mma_kernel<H><<<blocks, 128, smem2, st>>>(x, dy, dw, B, L, L0);
+  CPC_CHECK_CUDA(launch_k(conv0_wgrad_mma_kernel<H>, dim3(blocks), dim3(128), smem2, st, 1, x, dy, dw, B, L, L0));
   CPC_LAUNCHED_N("conv0_wgrad_mma", st);
   return 0;
 }

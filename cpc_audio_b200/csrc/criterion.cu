@@ -37,6 +37,8 @@ constexpr int KMAX = 16;
 
 __global__ void ext_idx_kernel(const long long* __restrict__ bi, const long long* __restrict__ si, int* __restrict__ ext,
                                long long n, int W, int S) {
+  pdl_wait();
+  pdl_trigger();
   const unsigned nn = (unsigned)n;  // n < 2^31 (checked on the host): 32-bit index arithmetic
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) {
     const unsigned w = i % (unsigned)W;
@@ -125,6 +127,8 @@ __global__ void score_fwd_kernel(const T* __restrict__ pred, const T* __restrict
 // deterministic mean over positions: out[k] = sum_p buf[p][k] / P
 __global__ void mean_over_positions_kernel(const float* __restrict__ a, const float* __restrict__ bq, float* __restrict__ oa,
                                            float* __restrict__ ob, int P, int K) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s1[256], s2[256];
   const int k = blockIdx.x;
   float x = 0.f, y = 0.f;
@@ -272,7 +276,7 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
       int* ext_t = reinterpret_cast<int*>(sv + lay.ext_t);
       CPC_TRY(score_transpose_ext(ext, ext_t, B, N, W, st));
       CPC_TRY(score_fwd_mma(pred, zp, ext_t, lossbuf, corrbuf, lse, B, S, W, H, K, N, st));
-      mean_over_positions_kernel<<<K, 256, 0, st>>>(lossbuf, corrbuf, losses, acc, P, K);
+      CPC_CHECK_CUDA(launch_k(mean_over_positions_kernel, dim3(K), dim3(256), 0, st, 1, lossbuf, corrbuf, losses, acc, P, K));
       CPC_LAUNCHED_N("mean_over_positions", st);
       return 0;
     }
@@ -351,7 +355,8 @@ int sample_ext_idx(const Geo& g, const int64_t* bi, const int64_t* si, int32_t* 
   const long long n = (long long)g.B * g.N * g.W;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  ext_idx_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(bi), reinterpret_cast<const long long*>(si), ext, n, g.W, g.S);
+  CPC_CHECK_CUDA(launch_k(ext_idx_kernel, dim3(blocks), dim3(256), 0, st, 1, reinterpret_cast<const long long*>(bi),
+                          reinterpret_cast<const long long*>(si), ext, n, g.W, g.S));
   CPC_LAUNCHED_N("ext_idx", st);
   return 0;
 }

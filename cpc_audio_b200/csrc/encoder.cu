@@ -314,6 +314,8 @@ template <int I, class T>
 __global__ void __launch_bounds__(256) cnorm_relu_fwd_kernel(const T* __restrict__ u, const float* __restrict__ gam,
                                                               const float* __restrict__ bet, T* __restrict__ y,
                                                               float* __restrict__ zout, int B, int Lc, int H) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long rows = (long long)B * Lc;
@@ -452,6 +454,8 @@ __global__ void __launch_bounds__(256, (I <= 2 ? 2 : 1)) cnorm_relu_bwd_kernel(c
                                                                  T* __restrict__ du, float* __restrict__ dgam,
                                                                  float* __restrict__ dbet, float* __restrict__ dbias, int B,
                                                                  int Lc, int H) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int kCbR = I <= 2 ? 4 : 2;
   extern __shared__ __align__(16) float red[];  // [8 warps][3][H]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -505,6 +509,8 @@ struct Conv4Ptrs { const float* w[4]; void* out[4]; float* acc[4]; int taps[4]; 
 // writes Wp[co][tap*Ci + ci] coalesced over ci
 template <class T>
 __global__ void prep_w_fwd_all_kernel(Conv4Ptrs P, int Ci) {
+  pdl_wait();
+  pdl_trigger();
   const int l = blockIdx.y, co = blockIdx.x, taps = P.taps[l];
   const float* w = P.w[l] + (size_t)co * Ci * taps;
   T* wp = static_cast<T*>(P.out[l]) + (size_t)co * Ci * taps;
@@ -515,6 +521,8 @@ __global__ void prep_w_fwd_all_kernel(Conv4Ptrs P, int Ci) {
 // dgrad GEMM weights: block (ci, layer), thread co: Wd[r][ci][half*Co + co] = W[co][ci][r + s*(1-half)]
 template <class T>
 __global__ void prep_w_dgrad_all_kernel(Conv4Ptrs P, int Co, int Ci) {
+  pdl_wait();
+  pdl_trigger();
   const int l = blockIdx.y, ci = blockIdx.x, taps = P.taps[l], s = P.s[l];
   T* wd = static_cast<T*>(P.out[l]);
   for (int co = threadIdx.x; co < Co; co += blockDim.x) {
@@ -527,6 +535,8 @@ __global__ void prep_w_dgrad_all_kernel(Conv4Ptrs P, int Co, int Ci) {
 }
 // dW[co][ci][tap] += scratch[co][tap*Ci + ci]: block (co, layer), thread ci
 __global__ void permute_add_wgrad_all_kernel(Conv4Ptrs P, int Ci) {
+  pdl_wait();
+  pdl_trigger();
   const int l = blockIdx.y, co = blockIdx.x, taps = P.taps[l];
   const float* sc = P.w[l] + (size_t)co * Ci * taps;
   float* dw = P.acc[l] + (size_t)co * Ci * taps;
@@ -565,7 +575,7 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   {
     Conv4Ptrs P{};
     for (int i = 1; i < 5; i++) { P.w[i - 1] = p->conv_w[i]; P.out[i - 1] = wp[i]; P.taps[i - 1] = kConvK[i]; P.s[i - 1] = kConvS[i]; }
-    prep_w_fwd_all_kernel<T><<<dim3(H, 4), 256, 0, st>>>(P, H);
+    CPC_CHECK_CUDA(launch_k(prep_w_fwd_all_kernel<T>, dim3(H, 4), dim3(256), 0, st, 1, P, H));
     CPC_LAUNCHED_N("prep_w_fwd_all", st);
   }
   // the zero rows around every window of y0..y3 are written by the kernels that produce the interior
@@ -603,7 +613,7 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     CPC_TRY(gemm_nt(g.bf16, false, B, H, kConvK[i] * H, A, wp[i], p->conv_b[i], C, st));
     const long long rows = (long long)B * Lo;
     const int blocks = (int)((rows * 32 + 255) / 256);
-#define LAUNCH_CN(II) cnorm_relu_fwd_kernel<II, T><<<blocks, 256, 0, st>>>(sv + e.u[i], p->norm_w[i], p->norm_b[i], yo, zo, B, Lo, H)
+#define LAUNCH_CN(II) CPC_CHECK_CUDA(launch_k(cnorm_relu_fwd_kernel<II, T>, dim3(blocks), dim3(256), 0, st, 1, sv + e.u[i], p->norm_w[i], p->norm_b[i], yo, zo, B, Lo, H))
     if (I == 1) LAUNCH_CN(1); else if (I == 2) LAUNCH_CN(2); else if (I == 3) LAUNCH_CN(3); else LAUNCH_CN(4);
 #undef LAUNCH_CN
     CPC_LAUNCHED_N("cnorm_relu_fwd", st);
@@ -634,7 +644,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   {
     Conv4Ptrs P{};
     for (int i = 1; i < 5; i++) { P.w[i - 1] = p->conv_w[i]; P.out[i - 1] = wd[i]; P.taps[i - 1] = kConvK[i]; P.s[i - 1] = kConvS[i]; }
-    prep_w_dgrad_all_kernel<T><<<dim3(H, 4), 256, 0, st>>>(P, H, H);
+    CPC_CHECK_CUDA(launch_k(prep_w_dgrad_all_kernel<T>, dim3(H, 4), dim3(256), 0, st, 1, P, H, H));
     CPC_LAUNCHED_N("prep_w_dgrad_all", st);
   }
   TnDesc wg[4];
@@ -649,8 +659,8 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       if (blocks < 1) blocks = 1;
       const size_t smem = 8 * 3 * (size_t)H * sizeof(float);
 #define LAUNCH_CB(II, TD, SRC)                                                                                       \
-  cnorm_relu_bwd_kernel<II, TD, T><<<blocks, 256, smem, st>>>(SRC, sv + e.u[i], p->norm_w[i], p->norm_b[i], du[i],  \
-                                                              gr->norm_w[i], gr->norm_b[i], gr->conv_b[i], B, Lo, H)
+  CPC_CHECK_CUDA(launch_k(cnorm_relu_bwd_kernel<II, TD, T>, dim3(blocks), dim3(256), smem, st, 1, SRC, sv + e.u[i], p->norm_w[i], \
+                          p->norm_b[i], du[i], gr->norm_w[i], gr->norm_b[i], gr->conv_b[i], B, Lo, H))
       if (i == 4) { if (I == 1) LAUNCH_CB(1, float, dz); else if (I == 2) LAUNCH_CB(2, float, dz); else if (I == 3) LAUNCH_CB(3, float, dz); else LAUNCH_CB(4, float, dz); }
       else { if (I == 1) LAUNCH_CB(1, T, dy[i]); else if (I == 2) LAUNCH_CB(2, T, dy[i]); else if (I == 3) LAUNCH_CB(3, T, dy[i]); else LAUNCH_CB(4, T, dy[i]); }
 #undef LAUNCH_CB
@@ -675,7 +685,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   {  // scratch (Co, k*Ci) layout -> parameter layout (Co, Ci, k), all four layers
     Conv4Ptrs P{};
     for (int i = 1; i < 5; i++) { P.w[i - 1] = dwp[i]; P.acc[i - 1] = gr->conv_w[i]; P.taps[i - 1] = kConvK[i]; P.s[i - 1] = kConvS[i]; }
-    permute_add_wgrad_all_kernel<<<dim3(H, 4), 256, 0, st>>>(P, H);
+    CPC_CHECK_CUDA(launch_k(permute_add_wgrad_all_kernel, dim3(H, 4), dim3(256), 0, st, 1, P, H));
     CPC_LAUNCHED_N("permute_add_wgrad_all", st);
   }
   bool c0_done = false;

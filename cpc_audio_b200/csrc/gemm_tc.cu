@@ -393,11 +393,6 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)ptx::cluster_ctarank();
   const int cluster_id = blockIdx.x / CM, num_clusters = gridDim.x / CM;
-  if (CN) {
-    for (int i = threadIdx.x; i < BN2; i += NT2_THREADS) {
-      cn_par[i] = bias != nullptr ? bias[i] : 0.f; cn_par[BN2 + i] = E.gam[i]; cn_par[2 * BN2 + i] = E.bet[i];
-    }
-  }
   const int m_groups = (m_tiles + CM - 1) / CM;
   const int total_groups = m_groups * n_tiles;
 
@@ -411,6 +406,14 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
   if (warp == 1) {
     ptx::tmem_alloc(tmem_holder, 512);
     ptx::tmem_relinquish();
+  }
+  // everything above touches no global memory: with a programmatic dependent launch it overlaps the previous kernel's tail
+  pdl_wait();
+  pdl_trigger();
+  if (CN) {
+    for (int i = threadIdx.x; i < BN2; i += NT2_THREADS) {
+      cn_par[i] = bias != nullptr ? bias[i] : 0.f; cn_par[BN2 + i] = E.gam[i]; cn_par[2 * BN2 + i] = E.bet[i];
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -597,10 +600,12 @@ int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt,
   cfg.blockDim = dim3(NT2_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CM; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, tmA, tmB, nkb, cpt, s, tpb, m_tiles, n_tiles, nb, bias, C, E));
   CPC_LAUNCHED_N(CN ? "gemm_nt_cnorm_tc2" : "gemm_nt_tc2", st);
   return 0;
@@ -673,6 +678,8 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_tn_tc2_kernel(const __gri
     ptx::tmem_alloc(tmem_holder, BN2);
     ptx::tmem_relinquish();
   }
+  pdl_wait();  // the prologue above overlaps the previous kernel's tail (programmatic dependent launch)
+  pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if (CM > 1) ptx::cluster_sync_all();
@@ -921,10 +928,12 @@ int gemm_tn_group_tc(int n, const TnDesc* d, cudaStream_t st, bool* handled) {
   cfg.blockDim = dim3(NT2_THREADS);
   cfg.dynamicSmemBytes = smem2;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k2, G));
   CPC_LAUNCHED_N("gemm_tn_tc2", st);
   *handled = true;

@@ -227,12 +227,16 @@ gru_rec_bwd_kernel(const float* __restrict__ dc, const float* __restrict__ c, co
 // ---------------------------------------------------------------------------------------------------------
 template <class T>
 __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, long long n) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f<T>(src[i]);
 }
 __global__ void cast3_bf16_kernel(const float* __restrict__ s0, bf16* __restrict__ d0, long long n0, const float* __restrict__ s1,
                                   bf16* __restrict__ d1, long long n1, const float* __restrict__ s2, bf16* __restrict__ d2,
                                   long long n2) {
+  pdl_wait();
+  pdl_trigger();
   const long long n = n0 + n1 + n2;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
     const float* s; bf16* d; long long j;
@@ -247,6 +251,8 @@ __global__ void cast3_bf16_kernel(const float* __restrict__ s0, bf16* __restrict
 // dst[c][r] = src[r][c]
 template <class T>
 __global__ void transpose_cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int R, int C) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -279,14 +285,14 @@ int launch_cast3_bf16(const float* s0, bf16* d0, long long n0, const float* s1, 
   const long long n = n0 + n1 + n2;
   int blocks = (int)((n / 4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  cast3_bf16_kernel<<<blocks, 256, 0, st>>>(s0, d0, n0, s1, d1, n1, s2, d2, n2);
+  CPC_CHECK_CUDA(launch_k(cast3_bf16_kernel, dim3(blocks), dim3(256), 0, st, 1, s0, d0, n0, s1, d1, n1, s2, d2, n2));
   CPC_LAUNCHED_N("cast3", st);
   return 0;
 }
 template <class T> int launch_cast(const float* src, T* dst, long long n, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  cast_kernel<T><<<blocks, 256, 0, st>>>(src, dst, n);
+  CPC_CHECK_CUDA(launch_k(cast_kernel<T>, dim3(blocks), dim3(256), 0, st, 1, src, dst, n));
   CPC_LAUNCHED_N("cast", st);
   return 0;
 }
@@ -295,7 +301,7 @@ template int launch_cast<float>(const float*, float*, long long, cudaStream_t);
 
 template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st) {
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
-  transpose_cast_kernel<T><<<grid, block, 0, st>>>(src, dst, R, C);
+  CPC_CHECK_CUDA(launch_k(transpose_cast_kernel<T>, grid, block, 0, st, 1, src, dst, R, C));
   CPC_LAUNCHED_N("transpose_cast", st);
   return 0;
 }

@@ -129,6 +129,10 @@ gru_rec_fwd_mma_kernel(const bf16* __restrict__ gi, const float* __restrict__ w_
       wf[gt][ks][3] = pack_bf16(__ldg(r1 + k + 8), __ldg(r1 + k + 9));
     }
   }
+  // W_hh was loaded ahead of the dependency wait: the kernel in front of this one in gru_fwd is always the input-projection
+  // GEMM, and with wait-then-trigger ordering only the immediate predecessor can still be running
+  pdl_wait();
+  pdl_trigger();
   // this thread finishes unit `col` (row g + 8*kh of the 16-block) for sequences b0 + 2*t4 + {0, 1}
   const int col = HC * rank + 16 * ub + 8 * kh + g;
   float bh[3];
@@ -281,6 +285,8 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
                        const uint2* __restrict__ gates4, const float* __restrict__ w_hh, bf16* __restrict__ dgi,
                        bf16* __restrict__ dgh, float* __restrict__ dh0, float* __restrict__ db_ih, float* __restrict__ db_hh,
                        int B, int S) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int G = 3 * HAR, KS = G / 16, KSH = KS / 2;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -465,10 +471,12 @@ int launch_cluster(const char* name, K kernel, int cs, int nclusters, cudaStream
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CPC_CHECK_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kernel), args));
   CPC_LAUNCHED_N(name, st);
   return 0;

@@ -66,6 +66,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // (P, N) <- (B, N, W): a position's N negative rows become contiguous
 __global__ void transpose_ext_kernel(const int* __restrict__ ext, int* __restrict__ ext_t, int B, int N, int W) {
+  pdl_wait();
+  pdl_trigger();
   const long long n = (long long)B * N * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % N);
@@ -113,6 +115,8 @@ __global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restri
                                                              const int* __restrict__ ext_t, float* __restrict__ lossbuf,
                                                              float* __restrict__ corrbuf, float* __restrict__ lsebuf, int B,
                                                              int S, int W, int K, int N, int warps_per_cta) {
+  pdl_wait();
+  pdl_trigger();
   using C = Cfg<H>;
   extern __shared__ __align__(128) unsigned char sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,6 +241,8 @@ __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(con
                                                             const float* __restrict__ dloss, bf16* __restrict__ dpred,
                                                             float* __restrict__ dz, int B, int S, int W, int K, int N,
                                                             int warps_per_cta) {
+  pdl_wait();
+  pdl_trigger();
   using C = Cfg<H>;
   constexpr int GRS = (CH + 8) * 2;     // bytes per row of Gs[16 heads][32 cand]
   constexpr int SRS = H * 4 + 32;                 // staging row stride: 32 B pad -> the 8-byte fragment stores of the 8 row
@@ -493,7 +499,7 @@ int launch_fwd(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf
   if (wpc > 8) wpc = 8;
   const size_t smem = wpc * fwd_warp_smem<H>();
   CPC_CHECK_CUDA(cudaFuncSetAttribute(score_fwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  score_fwd_mma_kernel<H><<<148, wpc * 32, smem, st>>>(pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, wpc);
+  CPC_CHECK_CUDA(launch_k(score_fwd_mma_kernel<H>, dim3(148), dim3(wpc * 32), smem, st, 1, pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, wpc));
   CPC_LAUNCHED_N("score_fwd_mma", st);
   return 0;
 }
@@ -505,7 +511,7 @@ int launch_bwd_red(const bf16* pred, const bf16* z, const int* ext_t, const floa
   if (wpc > cap) wpc = cap;
   const size_t smem = wpc * bwd_warp_smem<H, RED>();
   CPC_CHECK_CUDA(cudaFuncSetAttribute(score_bwd_mma_kernel<H, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  score_bwd_mma_kernel<H, RED><<<148, wpc * 32, smem, st>>>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, wpc);
+  CPC_CHECK_CUDA(launch_k(score_bwd_mma_kernel<H, RED>, dim3(148), dim3(wpc * 32), smem, st, 1, pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, wpc));
   CPC_LAUNCHED_N("score_bwd_mma", st);
   return 0;
 }
@@ -526,7 +532,7 @@ int score_transpose_ext(const int* ext, int* ext_t, int B, int N, int W, cudaStr
   const long long n = (long long)B * N * W;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  transpose_ext_kernel<<<blocks, 256, 0, st>>>(ext, ext_t, B, N, W);
+  CPC_CHECK_CUDA(launch_k(transpose_ext_kernel, dim3(blocks), dim3(256), 0, st, 1, ext, ext_t, B, N, W));
   CPC_LAUNCHED_N("transpose_ext", st);
   return 0;
 }
