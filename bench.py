@@ -34,6 +34,7 @@ if REPO not in sys.path:
 
 WINDOW = 20480
 SR = 16000.0
+L2_RED_CEILING_GBS = 5400.0  # fp32 scatter-add into an 8 MB L2-resident buffer, measured with tools/redbench.cu (B200)
 T0 = time.time()
 
 
@@ -55,6 +56,9 @@ def parse():
                     help="prediction heads: 'linear' = BASELINE config 2/3 (default), 'transformer' = config 4 (eval-mode heads)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="windows per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
+                    help="'graph' = the step is captured once as a CUDA graph (cpc_audio_b200.graph.GraphedTrainStep) and "
+                         "replayed; 'eager' = ~45 launches per step through the nn.Module surfaces, as cpc/train.py issues them")
     return ap.parse_args()
 
 
@@ -220,6 +224,7 @@ def algorithmic_work(B, bf16):
     w["conv0_wgrad"] = ("hbm", B * (WINDOW * 4 + L0 * H * es))
     w["conv0_fwd_mma"] = w["conv0_fwd"]
     w["conv0_bwd_du_mma"] = w["conv0_bwd_du"]
+    w["conv0_bwd2_mma"] = ("hbm", B * (WINDOW * 4 + L0 * H * es))   # one read of dy0 (+ the waveform); du0 never leaves the SM
     w["conv0_wgrad_mma"] = w["conv0_wgrad"]
     w["cnorm_relu_fwd"] = ("hbm", sum(B * lo * H * es * 2 for lo in (1024, 512, 256, 128)) + B * 128 * H * 4)
     w["cnorm_relu_bwd"] = ("hbm", sum(B * lo * H * es * 3 for lo in (1024, 512, 256, 128)))
@@ -233,8 +238,9 @@ def algorithmic_work(B, bf16):
     w["score_bwd_mma"] = ("hbm", B * W * (2 * K * H * es + N * 4 + K * 4) + B * S * H * (es + 4))
     # tensor-bound: FLOPs per step summed over that kernel's launches (reported per launch by dividing)
     conv = [(1024, 8), (512, 4), (256, 4), (128, 4)]
-    f_nt = sum(2.0 * B * lo * H * k * H for lo, k in conv)            # conv1-4 forward
-    f_nt += sum(2.0 * B * lo * H * k * H for lo, k in conv)           # dgrad
+    f_fwd = sum(2.0 * B * lo * H * k * H for lo, k in conv)           # conv1-4 forward (ChannelNorm+ReLU in the epilogue)
+    w["gemm_nt_cnorm_tc2"] = ("tensor", f_fwd)
+    f_nt = sum(2.0 * B * lo * H * k * H for lo, k in conv)            # dgrad
     f_nt += 2.0 * B * S * 3 * H * H * 2                               # GRU input projection fwd + d(input)
     f_nt += 2.0 * B * W * K * H * H * 2                               # heads fwd + dc
     f_tn = sum(2.0 * B * lo * H * k * H for lo, k in conv) + 2.0 * B * S * 3 * H * H * 2 + 2.0 * B * W * K * H * H
@@ -272,11 +278,12 @@ def run_ours(a):
     if a.heads == "transformer":
         crit.eval()  # the heads implement the reference's eval() semantics (no dropout); gradients still flow
     params = list(crit.parameters()) + list(model.parameters())  # cpc/train.py:332 order
+    use_graph = a.launch == "graph"
     if a.optimizer == "fused":
-        opt = FlatAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+        opt = FlatAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph, fuse_zero_grad=use_graph)
         bucket = opt.bucket
     else:
-        opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+        opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph)
         bucket = GradBucket(params)
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -286,7 +293,7 @@ def run_ours(a):
     x_host = x_dev.cpu().pin_memory()
     loss_host = torch.empty(1, 12).pin_memory()
 
-    def step(x):
+    def step_eager(x):
         c, z, _ = model(x, label)
         losses, acc = crit(c, z, label)
         losses.sum().backward()
@@ -295,6 +302,24 @@ def run_ours(a):
         opt.step()
         opt.zero_grad()
         return losses
+
+    gstep, launch_mode, launches_per_replay = None, "eager", None
+    if use_graph:
+        try:
+            from cpc_audio_b200.graph import GraphedTrainStep
+            n_before = lib.cpcb200_launch_count()
+            gstep = GraphedTrainStep(model, crit, opt, x_dev, label, allreduce=bucket.allreduce if world > 1 else None, warmup=3)
+            launches_per_replay = (lib.cpcb200_launch_count() - n_before) // 4  # 3 warm-up steps + the captured one
+            launch_mode = "cuda-graph replay (GraphedTrainStep)"
+        except Exception as e:  # noqa: BLE001 - report and run the eager loop instead (same kernels, same work)
+            log(f"CUDA-graph capture failed ({type(e).__name__}: {e}); running eager launches")
+            gstep = None
+            torch.cuda.synchronize(dev)
+
+    def step(x):
+        if gstep is not None:
+            return gstep(x)[0]
+        return step_eager(x)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -327,7 +352,7 @@ def run_ours(a):
         clocks.start()
     n0 = lib.cpcb200_launch_count()
     ms = timed(lambda: step(x_dev), a.steps)
-    launches = lib.cpcb200_launch_count() - n0
+    launches = lib.cpcb200_launch_count() - n0 if gstep is None else launches_per_replay * a.steps
     clk = clocks.stop() if clocks else None
     log(f"timed: {ms / a.steps:.3f} ms/step; e2e pass")
 
@@ -370,8 +395,8 @@ def run_ours(a):
     log(f"e2e: {ms_e2e / a.steps:.3f} ms/step; per-kernel pass")
     if rank == 0:
         lib.cpcb200_prof_enable(1)
-    for _ in range(min(a.steps, 10)):  # every rank runs these steps (they contain the all-reduce)
-        step(x_dev)
+    for _ in range(min(a.steps, 10)):  # every rank runs these steps (they contain the all-reduce); eager launches: the
+        step_eager(x_dev)              # event after every kernel serialises them (no programmatic overlap, no graph)
     torch.cuda.synchronize(dev)
     if rank == 0:
         buf = ctypes.create_string_buffer(1 << 16)
@@ -397,6 +422,13 @@ def run_ours(a):
                 else:
                     ach = amount / (tot / nst * 1e-3) / 1e12
                     ent.update(bound="tensor", achieved_tflops=round(ach, 1), frac=round(ach / pk["tf_sust"], 4))
+            if k == "score_bwd_mma":
+                # the kernel's real bound: fp32 scatter-adds of the negatives' / positives' gradient rows into the L2-resident
+                # dz (B*W*(N+K) rows of H floats per launch); ceiling measured by tools/redbench.cu on this GPU type
+                # (profiles/r1e_redbench_cpu_bound.txt: 5.4 TB/s for TMA bulk reductions and for red.global.v4 alike)
+                red = B * 116 * (128 + 12) * 256 * 4 / (tot / nst * 1e-3) / 1e9
+                ent.update(l2_scatter_add_gbs=round(red, 1), l2_scatter_add_ceiling_gbs=L2_RED_CEILING_GBS,
+                           frac_of_l2_scatter_add_ceiling=round(red / L2_RED_CEILING_GBS, 4))
             kernels[k] = ent
         t = kernels[top]
         if t.get("bound") == "hbm":
@@ -425,7 +457,7 @@ def run_ours(a):
                                         if a.heads == "linear" else
                                         "BASELINE config 4: --rnnMode transformer prediction heads (eval-mode), GRU context net, K=12, 128 negatives ")
                                        + f"batch={B}/GPU seq=20480, white-noise 16 kHz windows, random-init weights",
-                           "global_batch": B * world, "seq_len": WINDOW, "parallelism": f"dp{world}", "optimizer": a.optimizer,
+                           "global_batch": B * world, "seq_len": WINDOW, "parallelism": f"dp{world}", "optimizer": a.optimizer, "launch": launch_mode,
                            "l2": "no explicit flush: one step streams > 1 GB of activations (> 126 MB L2) between reuses"},
                 "e2e": {"value": sec / (ms_e2e / a.steps * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": ms_e2e / a.steps},

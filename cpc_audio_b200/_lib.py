@@ -64,6 +64,7 @@ SIGNATURES = {
     "cpcb200_criterion_t_fwd": (_I, [_DP, _P, _P, C.POINTER(THeadParams), _P, _P, _P, _P, _P, _SZ, _P]),
     "cpcb200_criterion_t_bwd": (_I, [_DP, _P, _P, C.POINTER(THeadParams), _P, _P, _P, _P, _P, C.POINTER(THeadParams), _P, _SZ, _P]),
     "cpcb200_adam_step": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
+    "cpcb200_adam_step_dev": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int, _P]),
     "cpcb200_test_gemm_nt": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "cpcb200_test_gemm_tn": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "cpcb200_test_gemm_nt_act": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -161,6 +161,67 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// graph-capturable variant: step count on the device (state[0]) together with beta1^step and beta2^step as running
+// float64 products (state[2..5]; double-precision pow() in the kernel costs ~90 us on this part), the last block to
+// finish (ticket in state[1]) publishes the next step's values - every block has read the current ones by then
+template <bool ZERO>
+__global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                size_t n, float lr, float b1, float b2, float eps, float wd, int* __restrict__ state) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float s_bc[2];
+  double* pw = reinterpret_cast<double*>(state + 2);  // beta1^(steps+1), beta2^(steps+1) once steps > 0
+  double p1 = 0.0, p2 = 0.0;
+  if (threadIdx.x == 0) {
+    const int done = *reinterpret_cast<volatile int*>(state);
+    p1 = done == 0 ? (double)b1 : *reinterpret_cast<volatile double*>(pw);
+    p2 = done == 0 ? (double)b2 : *reinterpret_cast<volatile double*>(pw + 1);
+    s_bc[0] = (float)(1.0 - p1);
+    s_bc[1] = sqrtf((float)(1.0 - p2));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+  const float step_size = lr / bc1;
+  auto upd = [&](float gi, float pi, float& mi, float& vi) {
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    mi = fmaf(b1, mi, (1.f - b1) * gi);
+    vi = fmaf(b2, vi, (1.f - b2) * gi * gi);
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    return pi - step_size * (mi / denom);
+  };
+  // all loads of a quad first, every store (the cleared gradient included) after the arithmetic
+  const size_t n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 gq = g4[i];
+    float4 pq = p4[i], mq = m4[i], vq = v4[i];
+    pq.x = upd(gq.x, pq.x, mq.x, vq.x); pq.y = upd(gq.y, pq.y, mq.y, vq.y);
+    pq.z = upd(gq.z, pq.z, mq.z, vq.z); pq.w = upd(gq.w, pq.w, mq.w, vq.w);
+    m4[i] = mq; v4[i] = vq; p4[i] = pq;
+    if (ZERO) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float mi = m[i], vi = v[i];
+    const float pn = upd(g[i], p[i], mi, vi);
+    m[i] = mi; v[i] = vi; p[i] = pn;
+    if (ZERO) g[i] = 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(state + 1, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      state[1] = 0;
+      pw[0] = p1 * (double)b1;
+      pw[1] = p2 * (double)b2;
+      __threadfence();
+      atomicAdd(state, 1);
+    }
+  }
+}
+
 }  // namespace cpcb200
 
 using namespace cpcb200;
@@ -349,6 +410,28 @@ int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CPC_CHECK_CUDA(launch_k(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
                           beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2)));
+  CPC_LAUNCHED_N("adam", st);
+  return 0;
+}
+
+int cpcb200_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, int32_t* state, int zero_grad, void* stream) {
+  NOT_NULL(param); NOT_NULL(grad); NOT_NULL(exp_avg); NOT_NULL(exp_avg_sq); NOT_NULL(state);
+  if (n == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+       reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+    return fail(CPCB200_ERR_BAD_DIMS, "adam_step_dev: buffers must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(state) & 7) return fail(CPCB200_ERR_BAD_DIMS, "adam_step_dev: state must be 8-byte aligned");
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (zero_grad)
+    CPC_CHECK_CUDA(launch_k(adam_dev_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, st, 1, param, grad, exp_avg, exp_avg_sq, n,
+                            lr, beta1, beta2, eps, weight_decay, reinterpret_cast<int*>(state)));
+  else
+    CPC_CHECK_CUDA(launch_k(adam_dev_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, 1, param, grad, exp_avg, exp_avg_sq, n,
+                            lr, beta1, beta2, eps, weight_decay, reinterpret_cast<int*>(state)));
   CPC_LAUNCHED_N("adam", st);
   return 0;
 }

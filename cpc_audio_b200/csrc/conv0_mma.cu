@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(128) conv0_wgrad_mma_kernel(const float* __res
 // tiles of the CTA - no ones-matrix MMAs, no shared-memory atomics; (ii) the dy tile and the waveform samples of
 // the next tile are prefetched with cp.async while the current one is processed; (iii) the weight gradient
 // dW0[c][tap] += sum_f du[f][c] x[5f-3+tap] is taken from the du tile while it is still in shared memory
-// (A = du^T by ldmatrix.trans, B = waveform samples; tap 10 = 1.0 yields dbias0), so du is not read again.
+// (A = du^T by ldmatrix.trans, B = waveform samples; tap 10 = 1.0 yields dbias0), so du never goes to HBM.
 // Row statistics cross the NW warps through two small shared arrays (sum / sum of squares, then s1 / s2).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -655,14 +655,9 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         mma16816(wacc[m][1], a, bx[1][0], bx[1][1]);
       }
     }
-    __syncthreads();  // (D) the du tile is complete
-    {
-      bf16* dst = dy + ((long long)b * L0 + f0) * H;
-      for (int i = tid; i < kFT * SEGS; i += NTHR) {
-        const int r = i / SEGS, sg = i - r * SEGS;
-        *reinterpret_cast<uint4*>(dst + (size_t)r * H + sg * 8) = *reinterpret_cast<const uint4*>(tl + r * RS + sg * 16);
-      }
-    }
+    // du0 has no consumer besides the weight gradient taken above (conv0 is the first layer: there is no data gradient),
+    // so the tile is NOT written back: the kernel's HBM traffic is one read of dy0.  Barrier (A) of the next iteration
+    // orders these ldmatrix reads against the prefetch that reuses the buffer.
   }
   cp_async_wait_all();
   // ---- flush the register accumulators -------------------------------------------------------------------

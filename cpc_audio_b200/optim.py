@@ -61,9 +61,14 @@ class GradBucket:
 
 
 class FlatAdam:
-    """torch.optim.Adam(lr, betas, eps, weight_decay) over one flat parameter buffer, one kernel per step."""
+    """torch.optim.Adam(lr, betas, eps, weight_decay) over one flat parameter buffer, one kernel per step.
 
-    def __init__(self, params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    ``capturable=True`` keeps the step count on the device (like ``torch.optim.Adam(capturable=True)``) so that
+    ``step()`` can be captured in a CUDA graph; ``fuse_zero_grad=True`` additionally clears the gradient bucket inside
+    the same kernel, which makes the following ``zero_grad()`` free."""
+
+    def __init__(self, params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, capturable=False,
+                 fuse_zero_grad=False):
         self.params = [p for p in params]
         dev = self.params[0].device
         sizes = [p.numel() for p in self.params]
@@ -75,16 +80,37 @@ class FlatAdam:
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.steps = 0
+        self.capturable = bool(capturable or fuse_zero_grad)
+        self.fuse_zero_grad = bool(fuse_zero_grad)
+        self._steps = 0
+        self._state = torch.zeros(8, device=dev, dtype=torch.int32) if self.capturable else None  # [steps, ticket, b1^t, b2^t]
+        self._grads_clean = False
+
+    @property
+    def steps(self):
+        return int(self._state[0].item()) if self.capturable else self._steps
 
     def step(self):
-        self.steps += 1
         dev = self.flat_p.device
         with torch.cuda.device(dev):
+            if self.capturable:
+                L.check(L.lib().cpcb200_adam_step_dev(L.ptr(self.flat_p), L.ptr(self.bucket.flat), L.ptr(self.exp_avg),
+                                                      L.ptr(self.exp_avg_sq), self.flat_p.numel(), self.lr, self.betas[0],
+                                                      self.betas[1], self.eps, self.weight_decay, L.ptr(self._state),
+                                                      1 if self.fuse_zero_grad else 0, L.stream_ptr(dev)), "adam_step_dev")
+                self._grads_clean = self.fuse_zero_grad
+                return
+            self._steps += 1
             L.check(L.lib().cpcb200_adam_step(L.ptr(self.flat_p), L.ptr(self.bucket.flat), L.ptr(self.exp_avg),
                                               L.ptr(self.exp_avg_sq), self.flat_p.numel(), self.lr, self.betas[0],
-                                              self.betas[1], self.eps, self.weight_decay, self.steps, L.stream_ptr(dev)),
+                                              self.betas[1], self.eps, self.weight_decay, self._steps, L.stream_ptr(dev)),
                     "adam_step")
 
     def zero_grad(self, set_to_none=False):
+        if self._grads_clean:  # the fused step already cleared the bucket; only re-attach the views if needed
+            self._grads_clean = False
+            for p, v in zip(self.bucket.params, self.bucket.views):
+                if p.grad is not v:
+                    p.grad = v
+            return
         self.bucket.zero()

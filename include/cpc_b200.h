@@ -151,6 +151,14 @@ int cpcb200_criterion_t_bwd(const cpcb200_dims* d, const float* c, const float* 
 /* ---- fused Adam over a flat fp32 bucket (cpc/train.py:335-337,90-91; torch.optim.Adam semantics) -------- */
 int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
+/* Same update with the step count kept ON THE DEVICE, so that the launch can be captured in a CUDA graph and replayed
+ * (torch.optim.Adam(capturable=True) semantics): `state` = 8 int32 words, zero-initialised by the caller and 8-byte
+ * aligned; state[0] = number of steps taken so far (incremented by the kernel after every block has read it), the rest
+ * is scratch (a block ticket and beta1^step, beta2^step as running float64 products).  zero_grad != 0 also clears `grad`
+ * (optimizer.zero_grad() of cpc/train.py:91 folded into the same pass). */
+int cpcb200_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, int32_t* state, int zero_grad,
+                          void* stream);
 
 /* ---- test hooks: the GEMM building blocks, exposed so tests can pin them against torch.matmul ----------
  * C[M,N] = A[M,Kd] * B[N,Kd]^T (+bias[N]) ; C2[N1,N2] += A[M,N1]^T * B[M,N2].  dtype as in cpcb200_dims. */

@@ -45,6 +45,8 @@ def test_size_queries_and_validation(built_lib):
     assert lib.cpcb200_gru_ws_bytes(bad2, 0) == 0
     st = lib.cpcb200_adam_step(None, z, z, z, 4, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None)
     assert st == -5 and b"NULL" in lib.cpcb200_last_error()
+    st = lib.cpcb200_adam_step_dev(z, z, z, z, 4, 1e-3, 0.9, 0.999, 1e-8, 0.0, None, 1, None)
+    assert st == -5 and b"NULL" in lib.cpcb200_last_error()
 
 
 REF_MODEL_KEYS = [f"gEncoder.{n}{i}.{p}" for i in range(5) for n in ("conv", "batchNorm") for p in ("weight", "bias")] + \

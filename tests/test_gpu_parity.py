@@ -220,6 +220,80 @@ def test_fused_adam_matches_torch_adam(built_lib):
         assert (a - b).abs().max().item() <= 2e-6 * max(1.0, a.abs().max().item())
 
 
+def test_capturable_adam_matches_torch_adam(built_lib):
+    """cpcb200_adam_step_dev (device-side step count, gradient clearing fused) vs torch.optim.Adam."""
+    from cpc_audio_b200.optim import FlatAdam
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    shapes = [(256, 256, 4), (768,), (12, 256, 256)]
+    p_t = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=gen)) for s in shapes]
+    p_f = [torch.nn.Parameter(p.detach().clone()) for p in p_t]
+    o_t = torch.optim.Adam(p_t, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+    o_f = FlatAdam(p_f, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, capturable=True, fuse_zero_grad=True)
+    for it in range(6):
+        for a, b in zip(p_t, p_f):
+            g = torch.randn(a.shape, device="cuda", generator=gen) * (10.0 ** (it - 4))
+            a.grad = g.clone()
+            b.grad.copy_(g)
+        o_t.step(); o_f.step()
+        assert all(b.grad.eq(0).all() for b in p_f)  # cleared by the step itself
+        o_t.zero_grad(); o_f.zero_grad()
+    assert o_f.steps == 6
+    o_f.bucket.detach()
+    for a, b in zip(p_t, p_f):
+        assert (a - b).abs().max().item() <= 2e-6 * max(1.0, a.abs().max().item())
+
+
+def test_graphed_step_matches_eager_steps(built_lib):
+    """GraphedTrainStep (whole step captured as one CUDA graph, replayed) must walk the same trajectory as the eager
+    loop of cpc/train.py:83-91: same losses step by step, same parameters at the end (bf16 path, B = 4)."""
+    import cpc_audio_b200 as M
+    from cpc_audio_b200.graph import GraphedTrainStep
+    from cpc_audio_b200.optim import FlatAdam
+    dev = torch.device("cuda:0")
+
+    def build():
+        torch.manual_seed(0)
+        model = M.CPCModel(M.CPCEncoder(256, "layerNorm", compute_dtype="bf16"),
+                           M.CPCAR(256, 256, False, 1, mode="GRU", reverse=False, compute_dtype="bf16")).to(dev)
+        crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode="linear", dropout=False, speakerEmbedding=0,
+                                          nSpeakers=0, sizeInputSeq=128, compute_dtype="bf16").to(dev)
+        params = list(crit.parameters()) + list(model.parameters())
+        opt = FlatAdam(params, lr=2e-4, capturable=True, fuse_zero_grad=True)
+        return model, crit, opt
+
+    gen = torch.Generator(device=dev).manual_seed(7)
+    xs = [torch.randn(4, 1, 20480, device=dev, generator=gen) * 0.1 for _ in range(4)]
+    label = torch.zeros(4, dtype=torch.long, device=dev)
+
+    def eager_step(model, crit, opt, x):
+        c, z, _ = model(x, label)
+        losses, acc = crit(c, z, label)
+        losses.sum().backward()
+        opt.step()
+        opt.zero_grad()
+        return losses.detach().clone()
+
+    # eager trajectory: 3 steps on xs[0] (what the graph's warm-up does) + 1 (the captured pass) then xs[1..3]
+    model, crit, opt = build()
+    torch.cuda.manual_seed(99)
+    ref = [eager_step(model, crit, opt, xs[0]) for _ in range(4)] + [eager_step(model, crit, opt, x) for x in xs[1:]]
+    ref_p = opt.flat_p.clone()
+    opt.bucket.detach()
+
+    model, crit, opt = build()
+    torch.cuda.manual_seed(99)
+    g = GraphedTrainStep(model, crit, opt, xs[0], label, warmup=3)   # 3 warm-up steps; the capture itself does not execute
+    got = [g(xs[0])[0].clone()] + [g(x)[0].clone() for x in xs[1:]]
+    assert opt.steps == 7
+    # the negative-sample draws of the eager run and of the replays come from the same generator sequence, so the
+    # trajectories agree up to the summation order of the fp32 atomics
+    for a, b in zip(ref[3:], got):
+        assert (a - b).abs().max().item() <= 2e-3, (a, b)
+    # Adam turns the tiny run-to-run differences of near-zero gradients into +-lr updates: compare loosely
+    assert Hh.rel_err(opt.flat_p, ref_p) <= 2e-2
+    opt.bucket.detach()
+
+
 def test_bucket_sinks_receive_the_same_gradients(built_lib):
     """With a GradBucket attached the backward kernels accumulate straight into the flat buffer; the result must
     equal the gradients autograd returns without a bucket (up to the atomics' summation order)."""
