@@ -464,7 +464,15 @@ def run_ours(a):
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a captured graph holds NCCL work: release it before the communicator goes away, and do not let a slow
+        # communicator teardown hold the job (every rank has finished and printed by now)
+        if gstep is not None:
+            gstep.graph.reset()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

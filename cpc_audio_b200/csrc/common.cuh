@@ -242,6 +242,7 @@ struct CNormEpi {
   void* y;
   float* z;
   int pad_rows;
+  float2* stats = nullptr;  // (mean, rstd) of every row, index b*rpb + t: saved for the ChannelNorm backward
 };
 
 // C[m,n] = sum_k A[m,k] * B[n,k] (+ bias[n]).  A row view (M = nb*rpb rows, inner Kd); B dense (N, Kd) ld=Kd.

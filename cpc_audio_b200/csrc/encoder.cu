@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(128) conv0_wgrad_kernel(const float* __restric
 template <int I, class T>
 __global__ void __launch_bounds__(256) cnorm_relu_fwd_kernel(const T* __restrict__ u, const float* __restrict__ gam,
                                                               const float* __restrict__ bet, T* __restrict__ y,
-                                                              float* __restrict__ zout, int B, int Lc, int H) {
+                                                              float* __restrict__ zout, float2* __restrict__ stats, int B, int Lc,
+                                                              int H) {
   pdl_wait();
   pdl_trigger();
   const int lane = threadIdx.x & 31;
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(256) cnorm_relu_fwd_kernel(const T* __restrict
   row_load<I>(u + prow, H, lane, v);
   float mean, rstd;
   row_stats<I>(v, H, lane, mean, rstd);
+  if (lane == 0) stats[warp] = make_float2(mean, rstd);  // saved for backward
 #pragma unroll
   for (int i = 0; i < I; i++) {
     int c = 4 * (lane + 32 * i);
@@ -360,7 +362,8 @@ __device__ __forceinline__ void warp_sum_n(float (&x)[R]) {
 }
 
 template <int I, int R, class TD, class T>
-__device__ __forceinline__ void cnorm_bwd_rows(const TD* __restrict__ dy, const T* __restrict__ u, T* __restrict__ du,
+__device__ __forceinline__ void cnorm_bwd_rows(const TD* __restrict__ dy, const T* __restrict__ u,
+                                               const float2* __restrict__ stats, T* __restrict__ du,
                                                long long r0l, int Lc, int H, int lane, const float (&g)[I][4],
                                                const float (&be)[I][4], float (&ag)[I][4], float (&abe)[I][4],
                                                float (&ab)[I][4], float inv_h, float inv_h1) {
@@ -380,33 +383,14 @@ __device__ __forceinline__ void cnorm_bwd_rows(const TD* __restrict__ dy, const 
       if (++t >= Lc) { t = 0; b++; }
     }
   }
-  float mean[R], rstd[R], nmr[R];
-#pragma unroll
-  for (int rr = 0; rr < R; rr++) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < I; i++) s += (v[rr][i][0] + v[rr][i][1]) + (v[rr][i][2] + v[rr][i][3]);  // lanes past H hold zeros
-    mean[rr] = s;
-  }
-  warp_sum_n<R>(mean);
-#pragma unroll
-  for (int rr = 0; rr < R; rr++) {
-    mean[rr] *= inv_h;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < I; i++)
-      if (4 * (lane + 32 * i) < H) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) { const float dl = v[rr][i][j] - mean[rr]; q = fmaf(dl, dl, q); }
-      }
-    rstd[rr] = q;
-  }
-  warp_sum_n<R>(rstd);
+  // (mean, rstd) of every row were saved by the forward pass (GEMM epilogue or cnorm_relu_fwd_kernel)
+  float rstd[R], nmr[R];
   float s1[R], s2[R];
 #pragma unroll
   for (int rr = 0; rr < R; rr++) {
-    rstd[rr] = rsqrtf(rstd[rr] * inv_h1 + kEps);
-    nmr[rr] = -mean[rr] * rstd[rr];
+    const float2 st = __ldg(stats + r0l + rr);
+    rstd[rr] = st.y;
+    nmr[rr] = -st.x * st.y;
     s1[rr] = s2[rr] = 0.f;
 #pragma unroll
     for (int i = 0; i < I; i++) {
@@ -451,7 +435,8 @@ __device__ __forceinline__ void cnorm_bwd_rows(const TD* __restrict__ dy, const 
 template <int I, class TD, class T>
 __global__ void __launch_bounds__(256, (I <= 2 ? 2 : 1)) cnorm_relu_bwd_kernel(const TD* __restrict__ dy, const T* __restrict__ u,
                                                                  const float* __restrict__ gam, const float* __restrict__ bet,
-                                                                 T* __restrict__ du, float* __restrict__ dgam,
+                                                                 const float2* __restrict__ stats, T* __restrict__ du,
+                                                                 float* __restrict__ dgam,
                                                                  float* __restrict__ dbet, float* __restrict__ dbias, int B,
                                                                  int Lc, int H) {
   pdl_wait();
@@ -476,9 +461,9 @@ __global__ void __launch_bounds__(256, (I <= 2 ? 2 : 1)) cnorm_relu_bwd_kernel(c
   const float inv_h = 1.f / (float)H, inv_h1 = 1.f / (float)(H - 1);
   const long long full = rows / kCbR;  // trips of kCbR rows; the < kCbR leftover rows go one at a time
   for (long long trip = warp0; trip < full; trip += nwarps)
-    cnorm_bwd_rows<I, kCbR, TD, T>(dy, u, du, trip * kCbR, Lc, H, lane, g, be, ag, abe, ab, inv_h, inv_h1);
+    cnorm_bwd_rows<I, kCbR, TD, T>(dy, u, stats, du, trip * kCbR, Lc, H, lane, g, be, ag, abe, ab, inv_h, inv_h1);
   for (long long r = full * kCbR + warp0; r < rows; r += nwarps)
-    cnorm_bwd_rows<I, 1, TD, T>(dy, u, du, r, Lc, H, lane, g, be, ag, abe, ab, inv_h, inv_h1);
+    cnorm_bwd_rows<I, 1, TD, T>(dy, u, stats, du, r, Lc, H, lane, g, be, ag, abe, ab, inv_h, inv_h1);
   float* mine = red + (size_t)wib * 3 * H;
 #pragma unroll
   for (int i = 0; i < I; i++) {
@@ -547,6 +532,7 @@ __global__ void permute_add_wgrad_all_kernel(Conv4Ptrs P, int Ci) {
 
 struct EncLayout {
   size_t y[4], u[5];  // element offsets into save (u[0] unused)
+  size_t st[5];       // (mean, rstd) per row of layers 1..4 (float2, offsets in elements of the activation type)
   size_t total;       // elements
 };
 EncLayout enc_layout(const Geo& g) {
@@ -555,6 +541,7 @@ EncLayout enc_layout(const Geo& g) {
   auto take = [&](size_t n) { size_t r = off; off += (n + 127) / 128 * 128; return r; };
   for (int i = 0; i < 4; i++) e.y[i] = take((size_t)g.B * (g.Lout[i] + 2 * kPad) * g.H);
   for (int i = 1; i < 5; i++) e.u[i] = take((size_t)g.B * (g.Lout[i] + 2 * kPad) * g.H);
+  for (int i = 1; i < 5; i++) e.st[i] = take((size_t)g.B * g.Lout[i] * 8 / (g.bf16 ? 2 : 4));
   e.total = off;
   return e;
 }
@@ -606,14 +593,15 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     float* zo = i == 4 ? z : nullptr;
     if (g.bf16 && H == 256) {  // ChannelNorm + ReLU inside the GEMM epilogue
       bool fused = false;
-      CNormEpi E{p->norm_w[i], p->norm_b[i], yo != nullptr ? static_cast<void*>(yo + (size_t)kPad * H) : nullptr, zo, kPad};
+      CNormEpi E{p->norm_w[i], p->norm_b[i], yo != nullptr ? static_cast<void*>(yo + (size_t)kPad * H) : nullptr, zo, kPad,
+                 reinterpret_cast<float2*>(sv + e.st[i])};
       CPC_TRY(gemm_nt_cnorm_tc(B, kConvK[i] * H, A, wp[i], p->conv_b[i], C, E, st, &fused));
       if (fused) continue;
     }
     CPC_TRY(gemm_nt(g.bf16, false, B, H, kConvK[i] * H, A, wp[i], p->conv_b[i], C, st));
     const long long rows = (long long)B * Lo;
     const int blocks = (int)((rows * 32 + 255) / 256);
-#define LAUNCH_CN(II) CPC_CHECK_CUDA(launch_k(cnorm_relu_fwd_kernel<II, T>, dim3(blocks), dim3(256), 0, st, 1, sv + e.u[i], p->norm_w[i], p->norm_b[i], yo, zo, B, Lo, H))
+#define LAUNCH_CN(II) CPC_CHECK_CUDA(launch_k(cnorm_relu_fwd_kernel<II, T>, dim3(blocks), dim3(256), 0, st, 1, sv + e.u[i], p->norm_w[i], p->norm_b[i], yo, zo, reinterpret_cast<float2*>(sv + e.st[i]), B, Lo, H))
     if (I == 1) LAUNCH_CN(1); else if (I == 2) LAUNCH_CN(2); else if (I == 3) LAUNCH_CN(3); else LAUNCH_CN(4);
 #undef LAUNCH_CN
     CPC_LAUNCHED_N("cnorm_relu_fwd", st);
@@ -660,7 +648,8 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       const size_t smem = 8 * 3 * (size_t)H * sizeof(float);
 #define LAUNCH_CB(II, TD, SRC)                                                                                       \
   CPC_CHECK_CUDA(launch_k(cnorm_relu_bwd_kernel<II, TD, T>, dim3(blocks), dim3(256), smem, st, 1, SRC, sv + e.u[i], p->norm_w[i], \
-                          p->norm_b[i], du[i], gr->norm_w[i], gr->norm_b[i], gr->conv_b[i], B, Lo, H))
+                          p->norm_b[i], reinterpret_cast<const float2*>(sv + e.st[i]), du[i], gr->norm_w[i], gr->norm_b[i],  \
+                          gr->conv_b[i], B, Lo, H))
       if (i == 4) { if (I == 1) LAUNCH_CB(1, float, dz); else if (I == 2) LAUNCH_CB(2, float, dz); else if (I == 3) LAUNCH_CB(3, float, dz); else LAUNCH_CB(4, float, dz); }
       else { if (I == 1) LAUNCH_CB(1, T, dy[i]); else if (I == 2) LAUNCH_CB(2, T, dy[i]); else if (I == 3) LAUNCH_CB(3, T, dy[i]); else LAUNCH_CB(4, T, dy[i]); }
 #undef LAUNCH_CB

@@ -520,6 +520,7 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
         const float dm = m_mine - oth.x;
         const float m2 = q_mine + oth.y + dm * dm * (float)(BN2 / 4);
         const float rstd = rsqrtf(m2 * (1.f / (BN2 - 1)) + 1e-5f);
+        if (hf == 0 && row_ok && E.stats != nullptr) E.stats[(long long)b * C.rpb + t] = make_float2(mean, rstd);
         bf16* ywarp = E.y != nullptr ? static_cast<bf16*>(E.y) + (long long)b * C.bs + (long long)(t - lane) * C.rs + hf * (BN2 / 2) : nullptr;
         float* zwarp = E.z != nullptr ? E.z + ((long long)b * C.rpb + (t - lane)) * BN2 + hf * (BN2 / 2) : nullptr;
 #pragma unroll 1
