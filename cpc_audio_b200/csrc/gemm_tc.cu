@@ -431,12 +431,14 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
         const int b = mt < m_tiles ? mt / tiles_per_batch : nb;  // b == nb: out of bounds -> zero fill
         const int t0 = (mt % tiles_per_batch) * BM;
         const int n0 = gn * BN2;
+        int c0 = 0, chunk = 0, tph = 0, tgr = 0;  // channel offset inside the tap; tap = tgr * s + tph
         for (int kb = 0; kb < nkb; kb++, it++) {
           const int st = it % STAGES, u = it / STAGES;
           if (u > 0) ptx::mbar_wait(&empty[st], (u - 1) & 1);
           ptx::mbar_arrive_expect_tx(&full[st], A_BYTES + B_BYTES);
-          const int tap = kb / chunks_per_tap, c0 = (kb - tap * chunks_per_tap) * BK;
-          ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES, c0, tap % s, t0 + tap / s, b);
+          ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES, c0, tph, t0 + tgr, b);
+          c0 += BK;
+          if (++chunk == chunks_per_tap) { chunk = 0; c0 = 0; if (++tph == s) { tph = 0; tgr++; } }
           if (CM == 1) ptx::tma_load_4d(&tmB, &full[st], smB + st * B_BYTES, kb * BK, n0, 0, 0);
           else ptx::tma_load_4d_mc(&tmB, &full[st], smB + st * B_BYTES + rank * B_SLICE, kb * BK, n0 + rank * (BN2 / CM), 0, 0, MASK);
           if (it == 0) TL_STAMP(1);
@@ -444,32 +446,40 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN2, 0, 0);
-      int it = 0, ti = 0;
-      for (int gid = cluster_id; gid < total_groups; gid += num_clusters, ti++) {
-        const int acc = ti & 1, ua = ti >> 1;
-        if (ua > 0) ptx::mbar_wait(&tempty[acc], (ua - 1) & 1);
+    // The whole warp walks the loop (uniform control flow keeps the descriptors in uniform registers; a single-lane
+    // loop costs ~120 issue slots per k-block in register-to-uniform moves, more than the 4 MMAs take to execute);
+    // one elected lane issues.  A shared-memory descriptor is the constant part + (byte offset >> 4).
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN2, 0, 0);
+    const uint64_t adesc0 = ptx::make_sdesc_sw128(ptx::smem_u32(smA), 16, 1024);
+    const uint64_t bdesc0 = ptx::make_sdesc_sw128(ptx::smem_u32(smB), 16, 1024);
+    const bool leader = ptx::elect_one();
+    int it = 0, ti = 0;
+    for (int gid = cluster_id; gid < total_groups; gid += num_clusters, ti++) {
+      const int acc = ti & 1, ua = ti >> 1;
+      if (ua > 0) ptx::mbar_wait(&tempty[acc], (ua - 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN2;
+      for (int kb = 0; kb < nkb; kb++, it++) {
+        const int st = it % STAGES, u = it / STAGES;
+        ptx::mbar_wait(&full[st], u & 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN2;
-        for (int kb = 0; kb < nkb; kb++, it++) {
-          const int st = it % STAGES, u = it / STAGES;
-          ptx::mbar_wait(&full[st], u & 1);
+        if (leader) {
           if (it == 0) TL_STAMP(2);
-          ptx::tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(smA + st * A_BYTES), b0 = ptx::smem_u32(smB + st * B_BYTES);
+          const uint64_t ad = adesc0 + (uint64_t)((st * A_BYTES) >> 4), bd = bdesc0 + (uint64_t)((st * B_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / UK; k++) {
-            const uint64_t ad = ptx::make_sdesc_sw128(a0 + k * UK * 2, 16, 1024);
-            const uint64_t bd = ptx::make_sdesc_sw128(b0 + k * UK * 2, 16, 1024);
-            ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / UK; k++)
+            ptx::umma_bf16(d_tmem, ad + (uint64_t)(k * ((UK * 2) >> 4)), bd + (uint64_t)(k * ((UK * 2) >> 4)), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
           if (CM == 1) ptx::umma_commit(&empty[st]);
           else ptx::umma_commit_mc(&empty[st], MASK);
         }
+        __syncwarp();
+      }
+      if (leader) {
         ptx::umma_commit(&tfull[acc]);
         TL_STAMP(3);
       }
+      __syncwarp();
     }
   } else {
     // epilogue: warp -> TMEM lane quadrant lg = warp % 4 (hardware rule), column half hf = (warp - 2) / 4
@@ -708,24 +718,29 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_tn_tc2_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN2, 1, 1);
-      for (int i = 0; i < nkb; i++) {
-        const int st = i % STAGES, u = i / STAGES;
-        ptx::mbar_wait(&full[st], u & 1);
-        ptx::tc_fence_after();
-        const uint32_t a0 = ptx::smem_u32(smA + st * A_BYTES), b0 = ptx::smem_u32(smB + st * B_BYTES);
+    // whole warp in the loop, one elected issuer (see gemm_nt_tc2_kernel)
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN2, 1, 1);
+    // MN-major SW128: LBO = stride between 64-wide MN blocks, SBO = stride between 8-row K groups
+    const uint64_t adesc0 = ptx::make_sdesc_sw128(ptx::smem_u32(smA), BLK, 1024);
+    const uint64_t bdesc0 = ptx::make_sdesc_sw128(ptx::smem_u32(smB), BLK, 1024);
+    const bool leader = ptx::elect_one();
+    for (int i = 0; i < nkb; i++) {
+      const int st = i % STAGES, u = i / STAGES;
+      ptx::mbar_wait(&full[st], u & 1);
+      ptx::tc_fence_after();
+      if (leader) {
+        const uint64_t ad = adesc0 + (uint64_t)((st * A_BYTES) >> 4), bd = bdesc0 + (uint64_t)((st * B_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < 64 / UK; k++) {
-          const uint64_t ad = ptx::make_sdesc_sw128(a0 + k * UK * 128, BLK, 1024);
-          const uint64_t bd = ptx::make_sdesc_sw128(b0 + k * UK * 128, BLK, 1024);
-          ptx::umma_bf16(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < 64 / UK; k++)
+          ptx::umma_bf16(tmem_acc, ad + (uint64_t)(k * ((UK * 128) >> 4)), bd + (uint64_t)(k * ((UK * 128) >> 4)), idesc,
+                         (i > 0 || k > 0) ? 1u : 0u);
         if (CM == 1) ptx::umma_commit(&empty[st]);
         else ptx::umma_commit_mc(&empty[st], MASK);
       }
-      ptx::umma_commit(acc_full);
+      __syncwarp();
     }
+    if (leader) ptx::umma_commit(acc_full);
+    __syncwarp();
   } else if (nkb > 0) {
     // epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves; rows go out as 64-byte runs through the staging buffer
     const int lg = warp & 3, hf = (warp - 2) >> 2;
