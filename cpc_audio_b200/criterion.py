@@ -179,7 +179,13 @@ class _CriterionFn(torch.autograd.Function):
         d = L.make_dims(B, S * 160, H, Har, K, N, 1, dtype_code)
         dc = torch.empty_like(c)
         dz = torch.empty_like(z)
-        dw = torch.empty(K, H, Har, device=dev, dtype=torch.float32)
+        # the weight gradient is accumulated (+=): straight into the gradient bucket when the K weights have their sinks
+        # there as one contiguous (K, H, Har) block, else into a fresh zero buffer handed back to autograd
+        from .optim import sinks_for
+        sinks = sinks_for(ctx.weights)
+        sunk = sinks is not None and all(s.is_contiguous() and s.data_ptr() == sinks[0].data_ptr() + i * H * Har * 4
+                                         for i, s in enumerate(sinks))
+        dw = sinks[0].as_strided((K, H, Har), (H * Har, Har, 1)) if sunk else torch.zeros(K, H, Har, device=dev, dtype=torch.float32)
         wsn = lib.cpcb200_criterion_ws_bytes(d, 1)
         ws = _bytes(wsn, dev)
         dlosses = dlosses.contiguous().float()
@@ -187,11 +193,7 @@ class _CriterionFn(torch.autograd.Function):
             L.check(lib.cpcb200_criterion_bwd(d, L.ptr(c), L.ptr(z), L.ptr(w_flat), L.ptr(ext), L.ptr(dlosses), L.ptr(save),
                                               L.ptr(dc), L.ptr(dz), L.ptr(dw), L.ptr(ws), wsn, L.stream_ptr(dev)),
                     "criterion_bwd")
-        from .optim import sinks_for
-        sinks = sinks_for(ctx.weights)
-        if sinks is not None and all(s.is_contiguous() and s.data_ptr() == sinks[0].data_ptr() + i * H * Har * 4
-                                     for i, s in enumerate(sinks)):
-            sinks[0].as_strided((K, H, Har), (H * Har, Har, 1)).add_(dw)  # one kernel into the bucket
+        if sunk:
             return (dc, dz, None, None, None, *([None] * K))
         return (dc, dz, None, None, None, *dw.unbind(0))
 

@@ -318,7 +318,6 @@ int criterion_bwd_t(const Geo& g, const float* c, const float* z, const float* w
   if (!tp) CPC_TRY(launch_transpose_cast<T>(w_pred, wTt, K * H, Har, st));
   CPC_CHECK_CUDA(cudaMemsetAsync(dz, 0, (size_t)B * S * H * sizeof(float), st));
   CPC_CHECK_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * S * Har * sizeof(float), st));
-  if (!tp) CPC_CHECK_CUDA(cudaMemsetAsync(dw_pred, 0, (size_t)K * H * Har * sizeof(float), st));
   bool done = false;
   if constexpr (!isf) {
     if (lay.mma) {

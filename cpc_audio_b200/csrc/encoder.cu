@@ -518,15 +518,25 @@ __global__ void prep_w_dgrad_all_kernel(Conv4Ptrs P, int Co, int Ci) {
     }
   }
 }
-// dW[co][ci][tap] += scratch[co][tap*Ci + ci]: block (co, layer), thread ci
+// dW[co][ci][tap] += scratch[co][tap*Ci + ci]: block (co, layer).  The scratch row is read coalesced into shared memory
+// (rows padded by one float: the transposed reads are conflict-free) and the parameter-layout row is updated as one
+// contiguous run.
 __global__ void permute_add_wgrad_all_kernel(Conv4Ptrs P, int Ci) {
   pdl_wait();
   pdl_trigger();
+  extern __shared__ float prow[];  // [taps][Ci + 1]
   const int l = blockIdx.y, co = blockIdx.x, taps = P.taps[l];
   const float* sc = P.w[l] + (size_t)co * Ci * taps;
   float* dw = P.acc[l] + (size_t)co * Ci * taps;
-  for (int ci = threadIdx.x; ci < Ci; ci += blockDim.x) {
-    for (int tap = 0; tap < taps; tap++) dw[(size_t)ci * taps + tap] += sc[(size_t)tap * Ci + ci];
+  const int n = Ci * taps;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int tap = i / Ci, ci = i - tap * Ci;
+    prow[tap * (Ci + 1) + ci] = sc[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / taps, tap = i - ci * taps;
+    dw[i] += prow[tap * (Ci + 1) + ci];
   }
 }
 
@@ -674,7 +684,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   {  // scratch (Co, k*Ci) layout -> parameter layout (Co, Ci, k), all four layers
     Conv4Ptrs P{};
     for (int i = 1; i < 5; i++) { P.w[i - 1] = dwp[i]; P.acc[i - 1] = gr->conv_w[i]; P.taps[i - 1] = kConvK[i]; P.s[i - 1] = kConvS[i]; }
-    CPC_CHECK_CUDA(launch_k(permute_add_wgrad_all_kernel, dim3(H, 4), dim3(256), 0, st, 1, P, H));
+    CPC_CHECK_CUDA(launch_k(permute_add_wgrad_all_kernel, dim3(H, 4), dim3(256), (size_t)8 * (H + 1) * sizeof(float), st, 1, P, H));
     CPC_LAUNCHED_N("permute_add_wgrad_all", st);
   }
   bool c0_done = false;

@@ -384,19 +384,30 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     dghp[q] = dgh + last * G + col;
   }
 
+  // operands of a step (dc_t, saved gates, h_{t-1}) are fetched ONE FULL STEP ahead of their use: a load issued at the top
+  // of the step that consumes it is still in flight (L2 / HBM latency) when the previous step's product has finished
+  float dcv_n[2], hp_n[2];
+  uint2 g4_n[2];
+  auto load_ops = [&](int tt) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      dcv_n[q] = *dcp[q];
+      g4_n[q] = *g4p[q];
+      if (tt > 0) hp_n[q] = *hpp[q];
+      else hp_n[q] = (h0 != nullptr && okq[q]) ? h0[(size_t)(b0 + 2 * t4 + q) * HAR + col] : 0.f;
+      dcp[q] -= HAR; g4p[q] -= HAR; hpp[q] -= HAR;
+    }
+  };
+  load_ops(S - 1);
+
   for (int it = 0; it < S; it++) {
     const int t = S - 1 - it, buf = t & 1;
-    // (A) this step's operands: raw loads only, consumed after the previous step's product
+    // (A) this step's operands were loaded during the previous step; start the loads of the next one
     float dcv[2], hp[2];
     uint2 g4[2];
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-      dcv[q] = *dcp[q];
-      g4[q] = *g4p[q];
-      if (t > 0) hp[q] = *hpp[q];
-      else hp[q] = (h0 != nullptr && okq[q]) ? h0[(size_t)(b0 + 2 * t4 + q) * HAR + col] : 0.f;
-      dcp[q] -= HAR; g4p[q] -= HAR; hpp[q] -= HAR;
-    }
+    for (int q = 0; q < 2; q++) { dcv[q] = dcv_n[q]; hp[q] = hp_n[q]; g4[q] = g4_n[q]; }
+    if (t > 0) load_ops(t - 1);
     // (B) finish the previous step
     if (it > 0) consume(it - 1);
     // (C) gate gradients of step t, publish dgh_t
@@ -429,15 +440,15 @@ gru_rec_bwd_mma_kernel(const float* __restrict__ dc, const float* __restrict__ c
     } else {
       publish_arrive();
     }
+    const ptrdiff_t back = -(ptrdiff_t)it * G;  // the store addresses are rebuilt from the fixed bases every step
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       if (okq[q]) {
-        bf16* pi = dgip[q];
-        bf16* ph = dghp[q];
+        bf16* pi = dgip[q] + back;
+        bf16* ph = dghp[q] + back;
         pi[0] = __float2bfloat16_rn(dr[q]); pi[HAR] = __float2bfloat16_rn(du[q]); pi[2 * HAR] = __float2bfloat16_rn(dnv[q]);
         ph[0] = __float2bfloat16_rn(dr[q]); ph[HAR] = __float2bfloat16_rn(du[q]); ph[2 * HAR] = __float2bfloat16_rn(dnr[q]);
       }
-      dgip[q] -= G; dghp[q] -= G;
     }
   }
   consume(S - 1);

@@ -123,7 +123,9 @@ size_t cpcb200_criterion_ws_bytes(const cpcb200_dims* d, int backward);
 int cpcb200_criterion_fwd(const cpcb200_dims* d, const float* c, const float* z, const float* w_pred,
                           const int32_t* ext, float* losses, float* acc, void* save, void* ws,
                           size_t ws_bytes, void* stream);
-/* dlosses (K) fp32 = d(total)/d(losses[k]).  dc (B,S,Har), dz (B,S,H), dw_pred (K,H,Har) are OVERWRITTEN. */
+/* dlosses (K) fp32 = d(total)/d(losses[k]).  dc (B,S,Har) and dz (B,S,H) are OVERWRITTEN; dw_pred (K,H,Har) is
+ * ACCUMULATED (+=) like every other parameter gradient of the library (the caller zero-fills it, or passes its
+ * gradient bucket). */
 int cpcb200_criterion_bwd(const cpcb200_dims* d, const float* c, const float* z, const float* w_pred,
                           const int32_t* ext, const float* dlosses, const void* save, float* dc, float* dz,
                           float* dw_pred, void* ws, size_t ws_bytes, void* stream);
