@@ -439,6 +439,16 @@ def run_ours(a):
                     "frac": t["frac"], "traffic": None, "peak_source": pk["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)"}
         else:
             roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+        # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture (profiles/), not measured live
+        try:
+            tj = json.load(open(os.path.join(REPO, "profiles", "r1n_traffic.json")))
+            roof["traffic"] = tj["kernels"][top]["dram_bytes_per_launch"]
+            roof["traffic_source"] = "profiles/r1n_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full)"
+            for k, ent in kernels.items():
+                if k in tj["kernels"]:
+                    ent["ncu_dram_bytes_per_launch"] = tj["kernels"][k]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roof["kernels"] = kernels
         roof["kernel_ms_per_step_total"] = round(sum(per_step.values()), 4)
 

@@ -3,6 +3,7 @@
     ncu -i gpurun_out/r1a_prof.ncu-rep --page raw --csv > /tmp/raw.csv && python profiles/summarize.py /tmp/raw.csv
 """
 import csv
+import re
 import sys
 
 COLS = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rd_MB"), ("dram__bytes_write.sum", "wr_MB"),
@@ -21,7 +22,9 @@ def main(path):
     print("| # | kernel | " + " | ".join(f"{n} ({u})" if u and n not in ("us",) else n for _, n, u in idx) + " |")
     print("|---|---|" + "---|" * len(idx))
     for i, r in enumerate(rows[2:]):
-        name = r[ki].split("::")[-1].split("(")[0][:40]
+        m = re.search(r"(\w+_kernel)(<[^>]*>)?", r[ki])
+        name = (m.group(1) + (m.group(2) or "")) if m else r[ki].split("::")[-1].split("(")[0]
+        name = name.replace("(int)", "").replace("(bool)", "").replace("__nv_bfloat16", "bf16")[:44]
         vals = []
         for j, n, u in idx:
             try:
