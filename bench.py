@@ -258,7 +258,7 @@ def run_ours(a):
     import torch.distributed as dist
     import cpc_audio_b200 as M
     from cpc_audio_b200 import _lib as L
-    from cpc_audio_b200.optim import FlatAdam, GradBucket
+    from cpc_audio_b200.optim import FlatAdam, GradBucket, PeerAdam
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -279,8 +279,18 @@ def run_ours(a):
         crit.eval()  # the heads implement the reference's eval() semantics (no dropout); gradients still flow
     params = list(crit.parameters()) + list(model.parameters())  # cpc/train.py:332 order
     use_graph = a.launch == "graph"
+    fused_ar = False  # all-reduce + Adam + zero_grad as ONE kernel over peer memory (PeerAdam) instead of NCCL + Adam
     if a.optimizer == "fused":
-        opt = FlatAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph, fuse_zero_grad=use_graph)
+        opt = None
+        if world > 1 and os.environ.get("CPC_B200_FUSED_AR", "1") != "0":
+            try:
+                opt = PeerAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, fuse_zero_grad=True)
+                fused_ar = True
+            except Exception as e:  # noqa: BLE001 - symmetric memory unavailable: NCCL all-reduce + fused Adam instead
+                log(f"peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
+                opt = None
+        if opt is None:
+            opt = FlatAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph, fuse_zero_grad=use_graph)
         bucket = opt.bucket
     else:
         opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph)
@@ -293,11 +303,17 @@ def run_ours(a):
     x_host = x_dev.cpu().pin_memory()
     loss_host = torch.empty(1, 12).pin_memory()
 
+    if world > 1 and not fused_ar and os.environ.get("CPC_B200_AR_OVERLAP", "0") != "0":  # measured slower: see DESIGN.md 5
+        enc = model.gEncoder  # all-reduce everything but conv0's gradients while the backward pass is still running
+        bucket.setup_overlap([enc.conv0.weight, enc.conv0.bias, enc.batchNorm0.weight, enc.batchNorm0.bias])
+
     def step_eager(x):
         c, z, _ = model(x, label)
         losses, acc = crit(c, z, label)
+        if world > 1 and not fused_ar:
+            bucket.arm_overlap()
         losses.sum().backward()
-        if world > 1:
+        if world > 1 and not fused_ar:
             bucket.allreduce()
         opt.step()
         opt.zero_grad()
@@ -308,7 +324,9 @@ def run_ours(a):
         try:
             from cpc_audio_b200.graph import GraphedTrainStep
             n_before = lib.cpcb200_launch_count()
-            gstep = GraphedTrainStep(model, crit, opt, x_dev, label, allreduce=bucket.allreduce if world > 1 else None, warmup=3)
+            nccl = world > 1 and not fused_ar
+            gstep = GraphedTrainStep(model, crit, opt, x_dev, label, allreduce=bucket.allreduce if nccl else None, warmup=3,
+                                     before_backward=bucket.arm_overlap if nccl else None)
             launches_per_replay = (lib.cpcb200_launch_count() - n_before) // 4  # 3 warm-up steps + the captured one
             launch_mode = "cuda-graph replay (GraphedTrainStep)"
         except Exception as e:  # noqa: BLE001 - report and run the eager loop instead (same kernels, same work)
@@ -468,6 +486,9 @@ def run_ours(a):
                                         "BASELINE config 4: --rnnMode transformer prediction heads (eval-mode), GRU context net, K=12, 128 negatives ")
                                        + f"batch={B}/GPU seq=20480, white-noise 16 kHz windows, random-init weights",
                            "global_batch": B * world, "seq_len": WINDOW, "parallelism": f"dp{world}", "optimizer": a.optimizer, "launch": launch_mode,
+                           "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                                 "one kernel: peer-memory all-reduce + Adam + zero_grad (cpcb200_allreduce_adam_step)"
+                                                 if fused_ar else "NCCL all-reduce + fused Adam"),
                            "l2": "no explicit flush: one step streams > 1 GB of activations (> 126 MB L2) between reuses"},
                 "e2e": {"value": sec / (ms_e2e / a.steps * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": ms_e2e / a.steps},

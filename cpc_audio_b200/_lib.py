@@ -37,6 +37,11 @@ class THeadParams(C.Structure):
 THEAD_FIELDS = ("wq", "wk", "wv", "wo", "krelpos", "ln1_w", "ln1_b", "w1", "b1", "w2", "b2", "ln2_w", "ln2_b")
 
 _P, _SZ, _I = C.c_void_p, C.c_size_t, C.c_int
+class Peers(C.Structure):
+    """cpcb200_peers: peer-mapped gradient buckets and signal words of the GPUs of one node."""
+    _fields_ = [("grads", C.c_void_p * 8), ("signals", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 _DP = C.POINTER(Dims)
 
 # name -> (restype, argtypes).  Must list every symbol include/cpc_b200.h declares (tests/test_abi.py checks).
@@ -64,6 +69,8 @@ SIGNATURES = {
     "cpcb200_criterion_t_fwd": (_I, [_DP, _P, _P, C.POINTER(THeadParams), _P, _P, _P, _P, _P, _SZ, _P]),
     "cpcb200_criterion_t_bwd": (_I, [_DP, _P, _P, C.POINTER(THeadParams), _P, _P, _P, _P, _P, C.POINTER(THeadParams), _P, _SZ, _P]),
     "cpcb200_adam_step": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
+    "cpcb200_encoder_bwd_set_event": (_I, [_P]),
+    "cpcb200_allreduce_adam_step": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int, _P]),
     "cpcb200_adam_step_dev": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int, _P]),
     "cpcb200_test_gemm_nt": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "cpcb200_test_gemm_tn": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

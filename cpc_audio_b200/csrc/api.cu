@@ -8,6 +8,7 @@
 #include <vector>
 
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace cpcb200 {
@@ -47,6 +48,9 @@ void prof_note(const char* name, cudaStream_t st) {
   if (e >= 0 && g_prof_last >= 0) g_prof_rec.push_back({name, g_prof_last, e});
   g_prof_last = e;
 }
+
+static std::atomic<void*> g_grads_ready_event{nullptr};
+cudaEvent_t take_grads_ready_event() { return static_cast<cudaEvent_t>(g_grads_ready_event.exchange(nullptr)); }
 
 bool pdl_enabled() {
   static const bool on = []() { const char* e = getenv("CPC_B200_PDL"); return !(e && atoi(e) == 0); }();
@@ -219,6 +223,142 @@ __global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, fl
       __threadfence();
       atomicAdd(state, 1);
     }
+  }
+}
+
+// ---- all-reduce + Adam + zero_grad over peer memory (cpcb200_allreduce_adam_step) ------------------------------------
+struct PeerPtrs { float* g[8]; unsigned* sig[8]; int rank, world; };
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_v4(float* p, const float4& v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// node-wide barrier, executed by the first `world` threads of block 0: tell every peer that this rank reached `epoch`,
+// wait until every peer has.  Epochs only grow, so a peer that is already one barrier ahead still satisfies the wait.
+__device__ __forceinline__ void node_barrier(const PeerPtrs& P, unsigned epoch) {
+  if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
+    __threadfence_system();
+    st_release_sys(P.sig[threadIdx.x] + P.rank, epoch);
+    const unsigned* mine = P.sig[P.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+      if (clock64() - t0 > (1ll << 33)) __trap();  // ~4 s: a rank that never arrives faults instead of hanging the GPU
+    }
+  }
+}
+
+template <bool ZERO>
+__global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, float* __restrict__ p, float* __restrict__ m,
+                                                             float* __restrict__ v, size_t n, float lr, float b1, float b2,
+                                                             float eps, float wd, int* __restrict__ state) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ float s_bc[2];
+  double* pw = reinterpret_cast<double*>(state + 2);
+  double p1 = 0.0, p2 = 0.0;
+  unsigned calls = 0;
+  if (threadIdx.x == 0) {
+    const int done = *reinterpret_cast<volatile int*>(state);
+    p1 = done == 0 ? (double)b1 : *reinterpret_cast<volatile double*>(pw);
+    p2 = done == 0 ? (double)b2 : *reinterpret_cast<volatile double*>(pw + 1);
+    s_bc[0] = (float)(1.0 - p1);
+    s_bc[1] = sqrtf((float)(1.0 - p2));
+  }
+  calls = (unsigned)*reinterpret_cast<volatile int*>(state + 6);  // node-barrier epoch base: 2 barriers per call
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+  const float step_size = lr / bc1;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  float* g = P.g[P.rank];
+
+  // ---- every rank's gradients are final ----
+  node_barrier(P, 2 * calls + 1);
+  grid.sync();
+  // ---- two-shot all-reduce, in place: this rank owns slice `rank` of every buffer ----
+  const size_t n4 = n / 4;
+  const size_t per = (n4 + P.world - 1) / P.world;
+  const size_t lo = per * P.rank, hi = lo + per < n4 ? lo + per : n4;
+  // (peer loads cost ~2 us each: all the loads of U quads are issued before the first add)
+  constexpr int U = 4;
+  for (size_t i0 = lo + tid; i0 < hi; i0 += U * nthr) {
+    float4 acc[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * nthr;
+      acc[u] = i < hi ? ld_relaxed_sys_v4(P.g[0] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int j = 1; j < P.world; j++) {
+      float4 t[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * nthr;
+        t[u] = i < hi ? ld_relaxed_sys_v4(P.g[j] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) { acc[u].x += t[u].x; acc[u].y += t[u].y; acc[u].z += t[u].z; acc[u].w += t[u].w; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * nthr;
+      if (i < hi)
+        for (int j = 0; j < P.world; j++) st_relaxed_sys_v4(P.g[j] + 4 * i, acc[u]);
+    }
+  }
+  if (P.rank == P.world - 1) {  // the < 4 floats past the last quad
+    for (size_t i = n4 * 4 + tid; i < n; i += nthr) {
+      float acc = 0.f;
+      for (int j = 0; j < P.world; j++) acc += *reinterpret_cast<volatile float*>(P.g[j] + i);
+      for (int j = 0; j < P.world; j++) *reinterpret_cast<volatile float*>(P.g[j] + i) = acc;
+    }
+  }
+  __threadfence_system();
+  grid.sync();
+  // ---- every slice of the local buffer has been written by its owner ----
+  node_barrier(P, 2 * calls + 2);
+  grid.sync();
+  // ---- Adam on the full local replica, gradients read past the L1 (peers wrote them) ----
+  auto upd = [&](float gi, float pi, float& mi, float& vi) {
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    mi = fmaf(b1, mi, (1.f - b1) * gi);
+    vi = fmaf(b2, vi, (1.f - b2) * gi * gi);
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    return pi - step_size * (mi / denom);
+  };
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (size_t i = tid; i < n4; i += nthr) {
+    const float4 gq = __ldcg(g4 + i);
+    float4 pq = p4[i], mq = m4[i], vq = v4[i];
+    pq.x = upd(gq.x, pq.x, mq.x, vq.x); pq.y = upd(gq.y, pq.y, mq.y, vq.y);
+    pq.z = upd(gq.z, pq.z, mq.z, vq.z); pq.w = upd(gq.w, pq.w, mq.w, vq.w);
+    m4[i] = mq; v4[i] = vq; p4[i] = pq;
+    if (ZERO) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += nthr) {
+    float mi = m[i], vi = v[i];
+    const float pn = upd(__ldcg(g + i), p[i], mi, vi);
+    m[i] = mi; v[i] = vi; p[i] = pn;
+    if (ZERO) g[i] = 0.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // every block read the state before the first grid.sync
+    pw[0] = p1 * (double)b1;
+    pw[1] = p2 * (double)b2;
+    state[6] = (int)(calls + 1);
+    __threadfence();
+    atomicAdd(state, 1);
   }
 }
 
@@ -414,6 +554,11 @@ int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   return 0;
 }
 
+int cpcb200_encoder_bwd_set_event(void* cuda_event) {
+  g_grads_ready_event.store(cuda_event);
+  return 0;
+}
+
 int cpcb200_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                           float beta2, float eps, float weight_decay, int32_t* state, int zero_grad, void* stream) {
   NOT_NULL(param); NOT_NULL(grad); NOT_NULL(exp_avg); NOT_NULL(exp_avg_sq); NOT_NULL(state);
@@ -433,6 +578,37 @@ int cpcb200_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_
     CPC_CHECK_CUDA(launch_k(adam_dev_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, 1, param, grad, exp_avg, exp_avg_sq, n,
                             lr, beta1, beta2, eps, weight_decay, reinterpret_cast<int*>(state)));
   CPC_LAUNCHED_N("adam", st);
+  return 0;
+}
+
+int cpcb200_allreduce_adam_step(const cpcb200_peers* peers, float* param, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int32_t* state, int zero_grad,
+                                void* stream) {
+  NOT_NULL(peers); NOT_NULL(param); NOT_NULL(exp_avg); NOT_NULL(exp_avg_sq); NOT_NULL(state);
+  if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world)
+    return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: rank %d / world %d (1..8 GPUs of one node)", peers->rank, peers->world);
+  PeerPtrs P{};
+  P.rank = peers->rank; P.world = peers->world;
+  for (int i = 0; i < peers->world; i++) {
+    if (!peers->grads[i] || !peers->signals[i]) return fail(CPCB200_ERR_NULL, "allreduce_adam: peer %d pointer is NULL", i);
+    if (reinterpret_cast<uintptr_t>(peers->grads[i]) & 15) return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: gradient buffers must be 16-byte aligned");
+    P.g[i] = static_cast<float*>(peers->grads[i]);
+    P.sig[i] = static_cast<unsigned*>(peers->signals[i]);
+  }
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+    return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: buffers must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(state) & 7) return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: state must be 8-byte aligned");
+  if (n == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  CPC_CHECK_CUDA(cudaGetDevice(&dev));
+  CPC_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const void* kern = zero_grad ? reinterpret_cast<const void*>(allreduce_adam_kernel<true>)
+                               : reinterpret_cast<const void*>(allreduce_adam_kernel<false>);
+  int* state_i = reinterpret_cast<int*>(state);
+  void* args[] = {&P, &param, &exp_avg, &exp_avg_sq, &n, &lr, &beta1, &beta2, &eps, &weight_decay, &state_i};
+  CPC_CHECK_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)(2 * sms)), dim3(256), args, 0, st));  // 2 CTAs per SM, all resident
+  CPC_LAUNCHED_N("allreduce_adam", st);
   return 0;
 }
 

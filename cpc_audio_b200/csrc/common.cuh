@@ -88,6 +88,10 @@ struct Carver {
 // no-ops and the stream order is the classic one.
 bool pdl_enabled();
 
+// one-shot hook (cpcb200_encoder_bwd_set_event): the next encoder backward records this event once every parameter
+// gradient except conv0's / batchNorm0's is final; returns nullptr when none is armed
+cudaEvent_t take_grads_ready_event();
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -672,6 +672,19 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       RowView Bv{sv + e.y[i - 1] + (size_t)(kPad - pp) * H, (long long)(Lin + 2 * kPad) * H, (long long)s * H, Lo, kConvK[i], s};
       wg[4 - i] = TnDesc{B, H, kConvK[i] * H, A, Bv, dwp[i], kConvK[i] * H, STORE_PLAIN, 0, 0};
     }
+    if (i == 1) {
+      // every du_i exists now: the four weight-gradient products run as ONE grouped launch BEFORE the last (largest) data
+      // gradient, so that all parameter gradients except conv0's are final ~200 us before the backward pass ends - the
+      // data-parallel all-reduce of those 99.9 % of the bucket overlaps dgrad_1 and the conv0 backward (GradBucket)
+      CPC_TRY(gemm_tn_group(g.bf16, 4, wg, st));  // wg[0] = layer 4 ... wg[3] = layer 1
+      {  // scratch (Co, k*Ci) layout -> parameter layout (Co, Ci, k), all four layers
+        Conv4Ptrs P{};
+        for (int l = 1; l < 5; l++) { P.w[l - 1] = dwp[l]; P.acc[l - 1] = gr->conv_w[l]; P.taps[l - 1] = kConvK[l]; P.s[l - 1] = kConvS[l]; }
+        CPC_CHECK_CUDA(launch_k(permute_add_wgrad_all_kernel, dim3(H, 4), dim3(256), (size_t)8 * (H + 1) * sizeof(float), st, 1, P, H));
+        CPC_LAUNCHED_N("permute_add_wgrad_all", st);
+      }
+      if (cudaEvent_t ev = take_grads_ready_event()) CPC_CHECK_CUDA(cudaEventRecord(ev, st));
+    }
     // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r].  All s residues in ONE GEMM with
     // N = s*H: row q of the product is the s consecutive input rows s q - p .. s q - p + s - 1.
     {
@@ -679,13 +692,6 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       OutView C{dy[i - 1] - (long long)pp * H, (long long)Lin * H, (long long)s * H, Lo + 1, 0, Lo + 1, H, pp};
       CPC_TRY(gemm_nt(g.bf16, false, B, s * H, 2 * H, A, wd[i], nullptr, C, st));
     }
-  }
-  CPC_TRY(gemm_tn_group(g.bf16, 4, wg, st));  // wg[0] = layer 4 ... wg[3] = layer 1
-  {  // scratch (Co, k*Ci) layout -> parameter layout (Co, Ci, k), all four layers
-    Conv4Ptrs P{};
-    for (int i = 1; i < 5; i++) { P.w[i - 1] = dwp[i]; P.acc[i - 1] = gr->conv_w[i]; P.taps[i - 1] = kConvK[i]; P.s[i - 1] = kConvS[i]; }
-    CPC_CHECK_CUDA(launch_k(permute_add_wgrad_all_kernel, dim3(H, 4), dim3(256), (size_t)8 * (H + 1) * sizeof(float), st, 1, P, H));
-    CPC_LAUNCHED_N("permute_add_wgrad_all", st);
   }
   bool c0_done = false;
   if constexpr (sizeof(T) == 2) {

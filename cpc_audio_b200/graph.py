@@ -18,9 +18,10 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, criterion, optimizer, example_batch, label, allreduce=None, warmup=3):
+    def __init__(self, model, criterion, optimizer, example_batch, label, allreduce=None, warmup=3, before_backward=None):
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.allreduce = allreduce
+        self.before_backward = before_backward  # e.g. GradBucket.arm_overlap
         self.static_x = example_batch.clone()
         self.label = label
         dev = example_batch.device
@@ -39,6 +40,8 @@ class GraphedTrainStep:
     def _body(self):
         c, z, _ = self.model(self.static_x, self.label)
         losses, acc = self.criterion(c, z, self.label)
+        if self.before_backward is not None:
+            self.before_backward()
         losses.sum().backward()
         if self.allreduce is not None:
             self.allreduce()

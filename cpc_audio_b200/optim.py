@@ -8,6 +8,7 @@ both moments flat as well, so ``optimizer.step()`` is one kernel (torch.optim.Ad
 """
 from __future__ import annotations
 
+import ctypes
 import weakref
 
 import torch
@@ -32,12 +33,16 @@ def sinks_for(params):
 
 
 class GradBucket:
-    def __init__(self, params):
+    def __init__(self, params, flat=None):
         self.params = [p for p in params]
         dev = self.params[0].device
         sizes = [p.numel() for p in self.params]
-        self.flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        if flat is None:
+            flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        assert flat.numel() == sum(sizes) and flat.dtype == torch.float32 and flat.is_contiguous()
+        self.flat = flat  # may live in symmetric (peer-mapped) memory: see PeerAdam
         self.views = [v.view_as(p) for v, p in zip(self.flat.split(sizes), self.params)]
+        self._overlap = None
         self.attach()
 
     def attach(self):
@@ -56,8 +61,60 @@ class GradBucket:
                 p.grad = v
 
     def allreduce(self):
+        """Sum the bucket over the data-parallel ranks (cpc/train.py:85 semantics).  If ``arm_overlap`` was called before
+        the backward pass, everything but the late (conv0 / batchNorm0) gradients is reduced on a side stream as soon as
+        the encoder backward signals that it is final - concurrently with the last data-gradient GEMM and the conv0
+        backward - and only the late range (a few KB) is reduced after the backward pass."""
         import torch.distributed as dist
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        ov = self._overlap
+        if ov is None or not ov["armed"]:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            return
+        ov["armed"] = False
+        cur = torch.cuda.current_stream(self.flat.device)
+        side = ov["side"]
+        side.wait_event(ov["ready"])
+        with torch.cuda.stream(side):
+            for lo, hi in ov["early"]:
+                dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM)
+            ov["done"].record(side)
+        for lo, hi in ov["late"]:
+            dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM)
+        cur.wait_event(ov["done"])
+
+    def setup_overlap(self, late_params):
+        """`late_params`: the parameters whose gradients only exist at the very end of the backward pass (the encoder's
+        conv0.weight / conv0.bias / batchNorm0.weight / batchNorm0.bias)."""
+        dev = self.flat.device
+        late_ids = {id(p) for p in late_params}
+        ranges, off = [], 0
+        for p in self.params:
+            n = p.numel()
+            ranges.append((off, off + n, id(p) in late_ids))
+            off += n
+        def merge(flag):
+            out = []
+            for lo, hi, is_late in ranges:
+                if is_late != flag:
+                    continue
+                if out and out[-1][1] == lo:
+                    out[-1] = (out[-1][0], hi)
+                else:
+                    out.append((lo, hi))
+            return out
+        ready, done = torch.cuda.Event(), torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))  # materialise the cudaEvent_t handles
+        done.record(torch.cuda.current_stream(dev))
+        self._overlap = {"early": merge(False), "late": merge(True), "side": torch.cuda.Stream(device=dev), "ready": ready,
+                         "done": done, "armed": False}
+
+    def arm_overlap(self):
+        """Call right before ``backward()``: the next encoder backward records the 'early gradients are final' event."""
+        ov = self._overlap
+        if ov is None:
+            return
+        L.check(L.lib().cpcb200_encoder_bwd_set_event(ctypes.c_void_p(ov["ready"].cuda_event)), "encoder_bwd_set_event")
+        ov["armed"] = True
 
 
 class FlatAdam:
@@ -76,7 +133,7 @@ class FlatAdam:
         for v, p in zip(self.flat_p.split(sizes), self.params):
             v.view_as(p).copy_(p.data)
             p.data = v.view_as(p)
-        self.bucket = GradBucket(self.params)
+        self.bucket = GradBucket(self.params, flat=self._alloc_grad_bucket(sum(sizes), dev))
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -85,6 +142,9 @@ class FlatAdam:
         self._steps = 0
         self._state = torch.zeros(8, device=dev, dtype=torch.int32) if self.capturable else None  # [steps, ticket, b1^t, b2^t]
         self._grads_clean = False
+
+    def _alloc_grad_bucket(self, n, dev):
+        return None  # GradBucket allocates an ordinary device buffer
 
     @property
     def steps(self):
@@ -114,3 +174,55 @@ class FlatAdam:
                     p.grad = v
             return
         self.bucket.zero()
+
+
+class PeerAdam(FlatAdam):
+    """FlatAdam whose ``step()`` also performs the data-parallel gradient exchange: ONE kernel per step does the
+    all-reduce(sum) of the bucket over the GPUs of the node through peer memory (NVLink / NVSwitch loads and stores, two
+    node-wide barriers on signal words), the Adam update and ``zero_grad`` (``cpcb200_allreduce_adam_step``) - instead of
+    an NCCL all-reduce followed by an optimizer kernel.  The gradient bucket and the signal words live in
+    ``torch.distributed._symmetric_memory`` (that module is only used to allocate and peer-map them).
+
+    Use it exactly like FlatAdam, WITHOUT calling ``bucket.allreduce()``; every rank must step the same number of times."""
+
+    def __init__(self, params, group=None, **kw):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self._symm, self._dist = symm, dist
+        self._group = group if group is not None else dist.group.WORLD
+        kw["capturable"] = True
+        try:  # older torch releases want the group registered first; newer ones do it on rendezvous
+            symm.enable_symm_mem_for_group(self._group.group_name)
+        except Exception:  # noqa: BLE001
+            pass
+        super().__init__(params, **kw)
+        dev = self.flat_p.device
+        self._hdl = symm.rendezvous(self.bucket.flat, self._group)
+        self._sig = symm.empty(64, dtype=torch.int32, device=dev)
+        self._sig.zero_()
+        self._sig_hdl = symm.rendezvous(self._sig, self._group)
+        world, rank = self._hdl.world_size, self._hdl.rank
+        if world > 8:
+            raise RuntimeError("PeerAdam: at most 8 GPUs (one NVSwitch node)")
+        self._peers = L.Peers()
+        for i in range(world):
+            self._peers.grads[i] = int(self._hdl.buffer_ptrs[i])
+            self._peers.signals[i] = int(self._sig_hdl.buffer_ptrs[i])
+        self._peers.rank, self._peers.world = rank, world
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self._group)  # every rank's buffers are zeroed and mapped before the first step
+
+    def _alloc_grad_bucket(self, n, dev):
+        flat = self._symm.empty(n, dtype=torch.float32, device=dev)
+        flat.zero_()
+        return flat
+
+    def step(self):
+        dev = self.flat_p.device
+        with torch.cuda.device(dev):
+            L.check(L.lib().cpcb200_allreduce_adam_step(ctypes.byref(self._peers), L.ptr(self.flat_p), L.ptr(self.exp_avg),
+                                                        L.ptr(self.exp_avg_sq), self.flat_p.numel(), self.lr, self.betas[0],
+                                                        self.betas[1], self.eps, self.weight_decay, L.ptr(self._state),
+                                                        1 if self.fuse_zero_grad else 0, L.stream_ptr(dev)),
+                    "allreduce_adam_step")
+        self._grads_clean = self.fuse_zero_grad

@@ -150,6 +150,12 @@ int cpcb200_criterion_t_bwd(const cpcb200_dims* d, const float* c, const float* 
                             const int32_t* ext, const float* dlosses, const void* save, float* dc, float* dz,
                             const cpcb200_thead_params* grads, void* ws, size_t ws_bytes, void* stream);
 
+/* One-shot hook for overlapping the data-parallel gradient all-reduce with the tail of the backward pass: the NEXT
+ * cpcb200_encoder_bwd call (from any thread) records `cuda_event` (a cudaEvent_t) on its stream at the point where every
+ * parameter gradient of the step except those of conv0 / batchNorm0 is final (the layer 1-4 weight gradients run before
+ * the last data gradient).  Pass NULL to disarm.  Process-wide: meant for one process per GPU. */
+int cpcb200_encoder_bwd_set_event(void* cuda_event);
+
 /* ---- fused Adam over a flat fp32 bucket (cpc/train.py:335-337,90-91; torch.optim.Adam semantics) -------- */
 int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
@@ -161,6 +167,26 @@ int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
 int cpcb200_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                           float beta1, float beta2, float eps, float weight_decay, int32_t* state, int zero_grad,
                           void* stream);
+
+/* ---- data-parallel exchange fused with the optimizer (the ONE collective of the path) --------------
+ * One kernel per step does  all-reduce(sum) of the flat gradient bucket over the `world` GPUs of the node  +  the Adam
+ * update of cpcb200_adam_step_dev  +  zero_grad, over PEER MEMORY (NVLink / NVSwitch loads and stores), instead of an
+ * NCCL all-reduce followed by an optimizer kernel:
+ *   barrier (every rank's backward pass is complete) -> rank r sums slice r of all `world` gradient buffers and writes the
+ *   sum back into slice r of every buffer (two-shot all-reduce, in place) -> barrier -> every rank applies Adam to its
+ *   full replica from its now-reduced local buffer and clears it.
+ * grads[i] = device pointer to rank i's gradient bucket (n floats, peer-mapped on this device; grads[rank] is the local
+ * one), signals[i] = rank i's signal words (>= 64 x uint32, zero-initialised, peer-mapped), both typically from
+ * torch.distributed._symmetric_memory.  state as in cpcb200_adam_step_dev (8 int32, zero-initialised).  Every rank must
+ * call it the same number of times.  The launch is cooperative (all CTAs co-resident) and graph-capturable. */
+typedef struct {
+  void* grads[8];
+  void* signals[8];
+  int32_t rank, world;
+} cpcb200_peers;
+int cpcb200_allreduce_adam_step(const cpcb200_peers* peers, float* param, float* exp_avg, float* exp_avg_sq, size_t n,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, int32_t* state,
+                                int zero_grad, void* stream);
 
 /* ---- test hooks: the GEMM building blocks, exposed so tests can pin them against torch.matmul ----------
  * C[M,N] = A[M,Kd] * B[N,Kd]^T (+bias[N]) ; C2[N1,N2] += A[M,N1]^T * B[M,N2].  dtype as in cpcb200_dims. */
