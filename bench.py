@@ -487,7 +487,8 @@ def run_ours(a):
                                        + f"batch={B}/GPU seq=20480, white-noise 16 kHz windows, random-init weights",
                            "global_batch": B * world, "seq_len": WINDOW, "parallelism": f"dp{world}", "optimizer": a.optimizer, "launch": launch_mode,
                            "gradient_exchange": ("none (1 GPU)" if world == 1 else
-                                                 "one kernel: peer-memory all-reduce + Adam + zero_grad (cpcb200_allreduce_adam_step)"
+                                                 "one kernel: peer-memory all-reduce + Adam + zero_grad (cpcb200_allreduce_adam_step"
+                                                 + (", NVSwitch multimem reduction)" if getattr(opt, "multicast", False) else ", peer loads/stores)")
                                                  if fused_ar else "NCCL all-reduce + fused Adam"),
                            "l2": "no explicit flush: one step streams > 1 GB of activations (> 126 MB L2) between reuses"},
                 "e2e": {"value": sec / (ms_e2e / a.steps * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4,

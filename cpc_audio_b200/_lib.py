@@ -39,7 +39,8 @@ THEAD_FIELDS = ("wq", "wk", "wv", "wo", "krelpos", "ln1_w", "ln1_b", "w1", "b1",
 _P, _SZ, _I = C.c_void_p, C.c_size_t, C.c_int
 class Peers(C.Structure):
     """cpcb200_peers: peer-mapped gradient buckets and signal words of the GPUs of one node."""
-    _fields_ = [("grads", C.c_void_p * 8), ("signals", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32)]
+    _fields_ = [("grads", C.c_void_p * 8), ("signals", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32),
+                ("grads_mc", C.c_void_p)]
 
 
 _DP = C.POINTER(Dims)

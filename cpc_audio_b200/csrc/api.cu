@@ -227,7 +227,17 @@ __global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, fl
 }
 
 // ---- all-reduce + Adam + zero_grad over peer memory (cpcb200_allreduce_adam_step) ------------------------------------
-struct PeerPtrs { float* g[8]; unsigned* sig[8]; int rank, world; };
+struct PeerPtrs { float* g[8]; unsigned* sig[8]; int rank, world; float* mc; };
+// NVSwitch in-fabric reduction: the sum over every GPU's copy of the 16 bytes at this multicast address / broadcast store
+__device__ __forceinline__ float4 multimem_ld_reduce_v4(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_v4(float* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -245,18 +255,30 @@ __device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
 __device__ __forceinline__ void st_relaxed_sys_v4(float* p, const float4& v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-// node-wide barrier, executed by the first `world` threads of block 0: tell every peer that this rank reached `epoch`,
-// wait until every peer has.  Epochs only grow, so a peer that is already one barrier ahead still satisfies the wait.
-__device__ __forceinline__ void node_barrier(const PeerPtrs& P, unsigned epoch) {
+// node-wide barrier on signal words.  arrive: one thread per peer (block 0) tells that peer this rank reached `epoch`;
+// wait: the first `world` threads of EVERY block poll this rank's own words (local memory, written by the peers) - no
+// grid-wide sync is needed to release the other blocks.  Epochs only grow, so a peer that is already one barrier ahead
+// still satisfies the wait.
+__device__ __forceinline__ void node_arrive(const PeerPtrs& P, unsigned epoch) {
   if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
     __threadfence_system();
     st_release_sys(P.sig[threadIdx.x] + P.rank, epoch);
+  }
+}
+__device__ __forceinline__ void node_wait(const PeerPtrs& P, unsigned epoch) {
+  if ((int)threadIdx.x < P.world) {
     const unsigned* mine = P.sig[P.rank] + threadIdx.x;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
       if (clock64() - t0 > (1ll << 33)) __trap();  // ~4 s: a rank that never arrives faults instead of hanging the GPU
     }
   }
+  __syncthreads();
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 template <bool ZERO>
@@ -282,15 +304,35 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, float* 
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
   float* g = P.g[P.rank];
 
+  // phase stamps (ns since kernel start) in this rank's signal words 40..44: read by tools/peer_adam_check.py
+  const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+  const unsigned long long t_start = stamp ? globaltimer_ns() : 0ull;
+  unsigned* dbg = P.sig[P.rank] + 40;
   // ---- every rank's gradients are final ----
-  node_barrier(P, 2 * calls + 1);
-  grid.sync();
+  node_arrive(P, 2 * calls + 1);
+  node_wait(P, 2 * calls + 1);
+  if (stamp) dbg[0] = (unsigned)(globaltimer_ns() - t_start);
   // ---- two-shot all-reduce, in place: this rank owns slice `rank` of every buffer ----
   const size_t n4 = n / 4;
   const size_t per = (n4 + P.world - 1) / P.world;
   const size_t lo = per * P.rank, hi = lo + per < n4 ? lo + per : n4;
   // (peer loads cost ~2 us each: all the loads of U quads are issued before the first add)
-  constexpr int U = 4;
+  constexpr int U = 8;
+  if (P.mc != nullptr) {
+    for (size_t i0 = lo + tid; i0 < hi; i0 += U * nthr) {
+      float4 acc[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * nthr;
+        if (i < hi) acc[u] = multimem_ld_reduce_v4(P.mc + 4 * i);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * nthr;
+        if (i < hi) multimem_st_v4(P.mc + 4 * i, acc[u]);
+      }
+    }
+  } else
   for (size_t i0 = lo + tid; i0 < hi; i0 += U * nthr) {
     float4 acc[U];
 #pragma unroll
@@ -322,11 +364,14 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, float* 
       for (int j = 0; j < P.world; j++) *reinterpret_cast<volatile float*>(P.g[j] + i) = acc;
     }
   }
-  __threadfence_system();
-  grid.sync();
+  __threadfence_system();  // this thread's peer stores are performed system-wide before it reports in
+  if (stamp) dbg[1] = (unsigned)(globaltimer_ns() - t_start);
+  grid.sync();  // every block of this rank is past its fence: block 0 may tell the peers
+  if (stamp) dbg[2] = (unsigned)(globaltimer_ns() - t_start);
   // ---- every slice of the local buffer has been written by its owner ----
-  node_barrier(P, 2 * calls + 2);
-  grid.sync();
+  node_arrive(P, 2 * calls + 2);
+  node_wait(P, 2 * calls + 2);
+  if (stamp) dbg[3] = (unsigned)(globaltimer_ns() - t_start);
   // ---- Adam on the full local replica, gradients read past the L1 (peers wrote them) ----
   auto upd = [&](float gi, float pi, float& mi, float& vi) {
     if (wd != 0.f) gi = fmaf(wd, pi, gi);
@@ -353,7 +398,8 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, float* 
     m[i] = mi; v[i] = vi; p[i] = pn;
     if (ZERO) g[i] = 0.f;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // every block read the state before the first grid.sync
+  if (stamp) dbg[4] = (unsigned)(globaltimer_ns() - t_start);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // every block read the state before the grid.sync
     pw[0] = p1 * (double)b1;
     pw[1] = p2 * (double)b2;
     state[6] = (int)(calls + 1);
@@ -589,6 +635,8 @@ int cpcb200_allreduce_adam_step(const cpcb200_peers* peers, float* param, float*
     return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: rank %d / world %d (1..8 GPUs of one node)", peers->rank, peers->world);
   PeerPtrs P{};
   P.rank = peers->rank; P.world = peers->world;
+  P.mc = static_cast<float*>(peers->grads_mc);
+  if (reinterpret_cast<uintptr_t>(P.mc) & 15) return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: multicast pointer must be 16-byte aligned");
   for (int i = 0; i < peers->world; i++) {
     if (!peers->grads[i] || !peers->signals[i]) return fail(CPCB200_ERR_NULL, "allreduce_adam: peer %d pointer is NULL", i);
     if (reinterpret_cast<uintptr_t>(peers->grads[i]) & 15) return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: gradient buffers must be 16-byte aligned");

@@ -183,6 +183,9 @@ typedef struct {
   void* grads[8];
   void* signals[8];
   int32_t rank, world;
+  void* grads_mc;  /* optional NVSwitch multicast mapping of the same gradient buckets (NULL: peer loads/stores): the
+                    * reduction of a slice is then ONE multimem.ld_reduce per 16 bytes, done inside the switch, and the
+                    * write-back ONE multimem.st */
 } cpcb200_peers;
 int cpcb200_allreduce_adam_step(const cpcb200_peers* peers, float* param, float* exp_avg, float* exp_avg_sq, size_t n,
                                 float lr, float beta1, float beta2, float eps, float weight_decay, int32_t* state,

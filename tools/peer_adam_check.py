@@ -32,7 +32,7 @@ for it in range(5):
     assert all(b.grad.eq(0).all() for b in p_new), "gradients not cleared"
     o_new.zero_grad()
 err = max(((a - b).abs().max() / a.abs().max().clamp_min(1.0)).item() for a, b in zip(p_ref, p_new))
-print(f"rank {rank}: steps {o_new.steps}, max rel param error vs NCCL + torch Adam: {err:.2e}", flush=True)
+print(f"rank {rank}: multicast={o_new.multicast} steps {o_new.steps}, max rel param error vs NCCL + torch Adam: {err:.2e}", flush=True)
 assert err < 5e-6, err
 
 # timing at the size of the CPC bucket (2.5 M floats)
@@ -60,6 +60,9 @@ def nccl_step():
 
 
 t_new, t_old = timeit(o_big.step), timeit(nccl_step)
+stamps = o_big._sig[40:45].tolist()
+print(f"rank {rank}: last fused step, ns since kernel start: barrier1 {stamps[0]}, slice reduced {stamps[1]}, grid sync {stamps[2]}, "
+      f"barrier2 {stamps[3]}, adam done {stamps[4]}", flush=True)
 if rank == 0:
     print(f"world {world}: fused peer-memory all-reduce+Adam {t_new:.1f} us/step; NCCL all-reduce + Adam kernel {t_old:.1f} us/step", flush=True)
 torch.cuda.synchronize(); dist.barrier()
