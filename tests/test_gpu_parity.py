@@ -9,6 +9,8 @@ committed reference fixtures.  Tolerances (stated per dtype, see DESIGN.md "Pari
 """
 import math
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -381,3 +383,17 @@ def test_transformer_heads_parity(name, dtype, built_lib):
             floor = 0.95 if (d.H < 256 or (k.endswith(".bias") and "conv" in k)) else 0.98
             assert _cos(out["grads"][k], gr) >= floor, (k, _cos(out["grads"][k], gr))
     assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else 0.03) + Hh.acc_tolerance(ref["logits"], d)).all()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node")
+def test_peer_adam_matches_nccl_allreduce_plus_adam(built_lib):
+    """cpcb200_allreduce_adam_step (all-reduce over peer memory + Adam + zero_grad in one kernel) on 2 GPUs against an NCCL
+    all-reduce + torch.optim.Adam on the same per-rank gradients (tools/peer_adam_check.py asserts <= 5e-6 relative)."""
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(repo, "tools", "peer_adam_check.py")],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "max rel param error" in r.stdout
