@@ -408,9 +408,11 @@ def run_ours(a):
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, a.steps)
-    t_load = time.time()
-    while clocks and time.time() - t_load < 0.6:  # keep the same load up for a few more sampler periods
+    # keep the same load up for ~0.5 s more (a few sampler periods); ms_e2e is the max over ranks, so every rank runs the
+    # same number of extra steps (they contain the gradient exchange)
+    for _ in range(min(2000, int(0.5 / max(ms_e2e / a.steps * 1e-3, 1e-5)))):
         e2e_step()
+    torch.cuda.synchronize(dev)
     clk = clocks.stop() if clocks else None
 
     # per-kernel timing pass (CUDA events on the launching stream, same workload, after the timed region)
