@@ -474,6 +474,10 @@ def run_ours(a):
                     ent["ncu_dram_bytes_per_launch"] = tj["kernels"][k]["dram_bytes_per_launch"]
         except Exception:
             pass
+        if "l2_scatter_add_gbs" in kernels[top]:  # the dominant kernel's real limiter, next to the contract's HBM column
+            roof["l2_scatter_add"] = {"achieved": kernels[top]["l2_scatter_add_gbs"], "ceiling": L2_RED_CEILING_GBS, "unit": "GB/s",
+                                      "frac": kernels[top]["frac_of_l2_scatter_add_ceiling"],
+                                      "note": "fp32 row reductions into the L2-resident dz; ceiling measured with tools/redbench.cu"}
         roof["kernels"] = kernels
         roof["kernel_ms_per_step_total"] = round(sum(per_step.values()), 4)
 

@@ -33,6 +33,20 @@ def sinks_for(params):
     return out
 
 
+def split_ranges(sizes, late):
+    """Flat-buffer ranges [lo, hi) of the early and of the late tensors, adjacent tensors of the same kind merged."""
+    out = ([], [])
+    off = 0
+    for n, is_late in zip(sizes, late):
+        dst = out[1 if is_late else 0]
+        if dst and dst[-1][1] == off:
+            dst[-1] = (dst[-1][0], off + n)
+        else:
+            dst.append((off, off + n))
+        off += n
+    return out
+
+
 class GradBucket:
     def __init__(self, params, flat=None):
         self.params = [p for p in params]
@@ -88,26 +102,12 @@ class GradBucket:
         conv0.weight / conv0.bias / batchNorm0.weight / batchNorm0.bias)."""
         dev = self.flat.device
         late_ids = {id(p) for p in late_params}
-        ranges, off = [], 0
-        for p in self.params:
-            n = p.numel()
-            ranges.append((off, off + n, id(p) in late_ids))
-            off += n
-        def merge(flag):
-            out = []
-            for lo, hi, is_late in ranges:
-                if is_late != flag:
-                    continue
-                if out and out[-1][1] == lo:
-                    out[-1] = (out[-1][0], hi)
-                else:
-                    out.append((lo, hi))
-            return out
+        early, late = split_ranges([p.numel() for p in self.params], [id(p) in late_ids for p in self.params])
         ready, done = torch.cuda.Event(), torch.cuda.Event()
         ready.record(torch.cuda.current_stream(dev))  # materialise the cudaEvent_t handles
         done.record(torch.cuda.current_stream(dev))
-        self._overlap = {"early": merge(False), "late": merge(True), "side": torch.cuda.Stream(device=dev), "ready": ready,
-                         "done": done, "armed": False}
+        self._overlap = {"early": early, "late": late, "side": torch.cuda.Stream(device=dev), "ready": ready, "done": done,
+                         "armed": False}
 
     def arm_overlap(self):
         """Call right before ``backward()``: the next encoder backward records the 'early gradients are final' event."""

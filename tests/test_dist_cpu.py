@@ -53,3 +53,17 @@ def test_flat_bucket_allreduce_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert all(out.get(r) for r in range(world))
+
+
+def test_split_ranges_for_overlapped_allreduce():
+    """GradBucket.setup_overlap: the late (conv0 / batchNorm0) tensors sit in the middle of the flat bucket; the early ranges
+    on both sides and the late range must tile it exactly, adjacent tensors merged."""
+    from cpc_audio_b200.optim import split_ranges
+    sizes = [786432, 2560, 256, 256, 256, 524288, 256, 196608, 768]
+    late = [False, True, True, True, True, False, False, False, False]
+    early, lt = split_ranges(sizes, late)
+    assert lt == [(786432, 786432 + 3328)]
+    assert early == [(0, 786432), (786432 + 3328, sum(sizes))]
+    covered = sorted(early + lt)
+    assert covered[0][0] == 0 and covered[-1][1] == sum(sizes) and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    assert split_ranges([4, 4], [True, False]) == ([(4, 8)], [(0, 4)])
