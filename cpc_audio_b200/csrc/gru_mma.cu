@@ -36,17 +36,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
-// ---- hidden-state exchange without a cluster barrier: every 32-bit store into a peer's shared memory also
-// completes 4 bytes on that peer's mbarrier (st.async), the consumer waits for the byte count of one step.
+// ---- hidden-state exchange without a cluster barrier: bulk shared->shared copies into the peers' shared memory complete
+// their byte count on the peer's mbarrier, the consumer waits for the byte count of one step.
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
   return r;
-}
-__device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
 }
 // one bulk copy local shared -> a peer's shared memory, completing `bytes` on the peer's mbarrier
 __device__ __forceinline__ void bulk_s2s(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {

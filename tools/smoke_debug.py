@@ -1,6 +1,6 @@
 """Development probe: f32 path, encoder + GRU + criterion gradients vs the CPU oracle for several batch sizes / seeds."""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from oracle import cpc_oracle as O
 from tests import helpers as Hh
 for B, seed, scale in ((1, 3, 30.0), (2, 3, 30.0), (2, 3, 1.0), (2, 11, 30.0), (3, 3, 30.0)):
