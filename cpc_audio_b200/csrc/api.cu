@@ -266,7 +266,8 @@ __device__ __forceinline__ void node_wait(const PeerPtrs& P, unsigned epoch) {
     const unsigned* mine = P.sig[P.rank] + threadIdx.x;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-      if (clock64() - t0 > (1ll << 33)) __trap();  // ~4 s: a rank that never arrives faults instead of hanging the GPU
+      if (clock64() - t0 > (1ll << 36)) __trap();  // ~35 s (ranks may start seconds apart while 8 processes load their
+                                                   // modules): a rank that never arrives faults instead of hanging the GPU
     }
   }
   __syncthreads();
