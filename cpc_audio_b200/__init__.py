@@ -8,7 +8,8 @@ See DESIGN.md (path, kernels, rooflines) and INTEGRATION.md (how the reference b
 from .model import ChannelNorm, CPCEncoder, CPCAR, CPCModel  # noqa: F401
 from .criterion import (BaseCriterion, PredictionNetwork, CPCUnsupersivedCriterion,  # noqa: F401
                         CPCUnsupervisedCriterion)
+from .transformers import TransformerLayer, buildTransformerAR  # noqa: F401
 from . import _lib  # noqa: F401
 
 __all__ = ["ChannelNorm", "CPCEncoder", "CPCAR", "CPCModel", "BaseCriterion", "PredictionNetwork",
-           "CPCUnsupersivedCriterion", "CPCUnsupervisedCriterion"]
+           "CPCUnsupersivedCriterion", "CPCUnsupervisedCriterion", "TransformerLayer", "buildTransformerAR"]

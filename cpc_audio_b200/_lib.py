@@ -31,7 +31,9 @@ class GruParams(C.Structure):
 
 class THeadParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("wq", "wk", "wv", "wo", "krelpos", "ln1_w", "ln1_b", "w1", "b1", "w2", "b2",
-                                          "ln2_w", "ln2_b")] + [("dff", C.c_int32), ("nheads", C.c_int32)]
+                                          "ln2_w", "ln2_b")] + [("dff", C.c_int32), ("nheads", C.c_int32),
+                                                                ("att_keep", C.c_void_p), ("ffn_keep", C.c_void_p),
+                                                                ("keep_scale", C.c_float)]
 
 
 THEAD_FIELDS = ("wq", "wk", "wv", "wo", "krelpos", "ln1_w", "ln1_b", "w1", "b1", "w2", "b2", "ln2_w", "ln2_b")
@@ -40,7 +42,7 @@ _P, _SZ, _I = C.c_void_p, C.c_size_t, C.c_int
 class Peers(C.Structure):
     """cpcb200_peers: peer-mapped gradient buckets and signal words of the GPUs of one node."""
     _fields_ = [("grads", C.c_void_p * 8), ("signals", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32),
-                ("grads_mc", C.c_void_p)]
+                ("grads_mc", C.c_void_p), ("timeout_ns", C.c_int64)]
 
 
 _DP = C.POINTER(Dims)
@@ -60,6 +62,14 @@ SIGNATURES = {
     "cpcb200_gru_ws_bytes": (_SZ, [_DP, _I]),
     "cpcb200_gru_fwd": (_I, [_DP, _P, _P, C.POINTER(GruParams), _P, _P, _P, _P, _SZ, _P]),
     "cpcb200_gru_bwd": (_I, [_DP, _P, _P, C.POINTER(GruParams), _P, _P, _P, _P, C.POINTER(GruParams), _P, _SZ, _P]),
+    "cpcb200_lstm_save_bytes": (_SZ, [_DP]),
+    "cpcb200_lstm_ws_bytes": (_SZ, [_DP, _I]),
+    "cpcb200_lstm_fwd": (_I, [_DP, _P, _P, _P, C.POINTER(GruParams), _P, _P, _P, _P, _P, _SZ, _P]),
+    "cpcb200_lstm_bwd": (_I, [_DP, _P, _P, _P, C.POINTER(GruParams), _P, _P, _P, _P, C.POINTER(GruParams), _P, _SZ, _P]),
+    "cpcb200_tlayer_save_bytes": (_SZ, [_DP, _I, _I]),
+    "cpcb200_tlayer_ws_bytes": (_SZ, [_DP, _I, _I, _I]),
+    "cpcb200_tlayer_fwd": (_I, [_DP, _P, C.POINTER(THeadParams), _P, _P, _P, _SZ, _P]),
+    "cpcb200_tlayer_bwd": (_I, [_DP, _P, C.POINTER(THeadParams), _P, _P, _P, C.POINTER(THeadParams), _P, _SZ, _P]),
     "cpcb200_sample_ext_idx": (_I, [_DP, _P, _P, _P, _P]),
     "cpcb200_criterion_save_bytes": (_SZ, [_DP]),
     "cpcb200_criterion_ws_bytes": (_SZ, [_DP, _I]),
@@ -70,8 +80,10 @@ SIGNATURES = {
     "cpcb200_criterion_t_fwd": (_I, [_DP, _P, _P, C.POINTER(THeadParams), _P, _P, _P, _P, _P, _SZ, _P]),
     "cpcb200_criterion_t_bwd": (_I, [_DP, _P, _P, C.POINTER(THeadParams), _P, _P, _P, _P, _P, C.POINTER(THeadParams), _P, _SZ, _P]),
     "cpcb200_adam_step": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
-    "cpcb200_encoder_bwd_set_event": (_I, [_P]),
-    "cpcb200_allreduce_adam_step": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int, _P]),
+    "cpcb200_encoder_bwd_set_event": (_I, [_P, _P]),
+    "cpcb200_allreduce_adam_step": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int,
+                                         _P, C.c_int, _P]),
+    "cpcb200_peer_reduce_range": (_I, [_P, _P, C.c_int, _P, _P]),
     "cpcb200_adam_step_dev": (_I, [_P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int, _P]),
     "cpcb200_test_gemm_nt": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "cpcb200_test_gemm_tn": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

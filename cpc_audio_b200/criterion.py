@@ -34,7 +34,30 @@ class _PredictorWeight(nn.Module):
         self.out_features = weight.shape[0]
 
 
-T_HEADS, T_DFF = 8, 2048  # cpc/transformers.py:98-99 defaults used by criterion.py:84-88
+T_HEADS, T_DFF, T_DROPOUT = 8, 2048, 0.1  # cpc/transformers.py:98-100 defaults used by criterion.py:84-88
+
+
+def draw_dropout_masks(n_layers, batch, seq, nheads, dff, p, device):
+    """Keep-masks of the train-mode dropouts of `n_layers` TransformerLayers applied one after the other
+    (transformers.py:49 on the attention probabilities (B*nheads, W, W), then :92 on the FFN hidden (B, W, dff)), drawn
+    with the SAME torch call the reference's nn.Dropout makes, on same-shaped fp32 tensors, in the same order: the fused
+    dropout kernel's mask depends on the generator state and the tensor's size only, so a reference run with the same
+    ``torch.cuda.manual_seed`` sees identical masks.  Returns uint8 tensors (n_layers, B*nheads, W, W), (n_layers, B*W, dff)."""
+    att = torch.empty(n_layers, batch * nheads, seq, seq, dtype=torch.uint8, device=device)
+    ffn = torch.empty(n_layers, batch * seq, dff, dtype=torch.uint8, device=device)
+    ones_a = torch.ones(batch * nheads, seq, seq, device=device)
+    ones_f = torch.ones(batch, seq, dff, device=device)
+    for k in range(n_layers):
+        att[k] = torch.nn.functional.dropout(ones_a, p, True) != 0
+        ffn[k] = (torch.nn.functional.dropout(ones_f, p, True) != 0).view(batch * seq, dff)
+    return att, ffn
+
+
+def _thead_struct(tensors, masks):
+    tp = L.THeadParams(*[t.data_ptr() for t in tensors], T_DFF, T_HEADS, None, None, 1.0)
+    if masks is not None:
+        tp.att_keep, tp.ffn_keep, tp.keep_scale = masks[0].data_ptr(), masks[1].data_ptr(), float(masks[2])
+    return tp
 
 
 class _Attention(nn.Module):
@@ -72,8 +95,12 @@ class _FFN(nn.Module):
 class _TransformerLayer(nn.Module):
     """Parameter holder with the module tree (hence state_dict keys) of transformers.py:98-106."""
 
-    def __init__(self, sizeSeq, dmodel, dff=T_DFF, nheads=T_HEADS):
+    def __init__(self, sizeSeq, dmodel, dff=T_DFF, nheads=T_HEADS, dropout=T_DROPOUT, compute_dtype=None):
         super().__init__()
+        if dff != T_DFF or nheads != T_HEADS:
+            raise NotImplementedError("cpc_audio_b200: TransformerLayer supports the reference defaults dff=2048, nheads=8")
+        self.dropout = float(dropout)
+        self.compute_dtype = compute_dtype or default_dtype()
         self.multihead = _MultiHead(sizeSeq, dmodel, nheads)
         self.ln_multihead = nn.LayerNorm(dmodel)
         self.ffnetwork = _FFN(dmodel, dff)
@@ -85,6 +112,67 @@ class _TransformerLayer(nn.Module):
                 self.ln_multihead.bias, self.ffnetwork.lin1.weight, self.ffnetwork.lin1.bias, self.ffnetwork.lin2.weight,
                 self.ffnetwork.lin2.bias, self.ln_ffnetwork.weight, self.ln_ffnetwork.bias]
 
+    def forward(self, x):
+        """transformers.py:109-111 over a whole window: x (B, S, D) -> (B, S, D).  This is how the layer runs as the
+        CONTEXT network (--arMode transformer, feature_loader.py:138-142); as a prediction head the criterion batches the K
+        layers itself.  train() applies the reference's dropout (masks drawn with torch's generator)."""
+        _require_cuda(x, "TransformerLayer")
+        B, S, D = x.shape
+        if S != self.multihead.Att.sizeSeq:
+            raise ValueError(f"TransformerLayer was built for sequences of {self.multihead.Att.sizeSeq} frames, got {S}")
+        masks = None
+        if self.training and self.dropout > 0:
+            att, ffn = self.dropoutMasks(B, S, x.device)
+            masks = (att, ffn, 1.0 / (1.0 - self.dropout))
+        return _TLayerFn.apply(x, _dtype_code(self.compute_dtype), masks, *self.thead_tensors())
+
+    def dropoutMasks(self, batchSize, seqSize, device):
+        """Train-mode keep-masks of this layer: attention (1, B*nheads, S, S), FFN (1, B*S, dff), uint8."""
+        return draw_dropout_masks(1, batchSize, seqSize, T_HEADS, T_DFF, self.dropout, device)
+
+
+class _TLayerFn(torch.autograd.Function):
+    """One TransformerLayer over (B, S, D): cpcb200_tlayer_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, x, dtype_code, masks, *params):
+        lib = L.lib()
+        B, S, D = x.shape
+        dev = x.device
+        x = x.contiguous().float()
+        params = [p.detach().contiguous() for p in params]
+        tp = _thead_struct(params, masks)
+        d = L.make_dims(B, S * 160, D, D, 1, 1, 1, dtype_code)
+        y = torch.empty(B, S, D, device=dev, dtype=torch.float32)
+        save = _bytes(lib.cpcb200_tlayer_save_bytes(d, T_DFF, T_HEADS), dev)
+        wsn = lib.cpcb200_tlayer_ws_bytes(d, T_DFF, T_HEADS, 0)
+        ws = _bytes(wsn, dev)
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_tlayer_fwd(d, L.ptr(x), tp, L.ptr(y), L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)), "tlayer_fwd")
+        ctx.save_for_backward(x, save, *params)
+        ctx.masks = masks
+        ctx.dims = (B, S, D, dtype_code)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.lib()
+        x, save, *params = ctx.saved_tensors
+        B, S, D, dtype_code = ctx.dims
+        dev = x.device
+        d = L.make_dims(B, S * 160, D, D, 1, 1, 1, dtype_code)
+        tp = _thead_struct(params, ctx.masks)
+        grads = [torch.zeros_like(t) for t in params]
+        tg = _thead_struct(grads, None)
+        dx = torch.empty_like(x)
+        wsn = lib.cpcb200_tlayer_ws_bytes(d, T_DFF, T_HEADS, 1)
+        ws = _bytes(wsn, dev)
+        dy = dy.contiguous().float()
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_tlayer_bwd(d, L.ptr(x), tp, L.ptr(dy), L.ptr(save), L.ptr(dx), tg, L.ptr(ws), wsn,
+                                           L.stream_ptr(dev)), "tlayer_bwd")
+        return (dx, None, None, *grads)
+
 
 class PredictionNetwork(nn.Module):
     """cpc/criterion/criterion.py:44-95: K prediction heads, ``rnnMode`` 'linear' (nn.Linear, criterion.py:89-95) or
@@ -95,7 +183,8 @@ class PredictionNetwork(nn.Module):
         super().__init__()
         if rnnMode in ("RNN", "LSTM", "ffd", "conv4", "conv8", "conv12"):
             raise NotImplementedError(f"cpc_audio_b200: rnnMode={rnnMode!r} prediction heads are outside the accelerated "
-                                      f"hot path of this build (use --rnnMode linear or --rnnMode transformer)")
+                                      f"hot path of this build (use --rnnMode linear or --rnnMode transformer; both train "
+                                      f"and evaluate through the unmodified cpc/train.py)")
         if dropout:
             raise NotImplementedError("cpc_audio_b200: criterion dropout is outside the accelerated hot path")
         self.RESIDUAL_STD = 0.01
@@ -108,6 +197,7 @@ class PredictionNetwork(nn.Module):
             if sizeInputSeq > 128:
                 raise NotImplementedError("cpc_audio_b200: transformer heads support at most 128 anchor positions")
             self.sizeInputSeq = sizeInputSeq
+            # criterion.py:84-88: buildTransformerAR(dimOutputEncoder, 1, sizeInputSeq, False) -> nn.Sequential(TransformerLayer)
             self.predictors = nn.ModuleList([nn.Sequential(_TransformerLayer(sizeInputSeq, dimOutputEncoder))
                                              for _ in range(nPredicts)])
             return
@@ -202,7 +292,7 @@ class _CriterionTFn(torch.autograd.Function):
     """Transformer heads + scoring + InfoNCE.  params = 13 tensors per head, head-major (see _TransformerLayer)."""
 
     @staticmethod
-    def forward(ctx, c, z, ext, dims, *params):
+    def forward(ctx, c, z, ext, dims, masks, *params):
         lib = L.lib()
         B, S, H, Har, K, N, dtype_code = dims
         dev = c.device
@@ -210,7 +300,7 @@ class _CriterionTFn(torch.autograd.Function):
         z = z.contiguous().float()
         nf = len(L.THEAD_FIELDS)
         stacked = [torch.stack([params[k * nf + j].detach() for k in range(K)]).contiguous() for j in range(nf)]
-        tp = L.THeadParams(*[t.data_ptr() for t in stacked], T_DFF, T_HEADS)
+        tp = _thead_struct(stacked, masks)
         d = L.make_dims(B, S * 160, H, Har, K, N, 1, dtype_code)
         losses = torch.empty(K, device=dev, dtype=torch.float32)
         acc = torch.empty(K, device=dev, dtype=torch.float32)
@@ -222,6 +312,7 @@ class _CriterionTFn(torch.autograd.Function):
                                                 L.ptr(ws), wsn, L.stream_ptr(dev)), "criterion_t_fwd")
         ctx.save_for_backward(c, z, ext, save, *stacked)
         ctx.dims = dims
+        ctx.masks = masks
         ctx.mark_non_differentiable(acc)
         return losses, acc
 
@@ -232,9 +323,9 @@ class _CriterionTFn(torch.autograd.Function):
         B, S, H, Har, K, N, dtype_code = ctx.dims
         dev = c.device
         d = L.make_dims(B, S * 160, H, Har, K, N, 1, dtype_code)
-        tp = L.THeadParams(*[t.data_ptr() for t in stacked], T_DFF, T_HEADS)
+        tp = _thead_struct(stacked, ctx.masks)
         grads = [torch.zeros_like(t) for t in stacked]
-        tg = L.THeadParams(*[t.data_ptr() for t in grads], T_DFF, T_HEADS)
+        tg = _thead_struct(grads, None)
         dc = torch.empty_like(c)
         dz = torch.empty_like(z)
         wsn = lib.cpcb200_criterion_t_ws_bytes(d, T_DFF, T_HEADS, 1)
@@ -245,7 +336,7 @@ class _CriterionTFn(torch.autograd.Function):
                                                 L.ptr(dz), tg, L.ptr(ws), wsn, L.stream_ptr(dev)), "criterion_t_bwd")
         nf = len(L.THEAD_FIELDS)
         flat = [grads[j][k] for k in range(K) for j in range(nf)]
-        return (dc, dz, None, None, *flat)
+        return (dc, dz, None, None, None, *flat)
 
 
 class CPCUnsupersivedCriterion(BaseCriterion):
@@ -277,6 +368,11 @@ class CPCUnsupersivedCriterion(BaseCriterion):
         seqIdx = torch.randint(low=1, high=seqSize, size=(n,), device=device)
         return batchIdx, seqIdx
 
+    def dropoutMasks(self, batchSize, windowSize, device, p):
+        """Train-mode dropout masks of the K transformer heads, head by head (att_k, ffn_k), as PredictionNetwork.forward
+        (criterion.py:106-108) would draw them."""
+        return draw_dropout_masks(self.nPredicts, batchSize, windowSize, T_HEADS, T_DFF, p, device)
+
     def extIndices(self, batchIdx, seqIdx, dims):
         """criterion.py:191-199 on the device: ext = ((seqIdx + w) mod S) + batchIdx * S, int32 (B, N, W)."""
         B, S, H, Har, K, N, dtype_code = dims
@@ -300,14 +396,15 @@ class CPCUnsupersivedCriterion(BaseCriterion):
         batchIdx, seqIdx = self.sampleIndices(batchSize, windowSize, seqSize, encodedData.device)
         ext = self.extIndices(batchIdx, seqIdx, dims)
         if self.wPrediction.transformer:
-            if self.training:
-                raise NotImplementedError("cpc_audio_b200: the transformer prediction heads apply dropout 0.1 in train() mode "
-                                          "(transformers.py:18,92); this build implements their eval() semantics - call "
-                                          "criterion.eval() (gradients are still computed)")
             if windowSize != self.wPrediction.sizeInputSeq:
                 raise ValueError(f"transformer heads were built for {self.wPrediction.sizeInputSeq} positions, got {windowSize}")
+            masks = None
+            p_drop = self.wPrediction.predictors[0][0].dropout
+            if self.training and p_drop > 0:  # transformers.py:49,92: drawn AFTER the negatives (criterion.py:234 precedes :241)
+                att, ffn = self.dropoutMasks(batchSize, windowSize, cFeature.device, p_drop)
+                masks = (att, ffn, 1.0 / (1.0 - p_drop))
             params = [t for p in self.wPrediction.predictors for t in p[0].thead_tensors()]
-            losses, acc = _CriterionTFn.apply(cFeature, encodedData, ext, dims, *params)
+            losses, acc = _CriterionTFn.apply(cFeature, encodedData, ext, dims, masks, *params)
             return losses.view(1, -1), acc.view(1, -1)
         w_flat = self.wPrediction.stacked()
         weights = [p.weight for p in self.wPrediction.predictors]

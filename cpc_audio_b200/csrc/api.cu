@@ -49,8 +49,18 @@ void prof_note(const char* name, cudaStream_t st) {
   g_prof_last = e;
 }
 
-static std::atomic<void*> g_grads_ready_event{nullptr};
-cudaEvent_t take_grads_ready_event() { return static_cast<cudaEvent_t>(g_grads_ready_event.exchange(nullptr)); }
+// one-shot 'early gradients are final' events, keyed by the stream the encoder backward will run on (one entry per
+// armed stream: DataParallel threads / several processes' streams do not see each other's events)
+static std::mutex g_ev_mu;
+static std::map<cudaStream_t, cudaEvent_t> g_grads_ready_events;
+cudaEvent_t take_grads_ready_event(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_ev_mu);
+  auto it = g_grads_ready_events.find(st);
+  if (it == g_grads_ready_events.end()) return nullptr;
+  cudaEvent_t ev = it->second;
+  g_grads_ready_events.erase(it);
+  return ev;
+}
 
 bool pdl_enabled() {
   static const bool on = []() { const char* e = getenv("CPC_B200_PDL"); return !(e && atoi(e) == 0); }();
@@ -67,18 +77,24 @@ int fail(int code, const char* fmt, ...) {
 
 int make_geo(const cpcb200_dims* d, Geo* g) {
   if (!d) return fail(CPCB200_ERR_NULL, "dims is NULL");
-  if (d->B <= 0 || d->L <= 0 || d->L % 160 != 0) return fail(CPCB200_ERR_BAD_DIMS, "B=%d L=%d (L must be a positive multiple of 160)", d->B, d->L);
+  if (d->B <= 0 || d->L <= 0) return fail(CPCB200_ERR_BAD_DIMS, "B=%d L=%d", d->B, d->L);
   if (d->H % 64 != 0 || d->H <= 0 || d->H > 512) return fail(CPCB200_ERR_BAD_DIMS, "H=%d must be a multiple of 64 in [64,512]", d->H);
   if (d->Har % 64 != 0 || d->Har <= 0 || d->Har > 512) return fail(CPCB200_ERR_BAD_DIMS, "Har=%d must be a multiple of 64 in [64,512]", d->Har);
   if (d->nLayers < 1 || d->nLayers > CPCB200_MAX_GRU_LAYERS) return fail(CPCB200_ERR_BAD_DIMS, "nLayers=%d", d->nLayers);
   if (d->dtype != CPCB200_F32 && d->dtype != CPCB200_BF16) return fail(CPCB200_ERR_UNSUPPORTED, "dtype=%d", d->dtype);
   g->B = d->B; g->L = d->L; g->H = d->H; g->Har = d->Har; g->K = d->K; g->N = d->N; g->nL = d->nLayers;
-  g->S = d->L / 160;
-  g->W = g->S - d->K;
   g->bf16 = d->dtype == CPCB200_BF16;
+  // frames per window: the conv stack of cpc/model.py:83-92 (L/160 when L is a multiple of 160; any L that leaves at least
+  // one frame after every layer is accepted - feature extraction feeds chunks of arbitrary length, feature_loader.py:228-269)
   int L = d->L;
-  for (int i = 0; i < 5; i++) { L = (L + 2 * kConvP[i] - kConvK[i]) / kConvS[i] + 1; g->Lout[i] = L; }
-  if (g->Lout[4] != g->S) return fail(CPCB200_ERR_BAD_DIMS, "internal: conv stack length %d != S %d", g->Lout[4], g->S);
+  for (int i = 0; i < 5; i++) {
+    const int num = L + 2 * kConvP[i] - kConvK[i];
+    if (num < 0) return fail(CPCB200_ERR_BAD_DIMS, "L=%d samples is too short for the encoder (no output frame after conv%d)", d->L, i);
+    L = num / kConvS[i] + 1;
+    g->Lout[i] = L;
+  }
+  g->S = g->Lout[4];
+  g->W = g->S - d->K;
   return 0;
 }
 
@@ -106,6 +122,18 @@ int criterion_fwd(const Geo&, const float*, const float*, const float*, const cp
                   void*, void*, size_t, cudaStream_t);
 int criterion_bwd(const Geo&, const float*, const float*, const float*, const cpcb200_thead_params*, const int*, const float*,
                   const void*, float*, float*, float*, const cpcb200_thead_params*, void*, size_t, cudaStream_t);
+
+size_t lstm_save_bytes(const Geo& g);
+size_t lstm_ws_bytes(const Geo& g, int mode);
+int lstm_fwd(const Geo&, const float*, const float*, const float*, const cpcb200_gru_params*, float*, float*, float*, void*, void*,
+             size_t, cudaStream_t);
+int lstm_bwd(const Geo&, const float*, const float*, const float*, const cpcb200_gru_params*, const float*, const float*, const void*,
+             float*, const cpcb200_gru_params*, void*, size_t, cudaStream_t);
+size_t tlayer_save_bytes(const Geo& g);
+size_t tlayer_ws_bytes(const Geo& g, int backward);
+int tlayer_fwd(const Geo&, const float*, const cpcb200_thead_params*, float*, void*, void*, size_t, cudaStream_t);
+int tlayer_bwd(const Geo&, const float*, const cpcb200_thead_params*, const float*, const void*, float*, const cpcb200_thead_params*,
+               void*, size_t, cudaStream_t);
 
 int gemm_nt_simt(bool, bool, int, int, int, const RowView&, const void*, const float*, const OutView&, cudaStream_t);
 int gemm_tn_simt(bool, int, int, int, const RowView&, const RowView&, float*, int, int, int, int, cudaStream_t);
@@ -165,6 +193,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// words of the device-side optimizer state (16 x int32, include/cpc_b200.h)
+constexpr int kStSteps = 0, kStTicket = 1, kStPow = 2, kStEpoch = 6, kStErr = 7, kStLr = 8, kStEarlyEpoch = 9, kStEarlyTicket = 10;
+
 // graph-capturable variant: step count on the device (state[0]) together with beta1^step and beta2^step as running
 // float64 products (state[2..5]; double-precision pow() in the kernel costs ~90 us on this part), the last block to
 // finish (ticket in state[1]) publishes the next step's values - every block has read the current ones by then
@@ -173,7 +204,7 @@ __global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, fl
                                 size_t n, float lr, float b1, float b2, float eps, float wd, int* __restrict__ state) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float s_bc[2];
+  __shared__ float s_bc[3];
   double* pw = reinterpret_cast<double*>(state + 2);  // beta1^(steps+1), beta2^(steps+1) once steps > 0
   double p1 = 0.0, p2 = 0.0;
   if (threadIdx.x == 0) {
@@ -182,10 +213,11 @@ __global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, fl
     p2 = done == 0 ? (double)b2 : *reinterpret_cast<volatile double*>(pw + 1);
     s_bc[0] = (float)(1.0 - p1);
     s_bc[1] = sqrtf((float)(1.0 - p2));
+    s_bc[2] = lr < 0.f ? __int_as_float(*reinterpret_cast<volatile int*>(state + kStLr)) : lr;  // lr < 0: device-side learning rate
   }
   __syncthreads();
   const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
-  const float step_size = lr / bc1;
+  const float step_size = s_bc[2] / bc1;
   auto upd = [&](float gi, float pi, float& mi, float& vi) {
     if (wd != 0.f) gi = fmaf(wd, pi, gi);
     mi = fmaf(b1, mi, (1.f - b1) * gi);
@@ -226,8 +258,13 @@ __global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, fl
   }
 }
 
-// ---- all-reduce + Adam + zero_grad over peer memory (cpcb200_allreduce_adam_step) ------------------------------------
-struct PeerPtrs { float* g[8]; unsigned* sig[8]; int rank, world; float* mc; };
+// ---- all-reduce + Adam + zero_grad over peer memory (cpcb200_allreduce_adam_step, cpcb200_peer_reduce_range) --------
+struct PeerPtrs { float* g[8]; unsigned* sig[8]; int rank, world; float* mc; long long timeout_ns; };
+struct RangeList { long long lo[4], hi[4]; int n; };  // [lo, hi) in floats; lo a multiple of 4
+// signal words of a rank (>= 64 x uint32): [0..7] arrivals at the step kernel's barriers (word j is written by rank j),
+// [16..23] arrivals at the early-reduce kernel's barrier, [40..44] phase stamps of the last step kernel (debug)
+constexpr int kSigStep = 0, kSigEarly = 16, kSigDbg = 40;
+
 // NVSwitch in-fabric reduction: the sum over every GPU's copy of the 16 bytes at this multicast address / broadcast store
 __device__ __forceinline__ float4 multimem_ld_reduce_v4(const float* p) {
   float4 v;
@@ -247,6 +284,11 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // Slice data is moved with ordinary L2-level accesses (ld.global.cg / st.global.cg): the node barriers (release / acquire
 // at system scope) order them, and sys-scoped data accesses measured ~4x slower than the link on this path.
 __device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -254,66 +296,37 @@ __device__ __forceinline__ void st_relaxed_sys_v4(float* p, const float4& v) { _
 // node-wide barrier on signal words.  arrive: one thread per peer (block 0) tells that peer this rank reached `epoch`;
 // wait: the first `world` threads of EVERY block poll this rank's own words (local memory, written by the peers) - no
 // grid-wide sync is needed to release the other blocks.  Epochs only grow, so a peer that is already one barrier ahead
-// still satisfies the wait.
-__device__ __forceinline__ void node_arrive(const PeerPtrs& P, unsigned epoch) {
+// still satisfies the wait.  A wait that exceeds P.timeout_ns returns false (block-uniform): the caller records the
+// error in the optimizer state and leaves the kernel without touching the parameters - no trap, the context survives.
+__device__ __forceinline__ void node_arrive(const PeerPtrs& P, int base, unsigned epoch) {
   if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
     __threadfence_system();
-    st_release_sys(P.sig[threadIdx.x] + P.rank, epoch);
+    st_release_sys(P.sig[threadIdx.x] + base + P.rank, epoch);
   }
 }
-__device__ __forceinline__ void node_wait(const PeerPtrs& P, unsigned epoch) {
+__device__ __forceinline__ bool node_wait(const PeerPtrs& P, int base, unsigned epoch) {
+  int bad = 0;
   if ((int)threadIdx.x < P.world) {
-    const unsigned* mine = P.sig[P.rank] + threadIdx.x;
-    const long long t0 = clock64();
+    const unsigned* mine = P.sig[P.rank] + base + threadIdx.x;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
     while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-      if (clock64() - t0 > (1ll << 36)) __trap();  // ~35 s (ranks may start seconds apart while 8 processes load their
-                                                   // modules): a rank that never arrives faults instead of hanging the GPU
+      if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > (unsigned long long)P.timeout_ns) { bad = 1; break; }
     }
   }
-  __syncthreads();
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
+  return __syncthreads_or(bad) == 0;
 }
 
-template <bool ZERO>
-__global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, float* __restrict__ p, float* __restrict__ m,
-                                                             float* __restrict__ v, size_t n, float lr, float b1, float b2,
-                                                             float eps, float wd, int* __restrict__ state) {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  __shared__ float s_bc[2];
-  double* pw = reinterpret_cast<double*>(state + 2);
-  double p1 = 0.0, p2 = 0.0;
-  unsigned calls = 0;
-  if (threadIdx.x == 0) {
-    const int done = *reinterpret_cast<volatile int*>(state);
-    p1 = done == 0 ? (double)b1 : *reinterpret_cast<volatile double*>(pw);
-    p2 = done == 0 ? (double)b2 : *reinterpret_cast<volatile double*>(pw + 1);
-    s_bc[0] = (float)(1.0 - p1);
-    s_bc[1] = sqrtf((float)(1.0 - p2));
-  }
-  calls = (unsigned)*reinterpret_cast<volatile int*>(state + 6);  // node-barrier epoch base: 2 barriers per call
-  __syncthreads();
-  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
-  const float step_size = lr / bc1;
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
-  float* g = P.g[P.rank];
-
-  // phase stamps (ns since kernel start) in this rank's signal words 40..44: read by tools/peer_adam_check.py
-  const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
-  const unsigned long long t_start = stamp ? globaltimer_ns() : 0ull;
-  unsigned* dbg = P.sig[P.rank] + 40;
-  // ---- every rank's gradients are final ----
-  node_arrive(P, 2 * calls + 1);
-  node_wait(P, 2 * calls + 1);
-  if (stamp) dbg[0] = (unsigned)(globaltimer_ns() - t_start);
-  // ---- two-shot all-reduce, in place: this rank owns slice `rank` of every buffer ----
-  const size_t n4 = n / 4;
+// Two-shot all-reduce of the float range [lo, hi), in place: this rank sums its 1/world slice of every rank's copy and
+// writes the sum back into that slice of every copy.  With a multicast mapping the sum is ONE multimem.ld_reduce per 16
+// bytes, computed inside the NVSwitch, and the write-back ONE multimem.st.
+// (peer loads cost ~2 us each: all the loads of U quads are issued before the first add)
+__device__ __forceinline__ void reduce_my_slice(const PeerPtrs& P, long long lo_f, long long hi_f, size_t tid, size_t nthr) {
+  const size_t n4 = (size_t)(hi_f - lo_f) / 4, base4 = (size_t)lo_f / 4;
   const size_t per = (n4 + P.world - 1) / P.world;
-  const size_t lo = per * P.rank, hi = lo + per < n4 ? lo + per : n4;
-  // (peer loads cost ~2 us each: all the loads of U quads are issued before the first add)
+  const size_t lo = base4 + per * P.rank;
+  size_t hi = lo + per;
+  if (hi > base4 + n4) hi = base4 + n4;
   constexpr int U = 8;
   if (P.mc != nullptr) {
     for (size_t i0 = lo + tid; i0 < hi; i0 += U * nthr) {
@@ -329,45 +342,119 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, float* 
         if (i < hi) multimem_st_v4(P.mc + 4 * i, acc[u]);
       }
     }
-  } else
-  for (size_t i0 = lo + tid; i0 < hi; i0 += U * nthr) {
-    float4 acc[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + (size_t)u * nthr;
-      acc[u] = i < hi ? ld_relaxed_sys_v4(P.g[0] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int j = 1; j < P.world; j++) {
-      float4 t[U];
+  } else {
+    for (size_t i0 = lo + tid; i0 < hi; i0 += U * nthr) {
+      float4 acc[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const size_t i = i0 + (size_t)u * nthr;
-        t[u] = i < hi ? ld_relaxed_sys_v4(P.g[j] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[u] = i < hi ? ld_relaxed_sys_v4(P.g[0] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int j = 1; j < P.world; j++) {
+        float4 t[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * nthr;
+          t[u] = i < hi ? ld_relaxed_sys_v4(P.g[j] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) { acc[u].x += t[u].x; acc[u].y += t[u].y; acc[u].z += t[u].z; acc[u].w += t[u].w; }
       }
 #pragma unroll
-      for (int u = 0; u < U; u++) { acc[u].x += t[u].x; acc[u].y += t[u].y; acc[u].z += t[u].z; acc[u].w += t[u].w; }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + (size_t)u * nthr;
-      if (i < hi)
-        for (int j = 0; j < P.world; j++) st_relaxed_sys_v4(P.g[j] + 4 * i, acc[u]);
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * nthr;
+        if (i < hi)
+          for (int j = 0; j < P.world; j++) st_relaxed_sys_v4(P.g[j] + 4 * i, acc[u]);
+      }
     }
   }
-  if (P.rank == P.world - 1) {  // the < 4 floats past the last quad
-    for (size_t i = n4 * 4 + tid; i < n; i += nthr) {
+  if (P.rank == P.world - 1) {  // the < 4 floats past the last quad of the range
+    for (size_t i = (size_t)lo_f + n4 * 4 + tid; i < (size_t)hi_f; i += nthr) {
       float acc = 0.f;
       for (int j = 0; j < P.world; j++) acc += *reinterpret_cast<volatile float*>(P.g[j] + i);
       for (int j = 0; j < P.world; j++) *reinterpret_cast<volatile float*>(P.g[j] + i) = acc;
     }
   }
+}
+
+// Early exchange (cpcb200_peer_reduce_range): all-reduce of the given ranges of the bucket on a side stream while the
+// backward pass is still producing the remaining (late) gradients.  An ordinary (non-cooperative) launch of a few CTAs:
+// no CTA ever waits for another CTA of the same grid, only for the peers' arrival words.  Completion needs no signal of
+// its own: a rank enters the step kernel's first barrier only after its own early kernel has finished (stream order), so
+// once every rank has arrived there every slice of every early range has been written everywhere.
+__global__ void __launch_bounds__(512) peer_reduce_kernel(PeerPtrs P, RangeList R, int* __restrict__ state) {
+  if (*reinterpret_cast<volatile int*>(state + kStErr) != 0) return;  // set by an earlier kernel only: grid-uniform
+  const unsigned ep = (unsigned)*reinterpret_cast<volatile int*>(state + kStEarlyEpoch);
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  node_arrive(P, kSigEarly, ep + 1);
+  const bool ok = node_wait(P, kSigEarly, ep + 1);
+  if (ok) {
+    for (int r = 0; r < R.n; r++) reduce_my_slice(P, R.lo[r], R.hi[r], tid, nthr);
+  } else if (threadIdx.x == 0) {
+    atomicExch(state + kStErr, 3);
+  }
+  __threadfence_system();  // this thread's peer stores are performed system-wide before the kernel counts as complete
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(state + kStEarlyTicket, 1);
+    if (t == (int)gridDim.x - 1) {  // last block out: every block has read the epoch
+      state[kStEarlyTicket] = 0;
+      __threadfence();
+      atomicAdd(state + kStEarlyEpoch, 1);
+    }
+  }
+}
+
+template <bool ZERO>
+__global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, RangeList R, float* __restrict__ p, float* __restrict__ m,
+                                                             float* __restrict__ v, size_t n, float lr, float b1, float b2,
+                                                             float eps, float wd, int* __restrict__ state) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  if (*reinterpret_cast<volatile int*>(state + kStErr) != 0) return;  // a previous exchange failed: grid-uniform, nothing is touched
+  __shared__ float s_bc[3];
+  double* pw = reinterpret_cast<double*>(state + kStPow);
+  double p1 = 0.0, p2 = 0.0;
+  unsigned calls = 0;
+  if (threadIdx.x == 0) {
+    const int done = *reinterpret_cast<volatile int*>(state);
+    p1 = done == 0 ? (double)b1 : *reinterpret_cast<volatile double*>(pw);
+    p2 = done == 0 ? (double)b2 : *reinterpret_cast<volatile double*>(pw + 1);
+    s_bc[0] = (float)(1.0 - p1);
+    s_bc[1] = sqrtf((float)(1.0 - p2));
+    s_bc[2] = lr < 0.f ? __int_as_float(*reinterpret_cast<volatile int*>(state + kStLr)) : lr;
+  }
+  calls = (unsigned)*reinterpret_cast<volatile int*>(state + kStEpoch);  // node-barrier epoch base: 2 barriers per call
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+  const float step_size = s_bc[2] / bc1;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  float* g = P.g[P.rank];
+
+  // phase stamps (ns since kernel start) in this rank's signal words 40..44: read by tools/peer_adam_check.py
+  const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+  const unsigned long long t_start = stamp ? globaltimer_ns() : 0ull;
+  unsigned* dbg = P.sig[P.rank] + kSigDbg;
+  // ---- every rank's gradients are final (and every rank's early exchange, if any, has completed) ----
+  node_arrive(P, kSigStep, 2 * calls + 1);
+  const bool ok1 = node_wait(P, kSigStep, 2 * calls + 1);
+  if (stamp) dbg[0] = (unsigned)(globaltimer_ns() - t_start);
+  // ---- two-shot all-reduce, in place, of the ranges that have not been exchanged yet ----
+  if (ok1) {
+    for (int r = 0; r < R.n; r++) reduce_my_slice(P, R.lo[r], R.hi[r], tid, nthr);
+  } else if (threadIdx.x == 0) {
+    atomicExch(state + kStErr, 1);
+  }
   __threadfence_system();  // this thread's peer stores are performed system-wide before it reports in
   if (stamp) dbg[1] = (unsigned)(globaltimer_ns() - t_start);
   grid.sync();  // every block of this rank is past its fence: block 0 may tell the peers
+  if (*reinterpret_cast<volatile int*>(state + kStErr) != 0) return;  // grid-uniform after the sync: no update is applied
   if (stamp) dbg[2] = (unsigned)(globaltimer_ns() - t_start);
   // ---- every slice of the local buffer has been written by its owner ----
-  node_arrive(P, 2 * calls + 2);
-  node_wait(P, 2 * calls + 2);
+  node_arrive(P, kSigStep, 2 * calls + 2);
+  if (!node_wait(P, kSigStep, 2 * calls + 2)) {  // a peer died inside this very kernel: give up, flag, keep the context alive
+    if (threadIdx.x == 0) atomicExch(state + kStErr, 2);
+    return;
+  }
   if (stamp) dbg[3] = (unsigned)(globaltimer_ns() - t_start);
   // ---- Adam on the full local replica, gradients read past the L1 (peers wrote them) ----
   auto upd = [&](float gi, float pi, float& mi, float& vi) {
@@ -377,6 +464,7 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, float* 
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     return pi - step_size * (mi / denom);
   };
+  const size_t n4 = n / 4;
   float4* p4 = reinterpret_cast<float4*>(p);
   float4* g4 = reinterpret_cast<float4*>(g);
   float4* m4 = reinterpret_cast<float4*>(m);
@@ -399,7 +487,7 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, float* 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // every block read the state before the grid.sync
     pw[0] = p1 * (double)b1;
     pw[1] = p2 * (double)b2;
-    state[6] = (int)(calls + 1);
+    state[kStEpoch] = (int)(calls + 1);
     __threadfence();
     atomicAdd(state, 1);
   }
@@ -465,7 +553,7 @@ size_t cpcb200_encoder_ws_bytes(const cpcb200_dims* d, int backward) {
 int cpcb200_encoder_fwd(const cpcb200_dims* d, const float* x, const cpcb200_encoder_params* p, float* z, void* save,
                         void* ws, size_t ws_bytes, void* stream) {
   GEO_OR_RETURN(d, g);
-  NOT_NULL(x); NOT_NULL(p); NOT_NULL(z); NOT_NULL(save); NOT_NULL(ws);
+  NOT_NULL(x); NOT_NULL(p); NOT_NULL(z); NOT_NULL(ws);  // save == NULL: inference forward
   prof_mark(static_cast<cudaStream_t>(stream));
   return encoder_fwd(g, x, p, z, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
@@ -501,6 +589,32 @@ int cpcb200_gru_bwd(const cpcb200_dims* d, const float* z, const float* h0, cons
   NOT_NULL(z); NOT_NULL(p); NOT_NULL(c); NOT_NULL(dc); NOT_NULL(save); NOT_NULL(dz); NOT_NULL(grads); NOT_NULL(ws);
   prof_mark(static_cast<cudaStream_t>(stream));
   return gru_bwd(g, z, h0, p, c, dc, save, dz, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t cpcb200_lstm_save_bytes(const cpcb200_dims* d) {
+  Geo g;
+  if (make_geo(d, &g)) return 0;
+  return lstm_save_bytes(g);
+}
+size_t cpcb200_lstm_ws_bytes(const cpcb200_dims* d, int mode) {
+  Geo g;
+  if (make_geo(d, &g)) return 0;
+  return lstm_ws_bytes(g, mode);
+}
+int cpcb200_lstm_fwd(const cpcb200_dims* d, const float* z, const float* h0, const float* c0, const cpcb200_gru_params* p, float* out,
+                     float* hT, float* cT, void* save, void* ws, size_t ws_bytes, void* stream) {
+  GEO_OR_RETURN(d, g);
+  NOT_NULL(z); NOT_NULL(p); NOT_NULL(out); NOT_NULL(ws);  // save == NULL: inference forward
+  prof_mark(static_cast<cudaStream_t>(stream));
+  return lstm_fwd(g, z, h0, c0, p, out, hT, cT, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int cpcb200_lstm_bwd(const cpcb200_dims* d, const float* z, const float* h0, const float* c0, const cpcb200_gru_params* p,
+                     const float* out, const float* dout, const void* save, float* dz, const cpcb200_gru_params* grads, void* ws,
+                     size_t ws_bytes, void* stream) {
+  GEO_OR_RETURN(d, g);
+  NOT_NULL(z); NOT_NULL(p); NOT_NULL(out); NOT_NULL(dout); NOT_NULL(save); NOT_NULL(dz); NOT_NULL(grads); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
+  return lstm_bwd(g, z, h0, c0, p, out, dout, save, dz, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int cpcb200_sample_ext_idx(const cpcb200_dims* d, const int64_t* batch_idx, const int64_t* seq_idx, int32_t* ext, void* stream) {
@@ -581,6 +695,45 @@ int cpcb200_criterion_t_bwd(const cpcb200_dims* d, const float* c, const float* 
   return criterion_bwd(g, c, z, nullptr, p, ext, dlosses, save, dc, dz, nullptr, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+// transformer context network: one TransformerLayer over the S frames of every window (d->Har, d->K, d->N are ignored)
+static int tlayer_geo(const cpcb200_dims* d, int dff, int nheads, Geo* g) {
+  CPC_TRY(make_geo(d, g));
+  if (dff <= 0 || dff % 64 != 0 || nheads <= 0 || g->H % nheads != 0)
+    return fail(CPCB200_ERR_BAD_DIMS, "transformer layer: dff=%d (multiple of 64), nheads=%d (divides H=%d)", dff, nheads, g->H);
+  if (g->S > 128) return fail(CPCB200_ERR_UNSUPPORTED, "transformer layer: %d frames per window > 128", g->S);
+  g->Har = g->H; g->K = 1; g->N = 1; g->W = g->S;
+  g->dff = dff; g->nheads = nheads;
+  return 0;
+}
+size_t cpcb200_tlayer_save_bytes(const cpcb200_dims* d, int dff, int nheads) {
+  Geo g;
+  if (tlayer_geo(d, dff, nheads, &g)) return 0;
+  return tlayer_save_bytes(g);
+}
+size_t cpcb200_tlayer_ws_bytes(const cpcb200_dims* d, int dff, int nheads, int backward) {
+  Geo g;
+  if (tlayer_geo(d, dff, nheads, &g)) return 0;
+  return tlayer_ws_bytes(g, backward);
+}
+int cpcb200_tlayer_fwd(const cpcb200_dims* d, const float* x, const cpcb200_thead_params* p, float* y, void* save, void* ws,
+                       size_t ws_bytes, void* stream) {
+  NOT_NULL(p);
+  Geo g;
+  CPC_TRY(tlayer_geo(d, p->dff, p->nheads, &g));
+  NOT_NULL(x); NOT_NULL(y); NOT_NULL(save); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
+  return tlayer_fwd(g, x, p, y, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int cpcb200_tlayer_bwd(const cpcb200_dims* d, const float* x, const cpcb200_thead_params* p, const float* dy, const void* save,
+                       float* dx, const cpcb200_thead_params* grads, void* ws, size_t ws_bytes, void* stream) {
+  NOT_NULL(p); NOT_NULL(grads);
+  Geo g;
+  CPC_TRY(tlayer_geo(d, p->dff, p->nheads, &g));
+  NOT_NULL(x); NOT_NULL(dy); NOT_NULL(save); NOT_NULL(dx); NOT_NULL(ws);
+  prof_mark(static_cast<cudaStream_t>(stream));
+  return tlayer_bwd(g, x, p, dy, save, dx, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                       float beta2, float eps, float weight_decay, int32_t step, void* stream) {
   NOT_NULL(param); NOT_NULL(grad); NOT_NULL(exp_avg); NOT_NULL(exp_avg_sq);
@@ -597,8 +750,10 @@ int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   return 0;
 }
 
-int cpcb200_encoder_bwd_set_event(void* cuda_event) {
-  g_grads_ready_event.store(cuda_event);
+int cpcb200_encoder_bwd_set_event(void* stream, void* cuda_event) {
+  std::lock_guard<std::mutex> lk(g_ev_mu);
+  if (cuda_event) g_grads_ready_events[static_cast<cudaStream_t>(stream)] = static_cast<cudaEvent_t>(cuda_event);
+  else g_grads_ready_events.erase(static_cast<cudaStream_t>(stream));
   return 0;
 }
 
@@ -624,22 +779,56 @@ int cpcb200_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_
   return 0;
 }
 
+static int fill_peers(const cpcb200_peers* peers, PeerPtrs* P) {
+  if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world)
+    return fail(CPCB200_ERR_BAD_DIMS, "peer exchange: rank %d / world %d (1..8 GPUs of one node)", peers->rank, peers->world);
+  P->rank = peers->rank; P->world = peers->world;
+  P->mc = static_cast<float*>(peers->grads_mc);
+  P->timeout_ns = peers->timeout_ns > 0 ? peers->timeout_ns : 600ll * 1000000000ll;
+  if (reinterpret_cast<uintptr_t>(P->mc) & 15) return fail(CPCB200_ERR_BAD_DIMS, "peer exchange: multicast pointer must be 16-byte aligned");
+  for (int i = 0; i < peers->world; i++) {
+    if (!peers->grads[i] || !peers->signals[i]) return fail(CPCB200_ERR_NULL, "peer exchange: peer %d pointer is NULL", i);
+    if (reinterpret_cast<uintptr_t>(peers->grads[i]) & 15) return fail(CPCB200_ERR_BAD_DIMS, "peer exchange: gradient buffers must be 16-byte aligned");
+    P->g[i] = static_cast<float*>(peers->grads[i]);
+    P->sig[i] = static_cast<unsigned*>(peers->signals[i]);
+  }
+  return 0;
+}
+static int fill_ranges(const int64_t* ranges, int n_ranges, size_t n, RangeList* R) {
+  if (n_ranges < 0 || n_ranges > 4) return fail(CPCB200_ERR_BAD_DIMS, "peer exchange: %d ranges (at most 4)", n_ranges);
+  R->n = n_ranges;
+  for (int i = 0; i < n_ranges; i++) {
+    const long long lo = ranges[2 * i], hi = ranges[2 * i + 1];
+    if (lo < 0 || hi < lo || (lo & 3) || (n && (size_t)hi > n))
+      return fail(CPCB200_ERR_BAD_DIMS, "peer exchange: range %d = [%lld, %lld) (start must be a multiple of 4 floats)", i, lo, hi);
+    R->lo[i] = lo; R->hi[i] = hi;
+  }
+  return 0;
+}
+
+int cpcb200_peer_reduce_range(const cpcb200_peers* peers, const int64_t* ranges, int n_ranges, int32_t* state, void* stream) {
+  NOT_NULL(peers); NOT_NULL(ranges); NOT_NULL(state);
+  PeerPtrs P{};
+  CPC_TRY(fill_peers(peers, &P));
+  RangeList R{};
+  CPC_TRY(fill_ranges(ranges, n_ranges, 0, &R));
+  if (n_ranges == 0) return 0;
+  static const int ctas = []() { const char* e = getenv("CPC_B200_EARLY_CTAS"); int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 148 ? 148 : v); }();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  peer_reduce_kernel<<<ctas, 512, 0, st>>>(P, R, reinterpret_cast<int*>(state));
+  CPC_LAUNCHED_N("peer_reduce", st);
+  return 0;
+}
+
 int cpcb200_allreduce_adam_step(const cpcb200_peers* peers, float* param, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                                 float beta1, float beta2, float eps, float weight_decay, int32_t* state, int zero_grad,
-                                void* stream) {
+                                const int64_t* ranges, int n_ranges, void* stream) {
   NOT_NULL(peers); NOT_NULL(param); NOT_NULL(exp_avg); NOT_NULL(exp_avg_sq); NOT_NULL(state);
-  if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world)
-    return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: rank %d / world %d (1..8 GPUs of one node)", peers->rank, peers->world);
   PeerPtrs P{};
-  P.rank = peers->rank; P.world = peers->world;
-  P.mc = static_cast<float*>(peers->grads_mc);
-  if (reinterpret_cast<uintptr_t>(P.mc) & 15) return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: multicast pointer must be 16-byte aligned");
-  for (int i = 0; i < peers->world; i++) {
-    if (!peers->grads[i] || !peers->signals[i]) return fail(CPCB200_ERR_NULL, "allreduce_adam: peer %d pointer is NULL", i);
-    if (reinterpret_cast<uintptr_t>(peers->grads[i]) & 15) return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: gradient buffers must be 16-byte aligned");
-    P.g[i] = static_cast<float*>(peers->grads[i]);
-    P.sig[i] = static_cast<unsigned*>(peers->signals[i]);
-  }
+  CPC_TRY(fill_peers(peers, &P));
+  RangeList R{};
+  if (ranges != nullptr) CPC_TRY(fill_ranges(ranges, n_ranges, n, &R));
+  else { R.n = 1; R.lo[0] = 0; R.hi[0] = (long long)n; }  // nothing exchanged yet: the whole bucket
   if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
     return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: buffers must be 16-byte aligned");
   if (reinterpret_cast<uintptr_t>(state) & 7) return fail(CPCB200_ERR_BAD_DIMS, "allreduce_adam: state must be 8-byte aligned");
@@ -651,7 +840,7 @@ int cpcb200_allreduce_adam_step(const cpcb200_peers* peers, float* param, float*
   const void* kern = zero_grad ? reinterpret_cast<const void*>(allreduce_adam_kernel<true>)
                                : reinterpret_cast<const void*>(allreduce_adam_kernel<false>);
   int* state_i = reinterpret_cast<int*>(state);
-  void* args[] = {&P, &param, &exp_avg, &exp_avg_sq, &n, &lr, &beta1, &beta2, &eps, &weight_decay, &state_i};
+  void* args[] = {&P, &R, &param, &exp_avg, &exp_avg_sq, &n, &lr, &beta1, &beta2, &eps, &weight_decay, &state_i};
   CPC_CHECK_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)(2 * sms)), dim3(256), args, 0, st));  // 2 CTAs per SM, all resident
   CPC_LAUNCHED_N("allreduce_adam", st);
   return 0;

@@ -88,9 +88,9 @@ struct Carver {
 // no-ops and the stream order is the classic one.
 bool pdl_enabled();
 
-// one-shot hook (cpcb200_encoder_bwd_set_event): the next encoder backward records this event once every parameter
-// gradient except conv0's / batchNorm0's is final; returns nullptr when none is armed
-cudaEvent_t take_grads_ready_event();
+// one-shot hook (cpcb200_encoder_bwd_set_event): the next encoder backward ON STREAM `st` records this event once every
+// parameter gradient except conv0's / batchNorm0's is final; returns nullptr when none is armed for that stream
+cudaEvent_t take_grads_ready_event(cudaStream_t st);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -218,19 +218,21 @@ struct OutView {
   long long bs, rs;
   int rpb;
   int t_lo, t_hi;  // only rows with t_lo <= t < t_hi are stored
-  // merged transposed-conv output (dgrad): the N columns are `s` residues of res_w channels each; column block
-  // r = n / res_w of logical row t is input row s*t + r - res_p, which exists unless (t == 0 && r < res_p) or
-  // (t == rpb-1 && r >= res_p).  res_w == 0: plain output.
+  // merged transposed-conv output (dgrad): the N columns are `res_s` residues of res_w channels each; column block
+  // r = n / res_w of logical row t is input row j = res_s*t + r - res_p, which exists iff 0 <= j < res_rows (the input
+  // length of the layer: res_s*(rpb-1) when the window length is a multiple of 160, up to res_s-1 rows more otherwise).
+  // res_w == 0: plain output.
   int res_w = 0;
   int res_p = 0;
+  int res_s = 0;
+  int res_rows = 0;
   int relu = 0;  // apply max(., 0) after the bias (FFN of the transformer prediction heads)
 };
 __host__ __device__ inline bool out_row_ok(const OutView& C, int t, int n0) {
   if (t >= C.rpb || t < C.t_lo || t >= C.t_hi) return false;
   if (C.res_w > 0) {
-    const int r = n0 / C.res_w;
-    if (t == 0 && r < C.res_p) return false;
-    if (t == C.rpb - 1 && r >= C.res_p) return false;
+    const int j = C.res_s * t + n0 / C.res_w - C.res_p;
+    if (j < 0 || j >= C.res_rows) return false;
   }
   return true;
 }
@@ -247,6 +249,7 @@ struct CNormEpi {
   float* z;
   int pad_rows;
   float2* stats = nullptr;  // (mean, rstd) of every row, index b*rpb + t: saved for the ChannelNorm backward
+  int save_u = 1;           // 0: inference - the pre-norm rows are not written (the OutView only supplies the row geometry)
 };
 
 // C[m,n] = sum_k A[m,k] * B[n,k] (+ bias[n]).  A row view (M = nb*rpb rows, inner Kd); B dense (N, Kd) ld=Kd.

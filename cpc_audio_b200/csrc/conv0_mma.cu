@@ -124,23 +124,27 @@ __device__ __forceinline__ void tile_stats(const float (&acc)[NT][4], int H, flo
 }
 
 // copy a staged [16][H] bf16 tile (row stride RS bytes) to 16 consecutive global rows of H channels
+// (nrows < 16: the last tile of a window whose frame count is not a multiple of 16 - rows past the end are not stored)
 template <int H>
-__device__ __forceinline__ void tile_to_global(const unsigned char* st, bf16* __restrict__ dst, int lane) {
+__device__ __forceinline__ void tile_to_global(const unsigned char* st, bf16* __restrict__ dst, int lane, int nrows = 16) {
   constexpr int SEGS = H / 8, RS = 2 * H + 16;
 #pragma unroll
   for (int it = 0; it < (16 * SEGS) / 32; it++) {
     const int flat = it * 32 + lane, r = flat / SEGS, sg = flat - r * SEGS;
     const uint4 v = *reinterpret_cast<const uint4*>(st + r * RS + sg * 16);
-    *reinterpret_cast<uint4*>(dst + (size_t)r * H + sg * 8) = v;
+    if (r < nrows) *reinterpret_cast<uint4*>(dst + (size_t)r * H + sg * 8) = v;
   }
 }
+// rows past the end of the window read as zero: a zero gradient row contributes nothing to any sum of the backward pass
 template <int H>
-__device__ __forceinline__ void tile_from_global(unsigned char* st, const bf16* __restrict__ src, int lane) {
+__device__ __forceinline__ void tile_from_global(unsigned char* st, const bf16* __restrict__ src, int lane, int nrows = 16) {
   constexpr int SEGS = H / 8, RS = 2 * H + 16;
 #pragma unroll
   for (int it = 0; it < (16 * SEGS) / 32; it++) {
     const int flat = it * 32 + lane, r = flat / SEGS, sg = flat - r * SEGS;
-    *reinterpret_cast<uint4*>(st + r * RS + sg * 16) = *reinterpret_cast<const uint4*>(src + (size_t)r * H + sg * 8);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < nrows) v = *reinterpret_cast<const uint4*>(src + (size_t)r * H + sg * 8);
+    *reinterpret_cast<uint4*>(st + r * RS + sg * 16) = v;
   }
 }
 
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(128, 3) conv0_fwd_mma_kernel(const float* __re
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int tpw = L0 / 16;  // tiles per window
+  const int tpw = (L0 + 15) / 16;  // tiles per window (the last one may be partial: L is not always a multiple of 160)
   const long long Lp0 = L0 + 2 * kPad;
   for (int tile = warp; tile < B * tpw; tile += nwarps) {
     const int b = tile / tpw, f0 = (tile - b * tpw) * 16;
@@ -195,11 +199,11 @@ __global__ void __launch_bounds__(128, 3) conv0_fwd_mma_kernel(const float* __re
     }
     __syncwarp();
     bf16* dst = y + ((long long)b * Lp0 + kPad + f0) * H;
-    tile_to_global<H>(stage, dst, lane);
-    if (f0 == 0 || f0 + 16 == L0) {  // zero rows around the window
+    tile_to_global<H>(stage, dst, lane, L0 - f0);
+    if (f0 == 0 || f0 + 16 >= L0) {  // zero rows around the window
       bf16* pad = y + ((long long)b * Lp0 + (f0 == 0 ? 0 : kPad + L0)) * H;
       for (int i = lane; i < kPad * H / 8; i += 32) reinterpret_cast<uint4*>(pad)[i] = make_uint4(0, 0, 0, 0);
-      if (f0 == 0 && f0 + 16 == L0) {
+      if (f0 == 0 && f0 + 16 >= L0) {
         bf16* pad2 = y + ((long long)b * Lp0 + kPad + L0) * H;
         for (int i = lane; i < kPad * H / 8; i += 32) reinterpret_cast<uint4*>(pad2)[i] = make_uint4(0, 0, 0, 0);
       }
@@ -235,12 +239,12 @@ __global__ void __launch_bounds__(128, 2) conv0_bwd_du_mma_kernel(const float* _
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int tpw = L0 / 16;
+  const int tpw = (L0 + 15) / 16;
   const uint32_t ones = 0x3f803f80u;  // bf16 (1, 1)
   for (int tile = warp; tile < B * tpw; tile += nwarps) {
     const int b = tile / tpw, f0 = (tile - b * tpw) * 16;
     bf16* drow = dy + ((long long)b * L0 + f0) * H;
-    tile_from_global<H>(t_a, drow, lane);
+    tile_from_global<H>(t_a, drow, lane, L0 - f0);
     uint32_t ah[4], al[4];
     load_xfrags(x + (long long)b * L, L, f0, g, t, ah, al);
     float acc[NT][4];
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(128, 2) conv0_bwd_du_mma_kernel(const float* _
       *reinterpret_cast<uint32_t*>(t_b + (g + 8) * RS + c * 2) = pack_bf16(o2, o3);
     }
     __syncwarp();
-    tile_to_global<H>(t_b, drow, lane);
+    tile_to_global<H>(t_b, drow, lane, L0 - f0);
 #pragma unroll
     for (int m = 0; m < H / 16; m++) {  // column sums of du
       const int mi = lane >> 3;
@@ -363,10 +367,10 @@ __global__ void __launch_bounds__(128) conv0_wgrad_mma_kernel(const float* __res
     for (int n = 0; n < 2; n++)
 #pragma unroll
       for (int e = 0; e < 4; e++) acc[m][n][e] = 0.f;
-  const int tpw = L0 / 16;
+  const int tpw = (L0 + 15) / 16;
   for (int tile = warp; tile < B * tpw; tile += nwarps) {
     const int b = tile / tpw, f0 = (tile - b * tpw) * 16;
-    tile_from_global<H>(stage, du + ((long long)b * L0 + f0) * H, lane);
+    tile_from_global<H>(stage, du + ((long long)b * L0 + f0) * H, lane, L0 - f0);
     // B fragments: X[k = frame][n = tap]: b0 = frames (2t, 2t+1), b1 = frames (2t+8, 2t+9); n = g (taps 0-7) / g+8
     const float* xb = x + (long long)b * L;
     uint32_t bx[2][2];
@@ -686,7 +690,7 @@ template <int H>
 int launch_all_fwd(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* y, int B, int L,
                    int L0, cudaStream_t st) {
   const size_t smem = 2 * H * 4 + (H / 8) * 32 * 8 + 4 * 16 * (2 * H + 16);
-  int blocks = (B * (L0 / 16) + 3) / 4;
+  int blocks = (B * ((L0 + 15) / 16) + 3) / 4;
   if (blocks > 148 * 3) blocks = 148 * 3;
   CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_fwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CPC_CHECK_CUDA(launch_k(conv0_fwd_mma_kernel<H>, dim3(blocks), dim3(128), smem, st, 1, x, w, bias, gam, bet, y, B, L, L0));
@@ -708,7 +712,7 @@ int launch_all_bwd(const float* x, const float* w, const float* bias, const floa
     CPC_LAUNCHED_N("conv0_bwd2_mma", st);
     return 0;
   }
-  int blocks = (B * (L0 / 16) + 3) / 4;
+  int blocks = (B * ((L0 + 15) / 16) + 3) / 4;
   if (blocks > 148 * 3) blocks = 148 * 3;
   CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd_du_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   CPC_CHECK_CUDA(launch_k(conv0_bwd_du_mma_kernel<H>, dim3(blocks), dim3(128), smem1, st, 1, x, w, bias, gam, bet, dy, dbias, dgam, dbet, B, L, L0));

@@ -77,7 +77,7 @@ __device__ __forceinline__ void row_stats(const float (&u)[I][4], int H, int lan
 // One warp per chunk of kC0Chunk consecutive frames of one window: the lane's 4*I x 10 weights live in registers,
 // the 10-sample input window slides by 5 samples per frame (5 broadcast loads), stores are channel-last vectors.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kC0Chunk = 32;  // L0 = L/5 is a multiple of 32 because L is a multiple of 160
+constexpr int kC0Chunk = 32;  // frames per warp trip (the last chunk of a window is shorter when L0 % 32 != 0)
 
 template <int I>
 __device__ __forceinline__ void conv0_load_w(const float* __restrict__ w, int H, int lane, float (&wr)[I][4][10]) {
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) conv0_fwd_kernel(const float* __restrict_
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   float wr[I][4][10];
   conv0_load_w<I>(w, H, lane, wr);
-  const int cpw = L0 / kC0Chunk;  // chunks per window
+  const int cpw = (L0 + kC0Chunk - 1) / kC0Chunk;  // chunks per window
   const long long Lp0 = L0 + 2 * kPad;
   for (int ch = warp; ch < B * cpw; ch += nwarps) {
     const int b = ch / cpw, t0 = (ch - b * cpw) * kC0Chunk;
@@ -145,12 +145,13 @@ __global__ void __launch_bounds__(128) conv0_fwd_kernel(const float* __restrict_
     conv0_window_init(xb, L, t0, xs);
     T* yrow = y + ((long long)b * Lp0 + kPad + t0) * H;
     if (t0 == 0) { for (int r = 0; r < kPad; r++) zero_row(y + ((long long)b * Lp0 + r) * H, H, lane); }
-    if (t0 + kC0Chunk == L0) { for (int r = 0; r < kPad; r++) zero_row(y + ((long long)b * Lp0 + kPad + L0 + r) * H, H, lane); }
+    if (t0 + kC0Chunk >= L0) { for (int r = 0; r < kPad; r++) zero_row(y + ((long long)b * Lp0 + kPad + L0 + r) * H, H, lane); }
+    const int nfr = min(kC0Chunk, L0 - t0);
 #pragma unroll 1
-    for (int tt = 0; tt < kC0Chunk; tt++) {
+    for (int tt = 0; tt < nfr; tt++) {
       float u[I][4];
       conv0_row<I>(wr, sm, xs, H, lane, u);
-      if (tt + 1 < kC0Chunk) conv0_window_next(xb, L, t0 + tt + 1, xs);
+      if (tt + 1 < nfr) conv0_window_next(xb, L, t0 + tt + 1, xs);
       float mean, rstd;
       row_stats<I>(u, H, lane, mean, rstd);
 #pragma unroll
@@ -192,19 +193,20 @@ __global__ void __launch_bounds__(128) conv0_bwd_du_kernel(const float* __restri
   for (int i = 0; i < I; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) ab[i][j] = ag[i][j] = abe[i][j] = 0.f;
-  const int cpw = L0 / kC0Chunk;
+  const int cpw = (L0 + kC0Chunk - 1) / kC0Chunk;
   for (int ch = warp; ch < B * cpw; ch += nwarps) {
     const int b = ch / cpw, t0 = (ch - b * cpw) * kC0Chunk;
     const float* xb = x + (long long)b * L;
     float xs[10];
     conv0_window_init(xb, L, t0, xs);
     T* drow = dy + ((long long)b * L0 + t0) * H;
+    const int nfr = min(kC0Chunk, L0 - t0);
 #pragma unroll 1
-    for (int tt = 0; tt < kC0Chunk; tt++) {
+    for (int tt = 0; tt < nfr; tt++) {
       float u[I][4], d[I][4];
       row_load<I>(drow + (long long)tt * H, H, lane, d);
       conv0_row<I>(wr, sm, xs, H, lane, u);
-      if (tt + 1 < kC0Chunk) conv0_window_next(xb, L, t0 + tt + 1, xs);
+      if (tt + 1 < nfr) conv0_window_next(xb, L, t0 + tt + 1, xs);
       float mean, rstd;
       row_stats<I>(u, H, lane, mean, rstd);
       float s1 = 0.f, s2 = 0.f;
@@ -273,15 +275,16 @@ __global__ void __launch_bounds__(128) conv0_wgrad_kernel(const float* __restric
     for (int j = 0; j < 4; j++)
 #pragma unroll
       for (int k = 0; k < 10; k++) aw[i][j][k] = 0.f;
-  const int cpw = L0 / kC0Chunk;
+  const int cpw = (L0 + kC0Chunk - 1) / kC0Chunk;
   for (int ch = warp; ch < B * cpw; ch += nwarps) {
     const int b = ch / cpw, t0 = (ch - b * cpw) * kC0Chunk;
     const float* xb = x + (long long)b * L;
     float xs[10];
     conv0_window_init(xb, L, t0, xs);
     const T* drow = du + ((long long)b * L0 + t0) * H;
+    const int nfr = min(kC0Chunk, L0 - t0);
 #pragma unroll 2
-    for (int tt = 0; tt < kC0Chunk; tt++) {
+    for (int tt = 0; tt < nfr; tt++) {
       float d[I][4];
       row_load<I>(drow + (long long)tt * H, H, lane, d);
 #pragma unroll
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(128) conv0_wgrad_kernel(const float* __restric
         for (int j = 0; j < 4; j++)
 #pragma unroll
           for (int k = 0; k < 10; k++) aw[i][j][k] = fmaf(d[i][j], xs[k], aw[i][j][k]);
-      if (tt + 1 < kC0Chunk) conv0_window_next(xb, L, t0 + tt + 1, xs);
+      if (tt + 1 < nfr) conv0_window_next(xb, L, t0 + tt + 1, xs);
     }
   }
 #pragma unroll
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(256) cnorm_relu_fwd_kernel(const T* __restrict
   row_load<I>(u + prow, H, lane, v);
   float mean, rstd;
   row_stats<I>(v, H, lane, mean, rstd);
-  if (lane == 0) stats[warp] = make_float2(mean, rstd);  // saved for backward
+  if (lane == 0 && stats != nullptr) stats[warp] = make_float2(mean, rstd);  // saved for backward
 #pragma unroll
   for (int i = 0; i < I; i++) {
     int c = 4 * (lane + 32 * i);
@@ -563,10 +566,27 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
                   size_t ws_bytes, cudaStream_t st) {
   const int H = g.H, B = g.B;
   EncLayout e = enc_layout(g);
-  T* sv = static_cast<T*>(save);
   Carver ws(wsp, ws_bytes);
   T* wp[5] = {nullptr};
   for (int i = 1; i < 5; i++) wp[i] = ws.take<T>((size_t)H * kConvK[i] * H);
+  // training: every activation lives in `save` (read again by the backward pass).  Inference (save == NULL: no_grad
+  // forward, feature extraction): y0..y3 ping-pong between two workspace buffers, the pre-norm rows and the row
+  // statistics are not kept at all on the fused path (one scratch buffer on the unfused one).
+  const bool infer = save == nullptr;
+  T* yb[4] = {nullptr};
+  T* ub[5] = {nullptr};
+  float2* stb[5] = {nullptr};
+  if (!infer) {
+    T* sv = static_cast<T*>(save);
+    for (int i = 0; i < 4; i++) yb[i] = sv + e.y[i];
+    for (int i = 1; i < 5; i++) { ub[i] = sv + e.u[i]; stb[i] = reinterpret_cast<float2*>(sv + e.st[i]); }
+  } else {
+    T* pa = ws.take<T>((size_t)B * (g.Lout[0] + 2 * kPad) * H);
+    T* pb = ws.take<T>((size_t)B * (g.Lout[1] + 2 * kPad) * H);
+    T* us = ws.take<T>((size_t)B * (g.Lout[1] + 2 * kPad) * H);
+    yb[0] = pa; yb[1] = pb; yb[2] = pa; yb[3] = pb;
+    for (int i = 1; i < 5; i++) ub[i] = us;
+  }
   if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "encoder_fwd: workspace %zu < %zu", ws_bytes, ws.off);
 
   {
@@ -580,38 +600,38 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   bool c0_done = false;
   if constexpr (sizeof(T) == 2) {
     if (conv0_mma_supported(H)) {
-      CPC_TRY(conv0_fwd_mma(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0], sv + e.y[0], B, g.L, g.Lout[0], H, st));
+      CPC_TRY(conv0_fwd_mma(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0], yb[0], B, g.L, g.Lout[0], H, st));
       c0_done = true;
     }
   }
   if (!c0_done) {
     const size_t smem = 3 * (size_t)H * sizeof(float);
-    int blocks = (B * (g.Lout[0] / kC0Chunk) + 3) / 4;
+    int blocks = (B * ((g.Lout[0] + kC0Chunk - 1) / kC0Chunk) + 3) / 4;
     if (blocks > 148 * 8) blocks = 148 * 8;
 #define LAUNCH_C0(II)                                                                                             \
   conv0_fwd_kernel<II, T><<<blocks, 128, smem, st>>>(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0],   \
-                                                     sv + e.y[0], B, g.L, g.Lout[0], H)
+                                                     yb[0], B, g.L, g.Lout[0], H)
     if (I == 1) LAUNCH_C0(1); else if (I == 2) LAUNCH_C0(2); else if (I == 3) LAUNCH_C0(3); else LAUNCH_C0(4);
 #undef LAUNCH_C0
     CPC_LAUNCHED_N("conv0_fwd", st);
   }
   for (int i = 1; i < 5; i++) {
     const int Lin = g.Lout[i - 1], Lo = g.Lout[i];
-    RowView A{sv + e.y[i - 1] + (size_t)(kPad - kConvP[i]) * H, (long long)(Lin + 2 * kPad) * H, (long long)kConvS[i] * H, Lo, kConvK[i], kConvS[i]};
-    OutView C{sv + e.u[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo, 0, Lo, 0};
-    T* yo = i < 4 ? sv + e.y[i] : nullptr;
+    RowView A{yb[i - 1] + (size_t)(kPad - kConvP[i]) * H, (long long)(Lin + 2 * kPad) * H, (long long)kConvS[i] * H, Lo, kConvK[i], kConvS[i]};
+    OutView C{ub[i] + (size_t)kPad * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo, 0, Lo, 0};
+    T* yo = i < 4 ? yb[i] : nullptr;
     float* zo = i == 4 ? z : nullptr;
     if (g.bf16 && H == 256) {  // ChannelNorm + ReLU inside the GEMM epilogue
       bool fused = false;
-      CNormEpi E{p->norm_w[i], p->norm_b[i], yo != nullptr ? static_cast<void*>(yo + (size_t)kPad * H) : nullptr, zo, kPad,
-                 reinterpret_cast<float2*>(sv + e.st[i])};
+      CNormEpi E{p->norm_w[i], p->norm_b[i], yo != nullptr ? static_cast<void*>(yo + (size_t)kPad * H) : nullptr, zo, kPad, stb[i]};
+      E.save_u = infer ? 0 : 1;
       CPC_TRY(gemm_nt_cnorm_tc(B, kConvK[i] * H, A, wp[i], p->conv_b[i], C, E, st, &fused));
       if (fused) continue;
     }
     CPC_TRY(gemm_nt(g.bf16, false, B, H, kConvK[i] * H, A, wp[i], p->conv_b[i], C, st));
     const long long rows = (long long)B * Lo;
     const int blocks = (int)((rows * 32 + 255) / 256);
-#define LAUNCH_CN(II) CPC_CHECK_CUDA(launch_k(cnorm_relu_fwd_kernel<II, T>, dim3(blocks), dim3(256), 0, st, 1, sv + e.u[i], p->norm_w[i], p->norm_b[i], yo, zo, reinterpret_cast<float2*>(sv + e.st[i]), B, Lo, H))
+#define LAUNCH_CN(II) CPC_CHECK_CUDA(launch_k(cnorm_relu_fwd_kernel<II, T>, dim3(blocks), dim3(256), 0, st, 1, ub[i], p->norm_w[i], p->norm_b[i], yo, zo, stb[i], B, Lo, H))
     if (I == 1) LAUNCH_CN(1); else if (I == 2) LAUNCH_CN(2); else if (I == 3) LAUNCH_CN(3); else LAUNCH_CN(4);
 #undef LAUNCH_CN
     CPC_LAUNCHED_N("cnorm_relu_fwd", st);
@@ -683,13 +703,16 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
         CPC_CHECK_CUDA(launch_k(permute_add_wgrad_all_kernel, dim3(H, 4), dim3(256), (size_t)8 * (H + 1) * sizeof(float), st, 1, P, H));
         CPC_LAUNCHED_N("permute_add_wgrad_all", st);
       }
-      if (cudaEvent_t ev = take_grads_ready_event()) CPC_CHECK_CUDA(cudaEventRecord(ev, st));
+      if (cudaEvent_t ev = take_grads_ready_event(st)) CPC_CHECK_CUDA(cudaEventRecord(ev, st));
     }
     // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r].  All s residues in ONE GEMM with
     // N = s*H: row q of the product is the s consecutive input rows s q - p .. s q - p + s - 1.
     {
       RowView A{du[i] + (size_t)(kPad - 1) * H, (long long)(Lo + 2 * kPad) * H, (long long)H, Lo + 1, 2, 1};
-      OutView C{dy[i - 1] - (long long)pp * H, (long long)Lin * H, (long long)s * H, Lo + 1, 0, Lo + 1, H, pp};
+      OutView C{dy[i - 1] - (long long)pp * H, (long long)Lin * H, (long long)s * H, Lo + 1, 0, Lo + 1, H, pp, s, Lin};
+      // window lengths that are not multiples of 160 leave up to s-1 trailing input rows that no output frame reads
+      // (zero gradient) and that the merged product does not cover: clear the buffer first (ragged shapes only)
+      if (Lin > s * Lo + s - pp) CPC_CHECK_CUDA(cudaMemsetAsync(dy[i - 1], 0, (size_t)B * Lin * H * sizeof(T), st));
       CPC_TRY(gemm_nt(g.bf16, false, B, s * H, 2 * H, A, wd[i], nullptr, C, st));
     }
   }
@@ -702,7 +725,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     }
   }
   if (!c0_done) {
-    int blocks = (B * (g.Lout[0] / kC0Chunk) + 3) / 4;
+    int blocks = (B * ((g.Lout[0] + kC0Chunk - 1) / kC0Chunk) + 3) / 4;
     if (blocks > 148 * 4) blocks = 148 * 4;
     const size_t smem1 = 6 * (size_t)H * sizeof(float), smem2 = 10 * (size_t)H * sizeof(float);
 #define LAUNCH_C0B(II)                                                                                              \
@@ -727,8 +750,12 @@ size_t encoder_save_elems(const Geo& g) { return enc_layout(g).total; }
 size_t encoder_ws_bytes(const Geo& g, int backward) {
   const size_t es = g.bf16 ? 2 : 4;
   size_t tot = 0;
-  if (!backward) {
+  if (backward != 1) {
     for (int i = 1; i < 5; i++) tot += align_up((size_t)g.H * kConvK[i] * g.H * es);
+    if (backward == 2) {  // inference forward (save == NULL): the activations ping-pong inside the workspace
+      tot += align_up((size_t)g.B * (g.Lout[0] + 2 * kPad) * g.H * es);
+      tot += 2 * align_up((size_t)g.B * (g.Lout[1] + 2 * kPad) * g.H * es);
+    }
   } else {
     for (int i = 1; i < 5; i++) tot += align_up((size_t)kConvS[i] * g.H * 2 * g.H * es);
     for (int i = 1; i < 5; i++) tot += align_up((size_t)g.B * (g.Lout[i] + 2 * kPad) * g.H * es);

@@ -27,7 +27,12 @@ constexpr int NT_THREADS = 192;
 
 // per-CTA cycle stamps of the last gemm_nt_tc2 launch (debug hook cpcb200_debug_gemm_timeline): 8 slots per CTA
 __device__ unsigned long long g_nt2_tl[148 * 8];
+// compiled in only with -DCPC_B200_TIMELINE (tools/gemm_probe.py builds that way): release builds carry no stamps
+#ifdef CPC_B200_TIMELINE
 #define TL_STAMP(slot) do { if (blockIdx.x < 148) g_nt2_tl[blockIdx.x * 8 + (slot)] = (unsigned long long)(clock64() - tl_t0); } while (0)
+#else
+#define TL_STAMP(slot) do { } while (0)
+#endif
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -389,7 +394,9 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
   float2* cn_xch = reinterpret_cast<float2*>(cn_par + 3 * BN2);                       // [tile parity][2 halves][128 rows] (mean, M2)
   unsigned char* stg_all = reinterpret_cast<unsigned char*>(cn_xch + 4 * BM);         // [8 warps][STG_WARP]
 
+#ifdef CPC_B200_TIMELINE
   const long long tl_t0 = clock64();
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)ptx::cluster_ctarank();
   const int cluster_id = blockIdx.x / CM, num_clusters = gridDim.x / CM;
@@ -541,7 +548,7 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]) + pb[c0 + j]));
-          emit_chunk<bf16>(stg, lane, v, static_cast<bf16*>(static_cast<void*>(cwarp)) + c0, C.rs, ok);
+          if (E.save_u) emit_chunk<bf16>(stg, lane, v, static_cast<bf16*>(static_cast<void*>(cwarp)) + c0, C.rs, ok);
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] = fmaxf(fmaf((v[j] - mean) * rstd, pb[BN2 + c0 + j], pb[2 * BN2 + c0 + j]), 0.f);
           if (ywarp != nullptr) emit_chunk<bf16>(stg, lane, v, ywarp + c0, C.rs, ok);

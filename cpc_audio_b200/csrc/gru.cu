@@ -541,6 +541,372 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
   return 0;
 }
 
+
+// =========================================================================================================
+// LSTM context network (cpc/model.py:171-173: nn.LSTM(batch_first=True), the reference's default --arMode,
+// cpc_default_config.py:74).  torch gate order (i, f, g, o):
+//   i = sigma(W_ii x + b_ii + W_hi h + b_hi)   f = sigma(..f..)   g = tanh(..g..)   o = sigma(..o..)
+//   c' = f c + i g                              h' = o tanh(c')
+// Same structure as the GRU: hoisted input projection / weight-gradient GEMMs, one persistent cluster kernel per
+// direction with the W_hh slice resident in shared memory; a CTA owns 32 hidden units (4 x 32 gate rows), the cell
+// state of a (unit, sequence) pair stays in the register of its gate thread for all S steps.
+// =========================================================================================================
+constexpr int LHC = 32;
+
+template <class WT, class T, int BT>
+__global__ void __launch_bounds__(256, 1)
+lstm_rec_fwd_kernel(const T* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+                    const float* __restrict__ h0, const float* __restrict__ c0, float* __restrict__ out, T* __restrict__ outT,
+                    T* __restrict__ sI, T* __restrict__ sF, T* __restrict__ sG, T* __restrict__ sO, float* __restrict__ cell,
+                    float* __restrict__ hT, float* __restrict__ cT, int B, int S, int Har) {
+  constexpr int KS = 2, ROWS = 4 * LHC;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int CS = (int)cluster.num_blocks();
+  const int b0 = (blockIdx.x / CS) * BT;
+  const int tid = threadIdx.x;
+  const int wstride = Har + WVec<WT>::V * KS;
+
+  extern __shared__ __align__(16) unsigned char smraw[];
+  WT* Wsm = reinterpret_cast<WT*>(smraw);                                                           // [ROWS][wstride]
+  float* hsm = reinterpret_cast<float*>(smraw + align_up((size_t)ROWS * wstride * sizeof(WT), 16));  // [2][BT][Har]
+  float* gsm = hsm + 2 * BT * Har;                                                                  // [ROWS][BT]
+  float* bsm = gsm + ROWS * BT;                                                                     // [ROWS]
+
+  // resident slice of W_hh: local row r = gate*32 + j  <->  global row gate*Har + 32*rank + j
+  for (int i = tid; i < ROWS * (Har / 4); i += blockDim.x) {
+    const int r = i / (Har / 4), k4 = (i - r * (Har / 4)) * 4;
+    const int grow = (r / LHC) * Har + LHC * rank + (r % LHC);
+    float4 v = *reinterpret_cast<const float4*>(w_hh + (size_t)grow * Har + k4);
+    WT* dst = Wsm + (size_t)r * wstride + k4;
+    dst[0] = from_f<WT>(v.x); dst[1] = from_f<WT>(v.y); dst[2] = from_f<WT>(v.z); dst[3] = from_f<WT>(v.w);
+  }
+  for (int i = tid; i < ROWS; i += blockDim.x) bsm[i] = b_hh[(i / LHC) * Har + LHC * rank + (i % LHC)];
+  for (int i = tid; i < BT * Har; i += blockDim.x) {
+    const int b = i / Har, k = i - b * Har;
+    hsm[i] = (h0 != nullptr && b0 + b < B) ? h0[(size_t)(b0 + b) * Har + k] : 0.f;
+  }
+  cluster.sync();
+
+  const int r = tid / KS, q = tid % KS;
+  const WT* wrow = Wsm + (size_t)r * wstride;
+  const bool gate_thread = tid < LHC * BT;
+  const int gj = tid % LHC, gb = tid / LHC;  // gate thread -> (hidden unit, sequence)
+  const int col = LHC * rank + gj;
+  const bool gvalid = gate_thread && (b0 + gb < B);
+  float cprev = (gvalid && c0 != nullptr) ? c0[(size_t)(b0 + gb) * Har + col] : 0.f;
+
+  for (int t = 0; t < S; t++) {
+    const float* hcur = hsm + (t & 1) * BT * Har;
+    float* hnxt = hsm + ((t + 1) & 1) * BT * Har;
+    float gin[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gvalid) {
+      const T* g = gi + ((size_t)(b0 + gb) * S + t) * 4 * Har + col;
+#pragma unroll
+      for (int k = 0; k < 4; k++) gin[k] = to_f(g[(size_t)k * Har]);
+    }
+    float acc[BT];
+    row_dot<WT, KS, BT>(wrow, hcur, Har, Har, q, acc);
+    if (q == 0) {
+#pragma unroll
+      for (int b = 0; b < BT; b++) gsm[r * BT + b] = acc[b];
+    }
+    __syncthreads();
+    if (gate_thread) {
+      const float ai = gin[0] + gsm[gj * BT + gb] + bsm[gj];
+      const float af = gin[1] + gsm[(LHC + gj) * BT + gb] + bsm[LHC + gj];
+      const float ag = gin[2] + gsm[(2 * LHC + gj) * BT + gb] + bsm[2 * LHC + gj];
+      const float ao = gin[3] + gsm[(3 * LHC + gj) * BT + gb] + bsm[3 * LHC + gj];
+      const float ig = sigmoidf_(ai), fg = sigmoidf_(af), gg = tanhf(ag), og = sigmoidf_(ao);
+      const float cn = fg * cprev + ig * gg;
+      const float hn = og * tanhf(cn);
+      cprev = cn;
+      for (int pr = 0; pr < CS; pr++) {
+        float* dst = cluster.map_shared_rank(hnxt, pr);
+        dst[gb * Har + col] = hn;
+      }
+      if (gvalid) {
+        const size_t o = ((size_t)(b0 + gb) * S + t) * Har + col;
+        out[o] = hn;
+        if (outT) outT[o] = from_f<T>(hn);
+        if (sI != nullptr) {
+          sI[o] = from_f<T>(ig); sF[o] = from_f<T>(fg); sG[o] = from_f<T>(gg); sO[o] = from_f<T>(og);
+          cell[o] = cn;
+        }
+        if (t == S - 1) {
+          if (hT != nullptr) hT[(size_t)(b0 + gb) * Har + col] = hn;
+          if (cT != nullptr) cT[(size_t)(b0 + gb) * Har + col] = cn;
+        }
+      }
+    }
+    cluster.sync();
+  }
+}
+
+// BPTT.  block = LHC*KS = 256 threads.  Wt[j][g] = W_hh[g][32*rank + j] resident (g over all 4*Har gate rows); per step:
+//   gate gradients of the local 32 units -> all-gather over DSMEM -> dh_prev = dgates . W_hh[:, slice]
+template <class WT, class T, int BT>
+__global__ void __launch_bounds__(256, 1)
+lstm_rec_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ c0, const T* __restrict__ sI,
+                    const T* __restrict__ sF, const T* __restrict__ sG, const T* __restrict__ sO, const float* __restrict__ cell,
+                    const float* __restrict__ w_hh, T* __restrict__ dg, int B, int S, int Har) {
+  constexpr int KS = 8;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int CS = (int)cluster.num_blocks();
+  const int b0 = (blockIdx.x / CS) * BT;
+  const int tid = threadIdx.x;
+  const int G = 4 * Har;
+  const int wstride = G + WVec<WT>::V * KS;
+
+  extern __shared__ __align__(16) unsigned char smraw[];
+  WT* Wsm = reinterpret_cast<WT*>(smraw);                                                          // [LHC][wstride]
+  float* dsm = reinterpret_cast<float*>(smraw + align_up((size_t)LHC * wstride * sizeof(WT), 16));  // [2][BT][G]
+  float* osm = dsm + 2 * BT * G;                                                                   // [LHC][BT]
+
+  for (int i = tid; i < LHC * G; i += blockDim.x) {
+    const int g = i / LHC, j = i - g * LHC;
+    Wsm[(size_t)j * wstride + g] = from_f<WT>(w_hh[(size_t)g * Har + LHC * rank + j]);
+  }
+  cluster.sync();
+
+  const int r = tid / KS, q = tid % KS;
+  const WT* wrow = Wsm + (size_t)r * wstride;
+  const bool gate_thread = tid < LHC * BT;
+  const int gj = tid % LHC, gb = tid / LHC;
+  const int col = LHC * rank + gj;
+  const bool gvalid = gate_thread && (b0 + gb < B);
+  float dh_carry = 0.f, dc_carry = 0.f;
+
+  for (int t = S - 1; t >= 0; t--) {
+    float* dbuf = dsm + (t & 1) * BT * G;
+    if (gate_thread) {
+      float da[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gvalid) {
+        const size_t o = ((size_t)(b0 + gb) * S + t) * Har + col;
+        const float dh = dh_carry + dout[o];
+        const float ig = to_f(sI[o]), fg = to_f(sF[o]), gg = to_f(sG[o]), og = to_f(sO[o]);
+        const float cn = cell[o];
+        const float cp = t > 0 ? cell[o - Har] : (c0 ? c0[(size_t)(b0 + gb) * Har + col] : 0.f);
+        const float tc = tanhf(cn);
+        const float dc = dc_carry + dh * og * (1.f - tc * tc);
+        da[0] = dc * gg * ig * (1.f - ig);
+        da[1] = dc * cp * fg * (1.f - fg);
+        da[2] = dc * ig * (1.f - gg * gg);
+        da[3] = dh * tc * og * (1.f - og);
+        dc_carry = dc * fg;
+        const size_t og_ = ((size_t)(b0 + gb) * S + t) * G + col;
+#pragma unroll
+        for (int k = 0; k < 4; k++) dg[og_ + (size_t)k * Har] = from_f<T>(da[k]);
+      }
+      for (int pr = 0; pr < CS; pr++) {
+        float* dst = cluster.map_shared_rank(dbuf, pr) + gb * G + col;
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k * Har] = da[k];
+      }
+    }
+    cluster.sync();
+    float acc[BT];
+    row_dot<WT, KS, BT>(wrow, dbuf, G, G, q, acc);
+    if (q == 0) {
+#pragma unroll
+      for (int b = 0; b < BT; b++) osm[r * BT + b] = acc[b];
+    }
+    __syncthreads();
+    if (gate_thread) dh_carry = osm[gj * BT + gb];
+    __syncthreads();
+  }
+}
+
+template <class WT> size_t lstm_fwd_smem(int Har) {
+  const int wstride = Har + WVec<WT>::V * 2;
+  return align_up((size_t)4 * LHC * wstride * sizeof(WT), 16) + (size_t)(2 * kBT * Har + 4 * LHC * kBT + 4 * LHC) * sizeof(float);
+}
+template <class WT> size_t lstm_bwd_smem(int Har) {
+  const int wstride = 4 * Har + WVec<WT>::V * 8;
+  return align_up((size_t)LHC * wstride * sizeof(WT), 16) + (size_t)(2 * kBT * 4 * Har + LHC * kBT) * sizeof(float);
+}
+
+struct LstmLayout {
+  size_t gates[CPCB200_MAX_GRU_LAYERS][4];  // byte offsets: I, F, G, O (T)
+  size_t cell[CPCB200_MAX_GRU_LAYERS];      // fp32 cell-state sequence
+  size_t hT[CPCB200_MAX_GRU_LAYERS];        // T copy of the layer output (bf16 path only)
+  size_t hf[CPCB200_MAX_GRU_LAYERS];        // fp32 output of non-last layers
+  size_t inT;                               // bf16 copy of the layer-0 input, bf16 path only
+  size_t total;
+};
+LstmLayout lstm_layout(const Geo& g) {
+  LstmLayout l{};
+  size_t off = 0;
+  const size_t es = g.bf16 ? 2 : 4;
+  const size_t n = (size_t)g.B * g.S * g.Har;
+  auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes); return r; };
+  for (int i = 0; i < g.nL; i++) {
+    for (int k = 0; k < 4; k++) l.gates[i][k] = take(n * es);
+    l.cell[i] = take(n * 4);
+    l.hT[i] = g.bf16 ? take(n * es) : 0;
+    l.hf[i] = (i < g.nL - 1) ? take(n * 4) : 0;
+  }
+  l.inT = g.bf16 ? take((size_t)g.B * g.S * g.H * 2) : 0;
+  l.total = off;
+  return l;
+}
+
+template <class T>
+int lstm_fwd_t(const Geo& g, const float* z, const float* h0, const float* c0, const cpcb200_gru_params* p, float* out, float* hT,
+               float* cT, void* save, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  typedef T WT;
+  const int B = g.B, S = g.S, Har = g.Har, G = 4 * Har;
+  const int cs = Har / LHC;
+  if (Har % LHC != 0 || cs > 16) return fail(CPCB200_ERR_UNSUPPORTED, "lstm: Har=%d needs a cluster of %d CTAs (max 16)", Har, cs);
+  const size_t smem = lstm_fwd_smem<WT>(Har);
+  if (smem > 227 * 1024) return fail(CPCB200_ERR_UNSUPPORTED, "lstm fwd: W_hh slice needs %zu B of shared memory (Har=%d, dtype %s)", smem, Har, g.bf16 ? "bf16" : "f32");
+  constexpr bool isf = sizeof(T) == 4;
+  const bool infer = save == nullptr;  // no_grad forward: gates / cell sequence are not kept
+  LstmLayout lay = lstm_layout(g);
+  char* sv = static_cast<char*>(save);
+  Carver ws(wsp, ws_bytes);
+  const int Hmax = g.H > Har ? g.H : Har;
+  T* wih = ws.take<T>((size_t)G * Hmax);
+  T* gi = ws.take<T>((size_t)B * S * G);
+  T* inT = nullptr;
+  T* hTs[2] = {nullptr, nullptr};
+  float* hfs[2] = {nullptr, nullptr};
+  if (!isf) inT = infer ? ws.take<T>((size_t)B * S * g.H) : reinterpret_cast<T*>(sv + lay.inT);
+  if (infer && g.nL > 1) {
+    for (int k = 0; k < 2; k++) { hfs[k] = ws.take<float>((size_t)B * S * Har); if (!isf) hTs[k] = ws.take<T>((size_t)B * S * Har); }
+  }
+  if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "lstm_fwd: workspace %zu < %zu", ws_bytes, ws.off);
+
+  const float* in_f = z;
+  const T* in_t = nullptr;
+  for (int l = 0; l < g.nL; l++) {
+    const int Hin = l == 0 ? g.H : Har;
+    const T* in;
+    const T* w;
+    if (isf) {
+      in = reinterpret_cast<const T*>(in_f);
+      w = reinterpret_cast<const T*>(p->w_ih[l]);
+    } else {
+      if (l == 0) {
+        CPC_TRY(launch_cast3_bf16(z, reinterpret_cast<bf16*>(inT), (long long)B * S * Hin, p->w_ih[l], reinterpret_cast<bf16*>(wih),
+                                  (long long)G * Hin, nullptr, nullptr, 0, st));
+        in = inT;
+      } else {
+        in = in_t;
+        CPC_TRY(launch_cast<T>(p->w_ih[l], wih, (long long)G * Hin, st));
+      }
+      w = wih;
+    }
+    RowView A{in, 0, (long long)Hin, B * S};
+    OutView C{gi, 0, (long long)G, B * S, 0, B * S, 0};
+    CPC_TRY(gemm_nt(g.bf16, false, 1, G, Hin, A, w, p->b_ih[l], C, st));
+
+    const bool last = l == g.nL - 1;
+    float* o_f = last ? out : (infer ? hfs[l & 1] : reinterpret_cast<float*>(sv + lay.hf[l]));
+    T* o_t = isf ? nullptr : (infer ? (last ? nullptr : hTs[l & 1]) : reinterpret_cast<T*>(sv + lay.hT[l]));
+    T* sI = infer ? nullptr : reinterpret_cast<T*>(sv + lay.gates[l][0]);
+    T* sF = infer ? nullptr : reinterpret_cast<T*>(sv + lay.gates[l][1]);
+    T* sG = infer ? nullptr : reinterpret_cast<T*>(sv + lay.gates[l][2]);
+    T* sO = infer ? nullptr : reinterpret_cast<T*>(sv + lay.gates[l][3]);
+    float* cellp = infer ? nullptr : reinterpret_cast<float*>(sv + lay.cell[l]);
+    const float* h0l = h0 ? h0 + (size_t)l * B * Har : nullptr;
+    const float* c0l = c0 ? c0 + (size_t)l * B * Har : nullptr;
+    float* hTl = hT ? hT + (size_t)l * B * Har : nullptr;
+    float* cTl = cT ? cT + (size_t)l * B * Har : nullptr;
+    const T* gic = gi;
+    const float* whh = p->w_hh[l];
+    const float* bhh = p->b_hh[l];
+    int Bv = B, Sv = S, Hv = Har;
+    void* args[] = {&gic, &whh, &bhh, &h0l, &c0l, &o_f, &o_t, &sI, &sF, &sG, &sO, &cellp, &hTl, &cTl, &Bv, &Sv, &Hv};
+    CPC_TRY(launch_cluster("lstm_rec_fwd", lstm_rec_fwd_kernel<WT, T, kBT>, cs, (B + kBT - 1) / kBT, 4 * LHC * 2, smem, st, args));
+    in_f = o_f;
+    in_t = o_t;
+  }
+  return 0;
+}
+
+template <class T>
+int lstm_bwd_t(const Geo& g, const float* z, const float* h0, const float* c0, const cpcb200_gru_params* p, const float* out,
+               const float* dout, const void* save, float* dz, const cpcb200_gru_params* gr, void* wsp, size_t ws_bytes,
+               cudaStream_t st) {
+  typedef T WT;
+  const int B = g.B, S = g.S, Har = g.Har, G = 4 * Har;
+  const int cs = Har / LHC;
+  if (Har % LHC != 0 || cs > 16) return fail(CPCB200_ERR_UNSUPPORTED, "lstm: Har=%d", Har);
+  const size_t smem = lstm_bwd_smem<WT>(Har);
+  if (smem > 227 * 1024) return fail(CPCB200_ERR_UNSUPPORTED, "lstm bwd: W_hh slice needs %zu B of shared memory", smem);
+  constexpr bool isf = sizeof(T) == 4;
+  LstmLayout lay = lstm_layout(g);
+  const char* sv = static_cast<const char*>(save);
+  Carver ws(wsp, ws_bytes);
+  const int Hmax = g.H > Har ? g.H : Har;
+  T* wihT = ws.take<T>((size_t)G * Hmax);
+  T* dg = ws.take<T>((size_t)B * S * G);
+  T* h0T = ws.take<T>((size_t)B * Har);
+  float* dmid = ws.take<float>(g.nL > 1 ? (size_t)B * S * Har : 1);
+  float* dmid2 = ws.take<float>(g.nL > 2 ? (size_t)B * S * Har : 1);
+  if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "lstm_bwd: workspace %zu < %zu", ws_bytes, ws.off);
+  const T* inT = isf ? nullptr : reinterpret_cast<const T*>(sv + lay.inT);
+
+  const float* dl = dout;
+  for (int l = g.nL - 1; l >= 0; l--) {
+    const int Hin = l == 0 ? g.H : Har;
+    const bool last = l == g.nL - 1;
+    const float* hl = last ? out : reinterpret_cast<const float*>(sv + lay.hf[l]);
+    const T* sI = reinterpret_cast<const T*>(sv + lay.gates[l][0]);
+    const T* sF = reinterpret_cast<const T*>(sv + lay.gates[l][1]);
+    const T* sG = reinterpret_cast<const T*>(sv + lay.gates[l][2]);
+    const T* sO = reinterpret_cast<const T*>(sv + lay.gates[l][3]);
+    const float* cellp = reinterpret_cast<const float*>(sv + lay.cell[l]);
+    const float* h0l = h0 ? h0 + (size_t)l * B * Har : nullptr;
+    const float* c0l = c0 ? c0 + (size_t)l * B * Har : nullptr;
+    const float* whh = p->w_hh[l];
+    int Bv = B, Sv = S, Hv = Har;
+    void* args[] = {&dl, &c0l, &sI, &sF, &sG, &sO, &cellp, &whh, &dg, &Bv, &Sv, &Hv};
+    CPC_TRY(launch_cluster("lstm_rec_bwd", lstm_rec_bwd_kernel<WT, T, kBT>, cs, (B + kBT - 1) / kBT, LHC * 8, smem, st, args));
+    // both bias vectors enter every pre-activation with coefficient 1: the same column sums
+    CPC_TRY(launch_colsum<T>(dg, gr->b_ih[l], (long long)B * S, G, st));
+    CPC_TRY(launch_colsum<T>(dg, gr->b_hh[l], (long long)B * S, G, st));
+    const T* in;
+    const T* hseq;
+    if (isf) {
+      in = reinterpret_cast<const T*>(l == 0 ? z : reinterpret_cast<const float*>(sv + lay.hf[l - 1]));
+      hseq = reinterpret_cast<const T*>(hl);
+    } else {
+      in = l == 0 ? inT : reinterpret_cast<const T*>(sv + lay.hT[l - 1]);
+      hseq = reinterpret_cast<const T*>(sv + lay.hT[l]);
+    }
+    {  // dW_ih += dg^T . in  and  dW_hh += sum_{t>=1} dg_t^T . h_{t-1}: one grouped launch
+      TnDesc wg[2];
+      int nw = 0;
+      wg[nw++] = TnDesc{1, G, Hin, RowView{dg, 0, (long long)G, B * S}, RowView{in, 0, (long long)Hin, B * S}, gr->w_ih[l], Hin,
+                        STORE_PLAIN, 0, 0};
+      if (S > 1)
+        wg[nw++] = TnDesc{B, G, Har, RowView{dg + G, (long long)S * G, (long long)G, S - 1},
+                          RowView{hseq, (long long)S * Har, (long long)Har, S - 1}, gr->w_hh[l], Har, STORE_PLAIN, 0, 0};
+      CPC_TRY(gemm_tn_group(g.bf16, nw, wg, st));
+    }
+    if (h0l) {  // t = 0 term with the carried hidden state
+      const T* h0p;
+      if (isf) h0p = reinterpret_cast<const T*>(h0l);
+      else { CPC_TRY(launch_cast<T>(h0l, h0T, (long long)B * Har, st)); h0p = h0T; }
+      RowView A{dg, (long long)S * G, (long long)G, 1};
+      RowView Bv2{h0p, (long long)Har, (long long)Har, 1};
+      CPC_TRY(gemm_tn(g.bf16, B, G, Har, A, Bv2, gr->w_hh[l], Har, STORE_PLAIN, 0, 0, st));
+    }
+    {  // d(input) = dg . W_ih   (as NT against the transposed weights)
+      CPC_TRY(launch_transpose_cast<T>(p->w_ih[l], wihT, G, Hin, st));
+      float* dst = l == 0 ? dz : (dl == dmid ? dmid2 : dmid);
+      RowView A{dg, 0, (long long)G, B * S};
+      OutView C{dst, 0, (long long)Hin, B * S, 0, B * S, 0};
+      CPC_TRY(gemm_nt(g.bf16, true, 1, Hin, G, A, wihT, nullptr, C, st));
+      dl = dst;
+    }
+  }
+  return 0;
+}
+
 }  // namespace
 
 size_t gru_save_bytes(const Geo& g) { return gru_layout(g).total + 256; }
@@ -568,4 +934,27 @@ int gru_bwd(const Geo& g, const float* z, const float* h0, const cpcb200_gru_par
   return gru_bwd_t<float>(g, z, h0, p, c, dc, save, dz, gr, ws, ws_bytes, st);
 }
 
+}  // namespace cpcb200
+
+namespace cpcb200 {
+size_t lstm_save_bytes(const Geo& g) { return lstm_layout(g).total + 256; }
+size_t lstm_ws_bytes(const Geo& g, int mode) {  // mode 0: training forward, 1: backward, 2: inference forward
+  const size_t es = g.bf16 ? 2 : 4;
+  const int Hmax = g.H > g.Har ? g.H : g.Har;
+  const size_t G = (size_t)4 * g.Har, n = (size_t)g.B * g.S;
+  size_t tot = align_up(G * Hmax * es) + align_up(n * G * es);
+  if (mode == 1) tot += align_up((size_t)g.B * g.Har * es) + align_up(g.nL > 1 ? n * g.Har * 4 : 4) + align_up(g.nL > 2 ? n * g.Har * 4 : 4);
+  if (mode == 2) tot += align_up(n * g.H * es) + 2 * (align_up(n * g.Har * 4) + align_up(n * g.Har * es));
+  return tot + 256;
+}
+int lstm_fwd(const Geo& g, const float* z, const float* h0, const float* c0, const cpcb200_gru_params* p, float* out, float* hT,
+             float* cT, void* save, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (g.bf16) return lstm_fwd_t<bf16>(g, z, h0, c0, p, out, hT, cT, save, ws, ws_bytes, st);
+  return lstm_fwd_t<float>(g, z, h0, c0, p, out, hT, cT, save, ws, ws_bytes, st);
+}
+int lstm_bwd(const Geo& g, const float* z, const float* h0, const float* c0, const cpcb200_gru_params* p, const float* out,
+             const float* dout, const void* save, float* dz, const cpcb200_gru_params* gr, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (g.bf16) return lstm_bwd_t<bf16>(g, z, h0, c0, p, out, dout, save, dz, gr, ws, ws_bytes, st);
+  return lstm_bwd_t<float>(g, z, h0, c0, p, out, dout, save, dz, gr, ws, ws_bytes, st);
+}
 }  // namespace cpcb200

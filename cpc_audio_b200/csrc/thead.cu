@@ -29,9 +29,12 @@ constexpr float kLnEps = 1e-5f;
 // attention forward: one CTA per (head, window), thread i = query row i.
 // qkv: (P, 3D) rows = (b, w); att: (P, D).
 // ---------------------------------------------------------------------------------------------------------
+// keep != NULL (train mode, transformers.py:18,49): probability (i, c) of (window b, head h) is multiplied by
+// keep[((b*nh + h)*W + i)*W + c] * dscale before it meets V - the mask torch's nn.Dropout drew for that element.
 template <class T, int DK>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ krel,
-                                                        T* __restrict__ att, int W, int D) {
+                                                        T* __restrict__ att, int W, int D, const unsigned char* __restrict__ keep,
+                                                        float dscale) {
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;                      // [W][DK+1]
   float* Vs = Ks + W * (DK + 1);       // [W][DK+1]
@@ -69,8 +72,10 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const T* __restrict__ qkv
   float o[DK];
 #pragma unroll
   for (int d = 0; d < DK; d++) o[d] = 0.f;
+  const unsigned char* krow = keep != nullptr ? keep + (((size_t)b * gridDim.x + h) * W + i) * W : nullptr;
   for (int c = 0; c <= i; c++) {
-    const float p = prow[c] * inv;
+    float p = prow[c] * inv;
+    if (krow != nullptr) p = krow[c] ? p * dscale : 0.f;
 #pragma unroll
     for (int d = 0; d < DK; d++) o[d] = fmaf(p, Vs[c * (DK + 1) + d], o[d]);
   }
@@ -83,7 +88,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const T* __restrict__ qkv
 template <class T, int DK>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ datt,
                                                         const float* __restrict__ krel, T* __restrict__ dqkv,
-                                                        float* __restrict__ dkrel, int W, int D) {
+                                                        float* __restrict__ dkrel, int W, int D,
+                                                        const unsigned char* __restrict__ keep, float dscale) {
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                      // [W][DK+1]
   float* Ks = Qs + W * (DK + 1);
@@ -124,6 +130,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const T* __restrict__ qkv
     float sum = 0.f;
     for (int c = 0; c <= i; c++) { const float e = __expf(prow[c] - mx); prow[c] = e; sum += e; }
     const float inv = 1.f / sum;
+    const unsigned char* krow = keep != nullptr ? keep + (((size_t)b * gridDim.x + h) * W + i) * W : nullptr;
     float dsum = 0.f;
     for (int c = 0; c <= i; c++) {
       const float p = prow[c] * inv;
@@ -131,6 +138,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const T* __restrict__ qkv
       float dp = 0.f;
 #pragma unroll
       for (int d = 0; d < DK; d++) dp = fmaf(Gs[i * (DK + 1) + d], Vs[c * (DK + 1) + d], dp);
+      if (krow != nullptr) dp = krow[c] ? dp * dscale : 0.f;  // gradient w.r.t. the probability before dropout
       srow[c] = dp;
       dsum = fmaf(dp, p, dsum);
     }
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const T* __restrict__ qkv
       const int m = W - 1 - i + c;
       const float ds = prow[c] * (srow[c] - dsum) * scale;
       srow[c] = ds;
+      if (krow != nullptr) prow[c] = krow[c] ? prow[c] * dscale : 0.f;  // dv below needs the dropped probability
 #pragma unroll
       for (int d = 0; d < DK; d++) dq[d] = fmaf(ds, Ks[c * (DK + 1) + d] + Rs[d * W + m], dq[d]);
     }
@@ -323,10 +332,20 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dya, 
   for (int i = threadIdx.x; i < D; i += blockDim.x) { atomicAdd(dgam + i, accs[i]); atomicAdd(dbet + i, accs[D + i]); }
 }
 
+// h is the FFN hidden AFTER relu (and after dropout in train mode): h > 0 <=> the unit was active and kept, and the
+// gradient through a kept unit carries the dropout scale (transformers.py:92-95)
 template <class T>
-__global__ void relu_mask_kernel(T* __restrict__ dh, const T* __restrict__ h, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+__global__ void relu_mask_kernel(T* __restrict__ dh, const T* __restrict__ h, long long n, float dscale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (!(to_f(h[i]) > 0.f)) dh[i] = from_f<T>(0.f);
+    else if (dscale != 1.f) dh[i] = from_f<T>(to_f(dh[i]) * dscale);
+  }
+}
+// train-mode dropout of the FFN hidden (transformers.py:92): h *= keep * dscale, in place
+template <class T>
+__global__ void dropout_apply_kernel(T* __restrict__ h, const unsigned char* __restrict__ keep, long long n, float dscale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    h[i] = keep[i] ? from_f<T>(to_f(h[i]) * dscale) : from_f<T>(0.f);
 }
 // acc (fp32, P x D) += a + b
 template <class T>
@@ -361,14 +380,15 @@ template <class T> size_t attn_fwd_smem(int W, int DK) { return (size_t)(2 * W *
 template <class T> size_t attn_bwd_smem(int W, int DK) { return (size_t)(4 * W * (DK + 1) + DK * W + 2 * W * (W + 1)) * 4; }
 
 template <class T>
-int launch_attn_fwd(const T* qkv, const float* krel, T* att, int B, int W, int D, int nh, cudaStream_t st) {
+int launch_attn_fwd(const T* qkv, const float* krel, T* att, int B, int W, int D, int nh, const unsigned char* keep, float dscale,
+                    cudaStream_t st) {
   const int DK = D / nh;
   const size_t smem = attn_fwd_smem<T>(W, DK);
   dim3 grid(nh, B);
 #define AF(DKV)                                                                                                   \
   {                                                                                                               \
     CPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<T, DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    attn_fwd_kernel<T, DKV><<<grid, 128, smem, st>>>(qkv, krel, att, W, D);                                        \
+    attn_fwd_kernel<T, DKV><<<grid, 128, smem, st>>>(qkv, krel, att, W, D, keep, dscale);                                        \
   }
   if (DK == 32) AF(32) else if (DK == 8) AF(8) else if (DK == 16) AF(16) else if (DK == 64) AF(64)
   else return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads: dk=%d", DK);
@@ -377,14 +397,15 @@ int launch_attn_fwd(const T* qkv, const float* krel, T* att, int B, int W, int D
   return 0;
 }
 template <class T>
-int launch_attn_bwd(const T* qkv, const T* datt, const float* krel, T* dqkv, float* dkrel, int B, int W, int D, int nh, cudaStream_t st) {
+int launch_attn_bwd(const T* qkv, const T* datt, const float* krel, T* dqkv, float* dkrel, int B, int W, int D, int nh,
+                    const unsigned char* keep, float dscale, cudaStream_t st) {
   const int DK = D / nh;
   const size_t smem = attn_bwd_smem<T>(W, DK);
   dim3 grid(nh, B);
 #define AB(DKV)                                                                                                   \
   {                                                                                                               \
     CPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<T, DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    attn_bwd_kernel<T, DKV><<<grid, 128, smem, st>>>(qkv, datt, krel, dqkv, dkrel, W, D);                          \
+    attn_bwd_kernel<T, DKV><<<grid, 128, smem, st>>>(qkv, datt, krel, dqkv, dkrel, W, D, keep, dscale);                          \
   }
   if (DK == 32) AB(32) else if (DK == 8) AB(8) else if (DK == 16) AB(16) else if (DK == 64) AB(64)
   else return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads: dk=%d", DK);
@@ -483,7 +504,9 @@ int thead_fwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, T* pred
       OutView C{qkv + (size_t)j * D, (long long)W * 3 * D, (long long)3 * D, W, 0, W, 0};
       CPC_TRY(gemm_nt(g.bf16, false, B, D, D, X, Wqkv[j], nullptr, C, st));
     }
-    CPC_TRY(launch_attn_fwd<T>(qkv, tp->krelpos + (size_t)k * (D / nh) * W, att, B, W, D, nh, st));
+    const bool drop = tp->att_keep != nullptr && tp->ffn_keep != nullptr;
+    CPC_TRY(launch_attn_fwd<T>(qkv, tp->krelpos + (size_t)k * (D / nh) * W, att, B, W, D, nh,
+                               drop ? tp->att_keep + (size_t)k * B * nh * W * W : nullptr, tp->keep_scale, st));
     {
       RowView A{att, 0, (long long)D, P};
       OutView C{o, 0, (long long)D, P, 0, P, 0};
@@ -496,6 +519,10 @@ int thead_fwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, T* pred
       OutView C{h, 0, (long long)F, P, 0, P, 0};
       C.relu = 1;
       CPC_TRY(gemm_nt(g.bf16, false, 1, F, D, A, W1, tp->b1 + (size_t)k * F, C, st));
+      if (drop) {
+        dropout_apply_kernel<T><<<grid_for((long long)P * F), 256, 0, st>>>(h, tp->ffn_keep + (size_t)k * P * F, (long long)P * F, tp->keep_scale);
+        CPC_LAUNCHED_N("dropout_apply", st);
+      }
     }
     {
       RowView A{h, 0, (long long)F, P};
@@ -544,7 +571,8 @@ int thead_bwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, const T
       OutView C{dh, 0, (long long)F, P, 0, P, 0};
       CPC_TRY(gemm_nt(g.bf16, false, 1, F, D, A, w2T, nullptr, C, st));                       // dh = ds2 . W2
     }
-    relu_mask_kernel<T><<<grid_for((long long)P * F), 256, 0, st>>>(dh, h, (long long)P * F);
+    const bool drop = tp->att_keep != nullptr && tp->ffn_keep != nullptr;
+    relu_mask_kernel<T><<<grid_for((long long)P * F), 256, 0, st>>>(dh, h, (long long)P * F, drop ? tp->keep_scale : 1.f);
     CPC_LAUNCHED_N("relu_mask", st);
     CPC_TRY(launch_colsum<T>(dh, gr->b1 + (size_t)k * F, P, F, st));
     {
@@ -562,7 +590,8 @@ int thead_bwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, const T
       OutView C{datt, 0, (long long)D, P, 0, P, 0};
       CPC_TRY(gemm_nt(g.bf16, false, 1, D, D, A, woT, nullptr, C, st));
     }
-    CPC_TRY(launch_attn_bwd<T>(qkv, datt, tp->krelpos + (size_t)k * DK * W, dqkv, gr->krelpos + (size_t)k * DK * W, B, W, D, nh, st));
+    CPC_TRY(launch_attn_bwd<T>(qkv, datt, tp->krelpos + (size_t)k * DK * W, dqkv, gr->krelpos + (size_t)k * DK * W, B, W, D, nh,
+                               drop ? tp->att_keep + (size_t)k * B * nh * W * W : nullptr, tp->keep_scale, st));
     {  // Wq, Wk, Wv and d(x)
       float* dw3[3] = {gr->wq + oDD, gr->wk + oDD, gr->wv + oDD};
       for (int j = 0; j < 3; j++) {
@@ -579,6 +608,50 @@ int thead_bwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, const T
   scatter_rows_kernel<<<grid_for((long long)P * D), 256, 0, st>>>(dcw, dc, B, S, W, D);
   CPC_LAUNCHED_N("scatter_rows", st);
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the same layer as a CONTEXT network (--arMode transformer: feature_loader.py:138-142 -> buildTransformerAR(hiddenEncoder,
+// 1, sizeWindow // 160, abspos=False), transformers.py:129-139): one TransformerLayer over all S frames of a window.
+// x (B, S, D) fp32 -> y (B, S, D) fp32; g.K == 1 and g.W == g.S here.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+}  // namespace
+
+size_t tlayer_save_bytes(const Geo& g) {
+  return thead_save_bytes(g) + (g.bf16 ? align_up((size_t)g.B * g.S * g.H * 2) : 0) + 256;
+}
+size_t tlayer_ws_bytes(const Geo& g, int backward) {
+  return thead_ws_bytes(g, backward) + (g.bf16 ? align_up((size_t)g.B * g.S * g.H * 2) : 0) + 256;
+}
+int tlayer_fwd(const Geo& g, const float* x, const cpcb200_thead_params* tp, float* y, void* save, void* wsp, size_t ws_bytes,
+               cudaStream_t st) {
+  const long long n = (long long)g.B * g.S * g.H;
+  Carver ws(wsp, ws_bytes);
+  if (!g.bf16) return thead_fwd<float>(g, x, tp, y, save, ws, st);
+  bf16* xT = static_cast<bf16*>(save);
+  char* sv = static_cast<char*>(save) + align_up((size_t)n * 2);
+  bf16* yT = ws.take<bf16>((size_t)n);
+  CPC_TRY(launch_cast<bf16>(x, xT, n, st));
+  CPC_TRY(thead_fwd<bf16>(g, xT, tp, yT, sv, ws, st));
+  bf16_to_f32_kernel<<<grid_for(n), 256, 0, st>>>(yT, y, n);
+  CPC_LAUNCHED_N("bf16_to_f32", st);
+  return 0;
+}
+int tlayer_bwd(const Geo& g, const float* x, const cpcb200_thead_params* tp, const float* dy, const void* save, float* dx,
+               const cpcb200_thead_params* gr, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  const long long n = (long long)g.B * g.S * g.H;
+  Carver ws(wsp, ws_bytes);
+  if (!g.bf16) return thead_bwd<float>(g, x, tp, dy, save, dx, gr, ws, st);
+  const bf16* xT = static_cast<const bf16*>(save);
+  const char* sv = static_cast<const char*>(save) + align_up((size_t)n * 2);
+  bf16* dyT = ws.take<bf16>((size_t)n);
+  CPC_TRY(launch_cast<bf16>(dy, dyT, n, st));
+  return thead_bwd<bf16>(g, xT, tp, dyT, sv, dx, gr, ws, st);
 }
 
 template int thead_fwd<float>(const Geo&, const float*, const cpcb200_thead_params*, float*, void*, Carver&, cudaStream_t);

@@ -46,12 +46,15 @@ class GraphedTrainStep:
         if self.allreduce is not None:
             self.allreduce()
         self.optimizer.step()
-        self.optimizer.zero_grad()
+        self.optimizer.zero_grad()  # set_to_none=True (torch default) is fine: GradBucket re-attaches its views
         return losses.detach(), acc.detach()
 
     def __call__(self, batch=None):
         if batch is not None and batch.data_ptr() != self.static_x.data_ptr():
             self.static_x.copy_(batch, non_blocking=True)
+        sync_lr = getattr(self.optimizer, "sync_lr", None)
+        if sync_lr is not None:
+            sync_lr()  # an lr_scheduler changed group['lr'] (cpc/train.py:351-370): one 4-byte upload, no re-capture
         self.graph.replay()
         self.replays += 1
         return self.losses, self.acc

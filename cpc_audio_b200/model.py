@@ -49,6 +49,20 @@ def _bytes(n, device):
     return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
 
 
+_CONV_GEOMETRY = ((10, 5, 3), (8, 4, 2), (4, 2, 1), (4, 2, 1), (4, 2, 1))  # (kernel, stride, padding), cpc/model.py:83-92
+
+
+def frames_for(n_samples: int) -> int:
+    """Output frames of the encoder for a window of `n_samples` (= n_samples // 160 when that divides; the reference's
+    Conv1d stack accepts any length, cpc/feature_loader.py:228-269 feeds it chunks whose last one is arbitrary)."""
+    n = int(n_samples)
+    for k, s, p in _CONV_GEOMETRY:
+        n = (n + 2 * p - k) // s + 1
+        if n < 1:
+            return 0
+    return n
+
+
 class ChannelNorm(nn.Module):
     """Parameter holder for cpc/model.py:25-58 (weight/bias of shape (1, C, 1)); the math is fused in the kernels."""
 
@@ -75,7 +89,7 @@ class _EncoderFn(torch.autograd.Function):
         x = x.contiguous().float()
         params = tuple(p.detach().contiguous() for p in params)
         d = L.make_dims(B, Lw, H, H, 1, 1, 1, dtype_code)
-        S = Lw // 160
+        S = frames_for(Lw)
         z = torch.empty(B, S, H, device=dev, dtype=torch.float32)
         save = _bytes(lib.cpcb200_encoder_save_bytes(d), dev)
         wsn = lib.cpcb200_encoder_ws_bytes(d, 0)
@@ -103,6 +117,26 @@ class _EncoderFn(torch.autograd.Function):
             L.check(lib.cpcb200_encoder_bwd(d, L.ptr(x), _encoder_params(params), L.ptr(dz), L.ptr(save),
                                             _encoder_params(grads), L.ptr(ws), wsn, L.stream_ptr(dev)), "encoder_bwd")
         return (None, None, *([None] * len(grads) if sunk else grads))
+
+
+def _encoder_infer(x, dtype_code, params):
+    """no_grad forward (valStep cpc/train.py:141-142, feature extraction feature_loader.py:33): nothing is saved for a
+    backward pass - the intermediate activations ping-pong inside one workspace, pre-norm rows are never written."""
+    _require_cuda(x, "CPCEncoder")
+    lib = L.lib()
+    B, one, Lw = x.shape
+    H = params[0].shape[0]
+    dev = x.device
+    x = x.contiguous().float()
+    params = tuple(p.detach().contiguous() for p in params)
+    d = L.make_dims(B, Lw, H, H, 1, 1, 1, dtype_code)
+    z = torch.empty(B, frames_for(Lw), H, device=dev, dtype=torch.float32)
+    wsn = lib.cpcb200_encoder_ws_bytes(d, 2)
+    ws = _bytes(wsn, dev)
+    with torch.cuda.device(dev):
+        L.check(lib.cpcb200_encoder_fwd(d, L.ptr(x), _encoder_params(params), L.ptr(z), None, L.ptr(ws), wsn, L.stream_ptr(dev)),
+                "encoder_fwd")
+    return z
 
 
 def _encoder_params(ts):
@@ -154,9 +188,12 @@ class CPCEncoder(nn.Module):
         return out
 
     def forward_channel_last(self, x):
-        if x.dim() != 3 or x.size(1) != 1 or x.size(2) % 160 != 0:
-            raise ValueError(f"CPCEncoder expects (B, 1, L) with L a multiple of 160, got {tuple(x.shape)}")
-        return _EncoderFn.apply(x, _dtype_code(self.compute_dtype), *self._params())
+        if x.dim() != 3 or x.size(1) != 1 or frames_for(x.size(2)) < 1:
+            raise ValueError(f"CPCEncoder expects (B, 1, L) with L long enough for one output frame, got {tuple(x.shape)}")
+        params = self._params()
+        if not torch.is_grad_enabled() or not (x.requires_grad or any(p.requires_grad for p in params)):
+            return _encoder_infer(x, _dtype_code(self.compute_dtype), params)
+        return _EncoderFn.apply(x, _dtype_code(self.compute_dtype), *params)
 
     def forward(self, x):
         return self.forward_channel_last(x).permute(0, 2, 1)
@@ -219,21 +256,75 @@ def _gru_params(ts, n_layers):
     return gp
 
 
+class _LstmFn(torch.autograd.Function):
+    """z (B,S,H), h0/c0 (nL,B,Har)|None -> out (B,S,Har), hT, cT.  torch.nn.LSTM(batch_first=True) semantics."""
+
+    @staticmethod
+    def forward(ctx, z, h0, c0, dtype_code, n_layers, train, *params):
+        _require_cuda(z, "CPCAR")
+        lib = L.lib()
+        B, S, H = z.shape
+        Har = params[1].shape[1]
+        dev = z.device
+        z = z.contiguous().float()
+        h0c = h0.contiguous().float() if h0 is not None else None
+        c0c = c0.contiguous().float() if c0 is not None else None
+        params = tuple(p.detach().contiguous() for p in params)
+        d = L.make_dims(B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
+        out = torch.empty(B, S, Har, device=dev, dtype=torch.float32)
+        hT = torch.empty(n_layers, B, Har, device=dev, dtype=torch.float32)
+        cT = torch.empty(n_layers, B, Har, device=dev, dtype=torch.float32)
+        save = _bytes(lib.cpcb200_lstm_save_bytes(d), dev) if train else None
+        wsn = lib.cpcb200_lstm_ws_bytes(d, 0 if train else 2)
+        ws = _bytes(wsn, dev)
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_lstm_fwd(d, L.ptr(z), L.ptr(h0c), L.ptr(c0c), _gru_params(params, n_layers), L.ptr(out), L.ptr(hT),
+                                         L.ptr(cT), L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)), "lstm_fwd")
+        if train:
+            ctx.save_for_backward(z, out, save, *params)
+        ctx.h0, ctx.c0 = h0c, c0c
+        ctx.dims = (B, S, H, Har, n_layers, dtype_code)
+        ctx.mark_non_differentiable(hT, cT)
+        return out, hT, cT
+
+    @staticmethod
+    def backward(ctx, dout, _dhT, _dcT):
+        lib = L.lib()
+        z, out, save, *params = ctx.saved_tensors
+        B, S, H, Har, n_layers, dtype_code = ctx.dims
+        dev = z.device
+        d = L.make_dims(B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
+        grads, sunk = _grad_targets(params, dev)
+        dz = torch.empty_like(z)
+        wsn = lib.cpcb200_lstm_ws_bytes(d, 1)
+        ws = _bytes(wsn, dev)
+        dout = dout.contiguous().float()
+        with torch.cuda.device(dev):
+            L.check(lib.cpcb200_lstm_bwd(d, L.ptr(z), L.ptr(ctx.h0), L.ptr(ctx.c0), _gru_params(params, n_layers), L.ptr(out),
+                                         L.ptr(dout), L.ptr(save), L.ptr(dz), _gru_params(grads, n_layers), L.ptr(ws), wsn,
+                                         L.stream_ptr(dev)), "lstm_bwd")
+        return (dz, None, None, None, None, None, *([None] * len(grads) if sunk else grads))
+
+
 class CPCAR(nn.Module):
-    """cpc/model.py:155-204, GRU branch.  LSTM / RNN / reverse are outside the accelerated path and raise."""
+    """cpc/model.py:155-204: GRU (--arMode GRU) and LSTM (--arMode LSTM, the reference default) context networks.
+    RNN / reverse are outside the accelerated path and raise."""
 
     def __init__(self, dimEncoded, dimOutput, keepHidden, nLevelsGRU, mode="GRU", reverse=False, compute_dtype=None):
         super().__init__()
         self.RESIDUAL_STD = 0.1
-        if mode != "GRU":
-            raise NotImplementedError(f"cpc_audio_b200: arMode={mode!r} is outside the accelerated hot path (GRU only); "
-                                      f"pass --arMode GRU")
+        if mode == "RNN":
+            raise NotImplementedError("cpc_audio_b200: arMode='RNN' is outside the accelerated hot path (GRU, LSTM and "
+                                      "transformer context networks are implemented)")
         if reverse:
             raise NotImplementedError("cpc_audio_b200: cpc_mode='reverse' is outside the accelerated hot path")
         if dimOutput % 64 != 0 or not 64 <= dimOutput <= 512 or not 1 <= nLevelsGRU <= L.MAX_GRU_LAYERS:
             raise NotImplementedError("cpc_audio_b200: hiddenGar must be a multiple of 64 in [64, 512], nLevelsGRU in [1, 4]")
-        # parameter holder: same keys (gAR.baseNet.weight_ih_l0 ...) and default init as the reference
-        self.baseNet = nn.GRU(dimEncoded, dimOutput, num_layers=nLevelsGRU, batch_first=True)
+        # parameter holder: same keys (gAR.baseNet.weight_ih_l0 ...) and default init as the reference (model.py:171-179:
+        # anything that is not 'LSTM' / 'RNN' builds a GRU)
+        self.lstm = mode == "LSTM"
+        cls = nn.LSTM if self.lstm else nn.GRU
+        self.baseNet = cls(dimEncoded, dimOutput, num_layers=nLevelsGRU, batch_first=True)
         self.hidden = None
         self.keepHidden = keepHidden
         self.reverse = reverse
@@ -249,7 +340,16 @@ class CPCAR(nn.Module):
         return out
 
     def forward(self, x):
-        c, hT = _GruFn.apply(x, self.hidden, _dtype_code(self.compute_dtype), self.baseNet.num_layers, *self._params())
+        params = self._params()
+        code, nl = _dtype_code(self.compute_dtype), self.baseNet.num_layers
+        if self.lstm:
+            h0, c0 = self.hidden if self.hidden is not None else (None, None)
+            train = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+            c, hT, cT = _LstmFn.apply(x, h0, c0, code, nl, train, *params)
+            if self.keepHidden:
+                self.hidden = (hT.detach(), cT.detach())  # model.py:194-196: a tuple for the LSTM
+            return c
+        c, hT = _GruFn.apply(x, self.hidden, code, nl, *params)
         if self.keepHidden:
             self.hidden = hT.detach()  # model.py:194-198
         return c

@@ -27,6 +27,11 @@ def install(cpc_package=None):
     for mod in (ref_crit_pkg, ref_crit):
         setattr(mod, "CPCUnsupersivedCriterion", our_crit.CPCUnsupersivedCriterion)
         setattr(mod, "PredictionNetwork", our_crit.PredictionNetwork)
+    # --arMode transformer: feature_loader.getAR does `from .transformers import buildTransformerAR` at call time
+    from . import transformers as our_tr
+    ref_tr = importlib.import_module(cpc_package.__name__ + ".transformers")
+    for name in ("TransformerLayer", "buildTransformerAR"):
+        setattr(ref_tr, name, getattr(our_tr, name))
     return ref_model, ref_crit
 
 

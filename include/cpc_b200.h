@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CPCB200_VERSION 100
+#define CPCB200_VERSION 200
 
 typedef enum {
   CPCB200_OK = 0,
@@ -109,6 +109,18 @@ int cpcb200_gru_bwd(const cpcb200_dims* d, const float* z, const float* h0, cons
                     const float* c, const float* dc, const void* save, float* dz,
                     const cpcb200_gru_params* grads, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- CPCAR.forward, LSTM branch (cpc/model.py:171-173 -> torch.nn.LSTM(batch_first=True); --arMode LSTM is the reference's
+ * default, cpc_default_config.py:74).  Same calling convention as the GRU; the parameter struct carries 4*Har gate rows
+ * (torch order i, f, g, o).  h0 / c0 (nLayers,B,Har) or NULL (= zeros); hT / cT receive the final states (keepHidden).
+ * mode of cpcb200_lstm_ws_bytes: 0 = training forward, 1 = backward, 2 = inference forward (save == NULL: nothing is kept). */
+size_t cpcb200_lstm_save_bytes(const cpcb200_dims* d);
+size_t cpcb200_lstm_ws_bytes(const cpcb200_dims* d, int mode);
+int cpcb200_lstm_fwd(const cpcb200_dims* d, const float* z, const float* h0, const float* c0, const cpcb200_gru_params* p,
+                     float* out, float* hT, float* cT, void* save, void* ws, size_t ws_bytes, void* stream);
+int cpcb200_lstm_bwd(const cpcb200_dims* d, const float* z, const float* h0, const float* c0, const cpcb200_gru_params* p,
+                     const float* out, const float* dout, const void* save, float* dz, const cpcb200_gru_params* grads,
+                     void* ws, size_t ws_bytes, void* stream);
+
 /* ---- negative sampling index arithmetic (criterion.py:191-199) -----------------------------------------
  * batch_idx, seq_idx: the two raw torch.randint draws of criterion.py:181-189, int64, length B*N*W, flat
  * layout (B,N,W).  ext[i] = ((seq_idx[i] + i%W) mod S) + batch_idx[i]*S  as int32.  Bit-exact. */
@@ -131,7 +143,7 @@ int cpcb200_criterion_bwd(const cpcb200_dims* d, const float* c, const float* z,
                           float* dw_pred, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- rnnMode='transformer' prediction heads (criterion.py:82-88 -> cpc/transformers.py:98-139): K one-layer
- * post-LN transformers with relative-position attention, eval-mode semantics (dropout = identity).  Every array is
+ * post-LN transformers with relative-position attention (eval() or train() semantics, see att_keep below).  Every array is
  * the per-head parameter stacked over K: wq/wk/wv/wo (K,H,H) = multihead.W{q,k,v,o}.weight, krelpos (K, H/nheads, W)
  * = multihead.Att.Krelpos, ln1_* (K,H) = ln_multihead, w1 (K,dff,H) b1 (K,dff) = ffnetwork.lin1, w2 (K,H,dff) b2 (K,H)
  * = ffnetwork.lin2, ln2_* (K,H) = ln_ffnetwork.  Requires Har == H and W <= 128.  The same struct carries the
@@ -140,6 +152,14 @@ typedef struct {
   float *wq, *wk, *wv, *wo, *krelpos, *ln1_w, *ln1_b, *w1, *b1, *w2, *b2, *ln2_w, *ln2_b;
   int32_t dff;     /* 2048 in the reference (transformers.py:98) */
   int32_t nheads;  /* 8 */
+  /* train() mode (dropout 0.1 at transformers.py:18,49 on the attention probabilities and :92 on the FFN hidden): the keep
+   * masks torch's nn.Dropout draws - generated by the caller with the same torch calls, in the same order, as the
+   * reference (so the same generator state gives the same masks) - as bytes (0 = dropped, 1 = kept):
+   * att_keep (K, B*nheads, W, W), ffn_keep (K, B*W, dff); kept values are multiplied by keep_scale = 1/(1-p).
+   * Both NULL = eval() semantics.  Ignored in the gradient struct. */
+  const uint8_t* att_keep;
+  const uint8_t* ffn_keep;
+  float keep_scale;
 } cpcb200_thead_params;
 size_t cpcb200_criterion_t_save_bytes(const cpcb200_dims* d, int dff, int nheads);
 size_t cpcb200_criterion_t_ws_bytes(const cpcb200_dims* d, int dff, int nheads, int backward);
@@ -150,20 +170,38 @@ int cpcb200_criterion_t_bwd(const cpcb200_dims* d, const float* c, const float* 
                             const int32_t* ext, const float* dlosses, const void* save, float* dc, float* dz,
                             const cpcb200_thead_params* grads, void* ws, size_t ws_bytes, void* stream);
 
-/* One-shot hook for overlapping the data-parallel gradient all-reduce with the tail of the backward pass: the NEXT
- * cpcb200_encoder_bwd call (from any thread) records `cuda_event` (a cudaEvent_t) on its stream at the point where every
+/* ---- transformer CONTEXT network (--arMode transformer: feature_loader.py:138-142 -> transformers.py:129-139, one
+ * TransformerLayer(sizeSeq = S = L/160 <= 128, dmodel = H) over all frames of a window): x (B,S,H) -> y (B,S,H) fp32.
+ * `p` holds ONE layer (the K dimension of the arrays is 1); att_keep (B*nheads, S, S) / ffn_keep (B*S, dff) as above. */
+size_t cpcb200_tlayer_save_bytes(const cpcb200_dims* d, int dff, int nheads);
+size_t cpcb200_tlayer_ws_bytes(const cpcb200_dims* d, int dff, int nheads, int backward);
+int cpcb200_tlayer_fwd(const cpcb200_dims* d, const float* x, const cpcb200_thead_params* p, float* y, void* save, void* ws,
+                       size_t ws_bytes, void* stream);
+int cpcb200_tlayer_bwd(const cpcb200_dims* d, const float* x, const cpcb200_thead_params* p, const float* dy, const void* save,
+                       float* dx, const cpcb200_thead_params* grads, void* ws, size_t ws_bytes, void* stream);
+
+/* One-shot hook for overlapping the data-parallel gradient exchange with the tail of the backward pass: the NEXT
+ * cpcb200_encoder_bwd call enqueued ON `stream` records `cuda_event` (a cudaEvent_t) on that stream at the point where every
  * parameter gradient of the step except those of conv0 / batchNorm0 is final (the layer 1-4 weight gradients run before
- * the last data gradient).  Pass NULL to disarm.  Process-wide: meant for one process per GPU. */
-int cpcb200_encoder_bwd_set_event(void* cuda_event);
+ * the last data gradient).  Pass cuda_event = NULL to disarm.  The hook is keyed by the stream: DataParallel threads /
+ * several streams of one process do not see each other's events. */
+int cpcb200_encoder_bwd_set_event(void* stream, void* cuda_event);
 
 /* ---- fused Adam over a flat fp32 bucket (cpc/train.py:335-337,90-91; torch.optim.Adam semantics) -------- */
 int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
 /* Same update with the step count kept ON THE DEVICE, so that the launch can be captured in a CUDA graph and replayed
- * (torch.optim.Adam(capturable=True) semantics): `state` = 8 int32 words, zero-initialised by the caller and 8-byte
- * aligned; state[0] = number of steps taken so far (incremented by the kernel after every block has read it), the rest
- * is scratch (a block ticket and beta1^step, beta2^step as running float64 products).  zero_grad != 0 also clears `grad`
- * (optimizer.zero_grad() of cpc/train.py:91 folded into the same pass). */
+ * (torch.optim.Adam(capturable=True) semantics): `state` = CPCB200_OPT_STATE_WORDS (16) int32 words, zero-initialised by
+ * the caller and 8-byte aligned:
+ *   [0] steps taken so far (incremented by the kernel after every block has read it)   [1] block ticket (scratch)
+ *   [2..5] beta1^(steps+1), beta2^(steps+1) as running float64 products                [6] node-barrier epoch (peer exchange)
+ *   [7] error flag of the peer exchange (0 = ok; 1/2/3 = a peer did not arrive within the timeout at the first / second
+ *       barrier of the step kernel / at the early exchange: the update was NOT applied, later calls return at once)
+ *   [8] learning rate as float bits, used when the `lr` ARGUMENT is negative - the host can then change the learning rate
+ *       of a captured graph (lr_scheduler.step(), cpc/train.py:351-370) with one 4-byte upload
+ *   [9], [10] epoch / block ticket of the early exchange; the rest is reserved.
+ * zero_grad != 0 also clears `grad` (optimizer.zero_grad() of cpc/train.py:91 folded into the same pass). */
+#define CPCB200_OPT_STATE_WORDS 16
 int cpcb200_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                           float beta1, float beta2, float eps, float weight_decay, int32_t* state, int zero_grad,
                           void* stream);
@@ -177,8 +215,16 @@ int cpcb200_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_
  *   full replica from its now-reduced local buffer and clears it.
  * grads[i] = device pointer to rank i's gradient bucket (n floats, peer-mapped on this device; grads[rank] is the local
  * one), signals[i] = rank i's signal words (>= 64 x uint32, zero-initialised, peer-mapped), both typically from
- * torch.distributed._symmetric_memory.  state as in cpcb200_adam_step_dev (8 int32, zero-initialised).  Every rank must
- * call it the same number of times.  The launch is cooperative (all CTAs co-resident) and graph-capturable. */
+ * torch.distributed._symmetric_memory.  state as in cpcb200_adam_step_dev (zero-initialised).  Every rank must call it
+ * the same number of times.  The launch is cooperative (all CTAs co-resident) and graph-capturable.
+ * A rank that waits longer than timeout_ns for its peers sets state[7], skips the update and returns normally (no trap):
+ * the host reads state[7] when it next synchronises.
+ *
+ * `ranges` (n_ranges <= 4 pairs [lo, hi) in floats, lo a multiple of 4; NULL = the whole bucket) restricts the exchange to
+ * the parts of the bucket that have NOT been exchanged yet: with cpcb200_peer_reduce_range the bulk of the bucket (every
+ * gradient that is final before the last data-gradient GEMM, see cpcb200_encoder_bwd_set_event) is all-reduced by a small
+ * kernel on a side stream WHILE the backward pass finishes, and the step kernel only exchanges the few KB of conv0 /
+ * batchNorm0 gradients.  Adam always covers the full bucket. */
 typedef struct {
   void* grads[8];
   void* signals[8];
@@ -186,10 +232,16 @@ typedef struct {
   void* grads_mc;  /* optional NVSwitch multicast mapping of the same gradient buckets (NULL: peer loads/stores): the
                     * reduction of a slice is then ONE multimem.ld_reduce per 16 bytes, done inside the switch, and the
                     * write-back ONE multimem.st */
+  int64_t timeout_ns; /* how long a barrier may wait for the peers (<= 0: 600 s) */
 } cpcb200_peers;
 int cpcb200_allreduce_adam_step(const cpcb200_peers* peers, float* param, float* exp_avg, float* exp_avg_sq, size_t n,
                                 float lr, float beta1, float beta2, float eps, float weight_decay, int32_t* state,
-                                int zero_grad, void* stream);
+                                int zero_grad, const int64_t* ranges, int n_ranges, void* stream);
+/* Early exchange: in-place all-reduce(sum) of `ranges` of the gradient buckets over peer memory, enqueued on `stream` (a
+ * side stream that waits for the event of cpcb200_encoder_bwd_set_event).  Ordinary launch of a few CTAs (CPC_B200_EARLY_CTAS,
+ * default 16) that co-reside with the GEMM / conv0 kernels of the backward tail.  Every rank must call it once per step,
+ * before that step's cpcb200_allreduce_adam_step, which must then be given the complementary ranges. */
+int cpcb200_peer_reduce_range(const cpcb200_peers* peers, const int64_t* ranges, int n_ranges, int32_t* state, void* stream);
 
 /* ---- test hooks: the GEMM building blocks, exposed so tests can pin them against torch.matmul ----------
  * C[M,N] = A[M,Kd] * B[N,Kd]^T (+bias[N]) ; C2[N1,N2] += A[M,N1]^T * B[M,N2].  dtype as in cpcb200_dims. */
@@ -202,7 +254,9 @@ int cpcb200_test_gemm_nt_act(int dtype, int M, int N, int Kd, const void* A, con
                              void* C, void* stream);
 /* debug: per-CTA cycle stamps (148 x 8 uint64, relative to each CTA's start) of the last persistent NT GEMM launch:
  * [0] prologue done, [1] first TMA issued, [2] first operands landed, [3] last MMA committed, [4] first accumulator
- * ready, [5] last epilogue done, [6] teardown done, [7] last accumulator ready.  Synchronises the device. */
+ * ready, [5] last epilogue done, [6] teardown done, [7] last accumulator ready.  Synchronises the device.  The stamps are
+ * only written by a library built with -DCPC_B200_TIMELINE (CPC_B200_TIMELINE=1 python -m cpc_audio_b200.build -f); a
+ * release build returns zeros. */
 int cpcb200_debug_gemm_timeline(unsigned long long* host_out);
 
 #ifdef __cplusplus

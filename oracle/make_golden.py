@@ -18,36 +18,39 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
-REF = os.environ.get("CPC_REFERENCE", "/root/reference")
 sys.path.insert(0, REPO)
 
 from oracle import cpc_oracle as O  # noqa: E402
+from oracle.ref_import import import_reference as _import_reference  # noqa: E402
 
 
 def import_reference():
-    for name in ("progressbar", "soundfile"):
-        if name not in sys.modules:
-            sys.modules[name] = types.ModuleType(name)
-    sys.path.insert(0, REF)
-    import cpc.model as ref_model
-    import cpc.transformers as ref_tr
-    sys.modules["transformers"] = ref_tr  # criterion.py:83 does a bare `from transformers import ...`
-    import cpc.criterion as ref_crit
-    return ref_model, ref_crit
+    ref = _import_reference(os.environ.get("CPC_REFERENCE"))
+    if ref is None:
+        raise SystemExit("the reference package is not importable here (/root/reference or baseline/_ref)")
+    return ref.model, ref.criterion
 
 
-def run_reference(d: O.Dims, pred_scale: float, seed: int, heads="linear"):
+def build_reference_ar(ref_model, d, ar):
+    """feature_loader.py:137-152 (getAR) without the argparse namespace."""
+    if ar == "transformer":
+        import cpc.transformers as ref_tr
+        return ref_tr.buildTransformerAR(d.H, 1, d.S, False)
+    return ref_model.CPCAR(d.H, d.Har, False, d.nLayers, mode=ar, reverse=False)
+
+
+def run_reference(d: O.Dims, pred_scale: float, seed: int, heads="linear", ar="GRU", train_dropout=False):
     ref_model, ref_crit = import_reference()
     torch.manual_seed(0)
     enc = ref_model.CPCEncoder(d.H, "layerNorm")
-    ar = ref_model.CPCAR(d.H, d.Har, False, d.nLayers, mode="GRU", reverse=False)
-    model = ref_model.CPCModel(enc, ar)
+    model = ref_model.CPCModel(enc, build_reference_ar(ref_model, d, ar))
     crit = ref_crit.CPCUnsupersivedCriterion(d.K, d.Har, d.H, d.N, mode=None, rnnMode=heads, dropout=False,
                                              speakerEmbedding=0, nSpeakers=0, sizeInputSeq=d.S)
-    mp, cp = O.make_params(d, seed=seed, pred_scale=pred_scale)
+    mp, cp = O.make_params(d, seed=seed, pred_scale=pred_scale, ar=ar)
     if heads == "transformer":
         cp = O.make_params_transformer(d, seed=seed, out_scale=pred_scale)
-    missing = model.load_state_dict(mp, strict=True)
+    missing = model.load_state_dict(mp, strict=False)  # a transformer context net holds the constant buffers Att.z / Att.mask
+    assert not missing.unexpected_keys and all(k.endswith(("Att.z", "Att.mask")) for k in missing.missing_keys), missing
     crit.load_state_dict(cp, strict=False)  # the transformer heads also hold the constant buffers Att.z / Att.mask
     assert all(k.endswith(("Att.z", "Att.mask")) for k in set(crit.state_dict()) - set(cp)), set(crit.state_dict()) - set(cp)
     x, label = O.make_batch(d, seed=1234 + seed)
@@ -64,17 +67,40 @@ def run_reference(d: O.Dims, pred_scale: float, seed: int, heads="linear"):
         assert int(out.min()) >= lo and int(out.max()) < hi
         return out
 
+    # train-mode dropout (transformers.py:18,49,92): nn.Dropout.forward is replaced by one that applies the seeded keep-masks
+    # of O.make_dropout_masks in call order (context network first, then head by head: attention, FFN) - this pins WHERE
+    # the reference applies dropout, the 1/(1-p) scale and the order of the draws
+    ar_masks, head_masks = O.make_dropout_masks(d, seed, ar=ar, heads=heads) if train_dropout else (None, None)
+    queue = []
+    if ar_masks is not None:
+        queue += [ar_masks[0], ar_masks[1]]
+    if head_masks is not None:
+        for k in range(d.K):
+            queue += [head_masks[0][k], head_masks[1][k]]
+    real_dropout_forward = torch.nn.Dropout.forward
+
+    def fake_dropout_forward(self, inp):
+        if not self.training:
+            return inp
+        keep = queue.pop(0)
+        assert keep.numel() == inp.numel() and abs(self.p - 0.1) < 1e-12, (keep.shape, inp.shape, self.p)
+        return inp * keep.to(inp.dtype).view(inp.shape) / (1.0 - self.p)
+
     torch.randint = fake_randint
+    torch.nn.Dropout.forward = fake_dropout_forward
     try:
         model.train()
         crit.train()
-        if heads == "transformer":
-            crit.eval()  # dropout 0.1 inside the heads (transformers.py:18,92): parity is defined in eval mode
+        if not train_dropout:
+            crit.eval()   # dropout 0.1 inside the transformer layers (transformers.py:18,92): eval-mode fixture
+            if ar == "transformer":
+                model.eval()
         c, z, _ = model(x, label)
         losses, acc = crit(c, z, label)
     finally:
         torch.randint = real_randint
-    assert not draws
+        torch.nn.Dropout.forward = real_dropout_forward
+    assert not draws and not queue
     losses.sum().backward()
     grads = {f"model.{k}": v.grad.detach().clone() for k, v in model.named_parameters()}
     grads.update({f"crit.{k}": v.grad.detach().clone() for k, v in crit.named_parameters()})
@@ -82,12 +108,13 @@ def run_reference(d: O.Dims, pred_scale: float, seed: int, heads="linear"):
                 acc=acc.detach(), grads=grads, mp=mp, cp=cp)
 
 
-def check_oracle(d, r, heads="linear"):
+def check_oracle(d, r, heads="linear", ar="GRU", train_dropout=False, seed=0):
     """The restatement must reproduce the reference (this is what pins the oracle)."""
     mp = {k: v.clone().requires_grad_(True) for k, v in r["mp"].items()}
     cp = {k: v.clone().requires_grad_(True) for k, v in r["cp"].items()}
-    c, z = O.model_forward(r["x"], mp, d.nLayers)
-    losses, acc, _ = O.criterion_forward(c, z, cp, r["bi"], r["si"], d.K, d.N, heads=heads)
+    ar_masks, head_masks = O.make_dropout_masks(d, seed, ar=ar, heads=heads) if train_dropout else (None, None)
+    c, z = O.model_forward(r["x"], mp, d.nLayers, ar_masks=ar_masks)
+    losses, acc, _ = O.criterion_forward(c, z, cp, r["bi"], r["si"], d.K, d.N, heads=heads, head_masks=head_masks)
     losses.sum().backward()
     errs = dict(z=(z - r["z"]).abs().max().item(), c=(c - r["c"]).abs().max().item(),
                 loss=(losses - r["losses"]).abs().max().item(), acc=(acc - r["acc"]).abs().max().item())
@@ -108,8 +135,8 @@ def subsample(t, n=4096):
     return f[::step][:n].numpy().copy()
 
 
-def save(name, d, r, pred_scale, seed, heads="linear"):
-    out = dict(heads=np.array(heads), dims=np.array([d.B, d.L, d.H, d.Har, d.K, d.N, d.nLayers], dtype=np.int64),
+def save(name, d, r, pred_scale, seed, heads="linear", ar="GRU", train_dropout=False):
+    out = dict(heads=np.array(heads), ar=np.array(ar), train_dropout=np.int64(int(train_dropout)), dims=np.array([d.B, d.L, d.H, d.Har, d.K, d.N, d.nLayers], dtype=np.int64),
                pred_scale=np.float32(pred_scale), seed=np.int64(seed),
                losses=r["losses"].numpy(), acc=r["acc"].numpy(),
                z_sub=subsample(r["z"]), c_sub=subsample(r["c"]),
@@ -135,6 +162,52 @@ CASES = {
     "cfg4_small": (O.Dims(B=3, L=3200, H=64, Har=64, K=3, N=8, nLayers=1), 30.0, 6, "transformer"),
 }
 
+# context networks other than the GRU and train-mode dropout (row T): name -> (Dims, scale, seed, heads, ar, train)
+CASES2 = {
+    "lstm_small": (O.Dims(B=3, L=3200, H=128, Har=64, K=5, N=16, nLayers=2), 30.0, 7, "linear", "LSTM", False),
+    "cfg1_lstm": (O.Dims(B=2, L=20480, H=256, Har=256, K=12, N=128, nLayers=1), 30.0, 8, "linear", "LSTM", False),   # reference default arMode
+    "tar_small": (O.Dims(B=3, L=3200, H=64, Har=64, K=3, N=8, nLayers=1), 30.0, 9, "linear", "transformer", False),
+    "cfg1_tar": (O.Dims(B=2, L=20480, H=256, Har=256, K=12, N=128, nLayers=1), 30.0, 10, "linear", "transformer", False),
+    "cfg4_small_train": (O.Dims(B=3, L=3200, H=64, Har=64, K=3, N=8, nLayers=1), 30.0, 11, "transformer", "GRU", True),
+    "cfg4_train": (O.Dims(B=2, L=20480, H=256, Har=256, K=12, N=128, nLayers=1), 30.0, 12, "transformer", "GRU", True),
+    "tar_small_train": (O.Dims(B=2, L=3200, H=64, Har=64, K=3, N=8, nLayers=1), 30.0, 13, "transformer", "transformer", True),
+}
+
+
+def make_feature_fixture():
+    """cpc/feature_loader.py: FeatureModule + buildFeature, UNMODIFIED, on CPU: torchaudio.load is replaced by a function
+    returning a seeded waveform and Tensor.cuda by the identity (the only device-specific calls of that code path)."""
+    ref_model, _ = import_reference()
+    import cpc.feature_loader as fl
+    out = {}
+    for name, ar, nl, n, chunk in (("feat_gru", "GRU", 1, 50000, 20480), ("feat_lstm", "LSTM", 2, 33333, 12345)):
+        d = O.Dims(B=1, L=chunk, H=64, Har=64, nLayers=nl)
+        mp, _ = O.make_params(d, seed=21, ar=ar)
+        seq = torch.randn(n, generator=torch.Generator().manual_seed(22)) * 0.1
+        model = ref_model.CPCModel(ref_model.CPCEncoder(d.H, "layerNorm"), ref_model.CPCAR(d.H, d.Har, True, nl, mode=ar, reverse=False))
+        model.load_state_dict(mp, strict=True)
+        model.eval()
+        fm = fl.FeatureModule(model, False)
+        real_load, real_cuda = fl.torchaudio.load, torch.Tensor.cuda
+        fl.torchaudio.load = lambda path: (seq.view(1, -1), 16000)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        try:
+            feat = fl.buildFeature(fm, "seeded.wav", strict=False, maxSizeSeq=chunk)
+        finally:
+            fl.torchaudio.load, torch.Tensor.cuda = real_load, real_cuda
+        mine = O.feature_forward(seq, mp, nl, max_size_seq=chunk, keep_hidden=True)
+        err = (feat - mine).abs().max().item()
+        print(f"[{name}] {tuple(feat.shape)} oracle-vs-reference buildFeature max err {err:.2e}")
+        assert feat.shape == mine.shape and err < 1e-5
+        out[name] = dict(ar=np.array(ar), nLayers=np.int64(nl), n=np.int64(n), chunk=np.int64(chunk), H=np.int64(d.H),
+                         feat_sub=subsample(feat), feat_norm=np.float64(feat.double().norm().item()),
+                         shape=np.array(feat.shape, dtype=np.int64))
+    for name, v in out.items():
+        path = os.path.join(REPO, "tests", "golden", f"{name}.npz")
+        np.savez_compressed(path, **v)
+        print(f"  wrote {path}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     only = sys.argv[1:]
@@ -148,3 +221,13 @@ if __name__ == "__main__":
         print("  losses", np.round(r["losses"].numpy().ravel(), 4), "\n  acc", np.round(r["acc"].numpy().ravel(), 4))
         check_oracle(d, r, heads)
         save(name, d, r, ps, seed, heads)
+    for name, (d, ps, seed, heads, ar, train) in CASES2.items():
+        if only and name not in only:
+            continue
+        print(f"[{name}] {d} pred_scale={ps} heads={heads} ar={ar} train_dropout={train}")
+        r = run_reference(d, ps, seed, heads, ar=ar, train_dropout=train)
+        print("  losses", np.round(r["losses"].numpy().ravel(), 4), "\n  acc", np.round(r["acc"].numpy().ravel(), 4))
+        check_oracle(d, r, heads, ar=ar, train_dropout=train, seed=seed)
+        save(name, d, r, ps, seed, heads, ar=ar, train_dropout=train)
+    if not only or "features" in only:
+        make_feature_fixture()

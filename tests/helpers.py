@@ -9,10 +9,28 @@ from oracle import cpc_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["small", "small2l", "cfg1", "cfg1_scaled"]
 T_CASES = ["cfg4_small", "cfg4"]  # rnnMode='transformer' prediction heads
+AR_CASES = ["lstm_small", "cfg1_lstm", "tar_small", "cfg1_tar"]  # --arMode LSTM / transformer context networks
+TRAIN_CASES = ["cfg4_small_train", "cfg4_train", "tar_small_train"]  # train() mode: dropout of the transformer layers (row T)
+FEATURE_CASES = ["feat_gru", "feat_lstm"]  # feature_loader.buildFeature over chunks of arbitrary length
 
 
 def case_heads(g):
     return str(g["heads"]) if "heads" in g.files else "linear"
+
+
+def case_ar(g):
+    return str(g["ar"]) if "ar" in g.files else "GRU"
+
+
+def case_train(g):
+    return bool(int(g["train_dropout"])) if "train_dropout" in g.files else False
+
+
+def case_masks(g, d):
+    """(ar_masks, head_masks) of a train-mode case, rebuilt from the seed exactly as oracle/make_golden.py did."""
+    if not case_train(g):
+        return None, None
+    return O.make_dropout_masks(d, int(g["seed"]), ar=case_ar(g), heads=case_heads(g))
 
 
 def load_case(name):
@@ -20,7 +38,7 @@ def load_case(name):
     B, L, H, Har, K, N, nL = [int(v) for v in g["dims"]]
     d = O.Dims(B=B, L=L, H=H, Har=Har, K=K, N=N, nLayers=nL)
     seed = int(g["seed"])
-    mp, cp = O.make_params(d, seed=seed, pred_scale=float(g["pred_scale"]))
+    mp, cp = O.make_params(d, seed=seed, pred_scale=float(g["pred_scale"]), ar=case_ar(g))
     if case_heads(g) == "transformer":
         cp = O.make_params_transformer(d, seed=seed, out_scale=float(g["pred_scale"]))
     x, label = O.make_batch(d, seed=1234 + seed)
@@ -34,37 +52,55 @@ def subsample(t, n=4096):
     return f[::step][:n].cpu().numpy().copy()
 
 
-def oracle_run(d, mp, cp, x, bi, si, materialize=True, heads="linear"):
+def oracle_run(d, mp, cp, x, bi, si, materialize=True, heads="linear", ar_masks=None, head_masks=None):
     """fwd + bwd of the CPU oracle; returns dict(c, z, losses, acc, grads{model.*, crit.*})."""
     mp = {k: v.clone().requires_grad_(True) for k, v in mp.items()}
     cp = {k: v.clone().requires_grad_(True) for k, v in cp.items()}
-    c, z = O.model_forward(x, mp, d.nLayers)
-    losses, acc, logits = O.criterion_forward(c, z, cp, bi, si, d.K, d.N, materialize=materialize, heads=heads)
+    c, z = O.model_forward(x, mp, d.nLayers, ar_masks=ar_masks)
+    losses, acc, logits = O.criterion_forward(c, z, cp, bi, si, d.K, d.N, materialize=materialize, heads=heads,
+                                              head_masks=head_masks)
     losses.sum().backward()
     grads = {f"model.{k}": v.grad for k, v in mp.items()}
     grads.update({f"crit.{k}": v.grad for k, v in cp.items()})
     return dict(c=c.detach(), z=z.detach(), losses=losses.detach(), acc=acc.detach(), grads=grads, logits=logits)
 
 
-def build_modules(d, mp, cp, dtype, device="cuda", heads="linear"):
+def build_modules(d, mp, cp, dtype, device="cuda", heads="linear", ar="GRU", keep_hidden=False):
     import cpc_audio_b200 as M
     enc = M.CPCEncoder(d.H, "layerNorm", compute_dtype=dtype)
-    ar = M.CPCAR(d.H, d.Har, False, d.nLayers, mode="GRU", reverse=False, compute_dtype=dtype)
-    model = M.CPCModel(enc, ar)
+    if ar == "transformer":  # feature_loader.py:138-142
+        arnet = M.buildTransformerAR(d.H, 1, d.S, False, compute_dtype=dtype)
+    else:
+        arnet = M.CPCAR(d.H, d.Har, keep_hidden, d.nLayers, mode=ar, reverse=False, compute_dtype=dtype)
+    model = M.CPCModel(enc, arnet)
     crit = M.CPCUnsupersivedCriterion(d.K, d.Har, d.H, d.N, mode=None, rnnMode=heads, dropout=False,
                                       speakerEmbedding=0, nSpeakers=0, sizeInputSeq=d.S, compute_dtype=dtype)
-    model.load_state_dict(mp, strict=True)
-    missing = crit.load_state_dict(cp, strict=False)
-    assert not missing.unexpected_keys and all(k.endswith(("Att.z", "Att.mask")) for k in missing.missing_keys), missing
+    for mod, sd in ((model, mp), (crit, cp)):
+        missing = mod.load_state_dict(sd, strict=False)
+        assert not missing.unexpected_keys and all(k.endswith(("Att.z", "Att.mask")) for k in missing.missing_keys), missing
     return model.to(device), crit.to(device)
 
 
-def run_modules(model, crit, x, label, bi, si):
-    """fwd + bwd through the B200 modules with the negative draws forced to (bi, si)."""
+def run_modules(model, crit, x, label, bi, si, ar_masks=None, head_masks=None):
+    """fwd + bwd through the B200 modules with the negative draws forced to (bi, si).  Transformer layers run in eval()
+    mode unless their train-mode dropout masks are given (then train(), with the draws forced to those masks)."""
     dev = next(model.parameters()).device
     crit.sampleIndices = lambda B, W, S, device: (bi.to(device), si.to(device))
+    model.train()
+    crit.train()
+    is_tar = not hasattr(model.gAR, "baseNet")
     if getattr(crit.wPrediction, "transformer", False):
-        crit.eval()  # the heads' dropout makes train() mode non-deterministic; parity is defined in eval mode
+        if head_masks is None:
+            crit.eval()  # parity without masks is defined in eval mode
+        else:
+            att, ffn = head_masks
+            crit.dropoutMasks = lambda B, W, device, p: (att.to(device), ffn.reshape(ffn.shape[0], B * W, -1).to(device))
+    if is_tar:
+        if ar_masks is None:
+            model.eval()
+        else:
+            a_att, a_ffn = ar_masks
+            model.gAR[0].dropoutMasks = lambda B, S, device: (a_att.unsqueeze(0).to(device), a_ffn.reshape(1, B * S, -1).to(device))
     model.zero_grad(set_to_none=True)
     crit.zero_grad(set_to_none=True)
     c, z, _ = model(x.to(dev), label.to(dev))
@@ -95,3 +131,29 @@ def acc_tolerance(logits_list, d, gap=1e-4):
         near = ((lg[:, 1:].max(1)[0] - lg[:, 0]).abs() <= gap * scale).float().sum()
         tol.append(near / lg.shape[0] + 1e-7)
     return torch.stack(tol).view(1, -1)
+
+
+def cosine(a, b):
+    a, b = a.detach().double().flatten().cpu(), b.detach().double().flatten().cpu()
+    return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+def record(case, **metrics):
+    """Append the MEASURED parity numbers of a GPU test to gpurun_out/parity.jsonl (merged back from the GPU box; the
+    per-round copy is committed as profiles/parity_rNN.json) - the bounds in the tests are these numbers with head-room."""
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity.jsonl"), "a") as f:
+            f.write(json.dumps({"case": case, **metrics}) + "\n")
+    except OSError:
+        pass
+
+
+def grad_report(out_grads, ref_grads):
+    """{tensor: (cosine, rel-L2)} and the worst of each."""
+    rep = {k: (cosine(out_grads[k], g), rel_err(out_grads[k], g)) for k, g in ref_grads.items()}
+    worst_cos = min(rep.items(), key=lambda kv: kv[1][0])
+    worst_rel = max(rep.items(), key=lambda kv: kv[1][1])
+    return rep, worst_cos, worst_rel

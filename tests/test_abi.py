@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(raw, s), f"{s} declared in include/cpc_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in cpc_audio_b200/_lib.py"
     assert sorted(_lib.SIGNATURES) == syms
-    assert _lib.lib().cpcb200_version() == 100
+    assert _lib.lib().cpcb200_version() == 200
 
 
 def test_size_queries_and_validation(built_lib):
@@ -36,11 +36,17 @@ def test_size_queries_and_validation(built_lib):
     assert lib.cpcb200_encoder_ws_bytes(d, 1) > lib.cpcb200_encoder_ws_bytes(d, 0) > 0
     assert lib.cpcb200_gru_save_bytes(d) > 0 and lib.cpcb200_gru_ws_bytes(d, 0) > 0
     assert lib.cpcb200_criterion_save_bytes(d) > 64 * 116 * 12 * 129 * 4
-    bad = L.make_dims(64, 20481, 256, 256, 12, 128, 1, L.BF16)
+    # any window long enough for one output frame is accepted (feature extraction feeds arbitrary chunk lengths) ...
+    odd = L.make_dims(3, 20481, 256, 256, 12, 128, 1, L.BF16)
+    assert lib.cpcb200_encoder_save_bytes(odd) > 0 and lib.cpcb200_encoder_ws_bytes(odd, 2) > 0
+    assert lib.cpcb200_lstm_save_bytes(d) > 0 and lib.cpcb200_lstm_ws_bytes(d, 2) > lib.cpcb200_lstm_ws_bytes(d, 0) > 0
+    assert lib.cpcb200_tlayer_save_bytes(d, 2048, 8) > 0 and lib.cpcb200_tlayer_ws_bytes(d, 2048, 8, 1) > 0
+    # ... a window without a single frame is not
+    bad = L.make_dims(64, 100, 256, 256, 12, 128, 1, L.BF16)
     assert lib.cpcb200_encoder_save_bytes(bad) == 0
     z = ctypes.c_void_p(16)
     st = lib.cpcb200_sample_ext_idx(bad, z, z, z, None)
-    assert st == -1 and b"multiple of 160" in lib.cpcb200_last_error()
+    assert st == -1 and b"too short" in lib.cpcb200_last_error()
     bad2 = L.make_dims(2, 20480, 100, 256, 12, 128, 1, L.F32)
     assert lib.cpcb200_gru_ws_bytes(bad2, 0) == 0
     st = lib.cpcb200_adam_step(None, z, z, z, 4, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None)
@@ -76,7 +82,13 @@ def test_module_surface_matches_reference():
 def test_unsupported_modes_raise_instead_of_falling_back():
     import cpc_audio_b200 as M
     with pytest.raises(NotImplementedError):
-        M.CPCAR(256, 256, False, 1, mode="LSTM")
+        M.CPCAR(256, 256, False, 1, mode="RNN")
+    with pytest.raises(NotImplementedError):
+        M.CPCAR(256, 256, False, 1, mode="GRU", reverse=True)
+    with pytest.raises(NotImplementedError):
+        M.buildTransformerAR(256, 1, 128, True)   # abspos
+    lstm = M.CPCAR(256, 256, True, 2, mode="LSTM")  # the reference default context network: same keys as nn.LSTM
+    assert lstm.baseNet.weight_hh_l1.shape == (1024, 256) and lstm.getDimOutput() == 256
     with pytest.raises(NotImplementedError):
         M.CPCEncoder(256, "batchNorm")
     with pytest.raises(ValueError):
@@ -117,12 +129,15 @@ def test_patch_install_swaps_reference_symbols(tmp_path, monkeypatch):
     model = types.ModuleType("cpc.model")
     crit_pkg = types.ModuleType("cpc.criterion"); crit_pkg.__path__ = []
     crit = types.ModuleType("cpc.criterion.criterion")
+    tr = types.ModuleType("cpc.transformers")
     for name in ("ChannelNorm", "CPCEncoder", "CPCAR", "CPCModel"):
         setattr(model, name, object)
     for m in (crit_pkg, crit):
         m.CPCUnsupersivedCriterion = object
         m.PredictionNetwork = object
-    for name, mod in (("cpc", pkg), ("cpc.model", model), ("cpc.criterion", crit_pkg), ("cpc.criterion.criterion", crit)):
+    tr.TransformerLayer = tr.buildTransformerAR = object
+    for name, mod in (("cpc", pkg), ("cpc.model", model), ("cpc.criterion", crit_pkg), ("cpc.criterion.criterion", crit),
+                      ("cpc.transformers", tr)):
         monkeypatch.setitem(sys.modules, name, mod)
     import cpc_audio_b200 as M
     from cpc_audio_b200 import patch
@@ -130,6 +145,7 @@ def test_patch_install_swaps_reference_symbols(tmp_path, monkeypatch):
     assert model.CPCEncoder is M.CPCEncoder and model.CPCAR is M.CPCAR and model.CPCModel is M.CPCModel
     assert crit.CPCUnsupersivedCriterion is M.CPCUnsupersivedCriterion
     assert crit_pkg.CPCUnsupersivedCriterion is M.CPCUnsupersivedCriterion
+    assert tr.buildTransformerAR is M.buildTransformerAR
     # the constructor calls made by cpc/feature_loader.py:133-152 and cpc/train.py:31-40 work on the mirrors
     enc = model.CPCEncoder(256, "layerNorm")
     ar = model.CPCAR(256, 256, False, 1, mode="GRU", reverse=False)

@@ -397,3 +397,249 @@ def test_peer_adam_matches_nccl_allreduce_plus_adam(built_lib):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "max rel param error" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: context networks, train-mode transformer layers (row T), arbitrary window lengths and the
+# feature path (N3), gradients at the benchmarked shape, measured parity numbers (gpurun_out/parity.jsonl)
+# ---------------------------------------------------------------------------------------------------------------
+def _check_case(name, dtype, tag):
+    g, d, mp, cp, x, label, bi, si = Hh.load_case(name)
+    heads, ar = Hh.case_heads(g), Hh.case_ar(g)
+    ar_masks, head_masks = Hh.case_masks(g, d)
+    ref = Hh.oracle_run(d, mp, cp, x, bi, si, heads=heads, ar_masks=ar_masks, head_masks=head_masks)
+    model, crit = Hh.build_modules(d, mp, cp, dtype, heads=heads, ar=ar)
+    out = Hh.run_modules(model, crit, x, label, bi, si, ar_masks=ar_masks, head_masks=head_masks)
+    rep, wc, wr = Hh.grad_report(out["grads"], ref["grads"])
+    dl = (out["losses"].cpu() - ref["losses"]).abs().max().item()
+    Hh.record(f"{tag}:{name}:{dtype}", z_rel=Hh.rel_err(out["z"], ref["z"]), c_rel=Hh.rel_err(out["c"], ref["c"]), dloss=dl,
+              dacc=(out["acc"].cpu() - ref["acc"]).abs().max().item(), worst_cos=[wc[0], wc[1][0]], worst_rel=[wr[0], wr[1][1]],
+              grads={k: [round(v[0], 6), float(f"{v[1]:.3e}")] for k, v in rep.items()})
+    if dtype == "f32":
+        assert Hh.max_rel(out["z"], ref["z"]) <= 1e-4 and Hh.max_rel(out["c"], ref["c"]) <= 2e-4
+        np.testing.assert_allclose(out["losses"].cpu().numpy(), g["losses"], rtol=1e-5, atol=2e-4)   # the reference fixture
+        np.testing.assert_allclose(out["losses"].cpu().numpy(), ref["losses"].numpy(), rtol=1e-5, atol=2e-4)
+        for k, (cs, rl) in rep.items():
+            assert rl <= 2e-3, (k, rl)
+    else:
+        assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2 and Hh.rel_err(out["c"], ref["c"]) <= 3e-2
+        assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.02 * ref["losses"].abs() + 1e-2).all()
+        for k, (cs, rl) in rep.items():
+            floor = 0.95 if (d.H < 256 or (k.endswith(".bias") and "conv" in k)) else 0.98
+            assert cs >= floor, (k, cs)
+    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else 0.03) + Hh.acc_tolerance(ref["logits"], d)).all()
+
+
+@pytest.mark.parametrize("name", Hh.AR_CASES)
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_context_networks_parity(name, dtype, built_lib):
+    """--arMode LSTM (the reference default, cpc_default_config.py:74) and --arMode transformer (feature_loader.py:138-142)
+    against the oracle and the fixtures generated from the unmodified reference."""
+    _check_case(name, dtype, "ar")
+
+
+@pytest.mark.parametrize("name", Hh.TRAIN_CASES)
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_train_mode_dropout_parity(name, dtype, built_lib):
+    """Transformer layers in train() mode (dropout 0.1 on the attention probabilities and the FFN hidden, transformers.py:
+    49, 92) with the keep-masks forced to the seeded ones of the fixture: loss, accuracy and every gradient."""
+    _check_case(name, dtype, "train")
+
+
+@pytest.mark.parametrize("L,B", [(20000, 2), (12345, 3), (7777, 1), (20480 + 163, 2)])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_arbitrary_window_length(L, B, dtype, built_lib):
+    """Window lengths that are not multiples of 160 (the Conv1d stack of model.py:83-92 floors at every layer): forward and
+    backward against the oracle.  Exercises the partial conv0 tiles, the ragged transposed-conv rows and odd S."""
+    d = O.Dims(B=B, L=L, H=256, Har=256, K=4, N=16, nLayers=1)
+    S = O.encoder_forward(torch.zeros(1, 1, L), O.make_params(d, seed=1)[0]).shape[2]
+    from cpc_audio_b200.model import frames_for
+    assert frames_for(L) == S
+    mp, cp = O.make_params(d, seed=80 + B, pred_scale=30.0)
+    x, label = O.make_batch(d, seed=81)
+    g = torch.Generator().manual_seed(82)
+    W = S - d.K
+    bi = torch.randint(0, B, (d.N * W * B,), generator=g)
+    si = torch.randint(1, S, (d.N * W * B,), generator=g)
+    ref = Hh.oracle_run(d, mp, cp, x, bi, si)
+    model, crit = Hh.build_modules(d, mp, cp, dtype)
+    crit.wPrediction  # noqa: B018
+    out = Hh.run_modules(model, crit, x, label, bi, si)
+    assert out["z"].shape == (B, S, 256)
+    rep, wc, wr = Hh.grad_report(out["grads"], ref["grads"])
+    Hh.record(f"ragged:L{L}:B{B}:{dtype}", z_rel=Hh.rel_err(out["z"], ref["z"]), worst_cos=[wc[0], wc[1][0]], worst_rel=[wr[0], wr[1][1]])
+    if dtype == "f32":
+        assert Hh.max_rel(out["z"], ref["z"]) <= 1e-4 and Hh.max_rel(out["c"], ref["c"]) <= 1e-4
+        np.testing.assert_allclose(out["losses"].cpu().numpy(), ref["losses"].numpy(), rtol=1e-5, atol=1e-4)
+        assert wr[1][1] <= 5e-4, wr
+    else:
+        assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2 and Hh.rel_err(out["c"], ref["c"]) <= 2e-2
+        assert wc[1][0] >= 0.95, wc
+    # no_grad forward (nothing saved, activations ping-pong in the workspace) gives the same features
+    with torch.no_grad():
+        c2, z2, _ = model(x.cuda(), label.cuda())
+    assert Hh.max_rel(z2, out["z"]) <= 1e-6 and Hh.max_rel(c2, out["c"]) <= 1e-6
+
+
+@pytest.mark.parametrize("name", Hh.FEATURE_CASES)
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_feature_path_chunks_with_carried_state(name, dtype, built_lib):
+    """feature_loader.py:228-269 semantics without the reference package: chunks of maxSizeSeq samples (the last one of
+    arbitrary length) through the no_grad model with keepHidden, against oracle.feature_forward and the fixture written from
+    the unmodified buildFeature."""
+    g = np.load(f"{Hh.GOLDEN}/{name}.npz")
+    nl, n, chunk, H = int(g["nLayers"]), int(g["n"]), int(g["chunk"]), int(g["H"])
+    d = O.Dims(B=1, L=chunk, H=H, Har=H, nLayers=nl)
+    mp, cp = O.make_params(d, seed=21, ar=str(g["ar"]))
+    seq = torch.randn(n, generator=torch.Generator().manual_seed(22)) * 0.1
+    want = O.feature_forward(seq, mp, nl, max_size_seq=chunk, keep_hidden=True)
+    model, _ = Hh.build_modules(d, mp, cp, dtype, ar=str(g["ar"]), keep_hidden=True)
+    model.eval()
+    outs, start = [], 0
+    with torch.no_grad():
+        while start < n:
+            sub = seq[start:min(n, start + chunk)].view(1, 1, -1).cuda()
+            c, z, _ = model(sub, None)
+            outs.append(c.cpu())
+            start += chunk
+    feat = torch.cat(outs, 1)
+    assert feat.shape == want.shape == tuple(g["shape"])
+    e = Hh.rel_err(feat, want)
+    Hh.record(f"features:{name}:{dtype}", rel=e)
+    assert e <= (2e-5 if dtype == "f32" else 3e-2), e
+    np.testing.assert_allclose(Hh.subsample(feat), g["feat_sub"], rtol=0, atol=(2e-4 if dtype == "f32" else 5e-2) * np.abs(g["feat_sub"]).max())
+
+
+_FULL = {}
+
+
+def _full_size_oracle():
+    if not _FULL:
+        d = O.Dims(B=64, L=20480, H=256, Har=256, K=12, N=128, nLayers=1)
+        mp, cp = O.make_params(d, seed=7, pred_scale=30.0)
+        x, label = O.make_batch(d, seed=77)
+        bi, si = O.make_raw_indices(d, seed=777)
+        torch.set_num_threads(max(1, min(32, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 8))))
+        _FULL["v"] = (d, mp, cp, x, label, bi, si, Hh.oracle_run(d, mp, cp, x, bi, si, materialize=False))
+    return _FULL["v"]
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_full_size_gradients_against_oracle(dtype, built_lib):
+    """BASELINE config 2 shape (B = 64 windows of 20480 samples, default widths): EVERY parameter gradient against the CPU
+    oracle (einsum scoring, no 11.8 GB materialisation).  This is the shape whose one-wave split-K weight gradients, 8-cluster
+    GRU tiling and 950 K-row scatter-add are benchmarked."""
+    d, mp, cp, x, label, bi, si, ref = _full_size_oracle()
+    model, crit = Hh.build_modules(d, mp, cp, dtype)
+    out = Hh.run_modules(model, crit, x, label, bi, si)
+    rep, wc, wr = Hh.grad_report(out["grads"], ref["grads"])
+    dl = (out["losses"].cpu() - ref["losses"]).abs().max().item()
+    Hh.record(f"full_size:{dtype}", z_rel=Hh.rel_err(out["z"], ref["z"]), c_rel=Hh.rel_err(out["c"], ref["c"]), dloss=dl,
+              dacc=(out["acc"].cpu() - ref["acc"]).abs().max().item(), worst_cos=[wc[0], wc[1][0]], worst_rel=[wr[0], wr[1][1]],
+              grads={k: [round(v[0], 6), float(f"{v[1]:.3e}")] for k, v in rep.items()})
+    if dtype == "f32":
+        assert dl <= 2e-4 and wr[1][1] <= 1e-3, (dl, wr)
+    else:
+        assert dl <= 0.02 * ref["losses"].abs().max().item() + 1e-2
+        for k, (cs, rl) in rep.items():
+            assert cs >= (0.97 if (k.endswith(".bias") and "conv" in k) else 0.995), (k, cs, rl)
+
+
+def test_config5_full_length_bf16(built_lib):
+    """BASELINE config 5 at its full window (hiddenEncoder = hiddenGar = 512, 2-level GRU, K = 16, 256 negatives,
+    81920 samples -> S = 512), B = 2: forward and every gradient against the oracle."""
+    d = O.Dims(B=2, L=81920, H=512, Har=512, K=16, N=256, nLayers=2)
+    mp, cp = O.make_params(d, seed=90, pred_scale=30.0)
+    x, label = O.make_batch(d, seed=91)
+    bi, si = O.make_raw_indices(d, seed=92)
+    ref = Hh.oracle_run(d, mp, cp, x, bi, si, materialize=False)
+    model, crit = Hh.build_modules(d, mp, cp, "bf16")
+    out = Hh.run_modules(model, crit, x, label, bi, si)
+    rep, wc, wr = Hh.grad_report(out["grads"], ref["grads"])
+    Hh.record("config5:S512:bf16", z_rel=Hh.rel_err(out["z"], ref["z"]), c_rel=Hh.rel_err(out["c"], ref["c"]),
+              dloss=(out["losses"].cpu() - ref["losses"]).abs().max().item(), worst_cos=[wc[0], wc[1][0]], worst_rel=[wr[0], wr[1][1]])
+    assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2 and Hh.rel_err(out["c"], ref["c"]) <= 4e-2
+    assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.03 * ref["losses"].abs() + 1e-2).all()
+    assert wc[1][0] >= 0.95, wc
+
+
+def test_optimizer_state_dict_interchanges_with_torch_adam(built_lib):
+    """cpc/train.py:220 saves optimizer.state_dict(), :339-343 loads it: a FlatAdam checkpoint loads into torch.optim.Adam
+    and vice versa, and both continue on the same trajectory; StepLR drives FlatAdam's learning rate (train.py:351-355)."""
+    from cpc_audio_b200.optim import FlatAdam
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    shapes = [(64, 64, 4), (192,), (1, 64, 1), (12, 64, 64)]
+
+    def grads(it):
+        g = torch.Generator(device="cuda").manual_seed(100 + it)
+        return [torch.randn(s, device="cuda", generator=g) for s in shapes]
+
+    p0 = [torch.randn(s, device="cuda", generator=gen) for s in shapes]
+    for capturable in (False, True):
+        pt = [torch.nn.Parameter(p.clone()) for p in p0]
+        pf = [torch.nn.Parameter(p.clone()) for p in p0]
+        ot = torch.optim.Adam(pt, lr=1e-3)
+        of = FlatAdam(pf, lr=1e-3, capturable=capturable, fuse_zero_grad=capturable)
+        st = torch.optim.lr_scheduler.StepLR(ot, 2, gamma=0.5)
+        sf = torch.optim.lr_scheduler.StepLR(of, 2, gamma=0.5)
+        for it in range(5):
+            for a, b, gg in zip(pt, pf, grads(it)):
+                a.grad = gg.clone()
+                b.grad.copy_(gg)
+            ot.step(); of.step(); ot.zero_grad(); of.zero_grad()
+            st.step(); sf.step()
+        assert of.param_groups[0]["lr"] == ot.param_groups[0]["lr"] == 1e-3 * 0.25
+        for a, b in zip(pt, pf):
+            assert (a - b).abs().max().item() <= 3e-6 * max(1.0, a.abs().max().item())
+        # cross-load: torch -> flat, flat -> torch, then 3 more steps on each
+        sd_t, sd_f = ot.state_dict(), of.state_dict()
+        assert set(sd_f["param_groups"][0]) >= {"lr", "betas", "eps", "weight_decay", "amsgrad", "params"}
+        assert int(float(sd_f["state"][0]["step"])) == 5 and sd_f["state"][0]["exp_avg"].shape == pf[0].shape
+        pt2 = [torch.nn.Parameter(p.detach().clone()) for p in pf]
+        pf2 = [torch.nn.Parameter(p.detach().clone()) for p in pt]
+        ot2 = torch.optim.Adam(pt2, lr=1e-3)
+        of2 = FlatAdam(pf2, lr=1e-3, capturable=capturable, fuse_zero_grad=capturable)
+        ot2.load_state_dict(sd_f)
+        of2.load_state_dict(sd_t)
+        assert of2.steps == 5 and of2.param_groups[0]["lr"] == 1e-3 * 0.25
+        for it in range(5, 8):
+            for a, b, c_, e, gg in zip(pt, pf, pt2, pf2, grads(it)):
+                a.grad = gg.clone(); c_.grad = gg.clone()
+                b.grad.copy_(gg); e.grad.copy_(gg)
+            for o in (ot, of, ot2, of2):
+                o.step(); o.zero_grad()
+        for a, b, c_, e in zip(pt, pf, pt2, pf2):
+            tol = 3e-6 * max(1.0, a.abs().max().item())
+            assert (a - b).abs().max().item() <= tol and (a - c_).abs().max().item() <= tol and (a - e).abs().max().item() <= tol
+        for o in (of, of2):
+            o.bucket.detach()
+
+
+def test_bucket_survives_default_zero_grad_of_torch_adam(built_lib):
+    """torch.optim.Optimizer.zero_grad() defaults to set_to_none=True; a GradBucket must keep receiving the
+    gradients (and must never all-reduce a stale buffer) when a stock torch.optim.Adam drives the loop."""
+    from cpc_audio_b200.optim import GradBucket
+    g, d, mp, cp, x, label, bi, si = Hh.load_case("small")
+    model, crit = Hh.build_modules(d, mp, cp, "f32")
+    crit.sampleIndices = lambda B, W, S, device: (bi.to(device), si.to(device))
+    params = list(crit.parameters()) + list(model.parameters())
+    bucket = GradBucket(params)
+    opt = torch.optim.Adam(params, lr=1e-3)
+    ref_model, ref_crit = Hh.build_modules(d, mp, cp, "f32")
+    ref_crit.sampleIndices = crit.sampleIndices
+    ref_params = list(ref_crit.parameters()) + list(ref_model.parameters())
+    ref_opt = torch.optim.Adam(ref_params, lr=1e-3)
+    for step in range(3):
+        for m, c_, o in ((model, crit, opt), (ref_model, ref_crit, ref_opt)):
+            cc, zz, _ = m(x.cuda(), label.cuda())
+            losses, _ = c_(cc, zz, label.cuda())
+            losses.sum().backward()
+        # every gradient sits in the bucket again although zero_grad() set it to None after the previous step
+        for p, v, q in zip(params, bucket.views, ref_params):
+            assert p.grad is v and Hh.rel_err(p.grad, q.grad) <= 1e-5, step
+        opt.step(); opt.zero_grad()          # set_to_none=True
+        ref_opt.step(); ref_opt.zero_grad()
+        assert all(p.grad is None for p in params)
+    for p, q in zip(params, ref_params):
+        assert Hh.rel_err(p, q) <= 1e-5
+    bucket.detach()
