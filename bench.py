@@ -56,6 +56,8 @@ def parse():
                     help="prediction heads: 'linear' = BASELINE config 2/3 (default), 'transformer' = config 4 (eval-mode heads)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="windows per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-py", action="store_true", help="skip the leg that drives the reference's trainStep loop")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the informational leg: unmodified reference modules on this GPU")
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
                     help="'graph' = the step is captured once as a CUDA graph (cpc_audio_b200.graph.GraphedTrainStep) and "
                          "replayed; 'eager' = ~45 launches per step through the nn.Module surfaces, as cpc/train.py issues them")
@@ -67,35 +69,68 @@ def parse():
 # present on the GPU box).  Bounded sample: `cpu_batch` windows per step.
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_reference_throughput(cpu_batch, steps, warmup):
+    """The reference's CPU path on the host cores.  kind = "reference": the UNMODIFIED reference package (baseline/_ref, a
+    pip --target install of /root/reference that travels with the snapshot; /root/reference in the authoring container) -
+    its own factories build the modules and its own ``trainStep`` (cpc/train.py:64-119) runs the steps, with ``Tensor.cuda``
+    neutralised (the one device-specific call of that loop).  kind = "port": the oracle restatement (same torch CPU ops),
+    used only when the reference package is absent."""
     import torch
-    from oracle import cpc_oracle as O
     threads = pick_cpu_threads()
     torch.set_num_threads(threads)
-    log(f"cpu arm: {threads} threads, {cpu_batch} windows/step")
-    d = O.Dims(B=cpu_batch, L=WINDOW, H=256, Har=256, K=12, N=128, nLayers=1)
-    mp, cp = O.make_params(d, seed=0)
-    x, _ = O.make_batch(d, seed=1)
-    bi, si = O.make_raw_indices(d, seed=2)
-    params = [v.requires_grad_(True) for v in list(cp.values()) + list(mp.values())]
-    opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+    ref = None
+    try:
+        from tests import ref_driver as R
+        ref = R.reference_or_none()
+    except Exception as e:  # noqa: BLE001
+        log(f"cpu arm: reference package not importable ({type(e).__name__}: {e}); timing the oracle port")
+    log(f"cpu arm: {threads} threads, {cpu_batch} windows/step, kind={'reference' if ref else 'port'}")
     times = []
     t_begin = time.perf_counter()
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        O.train_step_reference_style(x, mp, cp, bi, si, d)
-        opt.step()
-        opt.zero_grad()
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-        log(f"cpu arm: step {i} {time.perf_counter() - t0:.2f}s")
-        if times and time.perf_counter() - t_begin > 60:  # bounded sample
-            break
+    if ref is not None:
+        args = R.default_args(arMode="GRU", rnnMode="linear")
+        model, crit, model_dp, crit_dp, opt = R.build(args, b200=False, seed=0, device="cpu")
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(cpu_batch, 1, WINDOW, generator=g) * 0.1
+        label = torch.zeros(cpu_batch, dtype=torch.long)
+        real_cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        try:
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                R.train_steps(model_dp, crit_dp, opt, [(x, label)])
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+                log(f"cpu arm: step {i} {time.perf_counter() - t0:.2f}s")
+                if times and time.perf_counter() - t_begin > 60:  # bounded sample
+                    break
+        finally:
+            torch.Tensor.cuda = real_cuda
+        kind, what = "reference", "the unmodified reference (cpc/train.py:trainStep over cpc.model / cpc.criterion, torch CPU fp32)"
+    else:
+        from oracle import cpc_oracle as O
+        d = O.Dims(B=cpu_batch, L=WINDOW, H=256, Har=256, K=12, N=128, nLayers=1)
+        mp, cp = O.make_params(d, seed=0)
+        x, _ = O.make_batch(d, seed=1)
+        bi, si = O.make_raw_indices(d, seed=2)
+        params = [v.requires_grad_(True) for v in list(cp.values()) + list(mp.values())]
+        opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.train_step_reference_style(x, mp, cp, bi, si, d)
+            opt.step()
+            opt.zero_grad()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+            log(f"cpu arm: step {i} {time.perf_counter() - t0:.2f}s")
+            if times and time.perf_counter() - t_begin > 60:  # bounded sample
+                break
+        kind, what = "port", "the oracle port (fwd+bwd+Adam, fp32, torch CPU ops as the reference uses them)"
     steps = len(times)
     times.sort()
     med = times[len(times) // 2]
-    return dict(value=cpu_batch * WINDOW / SR / med, unit="audio-s/s", cores=threads, kind="port",
-                sample=f"{steps} steps of {cpu_batch} windows x {WINDOW} samples (fwd+bwd+Adam, fp32, torch CPU ops as the "
-                       f"reference uses them), median step {med * 1e3:.0f} ms", ms_per_step=med * 1e3)
+    return dict(value=cpu_batch * WINDOW / SR / med, unit="audio-s/s", cores=threads, kind=kind,
+                sample=f"{steps} steps of {cpu_batch} windows x {WINDOW} samples of {what}, median step {med * 1e3:.0f} ms",
+                ms_per_step=med * 1e3)
 
 
 def usable_cores():
@@ -158,7 +193,7 @@ def run_reference_arm(a):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "CPC default (H=256, 1-layer GRU, K=12, 128 negatives), 20480-sample windows, "
                                    f"{a.cpu_batch} windows per CPU step", "global_batch": a.cpu_batch, "seq_len": WINDOW},
-            "cpu_baseline": {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -253,6 +288,109 @@ def algorithmic_work(B, bf16):
     return w
 
 
+def _trainstep_like(loader, model, crit, opt):
+    """The body of cpc/train.py:64-119, statement for statement (used only when the reference package is absent)."""
+    import numpy as np
+    model.train()
+    crit.train()
+    logs = {}
+    it = 0
+    for step, (batchData, label) in enumerate(loader):
+        batchData = batchData.cuda(non_blocking=True)
+        label = label.cuda(non_blocking=True)
+        c_feature, encoded_data, label = model(batchData, label)
+        allLosses, allAcc = crit(c_feature, encoded_data, label)
+        totLoss = allLosses.sum()
+        totLoss.backward()
+        opt.step()
+        opt.zero_grad()
+        if "locLoss_train" not in logs:
+            logs["locLoss_train"] = np.zeros(allLosses.size(1))
+            logs["locAcc_train"] = np.zeros(allLosses.size(1))
+        it += 1
+        logs["locLoss_train"] += (allLosses.mean(dim=0)).detach().cpu().numpy()
+        logs["locAcc_train"] += (allAcc.mean(dim=0)).cpu().numpy()
+    return logs
+
+
+def _drive_trainstep(a, dev, x_host, label, b200, steps, warm):
+    """Build model / criterion / torch.optim.Adam as cpc/train.py:307-337 + 372-375 does and run `steps` steps of trainStep."""
+    import contextlib
+    import io
+    import torch
+    import cpc_audio_b200 as M
+    R = None
+    try:
+        from tests import ref_driver as R_
+        if R_.reference_or_none() is not None:
+            R = R_
+    except Exception:  # noqa: BLE001
+        R = None
+    if R is None and not b200:
+        return None
+    label_host = label.cpu()
+    if R is not None:
+        args = R.default_args(arMode="GRU", rnnMode=a.heads)
+        os.environ["CPC_B200_DTYPE"] = a.dtype
+        model, crit, model_dp, crit_dp, opt = R.build(args, b200=b200, seed=0, device=dev)
+        R.use_b200_modules(False)
+        ref = R.reference_or_none()
+        loop = lambda loader: ref.train.trainStep(loader, model_dp, crit_dp, opt, None, 10 ** 9)  # noqa: E731
+        how = "cpc/train.py:trainStep (unmodified, imported from the reference package)"
+    else:
+        torch.manual_seed(0)
+        model = M.CPCModel(M.CPCEncoder(256, "layerNorm", compute_dtype=a.dtype),
+                           M.CPCAR(256, 256, False, 1, mode="GRU", reverse=False, compute_dtype=a.dtype)).to(dev)
+        crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode=a.heads, dropout=False, speakerEmbedding=0,
+                                          nSpeakers=0, sizeInputSeq=WINDOW // 160, compute_dtype=a.dtype).to(dev)
+        opt = torch.optim.Adam(list(crit.parameters()) + list(model.parameters()), lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+        model_dp = torch.nn.DataParallel(model, device_ids=[dev.index]).to(dev)
+        crit_dp = torch.nn.DataParallel(crit, device_ids=[dev.index]).to(dev)
+        loop = lambda loader: _trainstep_like(loader, model_dp, crit_dp, opt)  # noqa: E731
+        how = "a statement-for-statement copy of the loop of cpc/train.py:64-119 (reference package absent on this box)"
+    with contextlib.redirect_stdout(io.StringIO()):
+        loop([(x_host, label_host)] * warm)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        logs = loop([(x_host, label_host)] * steps)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+    return dt / steps, how, float(logs["locLoss_train"].mean())
+
+
+def train_py_leg(a, dev, x_host, label):
+    from cpc_audio_b200 import _lib as L
+    n0 = L.lib().cpcb200_launch_count()
+    steps = max(10, a.steps)
+    r = _drive_trainstep(a, dev, x_host, label, True, steps, 5)
+    per_step, how, loss = r
+    launches = (L.lib().cpcb200_launch_count() - n0) / (steps + 5)
+    sec = x_host.shape[0] * WINDOW / SR
+    log(f"train.py-driven: {per_step * 1e3:.3f} ms/step ({launches:.0f} launches/step)")
+    return {"value": sec / per_step, "unit": "audio-s/s", "ms_per_step": per_step * 1e3, "steps": steps,
+            "h2d_bytes_per_step": x_host.numel() * 4 + label.numel() * 8, "d2h_bytes_per_step": 2 * 12 * 4,
+            "kernel_launches_per_step": launches, "driver": how, "optimizer": "torch.optim.Adam (as cpc/train.py:335 builds it)",
+            "timing": "host wall clock around the call, device synchronised on both sides (the loop itself reads the loss every step)",
+            "mean_loss": loss}
+
+
+def torch_gpu_leg(a, dev, x_host, label):
+    """Informational (SURVEY 8(d) optional row): the UNMODIFIED reference modules on this same B200 through torch / cuDNN /
+    cuBLAS in fp32 (the reference's own GPU path), driven by its own trainStep.  Not the baseline the contract names (that
+    is the CPU arm) - the honest same-box GPU comparator."""
+    import torch
+    steps = 5
+    r = _drive_trainstep(a, dev, x_host, label, False, steps, 2)
+    if r is None:
+        return {"unavailable": "reference package not present on this box (baseline/_ref)"}
+    per_step, how, loss = r
+    torch.cuda.empty_cache()
+    sec = x_host.shape[0] * WINDOW / SR
+    log(f"torch-on-GPU reference: {per_step * 1e3:.1f} ms/step")
+    return {"value": sec / per_step, "unit": "audio-s/s", "ms_per_step": per_step * 1e3, "steps": steps, "dtype": "f32 (TF32 convs: torch default)",
+            "driver": how, "mean_loss": loss}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -275,8 +413,8 @@ def run_ours(a):
                        M.CPCAR(256, 256, False, 1, mode="GRU", reverse=False, compute_dtype=a.dtype)).to(dev)
     crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode=a.heads, dropout=False, speakerEmbedding=0,
                                       nSpeakers=0, sizeInputSeq=WINDOW // 160, compute_dtype=a.dtype).to(dev)
-    if a.heads == "transformer":
-        crit.eval()  # the heads implement the reference's eval() semantics (no dropout); gradients still flow
+    model.train()
+    crit.train()  # cpc/train.py:71-72: the transformer heads then apply the reference's dropout 0.1 (masks from torch's generator)
     params = list(crit.parameters()) + list(model.parameters())  # cpc/train.py:332 order
     use_graph = a.launch == "graph"
     fused_ar = False  # all-reduce + Adam + zero_grad as ONE kernel over peer memory (PeerAdam) instead of NCCL + Adam
@@ -284,7 +422,10 @@ def run_ours(a):
         opt = None
         if world > 1 and os.environ.get("CPC_B200_FUSED_AR", "1") != "0":
             try:
-                opt = PeerAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, fuse_zero_grad=True)
+                enc = model.gEncoder
+                overlap = os.environ.get("CPC_B200_PEER_OVERLAP", "1") != "0"
+                opt = PeerAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, fuse_zero_grad=True, overlap=overlap,
+                               late_params=[enc.conv0.weight, enc.conv0.bias, enc.batchNorm0.weight, enc.batchNorm0.bias])
                 fused_ar = True
             except Exception as e:  # noqa: BLE001 - symmetric memory unavailable: NCCL all-reduce + fused Adam instead
                 log(f"peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
@@ -312,6 +453,8 @@ def run_ours(a):
         losses, acc = crit(c, z, label)
         if world > 1 and not fused_ar:
             bucket.arm_overlap()
+        elif fused_ar:
+            opt.arm_overlap()
         losses.sum().backward()
         if world > 1 and not fused_ar:
             bucket.allreduce()
@@ -326,7 +469,7 @@ def run_ours(a):
             n_before = lib.cpcb200_launch_count()
             nccl = world > 1 and not fused_ar
             gstep = GraphedTrainStep(model, crit, opt, x_dev, label, allreduce=bucket.allreduce if nccl else None, warmup=3,
-                                     before_backward=bucket.arm_overlap if nccl else None)
+                                     before_backward=bucket.arm_overlap if nccl else (opt.arm_overlap if fused_ar else None))
             launches_per_replay = (lib.cpcb200_launch_count() - n_before) // 4  # 3 warm-up steps + the captured one
             launch_mode = "cuda-graph replay (GraphedTrainStep)"
         except Exception as e:  # noqa: BLE001 - report and run the eager loop instead (same kernels, same work)
@@ -415,6 +558,24 @@ def run_ours(a):
     torch.cuda.synchronize(dev)
     clk = clocks.stop() if clocks else None
 
+    # The drop-in path itself (north_star: "cpc/train.py is unchanged"): the reference's OWN trainStep loop (cpc/train.py:64-119)
+    # - .cuda() of a pinned host batch, forward, backward, torch.optim.Adam.step/zero_grad, loss read back every step - over
+    # freshly built B200 modules behind DataParallel(device_ids=[0]), eager launches, no graph, no fused optimizer.
+    train_py = None
+    if world == 1 and not a.no_train_py:
+        try:
+            train_py = train_py_leg(a, dev, x_host, label)
+        except Exception as e:  # noqa: BLE001
+            log(f"train.py-driven leg failed: {type(e).__name__}: {e}")
+            train_py = {"error": f"{type(e).__name__}: {e}"}
+    torch_gpu = None
+    if world == 1 and not a.no_torch_gpu and a.heads == "linear":
+        try:
+            torch_gpu = torch_gpu_leg(a, dev, x_host, label)
+        except Exception as e:  # noqa: BLE001
+            log(f"torch-on-GPU reference leg failed: {type(e).__name__}: {e}")
+            torch_gpu = {"error": f"{type(e).__name__}: {e}"}
+
     # per-kernel timing pass (CUDA events on the launching stream, same workload, after the timed region)
     roof = None
     log(f"e2e: {ms_e2e / a.steps:.3f} ms/step; per-kernel pass")
@@ -494,16 +655,20 @@ def run_ours(a):
                 "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
                 "config": {"workload": ("BASELINE config 2: CPC default (hiddenEncoder=256, 1-layer GRU, K=12, 128 negatives) "
                                         if a.heads == "linear" else
-                                        "BASELINE config 4: --rnnMode transformer prediction heads (eval-mode), GRU context net, K=12, 128 negatives ")
+                                        "BASELINE config 4: --rnnMode transformer prediction heads (train mode, dropout 0.1), GRU context net, K=12, 128 negatives ")
                                        + f"batch={B}/GPU seq=20480, white-noise 16 kHz windows, random-init weights",
                            "global_batch": B * world, "seq_len": WINDOW, "parallelism": f"dp{world}", "optimizer": a.optimizer, "launch": launch_mode,
                            "gradient_exchange": ("none (1 GPU)" if world == 1 else
-                                                 "one kernel: peer-memory all-reduce + Adam + zero_grad (cpcb200_allreduce_adam_step"
+                                                 ("peer-memory all-reduce of the early gradients on a side stream during the backward tail "
+                                                  "(cpcb200_peer_reduce_range) + one kernel: late-gradient exchange + Adam + zero_grad "
+                                                  if getattr(opt, "overlap", False) else "one kernel: peer-memory all-reduce + Adam + zero_grad ")
+                                                 + "(cpcb200_allreduce_adam_step"
                                                  + (", NVSwitch multimem reduction)" if getattr(opt, "multicast", False) else ", peer loads/stores)")
                                                  if fused_ar else "NCCL all-reduce + fused Adam"),
                            "l2": "no explicit flush: one step streams > 1 GB of activations (> 126 MB L2) between reuses"},
                 "e2e": {"value": sec / (ms_e2e / a.steps * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": ms_e2e / a.steps},
+                "e2e_train_py": train_py, "torch_gpu_reference": torch_gpu,
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -54,6 +54,7 @@ SIGNATURES = {
     "cpcb200_launch_count": (C.c_uint64, []),
     "cpcb200_prof_enable": (_I, [_I]),
     "cpcb200_prof_report": (_I, [C.c_char_p, _SZ]),
+    "cpcb200_gather_windows": (_I, [_P, C.c_int64, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
     "cpcb200_encoder_save_bytes": (_SZ, [_DP]),
     "cpcb200_encoder_ws_bytes": (_SZ, [_DP, _I]),
     "cpcb200_encoder_fwd": (_I, [_DP, _P, C.POINTER(EncoderParams), _P, _P, _P, _SZ, _P]),

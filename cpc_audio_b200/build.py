@@ -7,11 +7,13 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcpc_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "encoder.cu", "gru.cu", "criterion.cu", "score_mma.cu", "gru_mma.cu", "conv0_mma.cu", "thead.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "encoder.cu", "gru.cu", "criterion.cu", "score_mma.cu", "gru_mma.cu", "conv0_mma.cu", "thead.cu", "feeder.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math=false", "-Xptxas", "-v"]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+if os.environ.get("CPC_B200_TIMELINE") == "1":  # debug build: per-CTA cycle stamps in the persistent GEMM (tools/gemm_probe.py)
+    FLAGS.append("-DCPC_B200_TIMELINE")
 
 
 def _stale(obj, src):

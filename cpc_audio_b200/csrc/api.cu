@@ -135,6 +135,8 @@ int tlayer_fwd(const Geo&, const float*, const cpcb200_thead_params*, float*, vo
 int tlayer_bwd(const Geo&, const float*, const cpcb200_thead_params*, const float*, const void*, float*, const cpcb200_thead_params*,
                void*, size_t, cudaStream_t);
 
+int gather_windows(const float*, long long, const long long*, int, int, float*, const long long*, int, long long*, int*, cudaStream_t);
+
 int gemm_nt_simt(bool, bool, int, int, int, const RowView&, const void*, const float*, const OutView&, cudaStream_t);
 int gemm_tn_simt(bool, int, int, int, const RowView&, const RowView&, float*, int, int, int, int, cudaStream_t);
 int debug_gemm_timeline(unsigned long long* host_out);
@@ -732,6 +734,15 @@ int cpcb200_tlayer_bwd(const cpcb200_dims* d, const float* x, const cpcb200_thea
   NOT_NULL(x); NOT_NULL(dy); NOT_NULL(save); NOT_NULL(dx); NOT_NULL(ws);
   prof_mark(static_cast<cudaStream_t>(stream));
   return tlayer_bwd(g, x, p, dy, save, dx, grads, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int cpcb200_gather_windows(const float* data, int64_t n_samples, const int64_t* starts, int B, int L, float* out,
+                           const int64_t* bounds, int n_bounds, int64_t* labels, int32_t* err, void* stream) {
+  NOT_NULL(data); NOT_NULL(starts); NOT_NULL(out); NOT_NULL(err);
+  if (labels != nullptr && (bounds == nullptr || n_bounds < 2)) return fail(CPCB200_ERR_NULL, "gather_windows: labels need >= 2 interval bounds");
+  return gather_windows(data, (long long)n_samples, reinterpret_cast<const long long*>(starts), B, L, out,
+                        reinterpret_cast<const long long*>(bounds), n_bounds, reinterpret_cast<long long*>(labels), err,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int cpcb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,

@@ -86,6 +86,15 @@ uint64_t cpcb200_launch_count(void);
 int cpcb200_prof_enable(int on);
 int cpcb200_prof_report(char* buf, size_t cap);
 
+/* ---- input side: AudioBatchData.__getitem__ + DataLoader collate + .cuda() (cpc/dataset.py:185-202,
+ * cpc/train.py:81) for a pack that is RESIDENT in HBM.  data (n_samples) fp32 = AudioBatchData.data; starts (B) int64 = the
+ * window start indices one batch of the sampler yields (dataset.py:361-408); out (B,1,L) fp32 (16-byte aligned);
+ * labels (B) int64 or NULL = getSpeakerLabel(idx) (dataset.py:177-180) over the interval bounds `bounds` (n_bounds int64,
+ * bounds[0] = 0: AudioBatchData.speakerLabel).  A start outside [0, n_samples - L] sets *err (device int32, caller-zeroed)
+ * and leaves that window untouched.  All pointers are device pointers. */
+int cpcb200_gather_windows(const float* data, int64_t n_samples, const int64_t* starts, int B, int L, float* out,
+                           const int64_t* bounds, int n_bounds, int64_t* labels, int32_t* err, void* stream);
+
 /* ---- CPCEncoder.forward  (cpc/model.py:99-105: 5 x [Conv1d -> ChannelNorm(model.py:50-58) -> ReLU]) -------
  * x (B,1,L) fp32  ->  z (B,S,H) fp32, channel-last (what model.py:287 obtains with .permute(0,2,1)). */
 size_t cpcb200_encoder_save_bytes(const cpcb200_dims* d);
