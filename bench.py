@@ -313,12 +313,16 @@ def _trainstep_like(loader, model, crit, opt):
     return logs
 
 
-def _drive_trainstep(a, dev, x_host, label, b200, steps, warm):
-    """Build model / criterion / torch.optim.Adam as cpc/train.py:307-337 + 372-375 does and run `steps` steps of trainStep."""
+def _drive_trainstep(a, dev, x_host, label, b200, steps, warm, patch_adam=False, feeder=False):
+    """Build model / criterion / torch.optim.Adam as cpc/train.py:307-337 + 372-375 does and run `steps` steps of trainStep.
+    patch_adam: cpc_audio_b200.patch.install(adam=True) - train.py's torch.optim.Adam(...) call then builds the flat fused
+    optimizer.  feeder: the dataLoader is a cpc_audio_b200.feeder.WindowFeeder over an HBM-resident pack (the .cuda() calls
+    of the loop become no-ops) instead of a list of pinned host batches."""
     import contextlib
     import io
     import torch
     import cpc_audio_b200 as M
+    import cpc_audio_b200.patch as patch
     R = None
     try:
         from tests import ref_driver as R_
@@ -329,49 +333,85 @@ def _drive_trainstep(a, dev, x_host, label, b200, steps, warm):
     if R is None and not b200:
         return None
     label_host = label.cpu()
-    if R is not None:
-        args = R.default_args(arMode="GRU", rnnMode=a.heads)
-        os.environ["CPC_B200_DTYPE"] = a.dtype
-        model, crit, model_dp, crit_dp, opt = R.build(args, b200=b200, seed=0, device=dev)
-        R.use_b200_modules(False)
-        ref = R.reference_or_none()
-        loop = lambda loader: ref.train.trainStep(loader, model_dp, crit_dp, opt, None, 10 ** 9)  # noqa: E731
-        how = "cpc/train.py:trainStep (unmodified, imported from the reference package)"
+    Bsz = x_host.shape[0]
+    if patch_adam:
+        patch.install_adam()
+    try:
+        if R is not None:
+            args = R.default_args(arMode="GRU", rnnMode=a.heads)
+            os.environ["CPC_B200_DTYPE"] = a.dtype
+            model, crit, model_dp, crit_dp, opt = R.build(args, b200=b200, seed=0, device=dev)
+            R.use_b200_modules(False)
+            ref = R.reference_or_none()
+            loop = lambda loader: ref.train.trainStep(loader, model_dp, crit_dp, opt, None, 10 ** 9)  # noqa: E731
+            how = "cpc/train.py:trainStep (unmodified, imported from the reference package)"
+        else:
+            torch.manual_seed(0)
+            model = M.CPCModel(M.CPCEncoder(256, "layerNorm", compute_dtype=a.dtype),
+                               M.CPCAR(256, 256, False, 1, mode="GRU", reverse=False, compute_dtype=a.dtype)).to(dev)
+            crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode=a.heads, dropout=False, speakerEmbedding=0,
+                                              nSpeakers=0, sizeInputSeq=WINDOW // 160, compute_dtype=a.dtype).to(dev)
+            opt = torch.optim.Adam(list(crit.parameters()) + list(model.parameters()), lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+            model_dp = torch.nn.DataParallel(model, device_ids=[dev.index]).to(dev)
+            crit_dp = torch.nn.DataParallel(crit, device_ids=[dev.index]).to(dev)
+            loop = lambda loader: _trainstep_like(loader, model_dp, crit_dp, opt)  # noqa: E731
+            how = "a statement-for-statement copy of the loop of cpc/train.py:64-119 (reference package absent on this box)"
+    finally:
+        if patch_adam:
+            patch.uninstall_adam()
+
+    if feeder:
+        import itertools
+        from cpc_audio_b200.feeder import ResidentPack, WindowFeeder
+        n_win = Bsz * 8 + 1
+        g = torch.Generator().manual_seed(3)
+        host_pack = torch.randn(n_win * WINDOW, generator=g) * 0.1
+        bounds = [0, host_pack.numel()]
+        pack = ResidentPack.from_host(host_pack, bounds, bounds, device=dev)
+        feed = WindowFeeder(pack, Bsz, WINDOW, sampling="uniform", random_offset=True)
+
+        def batches(n):  # n batches: as many passes over the resident pack as needed (a pass = 8 batches here)
+            return itertools.islice(itertools.chain.from_iterable(iter(feed) for _ in range(n)), n)
     else:
-        torch.manual_seed(0)
-        model = M.CPCModel(M.CPCEncoder(256, "layerNorm", compute_dtype=a.dtype),
-                           M.CPCAR(256, 256, False, 1, mode="GRU", reverse=False, compute_dtype=a.dtype)).to(dev)
-        crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode=a.heads, dropout=False, speakerEmbedding=0,
-                                          nSpeakers=0, sizeInputSeq=WINDOW // 160, compute_dtype=a.dtype).to(dev)
-        opt = torch.optim.Adam(list(crit.parameters()) + list(model.parameters()), lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
-        model_dp = torch.nn.DataParallel(model, device_ids=[dev.index]).to(dev)
-        crit_dp = torch.nn.DataParallel(crit, device_ids=[dev.index]).to(dev)
-        loop = lambda loader: _trainstep_like(loader, model_dp, crit_dp, opt)  # noqa: E731
-        how = "a statement-for-statement copy of the loop of cpc/train.py:64-119 (reference package absent on this box)"
+        def batches(n):
+            return [(x_host, label_host)] * n
     with contextlib.redirect_stdout(io.StringIO()):
-        loop([(x_host, label_host)] * warm)
+        loop(batches(warm))
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        logs = loop([(x_host, label_host)] * steps)
+        logs = loop(batches(steps))
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
-    return dt / steps, how, float(logs["locLoss_train"].mean())
+    if hasattr(opt, "bucket"):
+        opt.bucket.detach()
+    return dt / steps, how, float(logs["locLoss_train"].mean()), type(opt).__name__
 
 
 def train_py_leg(a, dev, x_host, label):
     from cpc_audio_b200 import _lib as L
-    n0 = L.lib().cpcb200_launch_count()
-    steps = max(10, a.steps)
-    r = _drive_trainstep(a, dev, x_host, label, True, steps, 5)
-    per_step, how, loss = r
-    launches = (L.lib().cpcb200_launch_count() - n0) / (steps + 5)
+    steps = max(20, a.steps)
     sec = x_host.shape[0] * WINDOW / SR
-    log(f"train.py-driven: {per_step * 1e3:.3f} ms/step ({launches:.0f} launches/step)")
-    return {"value": sec / per_step, "unit": "audio-s/s", "ms_per_step": per_step * 1e3, "steps": steps,
-            "h2d_bytes_per_step": x_host.numel() * 4 + label.numel() * 8, "d2h_bytes_per_step": 2 * 12 * 4,
-            "kernel_launches_per_step": launches, "driver": how, "optimizer": "torch.optim.Adam (as cpc/train.py:335 builds it)",
-            "timing": "host wall clock around the call, device synchronised on both sides (the loop itself reads the loss every step)",
-            "mean_loss": loss}
+    out = None
+    for name, kw in (("stock", {}), ("flat_adam", {"patch_adam": True}), ("flat_adam_feeder", {"patch_adam": True, "feeder": True})):
+        n0 = L.lib().cpcb200_launch_count()
+        per_step, how, loss, opt_name = _drive_trainstep(a, dev, x_host, label, True, steps, 5, **kw)
+        launches = (L.lib().cpcb200_launch_count() - n0) / (steps + 5)
+        log(f"train.py-driven [{name}]: {per_step * 1e3:.3f} ms/step ({launches:.0f} library launches/step, optimizer {opt_name})")
+        ent = {"value": sec / per_step, "unit": "audio-s/s", "ms_per_step": per_step * 1e3, "kernel_launches_per_step": launches,
+               "optimizer_class": opt_name, "mean_loss": loss}
+        if out is None:
+            out = dict(ent)
+            out.update({"steps": steps, "h2d_bytes_per_step": x_host.numel() * 4 + label.numel() * 8, "d2h_bytes_per_step": 2 * 12 * 4,
+                        "driver": how, "optimizer": "torch.optim.Adam (as cpc/train.py:335 builds it)",
+                        "timing": "host wall clock around the call, device synchronised on both sides (the loop itself reads the loss every step)",
+                        "variants": {}})
+        else:
+            ent["what"] = {"flat_adam": "cpc_audio_b200.patch.install(adam=True): train.py's torch.optim.Adam(...) call builds the flat fused "
+                                        "optimizer (one kernel per step); host batches as above",
+                           "flat_adam_feeder": "the same + the dataLoader is a WindowFeeder over an HBM-resident pack (SURVEY 8f N2): no "
+                                               "per-step host->device copy, batches cut by cpcb200_gather_windows"}[name]
+            out["variants"][name] = ent
+    return out
 
 
 def torch_gpu_leg(a, dev, x_host, label):
@@ -383,7 +423,7 @@ def torch_gpu_leg(a, dev, x_host, label):
     r = _drive_trainstep(a, dev, x_host, label, False, steps, 2)
     if r is None:
         return {"unavailable": "reference package not present on this box (baseline/_ref)"}
-    per_step, how, loss = r
+    per_step, how, loss, _ = r
     torch.cuda.empty_cache()
     sec = x_host.shape[0] * WINDOW / SR
     log(f"torch-on-GPU reference: {per_step * 1e3:.1f} ms/step")

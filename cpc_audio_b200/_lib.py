@@ -125,5 +125,41 @@ def stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class device_guard:
+    """``with torch.cuda.device(dev)`` without its cost when `dev` is already the current device (the usual case: one
+    process per GPU); DataParallel worker threads still get their own device set."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else 0
+        self.prev = None
+
+    def __enter__(self):
+        import torch
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            import torch
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def f32c(t):
+    """`t` as a contiguous fp32 tensor, without a dispatcher round trip when it already is one."""
+    import torch
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t
+    return t.contiguous().float()
+
+
+def cparams(params):
+    return tuple(p if p.is_contiguous() else p.contiguous() for p in params)
+
+
 def make_dims(B, L, H, Har, K, N, nLayers, dtype):
     return Dims(int(B), int(L), int(H), int(Har), int(K), int(N), int(nLayers), int(dtype))

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .model import _bytes, _dtype_code, _require_cuda, default_dtype
+from .model import _bytes, _dtype_code, _plan, _require_cuda, default_dtype
 
 
 class BaseCriterion(nn.Module):
@@ -139,7 +139,7 @@ class _TLayerFn(torch.autograd.Function):
         lib = L.lib()
         B, S, D = x.shape
         dev = x.device
-        x = x.contiguous().float()
+        x = L.f32c(x)
         params = [p.detach().contiguous() for p in params]
         tp = _thead_struct(params, masks)
         d = L.make_dims(B, S * 160, D, D, 1, 1, 1, dtype_code)
@@ -147,7 +147,7 @@ class _TLayerFn(torch.autograd.Function):
         save = _bytes(lib.cpcb200_tlayer_save_bytes(d, T_DFF, T_HEADS), dev)
         wsn = lib.cpcb200_tlayer_ws_bytes(d, T_DFF, T_HEADS, 0)
         ws = _bytes(wsn, dev)
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(lib.cpcb200_tlayer_fwd(d, L.ptr(x), tp, L.ptr(y), L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)), "tlayer_fwd")
         ctx.save_for_backward(x, save, *params)
         ctx.masks = masks
@@ -168,7 +168,7 @@ class _TLayerFn(torch.autograd.Function):
         wsn = lib.cpcb200_tlayer_ws_bytes(d, T_DFF, T_HEADS, 1)
         ws = _bytes(wsn, dev)
         dy = dy.contiguous().float()
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(lib.cpcb200_tlayer_bwd(d, L.ptr(x), tp, L.ptr(dy), L.ptr(save), L.ptr(dx), tg, L.ptr(ws), wsn,
                                            L.stream_ptr(dev)), "tlayer_bwd")
         return (dx, None, None, *grads)
@@ -213,6 +213,12 @@ class PredictionNetwork(nn.Module):
 
     def stacked(self):
         """Return the (K, H, Har) tensor the K weights live in, re-packing them if they are not contiguous."""
+        f = getattr(self, "_flat", None)
+        if f is not None:  # fast path (every step): first and last weight still sit where the packed buffer says
+            w0, wl = self.predictors[0].weight, self.predictors[-1].weight
+            if w0.data_ptr() == f.data_ptr() and wl.data_ptr() == f.data_ptr() + (f.shape[0] - 1) * f.stride(0) * 4 \
+                    and w0.device == f.device:
+                return f
         ws = [p.weight for p in self.predictors]
         K, (H, Har) = len(ws), ws[0].shape
         step = H * Har * ws[0].element_size()
@@ -243,15 +249,15 @@ class _CriterionFn(torch.autograd.Function):
         lib = L.lib()
         B, S, H, Har, K, N, dtype_code = dims
         dev = c.device
-        c = c.contiguous().float()
-        z = z.contiguous().float()
-        d = L.make_dims(B, S * 160, H, Har, K, N, 1, dtype_code)
+        c = L.f32c(c)
+        z = L.f32c(z)
+        d, save_n, wsns = _plan("crit", B, S * 160, H, Har, K, N, 1, dtype_code)
         losses = torch.empty(K, device=dev, dtype=torch.float32)
         acc = torch.empty(K, device=dev, dtype=torch.float32)
-        save = _bytes(lib.cpcb200_criterion_save_bytes(d), dev)
-        wsn = lib.cpcb200_criterion_ws_bytes(d, 0)
+        save = _bytes(save_n, dev)
+        wsn = wsns[0]
         ws = _bytes(wsn, dev)
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(lib.cpcb200_criterion_fwd(d, L.ptr(c), L.ptr(z), L.ptr(w_flat), L.ptr(ext), L.ptr(losses), L.ptr(acc),
                                               L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)), "criterion_fwd")
         ctx.save_for_backward(c, z, ext, save, w_flat)
@@ -266,7 +272,7 @@ class _CriterionFn(torch.autograd.Function):
         c, z, ext, save, w_flat = ctx.saved_tensors
         B, S, H, Har, K, N, dtype_code = ctx.dims
         dev = c.device
-        d = L.make_dims(B, S * 160, H, Har, K, N, 1, dtype_code)
+        d, _, wsns = _plan("crit", B, S * 160, H, Har, K, N, 1, dtype_code)
         dc = torch.empty_like(c)
         dz = torch.empty_like(z)
         # the weight gradient is accumulated (+=): straight into the gradient bucket when the K weights have their sinks
@@ -276,10 +282,10 @@ class _CriterionFn(torch.autograd.Function):
         sunk = sinks is not None and all(s.is_contiguous() and s.data_ptr() == sinks[0].data_ptr() + i * H * Har * 4
                                          for i, s in enumerate(sinks))
         dw = sinks[0].as_strided((K, H, Har), (H * Har, Har, 1)) if sunk else torch.zeros(K, H, Har, device=dev, dtype=torch.float32)
-        wsn = lib.cpcb200_criterion_ws_bytes(d, 1)
+        wsn = wsns[1]
         ws = _bytes(wsn, dev)
-        dlosses = dlosses.contiguous().float()
-        with torch.cuda.device(dev):
+        dlosses = L.f32c(dlosses)
+        with L.device_guard(dev):
             L.check(lib.cpcb200_criterion_bwd(d, L.ptr(c), L.ptr(z), L.ptr(w_flat), L.ptr(ext), L.ptr(dlosses), L.ptr(save),
                                               L.ptr(dc), L.ptr(dz), L.ptr(dw), L.ptr(ws), wsn, L.stream_ptr(dev)),
                     "criterion_bwd")
@@ -296,8 +302,8 @@ class _CriterionTFn(torch.autograd.Function):
         lib = L.lib()
         B, S, H, Har, K, N, dtype_code = dims
         dev = c.device
-        c = c.contiguous().float()
-        z = z.contiguous().float()
+        c = L.f32c(c)
+        z = L.f32c(z)
         nf = len(L.THEAD_FIELDS)
         stacked = [torch.stack([params[k * nf + j].detach() for k in range(K)]).contiguous() for j in range(nf)]
         tp = _thead_struct(stacked, masks)
@@ -307,7 +313,7 @@ class _CriterionTFn(torch.autograd.Function):
         save = _bytes(lib.cpcb200_criterion_t_save_bytes(d, T_DFF, T_HEADS), dev)
         wsn = lib.cpcb200_criterion_t_ws_bytes(d, T_DFF, T_HEADS, 0)
         ws = _bytes(wsn, dev)
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(lib.cpcb200_criterion_t_fwd(d, L.ptr(c), L.ptr(z), tp, L.ptr(ext), L.ptr(losses), L.ptr(acc), L.ptr(save),
                                                 L.ptr(ws), wsn, L.stream_ptr(dev)), "criterion_t_fwd")
         ctx.save_for_backward(c, z, ext, save, *stacked)
@@ -331,7 +337,7 @@ class _CriterionTFn(torch.autograd.Function):
         wsn = lib.cpcb200_criterion_t_ws_bytes(d, T_DFF, T_HEADS, 1)
         ws = _bytes(wsn, dev)
         dlosses = dlosses.contiguous().float()
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(lib.cpcb200_criterion_t_bwd(d, L.ptr(c), L.ptr(z), tp, L.ptr(ext), L.ptr(dlosses), L.ptr(save), L.ptr(dc),
                                                 L.ptr(dz), tg, L.ptr(ws), wsn, L.stream_ptr(dev)), "criterion_t_bwd")
         nf = len(L.THEAD_FIELDS)
@@ -379,8 +385,8 @@ class CPCUnsupersivedCriterion(BaseCriterion):
         lib = L.lib()
         dev = batchIdx.device
         ext = torch.empty(B, N, S - K, device=dev, dtype=torch.int32)
-        d = L.make_dims(B, S * 160, H, Har, K, N, 1, dtype_code)
-        with torch.cuda.device(dev):
+        d = _plan("crit", B, S * 160, H, Har, K, N, 1, dtype_code)[0]
+        with L.device_guard(dev):
             L.check(lib.cpcb200_sample_ext_idx(d, L.ptr(batchIdx.contiguous()), L.ptr(seqIdx.contiguous()), L.ptr(ext),
                                                L.stream_ptr(dev)), "sample_ext_idx")
         return ext

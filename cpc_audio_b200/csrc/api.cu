@@ -323,13 +323,13 @@ __device__ __forceinline__ bool node_wait(const PeerPtrs& P, int base, unsigned 
 // writes the sum back into that slice of every copy.  With a multicast mapping the sum is ONE multimem.ld_reduce per 16
 // bytes, computed inside the NVSwitch, and the write-back ONE multimem.st.
 // (peer loads cost ~2 us each: all the loads of U quads are issued before the first add)
+template <int U>
 __device__ __forceinline__ void reduce_my_slice(const PeerPtrs& P, long long lo_f, long long hi_f, size_t tid, size_t nthr) {
   const size_t n4 = (size_t)(hi_f - lo_f) / 4, base4 = (size_t)lo_f / 4;
   const size_t per = (n4 + P.world - 1) / P.world;
   const size_t lo = base4 + per * P.rank;
   size_t hi = lo + per;
   if (hi > base4 + n4) hi = base4 + n4;
-  constexpr int U = 8;
   if (P.mc != nullptr) {
     for (size_t i0 = lo + tid; i0 < hi; i0 += U * nthr) {
       float4 acc[U];
@@ -384,14 +384,17 @@ __device__ __forceinline__ void reduce_my_slice(const PeerPtrs& P, long long lo_
 // no CTA ever waits for another CTA of the same grid, only for the peers' arrival words.  Completion needs no signal of
 // its own: a rank enters the step kernel's first barrier only after its own early kernel has finished (stream order), so
 // once every rank has arrived there every slice of every early range has been written everywhere.
-__global__ void __launch_bounds__(512) peer_reduce_kernel(PeerPtrs P, RangeList R, int* __restrict__ state) {
+// Footprint: 256 threads x <= 64 registers, no shared memory - a CTA fits next to a persistent GEMM CTA (192 threads x 168
+// registers, ~200 KB of shared memory) on the same SM; measured with 512 threads x 128 registers (a whole register file)
+// the kernel could not start before the backward pass had drained and the 'overlap' cost 28 us instead of saving 20.
+__global__ void __launch_bounds__(256, 4) peer_reduce_kernel(PeerPtrs P, RangeList R, int* __restrict__ state) {
   if (*reinterpret_cast<volatile int*>(state + kStErr) != 0) return;  // set by an earlier kernel only: grid-uniform
   const unsigned ep = (unsigned)*reinterpret_cast<volatile int*>(state + kStEarlyEpoch);
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
   node_arrive(P, kSigEarly, ep + 1);
   const bool ok = node_wait(P, kSigEarly, ep + 1);
   if (ok) {
-    for (int r = 0; r < R.n; r++) reduce_my_slice(P, R.lo[r], R.hi[r], tid, nthr);
+    for (int r = 0; r < R.n; r++) reduce_my_slice<4>(P, R.lo[r], R.hi[r], tid, nthr);
   } else if (threadIdx.x == 0) {
     atomicExch(state + kStErr, 3);
   }
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, RangeLi
   if (stamp) dbg[0] = (unsigned)(globaltimer_ns() - t_start);
   // ---- two-shot all-reduce, in place, of the ranges that have not been exchanged yet ----
   if (ok1) {
-    for (int r = 0; r < R.n; r++) reduce_my_slice(P, R.lo[r], R.hi[r], tid, nthr);
+    for (int r = 0; r < R.n; r++) reduce_my_slice<8>(P, R.lo[r], R.hi[r], tid, nthr);
   } else if (threadIdx.x == 0) {
     atomicExch(state + kStErr, 1);
   }
@@ -824,9 +827,9 @@ int cpcb200_peer_reduce_range(const cpcb200_peers* peers, const int64_t* ranges,
   RangeList R{};
   CPC_TRY(fill_ranges(ranges, n_ranges, 0, &R));
   if (n_ranges == 0) return 0;
-  static const int ctas = []() { const char* e = getenv("CPC_B200_EARLY_CTAS"); int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 148 ? 148 : v); }();
+  static const int ctas = []() { const char* e = getenv("CPC_B200_EARLY_CTAS"); int v = e ? atoi(e) : 32; return v < 1 ? 1 : (v > 148 ? 148 : v); }();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  peer_reduce_kernel<<<ctas, 512, 0, st>>>(P, R, reinterpret_cast<int*>(state));
+  peer_reduce_kernel<<<ctas, 256, 0, st>>>(P, R, reinterpret_cast<int*>(state));
   CPC_LAUNCHED_N("peer_reduce", st);
   return 0;
 }

@@ -7,6 +7,7 @@ the C ABI of ``include/cpc_b200.h``; there is no eager/CPU fallback - CPU tensor
 """
 from __future__ import annotations
 
+import functools
 import os
 
 import torch
@@ -49,6 +50,27 @@ def _bytes(n, device):
     return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
 
 
+@functools.lru_cache(maxsize=512)
+def _plan(op, B, Lw, H, Har, K, N, nL, code, a=0, b=0):
+    """(dims struct, save bytes, workspace bytes for mode 0 / 1 / 2) of one op at one shape: the size queries cross the
+    C ABI once per shape, not once per step (the eager train.py-driven loop is host-bound)."""
+    lib = L.lib()
+    d = L.make_dims(B, Lw, H, Har, K, N, nL, code)
+    if op == "enc":
+        return d, lib.cpcb200_encoder_save_bytes(d), tuple(lib.cpcb200_encoder_ws_bytes(d, m) for m in (0, 1, 2))
+    if op == "gru":
+        return d, lib.cpcb200_gru_save_bytes(d), tuple(lib.cpcb200_gru_ws_bytes(d, m) for m in (0, 1))
+    if op == "lstm":
+        return d, lib.cpcb200_lstm_save_bytes(d), tuple(lib.cpcb200_lstm_ws_bytes(d, m) for m in (0, 1, 2))
+    if op == "crit":
+        return d, lib.cpcb200_criterion_save_bytes(d), tuple(lib.cpcb200_criterion_ws_bytes(d, m) for m in (0, 1))
+    if op == "crit_t":
+        return d, lib.cpcb200_criterion_t_save_bytes(d, a, b), tuple(lib.cpcb200_criterion_t_ws_bytes(d, a, b, m) for m in (0, 1))
+    if op == "tlayer":
+        return d, lib.cpcb200_tlayer_save_bytes(d, a, b), tuple(lib.cpcb200_tlayer_ws_bytes(d, a, b, m) for m in (0, 1))
+    raise KeyError(op)
+
+
 _CONV_GEOMETRY = ((10, 5, 3), (8, 4, 2), (4, 2, 1), (4, 2, 1), (4, 2, 1))  # (kernel, stride, padding), cpc/model.py:83-92
 
 
@@ -86,36 +108,34 @@ class _EncoderFn(torch.autograd.Function):
         B, one, Lw = x.shape
         H = params[0].shape[0]
         dev = x.device
-        x = x.contiguous().float()
-        params = tuple(p.detach().contiguous() for p in params)
-        d = L.make_dims(B, Lw, H, H, 1, 1, 1, dtype_code)
-        S = frames_for(Lw)
-        z = torch.empty(B, S, H, device=dev, dtype=torch.float32)
-        save = _bytes(lib.cpcb200_encoder_save_bytes(d), dev)
-        wsn = lib.cpcb200_encoder_ws_bytes(d, 0)
-        ws = _bytes(wsn, dev)
-        ep = _encoder_params(params)
-        with torch.cuda.device(dev):
-            L.check(lib.cpcb200_encoder_fwd(d, L.ptr(x), ep, L.ptr(z), L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)),
-                    "encoder_fwd")
-        ctx.save_for_backward(x, save, *params)
+        x = L.f32c(x)
+        params = L.cparams(params)
+        d, save_n, wsn = _plan("enc", B, Lw, H, H, 1, 1, 1, dtype_code)
+        z = torch.empty(B, frames_for(Lw), H, device=dev, dtype=torch.float32)
+        save = _bytes(save_n, dev)
+        ws = _bytes(wsn[0], dev)
+        with L.device_guard(dev):
+            L.check(lib.cpcb200_encoder_fwd(d, L.ptr(x), _encoder_params(params), L.ptr(z), L.ptr(save), L.ptr(ws), wsn[0],
+                                            L.stream_ptr(dev)), "encoder_fwd")
+        ctx.save_for_backward(x, save)
+        ctx.params = params
         ctx.dims = (B, Lw, H, dtype_code)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         lib = L.lib()
-        x, save, *params = ctx.saved_tensors
+        x, save = ctx.saved_tensors
+        params = ctx.params
         B, Lw, H, dtype_code = ctx.dims
         dev = x.device
-        d = L.make_dims(B, Lw, H, H, 1, 1, 1, dtype_code)
+        d, _, wsn = _plan("enc", B, Lw, H, H, 1, 1, 1, dtype_code)
         grads, sunk = _grad_targets(params, dev)
-        wsn = lib.cpcb200_encoder_ws_bytes(d, 1)
-        ws = _bytes(wsn, dev)
-        dz = dz.contiguous().float()
-        with torch.cuda.device(dev):
+        ws = _bytes(wsn[1], dev)
+        dz = L.f32c(dz)
+        with L.device_guard(dev):
             L.check(lib.cpcb200_encoder_bwd(d, L.ptr(x), _encoder_params(params), L.ptr(dz), L.ptr(save),
-                                            _encoder_params(grads), L.ptr(ws), wsn, L.stream_ptr(dev)), "encoder_bwd")
+                                            _encoder_params(grads), L.ptr(ws), wsn[1], L.stream_ptr(dev)), "encoder_bwd")
         return (None, None, *([None] * len(grads) if sunk else grads))
 
 
@@ -127,14 +147,13 @@ def _encoder_infer(x, dtype_code, params):
     B, one, Lw = x.shape
     H = params[0].shape[0]
     dev = x.device
-    x = x.contiguous().float()
-    params = tuple(p.detach().contiguous() for p in params)
-    d = L.make_dims(B, Lw, H, H, 1, 1, 1, dtype_code)
+    x = L.f32c(x)
+    params = L.cparams([p.detach() for p in params])
+    d, _, wsn = _plan("enc", B, Lw, H, H, 1, 1, 1, dtype_code)
     z = torch.empty(B, frames_for(Lw), H, device=dev, dtype=torch.float32)
-    wsn = lib.cpcb200_encoder_ws_bytes(d, 2)
-    ws = _bytes(wsn, dev)
-    with torch.cuda.device(dev):
-        L.check(lib.cpcb200_encoder_fwd(d, L.ptr(x), _encoder_params(params), L.ptr(z), None, L.ptr(ws), wsn, L.stream_ptr(dev)),
+    ws = _bytes(wsn[2], dev)
+    with L.device_guard(dev):
+        L.check(lib.cpcb200_encoder_fwd(d, L.ptr(x), _encoder_params(params), L.ptr(z), None, L.ptr(ws), wsn[2], L.stream_ptr(dev)),
                 "encoder_fwd")
     return z
 
@@ -209,19 +228,19 @@ class _GruFn(torch.autograd.Function):
         B, S, H = z.shape
         Har = params[1].shape[1]
         dev = z.device
-        z = z.contiguous().float()
-        h0c = h0.contiguous().float() if h0 is not None else None
-        params = tuple(p.detach().contiguous() for p in params)
-        d = L.make_dims(B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
+        z = L.f32c(z)
+        h0c = L.f32c(h0) if h0 is not None else None
+        params = L.cparams(params)
+        d, save_n, wsn = _plan("gru", B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
         c = torch.empty(B, S, Har, device=dev, dtype=torch.float32)
         hT = torch.empty(n_layers, B, Har, device=dev, dtype=torch.float32)
-        save = _bytes(lib.cpcb200_gru_save_bytes(d), dev)
-        wsn = lib.cpcb200_gru_ws_bytes(d, 0)
-        ws = _bytes(wsn, dev)
-        with torch.cuda.device(dev):
+        save = _bytes(save_n, dev)
+        ws = _bytes(wsn[0], dev)
+        with L.device_guard(dev):
             L.check(lib.cpcb200_gru_fwd(d, L.ptr(z), L.ptr(h0c), _gru_params(params, n_layers), L.ptr(c), L.ptr(hT),
-                                        L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)), "gru_fwd")
-        ctx.save_for_backward(z, c, save, *params)
+                                        L.ptr(save), L.ptr(ws), wsn[0], L.stream_ptr(dev)), "gru_fwd")
+        ctx.save_for_backward(z, c, save)
+        ctx.params = params
         ctx.h0 = h0c
         ctx.dims = (B, S, H, Har, n_layers, dtype_code)
         ctx.mark_non_differentiable(hT)
@@ -230,18 +249,18 @@ class _GruFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dc, _dhT):
         lib = L.lib()
-        z, c, save, *params = ctx.saved_tensors
+        z, c, save = ctx.saved_tensors
+        params = ctx.params
         B, S, H, Har, n_layers, dtype_code = ctx.dims
         dev = z.device
-        d = L.make_dims(B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
+        d, _, wsn = _plan("gru", B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
         grads, sunk = _grad_targets(params, dev)
         dz = torch.empty_like(z)
-        wsn = lib.cpcb200_gru_ws_bytes(d, 1)
-        ws = _bytes(wsn, dev)
-        dc = dc.contiguous().float()
-        with torch.cuda.device(dev):
+        ws = _bytes(wsn[1], dev)
+        dc = L.f32c(dc)
+        with L.device_guard(dev):
             L.check(lib.cpcb200_gru_bwd(d, L.ptr(z), L.ptr(ctx.h0), _gru_params(params, n_layers), L.ptr(c), L.ptr(dc),
-                                        L.ptr(save), L.ptr(dz), _gru_params(grads, n_layers), L.ptr(ws), wsn,
+                                        L.ptr(save), L.ptr(dz), _gru_params(grads, n_layers), L.ptr(ws), wsn[1],
                                         L.stream_ptr(dev)), "gru_bwd")
         return (dz, None, None, None, *([None] * len(grads) if sunk else grads))
 
@@ -266,22 +285,23 @@ class _LstmFn(torch.autograd.Function):
         B, S, H = z.shape
         Har = params[1].shape[1]
         dev = z.device
-        z = z.contiguous().float()
-        h0c = h0.contiguous().float() if h0 is not None else None
-        c0c = c0.contiguous().float() if c0 is not None else None
-        params = tuple(p.detach().contiguous() for p in params)
-        d = L.make_dims(B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
+        z = L.f32c(z)
+        h0c = L.f32c(h0) if h0 is not None else None
+        c0c = L.f32c(c0) if c0 is not None else None
+        params = L.cparams(params)
+        d, save_n, wsns = _plan("lstm", B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
         out = torch.empty(B, S, Har, device=dev, dtype=torch.float32)
         hT = torch.empty(n_layers, B, Har, device=dev, dtype=torch.float32)
         cT = torch.empty(n_layers, B, Har, device=dev, dtype=torch.float32)
-        save = _bytes(lib.cpcb200_lstm_save_bytes(d), dev) if train else None
-        wsn = lib.cpcb200_lstm_ws_bytes(d, 0 if train else 2)
+        save = _bytes(save_n, dev) if train else None
+        wsn = wsns[0 if train else 2]
         ws = _bytes(wsn, dev)
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(lib.cpcb200_lstm_fwd(d, L.ptr(z), L.ptr(h0c), L.ptr(c0c), _gru_params(params, n_layers), L.ptr(out), L.ptr(hT),
                                          L.ptr(cT), L.ptr(save), L.ptr(ws), wsn, L.stream_ptr(dev)), "lstm_fwd")
         if train:
-            ctx.save_for_backward(z, out, save, *params)
+            ctx.save_for_backward(z, out, save)
+        ctx.params = params
         ctx.h0, ctx.c0 = h0c, c0c
         ctx.dims = (B, S, H, Har, n_layers, dtype_code)
         ctx.mark_non_differentiable(hT, cT)
@@ -290,16 +310,17 @@ class _LstmFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dhT, _dcT):
         lib = L.lib()
-        z, out, save, *params = ctx.saved_tensors
+        z, out, save = ctx.saved_tensors
+        params = ctx.params
         B, S, H, Har, n_layers, dtype_code = ctx.dims
         dev = z.device
-        d = L.make_dims(B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
+        d, _, wsns = _plan("lstm", B, S * 160, H, Har, 1, 1, n_layers, dtype_code)
         grads, sunk = _grad_targets(params, dev)
         dz = torch.empty_like(z)
-        wsn = lib.cpcb200_lstm_ws_bytes(d, 1)
+        wsn = wsns[1]
         ws = _bytes(wsn, dev)
-        dout = dout.contiguous().float()
-        with torch.cuda.device(dev):
+        dout = L.f32c(dout)
+        with L.device_guard(dev):
             L.check(lib.cpcb200_lstm_bwd(d, L.ptr(z), L.ptr(ctx.h0), L.ptr(ctx.c0), _gru_params(params, n_layers), L.ptr(out),
                                          L.ptr(dout), L.ptr(save), L.ptr(dz), _gru_params(grads, n_layers), L.ptr(ws), wsn,
                                          L.stream_ptr(dev)), "lstm_bwd")

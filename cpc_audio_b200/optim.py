@@ -333,6 +333,27 @@ class FlatAdam(torch.optim.Optimizer):
         st.copy_(host)
 
 
+_TORCH_ADAM = torch.optim.Adam
+
+
+def Adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, **kw):
+    """``torch.optim.Adam``'s call signature over ``FlatAdam`` (``cpc_audio_b200.patch.install(adam=True)`` puts it in
+    torch.optim's place, so that the unchanged ``torch.optim.Adam(g_params, lr=..., betas=..., eps=...)`` of cpc/train.py:
+    335-337 builds the flat optimizer: ONE kernel per step, zero_grad folded in, gradients written by the backward kernels
+    straight into its bucket - same state_dict format, same param_groups).  Anything FlatAdam does not cover (CPU or
+    non-fp32 parameters, amsgrad, maximize) gets the stock optimizer."""
+    params = list(params)
+    flat_ok = not amsgrad and not kw.get("maximize", False) and not kw.get("differentiable", False)
+    tensors = [p for g in params for p in g["params"]] if params and isinstance(params[0], dict) else params
+    flat_ok = flat_ok and len(tensors) > 0 and all(isinstance(p, torch.Tensor) and p.is_cuda and p.dtype == torch.float32
+                                                   and p.device == tensors[0].device for p in tensors)
+    if params and isinstance(params[0], dict) and len(params) > 1:
+        flat_ok = flat_ok and all(sum(p.numel() for p in g["params"]) % 4 == 0 for g in params)
+    if not flat_ok:
+        return _TORCH_ADAM(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, **kw)
+    return FlatAdam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, capturable=True, fuse_zero_grad=True)
+
+
 class PeerAdam(FlatAdam):
     """FlatAdam whose ``step()`` also performs the data-parallel gradient exchange: the all-reduce(sum) of the bucket over
     the GPUs of the node runs through peer memory (NVLink / NVSwitch loads and stores, node-wide barriers on signal words)

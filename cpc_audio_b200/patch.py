@@ -12,8 +12,18 @@ import runpy
 import sys
 
 
-def install(cpc_package=None):
-    """Replace the hot-path classes inside an importable ``cpc`` package; returns the patched modules."""
+def install(cpc_package=None, adam=None):
+    """Replace the hot-path classes inside an importable ``cpc`` package; returns the patched modules.
+
+    ``adam=True`` (or env ``CPC_B200_PATCH_ADAM=1``) additionally puts ``cpc_audio_b200.optim.Adam`` in place of
+    ``torch.optim.Adam``: train.py:335 then builds the flat fused optimizer (one kernel per step instead of ~10 foreach
+    launches over 36 tensors; no per-parameter AccumulateGrad nodes) - still without touching train.py.  Opt-in because
+    it reaches outside the ``cpc`` package."""
+    import os
+    if adam is None:
+        adam = os.environ.get("CPC_B200_PATCH_ADAM", "0") == "1"
+    if adam:
+        install_adam()
     from . import criterion as our_crit
     from . import model as our_model
     if cpc_package is None:
@@ -33,6 +43,19 @@ def install(cpc_package=None):
     for name in ("TransformerLayer", "buildTransformerAR"):
         setattr(ref_tr, name, getattr(our_tr, name))
     return ref_model, ref_crit
+
+
+def install_adam():
+    """Put cpc_audio_b200.optim.Adam in place of torch.optim.Adam (see install(adam=True))."""
+    import torch
+    from . import optim as our_optim
+    torch.optim.Adam = our_optim.Adam
+
+
+def uninstall_adam():
+    import torch
+    from . import optim as our_optim
+    torch.optim.Adam = our_optim._TORCH_ADAM
 
 
 def main(argv=None):

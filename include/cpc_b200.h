@@ -248,7 +248,7 @@ int cpcb200_allreduce_adam_step(const cpcb200_peers* peers, float* param, float*
                                 int zero_grad, const int64_t* ranges, int n_ranges, void* stream);
 /* Early exchange: in-place all-reduce(sum) of `ranges` of the gradient buckets over peer memory, enqueued on `stream` (a
  * side stream that waits for the event of cpcb200_encoder_bwd_set_event).  Ordinary launch of a few CTAs (CPC_B200_EARLY_CTAS,
- * default 16) that co-reside with the GEMM / conv0 kernels of the backward tail.  Every rank must call it once per step,
+ * default 32; 256 threads x <= 64 registers each) that co-reside with the GEMM / conv0 kernels of the backward tail.  Every rank must call it once per step,
  * before that step's cpcb200_allreduce_adam_step, which must then be given the complementary ranges. */
 int cpcb200_peer_reduce_range(const cpcb200_peers* peers, const int64_t* ranges, int n_ranges, int32_t* state, void* stream);
 
