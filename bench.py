@@ -313,7 +313,7 @@ def _trainstep_like(loader, model, crit, opt):
     return logs
 
 
-def _drive_trainstep(a, dev, x_host, label, b200, steps, warm, patch_adam=False, feeder=False):
+def _drive_trainstep(a, dev, x_host, label, b200, steps, warm, patch_adam=False, feeder=False, patch_dp=False):
     """Build model / criterion / torch.optim.Adam as cpc/train.py:307-337 + 372-375 does and run `steps` steps of trainStep.
     patch_adam: cpc_audio_b200.patch.install(adam=True) - train.py's torch.optim.Adam(...) call then builds the flat fused
     optimizer.  feeder: the dataLoader is a cpc_audio_b200.feeder.WindowFeeder over an HBM-resident pack (the .cuda() calls
@@ -336,6 +336,8 @@ def _drive_trainstep(a, dev, x_host, label, b200, steps, warm, patch_adam=False,
     Bsz = x_host.shape[0]
     if patch_adam:
         patch.install_adam()
+    if patch_dp:
+        patch.install_dataparallel()
     try:
         if R is not None:
             args = R.default_args(arMode="GRU", rnnMode=a.heads)
@@ -359,6 +361,8 @@ def _drive_trainstep(a, dev, x_host, label, b200, steps, warm, patch_adam=False,
     finally:
         if patch_adam:
             patch.uninstall_adam()
+        if patch_dp:
+            patch.uninstall_dataparallel()
 
     if feeder:
         import itertools
@@ -392,7 +396,8 @@ def train_py_leg(a, dev, x_host, label):
     steps = max(20, a.steps)
     sec = x_host.shape[0] * WINDOW / SR
     out = None
-    for name, kw in (("stock", {}), ("flat_adam", {"patch_adam": True}), ("flat_adam_feeder", {"patch_adam": True, "feeder": True})):
+    for name, kw in (("stock", {}), ("flat_adam", {"patch_adam": True}), ("fast", {"patch_adam": True, "patch_dp": True}),
+                     ("fast_feeder", {"patch_adam": True, "patch_dp": True, "feeder": True})):
         n0 = L.lib().cpcb200_launch_count()
         per_step, how, loss, opt_name = _drive_trainstep(a, dev, x_host, label, True, steps, 5, **kw)
         launches = (L.lib().cpcb200_launch_count() - n0) / (steps + 5)
@@ -408,8 +413,10 @@ def train_py_leg(a, dev, x_host, label):
         else:
             ent["what"] = {"flat_adam": "cpc_audio_b200.patch.install(adam=True): train.py's torch.optim.Adam(...) call builds the flat fused "
                                         "optimizer (one kernel per step); host batches as above",
-                           "flat_adam_feeder": "the same + the dataLoader is a WindowFeeder over an HBM-resident pack (SURVEY 8f N2): no "
-                                               "per-step host->device copy, batches cut by cpcb200_gather_windows"}[name]
+                           "fast": "python -m cpc_audio_b200.patch --fast train.py: flat_adam + torch.nn.DataParallel(device_ids=[0]) "
+                                   "becomes a true pass-through (no scatter / gather for one device); host batches as above",
+                           "fast_feeder": "the same + the dataLoader is a WindowFeeder over an HBM-resident pack (SURVEY 8f N2): no "
+                                          "per-step host->device copy, batches cut by cpcb200_gather_windows"}[name]
             out["variants"][name] = ent
     return out
 
@@ -460,10 +467,17 @@ def run_ours(a):
     fused_ar = False  # all-reduce + Adam + zero_grad as ONE kernel over peer memory (PeerAdam) instead of NCCL + Adam
     if a.optimizer == "fused":
         opt = None
-        if world > 1 and os.environ.get("CPC_B200_FUSED_AR", "1") != "0":
+        force_peer = world == 1 and os.environ.get("CPC_B200_FORCE_PEER", "0") == "1"  # debug: PeerAdam on one GPU (gloo group)
+        if force_peer:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        if (world > 1 or force_peer) and os.environ.get("CPC_B200_FUSED_AR", "1") != "0":
             try:
                 enc = model.gEncoder
-                overlap = os.environ.get("CPC_B200_PEER_OVERLAP", "1") != "0"
+                # early-range overlap is OFF by default: measured on B200 (profiles/r2_multi_gpu.md) the side-stream kernel slows
+                # the dgrad GEMM / conv0 backward it runs beside by more than the exchange it hides
+                overlap = os.environ.get("CPC_B200_PEER_OVERLAP", "0") != "0"
                 opt = PeerAdam(params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, fuse_zero_grad=True, overlap=overlap,
                                late_params=[enc.conv0.weight, enc.conv0.bias, enc.batchNorm0.weight, enc.batchNorm0.bias])
                 fused_ar = True
@@ -682,6 +696,16 @@ def run_ours(a):
         roof["kernels"] = kernels
         roof["kernel_ms_per_step_total"] = round(sum(per_step.values()), 4)
 
+    if world > 1 and fused_ar and os.environ.get("CPC_B200_PEER_STAMPS", "0") == "1":
+        for _ in range(3):
+            step(x_dev)
+        torch.cuda.synchronize(dev)
+        sg = opt._sig.cpu()
+        rel = sg[40:45].tolist()
+        ab = sg[48:56].view(torch.int64).tolist()
+        print(f"[stamps rank {rank}] early kernel: start 0, peers arrived +{(ab[1] - ab[0]) / 1e3:.1f} us, done +{(ab[2] - ab[0]) / 1e3:.1f} us; "
+              f"step kernel starts +{(ab[3] - ab[0]) / 1e3:.1f} us after the early kernel started; inside the step kernel (ns): "
+              f"barrier1 {rel[0]}, reduced {rel[1]}, grid sync {rel[2]}, barrier2 {rel[3]}, adam done {rel[4]}", file=sys.stderr, flush=True)
     if world > 1:
         dist.barrier()
     if rank == 0:

@@ -265,7 +265,7 @@ struct PeerPtrs { float* g[8]; unsigned* sig[8]; int rank, world; float* mc; lon
 struct RangeList { long long lo[4], hi[4]; int n; };  // [lo, hi) in floats; lo a multiple of 4
 // signal words of a rank (>= 64 x uint32): [0..7] arrivals at the step kernel's barriers (word j is written by rank j),
 // [16..23] arrivals at the early-reduce kernel's barrier, [40..44] phase stamps of the last step kernel (debug)
-constexpr int kSigStep = 0, kSigEarly = 16, kSigDbg = 40;
+constexpr int kSigStep = 0, kSigEarly = 16, kSigDbg = 40, kSigAbs = 48;  // [48..55]: absolute globaltimer stamps (4 x u64)
 
 // NVSwitch in-fabric reduction: the sum over every GPU's copy of the 16 bytes at this multicast address / broadcast store
 __device__ __forceinline__ float4 multimem_ld_reduce_v4(const float* p) {
@@ -391,8 +391,12 @@ __global__ void __launch_bounds__(256, 4) peer_reduce_kernel(PeerPtrs P, RangeLi
   if (*reinterpret_cast<volatile int*>(state + kStErr) != 0) return;  // set by an earlier kernel only: grid-uniform
   const unsigned ep = (unsigned)*reinterpret_cast<volatile int*>(state + kStEarlyEpoch);
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  unsigned long long* abs_t = reinterpret_cast<unsigned long long*>(P.sig[P.rank] + kSigAbs);  // debug: absolute times
+  const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) abs_t[0] = globaltimer_ns();
   node_arrive(P, kSigEarly, ep + 1);
   const bool ok = node_wait(P, kSigEarly, ep + 1);
+  if (stamp) abs_t[1] = globaltimer_ns();
   if (ok) {
     for (int r = 0; r < R.n; r++) reduce_my_slice<4>(P, R.lo[r], R.hi[r], tid, nthr);
   } else if (threadIdx.x == 0) {
@@ -403,6 +407,7 @@ __global__ void __launch_bounds__(256, 4) peer_reduce_kernel(PeerPtrs P, RangeLi
   if (threadIdx.x == 0) {
     const int t = atomicAdd(state + kStEarlyTicket, 1);
     if (t == (int)gridDim.x - 1) {  // last block out: every block has read the epoch
+      abs_t[2] = globaltimer_ns();
       state[kStEarlyTicket] = 0;
       __threadfence();
       atomicAdd(state + kStEarlyEpoch, 1);
@@ -439,6 +444,7 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(PeerPtrs P, RangeLi
   const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
   const unsigned long long t_start = stamp ? globaltimer_ns() : 0ull;
   unsigned* dbg = P.sig[P.rank] + kSigDbg;
+  if (stamp) reinterpret_cast<unsigned long long*>(P.sig[P.rank] + kSigAbs)[3] = t_start;
   // ---- every rank's gradients are final (and every rank's early exchange, if any, has completed) ----
   node_arrive(P, kSigStep, 2 * calls + 1);
   const bool ok1 = node_wait(P, kSigStep, 2 * calls + 1);

@@ -13,13 +13,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import ref_driver as R  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+FLAT = "--flat-adam" in sys.argv
 dev = torch.device("cuda", 0)
 args = R.default_args(arMode="GRU", rnnMode="linear")
 ref = R.reference_or_none()
 
 
 def run(b, steps=30, prof=False):
+    import cpc_audio_b200.patch as patch
+    if FLAT:
+        patch.install_adam()
     model, crit, mdp, cdp, opt = R.build(args, b200=True, seed=0, device=dev)
+    patch.uninstall_adam()
     R.use_b200_modules(False)
     x = (torch.randn(b, 1, 20480) * 0.1).pin_memory()
     lab = torch.zeros(b, dtype=torch.long)
@@ -38,6 +43,6 @@ def run(b, steps=30, prof=False):
     return (time.perf_counter() - t0) / steps * 1e3
 
 
-print(f"B={B}: {run(B):.3f} ms/step   B=1 (host-bound): {run(1):.3f} ms/step")
+print(f"flat_adam={FLAT}  B={B}: {run(B):.3f} ms/step   B=1 (host-bound): {run(1):.3f} ms/step")
 p = run(B, prof=True)
-print(p.key_averages().table(sort_by="self_cpu_time_total", row_limit=40, max_name_column_width=60))
+print(p.key_averages().table(sort_by="self_cpu_time_total", row_limit=60, max_name_column_width=60))
