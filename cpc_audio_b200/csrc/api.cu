@@ -62,6 +62,10 @@ cudaEvent_t take_grads_ready_event(cudaStream_t st) {
   return ev;
 }
 
+static thread_local int g_sm_reserve = 0;
+int sm_reserve() { return g_sm_reserve; }
+void set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : (n > 64 ? 64 : n); }
+
 bool pdl_enabled() {
   static const bool on = []() { const char* e = getenv("CPC_B200_PDL"); return !(e && atoi(e) == 0); }();
   return on;
@@ -384,10 +388,12 @@ __device__ __forceinline__ void reduce_my_slice(const PeerPtrs& P, long long lo_
 // no CTA ever waits for another CTA of the same grid, only for the peers' arrival words.  Completion needs no signal of
 // its own: a rank enters the step kernel's first barrier only after its own early kernel has finished (stream order), so
 // once every rank has arrived there every slice of every early range has been written everywhere.
-// Footprint: 256 threads x <= 64 registers, no shared memory - a CTA fits next to a persistent GEMM CTA (192 threads x 168
-// registers, ~200 KB of shared memory) on the same SM; measured with 512 threads x 128 registers (a whole register file)
-// the kernel could not start before the backward pass had drained and the 'overlap' cost 28 us instead of saving 20.
-__global__ void __launch_bounds__(256, 4) peer_reduce_kernel(PeerPtrs P, RangeList R, int* __restrict__ state) {
+// Placement: a few CTAs of 1024 threads (a whole register file each), launched as ONE cluster so that they take
+// neighbouring SMs of one GPC, while the data-gradient GEMM that runs at the same time is launched on 148 - kEarlyExchangeSMs
+// SMs (sm_reserve).  Measured on B200: a CTA of this kernel and a persistent GEMM CTA never share an SM (the GEMM CTA waits
+// until the other one exits, whatever its size: 1 / 4 / 32 / 148 small CTAs cost +600 / +100 / +34 / +27 us per step) and the
+// GEMM's static tile schedule then waits for the slowest SM - so the exchange gets SMs of its own instead.
+__global__ void __launch_bounds__(1024, 1) peer_reduce_kernel(PeerPtrs P, RangeList R, int* __restrict__ state) {
   if (*reinterpret_cast<volatile int*>(state + kStErr) != 0) return;  // set by an earlier kernel only: grid-uniform
   const unsigned ep = (unsigned)*reinterpret_cast<volatile int*>(state + kStEarlyEpoch);
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
@@ -398,7 +404,8 @@ __global__ void __launch_bounds__(256, 4) peer_reduce_kernel(PeerPtrs P, RangeLi
   const bool ok = node_wait(P, kSigEarly, ep + 1);
   if (stamp) abs_t[1] = globaltimer_ns();
   if (ok) {
-    for (int r = 0; r < R.n; r++) reduce_my_slice<4>(P, R.lo[r], R.hi[r], tid, nthr);
+    if (P.mc != nullptr) { for (int r = 0; r < R.n; r++) reduce_my_slice<8>(P, R.lo[r], R.hi[r], tid, nthr); }
+    else { for (int r = 0; r < R.n; r++) reduce_my_slice<4>(P, R.lo[r], R.hi[r], tid, nthr); }
   } else if (threadIdx.x == 0) {
     atomicExch(state + kStErr, 3);
   }
@@ -833,9 +840,24 @@ int cpcb200_peer_reduce_range(const cpcb200_peers* peers, const int64_t* ranges,
   RangeList R{};
   CPC_TRY(fill_ranges(ranges, n_ranges, 0, &R));
   if (n_ranges == 0) return 0;
-  static const int ctas = []() { const char* e = getenv("CPC_B200_EARLY_CTAS"); int v = e ? atoi(e) : 32; return v < 1 ? 1 : (v > 148 ? 148 : v); }();
+  static const bool noop = []() { const char* e = getenv("CPC_B200_EARLY_NOOP"); return e && atoi(e) == 1; }();  // debug: fork / join only
+  if (noop) return 0;
+  static const int ctas = []() { const char* e = getenv("CPC_B200_EARLY_CTAS"); int v = e ? atoi(e) : kEarlyExchangeSMs; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  peer_reduce_kernel<<<ctas, 256, 0, st>>>(P, R, reinterpret_cast<int*>(state));
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;  // one cluster: the CTAs land on SMs of one GPC
+    at[0].val.clusterDim.x = (unsigned)ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int* state_i = reinterpret_cast<int*>(state);
+    CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, peer_reduce_kernel, P, R, state_i));
+  }
   CPC_LAUNCHED_N("peer_reduce", st);
   return 0;
 }

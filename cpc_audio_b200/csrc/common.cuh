@@ -92,6 +92,13 @@ bool pdl_enabled();
 // parameter gradient except conv0's / batchNorm0's is final; returns nullptr when none is armed for that stream
 cudaEvent_t take_grads_ready_event(cudaStream_t st);
 
+// SMs the persistent GEMMs launched by this thread must leave free (0 by default).  The encoder backward sets it around the
+// last data-gradient GEMM when an early gradient exchange has been armed: that exchange (cpcb200_peer_reduce_range) runs
+// beside the GEMM on its own SMs - a GEMM CTA (221 KB of shared memory) never shares an SM with it.
+int sm_reserve();
+void set_sm_reserve(int n);
+constexpr int kEarlyExchangeSMs = 4;  // 144 SMs = 72 clusters of 2 take the 1152 tile pairs of dgrad_1 in exactly 16 rounds
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -666,6 +666,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
     CPC_LAUNCHED_N("prep_w_dgrad_all", st);
   }
   TnDesc wg[4];
+  bool early_exchange = false;
   for (int i = 4; i >= 1; i--) {
     const int Lo = g.Lout[i], Lin = g.Lout[i - 1], s = kConvS[i], pp = kConvP[i];
     // ChannelNorm+ReLU backward -> du_i, dgamma_i, dbeta_i, dbias_i
@@ -703,7 +704,10 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
         CPC_CHECK_CUDA(launch_k(permute_add_wgrad_all_kernel, dim3(H, 4), dim3(256), (size_t)8 * (H + 1) * sizeof(float), st, 1, P, H));
         CPC_LAUNCHED_N("permute_add_wgrad_all", st);
       }
-      if (cudaEvent_t ev = take_grads_ready_event(st)) CPC_CHECK_CUDA(cudaEventRecord(ev, st));
+      if (cudaEvent_t ev = take_grads_ready_event(st)) {
+        CPC_CHECK_CUDA(cudaEventRecord(ev, st));
+        early_exchange = true;  // the caller runs the gradient exchange beside dgrad_1: leave it its SMs
+      }
     }
     // data gradient: input row j = s q + r - p gets [du[q-1], du[q]] . Wd[r].  All s residues in ONE GEMM with
     // N = s*H: row q of the product is the s consecutive input rows s q - p .. s q - p + s - 1.
@@ -713,7 +717,10 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
       // window lengths that are not multiples of 160 leave up to s-1 trailing input rows that no output frame reads
       // (zero gradient) and that the merged product does not cover: clear the buffer first (ragged shapes only)
       if (Lin > s * Lo + s - pp) CPC_CHECK_CUDA(cudaMemsetAsync(dy[i - 1], 0, (size_t)B * Lin * H * sizeof(T), st));
-      CPC_TRY(gemm_nt(g.bf16, false, B, s * H, 2 * H, A, wd[i], nullptr, C, st));
+      if (i == 1 && early_exchange) set_sm_reserve(kEarlyExchangeSMs);
+      const int rc = gemm_nt(g.bf16, false, B, s * H, 2 * H, A, wd[i], nullptr, C, st);
+      set_sm_reserve(0);
+      CPC_TRY(rc);
     }
   }
   bool c0_done = false;

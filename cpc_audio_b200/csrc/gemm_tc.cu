@@ -611,7 +611,7 @@ int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt,
   const size_t smem = nt2_smem();
   CPC_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int total_groups = ((m_tiles + CM - 1) / CM) * n_tiles;
-  int clusters = 148 / CM;
+  int clusters = (148 - sm_reserve()) / CM;  // sm_reserve() > 0: another kernel runs beside this one on SMs of its own
   if (clusters > total_groups) clusters = total_groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CM);

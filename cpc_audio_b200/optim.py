@@ -375,8 +375,11 @@ class PeerAdam(FlatAdam):
         self._symm, self._dist = symm, dist
         self._group = group if group is not None else dist.group.WORLD
         kw["capturable"] = True
-        try:  # older torch releases want the group registered first; newer ones do it on rendezvous
-            symm.enable_symm_mem_for_group(self._group.group_name)
+        try:  # older torch releases want the group registered first; newer ones do it on rendezvous (and warn)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", FutureWarning)
+                symm.enable_symm_mem_for_group(self._group.group_name)
         except (AttributeError, RuntimeError, TypeError):
             pass
         super().__init__(params, **kw)
