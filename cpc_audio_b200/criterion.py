@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .model import _bytes, _dtype_code, _plan, _require_cuda, default_dtype
+from .model import _bytes, _dtype_code, _plan, _require_cuda, default_dtype  # noqa: I001
 
 
 class BaseCriterion(nn.Module):
@@ -399,8 +399,25 @@ class CPCUnsupersivedCriterion(BaseCriterion):
             raise ValueError(f"sequence of {seqSize} frames is too short for nPredicts={self.nPredicts}")
         H = encodedData.size(2)
         dims = (batchSize, seqSize, H, dimAR, self.nPredicts, self.negativeSamplingExt, _dtype_code(self.compute_dtype))
-        batchIdx, seqIdx = self.sampleIndices(batchSize, windowSize, seqSize, encodedData.device)
-        ext = self.extIndices(batchIdx, seqIdx, dims)
+        dev = encodedData.device
+        ready = getattr(encodedData, "_cpcb200_ready", None)
+        if ready is not None:
+            # criterion.py:181-199 only needs the SHAPE of z: drawn on the side stream, beside the recurrence that is still
+            # producing cFeature on this stream (the generator is consumed in host order: same draws either way)
+            from .model import side_stream
+            main, side = torch.cuda.current_stream(dev), side_stream(dev)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                batchIdx, seqIdx = self.sampleIndices(batchSize, windowSize, seqSize, dev)
+                ext = self.extIndices(batchIdx, seqIdx, dims)
+                done = torch.cuda.Event()
+                done.record(side)
+            main.wait_event(done)
+            for t in (batchIdx, seqIdx, ext):
+                t.record_stream(main)
+        else:
+            batchIdx, seqIdx = self.sampleIndices(batchSize, windowSize, seqSize, dev)
+            ext = self.extIndices(batchIdx, seqIdx, dims)
         if self.wPrediction.transformer:
             if windowSize != self.wPrediction.sizeInputSeq:
                 raise ValueError(f"transformer heads were built for {self.wPrediction.sizeInputSeq} positions, got {windowSize}")

@@ -434,21 +434,25 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int kFT = 64;    // frames per tile
 constexpr int kXS = 336;   // floats reserved for the 5*64+5 samples of a tile
+constexpr int kCW = 64;    // channels per warp.  Measured on B200 (r2k): 32 channels per warp (8 warps per CTA, 128 registers, 16 warps
+                           // per SM instead of 8) is SLOWER - 0.152 vs 0.130 ms - because the per-row work (sample fragments,
+                           // statistics, s1 / s2 exchanges) is replicated in every warp; 64 stays.
+constexpr int kNJ = kCW / 8, kNM = kCW / 16;
 
 template <int H>
 constexpr size_t bwd2_smem() {
-  return (size_t)2 * H * 4 + (size_t)(H / 8) * 32 * 8 + (size_t)2 * (H / 64) * kFT * 8 + 2 * kXS * 4 + (size_t)2 * kFT * (2 * H + 16);
+  return (size_t)2 * H * 4 + (size_t)(H / 8) * 32 * 8 + (size_t)2 * (H / kCW) * kFT * 8 + 2 * kXS * 4 + (size_t)2 * kFT * (2 * H + 16);
 }
 
 template <int H>
-__global__ void __launch_bounds__(H / 2, (H <= 256 ? 2 : 1))
+__global__ void __launch_bounds__((H / kCW) * 32, (H <= 256 ? 2 : 1))
 conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       const float* __restrict__ gam, const float* __restrict__ bet, bf16* __restrict__ dy,
                       float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ dgam, float* __restrict__ dbet,
                       int B, int L, int L0) {
   pdl_wait();
   pdl_trigger();
-  constexpr int NW = H / 64, NTHR = NW * 32, RS = 2 * H + 16, TILE = kFT * RS, SEGS = H / 8;
+  constexpr int NW = H / kCW, NTHR = NW * 32, RS = 2 * H + 16, TILE = kFT * RS, SEGS = H / 8;
   extern __shared__ __align__(16) unsigned char sm[];
   float* gb = reinterpret_cast<float*>(sm);                                    // gamma[H], beta[H]
   uint2* wsm = reinterpret_cast<uint2*>(sm + 2 * H * 4);                       // weight fragments [H/8][32]
@@ -479,11 +483,11 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     cp_async_commit();
   };
 
-  float cdg[8][2], cdb[8][2], wacc[4][2][4];
+  float cdg[kNJ][2], cdb[kNJ][2], wacc[kNM][2][4];
 #pragma unroll
-  for (int j = 0; j < 8; j++) cdg[j][0] = cdg[j][1] = cdb[j][0] = cdb[j][1] = 0.f;
+  for (int j = 0; j < kNJ; j++) cdg[j][0] = cdg[j][1] = cdb[j][0] = cdb[j][1] = 0.f;
 #pragma unroll
-  for (int m = 0; m < 4; m++)
+  for (int m = 0; m < kNM; m++)
 #pragma unroll
     for (int n = 0; n < 2; n++)
 #pragma unroll
@@ -500,8 +504,8 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     const float* xt = xs + buf * kXS;
     const int b = tile / tpw, f0 = (tile - b * tpw) * kFT;
 
-    // ---- u = X . W0^T for the warp's 64 channels -------------------------------------------------------
-    float acc[4][8][4];
+    // ---- u = X . W0^T for the warp's kCW channels -------------------------------------------------------
+    float acc[4][kNJ][4];
     {
       uint32_t ah[4][4], al[4][4];
 #pragma unroll
@@ -522,8 +526,8 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         al[m][2] = pack_bf16(v[0][2] - h[0][2], v[0][3] - h[0][3]); al[m][3] = pack_bf16(v[1][2] - h[1][2], v[1][3] - h[1][3]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const uint2 wv = wsm[(8 * wp + j) * 32 + lane];
+      for (int j = 0; j < kNJ; j++) {
+        const uint2 wv = wsm[(kNJ * wp + j) * 32 + lane];
 #pragma unroll
         for (int m = 0; m < 4; m++) {
           acc[m][j][0] = acc[m][j][1] = acc[m][j][2] = acc[m][j][3] = 0.f;
@@ -540,7 +544,7 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
       for (int hf = 0; hf < 2; hf++) {
         float s = 0.f, q = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < kNJ; j++) {
           const float a0 = acc[m][j][2 * hf], a1 = acc[m][j][2 * hf + 1];
           s += a0 + a1; q = fmaf(a0, a0, q); q = fmaf(a1, a1, q);
         }
@@ -566,8 +570,8 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 #pragma unroll
     for (int m = 0; m < 4; m++) s1[m][0] = s1[m][1] = s2[m][0] = s2[m][1] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int c = 64 * wp + 8 * j + 2 * t;
+    for (int j = 0; j < kNJ; j++) {
+      const int c = kCW * wp + 8 * j + 2 * t;
       const float2 g2 = *reinterpret_cast<const float2*>(gb + c), b2 = *reinterpret_cast<const float2*>(gb + H + c);
 #pragma unroll
       for (int m = 0; m < 4; m++)
@@ -610,8 +614,8 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
       }
     // ---- pass 2: du = rstd * (dx - s1 - xhat * s2), in place over dy (this warp's columns only) -----------
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int c = 64 * wp + 8 * j + 2 * t;
+    for (int j = 0; j < kNJ; j++) {
+      const int c = kCW * wp + 8 * j + 2 * t;
       const float2 g2 = *reinterpret_cast<const float2*>(gb + c), b2 = *reinterpret_cast<const float2*>(gb + H + c);
       __nv_bfloat162 d2[4][2];
 #pragma unroll
@@ -651,10 +655,10 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         bx[n][1] = pack_bf16(v[2], v[3]);
       }
 #pragma unroll
-      for (int m = 0; m < 4; m++) {
+      for (int m = 0; m < kNM; m++) {
         const int mi = lane >> 3;
         uint32_t a[4];
-        ldsm_x4_t(a, s_u32(tl + (16 * ks + (mi >> 1) * 8 + (lane & 7)) * RS + (64 * wp + 16 * m + (mi & 1) * 8) * 2));
+        ldsm_x4_t(a, s_u32(tl + (16 * ks + (mi >> 1) * 8 + (lane & 7)) * RS + (kCW * wp + 16 * m + (mi & 1) * 8) * 2));
         mma16816(wacc[m][0], a, bx[0][0], bx[0][1]);
         mma16816(wacc[m][1], a, bx[1][0], bx[1][1]);
       }
@@ -666,21 +670,21 @@ conv0_bwd2_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   cp_async_wait_all();
   // ---- flush the register accumulators -------------------------------------------------------------------
 #pragma unroll
-  for (int j = 0; j < 8; j++)
+  for (int j = 0; j < kNJ; j++)
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       float a = cdg[j][q], c2 = cdb[j][q];
       a += __shfl_xor_sync(0xffffffffu, a, 4); a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
       c2 += __shfl_xor_sync(0xffffffffu, c2, 4); c2 += __shfl_xor_sync(0xffffffffu, c2, 8); c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
-      if (g == 0) { const int c = 64 * wp + 8 * j + 2 * t + q; atomicAdd(dgam + c, a); atomicAdd(dbet + c, c2); }
+      if (g == 0) { const int c = kCW * wp + 8 * j + 2 * t + q; atomicAdd(dgam + c, a); atomicAdd(dbet + c, c2); }
     }
 #pragma unroll
-  for (int m = 0; m < 4; m++)
+  for (int m = 0; m < kNM; m++)
 #pragma unroll
     for (int n = 0; n < 2; n++)
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        const int c = 64 * wp + 16 * m + g + 8 * (e >> 1), tap = 8 * n + 2 * t + (e & 1);
+        const int c = kCW * wp + 16 * m + g + 8 * (e >> 1), tap = 8 * n + 2 * t + (e & 1);
         if (tap < 10) atomicAdd(dw + c * 10 + tap, wacc[m][n][e]);
         else if (tap == 10) atomicAdd(dbias + c, wacc[m][n][e]);
       }
@@ -708,7 +712,7 @@ int launch_all_bwd(const float* x, const float* w, const float* bias, const floa
     int blocks2 = B * (L0 / kFT);
     if (blocks2 > 148 * 2) blocks2 = 148 * 2;
     CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd2_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CPC_CHECK_CUDA(launch_k(conv0_bwd2_mma_kernel<H>, dim3(blocks2), dim3(H / 2), smem, st, 1, x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0));
+    CPC_CHECK_CUDA(launch_k(conv0_bwd2_mma_kernel<H>, dim3(blocks2), dim3((H / kCW) * 32), smem, st, 1, x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0));
     CPC_LAUNCHED_N("conv0_bwd2_mma", st);
     return 0;
   }

@@ -42,8 +42,16 @@ __global__ void ext_idx_kernel(const long long* __restrict__ bi, const long long
   const unsigned nn = (unsigned)n;  // n < 2^31 (checked on the host): 32-bit index arithmetic
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) {
     const unsigned w = i % (unsigned)W;
-    long long s = (si[i] + (long long)w) % S;  // torch.remainder of non-negative operands
-    if (s < 0) s += S;
+    const long long sraw = si[i];
+    long long s;
+    if (sraw >= 0 && sraw < S) {  // what torch.randint(1, S) draws: one conditional subtraction instead of a 64-bit division
+      int sv = (int)sraw + (int)w;
+      if (sv >= S) sv -= S;
+      s = sv;
+    } else {                      // any other int64 input: torch.remainder semantics
+      s = (sraw + (long long)w) % S;
+      if (s < 0) s += S;
+    }
     ext[i] = (int)(s + bi[i] * S);
   }
 }

@@ -85,6 +85,27 @@ def frames_for(n_samples: int) -> int:
     return n
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(device):
+    """One library-owned side stream per device: work that does not depend on the recurrence of the context network (the
+    negative-sample draws and their index arithmetic) runs on it WHILE the recurrence - 128 dependent steps on 32 of the
+    148 SMs - runs on the caller's stream.  Fork and join are events, so the caller's stream order is preserved and the
+    pattern is captured as parallel branches by a CUDA graph."""
+    key = (device.type, device.index)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
+def overlap_enabled():
+    # opt-in: measured on B200 (r2k) the fork saves 7 us of a 1.46 ms step (the draws and the index arithmetic are short
+    # and already hidden by programmatic dependent launch)
+    return os.environ.get("CPC_B200_OVERLAP", "0") == "1"
+
+
 class ChannelNorm(nn.Module):
     """Parameter holder for cpc/model.py:25-58 (weight/bias of shape (1, C, 1)); the math is fused in the kernels."""
 
@@ -389,5 +410,10 @@ class CPCModel(nn.Module):
             encodedData = self.gEncoder.forward_channel_last(batchData)
         else:
             encodedData = self.gEncoder(batchData).permute(0, 2, 1)
+        if encodedData.is_cuda and overlap_enabled():
+            # 'z is ready': the criterion forks its generator draws / index arithmetic from here, beside the recurrence
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(encodedData.device))
+            encodedData._cpcb200_ready = ev
         cFeature = self.gAR(encodedData)
         return cFeature, encodedData, label
