@@ -62,6 +62,8 @@ cudaEvent_t take_grads_ready_event(cudaStream_t st) {
   return ev;
 }
 
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
+
 static thread_local int g_sm_reserve = 0;
 int sm_reserve() { return g_sm_reserve; }
 void set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : (n > 64 ? 64 : n); }

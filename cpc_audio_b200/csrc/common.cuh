@@ -25,6 +25,7 @@ int fail(int code, const char* fmt, ...);
                              cudaGetErrorString(_e));                                                \
   } while (0)
 
+bool prof_enabled();
 void prof_mark(cudaStream_t st);
 void prof_note(const char* name, cudaStream_t st);
 

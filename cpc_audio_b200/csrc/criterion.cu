@@ -13,7 +13,7 @@ int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A,
 int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode,
             int Ci, int taps, cudaStream_t st);
 template <class T> int launch_cast(const float* src, T* dst, long long n, cudaStream_t st);
-template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st);
+template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st, int nb = 1);
 
 bool score_mma_supported(int H, int K, int N);
 int score_transpose_ext(const int* ext, int* ext_t, int B, int N, int W, cudaStream_t st);

@@ -248,12 +248,14 @@ __global__ void cast3_bf16_kernel(const float* __restrict__ s0, bf16* __restrict
     *reinterpret_cast<uint2*>(d + j) = o;
   }
 }
-// dst[c][r] = src[r][c]
+// dst[c][r] = src[r][c]   (blockIdx.z = matrix index of a batch of equally shaped, densely stacked matrices)
 template <class T>
 __global__ void transpose_cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int R, int C) {
   pdl_wait();
   pdl_trigger();
   __shared__ float tile[32][33];
+  src += (size_t)blockIdx.z * R * C;
+  dst += (size_t)blockIdx.z * R * C;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int rr = r0 + i, cc = c0 + threadIdx.x;
@@ -299,14 +301,14 @@ template <class T> int launch_cast(const float* src, T* dst, long long n, cudaSt
 template int launch_cast<bf16>(const float*, bf16*, long long, cudaStream_t);
 template int launch_cast<float>(const float*, float*, long long, cudaStream_t);
 
-template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st) {
-  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st, int nb) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32, nb), block(32, 8);
   CPC_CHECK_CUDA(launch_k(transpose_cast_kernel<T>, grid, block, 0, st, 1, src, dst, R, C));
   CPC_LAUNCHED_N("transpose_cast", st);
   return 0;
 }
-template int launch_transpose_cast<bf16>(const float*, bf16*, int, int, cudaStream_t);
-template int launch_transpose_cast<float>(const float*, float*, int, int, cudaStream_t);
+template int launch_transpose_cast<bf16>(const float*, bf16*, int, int, cudaStream_t, int);
+template int launch_transpose_cast<float>(const float*, float*, int, int, cudaStream_t, int);
 
 template <class T> int launch_colsum(const T* src, float* out, long long M, int N, cudaStream_t st) {
   const int rpb = 256;
@@ -530,7 +532,7 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
       CPC_TRY(gemm_tn(g.bf16, B, G, Har, A, Bv2, gr->w_hh[l], Har, STORE_PLAIN, 0, 0, st));
     }
     {  // d(input) = dgi . W_ih   (as NT against the transposed weights)
-      CPC_TRY(launch_transpose_cast<T>(p->w_ih[l], wihT, G, Hin, st));
+      CPC_TRY(launch_transpose_cast<T>(p->w_ih[l], wihT, G, Hin, st, 1));
       float* dst = l == 0 ? dz : (dcl == dmid ? dmid2 : dmid);
       RowView A{dgi, 0, (long long)G, B * S};
       OutView C{dst, 0, (long long)Hin, B * S, 0, B * S, 0};
@@ -896,7 +898,7 @@ int lstm_bwd_t(const Geo& g, const float* z, const float* h0, const float* c0, c
       CPC_TRY(gemm_tn(g.bf16, B, G, Har, A, Bv2, gr->w_hh[l], Har, STORE_PLAIN, 0, 0, st));
     }
     {  // d(input) = dg . W_ih   (as NT against the transposed weights)
-      CPC_TRY(launch_transpose_cast<T>(p->w_ih[l], wihT, G, Hin, st));
+      CPC_TRY(launch_transpose_cast<T>(p->w_ih[l], wihT, G, Hin, st, 1));
       float* dst = l == 0 ? dz : (dl == dmid ? dmid2 : dmid);
       RowView A{dg, 0, (long long)G, B * S};
       OutView C{dst, 0, (long long)Hin, B * S, 0, B * S, 0};

@@ -18,7 +18,7 @@ int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A,
 int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode,
             int Ci, int taps, cudaStream_t st);
 template <class T> int launch_cast(const float* src, T* dst, long long n, cudaStream_t st);
-template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st);
+template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st, int nb = 1);
 template <class T> int launch_colsum(const T* src, float* out, long long M, int N, cudaStream_t st);
 
 namespace {
@@ -31,54 +31,87 @@ constexpr float kLnEps = 1e-5f;
 // ---------------------------------------------------------------------------------------------------------
 // keep != NULL (train mode, transformers.py:18,49): probability (i, c) of (window b, head h) is multiplied by
 // keep[((b*nh + h)*W + i)*W + c] * dscale before it meets V - the mask torch's nn.Dropout drew for that element.
+//
+// Thread i owns query row i.  Every inner loop walks an index that is THE SAME for all lanes of a warp (a key c, or a
+// relative-position column m), so the K / V / Krelpos rows it needs are warp-wide broadcasts read as float4 - the skew of
+// transformers.py:42-47 (key c <= query i reads column m = W-1-(i-c) of Q.Krelpos) is applied by first storing the row
+// QP[i][m] = q_i . Krelpos[:, m] to shared memory and then adding QP[i][W-1-i+c] in the key loop.
+template <int DK>
+__device__ __forceinline__ float dot_bcast(const float (&q)[DK], const float* __restrict__ row) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains: the loop is FMA-latency-bound at 4 warps per SM
+#pragma unroll
+  for (int d4 = 0; d4 < DK / 4; d4++) {
+    const float4 v = reinterpret_cast<const float4*>(row)[d4];
+    s0 = fmaf(q[4 * d4], v.x, s0); s1 = fmaf(q[4 * d4 + 1], v.y, s1); s2 = fmaf(q[4 * d4 + 2], v.z, s2); s3 = fmaf(q[4 * d4 + 3], v.w, s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+template <int DK>
+__device__ __forceinline__ void axpy_bcast(float (&o)[DK], float a, const float* __restrict__ row) {
+#pragma unroll
+  for (int d4 = 0; d4 < DK / 4; d4++) {
+    const float4 v = reinterpret_cast<const float4*>(row)[d4];
+    o[4 * d4] = fmaf(a, v.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(a, v.y, o[4 * d4 + 1]);
+    o[4 * d4 + 2] = fmaf(a, v.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(a, v.w, o[4 * d4 + 3]);
+  }
+}
+
 template <class T, int DK>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ krel,
                                                         T* __restrict__ att, int W, int D, const unsigned char* __restrict__ keep,
                                                         float dscale) {
   extern __shared__ __align__(16) float sm[];
-  float* Ks = sm;                      // [W][DK+1]
-  float* Vs = Ks + W * (DK + 1);       // [W][DK+1]
-  float* Rs = Vs + W * (DK + 1);       // [DK][W]  Krelpos
-  float* Ps = Rs + DK * W;             // [W][W+1]
+  float* Ks = sm;                      // [W][DK]
+  float* Vs = Ks + W * DK;             // [W][DK]
+  float* Rt = Vs + W * DK;             // [W][DK]   Krelpos transposed: Rt[m][d] = Krelpos[d][m]
+  float* Ps = Rt + W * DK;             // [W][W+1]  QP row, then scores / probabilities
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const T* base = qkv + (size_t)b * W * 3 * D + h * DK;
   for (int i = tid; i < W * DK; i += blockDim.x) {
     const int r = i / DK, d = i - r * DK;
-    Ks[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + D + d]);
-    Vs[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + 2 * D + d]);
+    Ks[i] = to_f(base[(size_t)r * 3 * D + D + d]);
+    Vs[i] = to_f(base[(size_t)r * 3 * D + 2 * D + d]);
   }
-  for (int i = tid; i < DK * W; i += blockDim.x) Rs[i] = krel[i];
+  for (int i = tid; i < DK * W; i += blockDim.x) { const int d = i / W, m = i - d * W; Rt[m * DK + d] = krel[i]; }
   __syncthreads();
-  const int i = tid;
-  if (i >= W) return;
+  const int i = tid < W ? tid : W - 1;  // (threads past the last row shadow it: warp-uniform loops, no stores)
+  const bool live = tid < W;
   float q[DK];
 #pragma unroll
   for (int d = 0; d < DK; d++) q[d] = to_f(base[(size_t)i * 3 * D + d]);
   const float scale = rsqrtf((float)DK);
   float* prow = Ps + (size_t)i * (W + 1);
+  const int i_hi = min(W - 1, (tid | 31));  // last row of this warp
+  // pass A: QP[i][m] for the columns this row needs (m >= W-1-i); all lanes walk the same m
+  for (int m = W - 1 - i_hi; m < W; m++) {
+    const float v = dot_bcast<DK>(q, Rt + m * DK);
+    if (live && m >= W - 1 - i) prow[m] = v;
+  }
+  __syncwarp();
+  // pass B: scaled, skewed scores of keys c <= i (in place: column c <= m = W-1-i+c, so the QP entry of c is read
+  // before anything overwrites it)
   float mx = -INFINITY;
-  for (int c = 0; c <= i; c++) {
-    const int m = W - 1 - i + c;
-    float s = 0.f;
-#pragma unroll
-    for (int d = 0; d < DK; d++) s = fmaf(q[d], Ks[c * (DK + 1) + d] + Rs[d * W + m], s);
-    s *= scale;
-    prow[c] = s;
-    mx = fmaxf(mx, s);
+  for (int c = 0; c <= i_hi; c++) {
+    const float v = dot_bcast<DK>(q, Ks + c * DK);
+    if (live && c <= i) {
+      const float sc = (v + prow[W - 1 - i + c]) * scale;
+      prow[c] = sc;
+      mx = fmaxf(mx, sc);
+    }
   }
   float sum = 0.f;
-  for (int c = 0; c <= i; c++) { const float e = __expf(prow[c] - mx); prow[c] = e; sum += e; }
-  const float inv = 1.f / sum;
+  if (live) for (int c = 0; c <= i; c++) { const float e = __expf(prow[c] - mx); prow[c] = e; sum += e; }
+  const float inv = live ? 1.f / sum : 0.f;
   float o[DK];
 #pragma unroll
   for (int d = 0; d < DK; d++) o[d] = 0.f;
   const unsigned char* krow = keep != nullptr ? keep + (((size_t)b * gridDim.x + h) * W + i) * W : nullptr;
-  for (int c = 0; c <= i; c++) {
-    float p = prow[c] * inv;
-    if (krow != nullptr) p = krow[c] ? p * dscale : 0.f;
-#pragma unroll
-    for (int d = 0; d < DK; d++) o[d] = fmaf(p, Vs[c * (DK + 1) + d], o[d]);
+  for (int c = 0; c <= i_hi; c++) {
+    float p = (live && c <= i) ? prow[c] * inv : 0.f;
+    if (krow != nullptr && live && c <= i) p = krow[c] ? p * dscale : 0.f;
+    axpy_bcast<DK>(o, p, Vs + c * DK);
   }
+  if (!live) return;
   T* orow = att + ((size_t)b * W + i) * D + h * DK;
 #pragma unroll
   for (int d = 0; d < DK; d++) orow[d] = from_f<T>(o[d]);
@@ -91,70 +124,94 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const T* __restrict__ qkv
                                                         float* __restrict__ dkrel, int W, int D,
                                                         const unsigned char* __restrict__ keep, float dscale) {
   extern __shared__ __align__(16) float sm[];
-  float* Qs = sm;                      // [W][DK+1]
-  float* Ks = Qs + W * (DK + 1);
-  float* Vs = Ks + W * (DK + 1);
-  float* Gs = Vs + W * (DK + 1);       // dO
-  float* Rs = Gs + W * (DK + 1);       // [DK][W]
-  float* Ps = Rs + DK * W;             // [W][W+1] probabilities
-  float* Ss = Ps + W * (W + 1);        // [W][W+1] d(scaled score)
+  float* Qs = sm;                      // [W][DK]
+  float* Ks = Qs + W * DK;
+  float* Vs = Ks + W * DK;
+  float* Gs = Vs + W * DK;             // dO
+  float* Rt = Gs + W * DK;             // [W][DK]  Krelpos transposed
+  float* Ps = Rt + W * DK;             // [W][W+1] probabilities (dropped ones after the query pass)
+  float* Ss = Ps + W * (W + 1);        // [W][W+1] QP row, then d(scaled score)
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const T* base = qkv + (size_t)b * W * 3 * D + h * DK;
   const T* gbase = datt + (size_t)b * W * D + h * DK;
   for (int i = tid; i < W * DK; i += blockDim.x) {
     const int r = i / DK, d = i - r * DK;
-    Qs[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + d]);
-    Ks[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + D + d]);
-    Vs[r * (DK + 1) + d] = to_f(base[(size_t)r * 3 * D + 2 * D + d]);
-    Gs[r * (DK + 1) + d] = to_f(gbase[(size_t)r * D + d]);
+    Qs[i] = to_f(base[(size_t)r * 3 * D + d]);
+    Ks[i] = to_f(base[(size_t)r * 3 * D + D + d]);
+    Vs[i] = to_f(base[(size_t)r * 3 * D + 2 * D + d]);
+    Gs[i] = to_f(gbase[(size_t)r * D + d]);
   }
-  for (int i = tid; i < DK * W; i += blockDim.x) Rs[i] = krel[i];
+  for (int i = tid; i < DK * W; i += blockDim.x) { const int d = i / W, m = i - d * W; Rt[m * DK + d] = krel[i]; }
   for (int i = tid; i < W * (W + 1); i += blockDim.x) { Ps[i] = 0.f; Ss[i] = 0.f; }
   __syncthreads();
   const float scale = rsqrtf((float)DK);
   T* dbase = dqkv + (size_t)b * W * 3 * D + h * DK;
-  if (tid < W) {
-    const int i = tid;
+  {
+    const int i = tid < W ? tid : W - 1;
+    const bool live = tid < W;
+    const int i_hi = min(W - 1, (tid | 31));
+    // threads past the last row shadow row W-1 (warp-uniform loops): they only READ shared memory, every write below is
+    // guarded by `live`
     float* prow = Ps + (size_t)i * (W + 1);
     float* srow = Ss + (size_t)i * (W + 1);
-    float mx = -INFINITY;
-    for (int c = 0; c <= i; c++) {
-      const int m = W - 1 - i + c;
-      float s = 0.f;
+    float q[DK], go[DK];
 #pragma unroll
-      for (int d = 0; d < DK; d++) s = fmaf(Qs[i * (DK + 1) + d], Ks[c * (DK + 1) + d] + Rs[d * W + m], s);
-      s *= scale;
-      prow[c] = s;
-      mx = fmaxf(mx, s);
+    for (int d = 0; d < DK; d++) { q[d] = Qs[i * DK + d]; go[d] = Gs[i * DK + d]; }
+    // QP[i][m] -> srow[m] (m >= W-1-i)
+    for (int m = W - 1 - i_hi; m < W; m++) {
+      const float v = dot_bcast<DK>(q, Rt + m * DK);
+      if (live && m >= W - 1 - i) srow[m] = v;
     }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int c = 0; c <= i_hi; c++) {
+      const float v = dot_bcast<DK>(q, Ks + c * DK);
+      if (c <= i) {
+        const float sc = (v + srow[W - 1 - i + c]) * scale;
+        if (live) prow[c] = sc;
+        mx = fmaxf(mx, sc);
+      }
+    }
+    __syncwarp();
     float sum = 0.f;
-    for (int c = 0; c <= i; c++) { const float e = __expf(prow[c] - mx); prow[c] = e; sum += e; }
-    const float inv = 1.f / sum;
+    if (live) for (int c = 0; c <= i; c++) { const float e = __expf(prow[c] - mx); prow[c] = e; sum += e; }
+    const float inv = live ? 1.f / sum : 0.f;
     const unsigned char* krow = keep != nullptr ? keep + (((size_t)b * gridDim.x + h) * W + i) * W : nullptr;
     float dsum = 0.f;
-    for (int c = 0; c <= i; c++) {
-      const float p = prow[c] * inv;
-      prow[c] = p;
-      float dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < DK; d++) dp = fmaf(Gs[i * (DK + 1) + d], Vs[c * (DK + 1) + d], dp);
-      if (krow != nullptr) dp = krow[c] ? dp * dscale : 0.f;  // gradient w.r.t. the probability before dropout
-      srow[c] = dp;
-      dsum = fmaf(dp, p, dsum);
+    for (int c = 0; c <= i_hi; c++) {
+      float dp = dot_bcast<DK>(go, Vs + c * DK);
+      if (live && c <= i) {
+        const float p = prow[c] * inv;
+        prow[c] = p;
+        if (krow != nullptr) dp = krow[c] ? dp * dscale : 0.f;  // gradient w.r.t. the probability before dropout
+        srow[c] = dp;                                           // (the QP entries of this row were consumed by the score pass)
+        dsum = fmaf(dp, p, dsum);
+      }
     }
+    // ds in place; probabilities become the DROPPED ones (dv below needs them)
+    if (live) for (int c = 0; c <= i; c++) {
+      const float ds = prow[c] * (srow[c] - dsum) * scale;
+      srow[c] = ds;
+      if (krow != nullptr) prow[c] = krow[c] ? prow[c] * dscale : 0.f;
+    }
+    __syncwarp();
+    // dq = sum_c ds[c] K[c]  +  sum_m ds[c = m - (W-1-i)] Krelpos[:, m]   (both loops: warp-uniform index, broadcast rows)
     float dq[DK];
 #pragma unroll
     for (int d = 0; d < DK; d++) dq[d] = 0.f;
-    for (int c = 0; c <= i; c++) {
-      const int m = W - 1 - i + c;
-      const float ds = prow[c] * (srow[c] - dsum) * scale;
-      srow[c] = ds;
-      if (krow != nullptr) prow[c] = krow[c] ? prow[c] * dscale : 0.f;  // dv below needs the dropped probability
-#pragma unroll
-      for (int d = 0; d < DK; d++) dq[d] = fmaf(ds, Ks[c * (DK + 1) + d] + Rs[d * W + m], dq[d]);
+    for (int c = 0; c <= i_hi; c++) {
+      const float ds = (live && c <= i) ? srow[c] : 0.f;
+      axpy_bcast<DK>(dq, ds, Ks + c * DK);
     }
+    for (int m = W - 1 - i_hi; m < W; m++) {
+      const int c = m - (W - 1 - i);
+      const float ds = (live && c >= 0) ? srow[c] : 0.f;
+      axpy_bcast<DK>(dq, ds, Rt + m * DK);
+    }
+    if (live) {
 #pragma unroll
-    for (int d = 0; d < DK; d++) dbase[(size_t)i * 3 * D + d] = from_f<T>(dq[d]);
+      for (int d = 0; d < DK; d++) dbase[(size_t)i * 3 * D + d] = from_f<T>(dq[d]);
+    }
   }
   __syncthreads();
   if (tid < W) {
@@ -162,13 +219,12 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const T* __restrict__ qkv
     float dk[DK], dv[DK];
 #pragma unroll
     for (int d = 0; d < DK; d++) { dk[d] = 0.f; dv[d] = 0.f; }
-    for (int i = c; i < W; i++) {
-      const float ds = Ss[(size_t)i * (W + 1) + c], p = Ps[(size_t)i * (W + 1) + c];
-#pragma unroll
-      for (int d = 0; d < DK; d++) {
-        dk[d] = fmaf(ds, Qs[i * (DK + 1) + d], dk[d]);
-        dv[d] = fmaf(p, Gs[i * (DK + 1) + d], dv[d]);
-      }
+    const int c_lo = tid & ~31;  // rows i >= c_lo can touch a key of this warp: warp-uniform loop, zeros above the diagonal
+    for (int i = c_lo; i < W; i++) {
+      // (entries above the diagonal of Ss hold left-over QP values: masked here)
+      const float ds = i >= c ? Ss[(size_t)i * (W + 1) + c] : 0.f, p = i >= c ? Ps[(size_t)i * (W + 1) + c] : 0.f;
+      axpy_bcast<DK>(dk, ds, Qs + i * DK);
+      axpy_bcast<DK>(dv, p, Gs + i * DK);
     }
 #pragma unroll
     for (int d = 0; d < DK; d++) {
@@ -180,10 +236,11 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const T* __restrict__ qkv
     float dr[DK];
 #pragma unroll
     for (int d = 0; d < DK; d++) dr[d] = 0.f;
-    for (int i = W - 1 - m; i < W; i++) {
-      const float ds = Ss[(size_t)i * (W + 1) + (i - (W - 1 - m))];
-#pragma unroll
-      for (int d = 0; d < DK; d++) dr[d] = fmaf(ds, Qs[i * (DK + 1) + d], dr[d]);
+    const int m_hi = min(W - 1, (tid | 31));
+    for (int i = W - 1 - m_hi; i < W; i++) {
+      const int cc = i - (W - 1 - m);
+      const float ds = cc >= 0 ? Ss[(size_t)i * (W + 1) + cc] : 0.f;
+      axpy_bcast<DK>(dr, ds, Qs + i * DK);
     }
 #pragma unroll
     for (int d = 0; d < DK; d++) atomicAdd(dkrel + d * W + m, dr[d]);
@@ -353,12 +410,15 @@ __global__ void acc_add_kernel(float* __restrict__ acc, const T* __restrict__ a,
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc[i] += to_f(a[i]) + to_f(b[i]);
 }
-// dc[b, w < W, :] = acc[(b, w), :]
-__global__ void scatter_rows_kernel(const float* __restrict__ acc, float* __restrict__ dc, int B, int S, int W, int D) {
+// dc[b, w < W, :] = sum over the lanes' accumulators acc[l][(b, w), :]
+__global__ void scatter_rows_kernel(const float* __restrict__ acc, size_t lane_stride, int nlanes, float* __restrict__ dc, int B, int S,
+                                    int W, int D) {
   const long long n = (long long)B * W * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int d = (int)(i % D); const long long pw = i / D; const int w = (int)(pw % W), b = (int)(pw / W);
-    dc[((long long)b * S + w) * D + d] = acc[i];
+    float v = 0.f;
+    for (int l = 0; l < nlanes; l++) v += acc[(size_t)l * lane_stride + i];
+    dc[((long long)b * S + w) * D + d] = v;
   }
 }
 // dst[d][j*D + r] = w_j[r][d]  for j in {q, k, v}: the (D, 3D) transposed concatenation used by d(x) = dqkv . [Wq;Wk;Wv]
@@ -366,6 +426,8 @@ template <class T>
 __global__ void concat_transpose3_kernel(const float* __restrict__ wq, const float* __restrict__ wk, const float* __restrict__ wv,
                                          T* __restrict__ dst, int D) {
   const long long n = (long long)3 * D * D;
+  wq += (size_t)blockIdx.z * D * D; wk += (size_t)blockIdx.z * D * D; wv += (size_t)blockIdx.z * D * D;  // head blockIdx.z
+  dst += (size_t)blockIdx.z * 3 * D * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % (3 * D)), d = (int)(i / (3 * D));
     const int j = col / D, r = col - j * D;
@@ -376,8 +438,8 @@ __global__ void concat_transpose3_kernel(const float* __restrict__ wq, const flo
 
 inline int grid_for(long long n) { long long b = (n + 255) / 256; return (int)(b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b)); }
 
-template <class T> size_t attn_fwd_smem(int W, int DK) { return (size_t)(2 * W * (DK + 1) + DK * W + W * (W + 1)) * 4; }
-template <class T> size_t attn_bwd_smem(int W, int DK) { return (size_t)(4 * W * (DK + 1) + DK * W + 2 * W * (W + 1)) * 4; }
+template <class T> size_t attn_fwd_smem(int W, int DK) { return (size_t)(3 * W * DK + W * (W + 1)) * 4; }
+template <class T> size_t attn_bwd_smem(int W, int DK) { return (size_t)(5 * W * DK + 2 * W * (W + 1)) * 4; }
 
 template <class T>
 int launch_attn_fwd(const T* qkv, const float* krel, T* att, int B, int W, int D, int nh, const unsigned char* keep, float dscale,
@@ -439,6 +501,50 @@ int launch_ln_bwd(const T* dya, long long dya_rs, const T* dyb, const T* s, cons
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Head-level concurrency.  The K heads are independent until their gradients meet in dc, and one head's kernels are small
+// (a (B*W) x 256 x 256 product is 29 output tiles on 148 SMs): the heads are dealt round-robin onto kLanes streams - the
+// caller's stream plus library-owned side streams forked from it and joined back before the call returns, so the caller
+// still sees plain stream order and a CUDA-graph capture records the lanes as parallel branches.  Every lane has its own
+// scratch (converted weights, intermediates, dc accumulator).  Per-kernel profiling (prof_enabled) runs single-lane.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kLanes = 4;
+struct Lanes {
+  cudaStream_t st[kLanes];
+  int n;
+};
+int lanes_fork(cudaStream_t main, int want, Lanes* L) {
+  static thread_local cudaStream_t side[kLanes - 1] = {nullptr, nullptr, nullptr};
+  static thread_local cudaEvent_t ev_fork = nullptr;
+  static thread_local int dev_of = -1;
+  int dev = 0;
+  CPC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev_of != dev) {  // (one set per host thread and device; a thread that changes device gets fresh ones)
+    for (int i = 0; i < kLanes - 1; i++) CPC_CHECK_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+    CPC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    dev_of = dev;
+  }
+  static const int env_lanes = []() { const char* e = getenv("CPC_B200_HEAD_LANES"); int v = e ? atoi(e) : kLanes; return v < 1 ? 1 : (v > kLanes ? kLanes : v); }();
+  int n = want < env_lanes ? want : env_lanes;
+  if (prof_enabled() || n < 1) n = 1;
+  L->n = n;
+  L->st[0] = main;
+  if (n > 1) {
+    CPC_CHECK_CUDA(cudaEventRecord(ev_fork, main));
+    for (int i = 1; i < n; i++) { L->st[i] = side[i - 1]; CPC_CHECK_CUDA(cudaStreamWaitEvent(side[i - 1], ev_fork, 0)); }
+  }
+  return 0;
+}
+int lanes_join(const Lanes& L) {
+  static thread_local cudaEvent_t ev_join[kLanes - 1] = {nullptr, nullptr, nullptr};
+  for (int i = 1; i < L.n; i++) {
+    if (ev_join[i - 1] == nullptr) CPC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join[i - 1], cudaEventDisableTiming));
+    CPC_CHECK_CUDA(cudaEventRecord(ev_join[i - 1], L.st[i]));
+    CPC_CHECK_CUDA(cudaStreamWaitEvent(L.st[0], ev_join[i - 1], 0));
+  }
+  return 0;
+}
+
 struct THeadLayout { size_t qkv, att, s1, y1, h, s2, per_k; };  // element offsets (units of T) inside one head's block
 THeadLayout thead_layout(const Geo& g) {
   THeadLayout l{};
@@ -456,16 +562,17 @@ size_t thead_save_bytes(const Geo& g) { return thead_layout(g).per_k * g.K * (g.
 
 size_t thead_ws_bytes(const Geo& g, int backward) {
   const size_t es = g.bf16 ? 2 : 4, P = (size_t)g.B * g.W, D = g.H, F = g.dff;
-  size_t t = 0;
+  size_t t = 0, w = 0;
+  const size_t K = (size_t)g.K;
   if (!backward) {
-    t += 4 * align_up(D * D * es) + 2 * align_up(F * D * es);   // Wq, Wk, Wv, Wo, W1, W2 in T
-    t += 2 * align_up(P * D * es);                              // o, f
+    w += 4 * align_up(D * D * es * K) + 2 * align_up(F * D * es * K);   // Wq, Wk, Wv, Wo, W1, W2 of all heads in T
+    t += 2 * align_up(P * D * es);                                      // o, f
   } else {
-    t += align_up(3 * D * D * es) + align_up(D * D * es) + 2 * align_up(F * D * es);   // transposed weights
+    w += align_up(3 * D * D * es * K) + align_up(D * D * es * K) + 2 * align_up(F * D * es * K);   // transposed weights, all heads
     t += 5 * align_up(P * D * es) + align_up(P * F * es) + align_up(P * 3 * D * es);   // ds2, dy1, ds1, datt, dx, dh, dqkv
     t += align_up(P * D * 4);                                                          // dc accumulator
   }
-  return t + 1024;
+  return t * kLanes + w + 1024;  // one scratch set per lane + the converted weights
 }
 
 template <class T>
@@ -477,12 +584,25 @@ int thead_fwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, T* pred
   constexpr bool isf = sizeof(T) == 4;
   const THeadLayout lay = thead_layout(g);
   T* sv = static_cast<T*>(save);
-  T* wq = ws.take<T>((size_t)D * D); T* wk = ws.take<T>((size_t)D * D); T* wv = ws.take<T>((size_t)D * D);
-  T* wo = ws.take<T>((size_t)D * D); T* w1 = ws.take<T>((size_t)F * D); T* w2 = ws.take<T>((size_t)F * D);
-  T* o = ws.take<T>((size_t)P * D); T* f = ws.take<T>((size_t)P * D);
+  struct FwdScratch { T *o, *f; } scr[kLanes];
+  for (int l = 0; l < kLanes; l++) { scr[l].o = ws.take<T>((size_t)P * D); scr[l].f = ws.take<T>((size_t)P * D); }
+  // the six weight matrices of ALL heads in the storage type: one conversion launch per parameter (K stacked matrices)
+  T* wall[6] = {nullptr};
+  const size_t wsz[6] = {(size_t)D * D, (size_t)D * D, (size_t)D * D, (size_t)D * D, (size_t)F * D, (size_t)F * D};
+  if (!isf) for (int j = 0; j < 6; j++) wall[j] = ws.take<T>(wsz[j] * K);
   if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "thead_fwd: workspace too small (%zu needed)", ws.off);
+  if (!isf) {
+    const float* src[6] = {tp->wq, tp->wk, tp->wv, tp->wo, tp->w1, tp->w2};
+    for (int j = 0; j < 6; j++) CPC_TRY(launch_cast<T>(src[j], wall[j], (long long)(wsz[j] * K), st));
+  }
   const RowView X{cp, (long long)S * D, (long long)D, W};
+  const cudaStream_t st_main = st;
+  Lanes lanes;
+  CPC_TRY(lanes_fork(st_main, K, &lanes));
   for (int k = 0; k < K; k++) {
+    const FwdScratch& sc = scr[k % lanes.n];
+    st = lanes.st[k % lanes.n];
+    T *o = sc.o, *f = sc.f;
     T* blk = sv + (size_t)k * lay.per_k;
     T *qkv = blk + lay.qkv, *att = blk + lay.att, *s1 = blk + lay.s1, *y1 = blk + lay.y1, *h = blk + lay.h, *s2 = blk + lay.s2;
     const T *Wq, *Wk, *Wv, *Wo, *W1, *W2;
@@ -491,13 +611,8 @@ int thead_fwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, T* pred
       Wv = reinterpret_cast<const T*>(tp->wv + (size_t)k * D * D); Wo = reinterpret_cast<const T*>(tp->wo + (size_t)k * D * D);
       W1 = reinterpret_cast<const T*>(tp->w1 + (size_t)k * F * D); W2 = reinterpret_cast<const T*>(tp->w2 + (size_t)k * D * F);
     } else {
-      CPC_TRY(launch_cast<T>(tp->wq + (size_t)k * D * D, wq, (long long)D * D, st));
-      CPC_TRY(launch_cast<T>(tp->wk + (size_t)k * D * D, wk, (long long)D * D, st));
-      CPC_TRY(launch_cast<T>(tp->wv + (size_t)k * D * D, wv, (long long)D * D, st));
-      CPC_TRY(launch_cast<T>(tp->wo + (size_t)k * D * D, wo, (long long)D * D, st));
-      CPC_TRY(launch_cast<T>(tp->w1 + (size_t)k * F * D, w1, (long long)F * D, st));
-      CPC_TRY(launch_cast<T>(tp->w2 + (size_t)k * D * F, w2, (long long)D * F, st));
-      Wq = wq; Wk = wk; Wv = wv; Wo = wo; W1 = w1; W2 = w2;
+      Wq = wall[0] + (size_t)k * D * D; Wk = wall[1] + (size_t)k * D * D; Wv = wall[2] + (size_t)k * D * D;
+      Wo = wall[3] + (size_t)k * D * D; W1 = wall[4] + (size_t)k * F * D; W2 = wall[5] + (size_t)k * D * F;
     }
     const T* Wqkv[3] = {Wq, Wk, Wv};
     for (int j = 0; j < 3; j++) {  // q | k | v column blocks of qkv
@@ -532,6 +647,7 @@ int thead_fwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, T* pred
     CPC_TRY((launch_add_ln<T, T>(y1, (long long)P * D, (long long)D, P, f, tp->ln2_w + (size_t)k * D, tp->ln2_b + (size_t)k * D, s2,
                                  pred + (size_t)k * D, (long long)K * D, P, D, st)));
   }
+  CPC_TRY(lanes_join(lanes));
   return 0;
 }
 
@@ -542,24 +658,39 @@ int thead_bwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, const T
   const int P = B * W, DK = D / nh;
   const THeadLayout lay = thead_layout(g);
   const T* sv = static_cast<const T*>(save);
-  T* wqkvT = ws.take<T>((size_t)3 * D * D); T* woT = ws.take<T>((size_t)D * D);
-  T* w1T = ws.take<T>((size_t)F * D); T* w2T = ws.take<T>((size_t)F * D);
-  T* ds2 = ws.take<T>((size_t)P * D); T* dy1 = ws.take<T>((size_t)P * D); T* ds1 = ws.take<T>((size_t)P * D);
-  T* datt = ws.take<T>((size_t)P * D); T* dx = ws.take<T>((size_t)P * D);
-  T* dh = ws.take<T>((size_t)P * F); T* dqkv = ws.take<T>((size_t)P * 3 * D);
-  float* dcw = ws.take<float>((size_t)P * D);
+  struct BwdScratch { T *ds2, *dy1, *ds1, *datt, *dx, *dh, *dqkv; float* dcw; } scr[kLanes];
+  // transposed weights of ALL heads: one launch per parameter (batched over the K stacked matrices)
+  T* wqkvT_all = ws.take<T>((size_t)3 * D * D * K); T* woT_all = ws.take<T>((size_t)D * D * K);
+  T* w1T_all = ws.take<T>((size_t)F * D * K); T* w2T_all = ws.take<T>((size_t)F * D * K);
+  for (int l = 0; l < kLanes; l++) {
+    scr[l].ds2 = ws.take<T>((size_t)P * D); scr[l].dy1 = ws.take<T>((size_t)P * D); scr[l].ds1 = ws.take<T>((size_t)P * D);
+    scr[l].datt = ws.take<T>((size_t)P * D); scr[l].dx = ws.take<T>((size_t)P * D);
+    scr[l].dh = ws.take<T>((size_t)P * F); scr[l].dqkv = ws.take<T>((size_t)P * 3 * D);
+  }
+  for (int l = 0; l < kLanes; l++) scr[l].dcw = ws.take<float>((size_t)P * D);  // contiguous: cleared with one memset
   if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "thead_bwd: workspace too small (%zu needed)", ws.off);
-  CPC_CHECK_CUDA(cudaMemsetAsync(dcw, 0, (size_t)P * D * 4, st));
+  const cudaStream_t st_main = st;
+  CPC_CHECK_CUDA(cudaMemsetAsync(scr[0].dcw, 0, (size_t)((char*)scr[kLanes - 1].dcw - (char*)scr[0].dcw) + (size_t)P * D * 4, st_main));
   const RowView X{cp, (long long)S * D, (long long)D, W};
+  concat_transpose3_kernel<T><<<dim3(grid_for((long long)3 * D * D), 1, K), 256, 0, st_main>>>(tp->wq, tp->wk, tp->wv, wqkvT_all, D);
+  CPC_LAUNCHED_N("concat_transpose3", st_main);
+  CPC_TRY(launch_transpose_cast<T>(tp->wo, woT_all, D, D, st_main, K));       // woT[a][o] = Wo[o][a]
+  CPC_TRY(launch_transpose_cast<T>(tp->w1, w1T_all, F, D, st_main, K));       // [D][F]
+  CPC_TRY(launch_transpose_cast<T>(tp->w2, w2T_all, D, F, st_main, K));       // [F][D]
+  Lanes lanes;
+  CPC_TRY(lanes_fork(st_main, K, &lanes));
   for (int k = 0; k < K; k++) {
+    const BwdScratch& sc = scr[k % lanes.n];
+    st = lanes.st[k % lanes.n];
+    T *ds2 = sc.ds2, *dy1 = sc.dy1, *ds1 = sc.ds1, *datt = sc.datt, *dx = sc.dx, *dh = sc.dh, *dqkv = sc.dqkv;
+    float* dcw = sc.dcw;
+    const T* wqkvT = wqkvT_all + (size_t)k * 3 * D * D;
+    const T* woT = woT_all + (size_t)k * D * D;
+    const T* w1T = w1T_all + (size_t)k * F * D;
+    const T* w2T = w2T_all + (size_t)k * F * D;
     const T* blk = sv + (size_t)k * lay.per_k;
     const T *qkv = blk + lay.qkv, *att = blk + lay.att, *s1 = blk + lay.s1, *y1 = blk + lay.y1, *h = blk + lay.h, *s2 = blk + lay.s2;
     const size_t oDD = (size_t)k * D * D, oFD = (size_t)k * F * D;
-    concat_transpose3_kernel<T><<<grid_for((long long)3 * D * D), 256, 0, st>>>(tp->wq + oDD, tp->wk + oDD, tp->wv + oDD, wqkvT, D);
-    CPC_LAUNCHED_N("concat_transpose3", st);
-    CPC_TRY(launch_transpose_cast<T>(tp->wo + oDD, woT, D, D, st));       // woT[a][o] = Wo[o][a]
-    CPC_TRY(launch_transpose_cast<T>(tp->w1 + oFD, w1T, F, D, st));       // [D][F]
-    CPC_TRY(launch_transpose_cast<T>(tp->w2 + oFD, w2T, D, F, st));       // [F][D]
     // LN2 backward
     CPC_TRY(launch_ln_bwd<T>(dpred + (size_t)k * D, (long long)K * D, nullptr, s2, tp->ln2_w + (size_t)k * D, ds2,
                              gr->ln2_w + (size_t)k * D, gr->ln2_b + (size_t)k * D, P, D, st));
@@ -605,7 +736,9 @@ int thead_bwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, const T
     acc_add_kernel<T><<<grid_for((long long)P * D), 256, 0, st>>>(dcw, dx, ds1, (long long)P * D);
     CPC_LAUNCHED_N("acc_add", st);
   }
-  scatter_rows_kernel<<<grid_for((long long)P * D), 256, 0, st>>>(dcw, dc, B, S, W, D);
+  CPC_TRY(lanes_join(lanes));
+  st = st_main;
+  scatter_rows_kernel<<<grid_for((long long)P * D), 256, 0, st>>>(scr[0].dcw, (size_t)((char*)scr[1].dcw - (char*)scr[0].dcw) / 4, kLanes, dc, B, S, W, D);
   CPC_LAUNCHED_N("scatter_rows", st);
   return 0;
 }
