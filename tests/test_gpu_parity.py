@@ -3,8 +3,10 @@ committed reference fixtures.  Tolerances (stated per dtype, see DESIGN.md "Pari
 
   f32 path : z, c max-rel <= 1e-4 ; per-step loss |d| <= 1e-4 (+1e-5 rel) ; acc equal except near-tie rows ;
              every parameter gradient rel-L2 <= 5e-4.
-  bf16 path: z, c rel-L2 <= 2e-2 ; loss |d| <= 3e-3 (reference init) / 2% (x30-scaled heads) ;
-             acc within 2% abs ; gradient cosine >= 0.99 per parameter tensor.
+  bf16 path: z, c rel-L2 <= 1.5e-2 (measured 4e-3 .. 8e-3) ; loss |d| <= 3e-3 (reference init) / 1% + 1e-2 (x30-scaled heads) ;
+             acc within 1% abs at default widths (0.5% at the benchmarked shape) ; gradient cosine per parameter tensor >=
+             tests/helpers.py:bf16_cos_floor - 0.999 except the named, measured exceptions (encoder tensors of tiny
+             batches, conv0.weight, transformer-layer parameters).  Measured values: profiles/parity_r2.json.
   indices  : bit-exact.
 """
 import math
@@ -70,26 +72,22 @@ def test_parity_bf16(name, built_lib):
     ref = Hh.oracle_run(d, mp, cp, x, bi, si)
     model, crit = Hh.build_modules(d, mp, cp, "bf16")
     out = Hh.run_modules(model, crit, x, label, bi, si)
-    assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2
-    assert Hh.rel_err(out["c"], ref["c"]) <= 2e-2
+    assert Hh.rel_err(out["z"], ref["z"]) <= 1.5e-2     # measured 5.0e-3 .. 6.5e-3
+    assert Hh.rel_err(out["c"], ref["c"]) <= 1.5e-2     # measured 4.4e-3 .. 7.8e-3
     scaled = float(g["pred_scale"]) != 1.0
     dl = (out["losses"].cpu() - ref["losses"]).abs()
     if scaled:
-        assert (dl <= 0.02 * ref["losses"].abs() + 1e-2).all(), dl
+        assert (dl <= 0.01 * ref["losses"].abs() + 1e-2).all(), dl
     else:
         assert (dl <= 3e-3).all(), dl
-    assert ((out["acc"].cpu() - ref["acc"]).abs() <= 0.02 + Hh.acc_tolerance(ref["logits"], d)).all()
+    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.01 if d.H >= 256 else 0.03) + Hh.acc_tolerance(ref["logits"], d)).all()
     rep, wc, wr = Hh.grad_report(out["grads"], ref["grads"])
     Hh.record(f"parity:{name}:bf16", z_rel=Hh.rel_err(out["z"], ref["z"]), c_rel=Hh.rel_err(out["c"], ref["c"]), dloss=dl.max().item(),
               dacc=(out["acc"].cpu() - ref["acc"]).abs().max().item(), worst_cos=[wc[0], wc[1][0]], worst_rel=[wr[0], wr[1][1]],
               grads={k: [round(v[0], 6), float(f"{v[1]:.3e}")] for k, v in rep.items()})
     for k, gr in ref["grads"].items():
         cs = _cos(out["grads"][k], gr)
-        # conv biases feed a ChannelNorm: their gradient is a heavily cancelling sum -> looser bound
-        floor = 0.95 if (k.endswith(".bias") and "conv" in k) else 0.99
-        if d.H < 256:
-            floor = 0.95  # toy widths (64 / 128 channels): per-tensor sums are short and bf16 noise shows
-        assert cs >= floor, (k, cs)
+        assert cs >= Hh.bf16_cos_floor(k, d), (k, cs)
 
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
@@ -344,12 +342,13 @@ def test_ragged_shapes_against_oracle(B, L, dtype, built_lib):
         for k, gr in ref["grads"].items():
             assert Hh.rel_err(out["grads"][k], gr) <= 5e-4, k
     else:
-        assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2 and Hh.rel_err(out["c"], ref["c"]) <= 2e-2
-        assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.02 * ref["losses"].abs() + 1e-2).all()
+        assert Hh.rel_err(out["z"], ref["z"]) <= 1.5e-2 and Hh.rel_err(out["c"], ref["c"]) <= 1.5e-2
+        assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.01 * ref["losses"].abs() + 1e-2).all()
+        rep, wc, wr = Hh.grad_report(out["grads"], ref["grads"])
+        Hh.record(f"ragged_batch:B{B}:L{L}:bf16", z_rel=Hh.rel_err(out["z"], ref["z"]), worst_cos=[wc[0], wc[1][0]], worst_rel=[wr[0], wr[1][1]])
         for k, gr in ref["grads"].items():
-            floor = 0.95 if (k.endswith(".bias") and "conv" in k) else 0.985
-            assert _cos(out["grads"][k], gr) >= floor, (k, _cos(out["grads"][k], gr))
-    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else 0.03) + Hh.acc_tolerance(ref["logits"], d)).all()
+            assert _cos(out["grads"][k], gr) >= Hh.bf16_cos_floor(k, d), (k, _cos(out["grads"][k], gr))
+    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else 0.02) + Hh.acc_tolerance(ref["logits"], d)).all()
 
 
 def test_config5_dims_bf16(built_lib):
@@ -363,11 +362,10 @@ def test_config5_dims_bf16(built_lib):
     ref = Hh.oracle_run(d, mp, cp, x, bi, si, materialize=False)
     model, crit = Hh.build_modules(d, mp, cp, "bf16")
     out = Hh.run_modules(model, crit, x, label, bi, si)
-    assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2 and Hh.rel_err(out["c"], ref["c"]) <= 3e-2
-    assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.03 * ref["losses"].abs() + 1e-2).all()
+    assert Hh.rel_err(out["z"], ref["z"]) <= 1.5e-2 and Hh.rel_err(out["c"], ref["c"]) <= 1.5e-2
+    assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.01 * ref["losses"].abs() + 1e-2).all()
     for k, gr in ref["grads"].items():
-        floor = 0.95 if (k.endswith(".bias") and "conv" in k) else 0.98
-        assert _cos(out["grads"][k], gr) >= floor, (k, _cos(out["grads"][k], gr))
+        assert _cos(out["grads"][k], gr) >= Hh.bf16_cos_floor(k, d), (k, _cos(out["grads"][k], gr))
 
 
 @pytest.mark.parametrize("name", Hh.T_CASES)
@@ -388,11 +386,11 @@ def test_transformer_heads_parity(name, dtype, built_lib):
             e = Hh.rel_err(out["grads"][k], gr)
             assert e <= 2e-3, (k, e)
     else:
-        assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.02 * ref["losses"].abs() + 1e-2).all()
+        assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.01 * ref["losses"].abs() + 1e-2).all()
         for k, gr in ref["grads"].items():
-            floor = 0.95 if (d.H < 256 or (k.endswith(".bias") and "conv" in k)) else 0.98
-            assert _cos(out["grads"][k], gr) >= floor, (k, _cos(out["grads"][k], gr))
-    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else 0.03) + Hh.acc_tolerance(ref["logits"], d)).all()
+            assert _cos(out["grads"][k], gr) >= Hh.bf16_cos_floor(k, d), (k, _cos(out["grads"][k], gr))
+    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else (0.01 if d.H >= 256 else 0.03))
+            + Hh.acc_tolerance(ref["logits"], d)).all()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node")
@@ -435,12 +433,12 @@ def _check_case(name, dtype, tag):
             # head's attention gradients by < 1e-2 (cosine stays >= 0.9999) - a knife edge of the function, not of the kernels
             assert rl <= 2e-3 or (rl <= 1e-2 and cs >= 0.9999), (k, rl, cs)
     else:
-        assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2 and Hh.rel_err(out["c"], ref["c"]) <= 3e-2
-        assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.02 * ref["losses"].abs() + 1e-2).all()
+        assert Hh.rel_err(out["z"], ref["z"]) <= 1.5e-2 and Hh.rel_err(out["c"], ref["c"]) <= 1.5e-2
+        assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.01 * ref["losses"].abs() + 1e-2).all()
         for k, (cs, rl) in rep.items():
-            floor = 0.95 if (d.H < 256 or (k.endswith(".bias") and "conv" in k)) else 0.98
-            assert cs >= floor, (k, cs)
-    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else 0.03) + Hh.acc_tolerance(ref["logits"], d)).all()
+            assert cs >= Hh.bf16_cos_floor(k, d), (k, cs)
+    assert ((out["acc"].cpu() - ref["acc"]).abs() <= (0.0 if dtype == "f32" else (0.01 if d.H >= 256 else 0.03))
+            + Hh.acc_tolerance(ref["logits"], d)).all()
 
 
 @pytest.mark.parametrize("name", Hh.AR_CASES)
@@ -486,8 +484,8 @@ def test_arbitrary_window_length(L, B, dtype, built_lib):
         np.testing.assert_allclose(out["losses"].cpu().numpy(), ref["losses"].numpy(), rtol=1e-5, atol=1e-4)
         assert wr[1][1] <= 5e-4, wr
     else:
-        assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2 and Hh.rel_err(out["c"], ref["c"]) <= 2e-2
-        assert wc[1][0] >= 0.95, wc
+        assert Hh.rel_err(out["z"], ref["z"]) <= 1.5e-2 and Hh.rel_err(out["c"], ref["c"]) <= 1.5e-2
+        assert wc[1][0] >= 0.985, wc      # measured 0.9931 .. 0.9949 (encoder tensors, B <= 3)
     # no_grad forward (nothing saved, activations ping-pong in the workspace) gives the same features
     with torch.no_grad():
         c2, z2, _ = model(x.cuda(), label.cuda())
@@ -553,9 +551,11 @@ def test_full_size_gradients_against_oracle(dtype, built_lib):
     if dtype == "f32":
         assert dl <= 2e-4 and wr[1][1] <= 1e-3, (dl, wr)
     else:
-        assert dl <= 0.02 * ref["losses"].abs().max().item() + 1e-2
+        assert dl <= 0.01 * ref["losses"].abs().max().item() + 1e-2
+        assert Hh.rel_err(out["z"], ref["z"]) <= 1e-2 and Hh.rel_err(out["c"], ref["c"]) <= 1e-2
+        assert (out["acc"].cpu() - ref["acc"]).abs().max().item() <= 0.005    # +-0.5 % abs (measured 0.013 %)
         for k, (cs, rl) in rep.items():
-            assert cs >= (0.97 if (k.endswith(".bias") and "conv" in k) else 0.995), (k, cs, rl)
+            assert cs >= Hh.bf16_cos_floor(k, d), (k, cs, rl)   # >= 0.999 on every tensor but conv0.weight (0.995)
 
 
 def test_config5_full_length_bf16(built_lib):
@@ -571,9 +571,9 @@ def test_config5_full_length_bf16(built_lib):
     rep, wc, wr = Hh.grad_report(out["grads"], ref["grads"])
     Hh.record("config5:S512:bf16", z_rel=Hh.rel_err(out["z"], ref["z"]), c_rel=Hh.rel_err(out["c"], ref["c"]),
               dloss=(out["losses"].cpu() - ref["losses"]).abs().max().item(), worst_cos=[wc[0], wc[1][0]], worst_rel=[wr[0], wr[1][1]])
-    assert Hh.rel_err(out["z"], ref["z"]) <= 2e-2 and Hh.rel_err(out["c"], ref["c"]) <= 4e-2
-    assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.03 * ref["losses"].abs() + 1e-2).all()
-    assert wc[1][0] >= 0.95, wc
+    assert Hh.rel_err(out["z"], ref["z"]) <= 1.5e-2 and Hh.rel_err(out["c"], ref["c"]) <= 1.5e-2
+    assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.01 * ref["losses"].abs() + 1e-2).all()
+    assert wc[1][0] >= 0.985, wc          # measured 0.9947 (gEncoder.conv0.weight, B = 2)
 
 
 def test_optimizer_state_dict_interchanges_with_torch_adam(built_lib):
