@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--heads", default="linear", choices=["linear", "transformer"],
                     help="prediction heads: 'linear' = BASELINE config 2/3 (default), 'transformer' = config 4 (eval-mode heads)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="windows per step of the CPU baseline sample")
+    ap.add_argument("--preset", default="default", choices=["default", "config5"],
+                    help="'config5' = BASELINE config 5 (hiddenEncoder = hiddenGar = 512, 2-level GRU, K = 16, 256 negatives, "
+                         "81920-sample windows; use --batch 8); its per-kernel rooflines are not tabulated")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-py", action="store_true", help="skip the leg that drives the reference's trainStep loop")
     ap.add_argument("--no-torch-gpu", action="store_true", help="skip the informational leg: unmodified reference modules on this GPU")
@@ -455,10 +458,15 @@ def run_ours(a):
     lib = L.lib()
     B = a.batch
 
+    global WINDOW
+    HID, NLEV, KP, NNEG = 256, 1, 12, 128
+    if a.preset == "config5":
+        HID, NLEV, KP, NNEG, WINDOW = 512, 2, 16, 256, 81920
+        a.no_train_py = a.no_torch_gpu = a.no_cpu_baseline = True
     torch.manual_seed(0)  # identical initial parameters on every rank (replicas)
-    model = M.CPCModel(M.CPCEncoder(256, "layerNorm", compute_dtype=a.dtype),
-                       M.CPCAR(256, 256, False, 1, mode="GRU", reverse=False, compute_dtype=a.dtype)).to(dev)
-    crit = M.CPCUnsupersivedCriterion(12, 256, 256, 128, mode=None, rnnMode=a.heads, dropout=False, speakerEmbedding=0,
+    model = M.CPCModel(M.CPCEncoder(HID, "layerNorm", compute_dtype=a.dtype),
+                       M.CPCAR(HID, HID, False, NLEV, mode="GRU", reverse=False, compute_dtype=a.dtype)).to(dev)
+    crit = M.CPCUnsupersivedCriterion(KP, HID, HID, NNEG, mode=None, rnnMode=a.heads, dropout=False, speakerEmbedding=0,
                                       nSpeakers=0, sizeInputSeq=WINDOW // 160, compute_dtype=a.dtype).to(dev)
     model.train()
     crit.train()  # cpc/train.py:71-72: the transformer heads then apply the reference's dropout 0.1 (masks from torch's generator)
@@ -496,7 +504,7 @@ def run_ours(a):
     x_dev = torch.randn(B, 1, WINDOW, device=dev, generator=gen) * 0.1
     label = torch.zeros(B, dtype=torch.long, device=dev)
     x_host = x_dev.cpu().pin_memory()
-    loss_host = torch.empty(1, 12).pin_memory()
+    loss_host = torch.empty(1, KP).pin_memory()
 
     if world > 1 and not fused_ar and os.environ.get("CPC_B200_AR_OVERLAP", "0") != "0":  # measured slower: see DESIGN.md 5
         enc = model.gEncoder  # all-reduce everything but conv0's gradients while the backward pass is still running
@@ -649,7 +657,7 @@ def run_ours(a):
             name, cnt, tot = line.split()
             rows[name] = (int(cnt), float(tot))
         pk = peaks()
-        work = algorithmic_work(B, a.dtype == "bf16")
+        work = algorithmic_work(B, a.dtype == "bf16") if a.preset == "default" else {}
         per_step = {k: v[1] / nst for k, v in rows.items()}
         # the dominant kernel = the library kernel with the largest time per step among those with a stated roofline
         top = max((k for k in per_step if k in work), key=per_step.get, default=max(per_step, key=per_step.get))
@@ -719,10 +727,11 @@ def run_ours(a):
         line = {"metric": "audio-seconds/sec", "value": sec / (ms / a.steps * 1e-3), "unit": "audio-s/s", "n_gpus": world,
                 "steps": a.steps, "warmup": W_, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-                "config": {"workload": ("BASELINE config 2: CPC default (hiddenEncoder=256, 1-layer GRU, K=12, 128 negatives) "
+                "config": {"workload": ("BASELINE config 5: hiddenEncoder=512, hiddenGar=512, nLevelsGRU=2, K=16, 256 negatives " if a.preset == "config5" else
+                                        "BASELINE config 2: CPC default (hiddenEncoder=256, 1-layer GRU, K=12, 128 negatives) "
                                         if a.heads == "linear" else
                                         "BASELINE config 4: --rnnMode transformer prediction heads (train mode, dropout 0.1), GRU context net, K=12, 128 negatives ")
-                                       + f"batch={B}/GPU seq=20480, white-noise 16 kHz windows, random-init weights",
+                                       + f"batch={B}/GPU seq={WINDOW}, white-noise 16 kHz windows, random-init weights",
                            "global_batch": B * world, "seq_len": WINDOW, "parallelism": f"dp{world}", "optimizer": a.optimizer, "launch": launch_mode,
                            "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                                  ("peer-memory all-reduce of the early gradients on a side stream during the backward tail "

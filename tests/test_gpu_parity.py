@@ -667,3 +667,42 @@ def test_bucket_survives_default_zero_grad_of_torch_adam(built_lib):
     for p, q in zip(params, ref_params):
         assert Hh.rel_err(p, q) <= 1e-5
     bucket.detach()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node")
+def test_dataparallel_two_devices_in_process(built_lib):
+    """cpc/train.py:372-375 with nGPU = 2: torch.nn.DataParallel replicates the modules and runs the replicas in two host
+    threads, each bound to its own device (the C ABI must be callable concurrently).  The gradients on the
+    master parameters must equal the SUM over the two halves computed one after the other (cpc/train.py:85 sums the
+    gathered per-replica losses), with each replica drawing its negatives from its own device generator."""
+    d = O.Dims(B=6, L=20480, H=256, Har=256, K=12, N=128, nLayers=1)
+    mp, cp = O.make_params(d, seed=33, pred_scale=30.0)
+    x, label = O.make_batch(d, seed=34)
+    model, crit = Hh.build_modules(d, mp, cp, "f32", device="cuda:0")
+    dp_model = torch.nn.DataParallel(model, device_ids=[0, 1])
+    dp_crit = torch.nn.DataParallel(crit, device_ids=[0, 1])
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            torch.cuda.manual_seed(100 + dev)
+    c, z, lab = dp_model(x.cuda(0), label.cuda(0))
+    losses, acc = dp_crit(c, z, lab)
+    assert losses.shape == (2, d.K) and acc.shape == (2, d.K)   # one row per replica, as train.py:85-99 expects
+    losses.sum().backward()
+    got = {**{f"model.{k}": v.grad.clone() for k, v in model.named_parameters()},
+           **{f"crit.{k}": v.grad.clone() for k, v in crit.named_parameters()}}
+    # the same two halves, sequentially, each on the device (and generator) its replica used
+    want = None
+    per_replica_losses = []
+    for dev, sl in ((0, slice(0, 3)), (1, slice(3, 6))):
+        m2, c2 = Hh.build_modules(d, mp, cp, "f32", device=f"cuda:{dev}")
+        with torch.cuda.device(dev):
+            torch.cuda.manual_seed(100 + dev)
+            cc, zz, _ = m2(x[sl].cuda(dev), label[sl].cuda(dev))
+            ll, _ = c2(cc, zz, label[sl].cuda(dev))
+            ll.sum().backward()
+        per_replica_losses.append(ll.detach().cpu())
+        g = {**{f"model.{k}": v.grad.cpu() for k, v in m2.named_parameters()}, **{f"crit.{k}": v.grad.cpu() for k, v in c2.named_parameters()}}
+        want = g if want is None else {k: want[k] + g[k] for k in g}
+    assert (losses.detach().cpu() - torch.cat(per_replica_losses)).abs().max().item() <= 1e-5
+    for k, v in want.items():
+        assert Hh.rel_err(got[k], v) <= 2e-5, (k, Hh.rel_err(got[k], v))
