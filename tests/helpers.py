@@ -161,16 +161,19 @@ def grad_report(out_grads, ref_grads):
 
 def bf16_cos_floor(name, d):
     """Lower bound on the cosine between a bf16-path gradient and the fp32 oracle's, per parameter tensor.  The bounds are
-    the values MEASURED on B200 in round 2 (profiles/parity_r2.json) with head-room, not wishes:
+    the minima MEASURED on B200 in round 2 over all cases of a category (profiles/parity_r2.json) with head-room, not wishes:
 
-      * context network, linear prediction heads: >= 0.9997 measured at every shape            -> 0.999
-      * encoder tensors at the benchmarked shape (B = 64): >= 0.9996 measured                   -> 0.999
-        except gEncoder.conv0.weight: 0.9974 measured                                            -> 0.995
+      category                                                               measured minimum      bound
+      context network + linear heads, benchmarked shape (B = 64)             0.99987              0.999
+      encoder tensors, benchmarked shape (B = 64)                             0.99964              0.999
+        except gEncoder.conv0.weight                                          0.9974               0.995
         (white-noise input: dW0 is the small residual of a 262 144-term random-sign sum; the bf16 storage of dy0 puts
         0.4 % of noise on every term, ~7 % on the residual - a property of the synthetic input, not of the kernels)
-      * encoder tensors at B <= 9 (the sums are 7-32x shorter): 0.992 - 0.998 measured           -> 0.985
-      * transformer-layer parameters (heads / context net, W x W attention in bf16): >= 0.997   -> 0.99
-      * toy widths (H < 256: 64 / 128 channels, the fixtures `small*`): >= 0.99 measured         -> 0.95
+      context network + linear heads, B = 2..9 (reference-init heads: every
+        logit ~ 0, the gradients themselves are residuals)                     0.9977               0.995
+      encoder tensors, B = 2..9 (sums 7-32x shorter than at B = 64)           0.9920               0.985
+      transformer-layer parameters (heads / context net)                      0.9973               0.99
+      toy widths (H < 256: the fixtures `small*`)                             0.9913               0.95
     """
     if d.H < 256:
         return 0.95
@@ -180,4 +183,4 @@ def bf16_cos_floor(name, d):
         return 0.985
     if ".multihead." in name or ".ffnetwork." in name or ".ln_" in name:
         return 0.99
-    return 0.999
+    return 0.999 if d.B >= 32 else 0.995
