@@ -21,6 +21,12 @@ template <class T> int launch_cast(const float* src, T* dst, long long n, cudaSt
 template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st, int nb = 1);
 template <class T> int launch_colsum(const T* src, float* out, long long M, int N, cudaStream_t st);
 
+bool attn_mma_supported(int W, int D, int nh);
+int attn_fwd_mma(const bf16* qkv, const float* krel, bf16* att, int B, int W, int D, int nh, const unsigned char* keep, float dscale,
+                 cudaStream_t st);
+int attn_bwd_mma(const bf16* qkv, const bf16* datt, const bf16* att, const float* krel, bf16* dqkv, float* dkrel, int B, int W, int D,
+                 int nh, const unsigned char* keep, float dscale, cudaStream_t st);
+
 namespace {
 
 constexpr float kLnEps = 1e-5f;
@@ -445,6 +451,9 @@ template <class T>
 int launch_attn_fwd(const T* qkv, const float* krel, T* att, int B, int W, int D, int nh, const unsigned char* keep, float dscale,
                     cudaStream_t st) {
   const int DK = D / nh;
+  if constexpr (sizeof(T) == 2) {  // bf16 path, dk = 32: tensor-core attention (attn_mma.cu)
+    if (attn_mma_supported(W, D, nh)) return attn_fwd_mma(qkv, krel, att, B, W, D, nh, keep, dscale, st);
+  }
   const size_t smem = attn_fwd_smem<T>(W, DK);
   dim3 grid(nh, B);
 #define AF(DKV)                                                                                                   \
@@ -459,9 +468,12 @@ int launch_attn_fwd(const T* qkv, const float* krel, T* att, int B, int W, int D
   return 0;
 }
 template <class T>
-int launch_attn_bwd(const T* qkv, const T* datt, const float* krel, T* dqkv, float* dkrel, int B, int W, int D, int nh,
+int launch_attn_bwd(const T* qkv, const T* datt, const T* att, const float* krel, T* dqkv, float* dkrel, int B, int W, int D, int nh,
                     const unsigned char* keep, float dscale, cudaStream_t st) {
   const int DK = D / nh;
+  if constexpr (sizeof(T) == 2) {
+    if (attn_mma_supported(W, D, nh)) return attn_bwd_mma(qkv, datt, att, krel, dqkv, dkrel, B, W, D, nh, keep, dscale, st);
+  }
   const size_t smem = attn_bwd_smem<T>(W, DK);
   dim3 grid(nh, B);
 #define AB(DKV)                                                                                                   \
@@ -721,7 +733,7 @@ int thead_bwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, const T
       OutView C{datt, 0, (long long)D, P, 0, P, 0};
       CPC_TRY(gemm_nt(g.bf16, false, 1, D, D, A, woT, nullptr, C, st));
     }
-    CPC_TRY(launch_attn_bwd<T>(qkv, datt, tp->krelpos + (size_t)k * DK * W, dqkv, gr->krelpos + (size_t)k * DK * W, B, W, D, nh,
+    CPC_TRY(launch_attn_bwd<T>(qkv, datt, att, tp->krelpos + (size_t)k * DK * W, dqkv, gr->krelpos + (size_t)k * DK * W, B, W, D, nh,
                                drop ? tp->att_keep + (size_t)k * B * nh * W * W : nullptr, tp->keep_scale, st));
     {  // Wq, Wk, Wv and d(x)
       float* dw3[3] = {gr->wq + oDD, gr->wk + oDD, gr->wv + oDD};
