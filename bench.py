@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--heads", default="linear", choices=["linear", "transformer"],
                     help="prediction heads: 'linear' = BASELINE config 2/3 (default), 'transformer' = config 4 (eval-mode heads)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="windows per step of the CPU baseline sample")
+    ap.add_argument("--ar", default="GRU", choices=["GRU", "LSTM", "transformer"],
+                    help="context network (--arMode of cpc/train.py; the reference default is LSTM, BASELINE configs use the GRU)")
     ap.add_argument("--preset", default="default", choices=["default", "config5"],
                     help="'config5' = BASELINE config 5 (hiddenEncoder = hiddenGar = 512, 2-level GRU, K = 16, 256 negatives, "
                          "81920-sample windows; use --batch 8); its per-kernel rooflines are not tabulated")
@@ -464,8 +466,11 @@ def run_ours(a):
         HID, NLEV, KP, NNEG, WINDOW = 512, 2, 16, 256, 81920
         a.no_train_py = a.no_torch_gpu = a.no_cpu_baseline = True
     torch.manual_seed(0)  # identical initial parameters on every rank (replicas)
-    model = M.CPCModel(M.CPCEncoder(HID, "layerNorm", compute_dtype=a.dtype),
-                       M.CPCAR(HID, HID, False, NLEV, mode="GRU", reverse=False, compute_dtype=a.dtype)).to(dev)
+    arnet = (M.buildTransformerAR(HID, 1, WINDOW // 160, False, compute_dtype=a.dtype) if a.ar == "transformer" else
+             M.CPCAR(HID, HID, False, NLEV, mode=a.ar, reverse=False, compute_dtype=a.dtype))
+    model = M.CPCModel(M.CPCEncoder(HID, "layerNorm", compute_dtype=a.dtype), arnet).to(dev)
+    if a.ar != "GRU":
+        a.no_train_py = a.no_torch_gpu = True
     crit = M.CPCUnsupersivedCriterion(KP, HID, HID, NNEG, mode=None, rnnMode=a.heads, dropout=False, speakerEmbedding=0,
                                       nSpeakers=0, sizeInputSeq=WINDOW // 160, compute_dtype=a.dtype).to(dev)
     model.train()
@@ -731,6 +736,7 @@ def run_ours(a):
                                         "BASELINE config 2: CPC default (hiddenEncoder=256, 1-layer GRU, K=12, 128 negatives) "
                                         if a.heads == "linear" else
                                         "BASELINE config 4: --rnnMode transformer prediction heads (train mode, dropout 0.1), GRU context net, K=12, 128 negatives ")
+                                       + (f"[context network: {a.ar}] " if a.ar != "GRU" else "")
                                        + f"batch={B}/GPU seq={WINDOW}, white-noise 16 kHz windows, random-init weights",
                            "global_batch": B * world, "seq_len": WINDOW, "parallelism": f"dp{world}", "optimizer": a.optimizer, "launch": launch_mode,
                            "gradient_exchange": ("none (1 GPU)" if world == 1 else

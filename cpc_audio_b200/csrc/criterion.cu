@@ -137,13 +137,13 @@ __global__ void mean_over_positions_kernel(const float* __restrict__ a, const fl
                                            float* __restrict__ ob, int P, int K) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float s1[256], s2[256];
+  __shared__ float s1[1024], s2[1024];  // 1024 threads: the strided column reads are latency-bound (7 trips instead of 29)
   const int k = blockIdx.x;
   float x = 0.f, y = 0.f;
-  for (int p = threadIdx.x; p < P; p += 256) { x += a[(size_t)p * K + k]; y += bq[(size_t)p * K + k]; }
+  for (int p = threadIdx.x; p < P; p += 1024) { x += a[(size_t)p * K + k]; y += bq[(size_t)p * K + k]; }
   s1[threadIdx.x] = x; s2[threadIdx.x] = y;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = 512; o > 0; o >>= 1) {
     if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
     __syncthreads();
   }
@@ -284,7 +284,7 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
       int* ext_t = reinterpret_cast<int*>(sv + lay.ext_t);
       CPC_TRY(score_transpose_ext(ext, ext_t, B, N, W, st));
       CPC_TRY(score_fwd_mma(pred, zp, ext_t, lossbuf, corrbuf, lse, B, S, W, H, K, N, st));
-      CPC_CHECK_CUDA(launch_k(mean_over_positions_kernel, dim3(K), dim3(256), 0, st, 1, lossbuf, corrbuf, losses, acc, P, K));
+      CPC_CHECK_CUDA(launch_k(mean_over_positions_kernel, dim3(K), dim3(1024), 0, st, 1, lossbuf, corrbuf, losses, acc, P, K));
       CPC_LAUNCHED_N("mean_over_positions", st);
       return 0;
     }
@@ -296,7 +296,7 @@ int criterion_fwd_t(const Geo& g, const float* c, const float* z, const float* w
   CPC_CHECK_CUDA(cudaFuncSetAttribute(score_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_fwd_kernel<T><<<P, threads, smem, st>>>(pred, zp, ext, logits, lossbuf, corrbuf, B, S, W, H, K, N);
   CPC_LAUNCHED_N("score_fwd", st);
-  mean_over_positions_kernel<<<K, 256, 0, st>>>(lossbuf, corrbuf, losses, acc, P, K);
+  mean_over_positions_kernel<<<K, 1024, 0, st>>>(lossbuf, corrbuf, losses, acc, P, K);
   CPC_LAUNCHED_N("mean_over_positions", st);
   return 0;
 }
