@@ -21,6 +21,11 @@ int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowVie
 bool gru_mma_supported(int Har);
 int gru_rec_fwd_mma(const bf16* gi, const float* w_hh, const float* b_hh, const float* h0, float* c, bf16* cT, bf16* sR, bf16* sU,
                     bf16* sN, bf16* sHN, float* hT, int B, int S, int Har, cudaStream_t st);
+bool lstm_mma_supported(int Har);
+int lstm_rec_fwd_mma(const bf16* gi, const float* w_hh, const float* b_hh, const float* h0, const float* c0, float* out, bf16* outT,
+                     void* gates4, float* cell, float* hT, float* cT, int B, int S, int Har, cudaStream_t st);
+int lstm_rec_bwd_mma(const float* dout, const float* c0, const void* gates4, const float* cell, const float* w_hh, bf16* dg,
+                     float* db_ih, float* db_hh, int B, int S, int Har, cudaStream_t st);
 int gru_rec_bwd_mma(const float* dc, const float* c, const float* h0, const bf16* sR, const bf16* sU, const bf16* sN,
                     const bf16* sHN, const float* w_hh, bf16* dgi, bf16* dgh, float* dh0, float* db_ih, float* db_hh, int B, int S,
                     int Har, cudaStream_t st);
@@ -821,6 +826,14 @@ int lstm_fwd_t(const Geo& g, const float* z, const float* h0, const float* c0, c
     const float* bhh = p->b_hh[l];
     int Bv = B, Sv = S, Hv = Har;
     void* args[] = {&gic, &whh, &bhh, &h0l, &c0l, &o_f, &o_t, &sI, &sF, &sG, &sO, &cellp, &hTl, &cTl, &Bv, &Sv, &Hv};
+    if constexpr (!isf) {
+      if (lstm_mma_supported(Har)) {  // tensor-core recurrence; the four gate arrays are one array of bf16 quadruples there
+        CPC_TRY(lstm_rec_fwd_mma(gic, whh, bhh, h0l, c0l, o_f, o_t, sI, cellp, hTl, cTl, B, S, Har, st));
+        in_f = o_f;
+        in_t = o_t;
+        continue;
+      }
+    }
     CPC_TRY(launch_cluster("lstm_rec_fwd", lstm_rec_fwd_kernel<WT, T, kBT>, cs, (B + kBT - 1) / kBT, 4 * LHC * 2, smem, st, args));
     in_f = o_f;
     in_t = o_t;
@@ -866,10 +879,19 @@ int lstm_bwd_t(const Geo& g, const float* z, const float* h0, const float* c0, c
     const float* whh = p->w_hh[l];
     int Bv = B, Sv = S, Hv = Har;
     void* args[] = {&dl, &c0l, &sI, &sF, &sG, &sO, &cellp, &whh, &dg, &Bv, &Sv, &Hv};
-    CPC_TRY(launch_cluster("lstm_rec_bwd", lstm_rec_bwd_kernel<WT, T, kBT>, cs, (B + kBT - 1) / kBT, LHC * 8, smem, st, args));
-    // both bias vectors enter every pre-activation with coefficient 1: the same column sums
-    CPC_TRY(launch_colsum<T>(dg, gr->b_ih[l], (long long)B * S, G, st));
-    CPC_TRY(launch_colsum<T>(dg, gr->b_hh[l], (long long)B * S, G, st));
+    bool done = false;
+    if constexpr (!isf) {
+      if (lstm_mma_supported(Har)) {
+        CPC_TRY(lstm_rec_bwd_mma(dl, c0l, sI, cellp, whh, dg, gr->b_ih[l], gr->b_hh[l], B, S, Har, st));
+        done = true;
+      }
+    }
+    if (!done) {
+      CPC_TRY(launch_cluster("lstm_rec_bwd", lstm_rec_bwd_kernel<WT, T, kBT>, cs, (B + kBT - 1) / kBT, LHC * 8, smem, st, args));
+      // both bias vectors enter every pre-activation with coefficient 1: the same column sums
+      CPC_TRY(launch_colsum<T>(dg, gr->b_ih[l], (long long)B * S, G, st));
+      CPC_TRY(launch_colsum<T>(dg, gr->b_hh[l], (long long)B * S, G, st));
+    }
     const T* in;
     const T* hseq;
     if (isf) {
