@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcpc_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "encoder.cu", "gru.cu", "criterion.cu", "score_mma.cu", "gru_mma.cu", "lstm_mma.cu", "conv0_mma.cu", "thead.cu", "feeder.cu", "attn_mma.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "encoder.cu", "gru.cu", "criterion.cu", "score_mma.cu", "gru_mma.cu", "gru_mma_wide.cu", "lstm_mma.cu", "conv0_mma.cu", "thead.cu", "feeder.cu", "attn_mma.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math=false", "-Xptxas", "-v"]

@@ -21,6 +21,12 @@ int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowVie
 bool gru_mma_supported(int Har);
 int gru_rec_fwd_mma(const bf16* gi, const float* w_hh, const float* b_hh, const float* h0, float* c, bf16* cT, bf16* sR, bf16* sU,
                     bf16* sN, bf16* sHN, float* hT, int B, int S, int Har, cudaStream_t st);
+bool gru_wide_supported(int Har);
+bool gru_wide_preferred(int Har);
+int gru_rec_fwd_wide(const bf16* gi, const float* w_hh, const float* b_hh, const float* h0, float* c, bf16* cT, bf16* sR,
+                     float* hT, int B, int S, int Har, cudaStream_t st);
+int gru_rec_bwd_wide(const float* dc, const float* c, const float* h0, const bf16* sR, const float* w_hh, bf16* dgi, bf16* dgh,
+                     float* dh0, float* db_ih, float* db_hh, int B, int S, int Har, cudaStream_t st);
 bool lstm_mma_supported(int Har);
 int lstm_rec_fwd_mma(const bf16* gi, const float* w_hh, const float* b_hh, const float* h0, const float* c0, float* out, bf16* outT,
                      void* gates4, float* cell, float* hT, float* cT, int B, int S, int Har, cudaStream_t st);
@@ -438,7 +444,11 @@ int gru_fwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     int Bv = B, Sv = S, Hv = Har;
     bool done = false;
     if constexpr (!isf) {
-      if (gru_mma_supported(Har) && ((size_t)B * S * Har * 2) % 256 == 0) {  // (gate arrays contiguous)  // tensor-core recurrence, W_hh slice resident in registers
+      const bool contiguous = ((size_t)B * S * Har * 2) % 256 == 0;  // the four gate arrays form one array of quadruples
+      if (contiguous && gru_wide_preferred(Har)) {  // 32 units per CTA: Har = 512 (config 5)
+        CPC_TRY(gru_rec_fwd_wide(gic, whh, bhh, h0l, cout, cTo, sR, hTl, B, S, Har, st));
+        done = true;
+      } else if (gru_mma_supported(Har) && contiguous) {  // tensor-core recurrence, W_hh slice resident in registers
         CPC_TRY(gru_rec_fwd_mma(gic, whh, bhh, h0l, cout, cTo, sR, sU, sN, sHN, hTl, B, S, Har, st));
         done = true;
       }
@@ -491,7 +501,11 @@ int gru_bwd_t(const Geo& g, const float* z, const float* h0, const cpcb200_gru_p
     int Bv = B, Sv = S, Hv = Har;
     bool done = false;
     if constexpr (!isf) {
-      if (gru_mma_supported(Har) && ((size_t)B * S * Har * 2) % 256 == 0) {  // (gate arrays contiguous)
+      const bool contiguous = ((size_t)B * S * Har * 2) % 256 == 0;
+      if (contiguous && gru_wide_preferred(Har)) {
+        CPC_TRY(gru_rec_bwd_wide(dcl, cl, h0l, sR, whh, dgi, dgh, dh0, gr->b_ih[l], gr->b_hh[l], B, S, Har, st));
+        done = true;
+      } else if (gru_mma_supported(Har) && contiguous) {
         CPC_TRY(gru_rec_bwd_mma(dcl, cl, h0l, sR, sU, sN, sHN, whh, dgi, dgh, dh0, gr->b_ih[l], gr->b_hh[l], B, S, Har, st));
         done = true;
       }

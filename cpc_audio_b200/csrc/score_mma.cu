@@ -23,8 +23,14 @@ namespace {
 
 constexpr int CH = 16;    // candidate rows per gather chunk (CH/16 m-tiles); small chunks -> more warps per SM
 constexpr int MPC = CH / 16;
-constexpr int NNEG = 8;   // negative chunks per position: the tensor-core path is specialised for N = NNEG*CH = 128
-constexpr int NMT = NNEG * MPC;  // m-tiles of negatives; m-tile NMT holds the positives
+// Template parameters of both kernels:
+//   H     feature columns one WARP covers (64 / 128 / 256)
+//   SPLIT warps per anchor position: 1, or 2 for feature dim 2*H = 512 (BASELINE config 5) - the two warps of a pair own the
+//         low / high half of every row (their share of the contraction for the logits, their columns of dz and dpred) and swap
+//         the 16 x 16 partial logits of every chunk through shared memory (one 64-thread named barrier per chunk)
+//   NNEG  negative chunks per position: N = NNEG * CH negatives (8 -> 128, 16 -> 256)
+constexpr int XCH = 2 * 8 * 32 * 4;  // bytes of the double-buffered partial-logit tile of one warp (SPLIT = 2)
+__device__ __forceinline__ void pair_bar(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -86,31 +92,32 @@ template <int H> struct Cfg {
 };
 
 // stage pred[p] (K x H bf16, contiguous) into psm[16][RS]; rows >= K stay zero
+// (ld = elements between rows in global memory: H, or 2*H when a warp pair splits the row)
 template <int H>
-__device__ __forceinline__ void stage_pred(unsigned char* psm, const bf16* __restrict__ pp, int K, int lane) {
+__device__ __forceinline__ void stage_pred(unsigned char* psm, const bf16* __restrict__ pp, int K, int lane, int ld) {
   constexpr int SEGS = Cfg<H>::SEGS, RS = Cfg<H>::RS;
   for (int i = lane; i < K * SEGS; i += 32) {
     const int k = i / SEGS, sg = i - k * SEGS;
-    cp_async16(s_u32(psm + k * RS + sg * 16), pp + (size_t)k * H + sg * 8);
+    cp_async16(s_u32(psm + k * RS + sg * 16), pp + (size_t)k * ld + sg * 8);
   }
 }
 // gather `rows` candidate rows (row index held by lane r) into buf
 template <int H>
-__device__ __forceinline__ void gather_rows(unsigned char* buf, const bf16* __restrict__ z, int my_row, int rows, int lane) {
+__device__ __forceinline__ void gather_rows(unsigned char* buf, const bf16* __restrict__ z, int my_row, int rows, int lane, int ld) {
   constexpr int SEGS = Cfg<H>::SEGS, RS = Cfg<H>::RS;
 #pragma unroll 4
   for (int it = 0; it < (CH * SEGS) / 32; it++) {
     const int flat = it * 32 + lane;
     const int r = flat / SEGS, sg = flat - r * SEGS;
     const int row = __shfl_sync(0xffffffffu, my_row, r);
-    if (r < rows) cp_async16(s_u32(buf + r * RS + sg * 16), z + (size_t)row * H + sg * 8);
+    if (r < rows) cp_async16(s_u32(buf + r * RS + sg * 16), z + (size_t)row * ld + sg * 8);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-template <int H>
+template <int H, int SPLIT, int NNEG>
 __global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
                                                              const int* __restrict__ ext_t, float* __restrict__ lossbuf,
                                                              float* __restrict__ corrbuf, float* __restrict__ lsebuf, int B,
@@ -118,24 +125,34 @@ __global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restri
   pdl_wait();
   pdl_trigger();
   using C = Cfg<H>;
+  constexpr int NMT = NNEG * MPC;  // m-tiles of negatives; m-tile NMT holds the positives
+  constexpr int HT = H * SPLIT;    // the feature dim
+  constexpr int PER_WARP = C::PSM + 2 * C::CBUF + (SPLIT == 2 ? XCH : 0);
   extern __shared__ __align__(128) unsigned char sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  unsigned char* psm = sm + (size_t)warp * (C::PSM + 2 * C::CBUF);
+  const int half = SPLIT == 2 ? (warp & 1) : 0, slot = warp / SPLIT, apc = warps_per_cta / SPLIT;
+  unsigned char* psm = sm + (size_t)warp * PER_WARP;
   unsigned char* cbuf = psm + C::PSM;
+  float* xmine = reinterpret_cast<float*>(cbuf + 2 * C::CBUF);
+  const float* xpeer = reinterpret_cast<const float*>(sm + (size_t)(warp ^ 1) * PER_WARP + C::PSM + 2 * C::CBUF);
   for (int i = lane; i < C::PSM / 16; i += 32) reinterpret_cast<uint4*>(psm)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
   const int P = B * W;
   constexpr int nneg = NNEG;
   constexpr int nchunks = nneg + 1;
-  const float invH = 1.f / (float)H;
-
-  for (int p = blockIdx.x * warps_per_cta + warp; p < P; p += gridDim.x * warps_per_cta) {
+  const float invH = 1.f / (float)HT;
+  const bf16* zh = z + half * H;
+  // (a pair walks the positions together: its two warps meet at a named barrier in every chunk.  The exchange tile is double
+  // buffered over ALL chunks of the walk - the chunk count per position is odd, xph carries the parity across positions -
+  // so that a buffer is rewritten only after a barrier that follows the partner's read of it)
+  int xph = 0;
+  for (int p = blockIdx.x * apc + slot; p < P; p += gridDim.x * apc, xph ^= (nchunks & 1)) {
     const int b = p / W, w = p - b * W;
-    stage_pred<H>(psm, pred + (size_t)p * K * H, K, lane);
+    stage_pred<H>(psm, pred + (size_t)p * K * HT + half * H, K, lane, HT);
     {
       const int row = lane < CH ? ext_t[(size_t)p * N + lane] : 0;
-      gather_rows<H>(cbuf, z, row, CH, lane);
+      gather_rows<H>(cbuf, zh, row, CH, lane, HT);
     }
     cp_async_commit();
     uint32_t bfr[C::KS][4];
@@ -155,10 +172,10 @@ __global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restri
           unsigned char* nxt = cbuf + ((c + 1) & 1) * C::CBUF;
           if (c + 1 < nneg) {
             const int row = lane < CH ? ext_t[(size_t)p * N + (c + 1) * CH + lane] : 0;
-            gather_rows<H>(nxt, z, row, CH, lane);
+            gather_rows<H>(nxt, zh, row, CH, lane, HT);
           } else {
             const int row = b * S + w + 1 + (lane < K ? lane : 0);
-            gather_rows<H>(nxt, z, row, K, lane);
+            gather_rows<H>(nxt, zh, row, K, lane, HT);
             for (int i = lane; i < (16 - K) * (C::RS / 16); i += 32)  // rows K..15 of the positive tile: zeros
               reinterpret_cast<uint4*>(nxt + K * C::RS)[i] = make_uint4(0, 0, 0, 0);
           }
@@ -192,6 +209,20 @@ __global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restri
             }
           }
         }
+        if constexpr (SPLIT == 2) {  // (MPC = 1) both warps of the pair end up with the full logits of the chunk
+          const int m = (c < nneg) ? c : NMT;
+          float* xo = xmine + ((c & 1) ^ xph) * 256;
+#pragma unroll
+          for (int n = 0; n < 2; n++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) xo[(n * 4 + e) * 32 + lane] = acc[m][n][e];
+          pair_bar(slot);
+          const float* xi = xpeer + ((c & 1) ^ xph) * 256;
+#pragma unroll
+          for (int n = 0; n < 2; n++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[m][n][e] += xi[(n * 4 + e) * 32 + lane];
+        }
         __syncwarp();
       }
     }
@@ -217,7 +248,7 @@ __global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restri
         sum += __shfl_xor_sync(0xffffffffu, sum, 8);
         sum += __shfl_xor_sync(0xffffffffu, sum, 16);
         sum += __expf(pos - M);
-        if (g == 0 && k < K) {
+        if (g == 0 && k < K && half == 0) {
           const float lse = M + __logf(sum);
           lossbuf[(size_t)p * K + k] = lse - pos;
           corrbuf[(size_t)p * K + k] = (pos >= mx) ? 1.f : 0.f;
@@ -235,7 +266,7 @@ __global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restri
 // 1 = red.global.add.v2.f32 straight from the accumulator fragments; 2 = red.global.add.v4.f32 after a lane-pair swap.
 // Both reach the same L2 reduction ceiling (tools/redbench: 5.4 TB/s); without the 16 KB staging tile a warp needs
 // 26 KB of shared memory instead of 42 KB, so 8 warps fit on an SM instead of 5.
-template <int H, int RED>
+template <int H, int RED, int SPLIT, int NNEG>
 __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
                                                             const int* __restrict__ ext_t, const float* __restrict__ lsebuf,
                                                             const float* __restrict__ dloss, bf16* __restrict__ dpred,
@@ -248,28 +279,34 @@ __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(con
   constexpr int SRS = H * 4 + 32;                 // staging row stride: 32 B pad -> the 8-byte fragment stores of the 8 row
                                                   // groups fall into distinct banks (an unpadded 1 KB stride is an 8-way conflict)
   constexpr int STG = RED == 0 ? 16 * SRS : 0;    // staging tile [16 rows][H] fp32
-  constexpr int PER_WARP = C::PSM + 2 * C::CBUF + 16 * GRS + STG;
+  constexpr int HT = H * SPLIT;
+  constexpr int PER_WARP = C::PSM + 2 * C::CBUF + 16 * GRS + STG + (SPLIT == 2 ? XCH : 0);
   extern __shared__ __align__(128) unsigned char sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const int half = SPLIT == 2 ? (warp & 1) : 0, slot = warp / SPLIT, apc = warps_per_cta / SPLIT;
   unsigned char* psm = sm + (size_t)warp * PER_WARP;
   unsigned char* cbuf = psm + C::PSM;
   unsigned char* gs = cbuf + 2 * C::CBUF;
   unsigned char* stg = gs + 16 * GRS;
+  float* xmine = reinterpret_cast<float*>(stg + STG);
+  const float* xpeer = reinterpret_cast<const float*>(sm + (size_t)(warp ^ 1) * PER_WARP + C::PSM + 2 * C::CBUF + 16 * GRS + STG);
   for (int i = lane; i < C::PSM / 16; i += 32) reinterpret_cast<uint4*>(psm)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
   const int P = B * W;
   constexpr int nneg = NNEG;
   constexpr int nchunks = nneg + 1;
-  const float invH = 1.f / (float)H;
-  const float gscale = 1.f / ((float)P * (float)H);
+  const float invH = 1.f / (float)HT;
+  const float gscale = 1.f / ((float)P * (float)HT);
+  const bf16* zh = z + half * H;
+  float* dzh = dz + half * H;
 
   // negative-sample rows of a position: lane l holds ext_t[p][32 j + l], j = 0..3 (N = 128); those of the NEXT position are
   // fetched while the current one is processed, so no index load sits in front of a gather
-  const int pstride = gridDim.x * warps_per_cta;
+  const int pstride = gridDim.x * apc;
   int nidx[NNEG * CH / 32];
   {
-    const int p0 = blockIdx.x * warps_per_cta + warp;
+    const int p0 = blockIdx.x * apc + slot;
 #pragma unroll
     for (int j = 0; j < NNEG * CH / 32; j++) nidx[j] = p0 < P ? ext_t[(size_t)p0 * N + 32 * j + lane] : 0;
   }
@@ -281,9 +318,10 @@ __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(con
     return __shfl_sync(0xffffffffu, v, ((c * CH) & 31) + (lane & (CH - 1)));
   };
 
-  for (int p = blockIdx.x * warps_per_cta + warp; p < P; p += pstride) {
+  int xph = 0;  // parity of the exchange buffer across positions (see the forward kernel)
+  for (int p = blockIdx.x * apc + slot; p < P; p += pstride, xph ^= (nchunks & 1)) {
     const int b = p / W, w = p - b * W;
-    stage_pred<H>(psm, pred + (size_t)p * K * H, K, lane);
+    stage_pred<H>(psm, pred + (size_t)p * K * HT + half * H, K, lane, HT);
     int cidx[NNEG * CH / 32];
 #pragma unroll
     for (int j = 0; j < NNEG * CH / 32; j++) cidx[j] = nidx[j];
@@ -292,7 +330,7 @@ __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(con
       for (int j = 0; j < NNEG * CH / 32; j++) nidx[j] = ext_t[(size_t)(p + pstride) * N + 32 * j + lane];
     }
     int my_row = chunk_rows(cidx, 0);
-    gather_rows<H>(cbuf, z, my_row, CH, lane);
+    gather_rows<H>(cbuf, zh, my_row, CH, lane, HT);
     cp_async_commit();
     float lse[2][2], gk[2][2];
 #pragma unroll
@@ -316,10 +354,10 @@ __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(con
         unsigned char* nxt = cbuf + ((c + 1) & 1) * C::CBUF;
         if (c + 1 < nneg) {
           my_row = chunk_rows(cidx, c + 1);
-          gather_rows<H>(nxt, z, my_row, CH, lane);
+          gather_rows<H>(nxt, zh, my_row, CH, lane, HT);
         } else {
           my_row = b * S + w + 1 + (lane < K ? lane : 0);
-          gather_rows<H>(nxt, z, my_row, K, lane);
+          gather_rows<H>(nxt, zh, my_row, K, lane, HT);
           for (int i = lane; i < (16 - K) * (C::RS / 16); i += 32)
             reinterpret_cast<uint4*>(nxt + K * C::RS)[i] = make_uint4(0, 0, 0, 0);
         }
@@ -364,6 +402,19 @@ __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(con
         for (int n = 0; n < 2; n++)
 #pragma unroll
           for (int e = 0; e < 4; e++) L[mt][n][e] += L2[mt][n][e];
+      if constexpr (SPLIT == 2) {  // (MPC = 1) the other half of the contraction comes from the partner warp
+        float* xo = xmine + ((c & 1) ^ xph) * 256;
+#pragma unroll
+        for (int n = 0; n < 2; n++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) xo[(n * 4 + e) * 32 + lane] = L[0][n][e];
+        pair_bar(slot);
+        const float* xi = xpeer + ((c & 1) ^ xph) * 256;
+#pragma unroll
+        for (int n = 0; n < 2; n++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) L[0][n][e] += xi[(n * 4 + e) * 32 + lane];
+      }
       // ---- G = (softmax - onehot) * dloss / (P*H); A fragments for dz and Gs[k][j] for dpred ----
       uint32_t ga[MPC][4];
 #pragma unroll
@@ -421,7 +472,7 @@ __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(con
             __syncwarp();
             const int drow = __shfl_sync(0xffffffffu, cur_row, (mt * 16 + lane) & 31);
             if (lane < 16 && (!is_pos || lane < K)) {
-              bulk_reduce_add_f32(dz + (size_t)drow * H, s_u32(stg + (size_t)lane * SRS), H * 4);
+              bulk_reduce_add_f32(dzh + (size_t)drow * HT, s_u32(stg + (size_t)lane * SRS), H * 4);
               bulk_commit();
             }
           } else {
@@ -429,8 +480,8 @@ __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(con
             const int row_lo = __shfl_sync(0xffffffffu, cur_row, mt * 16 + g);
             const int row_hi = __shfl_sync(0xffffffffu, cur_row, mt * 16 + g + 8);
             const bool ok_lo = !is_pos || g < K, ok_hi = !is_pos || g + 8 < K;
-            float* d_lo = dz + (size_t)row_lo * H;
-            float* d_hi = dz + (size_t)row_hi * H;
+            float* d_lo = dzh + (size_t)row_lo * HT;
+            float* d_hi = dzh + (size_t)row_hi * HT;
 #pragma unroll 4
             for (int np = 0; np < C::KS; np++) {
               uint32_t bq[4];
@@ -476,57 +527,80 @@ __global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(con
       __syncwarp();
     }
     // ---- dpred[p][k][d] (bf16) ----
-    bf16* dp = dpred + (size_t)p * K * H;
+    bf16* dp = dpred + (size_t)p * K * HT + half * H;
 #pragma unroll
     for (int n = 0; n < 2 * C::KS; n++) {
       const int d = n * 8 + 2 * t;
-      if (g < K) *reinterpret_cast<uint32_t*>(dp + (size_t)g * H + d) = pack_bf16(d1[n][0], d1[n][1]);
-      if (g + 8 < K) *reinterpret_cast<uint32_t*>(dp + (size_t)(g + 8) * H + d) = pack_bf16(d1[n][2], d1[n][3]);
+      if (g < K) *reinterpret_cast<uint32_t*>(dp + (size_t)g * HT + d) = pack_bf16(d1[n][0], d1[n][1]);
+      if (g + 8 < K) *reinterpret_cast<uint32_t*>(dp + (size_t)(g + 8) * HT + d) = pack_bf16(d1[n][2], d1[n][3]);
     }
   }
   if (RED == 0 && lane < 16) bulk_wait0();
 }
 
-template <int H> constexpr size_t fwd_warp_smem() { return Cfg<H>::PSM + 2 * Cfg<H>::CBUF; }
-template <int H, int RED> constexpr size_t bwd_warp_smem() {
-  return Cfg<H>::PSM + 2 * Cfg<H>::CBUF + 16 * (CH + 8) * 2 + (RED == 0 ? 16 * (H * 4 + 32) : 0);
+template <int H, int SPLIT> constexpr size_t fwd_warp_smem() { return Cfg<H>::PSM + 2 * Cfg<H>::CBUF + (SPLIT == 2 ? XCH : 0); }
+template <int H, int RED, int SPLIT> constexpr size_t bwd_warp_smem() {
+  return Cfg<H>::PSM + 2 * Cfg<H>::CBUF + 16 * (CH + 8) * 2 + (RED == 0 ? 16 * (H * 4 + 32) : 0) + (SPLIT == 2 ? XCH : 0);
 }
 
-template <int H>
+template <int H, int SPLIT, int NNEG>
 int launch_fwd(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf, float* corrbuf, float* lsebuf, int B, int S,
                int W, int K, int N, cudaStream_t st) {
-  int wpc = (int)((216 * 1024) / fwd_warp_smem<H>());
+  int wpc = (int)((216 * 1024) / fwd_warp_smem<H, SPLIT>());
   if (wpc > 8) wpc = 8;
-  const size_t smem = wpc * fwd_warp_smem<H>();
-  CPC_CHECK_CUDA(cudaFuncSetAttribute(score_fwd_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CPC_CHECK_CUDA(launch_k(score_fwd_mma_kernel<H>, dim3(148), dim3(wpc * 32), smem, st, 1, pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, wpc));
+  wpc -= wpc % SPLIT;
+  const size_t smem = wpc * fwd_warp_smem<H, SPLIT>();
+  auto kern = score_fwd_mma_kernel<H, SPLIT, NNEG>;
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CPC_CHECK_CUDA(launch_k(kern, dim3(148), dim3(wpc * 32), smem, st, 1, pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, wpc));
   CPC_LAUNCHED_N("score_fwd_mma", st);
   return 0;
 }
-template <int H, int RED>
+template <int H, int RED, int SPLIT, int NNEG>
 int launch_bwd_red(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred, float* dz,
                    int B, int S, int W, int K, int N, cudaStream_t st) {
-  int wpc = (int)((216 * 1024) / bwd_warp_smem<H, RED>());
+  int wpc = (int)((216 * 1024) / bwd_warp_smem<H, RED, SPLIT>());
   const int cap = RED == 0 ? 5 : 8;
   if (wpc > cap) wpc = cap;
-  const size_t smem = wpc * bwd_warp_smem<H, RED>();
-  CPC_CHECK_CUDA(cudaFuncSetAttribute(score_bwd_mma_kernel<H, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CPC_CHECK_CUDA(launch_k(score_bwd_mma_kernel<H, RED>, dim3(148), dim3(wpc * 32), smem, st, 1, pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, wpc));
+  wpc -= wpc % SPLIT;
+  const size_t smem = wpc * bwd_warp_smem<H, RED, SPLIT>();
+  auto kern = score_bwd_mma_kernel<H, RED, SPLIT, NNEG>;
+  CPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CPC_CHECK_CUDA(launch_k(kern, dim3(148), dim3(wpc * 32), smem, st, 1, pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, wpc));
   CPC_LAUNCHED_N("score_bwd_mma", st);
   return 0;
 }
-template <int H>
+template <int H, int SPLIT, int NNEG>
 int launch_bwd(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred, float* dz,
                int B, int S, int W, int K, int N, cudaStream_t st) {
-  static const int red = []() { const char* e = getenv("CPC_B200_SCORE_RED"); return e ? atoi(e) : 0; }();
-  if (red == 0) return launch_bwd_red<H, 0>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
-  if (red == 1) return launch_bwd_red<H, 1>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
-  return launch_bwd_red<H, 2>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
+  if constexpr (SPLIT == 1 && NNEG == 8) {  // the alternative reduction paths exist for the default shape only (experiments)
+    static const int red = []() { const char* e = getenv("CPC_B200_SCORE_RED"); return e ? atoi(e) : 0; }();
+    if (red == 1) return launch_bwd_red<H, 1, SPLIT, NNEG>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
+    if (red == 2) return launch_bwd_red<H, 2, SPLIT, NNEG>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
+  }
+  return launch_bwd_red<H, 0, SPLIT, NNEG>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
 }
+
+// (feature dim, negatives) -> instantiation
+#define CPC_SCORE_DISPATCH(FN, ...)                                            \
+  do {                                                                         \
+    if (N == 8 * CH) {                                                         \
+      if (H == 512) return FN<256, 2, 8>(__VA_ARGS__);                         \
+      if (H == 256) return FN<256, 1, 8>(__VA_ARGS__);                         \
+      if (H == 128) return FN<128, 1, 8>(__VA_ARGS__);                         \
+      return FN<64, 1, 8>(__VA_ARGS__);                                        \
+    }                                                                          \
+    if (H == 512) return FN<256, 2, 16>(__VA_ARGS__);                          \
+    if (H == 256) return FN<256, 1, 16>(__VA_ARGS__);                          \
+    if (H == 128) return FN<128, 1, 16>(__VA_ARGS__);                          \
+    return FN<64, 1, 16>(__VA_ARGS__);                                         \
+  } while (0)
 
 }  // namespace
 
-bool score_mma_supported(int H, int K, int N) { return (H == 64 || H == 128 || H == 256) && K >= 1 && K <= 16 && N == NNEG * CH; }
+bool score_mma_supported(int H, int K, int N) {
+  return (H == 64 || H == 128 || H == 256 || H == 512) && K >= 1 && K <= 16 && (N == 8 * CH || N == 16 * CH);
+}
 
 int score_transpose_ext(const int* ext, int* ext_t, int B, int N, int W, cudaStream_t st) {
   const long long n = (long long)B * N * W;
@@ -539,15 +613,11 @@ int score_transpose_ext(const int* ext, int* ext_t, int B, int N, int W, cudaStr
 
 int score_fwd_mma(const bf16* pred, const bf16* z, const int* ext_t, float* lossbuf, float* corrbuf, float* lsebuf, int B, int S,
                   int W, int H, int K, int N, cudaStream_t st) {
-  if (H == 256) return launch_fwd<256>(pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, st);
-  if (H == 128) return launch_fwd<128>(pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, st);
-  return launch_fwd<64>(pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, st);
+  CPC_SCORE_DISPATCH(launch_fwd, pred, z, ext_t, lossbuf, corrbuf, lsebuf, B, S, W, K, N, st);
 }
 int score_bwd_mma(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred,
                   float* dz, int B, int S, int W, int H, int K, int N, cudaStream_t st) {
-  if (H == 256) return launch_bwd<256>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
-  if (H == 128) return launch_bwd<128>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
-  return launch_bwd<64>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
+  CPC_SCORE_DISPATCH(launch_bwd, pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
 }
 
 }  // namespace cpcb200
