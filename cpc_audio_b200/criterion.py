@@ -47,9 +47,10 @@ def draw_dropout_masks(n_layers, batch, seq, nheads, dff, p, device):
     ffn = torch.empty(n_layers, batch * seq, dff, dtype=torch.uint8, device=device)
     ones_a = torch.ones(batch * nheads, seq, seq, device=device)
     ones_f = torch.ones(batch, seq, dff, device=device)
-    for k in range(n_layers):
-        att[k] = torch.nn.functional.dropout(ones_a, p, True) != 0
-        ffn[k] = (torch.nn.functional.dropout(ones_f, p, True) != 0).view(batch * seq, dff)
+    ffn_v = ffn.view(n_layers, batch, seq, dff)
+    for k in range(n_layers):  # (the comparison writes straight into the stacked uint8 buffers: one kernel per draw, no copy)
+        torch.ne(torch.nn.functional.dropout(ones_a, p, True), 0, out=att[k])
+        torch.ne(torch.nn.functional.dropout(ones_f, p, True), 0, out=ffn_v[k])
     return att, ffn
 
 

@@ -147,7 +147,7 @@ int gemm_nt_simt(bool, bool, int, int, int, const RowView&, const void*, const f
 int gemm_tn_simt(bool, int, int, int, const RowView&, const RowView&, float*, int, int, int, int, cudaStream_t);
 int debug_gemm_timeline(unsigned long long* host_out);
 int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C,
-               cudaStream_t st, bool* handled);
+               cudaStream_t st, bool* handled, const HeadBatch* hb = nullptr);
 int gemm_tn_tc(int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode, int Ci, int taps,
                cudaStream_t st, bool* handled);
 
@@ -160,6 +160,15 @@ int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A,
     if (handled) return 0;
   }
   return gemm_nt_simt(bf16_in, out_f32, nb, N, Kd, A, Bm, bias, C, st);
+}
+int gemm_nt_heads(bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C,
+                  int a_mod, int w_div, cudaStream_t st) {
+  HeadBatch hb{};
+  hb.a_mod = a_mod; hb.w_div = w_div;
+  bool handled = false;
+  CPC_TRY(gemm_nt_tc(out_f32, nb, N, Kd, A, Bm, bias, C, st, &handled, &hb));
+  if (!handled) return fail(CPCB200_ERR_UNSUPPORTED, "gemm_nt_heads: N=%d Kd=%d does not fit the 128 x 256 tensor-core tiling", N, Kd);
+  return 0;
 }
 int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowView& B, float* Cacc, int ldc, int mode,
             int Ci, int taps, cudaStream_t st) {

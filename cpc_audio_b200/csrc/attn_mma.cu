@@ -116,7 +116,7 @@ __device__ __forceinline__ void qp_to_scratch(const uint32_t (&aq)[2][2][4], con
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, const float* __restrict__ krel,
                                                             bf16* __restrict__ att, int W, int D,
-                                                            const unsigned char* __restrict__ keep, float dscale) {
+                                                            const unsigned char* __restrict__ keep, float dscale, int bph) {
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
   bf16* Ks = Qs + WP * RS;
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const bf16* __restric
   const int h = blockIdx.x, b = blockIdx.y, nh = gridDim.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   fill_tiles(qkv, nullptr, Qs, Ks, Vs, nullptr, b, h, W, D, tid);
+  if (bph > 0) krel += (size_t)(b / bph) * DKC * W;  // blockIdx.y = (prediction head, window): stacked Krelpos
   fill_relpos(krel, Rs, W, tid);
   __syncthreads();
   const int r0 = 32 * warp;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const bf16* __restric
 __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ datt,
                                                             const bf16* __restrict__ att, const float* __restrict__ krel,
                                                             bf16* __restrict__ dqkv, float* __restrict__ dkrel, int W, int D,
-                                                            const unsigned char* __restrict__ keep, float dscale) {
+                                                            const unsigned char* __restrict__ keep, float dscale, int bph) {
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
   bf16* Ks = Qs + WP * RS;
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
   const int h = blockIdx.x, b = blockIdx.y, nh = gridDim.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   fill_tiles(qkv, datt, Qs, Ks, Vs, Gs, b, h, W, D, tid);
+  if (bph > 0) { krel += (size_t)(b / bph) * DKC * W; dkrel += (size_t)(b / bph) * DKC * W; }
   fill_relpos(krel, Rs, W, tid);
   for (int idx = tid; idx < WP * SS / 8; idx += 128) {
     reinterpret_cast<uint4*>(dSs)[idx] = make_uint4(0, 0, 0, 0);
@@ -555,17 +557,18 @@ bool attn_mma_supported(int W, int D, int nh) {
   return !off && W <= WP && D == nh * DKC && D % 8 == 0;
 }
 
+// bph > 0: B counts (prediction head, window) pairs, bph windows per head; krel / dkrel are the heads' stacked (dk, W) matrices
 int attn_fwd_mma(const bf16* qkv, const float* krel, bf16* att, int B, int W, int D, int nh, const unsigned char* keep, float dscale,
-                 cudaStream_t st) {
+                 cudaStream_t st, int bph) {
   CPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
-  attn_fwd_mma_kernel<<<dim3(nh, B), 128, kFwdSmem, st>>>(qkv, krel, att, W, D, keep, dscale);
+  attn_fwd_mma_kernel<<<dim3(nh, B), 128, kFwdSmem, st>>>(qkv, krel, att, W, D, keep, dscale, bph);
   CPC_LAUNCHED_N("attn_fwd_mma", st);
   return 0;
 }
 int attn_bwd_mma(const bf16* qkv, const bf16* datt, const bf16* att, const float* krel, bf16* dqkv, float* dkrel, int B, int W, int D,
-                 int nh, const unsigned char* keep, float dscale, cudaStream_t st) {
+                 int nh, const unsigned char* keep, float dscale, cudaStream_t st, int bph) {
   CPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-  attn_bwd_mma_kernel<<<dim3(nh, B), 128, kBwdSmem, st>>>(qkv, datt, att, krel, dqkv, dkrel, W, D, keep, dscale);
+  attn_bwd_mma_kernel<<<dim3(nh, B), 128, kBwdSmem, st>>>(qkv, datt, att, krel, dqkv, dkrel, W, D, keep, dscale, bph);
   CPC_LAUNCHED_N("attn_bwd_mma", st);
   return 0;
 }

@@ -264,6 +264,11 @@ struct CNormEpi {
 // out_f32: C is fp32, else C has the activation dtype.
 int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias,
             const OutView& C, cudaStream_t st);
+// Stacked per-head weights (bf16 tensor-core path only; anything else is CPCB200_ERR_UNSUPPORTED): Bm / bias hold nb / w_div
+// matrices of (N, Kd) / vectors of N, batch b multiplies matrix b / w_div with A batch b % a_mod (a_mod = 0: A batch b).
+struct HeadBatch { int a_mod = 0, w_div = 0, w_rows = 0; };
+int gemm_nt_heads(bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C,
+                  int a_mod, int w_div, cudaStream_t st);
 // bf16 tensor-core path only: u = A.B^T + bias -> C (bf16), ChannelNorm+ReLU(u) -> E.y / E.z.  *handled = false
 // when the shape does not fit (N != 256, ...): the caller then runs gemm_nt + the stand-alone norm kernel.
 int gemm_nt_cnorm_tc(int nb, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C, const CNormEpi& E,

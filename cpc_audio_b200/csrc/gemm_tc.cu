@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
                                                                      const __grid_constant__ CUtensorMap tmB, int nkb,
                                                                      int chunks_per_tap, int s, int tiles_per_batch,
                                                                      int m_tiles, int n_tiles, int nb,
-                                                                     const float* __restrict__ bias, OutView C, CNormEpi E) {
+                                                                     const float* __restrict__ bias, OutView C, CNormEpi E,
+                                                                     HeadBatch HB) {
   constexpr int BN2 = 256, STAGES = 4;
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN2 * BK * 2, B_SLICE = B_BYTES / CM;
   constexpr uint16_t MASK = (uint16_t)((1u << CM) - 1);
@@ -437,13 +438,15 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
         const int mt = gm * CM + rank;
         const int b = mt < m_tiles ? mt / tiles_per_batch : nb;  // b == nb: out of bounds -> zero fill
         const int t0 = (mt % tiles_per_batch) * BM;
-        const int n0 = gn * BN2;
+        // stacked per-head weights (HeadBatch): batch b reads A batch b % a_mod and weight rows (b / w_div) * w_rows + n
+        const int ba = (HB.a_mod > 0 && b < nb) ? b % HB.a_mod : (HB.a_mod > 0 ? HB.a_mod : b);
+        const int n0 = gn * BN2 + (HB.w_div > 0 ? ((b < nb ? b : nb - 1) / HB.w_div) * HB.w_rows : 0);
         int c0 = 0, chunk = 0, tph = 0, tgr = 0;  // channel offset inside the tap; tap = tgr * s + tph
         for (int kb = 0; kb < nkb; kb++, it++) {
           const int st = it % STAGES, u = it / STAGES;
           if (u > 0) ptx::mbar_wait(&empty[st], (u - 1) & 1);
           ptx::mbar_arrive_expect_tx(&full[st], A_BYTES + B_BYTES);
-          ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES, c0, tph, t0 + tgr, b);
+          ptx::tma_load_4d(&tmA, &full[st], smA + st * A_BYTES, c0, tph, t0 + tgr, ba);
           c0 += BK;
           if (++chunk == chunks_per_tap) { chunk = 0; c0 = 0; if (++tph == s) { tph = 0; tgr++; } }
           if (CM == 1) ptx::tma_load_4d(&tmB, &full[st], smB + st * B_BYTES, kb * BK, n0, 0, 0);
@@ -579,8 +582,9 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) gemm_nt_tc2_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[c & 1][j]);
           if (bias != nullptr) {
+            const float* bb = bias + (HB.w_div > 0 ? ((b < nb ? b : nb - 1) / HB.w_div) * HB.w_rows : 0);
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] += __ldg(bias + n0 + cc + j);
+            for (int j = 0; j < 32; j++) v[j] += __ldg(bb + n0 + cc + j);
           }
           if (C.relu) {
 #pragma unroll
@@ -606,7 +610,8 @@ constexpr size_t nt2_smem() { return (size_t)4 * (BM * BK * 2 + 256 * BK * 2) + 
 
 template <int CM, class TO, bool CN = false>
 int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt, int s, int tpb, int m_tiles, int n_tiles, int nb,
-               const float* bias, const OutView& C, cudaStream_t st, const CNormEpi& E = CNormEpi{}) {
+               const float* bias, const OutView& C, cudaStream_t st, const CNormEpi& E = CNormEpi{},
+               const HeadBatch& HB = HeadBatch{}) {
   auto k = gemm_nt_tc2_kernel<CM, TO, CN>;
   const size_t smem = nt2_smem();
   CPC_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -624,7 +629,7 @@ int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int nkb, int cpt,
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, tmA, tmB, nkb, cpt, s, tpb, m_tiles, n_tiles, nb, bias, C, E));
+  CPC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, tmA, tmB, nkb, cpt, s, tpb, m_tiles, n_tiles, nb, bias, C, E, HB));
   CPC_LAUNCHED_N(CN ? "gemm_nt_cnorm_tc2" : "gemm_nt_tc2", st);
   return 0;
 }
@@ -802,8 +807,11 @@ template <int BN, int STAGES> constexpr size_t tn_smem() { return (size_t)STAGES
 
 }  // namespace
 
+// hb != NULL: the weights (and the bias) are `heads` stacked (N, Kd) matrices, batch b multiplies matrix b / hb->w_div with
+// A batch b % hb->a_mod (a_mod = 0: A batch b) - the per-head products of the transformer prediction heads in ONE launch.
+// Second-generation kernel only; clusters never span two heads (CM drops to 1 when the tiles of a head are odd).
 int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void* Bm, const float* bias, const OutView& C,
-               cudaStream_t st, bool* handled) {
+               cudaStream_t st, bool* handled, const HeadBatch* hb) {
   *handled = false;
   constexpr int BN = 128, STAGES = 3;
   const int cin = Kd / A.taps;
@@ -811,26 +819,34 @@ int gemm_nt_tc(bool out_f32, int nb, int N, int Kd, const RowView& A, const void
   if ((A.rs % 8) != 0 || (A.bs % 8) != 0 || (reinterpret_cast<uintptr_t>(A.p) & 15) || (reinterpret_cast<uintptr_t>(Bm) & 15)) return 0;
   if ((C.rs % 8) != 0 || (C.bs % 8) != 0) return 0;
   CUtensorMap tmA, tmB;
-  CPC_TRY(make_rowview_map(&tmA, A, Kd, nb, BM, false));
+  const int heads = (hb != nullptr && hb->w_div > 0) ? nb / hb->w_div : 1;
+  CPC_TRY(make_rowview_map(&tmA, A, Kd, (hb != nullptr && hb->a_mod > 0) ? hb->a_mod : nb, BM, false));
   static const int gen = []() { const char* e = getenv("CPC_B200_GEMM_GEN"); return e ? atoi(e) : 2; }();
   static const int cm_env = []() { const char* e = getenv("CPC_B200_GEMM_CM"); return e ? atoi(e) : 2; }();
   if (C.res_w > 0 && C.res_w % BN != 0) return 0;  // an output tile must not straddle two dgrad residues
   if (gen == 2 && N % 256 == 0 && (C.res_w == 0 || C.res_w % 256 == 0)) {
-    const int cm = (cm_env == 1 || cm_env == 2 || cm_env == 4) ? cm_env : 2;
-    unsigned long long dims[4] = {(unsigned long long)Kd, (unsigned long long)N, 1, 1};
-    unsigned long long stq[3] = {(unsigned long long)Kd, (unsigned long long)Kd * N, (unsigned long long)Kd * N};
+    int cm = (cm_env == 1 || cm_env == 2 || cm_env == 4) ? cm_env : 2;
+    const int tpb2 = (A.rpb + BM - 1) / BM;
+    HeadBatch HB{};
+    if (hb != nullptr) {
+      HB = *hb;
+      HB.w_rows = N;
+      while (cm > 1 && HB.w_div > 0 && (HB.w_div * tpb2) % cm != 0) cm >>= 1;  // the CTAs of a cluster share ONE weight tile
+    }
+    unsigned long long dims[4] = {(unsigned long long)Kd, (unsigned long long)N * heads, 1, 1};
+    unsigned long long stq[3] = {(unsigned long long)Kd, (unsigned long long)Kd * N * heads, (unsigned long long)Kd * N * heads};
     unsigned box[4] = {64, (unsigned)(256 / cm), 1, 1};
     CPC_TRY(make_map4(&tmB, Bm, dims, stq, box));
-    const int tpb2 = (A.rpb + BM - 1) / BM;
     const int m_tiles = nb * tpb2, n_tiles = N / 256;
-#define NT2(CMV)                                                                                                         \
-  (out_f32 ? launch_nt2<CMV, float>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb2, m_tiles, n_tiles, nb, bias, C, st)            \
-           : launch_nt2<CMV, bf16>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb2, m_tiles, n_tiles, nb, bias, C, st))
+#define NT2(CMV)                                                                                                                    \
+  (out_f32 ? launch_nt2<CMV, float>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb2, m_tiles, n_tiles, nb, bias, C, st, CNormEpi{}, HB)       \
+           : launch_nt2<CMV, bf16>(tmA, tmB, Kd / BK, cin / BK, A.s, tpb2, m_tiles, n_tiles, nb, bias, C, st, CNormEpi{}, HB))
     if (cm == 4) CPC_TRY(NT2(4)); else if (cm == 2) CPC_TRY(NT2(2)); else CPC_TRY(NT2(1));
 #undef NT2
     *handled = true;
     return 0;
   }
+  if (hb != nullptr) return 0;  // (first-generation kernel: one weight matrix)
   {
     unsigned long long dims[4] = {(unsigned long long)Kd, (unsigned long long)N, 1, 1};
     unsigned long long stq[3] = {(unsigned long long)Kd, (unsigned long long)Kd * N, (unsigned long long)Kd * N};

@@ -285,6 +285,8 @@ __global__ void colsum_kernel(const T* __restrict__ src, float* __restrict__ out
   const long long m1 = min(M, m0 + rows_per_block);
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
+  src += (size_t)blockIdx.z * M * N;  // stacked matrices: one (M, N) block and one output vector per blockIdx.z
+  out += (size_t)blockIdx.z * N;
   float s = 0.f;
   for (long long m = m0; m < m1; m++) s += to_f(src[m * N + n]);
   atomicAdd(out + n, s);
@@ -321,15 +323,15 @@ template <class T> int launch_transpose_cast(const float* src, T* dst, int R, in
 template int launch_transpose_cast<bf16>(const float*, bf16*, int, int, cudaStream_t, int);
 template int launch_transpose_cast<float>(const float*, float*, int, int, cudaStream_t, int);
 
-template <class T> int launch_colsum(const T* src, float* out, long long M, int N, cudaStream_t st) {
-  const int rpb = 256;
-  dim3 grid((N + 127) / 128, (unsigned)((M + rpb - 1) / rpb));
+template <class T> int launch_colsum(const T* src, float* out, long long M, int N, cudaStream_t st, int nb = 1) {
+  const int rpb = nb > 1 ? 64 : 256;
+  dim3 grid((N + 127) / 128, (unsigned)((M + rpb - 1) / rpb), nb);
   colsum_kernel<T><<<grid, 128, 0, st>>>(src, out, M, N, rpb);
   CPC_LAUNCHED_N("colsum", st);
   return 0;
 }
-template int launch_colsum<bf16>(const bf16*, float*, long long, int, cudaStream_t);
-template int launch_colsum<float>(const float*, float*, long long, int, cudaStream_t);
+template int launch_colsum<bf16>(const bf16*, float*, long long, int, cudaStream_t, int);
+template int launch_colsum<float>(const float*, float*, long long, int, cudaStream_t, int);
 
 namespace {
 

@@ -19,13 +19,14 @@ int gemm_tn(bool bf16_in, int nb, int N1, int N2, const RowView& A, const RowVie
             int Ci, int taps, cudaStream_t st);
 template <class T> int launch_cast(const float* src, T* dst, long long n, cudaStream_t st);
 template <class T> int launch_transpose_cast(const float* src, T* dst, int R, int C, cudaStream_t st, int nb = 1);
-template <class T> int launch_colsum(const T* src, float* out, long long M, int N, cudaStream_t st);
+template <class T> int launch_colsum(const T* src, float* out, long long M, int N, cudaStream_t st, int nb = 1);
+int gemm_tn_group(bool bf16_in, int n, const TnDesc* d, cudaStream_t st);
 
 bool attn_mma_supported(int W, int D, int nh);
 int attn_fwd_mma(const bf16* qkv, const float* krel, bf16* att, int B, int W, int D, int nh, const unsigned char* keep, float dscale,
-                 cudaStream_t st);
+                 cudaStream_t st, int bph = 0);
 int attn_bwd_mma(const bf16* qkv, const bf16* datt, const bf16* att, const float* krel, bf16* dqkv, float* dkrel, int B, int W, int D,
-                 int nh, const unsigned char* keep, float dscale, cudaStream_t st);
+                 int nh, const unsigned char* keep, float dscale, cudaStream_t st, int bph = 0);
 
 namespace {
 
@@ -292,15 +293,24 @@ __device__ __forceinline__ void ln_stats(const float (&u)[I][4], int D, int lane
 }
 
 // s = a + b ; y = LN(s).  a: rows (p / rpb, p % rpb) with strides (a_bs, a_rs); b, s dense (P, D); y rows stride y_rs.
+// Stacked heads (HS.rph > 0): P counts the rows of ALL heads, head = p / rph owns gamma / beta + head * D, its rows of a start
+// at a + head * a_hs (a_hs = 0: the heads share a) and its rows of y at y + head * y_hs.
+struct HeadStride { int rph = 0; long long a_hs = 0, y_hs = 0; };
 template <int I, class TA, class T>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const TA* __restrict__ a, long long a_bs, long long a_rs, int rpb,
                                                           const T* __restrict__ b, const float* __restrict__ gam,
                                                           const float* __restrict__ bet, T* __restrict__ s_out,
-                                                          T* __restrict__ y, long long y_rs, int P, int D) {
+                                                          T* __restrict__ y, long long y_rs, int P, int D, HeadStride HS) {
   const int lane = threadIdx.x & 31;
   const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (p >= P) return;
-  const int bi = (int)(p / rpb), ti = (int)(p - (long long)bi * rpb);
+  long long pl = p;  // row inside its head
+  if (HS.rph > 0) {
+    const int head = (int)(p / HS.rph);
+    pl = p - (long long)head * HS.rph;
+    a += head * HS.a_hs; y += head * HS.y_hs; gam += (size_t)head * D; bet += (size_t)head * D;
+  }
+  const int bi = (int)(pl / rpb), ti = (int)(pl - (long long)bi * rpb);
   float va[I][4], vb[I][4];
   rload<I>(a + (long long)bi * a_bs + (long long)ti * a_rs, D, lane, va);
   rload<I>(b + p * D, D, lane, vb);
@@ -323,26 +333,35 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const TA* __restrict__ 
       for (int j = 0; j < 4; j++) va[i][j] = fmaf((va[i][j] - mean) * rstd, g[j], be[j]);
     }
   }
-  rstore<I>(y + p * y_rs, D, lane, va);
+  rstore<I>(y + pl * y_rs, D, lane, va);
 }
 
 // LayerNorm backward: dy = dya (+ dyb); ds = rstd (dxh - mean(dxh) - xh mean(dxh xh)); dgamma += dy xh; dbeta += dy
+// blockIdx.y = head (stacked heads: every per-head array advances by its head stride, dya by dya_hs).  dsum != NULL: the column
+// sums of ds are added there too (the bias gradient of the linear layer that produced the LayerNorm input).
 template <int I, class T>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dya, long long dya_rs, const T* __restrict__ dyb,
                                                       const T* __restrict__ s, const float* __restrict__ gam,
                                                       T* __restrict__ ds, float* __restrict__ dgam, float* __restrict__ dbet,
-                                                      int P, int D) {
-  extern __shared__ __align__(16) float accs[];  // [2][D]
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) accs[i] = 0.f;
+                                                      int P, int D, long long dya_hs, float* __restrict__ dsum) {
+  extern __shared__ __align__(16) float accs[];  // [3][D]
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) accs[i] = 0.f;
+  {
+    const size_t head = blockIdx.y;
+    dya += head * dya_hs; s += head * (size_t)P * D; ds += head * (size_t)P * D;
+    if (dyb != nullptr) dyb += head * (size_t)P * D;
+    gam += head * D; dgam += head * D; dbet += head * D;
+    if (dsum != nullptr) dsum += head * D;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  float ag[I][4], ab[I][4];
+  float ag[I][4], ab[I][4], as[I][4];
 #pragma unroll
   for (int i = 0; i < I; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) ag[i][j] = ab[i][j] = 0.f;
+    for (int j = 0; j < 4; j++) ag[i][j] = ab[i][j] = as[i][j] = 0.f;
   for (long long p = w0; p < P; p += nw) {
     float v[I][4], d[I][4];
     rload<I>(s + p * D, D, lane, v);
@@ -382,33 +401,87 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dya, 
 #pragma unroll
       for (int j = 0; j < 4; j++) d[i][j] = rstd * (d[i][j] - s1 - v[i][j] * s2);
     rstore<I>(ds + p * D, D, lane, d);
+    if (dsum != nullptr) {  // (of the values as stored: what a separate column-sum pass over ds would read)
+      rload<I>(ds + p * D, D, lane, d);
+#pragma unroll
+      for (int i = 0; i < I; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) as[i][j] += d[i][j];
+    }
   }
 #pragma unroll
   for (int i = 0; i < I; i++) {
     const int c = 4 * (lane + 32 * i);
     if (c < D) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) { atomicAdd(&accs[c + j], ag[i][j]); atomicAdd(&accs[D + c + j], ab[i][j]); }
+      for (int j = 0; j < 4; j++) {
+        atomicAdd(&accs[c + j], ag[i][j]); atomicAdd(&accs[D + c + j], ab[i][j]);
+        if (dsum != nullptr) atomicAdd(&accs[2 * D + c + j], as[i][j]);
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) { atomicAdd(dgam + i, accs[i]); atomicAdd(dbet + i, accs[D + i]); }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgam + i, accs[i]); atomicAdd(dbet + i, accs[D + i]);
+    if (dsum != nullptr) atomicAdd(dsum + i, accs[2 * D + i]);
+  }
 }
 
 // h is the FFN hidden AFTER relu (and after dropout in train mode): h > 0 <=> the unit was active and kept, and the
 // gradient through a kept unit carries the dropout scale (transformers.py:92-95)
 template <class T>
 __global__ void relu_mask_kernel(T* __restrict__ dh, const T* __restrict__ h, long long n, float dscale) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (!(to_f(h[i]) > 0.f)) dh[i] = from_f<T>(0.f);
-    else if (dscale != 1.f) dh[i] = from_f<T>(to_f(dh[i]) * dscale);
+  if constexpr (sizeof(T) == 2) {  // bf16: 8 elements (16 B) per thread and iteration
+    const long long n8 = n >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+      uint4 dv = reinterpret_cast<const uint4*>(dh)[i];
+      const uint4 hv = reinterpret_cast<const uint4*>(h)[i];
+      __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(&dv);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float2 hf = __bfloat1622float2(h2[j]);
+        float2 df = __bfloat1622float2(d2[j]);
+        df.x = hf.x > 0.f ? df.x * dscale : 0.f;
+        df.y = hf.y > 0.f ? df.y * dscale : 0.f;
+        d2[j] = __floats2bfloat162_rn(df.x, df.y);
+      }
+      reinterpret_cast<uint4*>(dh)[i] = dv;
+    }
+    for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      dh[i] = from_f<T>(to_f(h[i]) > 0.f ? to_f(dh[i]) * dscale : 0.f);
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      if (!(to_f(h[i]) > 0.f)) dh[i] = from_f<T>(0.f);
+      else if (dscale != 1.f) dh[i] = from_f<T>(to_f(dh[i]) * dscale);
+    }
   }
 }
 // train-mode dropout of the FFN hidden (transformers.py:92): h *= keep * dscale, in place
 template <class T>
 __global__ void dropout_apply_kernel(T* __restrict__ h, const unsigned char* __restrict__ keep, long long n, float dscale) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    h[i] = keep[i] ? from_f<T>(to_f(h[i]) * dscale) : from_f<T>(0.f);
+  if constexpr (sizeof(T) == 2) {
+    const long long n8 = n >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+      uint4 hv = reinterpret_cast<const uint4*>(h)[i];
+      const uint2 kv = reinterpret_cast<const uint2*>(keep)[i];
+      const unsigned char* kb = reinterpret_cast<const unsigned char*>(&kv);
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hv);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float2 f = __bfloat1622float2(h2[j]);
+        f.x = kb[2 * j] ? f.x * dscale : 0.f;
+        f.y = kb[2 * j + 1] ? f.y * dscale : 0.f;
+        h2[j] = __floats2bfloat162_rn(f.x, f.y);
+      }
+      reinterpret_cast<uint4*>(h)[i] = hv;
+    }
+    for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      h[i] = keep[i] ? from_f<T>(to_f(h[i]) * dscale) : from_f<T>(0.f);
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      h[i] = keep[i] ? from_f<T>(to_f(h[i]) * dscale) : from_f<T>(0.f);
+  }
 }
 // acc (fp32, P x D) += a + b
 template <class T>
@@ -424,6 +497,18 @@ __global__ void scatter_rows_kernel(const float* __restrict__ acc, size_t lane_s
     const int d = (int)(i % D); const long long pw = i / D; const int w = (int)(pw % W), b = (int)(pw / W);
     float v = 0.f;
     for (int l = 0; l < nlanes; l++) v += acc[(size_t)l * lane_stride + i];
+    dc[((long long)b * S + w) * D + d] = v;
+  }
+}
+// stacked heads: dc[b, w < W, :] = sum_k (a[k][(b, w), :] + b[k][(b, w), :])
+template <class T>
+__global__ void sum_heads_scatter_kernel(const T* __restrict__ a, const T* __restrict__ bsrc, int K, float* __restrict__ dc, int B, int S,
+                                         int W, int D) {
+  const long long n = (long long)B * W * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D); const long long pw = i / D; const int w = (int)(pw % W), b = (int)(pw / W);
+    float v = 0.f;
+    for (int k = 0; k < K; k++) v += to_f(a[(size_t)k * n + i]) + to_f(bsrc[(size_t)k * n + i]);
     dc[((long long)b * S + w) * D + d] = v;
   }
 }
@@ -490,10 +575,10 @@ int launch_attn_bwd(const T* qkv, const T* datt, const T* att, const float* krel
 
 template <class TA, class T>
 int launch_add_ln(const TA* a, long long a_bs, long long a_rs, int rpb, const T* b, const float* gam, const float* bet, T* s_out,
-                  T* y, long long y_rs, int P, int D, cudaStream_t st) {
+                  T* y, long long y_rs, int P, int D, cudaStream_t st, const HeadStride& HS = HeadStride{}) {
   const int I = (D + 127) / 128;
   const int blocks = (int)(((long long)P * 32 + 255) / 256);
-#define AL(II) add_ln_fwd_kernel<II, TA, T><<<blocks, 256, 0, st>>>(a, a_bs, a_rs, rpb, b, gam, bet, s_out, y, y_rs, P, D)
+#define AL(II) add_ln_fwd_kernel<II, TA, T><<<blocks, 256, 0, st>>>(a, a_bs, a_rs, rpb, b, gam, bet, s_out, y, y_rs, P, D, HS)
   if (I == 1) AL(1); else if (I == 2) AL(2); else if (I == 3) AL(3); else AL(4);
 #undef AL
   CPC_LAUNCHED_N("add_ln_fwd", st);
@@ -501,12 +586,13 @@ int launch_add_ln(const TA* a, long long a_bs, long long a_rs, int rpb, const T*
 }
 template <class T>
 int launch_ln_bwd(const T* dya, long long dya_rs, const T* dyb, const T* s, const float* gam, T* ds, float* dgam, float* dbet, int P,
-                  int D, cudaStream_t st) {
+                  int D, cudaStream_t st, int heads = 1, long long dya_hs = 0, float* dsum = nullptr) {
   const int I = (D + 127) / 128;
   int blocks = (int)(((long long)P * 32 + 255) / 256);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  const size_t smem = 2 * (size_t)D * 4;
-#define LB(II) ln_bwd_kernel<II, T><<<blocks, 256, smem, st>>>(dya, dya_rs, dyb, s, gam, ds, dgam, dbet, P, D)
+  const int cap = heads > 1 ? (148 * 8 + heads - 1) / heads : 148 * 4;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = 3 * (size_t)D * 4;
+#define LB(II) ln_bwd_kernel<II, T><<<dim3(blocks, heads), 256, smem, st>>>(dya, dya_rs, dyb, s, gam, ds, dgam, dbet, P, D, dya_hs, dsum)
   if (I == 1) LB(1); else if (I == 2) LB(2); else if (I == 3) LB(3); else LB(4);
 #undef LB
   CPC_LAUNCHED_N("ln_bwd", st);
@@ -568,6 +654,171 @@ THeadLayout thead_layout(const Geo& g) {
   return l;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Stacked heads (bf16 path): the K heads run as ONE sequence of launches.  Every activation is an array over (head, row):
+// [K][P][.] - so that a per-head product is one batch of a batched GEMM whose weights are the heads' stacked matrices
+// (gemm_nt_heads), a per-head weight gradient is one problem of a grouped TN launch, and the row / element kernels walk
+// K*P rows with the head's parameters looked up from the row index.  ~30 launches per direction instead of ~9 per head
+// and direction on four stream lanes; a (B*W) x 256 x 256 product becomes 12 x 29 = 348 output tiles instead of 29.
+// CPC_B200_HEAD_STACK=0 returns to the per-head lanes (also used by the fp32 path and when a product does not fit the
+// 128 x 256 tensor-core tiling).
+// ---------------------------------------------------------------------------------------------------------
+struct StackLayout { size_t qkv, att, s1, y1, h, s2; };  // element offsets of the [K][P][.] arrays in the save buffer
+StackLayout stack_layout(const Geo& g) {
+  const size_t KP = (size_t)g.K * g.B * g.W, D = g.H, F = g.dff;
+  StackLayout l{};
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t r = off; off += (n + 127) / 128 * 128; return r; };
+  l.qkv = take(KP * 3 * D); l.att = take(KP * D); l.s1 = take(KP * D); l.y1 = take(KP * D); l.h = take(KP * F); l.s2 = take(KP * D);
+  return l;  // (never more than K * thead_layout(g).per_k elements: the per-head layout rounds every array of every head up)
+}
+bool heads_stacked(const Geo& g) {
+  static const bool off = []() { const char* e = getenv("CPC_B200_HEAD_STACK"); return e && atoi(e) == 0; }();
+  return !off && g.bf16 && g.H % 256 == 0 && g.dff % 256 == 0 && g.H == g.Har && attn_mma_supported(g.W, g.H, g.nheads);
+}
+
+int thead_fwd_stacked(const Geo& g, const bf16* cp, const cpcb200_thead_params* tp, bf16* pred, void* save, Carver& ws, cudaStream_t st) {
+  typedef bf16 T;
+  const int B = g.B, S = g.S, W = g.W, D = g.H, K = g.K, F = g.dff, nh = g.nheads;
+  const int P = B * W;
+  const long long KP = (long long)K * P;
+  const StackLayout lay = stack_layout(g);
+  T* sv = static_cast<T*>(save);
+  T *qkv = sv + lay.qkv, *att = sv + lay.att, *s1 = sv + lay.s1, *y1 = sv + lay.y1, *h = sv + lay.h, *s2 = sv + lay.s2;
+  T* o = ws.take<T>((size_t)KP * D);
+  T* f = ws.take<T>((size_t)KP * D);
+  T* wall[6] = {nullptr};
+  const size_t wsz[6] = {(size_t)D * D, (size_t)D * D, (size_t)D * D, (size_t)D * D, (size_t)F * D, (size_t)F * D};
+  for (int j = 0; j < 6; j++) wall[j] = ws.take<T>(wsz[j] * K);
+  if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "thead_fwd: workspace too small (%zu needed)", ws.off);
+  const float* src[6] = {tp->wq, tp->wk, tp->wv, tp->wo, tp->w1, tp->w2};
+  for (int j = 0; j < 6; j++) CPC_TRY(launch_cast<T>(src[j], wall[j], (long long)(wsz[j] * K), st));
+  const bool drop = tp->att_keep != nullptr && tp->ffn_keep != nullptr;
+  // q | k | v: batch (head, window) reads window b of x and the head's matrix
+  const RowView X{cp, (long long)S * D, (long long)D, W};
+  for (int j = 0; j < 3; j++) {
+    OutView C{qkv + (size_t)j * D, (long long)W * 3 * D, (long long)3 * D, W, 0, W, 0};
+    CPC_TRY(gemm_nt_heads(false, K * B, D, D, X, wall[j], nullptr, C, B, B, st));
+  }
+  CPC_TRY(attn_fwd_mma(qkv, tp->krelpos, att, K * B, W, D, nh, drop ? tp->att_keep : nullptr, tp->keep_scale, st, B));
+  {
+    RowView A{att, (long long)P * D, (long long)D, P};
+    OutView C{o, (long long)P * D, (long long)D, P, 0, P, 0};
+    CPC_TRY(gemm_nt_heads(false, K, D, D, A, wall[3], nullptr, C, 0, 1, st));
+  }
+  {
+    HeadStride HS; HS.rph = P; HS.a_hs = 0; HS.y_hs = (long long)P * D;
+    CPC_TRY((launch_add_ln<T, T>(cp, (long long)S * D, (long long)D, W, o, tp->ln1_w, tp->ln1_b, s1, y1, (long long)D, (int)KP, D, st, HS)));
+  }
+  {
+    RowView A{y1, (long long)P * D, (long long)D, P};
+    OutView C{h, (long long)P * F, (long long)F, P, 0, P, 0};
+    C.relu = 1;
+    CPC_TRY(gemm_nt_heads(false, K, F, D, A, wall[4], tp->b1, C, 0, 1, st));
+    if (drop) {
+      dropout_apply_kernel<T><<<grid_for(KP * F), 256, 0, st>>>(h, tp->ffn_keep, KP * F, tp->keep_scale);
+      CPC_LAUNCHED_N("dropout_apply", st);
+    }
+  }
+  {
+    RowView A{h, (long long)P * F, (long long)F, P};
+    OutView C{f, (long long)P * D, (long long)D, P, 0, P, 0};
+    CPC_TRY(gemm_nt_heads(false, K, D, F, A, wall[5], tp->b2, C, 0, 1, st));
+  }
+  {  // pred[(b, w), k, :] = LN2(y1 + f) of head k
+    HeadStride HS; HS.rph = P; HS.a_hs = (long long)P * D; HS.y_hs = (long long)D;
+    CPC_TRY((launch_add_ln<T, T>(y1, (long long)P * D, (long long)D, P, f, tp->ln2_w, tp->ln2_b, s2, pred, (long long)K * D, (int)KP, D, st, HS)));
+  }
+  return 0;
+}
+
+int thead_bwd_stacked(const Geo& g, const bf16* cp, const cpcb200_thead_params* tp, const bf16* dpred, const void* save, float* dc,
+                      const cpcb200_thead_params* gr, Carver& ws, cudaStream_t st) {
+  typedef bf16 T;
+  const int B = g.B, S = g.S, W = g.W, D = g.H, K = g.K, F = g.dff, nh = g.nheads;
+  const int P = B * W, DK = D / nh;
+  const long long KP = (long long)K * P;
+  const StackLayout lay = stack_layout(g);
+  const T* sv = static_cast<const T*>(save);
+  const T *qkv = sv + lay.qkv, *att = sv + lay.att, *s1 = sv + lay.s1, *y1 = sv + lay.y1, *h = sv + lay.h, *s2 = sv + lay.s2;
+  T* wqkvT = ws.take<T>((size_t)3 * D * D * K); T* woT = ws.take<T>((size_t)D * D * K);
+  T* w1T = ws.take<T>((size_t)F * D * K); T* w2T = ws.take<T>((size_t)F * D * K);
+  T* ds2 = ws.take<T>((size_t)KP * D); T* dy1 = ws.take<T>((size_t)KP * D); T* ds1 = ws.take<T>((size_t)KP * D);
+  T* datt = ws.take<T>((size_t)KP * D); T* dx = ws.take<T>((size_t)KP * D);
+  T* dh = ws.take<T>((size_t)KP * F); T* dqkv = ws.take<T>((size_t)KP * 3 * D);
+  if (!ws.ok()) return fail(CPCB200_ERR_WORKSPACE, "thead_bwd: workspace too small (%zu needed)", ws.off);
+  concat_transpose3_kernel<T><<<dim3(grid_for((long long)3 * D * D), 1, K), 256, 0, st>>>(tp->wq, tp->wk, tp->wv, wqkvT, D);
+  CPC_LAUNCHED_N("concat_transpose3", st);
+  CPC_TRY(launch_transpose_cast<T>(tp->wo, woT, D, D, st, K));
+  CPC_TRY(launch_transpose_cast<T>(tp->w1, w1T, F, D, st, K));
+  CPC_TRY(launch_transpose_cast<T>(tp->w2, w2T, D, F, st, K));
+  const bool drop = tp->att_keep != nullptr && tp->ffn_keep != nullptr;
+  const size_t PD = (size_t)P * D, PF = (size_t)P * F;
+  // per-head weight gradients: four problems per grouped TN launch
+  auto tn_heads = [&](const T* a, size_t a_hs, int N1, const T* b, size_t b_hs, int N2, float* dw) -> int {
+    TnDesc d[4];
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const int n = K - k0 < 4 ? K - k0 : 4;
+      for (int i = 0; i < n; i++) {
+        const int k = k0 + i;
+        d[i] = TnDesc{1, N1, N2, RowView{a + k * a_hs, 0, (long long)N1, P}, RowView{b + k * b_hs, 0, (long long)N2, P},
+                      dw + (size_t)k * N1 * N2, N2, STORE_PLAIN, 0, 0};
+      }
+      CPC_TRY(gemm_tn_group(true, n, d, st));
+    }
+    return 0;
+  };
+  // LN2 backward (+ db2 = column sums of ds2)
+  CPC_TRY(launch_ln_bwd<T>(dpred, (long long)K * D, nullptr, s2, tp->ln2_w, ds2, gr->ln2_w, gr->ln2_b, P, D, st, K, (long long)D, gr->b2));
+  // FFN backward
+  CPC_TRY(tn_heads(ds2, PD, D, h, PF, F, gr->w2));                                            // dW2[d][f]
+  {
+    RowView A{ds2, (long long)PD, (long long)D, P};
+    OutView C{dh, (long long)PF, (long long)F, P, 0, P, 0};
+    CPC_TRY(gemm_nt_heads(false, K, F, D, A, w2T, nullptr, C, 0, 1, st));                     // dh = ds2 . W2
+  }
+  relu_mask_kernel<T><<<grid_for(KP * F), 256, 0, st>>>(dh, h, KP * F, drop ? tp->keep_scale : 1.f);
+  CPC_LAUNCHED_N("relu_mask", st);
+  CPC_TRY(launch_colsum<T>(dh, gr->b1, P, F, st, K));
+  CPC_TRY(tn_heads(dh, PF, F, y1, PD, D, gr->w1));                                            // dW1[f][d]
+  {
+    RowView A{dh, (long long)PF, (long long)F, P};
+    OutView C{dy1, (long long)PD, (long long)D, P, 0, P, 0};
+    CPC_TRY(gemm_nt_heads(false, K, D, F, A, w1T, nullptr, C, 0, 1, st));                     // dy1 (FFN branch)
+  }
+  // LN1 backward on dy1 + ds2 (residual)
+  CPC_TRY(launch_ln_bwd<T>(dy1, (long long)D, ds2, s1, tp->ln1_w, ds1, gr->ln1_w, gr->ln1_b, P, D, st, K, (long long)PD, nullptr));
+  CPC_TRY(tn_heads(ds1, PD, D, att, PD, D, gr->wo));
+  {
+    RowView A{ds1, (long long)PD, (long long)D, P};
+    OutView C{datt, (long long)PD, (long long)D, P, 0, P, 0};
+    CPC_TRY(gemm_nt_heads(false, K, D, D, A, woT, nullptr, C, 0, 1, st));
+  }
+  CPC_TRY(attn_bwd_mma(qkv, datt, att, tp->krelpos, dqkv, gr->krelpos, K * B, W, D, nh, drop ? tp->att_keep : nullptr, tp->keep_scale, st, B));
+  (void)DK;
+  {  // Wq, Wk, Wv: 3 K problems, each a sum over the B windows
+    const RowView X{cp, (long long)S * D, (long long)D, W};
+    float* dw3[3] = {gr->wq, gr->wk, gr->wv};
+    TnDesc d[4];
+    int n = 0;
+    for (int k = 0; k < K; k++)
+      for (int j = 0; j < 3; j++) {
+        d[n++] = TnDesc{B, D, D, RowView{dqkv + (size_t)k * P * 3 * D + (size_t)j * D, (long long)W * 3 * D, (long long)3 * D, W}, X,
+                        dw3[j] + (size_t)k * D * D, D, STORE_PLAIN, 0, 0};
+        if (n == 4 || (k == K - 1 && j == 2)) { CPC_TRY(gemm_tn_group(true, n, d, st)); n = 0; }
+      }
+  }
+  {
+    RowView A{dqkv, (long long)P * 3 * D, (long long)3 * D, P};
+    OutView C{dx, (long long)PD, (long long)D, P, 0, P, 0};
+    CPC_TRY(gemm_nt_heads(false, K, D, 3 * D, A, wqkvT, nullptr, C, 0, 1, st));
+  }
+  sum_heads_scatter_kernel<T><<<grid_for((long long)P * D), 256, 0, st>>>(dx, ds1, K, dc, B, S, W, D);
+  CPC_LAUNCHED_N("sum_heads_scatter", st);
+  return 0;
+}
+
 }  // namespace
 
 size_t thead_save_bytes(const Geo& g) { return thead_layout(g).per_k * g.K * (g.bf16 ? 2 : 4) + 256; }
@@ -584,7 +835,12 @@ size_t thead_ws_bytes(const Geo& g, int backward) {
     t += 5 * align_up(P * D * es) + align_up(P * F * es) + align_up(P * 3 * D * es);   // ds2, dy1, ds1, datt, dx, dh, dqkv
     t += align_up(P * D * 4);                                                          // dc accumulator
   }
-  return t * kLanes + w + 1024;  // one scratch set per lane + the converted weights
+  size_t lanes = t * kLanes + w + 1024;  // one scratch set per lane + the converted weights
+  if (heads_stacked(g)) {               // stacked heads: one scratch set over all K heads (no dc accumulators)
+    size_t ts = backward ? 5 * align_up(K * P * D * es) + align_up(K * P * F * es) + align_up(K * P * 3 * D * es) : 2 * align_up(K * P * D * es);
+    if (ts + w + 1024 > lanes) lanes = ts + w + 1024;
+  }
+  return lanes;
 }
 
 template <class T>
@@ -594,6 +850,9 @@ int thead_fwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, T* pred
   if (g.Har != g.H) return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads need hiddenGar == hiddenEncoder (criterion.py:85)");
   if (W > 128 || D % nh != 0) return fail(CPCB200_ERR_UNSUPPORTED, "transformer heads: W=%d (max 128), D=%d, heads=%d", W, D, nh);
   constexpr bool isf = sizeof(T) == 4;
+  if constexpr (!isf) {
+    if (heads_stacked(g)) return thead_fwd_stacked(g, cp, tp, pred, save, ws, st);
+  }
   const THeadLayout lay = thead_layout(g);
   T* sv = static_cast<T*>(save);
   struct FwdScratch { T *o, *f; } scr[kLanes];
@@ -668,6 +927,9 @@ int thead_bwd(const Geo& g, const T* cp, const cpcb200_thead_params* tp, const T
               const cpcb200_thead_params* gr, Carver& ws, cudaStream_t st) {
   const int B = g.B, S = g.S, W = g.W, D = g.H, K = g.K, F = g.dff, nh = g.nheads;
   const int P = B * W, DK = D / nh;
+  if constexpr (sizeof(T) == 2) {
+    if (heads_stacked(g)) return thead_bwd_stacked(g, cp, tp, dpred, save, dc, gr, ws, st);
+  }
   const THeadLayout lay = thead_layout(g);
   const T* sv = static_cast<const T*>(save);
   struct BwdScratch { T *ds2, *dy1, *ds1, *datt, *dx, *dh, *dqkv; float* dcw; } scr[kLanes];
