@@ -696,9 +696,9 @@ def run_ours(a):
             roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
         # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture (profiles/), not measured live
         try:
-            tj = json.load(open(os.path.join(REPO, "profiles", "r2p_traffic.json")))
+            tj = json.load(open(os.path.join(REPO, "profiles", "r2f_traffic.json")))
             roof["traffic"] = tj["kernels"][top]["dram_bytes_per_launch"]
-            roof["traffic_source"] = "profiles/r2p_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, round 2)"
+            roof["traffic_source"] = "profiles/r2f_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, round 2)"
             for k, ent in kernels.items():
                 if k in tj["kernels"]:
                     ent["ncu_dram_bytes_per_launch"] = tj["kernels"][k]["dram_bytes_per_launch"]

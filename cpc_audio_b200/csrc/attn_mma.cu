@@ -4,8 +4,9 @@
 //   scores[i][c] = (q_i . k_c + q_i . Krelpos[:, W-1-(i-c)]) / sqrt(dk)   for c <= i      (the "skew" of transformers.py:42-47)
 //   a = softmax_c(scores) ; (train mode) a~ = a * keep * 1/(1-p) ; o_i = sum_c a~[i][c] v_c
 //
-// One CTA per (head, window), 4 warps, warp w owns query rows 32w .. 32w+31 (two m16 tiles).  Every product is an
-// m16n8k16 bf16 MMA with fp32 accumulation:
+// One CTA per (head, window), 4 warps.  The mask is causal, so the work of a 16-row tile grows with its index: warp w owns the
+// row tiles w and 7-w (rows 16w.. and 16(7-w)..) - every warp then sees the same number of keys - and, on the key side of
+// backward, the key tiles w and 7-w.  Every product is an m16n8k16 bf16 MMA with fp32 accumulation:
 //   QP = Q . Krelpos   -> per-warp fp32 scratch in shared memory (the skew is a row-dependent shift: it needs a round trip)
 //   S  = Q . K^T (+ shifted QP), softmax in the accumulator registers, O = P . V with the accumulator-to-A-fragment reuse
 // Backward recomputes S chunk by chunk (32 keys) from the row statistics, uses delta_i = dO_i . O_i (= sum_c da[i][c] a[i][c], also
@@ -90,7 +91,8 @@ __device__ __forceinline__ void fill_relpos(const float* __restrict__ krel, bf16
 
 // QP[il][m] = q_{r0+il} . Krelpos[:, m] for the 32 rows of a warp -> fp32 scratch, ZERO where the entry belongs to no key
 // (m < W-1-i, or a padding row): the backward pass overwrites the live cells with dS and then reads the whole row as dS~
-__device__ __forceinline__ void qp_to_scratch(const uint32_t (&aq)[2][2][4], const bf16* Rs, float* qp, int r0, int W, int lane) {
+__device__ __forceinline__ void qp_to_scratch(const uint32_t (&aq)[2][2][4], const bf16* Rs, float* qp, const int (&row0)[2], int W,
+                                              int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int nt = 0; nt < 16; nt++) {
@@ -103,7 +105,7 @@ __device__ __forceinline__ void qp_to_scratch(const uint32_t (&aq)[2][2][4], con
       mma16816(acc, aq[mt][1], bb[2], bb[3]);
 #pragma unroll
       for (int hf = 0; hf < 2; hf++) {
-        const int il = 16 * mt + g + 8 * hf, i = r0 + il, m = 8 * nt + 2 * t;
+        const int il = 16 * mt + g + 8 * hf, i = row0[mt] + g + 8 * hf, m = 8 * nt + 2 * t;
         float2 v = make_float2(acc[2 * hf], acc[2 * hf + 1]);
         if (i >= W || m < W - 1 - i || m >= W) v.x = 0.f;
         if (i >= W || m + 1 < W - 1 - i || m + 1 >= W) v.y = 0.f;
@@ -129,28 +131,29 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const bf16* __restric
   if (bph > 0) krel += (size_t)(b / bph) * DKC * W;  // blockIdx.y = (prediction head, window): stacked Krelpos
   fill_relpos(krel, Rs, W, tid);
   __syncthreads();
-  const int r0 = 32 * warp;
-  if (r0 >= W) return;
+  const int row0[2] = {16 * warp, 16 * (7 - warp)};          // first rows of this warp's two m-tiles
+  const int ntm[2] = {2 * (warp + 1), 2 * (8 - warp)};       // 8-key tiles a row tile can see: keys c <= i < row0 + 16
   uint32_t aq[2][2][4];
 #pragma unroll
   for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-    for (int ks = 0; ks < 2; ks++) load_a(aq[mt][ks], Qs, RS, r0 + 16 * mt, 16 * ks, lane);
+    for (int ks = 0; ks < 2; ks++) load_a(aq[mt][ks], Qs, RS, row0[mt], 16 * ks, lane);
   float* qp = QP + warp * 32 * QS;
-  qp_to_scratch(aq, Rs, qp, r0, W, lane);
+  qp_to_scratch(aq, Rs, qp, row0, W, lane);
   __syncwarp();
-  const int nt_max = 4 * (warp + 1);  // keys c <= i < 32 (warp + 1)
   float S[2][16][4];
 #pragma unroll
   for (int nt = 0; nt < 16; nt++) {
-    if (nt < nt_max) {
+    if (nt < ntm[1]) {
       uint32_t bb[4];
       load_b_nk(bb, Ks, 8 * nt, lane);
 #pragma unroll
       for (int mt = 0; mt < 2; mt++) {
-        S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.f;
-        mma16816(S[mt][nt], aq[mt][0], bb[0], bb[1]);
-        mma16816(S[mt][nt], aq[mt][1], bb[2], bb[3]);
+        if (nt < ntm[mt]) {
+          S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.f;
+          mma16816(S[mt][nt], aq[mt][0], bb[0], bb[1]);
+          mma16816(S[mt][nt], aq[mt][1], bb[2], bb[3]);
+        }
       }
     }
   }
@@ -160,11 +163,11 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const bf16* __restric
   for (int mt = 0; mt < 2; mt++)
 #pragma unroll
     for (int hf = 0; hf < 2; hf++) {
-      const int il = 16 * mt + g + 8 * hf, i = r0 + il;
+      const int il = 16 * mt + g + 8 * hf, i = row0[mt] + g + 8 * hf;
       float m_ = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 16; nt++) {
-        if (nt < nt_max) {
+        if (nt < ntm[mt]) {
 #pragma unroll
           for (int q = 0; q < 2; q++) {
             const int c = 8 * nt + 2 * t + q;
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const bf16* __restric
       float sum = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 16; nt++) {
-        if (nt < nt_max) {
+        if (nt < ntm[mt]) {
 #pragma unroll
           for (int q = 0; q < 2; q++) {
             const float e = __expf(S[mt][nt][2 * hf + q] - m_);
@@ -200,11 +203,11 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const bf16* __restric
   for (int mt = 0; mt < 2; mt++)
 #pragma unroll
     for (int hf = 0; hf < 2; hf++) {
-      const int i = r0 + 16 * mt + g + 8 * hf;
+      const int i = row0[mt] + g + 8 * hf;
       const unsigned char* krow = (keep != nullptr && i < W) ? keep + (((size_t)b * nh + h) * W + i) * W : nullptr;
 #pragma unroll
       for (int nt = 0; nt < 16; nt++) {
-        if (nt < nt_max) {
+        if (nt < ntm[mt]) {
 #pragma unroll
           for (int q = 0; q < 2; q++) {
             const int c = 8 * nt + 2 * t + q;
@@ -224,12 +227,13 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const bf16* __restric
     for (int nd = 0; nd < 4; nd++) O[mt][nd][0] = O[mt][nd][1] = O[mt][nd][2] = O[mt][nd][3] = 0.f;
 #pragma unroll
   for (int kk = 0; kk < 8; kk++) {
-    if (2 * kk < nt_max) {
+    if (2 * kk < ntm[1]) {
       uint32_t bv[2][4];
       load_b_kn(bv[0], Vs, RS, 16 * kk, 0, lane);
       load_b_kn(bv[1], Vs, RS, 16 * kk, 16, lane);
 #pragma unroll
       for (int mt = 0; mt < 2; mt++) {
+        if (2 * kk >= ntm[mt]) continue;
         uint32_t a[4];
         a[0] = pack_bf16(S[mt][2 * kk][0], S[mt][2 * kk][1]);
         a[1] = pack_bf16(S[mt][2 * kk][2], S[mt][2 * kk][3]);
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const bf16* __restric
   for (int mt = 0; mt < 2; mt++)
 #pragma unroll
     for (int hf = 0; hf < 2; hf++) {
-      const int i = r0 + 16 * mt + g + 8 * hf;
+      const int i = row0[mt] + g + 8 * hf;
       if (i < W) {
         bf16* orow = att + ((size_t)b * W + i) * D + h * DKC;
 #pragma unroll
@@ -281,36 +285,39 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
   }
   for (int idx = tid; idx < 4 * 32 * QS / 4; idx += 128) reinterpret_cast<float4*>(QP)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  const int r0 = 32 * warp;
+  const int row0[2] = {16 * warp, 16 * (7 - warp)};          // this warp's two row tiles (and, below, key tiles)
+  const int ntm[2] = {2 * (warp + 1), 2 * (8 - warp)};       // 8-key tiles a row tile can see
+  const int kcm[2] = {warp >> 1, (7 - warp) >> 1};           // last 32-key chunk a row tile can see
   const float scale = rsqrtf((float)DKC);
   float* qp = QP + warp * 32 * QS;
   bf16* dbase = dqkv + (size_t)b * W * 3 * D + h * DKC;
-  if (r0 < W) {
+  {
     uint32_t aq[2][2][4], ag[2][2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; mt++)
 #pragma unroll
       for (int ks = 0; ks < 2; ks++) {
-        load_a(aq[mt][ks], Qs, RS, r0 + 16 * mt, 16 * ks, lane);
-        load_a(ag[mt][ks], Gs, RS, r0 + 16 * mt, 16 * ks, lane);
+        load_a(aq[mt][ks], Qs, RS, row0[mt], 16 * ks, lane);
+        load_a(ag[mt][ks], Gs, RS, row0[mt], 16 * ks, lane);
       }
-    qp_to_scratch(aq, Rs, qp, r0, W, lane);
+    qp_to_scratch(aq, Rs, qp, row0, W, lane);
     __syncwarp();
-    const int nt_max = 4 * (warp + 1);
     // ---- row statistics (max, 1 / sum) from a full pass over the keys; delta_i = dO_i . O_i ----
     float mx[2][2], inv[2][2], delta[2][2];
     {
       float S[2][16][4];
 #pragma unroll
       for (int nt = 0; nt < 16; nt++) {
-        if (nt < nt_max) {
+        if (nt < ntm[1]) {
           uint32_t bb[4];
           load_b_nk(bb, Ks, 8 * nt, lane);
 #pragma unroll
           for (int mt = 0; mt < 2; mt++) {
-            S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.f;
-            mma16816(S[mt][nt], aq[mt][0], bb[0], bb[1]);
-            mma16816(S[mt][nt], aq[mt][1], bb[2], bb[3]);
+            if (nt < ntm[mt]) {
+              S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.f;
+              mma16816(S[mt][nt], aq[mt][0], bb[0], bb[1]);
+              mma16816(S[mt][nt], aq[mt][1], bb[2], bb[3]);
+            }
           }
         }
       }
@@ -318,11 +325,11 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
         for (int hf = 0; hf < 2; hf++) {
-          const int il = 16 * mt + g + 8 * hf, i = r0 + il;
+          const int il = 16 * mt + g + 8 * hf, i = row0[mt] + g + 8 * hf;
           float m_ = -INFINITY;
 #pragma unroll
           for (int nt = 0; nt < 16; nt++) {
-            if (nt < nt_max) {
+            if (nt < ntm[mt]) {
 #pragma unroll
               for (int q = 0; q < 2; q++) {
                 const int c = 8 * nt + 2 * t + q;
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
           float sum = 0.f;
 #pragma unroll
           for (int nt = 0; nt < 16; nt++) {
-            if (nt < nt_max) {
+            if (nt < ntm[mt]) {
 #pragma unroll
               for (int q = 0; q < 2; q++) sum += __expf(S[mt][nt][2 * hf + q] - m_);
             }
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
 #pragma unroll
       for (int nd = 0; nd < 4; nd++) dQ[mt][nd][0] = dQ[mt][nd][1] = dQ[mt][nd][2] = dQ[mt][nd][3] = 0.f;
 #pragma unroll 1
-    for (int kc = 0; kc <= warp; kc++) {
+    for (int kc = 0; kc <= kcm[1]; kc++) {
       float S[2][4][4], dP[2][4][4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -383,6 +390,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
         load_b_nk(bv, Vs, 8 * nt, lane);
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
+          if (kc > kcm[mt]) continue;  // (warp-uniform: the low row tile sees fewer chunks)
           S[mt][j][0] = S[mt][j][1] = S[mt][j][2] = S[mt][j][3] = 0.f;
           dP[mt][j][0] = dP[mt][j][1] = dP[mt][j][2] = dP[mt][j][3] = 0.f;
           mma16816(S[mt][j], aq[mt][0], bk[0], bk[1]);
@@ -395,7 +403,8 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
         for (int hf = 0; hf < 2; hf++) {
-          const int il = 16 * mt + g + 8 * hf, i = r0 + il;
+          if (kc > kcm[mt]) continue;  // (its dS / P~ cells keep the zeros of the initial fill)
+          const int il = 16 * mt + g + 8 * hf, i = row0[mt] + g + 8 * hf;
           const unsigned char* krow = (keep != nullptr && i < W) ? keep + (((size_t)b * nh + h) * W + i) * W : nullptr;
 #pragma unroll
           for (int j = 0; j < 4; j++) {
@@ -433,6 +442,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
         load_b_kn(bk2[1], Ks, RS, 32 * kc + 16 * kk, 16, lane);
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
+          if (kc > kcm[mt]) continue;
           uint32_t a[4];
           a[0] = pack_bf16(S[mt][2 * kk][0], S[mt][2 * kk][1]);
           a[1] = pack_bf16(S[mt][2 * kk][2], S[mt][2 * kk][3]);
@@ -471,7 +481,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
     for (int mt = 0; mt < 2; mt++)
 #pragma unroll
       for (int hf = 0; hf < 2; hf++) {
-        const int i = r0 + 16 * mt + g + 8 * hf;
+        const int i = row0[mt] + g + 8 * hf;
         if (i < W) {
 #pragma unroll
           for (int nd = 0; nd < 4; nd++)
@@ -480,9 +490,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
       }
   }
   __syncthreads();
-  // ---- key side: warp w owns keys / columns 32w .. 32w+31 ----
-  const int c0 = 32 * warp;
-  if (c0 >= W) return;
+  // ---- key side: warp w owns the key / column tiles w and 7-w (16 each): key tile j meets the row tiles ki >= j ----
   float dK[2][4][4], dV[2][4][4], dR[2][4][4];
 #pragma unroll
   for (int mt = 0; mt < 2; mt++)
@@ -496,14 +504,15 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
     uint32_t bq[2][4], bg[2][4];
     load_b_kn(bq[0], Qs, RS, 16 * ki, 0, lane);
     load_b_kn(bq[1], Qs, RS, 16 * ki, 16, lane);
-    if (16 * ki + 15 >= c0) {  // rows i >= c only: tiles entirely above the diagonal hold zeros
+    if (16 * ki >= row0[0]) {  // rows i >= c only: tiles entirely above the diagonal hold zeros
       load_b_kn(bg[0], Gs, RS, 16 * ki, 0, lane);
       load_b_kn(bg[1], Gs, RS, 16 * ki, 16, lane);
 #pragma unroll
       for (int mt = 0; mt < 2; mt++) {
+        if (16 * ki < row0[mt]) continue;
         uint32_t a[4], ap[4];
-        load_a_t(a, dSs, SS, c0 + 16 * mt, 16 * ki, lane);
-        load_a_t(ap, Pds, SS, c0 + 16 * mt, 16 * ki, lane);
+        load_a_t(a, dSs, SS, row0[mt], 16 * ki, lane);
+        load_a_t(ap, Pds, SS, row0[mt], 16 * ki, lane);
         mma16816(dK[mt][0], a, bq[0][0], bq[0][1]);
         mma16816(dK[mt][1], a, bq[0][2], bq[0][3]);
         mma16816(dK[mt][2], a, bq[1][0], bq[1][1]);
@@ -514,11 +523,12 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
         mma16816(dV[mt][3], ap, bg[1][2], bg[1][3]);
       }
     }
-    // dKrelpos^T[m][d] += sum_i dS~[i][m] q_i[d] : A[m][k = i] from the fp32 scratch of the warp that owns rows 16ki..16ki+15
-    const float* sc = QP + (16 * ki / 32) * 32 * QS + ((16 * ki) % 32) * QS;
+    // dKrelpos^T[m][d] += sum_i dS~[i][m] q_i[d] : A[m][k = i] from the fp32 scratch of the warp that owns row tile ki
+    // (warp ki holds it as its first tile when ki < 4, warp 7-ki as its second otherwise)
+    const float* sc = QP + (ki < 4 ? ki * 32 : (7 - ki) * 32 + 16) * QS;
 #pragma unroll
     for (int mt = 0; mt < 2; mt++) {
-      const int m = c0 + 16 * mt + g;
+      const int m = row0[mt] + g;
       uint32_t a[4];
       a[0] = pack_bf16(sc[(2 * t) * QS + m], sc[(2 * t + 1) * QS + m]);
       a[1] = pack_bf16(sc[(2 * t) * QS + m + 8], sc[(2 * t + 1) * QS + m + 8]);
@@ -534,7 +544,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const bf16* __restric
   for (int mt = 0; mt < 2; mt++)
 #pragma unroll
     for (int hf = 0; hf < 2; hf++) {
-      const int c = c0 + 16 * mt + g + 8 * hf;
+      const int c = row0[mt] + g + 8 * hf;
       if (c < W) {
 #pragma unroll
         for (int nd = 0; nd < 4; nd++) {
