@@ -353,8 +353,8 @@ def test_ragged_shapes_against_oracle(B, L, dtype, built_lib):
 
 def test_config5_dims_bf16(built_lib):
     """BASELINE config 5 widths (hiddenEncoder=512, hiddenGar=512, 2-level GRU, K=16, 256 negatives) on a half-length
-    window (S=256): exercises H=512 tiles, the 8-CTA GRU clusters of the CUDA-core recurrence and the CUDA-core
-    scoring kernels (the tensor-core scoring / GRU specialisations cover N=128 / Har<=256 only)."""
+    window (S=256): exercises H=512 tiles, the 16-CTA clusters of the wide tensor-core GRU recurrence (gru_mma_wide.cu) and
+    the warp-pair scoring kernels (H = 512, 16 chunks of negatives)."""
     d = O.Dims(B=2, L=40960, H=512, Har=512, K=16, N=256, nLayers=2)
     mp, cp = O.make_params(d, seed=70, pred_scale=30.0)
     x, label = O.make_batch(d, seed=71)
@@ -574,6 +574,25 @@ def test_config5_full_length_bf16(built_lib):
     assert Hh.rel_err(out["z"], ref["z"]) <= 1.5e-2 and Hh.rel_err(out["c"], ref["c"]) <= 1.5e-2
     assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.01 * ref["losses"].abs() + 1e-2).all()
     assert wc[1][0] >= 0.985, wc          # measured 0.9947 (gEncoder.conv0.weight, B = 2)
+
+
+def test_wide_lstm_hidden512_bf16(built_lib):
+    """--arMode LSTM at hiddenGar = 512, 2 levels, B = 3 (a partly filled batch tile): the 16-CTA-cluster wide LSTM recurrence
+    (lstm_mma.cu) forward and every gradient against the oracle."""
+    d = O.Dims(B=3, L=20480, H=512, Har=512, K=12, N=128, nLayers=2)
+    mp, cp = O.make_params(d, seed=93, pred_scale=30.0, ar="LSTM")
+    x, label = O.make_batch(d, seed=94)
+    bi, si = O.make_raw_indices(d, seed=95)
+    ref = Hh.oracle_run(d, mp, cp, x, bi, si, materialize=False)
+    model, crit = Hh.build_modules(d, mp, cp, "bf16", ar="LSTM")
+    out = Hh.run_modules(model, crit, x, label, bi, si)
+    rep, wc, wr = Hh.grad_report(out["grads"], ref["grads"])
+    Hh.record("lstm512:bf16", z_rel=Hh.rel_err(out["z"], ref["z"]), c_rel=Hh.rel_err(out["c"], ref["c"]),
+              dloss=(out["losses"].cpu() - ref["losses"]).abs().max().item(), worst_cos=[wc[0], wc[1][0]], worst_rel=[wr[0], wr[1][1]])
+    assert Hh.rel_err(out["z"], ref["z"]) <= 1.5e-2 and Hh.rel_err(out["c"], ref["c"]) <= 1.5e-2
+    assert ((out["losses"].cpu() - ref["losses"]).abs() <= 0.01 * ref["losses"].abs() + 1e-2).all()
+    for k, gr in ref["grads"].items():
+        assert _cos(out["grads"][k], gr) >= Hh.bf16_cos_floor(k, d), (k, _cos(out["grads"][k], gr))
 
 
 def test_optimizer_state_dict_interchanges_with_torch_adam(built_lib):
