@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) score_fwd_mma_kernel(const bf16* __restri
 // Both reach the same L2 reduction ceiling (tools/redbench: 5.4 TB/s); without the 16 KB staging tile a warp needs
 // 26 KB of shared memory instead of 42 KB, so 8 warps fit on an SM instead of 5.
 template <int H, int RED, int SPLIT, int NNEG>
-__global__ void __launch_bounds__(RED == 0 ? 160 : 256) score_bwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
+__global__ void __launch_bounds__((RED == 0 && SPLIT == 1) ? 160 : 256) score_bwd_mma_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ z,
                                                             const int* __restrict__ ext_t, const float* __restrict__ lsebuf,
                                                             const float* __restrict__ dloss, bf16* __restrict__ dpred,
                                                             float* __restrict__ dz, int B, int S, int W, int K, int N,
@@ -560,7 +560,7 @@ template <int H, int RED, int SPLIT, int NNEG>
 int launch_bwd_red(const bf16* pred, const bf16* z, const int* ext_t, const float* lsebuf, const float* dloss, bf16* dpred, float* dz,
                    int B, int S, int W, int K, int N, cudaStream_t st) {
   int wpc = (int)((216 * 1024) / bwd_warp_smem<H, RED, SPLIT>());
-  const int cap = RED == 0 ? 5 : 8;
+  const int cap = (RED == 0 && SPLIT == 1) ? 5 : 8;
   if (wpc > cap) wpc = cap;
   wpc -= wpc % SPLIT;
   const size_t smem = wpc * bwd_warp_smem<H, RED, SPLIT>();
@@ -581,11 +581,18 @@ int launch_bwd(const bf16* pred, const bf16* z, const int* ext_t, const float* l
   return launch_bwd_red<H, 0, SPLIT, NNEG>(pred, z, ext_t, lsebuf, dloss, dpred, dz, B, S, W, K, N, st);
 }
 
+// experiment: H = 256 as a warp pair of 128 columns each (half the shared memory per warp -> 8 warps per SM, half the dz / dpred
+// products per warp).  CPC_B200_SCORE_SPLIT=1
+bool split256() {
+  static const bool on = []() { const char* e = getenv("CPC_B200_SCORE_SPLIT"); return e && atoi(e) == 1; }();
+  return on;
+}
 // (feature dim, negatives) -> instantiation
 #define CPC_SCORE_DISPATCH(FN, ...)                                            \
   do {                                                                         \
     if (N == 8 * CH) {                                                         \
       if (H == 512) return FN<256, 2, 8>(__VA_ARGS__);                         \
+      if (H == 256 && split256()) return FN<128, 2, 8>(__VA_ARGS__);           \
       if (H == 256) return FN<256, 1, 8>(__VA_ARGS__);                         \
       if (H == 128) return FN<128, 1, 8>(__VA_ARGS__);                         \
       return FN<64, 1, 8>(__VA_ARGS__);                                        \
