@@ -212,6 +212,92 @@ __global__ void __launch_bounds__(128, 3) conv0_fwd_mma_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// forward, H = 512 (BASELINE config 5): one warp still owns a 16-frame tile and all channels, but 512 channels of fp32
+// accumulators do not fit the register file, so the product is formed twice, 256 channels at a time: pass A only accumulates
+// the row sums (sum u, sum u^2), pass B recomputes, normalises and stages.  conv0 is HBM-bound (the MMAs are ~17 % of the
+// tensor pipe at H = 256), the second product is cheaper than a round trip through shared memory.
+// ---------------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(128, 2) conv0_fwd_mma_wide_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                  const float* __restrict__ bias, const float* __restrict__ gam,
+                                                                  const float* __restrict__ bet, bf16* __restrict__ y, int B, int L,
+                                                                  int L0) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int NT = H / 8, NTH = NT / 2, RS = 2 * H + 16;
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* gb = reinterpret_cast<float*>(sm);
+  uint2* wsm = reinterpret_cast<uint2*>(sm + 2 * H * 4);
+  unsigned char* stage = sm + 2 * H * 4 + NT * 32 * 8 + (threadIdx.x >> 5) * (16 * RS);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { gb[i] = gam[i]; gb[H + i] = bet[i]; }
+  stage_wfrags<H>(w, bias, wsm);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int tpw = (L0 + 15) / 16;
+  const long long Lp0 = L0 + 2 * kPad;
+  for (int tile = warp; tile < B * tpw; tile += nwarps) {
+    const int b = tile / tpw, f0 = (tile - b * tpw) * 16;
+    uint32_t ah[4], al[4];
+    load_xfrags(x + (long long)b * L, L, f0, g, t, ah, al);
+    float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+      for (int j = 0; j < NTH; j++) {
+        const uint2 wv = wsm[(hh * NTH + j) * 32 + lane];
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(a, ah, wv.x, wv.y);
+        mma16816(a, al, wv.x, wv.y);
+        s[0] += a[0] + a[1]; s[1] += a[2] + a[3];
+        q[0] = fmaf(a[0], a[0], q[0]); q[0] = fmaf(a[1], a[1], q[0]);
+        q[1] = fmaf(a[2], a[2], q[1]); q[1] = fmaf(a[3], a[3], q[1]);
+      }
+    }
+    float mean[2], rstd[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {
+      s[hf] += __shfl_xor_sync(0xffffffffu, s[hf], 1); s[hf] += __shfl_xor_sync(0xffffffffu, s[hf], 2);
+      q[hf] += __shfl_xor_sync(0xffffffffu, q[hf], 1); q[hf] += __shfl_xor_sync(0xffffffffu, q[hf], 2);
+      mean[hf] = s[hf] / (float)H;
+      rstd[hf] = rsqrtf(fmaxf((q[hf] - s[hf] * mean[hf]) / (float)(H - 1), 0.f) + kEps);  // unbiased variance, model.py:52-54
+    }
+    __syncwarp();
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+      for (int j = 0; j < NTH; j++) {
+        const uint2 wv = wsm[(hh * NTH + j) * 32 + lane];
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(a, ah, wv.x, wv.y);
+        mma16816(a, al, wv.x, wv.y);
+        const int c = 8 * (hh * NTH + j) + 2 * t;
+        const float2 g2 = *reinterpret_cast<const float2*>(gb + c), b2 = *reinterpret_cast<const float2*>(gb + H + c);
+        const float y0 = fmaxf(fmaf((a[0] - mean[0]) * rstd[0], g2.x, b2.x), 0.f);
+        const float y1 = fmaxf(fmaf((a[1] - mean[0]) * rstd[0], g2.y, b2.y), 0.f);
+        const float y2 = fmaxf(fmaf((a[2] - mean[1]) * rstd[1], g2.x, b2.x), 0.f);
+        const float y3 = fmaxf(fmaf((a[3] - mean[1]) * rstd[1], g2.y, b2.y), 0.f);
+        *reinterpret_cast<uint32_t*>(stage + g * RS + c * 2) = pack_bf16(y0, y1);
+        *reinterpret_cast<uint32_t*>(stage + (g + 8) * RS + c * 2) = pack_bf16(y2, y3);
+      }
+    }
+    __syncwarp();
+    bf16* dst = y + ((long long)b * Lp0 + kPad + f0) * H;
+    tile_to_global<H>(stage, dst, lane, L0 - f0);
+    if (f0 == 0 || f0 + 16 >= L0) {  // zero rows around the window
+      bf16* pad = y + ((long long)b * Lp0 + (f0 == 0 ? 0 : kPad + L0)) * H;
+      for (int i = lane; i < kPad * H / 8; i += 32) reinterpret_cast<uint4*>(pad)[i] = make_uint4(0, 0, 0, 0);
+      if (f0 == 0 && f0 + 16 >= L0) {
+        bf16* pad2 = y + ((long long)b * Lp0 + kPad + L0) * H;
+        for (int i = lane; i < kPad * H / 8; i += 32) reinterpret_cast<uint4*>(pad2)[i] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    __syncwarp();  // the staging tile is rewritten by the next tile's pass B
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // backward part 1: recompute u, ChannelNorm+ReLU backward in place (dy0 -> du0), dbias0/dgamma0/dbeta0.
 // The three per-channel sums over frames are column sums of bf16 tiles: computed with MMAs against a ones
 // matrix (A = tile^T via ldmatrix.trans) and accumulated in shared memory.
@@ -730,15 +816,39 @@ int launch_all_bwd(const float* x, const float* w, const float* bias, const floa
 }  // namespace
 
 bool conv0_mma_supported(int H) { return H == 64 || H == 128 || H == 256; }
+// H = 512: forward with the two-pass kernel; backward with conv0_bwd2_mma (8 warps x 64 channels) when the frame count is a
+// multiple of its 64-frame tiles, else the CUDA-core kernels of encoder.cu
+bool conv0_mma_wide_fwd_supported(int H) { return H == 512; }
+bool conv0_mma_wide_bwd_supported(int H, int L0) { return H == 512 && L0 % kFT == 0; }
 
 int conv0_fwd_mma(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* y, int B, int L, int L0,
                   int H, cudaStream_t st) {
+  if (H == 512) {
+    constexpr int HW = 512;
+    const size_t smem = 2 * HW * 4 + (HW / 8) * 32 * 8 + 4 * 16 * (2 * HW + 16);
+    int blocks = (B * ((L0 + 15) / 16) + 3) / 4;
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_fwd_mma_wide_kernel<HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPC_CHECK_CUDA(launch_k(conv0_fwd_mma_wide_kernel<HW>, dim3(blocks), dim3(128), smem, st, 1, x, w, bias, gam, bet, y, B, L, L0));
+    CPC_LAUNCHED_N("conv0_fwd_mma", st);
+    return 0;
+  }
   if (H == 256) return launch_all_fwd<256>(x, w, bias, gam, bet, y, B, L, L0, st);
   if (H == 128) return launch_all_fwd<128>(x, w, bias, gam, bet, y, B, L, L0, st);
   return launch_all_fwd<64>(x, w, bias, gam, bet, y, B, L, L0, st);
 }
 int conv0_bwd_mma(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* dy, float* dw,
                   float* dbias, float* dgam, float* dbet, int B, int L, int L0, int H, cudaStream_t st) {
+  if (H == 512) {  // (conv0_mma_wide_bwd_supported: L0 % 64 == 0)
+    constexpr int HW = 512;
+    const size_t smem = bwd2_smem<HW>();
+    int blocks2 = B * (L0 / kFT);
+    if (blocks2 > 148) blocks2 = 148;
+    CPC_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd2_mma_kernel<HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPC_CHECK_CUDA(launch_k(conv0_bwd2_mma_kernel<HW>, dim3(blocks2), dim3((HW / kCW) * 32), smem, st, 1, x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0));
+    CPC_LAUNCHED_N("conv0_bwd2_mma", st);
+    return 0;
+  }
   if (H == 256) return launch_all_bwd<256>(x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0, st);
   if (H == 128) return launch_all_bwd<128>(x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0, st);
   return launch_all_bwd<64>(x, w, bias, gam, bet, dy, dw, dbias, dgam, dbet, B, L, L0, st);

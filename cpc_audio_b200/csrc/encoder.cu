@@ -17,6 +17,8 @@ int gemm_nt(bool bf16_in, bool out_f32, int nb, int N, int Kd, const RowView& A,
             const OutView& C, cudaStream_t st);
 
 bool conv0_mma_supported(int H);
+bool conv0_mma_wide_fwd_supported(int H);
+bool conv0_mma_wide_bwd_supported(int H, int L0);
 int conv0_fwd_mma(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* y, int B, int L, int L0,
                   int H, cudaStream_t st);
 int conv0_bwd_mma(const float* x, const float* w, const float* bias, const float* gam, const float* bet, bf16* dy, float* dw,
@@ -599,7 +601,7 @@ int encoder_fwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   const int I = ilog_I(H);
   bool c0_done = false;
   if constexpr (sizeof(T) == 2) {
-    if (conv0_mma_supported(H)) {
+    if (conv0_mma_supported(H) || conv0_mma_wide_fwd_supported(H)) {
       CPC_TRY(conv0_fwd_mma(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0], yb[0], B, g.L, g.Lout[0], H, st));
       c0_done = true;
     }
@@ -725,7 +727,7 @@ int encoder_bwd_t(const Geo& g, const float* x, const cpcb200_encoder_params* p,
   }
   bool c0_done = false;
   if constexpr (sizeof(T) == 2) {
-    if (conv0_mma_supported(H)) {
+    if (conv0_mma_supported(H) || conv0_mma_wide_bwd_supported(H, g.Lout[0])) {
       CPC_TRY(conv0_bwd_mma(x, p->conv_w[0], p->conv_b[0], p->norm_w[0], p->norm_b[0], dy[0], gr->conv_w[0], gr->conv_b[0],
                             gr->norm_w[0], gr->norm_b[0], B, g.L, g.Lout[0], H, st));
       c0_done = true;
