@@ -120,6 +120,22 @@ def test_on_device_randint_stream_equals_reference_sampleClean(built_lib):
     assert np.array_equal(ext, O.ext_indices_np(bi.cpu().numpy(), si.cpu().numpy(), B, 128, S - 12, S))
 
 
+def test_dropout_masks_follow_the_reference_call_order_cpu():
+    """Host logic of row T in train(): ``draw_dropout_masks`` makes, per layer, one nn.Dropout-style draw for the attention
+    probabilities (B*heads, W, W) and then one for the FFN hidden (B, W, dff) - the order of transformers.py:49 then :92 -
+    and the stacked uint8 buffers hold exactly those draws (checked on the CPU generator)."""
+    from cpc_audio_b200.criterion import draw_dropout_masks
+    K, B, W, nh, dff, p = 3, 2, 7, 4, 16, 0.25
+    torch.manual_seed(1234)
+    att, ffn = draw_dropout_masks(K, B, W, nh, dff, p, torch.device("cpu"))
+    assert att.shape == (K, B * nh, W, W) and ffn.shape == (K, B * W, dff) and att.dtype == torch.uint8 and ffn.dtype == torch.uint8
+    torch.manual_seed(1234)
+    for k in range(K):
+        a = torch.nn.functional.dropout(torch.ones(B * nh, W, W), p, True) != 0
+        f = torch.nn.functional.dropout(torch.ones(B, W, dff), p, True) != 0
+        assert torch.equal(att[k].bool(), a) and torch.equal(ffn[k].bool(), f.view(B * W, dff)), k
+
+
 @needs_ref
 @pytest.mark.gpu
 def test_train_mode_dropout_masks_equal_the_reference_draws(built_lib):
