@@ -5,6 +5,8 @@
 // CTAs owns a tile of BT sequences, each CTA keeps its 192 x Har slice of W_hh resident in shared memory for
 // the whole sequence, and the CTAs exchange the 64 hidden units they produce through distributed shared
 // memory (one cluster barrier per time step).  BPTT mirrors it with the transposed slice (64 x 3Har).
+// That is the fp32 / CUDA-core form kept in this file (and the LSTM twin further down); on the bf16 path the recurrences run on
+// tensor cores with the W_hh slice in registers: gru_mma.cu, gru_mma_wide.cu, lstm_mma.cu (dispatched from here).
 #include <cooperative_groups.h>
 
 #include "common.cuh"

@@ -2,7 +2,7 @@
 //
 // One WARP per anchor position p = (b, w), persistent over positions.  Per position the candidates are the N
 // negatives z[ext[b, :, w]] (gathered row by row with cp.async, 512 B per instruction, double-buffered in chunks
-// of 32 rows) followed by the K positives z[b, w+1 .. w+K] (contiguous rows).  All contractions run on
+// of 16 rows) followed by the K positives z[b, w+1 .. w+K] (contiguous rows).  All contractions run on
 // mma.sync.m16n8k16 (bf16 x bf16 -> fp32):
 //   forward : logits[j][k] = cand_j . pred_k / H        M = candidates, N = heads (padded to 16), K = H
 //             softmax / cross-entropy / argmax in the accumulator registers (reduction over candidates =
@@ -13,6 +13,8 @@
 //                           one 1 KB row per instruction) instead of per-lane atomics;
 //             dpred      += G . cand     accumulated over chunks in registers.
 // The kernel is bound by the L2 gather (N x 512 B per position) and the scatter-add, not by the tensor pipe.
+// Templates cover H = 64 / 128 / 256 columns per warp, N = 128 / 256 negatives, and a warp PAIR per position for a feature
+// dim of 512 (each warp one half of every row; partial logits swapped per chunk).
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -4,11 +4,14 @@
 // Per head k (input x = c[:, :W], D = dmodel = H = Har, nh heads of dk = D/nh, F = dff):
 //   q,k,v = x Wq^T, x Wk^T, x Wv^T                                   transformers.py:60-65,76-80   (GEMMs)
 //   scores[i][c] = (q_i.k_c + q_i.Krelpos[:, W-1-(i-c)]) / sqrt(dk), c <= i   38-48 (relative-position "skew")
-//   a = softmax(scores) ; att = a v                                  48-49 (dropout: eval mode only)   attn kernels
+//   a = softmax(scores) ; att = dropout(a) v                         48-49 (train mode: caller-supplied keep masks)   attn kernels
 //   y1 = LN(x + att Wo^T)                                            81-83, 109                       GEMM + add_ln
 //   out = LN(y1 + relu(y1 W1^T + b1) W2^T + b2)                      86-95, 110-111                   GEMMs + add_ln
-// Everything dense goes through gemm_nt / gemm_tn (tcgen05 on the bf16 path); attention, LayerNorm and the ReLU
-// mask are CUDA-core kernels (fp32 math, T storage).  Backward recomputes the attention probabilities.
+// Everything dense goes through gemm_nt / gemm_tn (tcgen05 on the bf16 path); attention runs on mma.sync (attn_mma.cu) on the
+// bf16 path and on the CUDA-core kernels below otherwise; LayerNorm, the ReLU mask and dropout are row / element kernels (fp32
+// math, T storage).  Backward recomputes the attention probabilities.  On the bf16 path the K heads run STACKED - batched
+// GEMMs over stacked per-head weights, one launch per stage for all heads (thead_fwd_stacked / thead_bwd_stacked below); the
+// per-head form on stream lanes remains for fp32.
 #include "common.cuh"
 
 namespace cpcb200 {
