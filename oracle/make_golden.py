@@ -171,6 +171,10 @@ CASES2 = {
     "cfg4_small_train": (O.Dims(B=3, L=3200, H=64, Har=64, K=3, N=8, nLayers=1), 30.0, 11, "transformer", "GRU", True),
     "cfg4_train": (O.Dims(B=2, L=20480, H=256, Har=256, K=12, N=128, nLayers=1), 30.0, 12, "transformer", "GRU", True),
     "tar_small_train": (O.Dims(B=2, L=3200, H=64, Har=64, K=3, N=8, nLayers=1), 30.0, 13, "transformer", "transformer", True),
+    # BASELINE config 5 widths (hidden 512, 2 levels, K = 16, 256 negatives) on a 20480-sample window, and a 2-level LSTM at 512:
+    # they pin the ORACLE at the wide dims (tests/test_oracle_golden.py); the CUDA path is compared with the oracle at these dims
+    "cfg5_s128": (O.Dims(B=2, L=20480, H=512, Har=512, K=16, N=256, nLayers=2), 30.0, 14, "linear", "GRU", False),
+    "lstm512": (O.Dims(B=2, L=10240, H=512, Har=512, K=8, N=32, nLayers=2), 30.0, 15, "linear", "LSTM", False),
 }
 
 

@@ -11,6 +11,7 @@ CASES = ["small", "small2l", "cfg1", "cfg1_scaled"]
 T_CASES = ["cfg4_small", "cfg4"]  # rnnMode='transformer' prediction heads
 AR_CASES = ["lstm_small", "cfg1_lstm", "tar_small", "cfg1_tar"]  # --arMode LSTM / transformer context networks
 TRAIN_CASES = ["cfg4_small_train", "cfg4_train", "tar_small_train"]  # train() mode: dropout of the transformer layers (row T)
+WIDE_CASES = ["cfg5_s128", "lstm512"]  # BASELINE config 5 widths / LSTM at 512: pin the oracle there (CPU test only)
 FEATURE_CASES = ["feat_gru", "feat_lstm"]  # feature_loader.buildFeature over chunks of arbitrary length
 
 

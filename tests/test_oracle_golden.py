@@ -11,7 +11,7 @@ from oracle import cpc_oracle as O
 from tests import helpers as Hh
 
 
-@pytest.mark.parametrize("name", Hh.CASES + Hh.T_CASES + Hh.AR_CASES + Hh.TRAIN_CASES)
+@pytest.mark.parametrize("name", Hh.CASES + Hh.T_CASES + Hh.AR_CASES + Hh.TRAIN_CASES + Hh.WIDE_CASES)
 def test_oracle_matches_reference_fixture(name):
     g, d, mp, cp, x, label, bi, si = Hh.load_case(name)
     ar_masks, head_masks = Hh.case_masks(g, d)
